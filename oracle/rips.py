@@ -1,0 +1,132 @@
+"""oracle/rips.py -- TEST INFRASTRUCTURE ONLY (checker + CPU baseline); the product never imports it.
+
+Python front end of the CPU Rips oracle.  Restates what ``ripser.ripser`` (ripser.py, unpinned third
+party dependency of the reference, README.md:28) does around its C++ core for the arguments the
+reference uses (debug_tda_pipeline.py:109-110, analyze_tda_over_layers.py:76,
+analyze_adversarial_tda.py:100-101): euclidean ``pairwise_distances`` on the point cloud, cast to
+float32, dense Rips persistence over Z/2 up to ``maxdim`` with the enclosing-radius threshold, and a
+result dict whose ``dgms`` are float64 ``(n_k, 2)`` arrays.  SURVEY.md Appendix B is the spec.
+
+Parity: PINNED by tests/test_oracle_golden.py (32 shipped clouds -> summary_stats.json).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "librips_oracle.so")
+    src = os.path.join(_HERE, "rips_oracle.cpp")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "librips_oracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        lib = ctypes.CDLL(build())
+        lib.rips_oracle_run.restype = ctypes.c_void_p
+        lib.rips_oracle_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float]
+        lib.rips_oracle_count.restype = ctypes.c_int64
+        lib.rips_oracle_count.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        lib.rips_oracle_get.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        lib.rips_oracle_num_edges.restype = ctypes.c_int64
+        lib.rips_oracle_num_edges.argtypes = [ctypes.c_void_p]
+        lib.rips_oracle_thresh.restype = ctypes.c_float
+        lib.rips_oracle_thresh.argtypes = [ctypes.c_void_p]
+        lib.rips_oracle_stats.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        lib.rips_oracle_free.argtypes = [ctypes.c_void_p]
+        _LIB = lib
+    return _LIB
+
+
+def euclidean_dm_f32(X):
+    """Distance matrix exactly as the GPU path defines it: squared distance by exact differences in
+    float64, rounded to float32, then a correctly rounded float32 sqrt.  ripser.py gets its matrix from
+    sklearn ``pairwise_distances`` (float32 input -> float64 ||x||^2+||y||^2-2xy -> float32 -> float32
+    sqrt); on the reference's 32 shipped clouds both definitions reproduce summary_stats.json bit for
+    bit (tests/test_oracle_golden.py)."""
+    X = np.asarray(X, dtype=np.float64)
+    diff = X[:, None, :] - X[None, :, :]
+    d2 = np.einsum("ijk,ijk->ij", diff, diff).astype(np.float32)
+    return np.sqrt(d2)
+
+
+def greedy_permutation(dm, n_perm):
+    """Furthest-point sampling as ripser.py's ``n_perm`` does it: start at index 0."""
+    n = dm.shape[0]
+    idx = np.zeros(n_perm, dtype=np.int64)
+    lambdas = np.zeros(n_perm)
+    ds = dm[0].astype(np.float64).copy()
+    for i in range(1, n_perm):
+        j = int(np.argmax(ds))
+        idx[i] = j
+        lambdas[i - 1] = ds[j]
+        ds = np.minimum(ds, dm[j])
+    lambdas[-1] = ds.max()
+    return idx, lambdas
+
+
+def rips_dm(dm, maxdim=1, thresh=np.inf, with_simplices=False, with_stats=False):
+    """Persistence of the Rips filtration of a full float32 distance matrix."""
+    dm = np.ascontiguousarray(dm, dtype=np.float32)
+    n = dm.shape[0]
+    lib = _lib()
+    h = lib.rips_oracle_run(dm.ctypes.data, n, int(maxdim), float(thresh))
+    try:
+        dgms, simp, stats = [], [], []
+        for q in range(maxdim + 1):
+            c = lib.rips_oracle_count(h, q)
+            p = np.zeros((c, 2), dtype=np.float64)
+            s = np.zeros((c, 2), dtype=np.int64)
+            if c:
+                lib.rips_oracle_get(h, q, p.ctypes.data, s.ctypes.data)
+            dgms.append(p)
+            simp.append(s)
+            st = np.zeros(7, dtype=np.int64)
+            lib.rips_oracle_stats(h, q, st.ctypes.data)
+            stats.append(dict(zip(["columns", "emergent", "reduced", "additions", "pops", "max_v", "cofacets"], st.tolist())))
+        out = {"dgms": dgms, "num_edges": int(lib.rips_oracle_num_edges(h)), "thresh": float(lib.rips_oracle_thresh(h))}
+        if with_simplices:
+            out["simplices"] = simp
+        if with_stats:
+            out["stats"] = stats
+        return out
+    finally:
+        lib.rips_oracle_free(h)
+
+
+def ripser(X, maxdim=1, thresh=np.inf, coeff=2, distance_matrix=False, do_cocycles=False,
+           metric="euclidean", n_perm=None, _sklearn_dm=False, **extra):
+    """Oracle twin of ``ripser.ripser`` (same keyword surface, same result keys)."""
+    if coeff != 2:
+        raise NotImplementedError("oracle supports coeff=2 only")
+    X = np.asarray(X)
+    if distance_matrix:
+        if X.shape[0] != X.shape[1]:
+            raise ValueError("Distance matrix is not square")
+        dm = X.astype(np.float32)
+    elif metric == "euclidean" and not _sklearn_dm:
+        dm = euclidean_dm_f32(X)
+    else:
+        from sklearn.metrics import pairwise_distances
+        dm = pairwise_distances(X, metric=metric).astype(np.float32)
+    n = dm.shape[0]
+    idx_perm = np.arange(n)
+    r_cover = 0.0
+    dperm2all = dm
+    if n_perm is not None and n_perm < n:
+        idx_perm, lambdas = greedy_permutation(dm, n_perm)
+        r_cover = float(lambdas[-1])
+        dperm2all = dm[idx_perm, :]
+        dm = dperm2all[:, idx_perm]
+    res = rips_dm(dm, maxdim=maxdim, thresh=thresh, **extra)
+    res.update({"cocycles": [[] for _ in range(maxdim + 1)], "dperm2all": dperm2all,
+                "idx_perm": idx_perm, "r_cover": r_cover})
+    return res

@@ -1,0 +1,338 @@
+// oracle/rips_oracle.cpp -- TEST INFRASTRUCTURE ONLY (checker + CPU baseline), never the product path.
+//
+// CPU restatement of the Vietoris-Rips persistent cohomology algorithm that the reference
+// reaches through `from ripser import ripser` (debug_tda_pipeline.py:10,109-110;
+// analyze_tda_over_layers.py:5,76; analyze_adversarial_tda.py:12,100-101).  The algorithm
+// itself lives in the third-party package `ripser` (ripser.py, UNPINNED in README.md:28; C++
+// core = Bauer's Ripser), which is not vendored under /root/reference and not installed in
+// this image, so this file restates the published algorithm (U. Bauer, "Ripser: efficient
+// computation of Vietoris-Rips persistence barcodes", JACT 2021):
+//   * dense float32 distances, Z/2 coefficients, enclosing-radius threshold,
+//   * simplices indexed by the combinatorial number system (64-bit),
+//   * filtration order = (diameter asc, index desc); columns processed in reverse order,
+//   * H0 by union-find over sorted edges, emitting (0,d) for every merging edge with d != 0,
+//   * H_q (q>=1) by implicit coboundary-matrix reduction with a binary heap working column,
+//     the emergent-pair shortcut, a pivot->column hash map and clearing between dimensions,
+//   * pairs emitted in processing order, zero-persistence pairs dropped.
+// Parity is PINNED for this file: tests/test_oracle_golden.py checks it against the 32
+// shipped point clouds + summary_stats.json of the reference (tda-output/), see tests/golden/.
+//
+// Single-threaded on purpose (Ripser is single-threaded) -- it doubles as the CPU baseline.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <queue>
+#include <unordered_map>
+#include <vector>
+
+namespace {
+
+typedef int64_t idx_t;
+typedef float val_t;
+
+struct Simplex {
+  val_t diam;
+  idx_t idx;
+};
+
+// "reverse filtration" comparator: greater diameter first, ties -> smaller index first.
+struct RevFiltLess {
+  bool operator()(const Simplex& a, const Simplex& b) const {
+    return (a.diam > b.diam) || (a.diam == b.diam && a.idx < b.idx);
+  }
+};
+// heap comparator: top() = smallest diameter, ties -> largest index (the column pivot).
+struct HeapCmp {
+  bool operator()(const Simplex& a, const Simplex& b) const {
+    return (a.diam > b.diam) || (a.diam == b.diam && a.idx < b.idx);
+  }
+};
+typedef std::priority_queue<Simplex, std::vector<Simplex>, HeapCmp> Heap;
+
+struct Binom {
+  std::vector<std::vector<idx_t>> t;  // t[k][n]
+  void init(int n, int k) {
+    t.assign(k + 1, std::vector<idx_t>(n + 1, 0));
+    for (int i = 0; i <= n; ++i) {
+      t[0][i] = 1;
+      for (int j = 1; j <= std::min(i, k); ++j) t[j][i] = (j == i) ? 1 : t[j - 1][i - 1] + t[j][i - 1];
+    }
+  }
+  idx_t operator()(int n, int k) const { return (k > n || n < 0) ? 0 : t[k][n]; }
+};
+
+struct Stats {
+  int64_t columns[3], emergent[3], reduced[3], additions[3], pops[3], max_v[3], cofacets[3];
+};
+
+struct Rips {
+  int n;
+  int maxdim;
+  val_t thresh;
+  std::vector<val_t> dist;  // full n*n
+  Binom C;
+  std::vector<std::vector<double>> dgm;       // per dim: flat (birth, death)
+  std::vector<std::vector<idx_t>> pair_simplex;  // per dim: flat (birth idx, death idx or -1)
+  int64_t num_edges;
+  Stats st;
+
+  val_t d(int i, int j) const { return dist[(size_t)i * n + j]; }
+
+  int max_vertex(idx_t idx, int k, int top) const {
+    // largest v <= top with C(v,k) <= idx
+    int lo = k - 1, hi = top;  // C(k-1,k)=0 <= idx always
+    while (lo < hi) {
+      int mid = lo + (hi - lo + 1) / 2;
+      if (C(mid, k) <= idx) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+  }
+  void vertices(idx_t idx, int dim, int* out) const {
+    int top = n - 1;
+    for (int k = dim + 1; k > 0; --k) {
+      int v = max_vertex(idx, k, top);
+      out[dim + 1 - k] = v;  // descending order
+      idx -= C(v, k);
+      top = v - 1;
+    }
+  }
+  val_t diameter(idx_t idx, int dim) const {
+    int vs[8];
+    vertices(idx, dim, vs);
+    val_t m = 0;
+    for (int a = 0; a <= dim; ++a)
+      for (int b = a + 1; b <= dim; ++b) m = std::max(m, d(vs[a], vs[b]));
+    return m;
+  }
+
+  // cofacet enumeration in decreasing order of the added vertex (= decreasing cofacet index)
+  struct Cofacets {
+    const Rips& r;
+    idx_t below, above;
+    int v, k, dim;
+    int vs[8];
+    val_t sdiam;
+    Cofacets(const Rips& r_, Simplex s, int dim_) : r(r_), below(s.idx), above(0), v(r_.n - 1), k(dim_ + 1), dim(dim_), sdiam(s.diam) {
+      r.vertices(s.idx, dim, vs);
+    }
+    bool has_next(bool all = true) {
+      if (!all) return v >= k && r.C(v, k) > below;  // only vertices above every simplex vertex
+      while (v != -1 && r.C(v, k) <= below) {
+        below -= r.C(v, k);
+        above += r.C(v, k + 1);
+        --v; --k;
+      }
+      return v != -1;
+    }
+    Simplex next() {
+      val_t cd = sdiam;
+      for (int a = 0; a <= dim; ++a) cd = std::max(cd, r.d(v, vs[a]));
+      idx_t ci = above + r.C(v, k + 1) + below;
+      --v;
+      return Simplex{cd, ci};
+    }
+  };
+
+  static Simplex pop_pivot(Heap& h, int64_t& pops) {
+    if (h.empty()) return Simplex{0, -1};
+    Simplex p = h.top(); h.pop(); ++pops;
+    while (!h.empty() && h.top().idx == p.idx) {
+      h.pop(); ++pops;
+      if (h.empty()) return Simplex{0, -1};
+      p = h.top(); h.pop(); ++pops;
+    }
+    return p;
+  }
+  static Simplex get_pivot(Heap& h, int64_t& pops) {
+    Simplex p = pop_pivot(h, pops);
+    if (p.idx != -1) h.push(p);
+    return p;
+  }
+
+  void run() {
+    C.init(n, maxdim + 2);
+    dgm.assign(maxdim + 1, {});
+    pair_simplex.assign(maxdim + 1, {});
+    std::memset(&st, 0, sizeof(st));
+    const double INF = std::numeric_limits<double>::infinity();
+    if (!(thresh < std::numeric_limits<val_t>::infinity())) {
+      // enclosing radius: min_i max_j d(i,j)
+      val_t enc = std::numeric_limits<val_t>::infinity();
+      for (int i = 0; i < n; ++i) {
+        val_t r = 0;
+        for (int j = 0; j < n; ++j) r = std::max(r, d(i, j));
+        enc = std::min(enc, r);
+      }
+      thresh = (n > 0) ? enc : 0;
+    }
+    // ---- dimension 0
+    std::vector<Simplex> edges;
+    for (int i = 1; i < n; ++i)
+      for (int j = 0; j < i; ++j)
+        if (d(i, j) <= thresh) edges.push_back(Simplex{d(i, j), C(i, 2) + j});
+    num_edges = (int64_t)edges.size();
+    std::sort(edges.begin(), edges.end(), RevFiltLess());  // reverse filtration order
+    std::vector<int> parent(n), rnk(n, 0);
+    for (int i = 0; i < n; ++i) parent[i] = i;
+    auto find = [&](int x) {
+      int y = x, z;
+      while ((z = parent[y]) != y) y = z;
+      while ((z = parent[x]) != y) { parent[x] = y; x = z; }
+      return y;
+    };
+    std::vector<Simplex> columns;
+    for (auto it = edges.rbegin(); it != edges.rend(); ++it) {  // filtration order
+      int vs[2];
+      vertices(it->idx, 1, vs);
+      int u = find(vs[0]), v = find(vs[1]);
+      if (u != v) {
+        if (it->diam != 0) {
+          dgm[0].push_back(0.0); dgm[0].push_back((double)it->diam);
+          pair_simplex[0].push_back(-1); pair_simplex[0].push_back(it->idx);
+        }
+        if (rnk[u] > rnk[v]) parent[v] = u;
+        else { parent[u] = v; if (rnk[u] == rnk[v]) ++rnk[v]; }
+      } else if (maxdim >= 1) {
+        columns.push_back(*it);
+      }
+    }
+    std::reverse(columns.begin(), columns.end());
+    for (int i = 0; i < n; ++i)
+      if (find(i) == i) {
+        dgm[0].push_back(0.0); dgm[0].push_back(INF);
+        pair_simplex[0].push_back(i); pair_simplex[0].push_back(-1);
+      }
+    // ---- higher dimensions
+    std::vector<Simplex> simplices = edges;  // all dim-1 simplices <= thresh (any order)
+    for (int dim = 1; dim <= maxdim; ++dim) {
+      std::unordered_map<idx_t, int64_t> pivot_col;
+      pivot_col.reserve(columns.size());
+      reduce(columns, pivot_col, dim);
+      if (dim < maxdim) {
+        std::vector<Simplex> next_simplices, next_columns;
+        for (const Simplex& s : simplices) {
+          Cofacets cf(*this, s, dim);
+          while (cf.has_next(false)) {
+            Simplex c = cf.next();
+            if (c.diam <= thresh) {
+              next_simplices.push_back(c);
+              if (pivot_col.find(c.idx) == pivot_col.end()) next_columns.push_back(c);
+            }
+          }
+        }
+        std::sort(next_columns.begin(), next_columns.end(), RevFiltLess());
+        simplices.swap(next_simplices);
+        columns.swap(next_columns);
+      }
+    }
+  }
+
+  void reduce(const std::vector<Simplex>& columns, std::unordered_map<idx_t, int64_t>& pivot_col, int dim) {
+    const double INF = std::numeric_limits<double>::infinity();
+    std::vector<std::vector<idx_t>> V(columns.size());  // reduction columns (excluding the column itself)
+    st.columns[dim] = (int64_t)columns.size();
+    std::vector<Simplex> buf;
+    for (size_t j = 0; j < columns.size(); ++j) {
+      const Simplex col = columns[j];
+      Heap work;           // working coboundary
+      std::vector<idx_t> vcol;  // working reduction column entries (with multiplicity)
+      Simplex pivot{0, -1};
+      bool emergent = false;
+      {  // init coboundary + emergent-pair check
+        buf.clear();
+        bool check = true;
+        Cofacets cf(*this, col, dim);
+        while (cf.has_next()) {
+          Simplex c = cf.next();
+          ++st.cofacets[dim];
+          if (c.diam <= thresh) {
+            buf.push_back(c);
+            if (check && c.diam == col.diam) {
+              if (pivot_col.find(c.idx) == pivot_col.end()) { pivot = c; emergent = true; break; }
+              check = false;
+            }
+          }
+        }
+        if (!emergent) {
+          for (const Simplex& c : buf) work.push(c);
+          pivot = get_pivot(work, st.pops[dim]);
+        }
+      }
+      if (emergent) ++st.emergent[dim]; else ++st.reduced[dim];
+      for (;;) {
+        if (pivot.idx == -1) {
+          dgm[dim].push_back((double)col.diam); dgm[dim].push_back(INF);
+          pair_simplex[dim].push_back(col.idx); pair_simplex[dim].push_back(-1);
+          break;
+        }
+        auto it = pivot_col.find(pivot.idx);
+        if (it != pivot_col.end()) {
+          size_t a = (size_t)it->second;
+          ++st.additions[dim];
+          // add column a: its own coboundary plus the coboundaries of its reduction column
+          auto add_simplex = [&](idx_t sidx) {
+            vcol.push_back(sidx);
+            Simplex s{diameter(sidx, dim), sidx};
+            Cofacets cf(*this, s, dim);
+            while (cf.has_next()) {
+              Simplex c = cf.next();
+              ++st.cofacets[dim];
+              if (c.diam <= thresh) work.push(c);
+            }
+          };
+          add_simplex(columns[a].idx);
+          for (idx_t s : V[a]) add_simplex(s);
+          pivot = get_pivot(work, st.pops[dim]);
+          continue;
+        }
+        if (pivot.diam > col.diam) {
+          dgm[dim].push_back((double)col.diam); dgm[dim].push_back((double)pivot.diam);
+          pair_simplex[dim].push_back(col.idx); pair_simplex[dim].push_back(pivot.idx);
+        }
+        pivot_col.emplace(pivot.idx, (int64_t)j);
+        // store the reduction column mod 2
+        std::sort(vcol.begin(), vcol.end());
+        for (size_t a = 0; a < vcol.size();) {
+          size_t b = a;
+          while (b < vcol.size() && vcol[b] == vcol[a]) ++b;
+          if ((b - a) & 1) V[j].push_back(vcol[a]);
+          a = b;
+        }
+        st.max_v[dim] = std::max<int64_t>(st.max_v[dim], (int64_t)V[j].size());
+        break;
+      }
+    }
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+// dist: full n*n float32 matrix (row-major, symmetric, zero diagonal). thresh = +inf -> enclosing radius.
+void* rips_oracle_run(const float* dist, int n, int maxdim, float thresh) {
+  Rips* r = new Rips();
+  r->n = n; r->maxdim = maxdim; r->thresh = thresh;
+  r->dist.assign(dist, dist + (size_t)n * n);
+  r->run();
+  return r;
+}
+int64_t rips_oracle_count(void* h, int dim) { return (int64_t)((Rips*)h)->dgm[dim].size() / 2; }
+void rips_oracle_get(void* h, int dim, double* pairs, int64_t* simplices) {
+  Rips* r = (Rips*)h;
+  if (pairs) std::memcpy(pairs, r->dgm[dim].data(), r->dgm[dim].size() * sizeof(double));
+  if (simplices) std::memcpy(simplices, r->pair_simplex[dim].data(), r->pair_simplex[dim].size() * sizeof(int64_t));
+}
+int64_t rips_oracle_num_edges(void* h) { return ((Rips*)h)->num_edges; }
+float rips_oracle_thresh(void* h) { return ((Rips*)h)->thresh; }
+// stats layout per dim: columns, emergent, reduced, additions, pops, max_v, cofacets
+void rips_oracle_stats(void* h, int dim, int64_t* out) {
+  Rips* r = (Rips*)h;
+  out[0] = r->st.columns[dim]; out[1] = r->st.emergent[dim]; out[2] = r->st.reduced[dim];
+  out[3] = r->st.additions[dim]; out[4] = r->st.pops[dim]; out[5] = r->st.max_v[dim]; out[6] = r->st.cofacets[dim];
+}
+void rips_oracle_free(void* h) { delete (Rips*)h; }
+
+}  // extern "C"
