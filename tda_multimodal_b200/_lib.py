@@ -1,0 +1,70 @@
+"""ctypes binding of libtda_b200.so (the C ABI declared in include/tda_b200.h)."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtda_b200.so")
+
+c_void_p, c_int, c_float, c_size_t, c_int64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_int64
+
+# name -> (restype, argtypes); every symbol include/tda_b200.h declares must be listed here
+PROTOTYPES = {
+    "tda_version": (c_int, []),
+    "tda_last_error": (ctypes.c_char_p, []),
+    "tda_launch_count": (c_int64, []),
+    "tda_launch_count_reset": (None, []),
+    "tda_pdist_lowdim": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tda_rips_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_size_t]),
+    "tda_rips": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                         c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]),
+    "tda_rips_stats": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_size_t, c_void_p]),
+}
+
+TDA_ERR_CAPACITY = -4
+
+
+class TdaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libtda_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Loads the library; fails loudly when it has not been built (no CPU fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C tda_multimodal_b200/csrc`). There is no CPU fallback for this path.")
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(code):
+    if code != 0:
+        raise TdaError(code, lib().tda_last_error().decode("utf-8", "replace"))
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("tda_multimodal_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch
+
+
+def ptr(t):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+def stream_ptr():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)

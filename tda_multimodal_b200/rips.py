@@ -1,0 +1,170 @@
+"""Vietoris-Rips persistence on the GPU: host side of `ripser(X, maxdim)` (reference call sites
+debug_tda_pipeline.py:109-110, analyze_tda_over_layers.py:76, analyze_adversarial_tda.py:100-101).
+
+`rips_batch` is the batched device entry (layers x bootstrap resamples in one call); `ripser` mirrors the
+keyword surface and the result dict of ripser.py's `ripser` for a single cloud.
+"""
+import warnings
+
+import numpy as np
+
+from . import _lib
+
+
+def _next_pow2(x):
+    p = 1
+    while p < x:
+        p <<= 1
+    return p
+
+
+def pdist_lowdim(pts):
+    """[B,n,d] float32 cuda tensor -> [B,n,n] float32 euclidean distances (ripser.py front-end definition)."""
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    B, n, d = pts.shape
+    dm = torch.empty((B, n, n), dtype=torch.float32, device=pts.device)
+    _lib.check(L.tda_pdist_lowdim(_lib.ptr(pts), n, d, B, _lib.ptr(dm), _lib.stream_ptr()))
+    return dm
+
+
+def rips_batch(dm, maxdim=1, thresh=float("inf"), cap1=None, pool_bytes=None, want_simplices=False, want_stats=False):
+    """Persistence of `B` dense distance matrices `dm` [B,n,n] (float32, CUDA).
+
+    Returns a list of B dicts: {'dgms': [float64 (n_k,2)]*(maxdim+1), 'num_edges': int, 'thresh': float
+    [, 'simplices': [...], 'stats': {...}]}.  Grows cap1 / the column pool and retries when the library
+    reports TDA_ERR_CAPACITY.
+    """
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    if maxdim > 1:
+        raise NotImplementedError("tda_multimodal_b200: Rips persistence is implemented for maxdim <= 1 in this round")
+    assert dm.is_cuda and dm.dtype == torch.float32 and dm.dim() == 3 and dm.shape[1] == dm.shape[2]
+    dm = dm.contiguous()
+    B, n, _ = dm.shape
+    dev = dm.device
+    cap1 = _next_pow2(cap1 or max(64, 4 * n))
+    pool_bytes = int(pool_bytes or max(64 << 20, 64 * n * n * min(B, 8)))
+    free_bytes = torch.cuda.mem_get_info(dev)[0]
+    with torch.cuda.device(dev):
+        while True:
+            ws_bytes = int(L.tda_rips_workspace_bytes(n, B, maxdim, cap1, pool_bytes))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            h0 = torch.empty((B, n, 2), dtype=torch.float32, device=dev)
+            h0s = torch.empty((B, n, 2), dtype=torch.int64, device=dev) if want_simplices else None
+            h1 = torch.empty((B, cap1, 2), dtype=torch.float32, device=dev) if maxdim >= 1 else None
+            h1s = torch.empty((B, cap1, 2), dtype=torch.int64, device=dev) if (want_simplices and maxdim >= 1) else None
+            counts = torch.zeros((B, 4), dtype=torch.int32, device=dev)
+            th = torch.empty((B,), dtype=torch.float32, device=dev)
+            code = L.tda_rips(_lib.ptr(dm), n, B, maxdim, float(thresh), _lib.ptr(h0), _lib.ptr(h0s), _lib.ptr(h1), _lib.ptr(h1s),
+                              cap1, _lib.ptr(counts), _lib.ptr(th), _lib.ptr(ws), ws_bytes, pool_bytes, _lib.stream_ptr())
+            if code == _lib.TDA_ERR_CAPACITY and pool_bytes < free_bytes // 2:
+                cap1 *= 2
+                pool_bytes *= 4
+                del ws
+                continue
+            _lib.check(code)
+            break
+        stats = None
+        if want_stats and maxdim >= 1:
+            stats = np.zeros((B, 8), dtype=np.int64)
+            _lib.check(L.tda_rips_stats(_lib.ptr(ws), n, B, maxdim, cap1, pool_bytes, stats.ctypes.data))
+    counts_h = counts.cpu().numpy()
+    h0_h = h0.cpu().numpy()
+    h1_h = h1.cpu().numpy() if h1 is not None else None
+    th_h = th.cpu().numpy()
+    h0s_h = h0s.cpu().numpy() if h0s is not None else None
+    h1s_h = h1s.cpu().numpy() if h1s is not None else None
+    out = []
+    for p in range(B):
+        c0, c1 = int(counts_h[p, 0]), int(counts_h[p, 1])
+        dgms = [h0_h[p, :c0].astype(np.float64)]
+        if maxdim >= 1:
+            dgms.append(h1_h[p, :c1].astype(np.float64))
+        r = {"dgms": dgms, "num_edges": int(counts_h[p, 2]), "thresh": float(th_h[p])}
+        if want_simplices:
+            r["simplices"] = [h0s_h[p, :c0]] + ([h1s_h[p, :c1]] if maxdim >= 1 else [])
+        if stats is not None:
+            r["stats"] = dict(zip(["columns", "apparent", "reduced", "additions", "pushes", "pops", "extensions", "max_v"], stats[p].tolist()))
+        out.append(r)
+    return out
+
+
+def _as_cuda_f32(X):
+    torch = _lib.require_cuda()
+    if isinstance(X, torch.Tensor):
+        return X.to(device="cuda", dtype=torch.float32)
+    return torch.from_numpy(np.ascontiguousarray(X, dtype=np.float32)).cuda()
+
+
+def greedy_permutation_device(dm, n_perm):
+    """Furthest-point sampling with ripser.py's `n_perm` semantics (start at index 0), on the device."""
+    torch = _lib.require_cuda()
+    n = dm.shape[0]
+    idx = torch.zeros(n_perm, dtype=torch.long, device=dm.device)
+    lambdas = torch.zeros(n_perm, dtype=torch.float32, device=dm.device)
+    ds = dm[0].clone()
+    for i in range(1, n_perm):
+        j = torch.argmax(ds)
+        idx[i] = j
+        lambdas[i - 1] = ds[j]
+        ds = torch.minimum(ds, dm[j])
+    lambdas[-1] = ds.max()
+    return idx, lambdas
+
+
+def ripser(X, maxdim=1, thresh=np.inf, coeff=2, distance_matrix=False, do_cocycles=False, metric="euclidean", n_perm=None):
+    """Drop-in for ``ripser.ripser`` (ripser.py): same arguments, same result keys; `dgms` are float64
+    ``(n_k, 2)`` arrays (debug_tda_pipeline.py:124-127 json-dumps np.max of them, which needs float64)."""
+    torch = _lib.require_cuda()
+    if coeff != 2:
+        raise NotImplementedError("tda_multimodal_b200.ripser: only coeff=2 (the reference's setting) is implemented")
+    if do_cocycles:
+        raise NotImplementedError("tda_multimodal_b200.ripser: do_cocycles=True is not implemented")
+    if hasattr(X, "tocoo"):
+        raise NotImplementedError("tda_multimodal_b200.ripser: sparse distance matrices are not implemented")
+    is_tensor = isinstance(X, torch.Tensor)
+    shape = tuple(X.shape)
+    if len(shape) != 2:
+        raise ValueError("ripser expects a 2-D array")
+    if distance_matrix:
+        if shape[0] != shape[1]:
+            raise ValueError("Distance matrix is not square")
+    else:
+        if shape[0] == shape[1]:
+            warnings.warn("The input matrix is square, but the distance_matrix flag is off.  Did you mean to indicate that "
+                          "this was a distance matrix?")
+        elif shape[0] < shape[1]:
+            warnings.warn("The input point cloud has more columns than rows; did you mean to transpose?")
+    n = shape[0]
+    if n_perm is not None:
+        if n_perm > n:
+            raise ValueError("Number of points in greedy permutation is greater than number of points in the point cloud")
+        if n_perm < 0:
+            raise ValueError("Should be a strictly positive number of points in the greedy permutation")
+    Xd = _as_cuda_f32(X)
+    if distance_matrix:
+        dm = Xd
+    elif metric == "euclidean" and shape[1] <= 64:
+        dm = pdist_lowdim(Xd[None])[0]
+    else:
+        from .pdist import pdist  # tensor-core distance matrix for high-dimensional clouds
+        dm = pdist(Xd[None], metric=metric)[0]
+    idx_perm = np.arange(n)
+    r_cover = 0.0
+    dperm2all = dm
+    if n_perm is not None and n_perm < n:
+        idx_t, lambdas = greedy_permutation_device(dm, n_perm)
+        r_cover = float(lambdas[-1])
+        dperm2all = dm[idx_t, :]
+        dm = dperm2all[:, idx_t].contiguous()
+        idx_perm = idx_t.cpu().numpy()
+    res = rips_batch(dm[None], maxdim=maxdim, thresh=float(thresh))[0]
+    return {
+        "dgms": res["dgms"],
+        "cocycles": [[] for _ in range(maxdim + 1)],
+        "num_edges": res["num_edges"],
+        "dperm2all": dperm2all if is_tensor else dperm2all.cpu().numpy(),
+        "idx_perm": idx_perm,
+        "r_cover": r_cover,
+    }

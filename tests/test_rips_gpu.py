@@ -1,0 +1,134 @@
+"""GPU parity: libtda_b200 Rips (through the C ABI) vs the reference's shipped results and the CPU oracle."""
+import numpy as np
+import pytest
+
+from tests.helpers import load_ref_rips_golden, reference_stats, torus3d, blobs3d, circle2d, same_diagram
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def test_reference_golden_clouds_batched(torch_cuda):
+    """All 32 shipped clouds in ONE batched call; every summary_stats.json field bit-exact."""
+    torch = torch_cuda
+    from tda_multimodal_b200 import rips
+    clouds, stats = load_ref_rips_golden()
+    dm = rips.pdist_lowdim(torch.from_numpy(clouds).cuda())
+    res = rips.rips_batch(dm, maxdim=1)
+    for i in range(32):
+        got = reference_stats(res[i]["dgms"])
+        for key in ("n_h1_features", "max_h1_persistence", "all_h1_persistence_values", "n_h0_features", "max_h0_persistence"):
+            assert got[key] == stats[i][key], (i, key, got[key], stats[i][key])
+
+
+def test_reference_golden_via_shim(torch_cuda):
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "shims"))
+    from ripser import ripser
+    clouds, stats = load_ref_rips_golden()
+    for i in (0, 13, 25, 31):
+        r = ripser(clouds[i], maxdim=1)
+        assert set(r) >= {"dgms", "cocycles", "num_edges", "dperm2all", "idx_perm", "r_cover"}
+        assert r["dgms"][0].dtype == np.float64 and r["dgms"][1].dtype == np.float64
+        got = reference_stats(r["dgms"])
+        assert got["all_h1_persistence_values"] == stats[i]["all_h1_persistence_values"]
+        assert got["max_h0_persistence"] == stats[i]["max_h0_persistence"]
+
+
+@pytest.mark.parametrize("gen,n,seed", [(torus3d, 100, 0), (torus3d, 400, 1), (blobs3d, 300, 2), (blobs3d, 1000, 3),
+                                        (circle2d, 257, 4), (torus3d, 1000, 5)])
+def test_matches_oracle_bit_exact(torch_cuda, gen, n, seed):
+    torch = torch_cuda
+    from tda_multimodal_b200 import rips
+    from oracle import rips as orips
+    X = gen(n, np.random.default_rng(seed))
+    want = orips.ripser(X, maxdim=1, with_simplices=True)
+    dm = rips.pdist_lowdim(torch.from_numpy(X).cuda()[None])
+    assert np.array_equal(dm[0].cpu().numpy(), orips.euclidean_dm_f32(X))  # distance matrix bit-exact
+    got = rips.rips_batch(dm, maxdim=1, want_simplices=True, want_stats=True)[0]
+    assert got["num_edges"] == want["num_edges"]
+    assert np.float32(got["thresh"]) == np.float32(want["thresh"])
+    # H0: same rows in the same order, same death-edge indices (tie-free data)
+    assert np.array_equal(got["dgms"][0], want["dgms"][0])
+    assert np.array_equal(got["simplices"][0][:-1, 1], want["simplices"][0][:-1, 1])
+    # H1: same multiset of (birth, death), births descending, same birth edges
+    assert same_diagram(got["dgms"][1], want["dgms"][1])
+    assert np.all(np.diff(got["dgms"][1][:, 0]) <= 0)
+    assert np.array_equal(got["dgms"][1], want["dgms"][1])
+    assert np.array_equal(got["simplices"][1][:, 0], want["simplices"][1][:, 0])
+
+
+def test_edge_cases(torch_cuda):
+    torch = torch_cuda
+    from tda_multimodal_b200 import rips
+    from oracle import rips as orips
+    sq = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], dtype=np.float32)
+    d = rips.ripser(sq, maxdim=1)["dgms"]
+    assert d[1].shape == (1, 2) and d[1][0, 0] == 1.0 and d[1][0, 1] == np.float32(np.sqrt(np.float32(2.0)))
+    # single point, two points
+    one = rips.ripser(np.zeros((1, 3), np.float32), maxdim=1)["dgms"]
+    assert one[0].shape == (1, 2) and np.isinf(one[0][0, 1]) and one[1].shape == (0, 2)
+    two = rips.ripser(np.array([[0, 0, 0], [3, 4, 0]], np.float32), maxdim=1)["dgms"]
+    assert np.array_equal(two[0], np.array([[0, 5.0], [0, np.inf]])) and two[1].shape == (0, 2)
+    # duplicate points (zero-length edges) and ties: diagrams equal as multisets
+    rng = np.random.default_rng(9)
+    X = blobs3d(120, rng)
+    X = np.concatenate([X, X[:20]])  # bootstrap-with-replacement style duplicates
+    want = orips.ripser(X, maxdim=1)["dgms"]
+    got = rips.ripser(X, maxdim=1)["dgms"]
+    assert same_diagram(got[0], want[0]) and same_diagram(got[1], want[1])
+    # integer grid: massive ties
+    g = np.stack(np.meshgrid(np.arange(6), np.arange(6)), -1).reshape(-1, 2).astype(np.float32)
+    want = orips.ripser(g, maxdim=1)["dgms"]
+    got = rips.ripser(g, maxdim=1)["dgms"]
+    assert same_diagram(got[0], want[0]) and same_diagram(got[1], want[1])
+    # explicit threshold below the enclosing radius: several essential H0 classes
+    X = blobs3d(200, rng)
+    want = orips.ripser(X, maxdim=1, thresh=1.5)["dgms"]
+    got = rips.ripser(X, maxdim=1, thresh=1.5)["dgms"]
+    assert same_diagram(got[0], want[0]) and same_diagram(got[1], want[1])
+    # distance-matrix input, non-square rejected
+    dm = orips.euclidean_dm_f32(X)
+    got = rips.ripser(dm, maxdim=1, distance_matrix=True)["dgms"]
+    want = orips.ripser(dm, maxdim=1, distance_matrix=True)["dgms"]
+    assert same_diagram(got[1], want[1])
+    with pytest.raises(ValueError):
+        rips.ripser(np.zeros((3, 4), np.float32), distance_matrix=True)
+    with pytest.raises(NotImplementedError):
+        rips.ripser(X, coeff=3)
+
+
+def test_n_perm_landmarks(torch_cuda):
+    from tda_multimodal_b200 import rips
+    from oracle import rips as orips
+    X = torus3d(600, np.random.default_rng(21))
+    got = rips.ripser(X, maxdim=1, n_perm=150)
+    want = orips.ripser(X, maxdim=1, n_perm=150)
+    assert np.array_equal(got["idx_perm"], want["idx_perm"])
+    assert np.float32(got["r_cover"]) == np.float32(want["r_cover"])
+    assert same_diagram(got["dgms"][1], want["dgms"][1]) and same_diagram(got["dgms"][0], want["dgms"][0])
+
+
+def test_large_cloud_properties(torch_cuda):
+    """BASELINE-size cloud (n=2000): size-independent properties instead of the (slow) oracle."""
+    torch = torch_cuda
+    from tda_multimodal_b200 import rips
+    rng = np.random.default_rng(2000)
+    X = blobs3d(2000, rng)
+    dm = rips.pdist_lowdim(torch.from_numpy(X).cuda()[None])
+    r = rips.rips_batch(dm, maxdim=1)[0]
+    d0, d1 = r["dgms"]
+    assert d0.shape == (2000, 2) and np.isinf(d0[-1, 1]) and np.all(np.diff(d0[:-1, 1]) >= 0)
+    from scipy.sparse.csgraph import minimum_spanning_tree
+    mst = np.sort(minimum_spanning_tree(dm[0].cpu().numpy().astype(np.float64)).data)
+    assert np.array_equal(mst.astype(np.float32), d0[:-1, 1].astype(np.float32))
+    assert np.all(d1[:, 1] > d1[:, 0]) and np.all(np.diff(d1[:, 0]) <= 0)
+    perm = rng.permutation(2000)
+    r2 = rips.rips_batch(rips.pdist_lowdim(torch.from_numpy(X[perm]).cuda()[None]), maxdim=1)[0]
+    assert same_diagram(r2["dgms"][1], d1) and same_diagram(r2["dgms"][0], d0)
