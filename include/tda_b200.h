@@ -62,8 +62,10 @@ size_t tda_rips_workspace_bytes(int n, int batch, int maxdim, int cap1, size_t p
 int tda_rips(const float* dm, int n, int batch, int maxdim, float thresh,
              float* h0_pairs, int64_t* h0_simplex, float* h1_pairs, int64_t* h1_simplex, int cap1,
              int32_t* counts, float* thresh_out, void* ws, size_t ws_bytes, size_t pool_bytes, void* stream);
-/* device statistics of the last tda_rips call on this workspace: [batch,8] int64:
- * columns(non-MST edges<=thresh), apparent, reduced, additions, pushes, pops, horizon_extensions, max_V */
+/* device statistics of the last tda_rips call on this workspace: [batch,16] int64:
+ * columns(non-MST edges<=thresh), apparent, reduced, additions, pushes, pops, horizon_extensions, max_V,
+ * SM cycles in extract / owner lookup / apparent add / reduced-column add / horizon extension / finalise,
+ * edges re-enumerated by reduced-column adds, edges re-enumerated by horizon extensions */
 int tda_rips_stats(const void* ws, int n, int batch, int maxdim, int cap1, size_t pool_bytes, int64_t* stats_host);
 
 #ifdef __cplusplus

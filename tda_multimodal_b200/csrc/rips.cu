@@ -36,7 +36,8 @@ constexpr int kMaxNew = kReduceThreads * kGenItems / kChunk + 2;
 constexpr int kRankDiag = 0x7fffffff;
 
 // stats slots
-enum { ST_COLUMNS = 0, ST_APPARENT, ST_REDUCED, ST_ADDITIONS, ST_PUSHES, ST_POPS, ST_EXTENSIONS, ST_MAXV, ST_N };
+enum { ST_COLUMNS = 0, ST_APPARENT, ST_REDUCED, ST_ADDITIONS, ST_PUSHES, ST_POPS, ST_EXTENSIONS, ST_MAXV,
+       ST_CYC_EXTRACT, ST_CYC_OWNER, ST_CYC_GEN, ST_CYC_BADD, ST_CYC_EXT, ST_CYC_FINAL, ST_BADD_EDGES, ST_EXT_EDGES, ST_N };
 
 // ------------------------------------------------------------------------------------------------
 // low-dimensional euclidean distance matrix (ripser.py front end)
@@ -118,80 +119,97 @@ __global__ void rank_diag_kernel(int n, int* __restrict__ rank) {  // n == 1 or 
 }
 
 // ------------------------------------------------------------------------------------------------
-// H0: Boruvka MST on the rank matrix, one CTA per cloud.  Ranks are distinct, so the minimum
-// spanning forest is unique and equals the set of merging edges of ripser's union-find sweep.
-// dynamic smem: comp[n], parent[n], cbest[n] (uint32)
-__global__ void __launch_bounds__(1024) boruvka_kernel(const int* __restrict__ rank, const uint32_t* __restrict__ ends,
-                                                       const float* __restrict__ sdist, const int* __restrict__ Tarr, int n, int64_t E,
-                                                       uint8_t* __restrict__ mst, float* __restrict__ h0_pairs, int64_t* __restrict__ h0_simplex,
-                                                       int32_t* __restrict__ counts, int* __restrict__ mstlist_g) {
-  extern __shared__ uint32_t sm[];
-  uint32_t* comp = sm;
-  uint32_t* parent = sm + n;
-  uint32_t* cbest = sm + 2 * n;
-  __shared__ int s_merged, s_nmst;
+// H0: Boruvka MST on the rank matrix.  Ranks are distinct, so the minimum spanning forest is unique and
+// equals the set of merging edges of ripser's union-find sweep.  Per round: a grid-wide scan kernel (one
+// warp per matrix row: smallest rank leaving the row's component -> atomicMin per component) and a
+// one-CTA-per-cloud merge kernel (hook, break 2-cycles, pointer jumping, relabel).
+constexpr uint32_t kNoEdge = 0xffffffffu;
+__global__ void boruvka_init_kernel(int n, uint32_t* __restrict__ comp, uint32_t* __restrict__ cbest, int* __restrict__ done) {
+  int p = blockIdx.y;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { comp[(size_t)p * n + i] = i; cbest[(size_t)p * n + i] = kNoEdge; }
+  if (i == 0) done[p] = 0;
+}
+__global__ void __launch_bounds__(256) boruvka_scan_kernel(const int* __restrict__ rank, const int* __restrict__ Tarr, int n,
+                                                           const uint32_t* __restrict__ comp_g, uint32_t* __restrict__ cbest_g,
+                                                           const int* __restrict__ done) {
+  const int p = blockIdx.y;
+  if (done[p]) return;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const int T = Tarr[p];
+  const uint32_t* comp = comp_g + (size_t)p * n;
+  const int* row = rank + ((size_t)p * n + i) * n;
+  const uint32_t ci = comp[i];
+  uint32_t best = kNoEdge;
+  for (int j = lane; j < n; j += 32) {
+    int r = row[j];
+    if (r < T && comp[j] != ci) best = min(best, (uint32_t)r);
+  }
+  best = warp_min_u32(best);
+  if (lane == 0 && best != kNoEdge) atomicMin(&cbest_g[(size_t)p * n + ci], best);
+}
+__global__ void __launch_bounds__(1024) boruvka_merge_kernel(const uint32_t* __restrict__ ends, int n, int64_t E, uint32_t* __restrict__ comp_g,
+                                                             uint32_t* __restrict__ parent_g, uint32_t* __restrict__ cbest_g,
+                                                             uint8_t* __restrict__ mst, int* __restrict__ done) {
+  const int p = blockIdx.x;
+  if (done[p]) return;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  uint32_t* comp = comp_g + (size_t)p * n;
+  uint32_t* parent = parent_g + (size_t)p * n;
+  uint32_t* cbest = cbest_g + (size_t)p * n;
+  const uint32_t* EN = ends + (size_t)p * E;
+  uint8_t* M = mst + (size_t)p * E;
+  int merged = 0;
+  for (int c = tid; c < n; c += nt) {
+    uint32_t r = cbest[c];
+    uint32_t par = c;
+    if (r != kNoEdge) {  // only component roots ever receive a candidate
+      uint32_t e = EN[r];
+      uint32_t u = e >> 16, v = e & 0xffffu;
+      par = comp[u] == (uint32_t)c ? comp[v] : comp[u];
+      M[r] = 1;  // both sides may pick the same edge: same value written twice
+      merged = 1;
+    }
+    parent[c] = par;
+  }
+  if (!__syncthreads_or(merged)) {
+    if (tid == 0) done[p] = 1;
+    return;
+  }
+  // two components that chose each other did so through the same edge: the smaller id becomes the root
+  for (int c = tid; c < n; c += nt) {
+    uint32_t q = parent[c];
+    if (q != (uint32_t)c && parent[q] == (uint32_t)c && (uint32_t)c < q) parent[c] = c;
+  }
+  __syncthreads();
+  for (int it = 0; it < 32; ++it) {  // pointer jumping
+    int changed = 0;
+    for (int c = tid; c < n; c += nt) {
+      uint32_t q = parent[c], g = parent[q];
+      if (g != q) { parent[c] = g; changed = 1; }
+    }
+    if (!__syncthreads_or(changed)) break;
+  }
+  for (int i = tid; i < n; i += nt) { comp[i] = parent[comp[i]]; cbest[i] = kNoEdge; }
+}
+
+// gather the MST ranks, sort them, emit the H0 rows.  One CTA per cloud.
+__global__ void __launch_bounds__(1024) h0_emit_kernel(const uint32_t* __restrict__ ends, const float* __restrict__ sdist,
+                                                       const int* __restrict__ Tarr, int n, int64_t E, const uint8_t* __restrict__ mst,
+                                                       const uint32_t* __restrict__ comp_g, float* __restrict__ h0_pairs,
+                                                       int64_t* __restrict__ h0_simplex, int32_t* __restrict__ counts, int* __restrict__ mstlist_g) {
+  __shared__ int s_zero, s_nmst;
   const int p = blockIdx.x;
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-  const int* R = rank + (size_t)p * n * n;
   const uint32_t* EN = ends + (size_t)p * E;
+  const uint32_t* comp = comp_g + (size_t)p * n;
   const int T = Tarr[p];
-  uint8_t* M = mst + (size_t)p * E;
+  const uint8_t* M = mst + (size_t)p * E;
   int* mstlist = mstlist_g + (size_t)p * n;
-  for (int i = tid; i < n; i += nt) comp[i] = i;
-  if (tid == 0) s_nmst = 0;
+  if (tid == 0) { s_nmst = 0; s_zero = 0; }
   __syncthreads();
-  for (int round = 0; round < 40; ++round) {
-    for (int i = tid; i < n; i += nt) { cbest[i] = 0xffffffffu; parent[i] = i; }
-    if (tid == 0) s_merged = 0;
-    __syncthreads();
-    for (int i = warp; i < n; i += nwarps) {
-      uint32_t ci = comp[i];
-      uint32_t best = 0xffffffffu;
-      const int* row = R + (size_t)i * n;
-      for (int j = lane; j < n; j += 32) {
-        int r = row[j];
-        if (r < T && comp[j] != ci) best = min(best, (uint32_t)r);
-      }
-      best = warp_min_u32(best);
-      if (lane == 0 && best != 0xffffffffu) atomicMin(&cbest[ci], best);
-    }
-    __syncthreads();
-    for (int c = tid; c < n; c += nt) {
-      uint32_t r = cbest[c];
-      if (r != 0xffffffffu) {  // only roots (comp ids) ever receive a value
-        uint32_t e = EN[r];
-        uint32_t u = e >> 16, v = e & 0xffffu;
-        uint32_t other = comp[u] == (uint32_t)c ? comp[v] : comp[u];
-        parent[c] = other;
-        if (M[r] == 0) {  // both sides may pick the same edge; benign duplicate writes of the same value
-          M[r] = 1;
-        }
-        s_merged = 1;
-      }
-    }
-    __syncthreads();
-    if (!s_merged) break;
-    // break 2-cycles (two components choosing the same edge): smaller id becomes the root
-    for (int c = tid; c < n; c += nt) {
-      uint32_t q = parent[c];
-      if (q != (uint32_t)c && parent[q] == (uint32_t)c && (uint32_t)c < q) parent[c] = c;
-    }
-    __syncthreads();
-    // pointer jumping (parent trees have depth <= n; log rounds)
-    for (int it = 0; it < 20; ++it) {
-      int changed = 0;
-      for (int c = tid; c < n; c += nt) {
-        uint32_t q = parent[c], g = parent[q];
-        if (g != q) { parent[c] = g; changed = 1; }
-      }
-      if (!__syncthreads_or(changed)) break;
-    }
-    for (int i = tid; i < n; i += nt) comp[i] = parent[comp[i]];
-    __syncthreads();
-  }
-  // collect MST ranks: each merging edge was flagged exactly once in M; gather through cbest history is
-  // not kept, so rescan the flags of the ranks < T (cheap: one pass, coalesced bytes)
   for (int64_t r = tid; r < T; r += nt)
     if (M[r]) {
       int pos = atomicAdd(&s_nmst, 1);
@@ -199,12 +217,11 @@ __global__ void __launch_bounds__(1024) boruvka_kernel(const int* __restrict__ r
     }
   __syncthreads();
   const int nm = min(s_nmst, n - 1);
-  // sort the <= n-1 MST ranks ascending (bitonic in global/L2, small)
   int np2 = 1;
   while (np2 < nm) np2 <<= 1;
-  for (int i = nm + tid; i < np2 && i < n; i += nt) mstlist[i] = 0x7fffffff;
-  __syncthreads();
   if (np2 <= n) {
+    for (int i = nm + tid; i < np2; i += nt) mstlist[i] = 0x7fffffff;
+    __syncthreads();
     for (int k = 2; k <= np2; k <<= 1)
       for (int j = k >> 1; j > 0; j >>= 1) {
         for (int i = tid; i < np2; i += nt) {
@@ -217,7 +234,7 @@ __global__ void __launch_bounds__(1024) boruvka_kernel(const int* __restrict__ r
         }
         __syncthreads();
       }
-  } else {  // np2 > n can only happen for tiny n; fall back to a serial insertion sort
+  } else {  // np2 > n only for tiny n: serial insertion sort
     if (tid == 0)
       for (int i = 1; i < nm; ++i) {
         int v = mstlist[i], k = i - 1;
@@ -226,16 +243,14 @@ __global__ void __launch_bounds__(1024) boruvka_kernel(const int* __restrict__ r
       }
     __syncthreads();
   }
-  // emit H0 rows: (0, d) for d != 0 ascending, then one (0, inf) per remaining component.
-  // zero-length merging edges have the smallest ranks, so they are a prefix of the sorted list.
+  // rows: (0, d) for d != 0 ascending, then one (0, inf) per remaining component.  Zero-length merging
+  // edges have the smallest ranks, so they are a prefix of the sorted list.
   float* out = h0_pairs + (size_t)p * n * 2;
   int64_t* outs = h0_simplex ? h0_simplex + (size_t)p * n * 2 : nullptr;
-  if (tid == 0) s_merged = 0;  // reused: number of zero-length MST edges
-  __syncthreads();
   for (int k = tid; k < nm; k += nt)
-    if (sdist[(size_t)p * E + mstlist[k]] == 0.f) atomicAdd(&s_merged, 1);
+    if (sdist[(size_t)p * E + mstlist[k]] == 0.f) atomicAdd(&s_zero, 1);
   __syncthreads();
-  const int z = s_merged;
+  const int z = s_zero;
   for (int k = z + tid; k < nm; k += nt) {
     int r = mstlist[k];
     int row = k - z;
@@ -296,17 +311,39 @@ __global__ void apparent_kernel(const int* __restrict__ rank, const uint32_t* __
 
 // ------------------------------------------------------------------------------------------------
 // residual reduction
+//
+// Working column of one edge b with an empty lune = set of triangle keys with odd multiplicity in
+// delta(V), V = edges added so far.  Three levels, all owned by one CTA:
+//   F      : open-addressing hash SET in shared memory holding the keys in [base, fmax]; inserting a key
+//            that is already present removes it (Z/2 cancellation is free); pop-min = block-wide scan.
+//   heap   : monotone radix heap for the keys > fmax: bucket q>=1 holds keys whose highest bit differing
+//            from `base` is q-1, as linked lists of 512-key chunks in a global pool (per-CTA free list +
+//            global bump).  When F runs dry the first non-empty bucket [L,U] is streamed into F
+//            (base=L, fmax=U); when F overflows its upper half is spilled back (fmax lowered).
+// Keys above the horizon H are not stored at all; when everything <= H is consumed the horizon is
+// extended and delta(V) re-enumerated for the new window.
 template <typename K> struct KeyTraits;
 template <> struct KeyTraits<uint32_t> {
   static constexpr int NB = 33;
   static __device__ __forceinline__ int bucket(uint32_t x) { return 32 - __clz(x); }
   static __device__ __forceinline__ uint32_t maxv() { return 0xffffffffu; }
+  static __device__ __forceinline__ uint32_t low_mask(int b) { return b >= 32 ? 0xffffffffu : ((1u << b) - 1u); }
+  static __device__ __forceinline__ uint32_t cas(uint32_t* a, uint32_t c, uint32_t v) { return atomicCAS(a, c, v); }
 };
 template <> struct KeyTraits<uint64_t> {
   static constexpr int NB = 65;
   static __device__ __forceinline__ int bucket(uint64_t x) { return 64 - __clzll((long long)x); }
   static __device__ __forceinline__ uint64_t maxv() { return ~0ull; }
+  static __device__ __forceinline__ uint64_t low_mask(int b) { return b >= 64 ? ~0ull : ((1ull << b) - 1ull); }
+  static __device__ __forceinline__ uint64_t cas(uint64_t* a, uint64_t c, uint64_t v) {
+    return (uint64_t)atomicCAS((unsigned long long*)a, (unsigned long long)c, (unsigned long long)v);
+  }
 };
+
+constexpr int kFCap = 4096;        // slots of the shared-memory front set
+constexpr int kFLoad = 1024;       // largest bucket loaded into F in one go / live keys kept after a spill
+constexpr int kFUsedMax = 1536;    // used slots (live + tombstones) allowed before a 2048-key batch
+constexpr int kFreeCache = 48;
 
 struct ReduceParams {
   const int* rank; const uint32_t* ends; const float* sdist; const int* T; const int* apex;
@@ -327,13 +364,16 @@ struct ReduceParams {
 
 template <typename K>
 struct ReduceSmem {
-  K last, horizon, red[kReduceThreads / 32];
-  K bc_key;
+  K F[kFCap];
+  K base, fmax, red[kReduceThreads / 32], red2[kReduceThreads / 32];
   uint32_t head[KeyTraits<K>::NB], tail[KeyTraits<K>::NB], fill[KeyTraits<K>::NB], count[KeyTraits<K>::NB];
   uint32_t bcnt[KeyTraits<K>::NB], oldtail[KeyTraits<K>::NB], oldfill[KeyTraits<K>::NB];
   uint32_t newchunk[KeyTraits<K>::NB][kMaxNew];
-  uint32_t cnt0, freehead, vcount, vcount2, vsel;
-  int bc_int, bc_int2, abort_flag, problem;
+  uint32_t fcache[kFreeCache];
+  uint32_t nzmask[3];
+  uint32_t fcache_n, freehead, vcount, vcount2, vsel, f_used;
+  int f_live;
+  int bc_int, abort_flag, problem;
   unsigned long long pushes, pops;
 };
 
@@ -341,13 +381,16 @@ template <typename K>
 struct Reducer {
   using TR = KeyTraits<K>;
   static constexpr int NB = TR::NB;
+  static constexpr int kFItems = kFCap / kReduceThreads;
   const ReduceParams& P;
   ReduceSmem<K>& S;
   const int tid;
-  // per-problem views
   const int* R; const uint32_t* EN; const int* A; int T; int n;
   K* pool; uint32_t* vbits; uint32_t* vl[2];
   K* hkeys; int* hvals;
+
+  static __device__ __forceinline__ K empty_key() { return TR::maxv(); }
+  static __device__ __forceinline__ K tomb_key() { return TR::maxv() - 1; }
 
   __device__ Reducer(const ReduceParams& p, ReduceSmem<K>& s) : P(p), S(s), tid(threadIdx.x) {
     pool = (K*)P.pool_keys;
@@ -359,6 +402,7 @@ struct Reducer {
 
   // ---- chunk pool (thread 0 only)
   __device__ uint32_t alloc_chunk() {
+    if (S.fcache_n) return S.fcache[--S.fcache_n];
     uint32_t c = S.freehead;
     if (c != kNil) { S.freehead = P.pool_next[c]; return c; }
     c = atomicAdd(P.pool_top, 1u);
@@ -367,6 +411,7 @@ struct Reducer {
   }
   __device__ void free_chunk(uint32_t c) {
     if (c >= P.pool_chunks) return;
+    if (S.fcache_n < (uint32_t)kFreeCache) { S.fcache[S.fcache_n++] = c; return; }
     P.pool_next[c] = S.freehead;
     S.freehead = c;
   }
@@ -388,41 +433,118 @@ struct Reducer {
     __syncthreads();
   }
 
-  // ---- push a batch of keys held in registers (all threads call; keys strictly greater than S.last)
+  // ---- F: shared-memory front set with toggle semantics
+  __device__ void f_clear() {
+#pragma unroll
+    for (int it = 0; it < kFItems; ++it) S.F[tid + it * kReduceThreads] = empty_key();
+    if (tid == 0) { S.f_used = 0; S.f_live = 0; }
+    __syncthreads();
+  }
+  __device__ __forceinline__ void f_toggle(K key) {
+    uint32_t h = (uint32_t)(((uint64_t)key * 0x9E3779B97F4A7C15ull) >> 40) & (kFCap - 1);
+    for (;;) {
+      K cur = S.F[h];
+      if (cur == key) {
+        if (TR::cas(&S.F[h], key, tomb_key()) == key) { atomicSub(&S.f_live, 1); return; }
+        cur = S.F[h];  // someone else removed it first: keep probing
+      }
+      if (cur == empty_key()) {
+        K prev = TR::cas(&S.F[h], empty_key(), key);
+        if (prev == empty_key()) { atomicAdd(&S.f_used, 1u); atomicAdd(&S.f_live, 1); return; }
+        if (prev == key) continue;  // the same key landed here concurrently: retry this slot (will remove it)
+      }
+      h = (h + 1) & (kFCap - 1);
+    }
+  }
+  __device__ K block_min(K v) {
+    v = sizeof(K) == 4 ? (K)warp_min_u32((uint32_t)v) : (K)warp_min_u64((uint64_t)v);
+    if ((tid & 31) == 0) S.red[tid >> 5] = v;
+    __syncthreads();
+    K m = S.red[0];
+#pragma unroll
+    for (int w = 1; w < kReduceThreads / 32; ++w) m = S.red[w] < m ? S.red[w] : m;
+    __syncthreads();
+    return m;
+  }
+  // smallest live key of F, removed; false if F holds no live key
+  __device__ bool f_popmin(K& out) {
+    if (S.f_live <= 0) return false;
+    K m = tomb_key();
+    int at = -1;
+#pragma unroll
+    for (int it = 0; it < kFItems; ++it) {
+      int i = tid + it * kReduceThreads;
+      K k = S.F[i];
+      if (k < m) { m = k; at = i; }
+    }
+    const K g = block_min(m);
+    if (g >= tomb_key()) return false;
+    if (m == g && at >= 0) { S.F[at] = tomb_key(); S.f_live -= 1; }  // exactly one slot holds a live key
+    __syncthreads();
+    out = g;
+    return true;
+  }
+
+  // ---- push a batch of keys held in registers to the heap (all threads call).
+  // force_bucket: -1 => by radix relative to S.base (keys > fmax >= base)
   template <int ITEMS>
-  __device__ void push_batch(const K (&keys)[ITEMS], const bool (&valid)[ITEMS]) {
+  __device__ void push_batch(const K (&keys)[ITEMS], const bool (&valid)[ITEMS], int force_bucket) {
+    int any = 0;
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) any |= valid[it] ? 1 : 0;
+    if (tid < NB) S.bcnt[tid] = 0;
+    if (!__syncthreads_or(any)) return;
     int bk[ITEMS];
     uint32_t off[ITEMS];
-    if (tid < NB) S.bcnt[tid] = 0;
-    __syncthreads();
-    const K last = S.last;
+    const K base = S.base;
+    const unsigned lane_lt = (1u << (tid & 31)) - 1u;
 #pragma unroll
-    for (int it = 0; it < ITEMS; ++it)
-      if (valid[it]) {
-        bk[it] = TR::bucket(keys[it] ^ last);
-        off[it] = atomicAdd(&S.bcnt[bk[it]], 1u);
+    for (int it = 0; it < ITEMS; ++it) {
+      // warp-aggregated slot reservation: one shared-memory atomic per distinct bucket per warp
+      bk[it] = valid[it] ? (force_bucket >= 0 ? force_bucket : TR::bucket(keys[it] ^ base)) : -1;
+      unsigned act = __ballot_sync(0xffffffffu, valid[it]);
+      if (act) {
+        unsigned peers = __match_any_sync(0xffffffffu, bk[it]);
+        if (valid[it]) {
+          int leader = __ffs(peers) - 1;
+          uint32_t b0 = 0;
+          if ((tid & 31) == leader) b0 = atomicAdd(&S.bcnt[bk[it]], (uint32_t)__popc(peers));
+          b0 = __shfl_sync(peers, b0, leader);
+          off[it] = b0 + __popc(peers & lane_lt);
+        }
       }
+    }
+    __syncthreads();
+    if (tid < NB) {
+      if (S.bcnt[tid]) {
+        S.oldtail[tid] = S.tail[tid];
+        S.oldfill[tid] = S.fill[tid];
+        atomicOr(&S.nzmask[tid >> 5], 1u << (tid & 31));
+      }
+    }
     __syncthreads();
     if (tid == 0) {
       unsigned long long added = 0;
-      for (int b = 1; b < NB; ++b) {
-        uint32_t c = S.bcnt[b];
-        if (!c) continue;
-        added += c;
-        S.oldtail[b] = S.tail[b];
-        S.oldfill[b] = S.fill[b];
-        uint32_t total = S.fill[b] + c;
-        uint32_t nnew = total > (uint32_t)kChunk ? (total - kChunk + kChunk - 1) / kChunk : 0;
-        uint32_t prev = S.tail[b];
-        for (uint32_t j = 0; j < nnew; ++j) {
-          uint32_t ch = alloc_chunk();
-          S.newchunk[b][j] = ch;
-          if (ch < P.pool_chunks) P.pool_next[ch] = kNil;
-          if (prev != kNil && prev < P.pool_chunks) P.pool_next[prev] = ch; else if (prev == kNil) S.head[b] = ch;
-          prev = ch;
+      for (int wq = 0; wq < 3; ++wq) {
+        unsigned msk = S.nzmask[wq];
+        S.nzmask[wq] = 0;
+        while (msk) {
+          int b = wq * 32 + __ffs(msk) - 1;
+          msk &= msk - 1;
+          uint32_t c = S.bcnt[b];
+          added += c;
+          uint32_t total = S.fill[b] + c;
+          uint32_t nnew = total > (uint32_t)kChunk ? (total - kChunk + kChunk - 1) / kChunk : 0;
+          uint32_t prev = S.tail[b];
+          for (uint32_t j = 0; j < nnew; ++j) {
+            uint32_t ch = alloc_chunk();
+            S.newchunk[b][j] = ch;
+            if (prev != kNil && prev < P.pool_chunks) P.pool_next[prev] = ch; else if (prev == kNil) S.head[b] = ch;
+            prev = ch;
+          }
+          if (nnew) { S.tail[b] = prev; S.fill[b] = total - kChunk * nnew; } else S.fill[b] = total;
+          S.count[b] += c;
         }
-        if (nnew) { S.tail[b] = prev; S.fill[b] = total - kChunk * nnew; } else S.fill[b] = total;
-        S.count[b] += c;
       }
       S.pushes += added;
     }
@@ -440,82 +562,102 @@ struct Reducer {
     __syncthreads();
   }
 
-  __device__ K block_min(K v) {
-    v = sizeof(K) == 4 ? (K)warp_min_u32((uint32_t)v) : (K)warp_min_u64((uint64_t)v);
-    if ((tid & 31) == 0) S.red[tid >> 5] = v;
-    __syncthreads();
-    K m = S.red[0];
+  // ---- keep F within its load limits: compact tombstones, spill the upper half to the heap when too many live keys
+  __device__ void f_maintain(uint32_t max_used) {
+    if (S.f_used <= max_used) return;
+    K keep[kFItems];
+    bool live[kFItems];
+    for (;;) {
 #pragma unroll
-    for (int w = 1; w < kReduceThreads / 32; ++w) m = S.red[w] < m ? S.red[w] : m;
-    __syncthreads();
-    return m;
+      for (int it = 0; it < kFItems; ++it) {
+        keep[it] = S.F[tid + it * kReduceThreads];
+        live[it] = keep[it] < tomb_key();
+      }
+      const int nlive = S.f_live;
+      __syncthreads();
+      K mid = TR::maxv();
+      if (nlive > kFLoad) {  // spill keys above the midpoint of the live range
+        K mn = TR::maxv(), mx = 0;
+#pragma unroll
+        for (int it = 0; it < kFItems; ++it)
+          if (live[it]) { mn = keep[it] < mn ? keep[it] : mn; mx = keep[it] > mx ? keep[it] : mx; }
+        mn = block_min(mn);
+        mx = ~block_min((K)~mx);
+        mid = mn + (mx - mn) / 2;
+      }
+      f_clear();
+      bool spill[kFItems];
+#pragma unroll
+      for (int it = 0; it < kFItems; ++it) {
+        spill[it] = live[it] && keep[it] > mid;
+        if (live[it] && !spill[it]) f_toggle(keep[it]);
+      }
+      if (nlive > kFLoad) {
+        if (tid == 0) S.fmax = mid;
+        push_batch<kFItems>(keep, spill, -1);
+      }
+      __syncthreads();
+      if (S.f_live <= kFLoad) break;
+    }
   }
 
-  // ---- extract the smallest key with odd multiplicity; false if the heap holds none
-  __device__ bool extract(K& out) {
+  // ---- refill F from the radix heap; false when nothing is stored at all
+  __device__ bool refill() {
     for (;;) {
+      if (S.f_live > 0) return true;
       int b = 0;
       for (int q = 1; q < NB; ++q)
         if (S.count[q]) { b = q; break; }
       if (!b) return false;
+      f_clear();
       const uint32_t hb = S.head[b], tb = S.tail[b], fb = S.fill[b], cb = S.count[b];
-      // pass 1: minimum of the bucket
-      K m = TR::maxv();
-      for (uint32_t c = hb; c != kNil;) {
-        uint32_t cnt = (c == tb) ? fb : (uint32_t)kChunk;
-        for (uint32_t i = tid; i < cnt; i += kReduceThreads) {
-          K k = pool[(size_t)c * kChunk + i];
-          m = k < m ? k : m;
-        }
-        c = (c == tb) ? kNil : P.pool_next[c];
-      }
-      const K newlast = block_min(m);  // contains the barriers that order the reads above
-      if (tid == 0) {
-        S.last = newlast; S.cnt0 = 0;
+      if (tid == 0) {  // detach the list; F now covers the bucket's whole key range [L, U]
         S.head[b] = kNil; S.tail[b] = kNil; S.fill[b] = kChunk; S.count[b] = 0;
         S.pops += cb;
+        const K old = S.base;
+        S.fmax = old | TR::low_mask(b);
+        S.base = (old & ~TR::low_mask(b)) | ((K)1 << (b - 1));
       }
       __syncthreads();
-      if (cb == 1) {  // common case: a lone key
-        if (tid == 0) free_chunk(hb);
-        __syncthreads();
-        out = newlast;
-        return true;
-      }
-      // pass 2: redistribute relative to the new minimum
       for (uint32_t c = hb; c != kNil;) {
-        uint32_t cnt = (c == tb) ? fb : (uint32_t)kChunk;
-        uint32_t nxt = (c == tb) ? kNil : P.pool_next[c];
+        const uint32_t cnt = (c == tb) ? fb : (uint32_t)kChunk;
+        const uint32_t nxt = (c == tb) ? kNil : P.pool_next[c];
+        const K fmax = S.fmax;  // may have been lowered by a spill while streaming a long list
         K keys[kChunk / kReduceThreads];
         bool valid[kChunk / kReduceThreads];
-        uint32_t eq = 0;
 #pragma unroll
         for (int it = 0; it < kChunk / kReduceThreads; ++it) {
           uint32_t i = tid + it * kReduceThreads;
           valid[it] = false;
           if (i < cnt) {
             K k = pool[(size_t)c * kChunk + i];
-            if (k == newlast) ++eq; else { keys[it] = k; valid[it] = true; }
+            if (k <= fmax) f_toggle(k); else { keys[it] = k; valid[it] = true; }
           }
         }
-        if (eq) atomicAdd(&S.cnt0, eq);
         __syncthreads();
         if (tid == 0) free_chunk(c);
-        push_batch<kChunk / kReduceThreads>(keys, valid);
+        push_batch<kChunk / kReduceThreads>(keys, valid, -1);
+        f_maintain(kFCap - 2 * kChunk);
         c = nxt;
       }
       __syncthreads();
-      if (S.cnt0 & 1u) { out = newlast; return true; }
     }
   }
 
-  // ---- cofacets of edge `re` with key in (lo, hi] -> heap
+  // next pivot: smallest key with odd multiplicity; false when the stored part of the column is empty
+  __device__ bool extract(K& out) {
+    if (!refill()) return false;
+    return f_popmin(out);
+  }
+
+  // ---- cofacets of edge `re` with key in (lo, hi] -> F / heap
   __device__ void gen_push(int re, K lo, K hi) {
     const uint32_t e = EN[re];
     const int a = (int)(e >> 16), b = (int)(e & 0xffffu);
     const int* rowa = R + (size_t)a * n;
     const int* rowb = R + (size_t)b * n;
     for (int v0 = 0; v0 < n; v0 += kReduceThreads * kGenItems) {
+      f_maintain(kFUsedMax);
       K keys[kGenItems];
       bool valid[kGenItems];
       int ra[kGenItems], rb[kGenItems];
@@ -525,6 +667,7 @@ struct Reducer {
         ra[it] = v < n ? rowa[v] : kRankDiag;
         rb[it] = v < n ? rowb[v] : kRankDiag;
       }
+      const K fmax = S.fmax;
 #pragma unroll
       for (int it = 0; it < kGenItems; ++it) {
         int v = v0 + it * kReduceThreads + tid;
@@ -533,10 +676,13 @@ struct Reducer {
         if (M < T) {
           int opp = (M == re) ? v : (M == ra[it] ? b : a);
           K key = (K)M * (K)n + (K)(n - 1 - opp);
-          if (key > lo && key <= hi) { keys[it] = key; valid[it] = true; }
+          if (key > lo && key <= hi) {
+            keys[it] = key;
+            if (key <= fmax) f_toggle(key); else valid[it] = true;
+          }
         }
       }
-      push_batch<kGenItems>(keys, valid);
+      push_batch<kGenItems>(keys, valid, -1);
     }
   }
 
@@ -568,10 +714,10 @@ struct Reducer {
         keep = (atomicAnd(&vbits[e >> 5], ~m) & m) != 0;
       }
       unsigned bal = __ballot_sync(0xffffffffu, keep);
-      uint32_t base = 0;
-      if ((tid & 31) == 0 && bal) base = atomicAdd(&S.vcount2, (uint32_t)__popc(bal));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (keep) dst[base + __popc(bal & ((1u << (tid & 31)) - 1))] = e;
+      uint32_t bs = 0;
+      if ((tid & 31) == 0 && bal) bs = atomicAdd(&S.vcount2, (uint32_t)__popc(bal));
+      bs = __shfl_sync(0xffffffffu, bs, 0);
+      if (keep) dst[bs + __popc(bal & ((1u << (tid & 31)) - 1))] = e;
     }
     __syncthreads();
     const uint32_t nout = S.vcount2;
@@ -653,10 +799,13 @@ struct Reducer {
     heap_reset();
     __syncthreads();
     const K kmax = (K)T * (K)n - 1;
-    const uint64_t span0 = (uint64_t)max(T / 256, 64) * (uint64_t)n;
+    const uint64_t span0 = (uint64_t)max(T / 64, 256) * (uint64_t)n;
     int nrows = 0;
     int64_t vpool_used = 0;
     unsigned long long additions = 0, extensions = 0, maxv = 0;
+    long long cyc[6] = {0, 0, 0, 0, 0, 0};
+    unsigned long long badd_edges = 0, ext_edges = 0;
+    long long t0;
     float* out = P.h1_pairs + (size_t)p * P.cap1 * 2;
     int64_t* outs = P.h1_simplex ? P.h1_simplex + (size_t)p * P.cap1 * 2 : nullptr;
 
@@ -665,7 +814,8 @@ struct Reducer {
       const K start = (K)(rbirth + 1) * (K)n - 1;
       K H = ((uint64_t)(kmax - start) > span0) ? (K)(start + (K)span0) : kmax;
       uint64_t span = span0;
-      if (tid == 0) { S.last = start; S.horizon = H; v_toggle_single(rbirth); }
+      f_clear();
+      if (tid == 0) { S.base = start; S.fmax = start; v_toggle_single(rbirth); }
       __syncthreads();
       gen_push(rbirth, start, H);
       bool essential = false;
@@ -673,10 +823,13 @@ struct Reducer {
       for (;;) {
         if (S.abort_flag) break;
         K pk;
+        t0 = clock64();
         bool ok = extract(pk);
+        cyc[0] += clock64() - t0;
         if (!ok) {
           if (H >= kmax) { essential = true; break; }
           // extend the horizon: re-enumerate V for keys in (H, H2]
+          t0 = clock64();
           span = span * 4;
           K H2 = ((uint64_t)(kmax - H) > span) ? (K)(H + (K)span) : kmax;
           v_compact();
@@ -685,9 +838,12 @@ struct Reducer {
           for (uint32_t i = 0; i < nv; ++i) gen_push((int)list[i], H, H2);
           H = H2;
           ++extensions;
+          ext_edges += nv;
+          cyc[4] += clock64() - t0;
           continue;
         }
         // owner of the pivot
+        t0 = clock64();
         const int M = (int)(pk / (K)n);
         const int w = n - 1 - (int)(pk % (K)n);
         if (tid == 0) {
@@ -698,12 +854,15 @@ struct Reducer {
         __syncthreads();
         const int owner = S.bc_int;
         __syncthreads();
+        cyc[1] += clock64() - t0;
         if (owner == -1) { pivot = pk; break; }
         ++additions;
+        t0 = clock64();
         if (owner == -2) {
           if (tid == 0) v_toggle_single(M);
           __syncthreads();
           gen_push(M, pk, H);
+          cyc[2] += clock64() - t0;
         } else {
           const int64_t vs = P.vstart[(size_t)p * P.cap1 + owner];
           const int vn = P.vlen[(size_t)p * P.cap1 + owner];
@@ -714,9 +873,12 @@ struct Reducer {
             if (tid == 0) v_toggle_single(re);
             gen_push(re, pk, H);
           }
+          badd_edges += vn;
+          cyc[3] += clock64() - t0;
         }
       }
       if (S.abort_flag) break;
+      t0 = clock64();
       // finalise the column
       v_compact();
       const uint32_t nv = S.vcount;
@@ -759,6 +921,7 @@ struct Reducer {
       }
       v_clear();
       heap_release();
+      cyc[5] += clock64() - t0;
     }
     __syncthreads();
     if (S.abort_flag) {  // leave the scratch clean for the next problem
@@ -775,16 +938,19 @@ struct Reducer {
       st[ST_POPS] = S.pops;
       st[ST_EXTENSIONS] = extensions;
       st[ST_MAXV] = maxv;
+      for (int q = 0; q < 6; ++q) st[ST_CYC_EXTRACT + q] = (unsigned long long)cyc[q];
+      st[ST_BADD_EDGES] = badd_edges;
+      st[ST_EXT_EDGES] = ext_edges;
     }
     __syncthreads();
   }
 };
 
 template <typename K>
-__global__ void __launch_bounds__(kReduceThreads) reduce_kernel(ReduceParams P) {
+__global__ void __launch_bounds__(kReduceThreads, 1) reduce_kernel(ReduceParams P) {
   __shared__ ReduceSmem<K> S;
   Reducer<K> red(P, S);
-  if (threadIdx.x == 0) S.freehead = kNil;
+  if (threadIdx.x == 0) { S.freehead = kNil; S.fcache_n = 0; S.nzmask[0] = S.nzmask[1] = S.nzmask[2] = 0; }
   __syncthreads();
   for (;;) {
     if (threadIdx.x == 0) S.problem = atomicAdd(P.work_counter, 1);
@@ -816,6 +982,7 @@ struct Layout {
   void* cub_tmp; size_t cub_bytes;
   int* rank; uint32_t* ends; float* sdist; uint32_t* thresh_bits; int* T;
   uint8_t* mst; int* mstlist; int* apex; int* blist; int* bcount;
+  uint32_t *comp, *parent, *cbest; int* done;
   uint32_t* vbits; int64_t vwords; uint32_t* vlist; int64_t vcap;
   void* hkeys; int* hvals; int hcap;
   uint32_t* vpool; int64_t vpool_cap; int64_t* vstart; int* vlen;
@@ -849,6 +1016,10 @@ static Layout make_layout(void* ws, int n, int batch, int maxdim, int cap1, size
   L.T = c.take<int>(batch);
   L.mst = c.take<uint8_t>(BE);
   L.mstlist = c.take<int>((int64_t)batch * n);
+  L.comp = c.take<uint32_t>((int64_t)batch * n);
+  L.parent = c.take<uint32_t>((int64_t)batch * n);
+  L.cbest = c.take<uint32_t>((int64_t)batch * n);
+  L.done = c.take<int>(batch);
   L.stats = c.take<unsigned long long>((int64_t)batch * ST_N);
   L.work_counter = c.take<int>(1);
   if (maxdim >= 1) {
@@ -965,11 +1136,19 @@ extern "C" int tda_rips(const float* dm, int n, int batch, int maxdim, float thr
   }
   TDA_CUDA_CHECK(cudaMemsetAsync(L.mst, 0, (size_t)(BE > 0 ? BE : 1), stream));
   {
-    size_t smem = sizeof(uint32_t) * 3 * (size_t)n;
-    if (smem > 200 * 1024) return set_error(TDA_ERR_UNSUPPORTED, "tda_rips: n=%d too large for the single-CTA Boruvka (smem)", n);
-    TDA_CUDA_CHECK(cudaFuncSetAttribute(boruvka_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int threads = n >= 512 ? 1024 : (n >= 128 ? 512 : 128);
-    boruvka_kernel<<<batch, threads, smem, stream>>>(L.rank, L.ends, L.sdist, L.T, n, E, L.mst, h0_pairs, h0_simplex, counts, L.mstlist);
+    dim3 gi((n + 255) / 256, batch);
+    boruvka_init_kernel<<<gi, 256, 0, stream>>>(n, L.comp, L.cbest, L.done);
+    count_launch();
+    int rounds = 1;
+    while ((1 << rounds) < n) ++rounds;
+    ++rounds;  // one extra round detects "no merge" and is a no-op otherwise
+    dim3 gs((n + 7) / 8, batch);
+    for (int r = 0; r < rounds && E > 0; ++r) {
+      boruvka_scan_kernel<<<gs, 256, 0, stream>>>(L.rank, L.T, n, L.comp, L.cbest, L.done);
+      boruvka_merge_kernel<<<batch, 1024, 0, stream>>>(L.ends, n, E, L.comp, L.parent, L.cbest, L.mst, L.done);
+      count_launch(2);
+    }
+    h0_emit_kernel<<<batch, 1024, 0, stream>>>(L.ends, L.sdist, L.T, n, E, L.mst, L.comp, h0_pairs, h0_simplex, counts, L.mstlist);
     count_launch();
     TDA_LAUNCH_CHECK();
   }

@@ -67,7 +67,7 @@ def rips_batch(dm, maxdim=1, thresh=float("inf"), cap1=None, pool_bytes=None, wa
             break
         stats = None
         if want_stats and maxdim >= 1:
-            stats = np.zeros((B, 8), dtype=np.int64)
+            stats = np.zeros((B, 16), dtype=np.int64)
             _lib.check(L.tda_rips_stats(_lib.ptr(ws), n, B, maxdim, cap1, pool_bytes, stats.ctypes.data))
     counts_h = counts.cpu().numpy()
     h0_h = h0.cpu().numpy()
@@ -85,7 +85,8 @@ def rips_batch(dm, maxdim=1, thresh=float("inf"), cap1=None, pool_bytes=None, wa
         if want_simplices:
             r["simplices"] = [h0s_h[p, :c0]] + ([h1s_h[p, :c1]] if maxdim >= 1 else [])
         if stats is not None:
-            r["stats"] = dict(zip(["columns", "apparent", "reduced", "additions", "pushes", "pops", "extensions", "max_v"], stats[p].tolist()))
+            r["stats"] = dict(zip(["columns", "apparent", "reduced", "additions", "pushes", "pops", "extensions", "max_v", "cyc_extract",
+                                   "cyc_owner", "cyc_gen", "cyc_badd", "cyc_ext", "cyc_final", "badd_edges", "ext_edges"], stats[p].tolist()))
         out.append(r)
     return out
 
