@@ -34,6 +34,68 @@ const char* tda_last_error(void);
 int64_t tda_launch_count(void);
 void tda_launch_count_reset(void);
 
+/* ---- pairwise distances on high-dimensional activations (tcgen05 / TMEM / TMA GEMM, 3xTF32) ------
+ * Replaces sklearn.metrics.pairwise_distances inside umap-learn's small-data path (metric='cosine';
+ * debug_tda_pipeline.py:96-104, analyze_tda_over_layers.py:69,72, analyze_adversarial_tda.py:85-93), inside
+ * ripser.py for raw high-dimensional clouds, torch.cdist of metrics.py:143 and the Gram matrix of
+ * metrics.py:368.
+ *   X [batch,n,d] float32; Y [batch,m,d] float32 or NULL (=> Y = X, m = n, exact-zero diagonal)
+ *   metric TDA_METRIC_*; disconnect: distances >= disconnect become +inf (umap-learn's
+ *   disconnection_distance, 2.0 for cosine); pass +inf to disable
+ *   D [batch,n,m] float32
+ */
+size_t tda_pdist_workspace_bytes(int n, int m, int d, int batch, int symmetric);
+int tda_pdist(const float* X, const float* Y, int n, int m, int d, int batch, int metric, float disconnect, float* D,
+              void* ws, size_t ws_bytes, void* stream);
+
+/* ---- UMAP stages ----------------------------------------------------------------------------------
+ * Replace the inside of umap.UMAP(n_neighbors, n_components=3, min_dist=0.1, random_state=42, metric='cosine')
+ * .fit_transform / .fit / .transform (debug_tda_pipeline.py:96-104; analyze_tda_over_layers.py:38-44,69,72;
+ * analyze_adversarial_tda.py:85-93).  Stage names are umap-learn's.
+ *
+ * tda_knn_smooth: fast_knn_indices + smooth_knn_dist, fused, one warp per row of D.
+ *   D [batch,n,m] float32 (m = n for fit; m = n_train for transform); k <= 256
+ *   knn_idx [batch,n,k] int32 ascending by (distance, index), self included, -1 where the distance is +inf
+ *   knn_dist [batch,n,k] float32; sigma, rho [batch,n] float32; ws: 8*batch bytes
+ */
+int tda_knn_smooth(const float* D, int n, int m, int batch, int k, float local_connectivity, float bandwidth, int n_iter,
+                   int32_t* knn_idx, float* knn_dist, float* sigma, float* rho, void* ws, size_t ws_bytes, void* stream);
+/* tda_fuzzy_graph: compute_membership_strengths + fuzzy union mix*(P+P^T-P.P^T)+(1-mix)*P.P^T + make_epochs_per_sample.
+ *   Output is a slot table of 2*n*k directed entries per cloud: head, tail [batch,2nk] int32, weight [batch,2nk]
+ *   float32 (0 = empty slot), eps [batch,2nk] float32 = max_w/w, or -1 for empty slots and for entries pruned by
+ *   w < max_w/n_epochs; max_weight [batch] float32.
+ */
+int tda_fuzzy_graph(const int32_t* knn_idx, const float* knn_dist, const float* sigma, const float* rho, int n, int k, int batch,
+                    float mix_ratio, int n_epochs, int32_t* head, int32_t* tail, float* weight, float* eps, float* max_weight,
+                    void* stream);
+/* tda_umap_sgd: optimize_layout_euclidean.  Y [batch,n_head,dim] in/out; Y_other [batch,n_tail,dim] (NULL and
+ *   move_other=1 for fit: tail == head embedding); slot table as produced above; dim 1..4. */
+int tda_umap_sgd(float* Y, const float* Y_other, const int32_t* head, const int32_t* tail, const float* eps, int slots, int n_head,
+                 int n_tail, int dim, int batch, int n_epochs, float a, float b, float gamma, float alpha0,
+                 float negative_sample_rate, int move_other, uint64_t seed, void* stream);
+int tda_umap_init_random(float* Y, int n, int dim, int batch, float lo, float hi, uint64_t seed, void* stream);
+/* noisy_scale_coords (max|Y| -> 10, + N(0,noise)) followed by the per-axis rescale to [0,10] */
+int tda_umap_rescale(float* Y, int n, int dim, int batch, float noise, uint64_t seed, void* stream);
+/* transform(): bipartite membership strengths, init_transform (weighted mean of the train embedding) and schedule */
+int tda_umap_transform_init(const int32_t* knn_idx, const float* knn_dist, const float* sigma, const float* rho,
+                            const float* train_embedding, int n_query, int n_train, int k, int dim, int batch, int n_epochs,
+                            float* Y, int32_t* head, int32_t* tail, float* weight, float* eps, float* max_weight, void* stream);
+
+/* spectral initialisation (umap-learn spectral_layout / multi_component_layout):
+ *  tda_graph_components: connected components of the pruned graph (entries with eps > 0); comp [batch,n] ids numbered
+ *   by smallest member vertex (scipy order), ncomp [batch], comp_size [batch,n] (first ncomp entries), degree [batch,n];
+ *   ws: 4*batch*n bytes.
+ *  tda_spectral_embed: for every component with >= min_size vertices, the `dim` non-trivial bottom eigenvectors of the
+ *   symmetric normalised Laplacian (Lanczos, full reorthogonalisation), written as unit vectors into the component's
+ *   rows of Y [batch,n,dim]; evals [batch,maxcomp,4] (eigenvalues of D^-1/2 W D^-1/2) or NULL.
+ */
+size_t tda_spectral_workspace_bytes(int n, int batch, int maxcomp);
+int tda_graph_components(const int32_t* head, const int32_t* tail, const float* weight, const float* eps, int slots, int n, int batch,
+                         int32_t* comp, int32_t* ncomp, int32_t* comp_size, float* degree, void* ws, size_t ws_bytes, void* stream);
+int tda_spectral_embed(const int32_t* head, const int32_t* tail, const float* weight, const float* eps, int slots, int n, int dim,
+                       int batch, const int32_t* comp, const int32_t* ncomp, const int32_t* comp_size, const float* degree,
+                       int maxcomp, int min_size, uint64_t seed, float* Y, float* evals, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- Rips persistence -------------------------------------------------------------------------
  * Replaces ripser(X, maxdim=1)['dgms'] (debug_tda_pipeline.py:109-110; analyze_tda_over_layers.py:76;
  * analyze_adversarial_tda.py:100-101).

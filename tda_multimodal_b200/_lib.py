@@ -14,6 +14,23 @@ PROTOTYPES = {
     "tda_launch_count": (c_int64, []),
     "tda_launch_count_reset": (None, []),
     "tda_pdist_lowdim": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tda_pdist_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "tda_pdist": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tda_knn_smooth": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_size_t, c_void_p]),
+    "tda_fuzzy_graph": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tda_umap_sgd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                             c_float, c_float, c_float, c_float, c_int, ctypes.c_uint64, c_void_p]),
+    "tda_umap_init_random": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, ctypes.c_uint64, c_void_p]),
+    "tda_umap_rescale": (c_int, [c_void_p, c_int, c_int, c_int, c_float, ctypes.c_uint64, c_void_p]),
+    "tda_umap_transform_init": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tda_spectral_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "tda_graph_components": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tda_spectral_embed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_int, c_int, ctypes.c_uint64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tda_rips_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_size_t]),
     "tda_rips": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                          c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]),

@@ -1,0 +1,372 @@
+// spectral.cu -- UMAP's spectral initialisation on the device.
+//
+// Replaces umap-learn's spectral_layout / multi_component_layout (scipy connected_components + ARPACK eigsh of
+// the symmetric normalised Laplacian L = I - D^-1/2 W D^-1/2, k = dim+1 smallest eigenpairs, first dropped)
+// as reached from umap.UMAP(init='spectral') (debug_tda_pipeline.py:96-104 and the other call sites).
+//
+//   components_kernel : connected components of the pruned fuzzy graph (min-label propagation + pointer
+//                       jumping), component ids numbered by smallest member vertex like scipy does, degrees.
+//   lanczos_kernel    : one CTA per (cloud, component): Lanczos with full (CGS2) reorthogonalisation on
+//                       A = D^-1/2 W D^-1/2 restricted to the component, the trivial eigenvector D^1/2 1
+//                       deflated; the small tridiagonal problem is solved by Sturm-sequence multisection +
+//                       inverse iteration (fp64); Ritz vectors of the `dim` largest eigenvalues of A
+//                       (= smallest non-trivial of L) are written as unit vectors, like ARPACK returns them.
+// Signs / rotations inside degenerate eigenspaces are arbitrary in ARPACK too; parity is judged on the
+// embedding's trustworthiness and the downstream diagrams (BASELINE.json north_star).
+#include "common.cuh"
+#include "launch_count.cuh"
+#include "../../include/tda_b200.h"
+#include <cmath>
+
+namespace tda {
+namespace spectral {
+
+constexpr int kMaxKrylov = 96;
+constexpr int kLanczosThreads = 512;
+constexpr int kMaxDim = 4;
+
+// one CTA per cloud
+__global__ void __launch_bounds__(1024) components_kernel(const int* __restrict__ head_g, const int* __restrict__ tail_g,
+                                                          const float* __restrict__ weight_g, const float* __restrict__ eps_g, int slots, int n,
+                                                          int* __restrict__ label_g, int* __restrict__ comp_g, float* __restrict__ deg_g,
+                                                          int* __restrict__ ncomp_g, int* __restrict__ csize_g) {
+  __shared__ int s_scan[1024];
+  __shared__ int s_carry;
+  const int p = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int* head = head_g + (size_t)p * slots;
+  const int* tail = tail_g + (size_t)p * slots;
+  const float* weight = weight_g + (size_t)p * slots;
+  const float* eps = eps_g + (size_t)p * slots;
+  int* label = label_g + (size_t)p * n;
+  int* comp = comp_g + (size_t)p * n;
+  float* deg = deg_g + (size_t)p * n;
+  int* csize = csize_g + (size_t)p * n;
+  for (int i = tid; i < n; i += nt) { label[i] = i; deg[i] = 0.f; csize[i] = 0; }
+  __syncthreads();
+  for (int e = tid; e < slots; e += nt)
+    if (eps[e] > 0.f) atomicAdd(&deg[head[e]], weight[e]);
+  for (int round = 0; round < 4 * 1024; ++round) {
+    int changed = 0;
+    for (int e = tid; e < slots; e += nt)
+      if (eps[e] > 0.f) {
+        const int u = head[e], v = tail[e];
+        const int lu = label[u], lv = label[v];
+        if (lu < lv) { atomicMin(&label[v], lu); changed = 1; }
+        else if (lv < lu) { atomicMin(&label[u], lv); changed = 1; }
+      }
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) {  // pointer jumping
+      int l = label[i];
+      while (label[l] != l) l = label[l];
+      label[i] = l;
+    }
+    if (!__syncthreads_or(changed)) break;
+  }
+  // component ids in order of the smallest member (roots are exactly the vertices with label[i] == i)
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += nt) {
+    const int i = base + tid;
+    const int isroot = (i < n && label[i] == i) ? 1 : 0;
+    s_scan[tid] = isroot;
+    __syncthreads();
+    for (int off = 1; off < nt; off <<= 1) {
+      int v = tid >= off ? s_scan[tid - off] : 0;
+      __syncthreads();
+      s_scan[tid] += v;
+      __syncthreads();
+    }
+    if (isroot) comp[i] = s_carry + s_scan[tid] - 1;
+    __syncthreads();
+    if (tid == nt - 1) s_carry += s_scan[tid];
+    __syncthreads();
+  }
+  for (int i = tid; i < n; i += nt) {
+    const int c = comp[label[i]];
+    if (label[i] != i) comp[i] = c;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += nt) atomicAdd(&csize[comp[i]], 1);
+  if (tid == 0) ncomp_g[p] = s_carry;
+}
+
+__device__ __forceinline__ uint32_t hash32(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+  return (uint32_t)x;
+}
+
+struct LanczosParams {
+  const int* head; const int* tail; const float* weight; const float* eps; int slots; int n; int dim;
+  const int* comp; const float* deg; const int* ncomp; const int* csize;
+  float* Q;        // [batch, maxcomp, kMaxKrylov + 2, n]
+  float* out;      // [batch, n, dim] eigenvectors (rows of other components untouched)
+  float* evals;    // [batch, maxcomp, kMaxDim]
+  int maxcomp; int min_size; uint64_t seed;
+};
+
+__global__ void __launch_bounds__(kLanczosThreads) lanczos_kernel(LanczosParams P) {
+  __shared__ double s_alpha[kMaxKrylov], s_beta[kMaxKrylov];
+  __shared__ float s_coef[kMaxKrylov + 2];
+  __shared__ float s_red[kLanczosThreads / 32];
+  __shared__ double s_lam[kMaxDim];
+  __shared__ double s_vec[kMaxDim][kMaxKrylov];
+  __shared__ int s_m;
+  const int p = blockIdx.y, c = blockIdx.x;
+  if (c >= P.ncomp[p]) return;
+  const int n = P.n, dim = P.dim;
+  const int nc = P.csize[(size_t)p * n + c];
+  if (nc < P.min_size) return;  // tiny components are placed at random by the host
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kLanczosThreads / 32;
+  const int* head = P.head + (size_t)p * P.slots;
+  const int* tail = P.tail + (size_t)p * P.slots;
+  const float* weight = P.weight + (size_t)p * P.slots;
+  const float* eps = P.eps + (size_t)p * P.slots;
+  const int* comp = P.comp + (size_t)p * n;
+  const float* deg = P.deg + (size_t)p * n;
+  float* Q = P.Q + ((size_t)p * P.maxcomp + c) * (size_t)(kMaxKrylov + 2) * n;
+  float* u1 = Q;            // trivial eigenvector, normalised
+  float* q0 = Q + n;        // Lanczos vectors q_0 ..
+  const int m = min(kMaxKrylov, nc - 1);
+
+  auto block_sum = [&](float v) -> float {
+    v = warp_sum_f32(v);
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int w = 0; w < nwarps; ++w) t += s_red[w];
+    __syncthreads();
+    return t;
+  };
+  // u1 = D^1/2 1 restricted to the component, q_0 = random, orthogonal to u1
+  float acc = 0.f;
+  for (int i = tid; i < n; i += kLanczosThreads) {
+    const float v = comp[i] == c ? sqrtf(deg[i]) : 0.f;
+    u1[i] = v;
+    acc += v * v;
+  }
+  float nrm = sqrtf(block_sum(acc));
+  acc = 0.f;
+  float acc2 = 0.f;
+  for (int i = tid; i < n; i += kLanczosThreads) {
+    const float u = u1[i] / nrm;
+    u1[i] = u;
+    const float r = comp[i] == c ? ((float)(hash32(P.seed + ((uint64_t)p << 40) + (uint64_t)i) >> 8) * (1.f / 8388608.f) - 1.f) : 0.f;
+    q0[i] = r;
+    acc += r * u;
+  }
+  const float d0 = block_sum(acc);
+  for (int i = tid; i < n; i += kLanczosThreads) { const float r = q0[i] - d0 * u1[i]; q0[i] = r; acc2 += r * r; }
+  nrm = sqrtf(block_sum(acc2));
+  for (int i = tid; i < n; i += kLanczosThreads) q0[i] /= nrm;
+  __syncthreads();
+
+  int meff = m;
+  for (int j = 0; j < m; ++j) {
+    const float* qj = q0 + (size_t)j * n;
+    float* w = q0 + (size_t)(j + 1) * n;  // becomes q_{j+1}
+    for (int i = tid; i < n; i += kLanczosThreads) w[i] = 0.f;
+    __syncthreads();
+    for (int e = tid; e < P.slots; e += kLanczosThreads)
+      if (eps[e] > 0.f) {
+        const int h = head[e], t = tail[e];
+        if (comp[h] == c) atomicAdd(&w[h], weight[e] * rsqrtf(deg[h] * deg[t]) * qj[t]);
+      }
+    __syncthreads();
+    // classical Gram-Schmidt, twice, against u1 and q_0..q_j; the first pass's coefficient on q_j is alpha_j
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int v = warp; v <= j + 1; v += nwarps) {  // v = 0: u1, v = 1..j+1: q_{v-1}
+        const float* qv = Q + (size_t)v * n;
+        float s = 0.f;
+        for (int i = lane; i < n; i += 32) s += w[i] * qv[i];
+        s = warp_sum_f32(s);
+        if (lane == 0) s_coef[v] = s;
+      }
+      __syncthreads();
+      if (pass == 0 && tid == 0) s_alpha[j] = (double)s_coef[j + 1];
+      else if (pass == 1 && tid == 0) s_alpha[j] += (double)s_coef[j + 1];
+      for (int i = tid; i < n; i += kLanczosThreads) {
+        float v = w[i];
+        for (int t = 0; t <= j + 1; ++t) v -= s_coef[t] * Q[(size_t)t * n + i];
+        w[i] = v;
+      }
+      __syncthreads();
+    }
+    float a2 = 0.f;
+    for (int i = tid; i < n; i += kLanczosThreads) a2 += w[i] * w[i];
+    const float beta = sqrtf(block_sum(a2));
+    if (tid == 0) s_beta[j] = (double)beta;
+    if (beta < 1e-6f || j == m - 1) { meff = j + 1; break; }
+    for (int i = tid; i < n; i += kLanczosThreads) w[i] /= beta;
+    __syncthreads();
+  }
+  __syncthreads();
+  // ---- eigenpairs of the meff x meff tridiagonal T (alpha diagonal, beta off-diagonal), `dim` largest
+  const int nev = min(dim, meff);
+  if (warp < nev) {
+    // Gershgorin bounds
+    double lo = 1e300, hi = -1e300;
+    for (int i = 0; i < meff; ++i) {
+      const double r = (i > 0 ? fabs(s_beta[i - 1]) : 0.0) + (i < meff - 1 ? fabs(s_beta[i]) : 0.0);
+      lo = fmin(lo, s_alpha[i] - r); hi = fmax(hi, s_alpha[i] + r);
+    }
+    const int want = meff - 1 - warp;  // index (ascending) of the eigenvalue this warp looks for
+    for (int round = 0; round < 14; ++round) {
+      const double x = lo + (hi - lo) * (double)(lane + 1) / 33.0;
+      int cnt = 0;  // number of eigenvalues < x (Sturm sequence)
+      double d = 1.0;
+      for (int i = 0; i < meff; ++i) {
+        const double b2 = i > 0 ? s_beta[i - 1] * s_beta[i - 1] : 0.0;
+        d = s_alpha[i] - x - (i > 0 ? b2 / d : 0.0);
+        if (fabs(d) < 1e-300) d = -1e-300;
+        if (d < 0.0) ++cnt;
+      }
+      // eigenvalue `want` lies in (x_l, x_{l+1}] where l = last lane with cnt <= want
+      const unsigned below = __ballot_sync(0xffffffffu, cnt <= want);
+      const int nb = __popc(below);  // lanes 0..nb-1 have cnt <= want (monotone)
+      const double step = (hi - lo) / 33.0;
+      const double nlo = lo + step * nb, nhi = lo + step * (nb + 1);
+      lo = nlo; hi = nhi;
+    }
+    if (lane == 0) s_lam[warp] = 0.5 * (lo + hi);
+  }
+  __syncthreads();
+  if (tid < nev) {
+    // inverse iteration on (T - lam I) with a tiny shift; tridiagonal LU with partial pivoting, 3 sweeps
+    const double lam = s_lam[tid] + 1e-9 * (1.0 + fabs(s_lam[tid])) * (tid + 1);
+    double* y = s_vec[tid];
+    for (int i = 0; i < meff; ++i) y[i] = 1.0 + 0.01 * ((i * 37 + tid * 11) % 17);
+    double dl[kMaxKrylov], dd[kMaxKrylov], du[kMaxKrylov], du2[kMaxKrylov];
+    unsigned char piv[kMaxKrylov];
+    for (int sweep = 0; sweep < 3; ++sweep) {
+      for (int i = 0; i < meff; ++i) {
+        dd[i] = s_alpha[i] - lam;
+        du[i] = i < meff - 1 ? s_beta[i] : 0.0;
+        dl[i] = i < meff - 1 ? s_beta[i] : 0.0;
+        du2[i] = 0.0;
+      }
+      for (int i = 0; i < meff - 1; ++i) {
+        if (fabs(dd[i]) >= fabs(dl[i])) {
+          piv[i] = 0;
+          if (dd[i] == 0.0) dd[i] = 1e-300;
+          const double f = dl[i] / dd[i];
+          dl[i] = f;
+          dd[i + 1] -= f * du[i];
+        } else {
+          piv[i] = 1;
+          const double f = dd[i] / dl[i];
+          dd[i] = dl[i];
+          dl[i] = f;
+          const double t = du[i];
+          du[i] = dd[i + 1];
+          dd[i + 1] = t - f * du[i];
+          du2[i] = du[i + 1];
+          du[i + 1] = -f * du2[i];
+        }
+      }
+      if (dd[meff - 1] == 0.0) dd[meff - 1] = 1e-300;
+      for (int i = 0; i < meff - 1; ++i) {
+        if (piv[i]) { const double t = y[i]; y[i] = y[i + 1]; y[i + 1] = t - dl[i] * y[i]; }
+        else y[i + 1] -= dl[i] * y[i];
+      }
+      y[meff - 1] /= dd[meff - 1];
+      if (meff > 1) y[meff - 2] = (y[meff - 2] - du[meff - 2] * y[meff - 1]) / dd[meff - 2];
+      for (int i = meff - 3; i >= 0; --i) y[i] = (y[i] - du[i] * y[i + 1] - du2[i] * y[i + 2]) / dd[i];
+      double nn = 0.0;
+      for (int i = 0; i < meff; ++i) nn += y[i] * y[i];
+      nn = 1.0 / sqrt(nn);
+      for (int i = 0; i < meff; ++i) y[i] *= nn;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {  // Gram-Schmidt between the few Ritz coefficient vectors (clustered eigenvalues)
+    for (int a = 0; a < nev; ++a) {
+      for (int b = 0; b < a; ++b) {
+        double dot = 0.0;
+        for (int i = 0; i < meff; ++i) dot += s_vec[a][i] * s_vec[b][i];
+        for (int i = 0; i < meff; ++i) s_vec[a][i] -= dot * s_vec[b][i];
+      }
+      double nn = 0.0;
+      for (int i = 0; i < meff; ++i) nn += s_vec[a][i] * s_vec[a][i];
+      nn = nn > 0.0 ? 1.0 / sqrt(nn) : 0.0;
+      for (int i = 0; i < meff; ++i) s_vec[a][i] *= nn;
+    }
+    for (int a = 0; a < kMaxDim; ++a) P.evals[((size_t)p * P.maxcomp + c) * kMaxDim + a] = a < nev ? (float)s_lam[a] : 0.f;
+    s_m = meff;
+  }
+  __syncthreads();
+  // Ritz vectors
+  float* out = P.out + (size_t)p * n * dim;
+  for (int i = tid; i < n; i += kLanczosThreads) {
+    if (comp[i] != c) continue;
+    for (int a = 0; a < dim; ++a) {
+      float v = 0.f;
+      if (a < nev)
+        for (int t = 0; t < meff; ++t) v += (float)s_vec[a][t] * q0[(size_t)t * n + i];
+      else  // fewer Ritz pairs than dimensions (tiny component): fill with small hash noise
+        v = ((float)(hash32(P.seed * 31 + (uint64_t)i * 7 + a) >> 8) * (1.f / 8388608.f) - 1.f) * 1e-3f;
+      out[(size_t)i * dim + a] = v;
+    }
+  }
+}
+
+struct Layout {
+  int *label, *comp, *ncomp, *csize;
+  float *deg, *Q, *evals;
+  size_t total;
+};
+static Layout make_layout(void* ws, int n, int batch, int maxcomp) {
+  Layout L;
+  Carver c(ws, ~size_t(0));
+  L.label = c.take<int>((size_t)batch * n);
+  L.comp = c.take<int>((size_t)batch * n);
+  L.csize = c.take<int>((size_t)batch * n);
+  L.ncomp = c.take<int>(batch);
+  L.deg = c.take<float>((size_t)batch * n);
+  L.evals = c.take<float>((size_t)batch * (maxcomp > 0 ? maxcomp : 1) * kMaxDim);
+  L.Q = c.take<float>((size_t)batch * (maxcomp > 0 ? maxcomp : 0) * (kMaxKrylov + 2) * n);
+  L.total = c.off;
+  return L;
+}
+
+}  // namespace spectral
+}  // namespace tda
+
+using namespace tda;
+using namespace tda::spectral;
+
+extern "C" size_t tda_spectral_workspace_bytes(int n, int batch, int maxcomp) {
+  if (n <= 0 || batch <= 0 || maxcomp < 0) return 0;
+  return make_layout(nullptr, n, batch, maxcomp).total + 1024;
+}
+
+extern "C" int tda_graph_components(const int32_t* head, const int32_t* tail, const float* weight, const float* eps, int slots, int n, int batch,
+                                    int32_t* comp, int32_t* ncomp, int32_t* comp_size, float* degree, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!head || !tail || !weight || !eps || !comp || !ncomp || !comp_size || !degree || !ws || n <= 0 || batch <= 0)
+    return set_error(TDA_ERR_INVALID, "tda_graph_components: bad arguments");
+  if (ws_bytes < sizeof(int) * (size_t)batch * n) return set_error(TDA_ERR_WORKSPACE, "tda_graph_components: workspace too small");
+  components_kernel<<<batch, 1024, 0, stream>>>(head, tail, weight, eps, slots, n, (int*)ws, comp, degree, ncomp, comp_size);
+  count_launch();
+  TDA_LAUNCH_CHECK();
+  return TDA_OK;
+}
+
+extern "C" int tda_spectral_embed(const int32_t* head, const int32_t* tail, const float* weight, const float* eps, int slots, int n, int dim,
+                                  int batch, const int32_t* comp, const int32_t* ncomp, const int32_t* comp_size, const float* degree,
+                                  int maxcomp, int min_size, uint64_t seed, float* Y, float* evals, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!head || !tail || !weight || !eps || !comp || !ncomp || !comp_size || !degree || !Y || !ws || n <= 0 || batch <= 0 || maxcomp <= 0)
+    return set_error(TDA_ERR_INVALID, "tda_spectral_embed: bad arguments");
+  if (dim < 1 || dim > kMaxDim) return set_error(TDA_ERR_UNSUPPORTED, "tda_spectral_embed: dim=%d (supported 1..%d)", dim, kMaxDim);
+  Layout L = make_layout(ws, n, batch, maxcomp);
+  if (L.total > ws_bytes) return set_error(TDA_ERR_WORKSPACE, "tda_spectral_embed: workspace %zu < required %zu", ws_bytes, L.total);
+  LanczosParams P;
+  P.head = head; P.tail = tail; P.weight = weight; P.eps = eps; P.slots = slots; P.n = n; P.dim = dim;
+  P.comp = comp; P.deg = degree; P.ncomp = ncomp; P.csize = comp_size;
+  P.Q = L.Q; P.out = Y; P.evals = evals ? evals : L.evals; P.maxcomp = maxcomp; P.min_size = min_size; P.seed = seed;
+  dim3 grid(maxcomp, batch);
+  lanczos_kernel<<<grid, kLanczosThreads, 0, stream>>>(P);
+  count_launch();
+  TDA_LAUNCH_CHECK();
+  return TDA_OK;
+}

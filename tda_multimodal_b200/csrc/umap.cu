@@ -1,0 +1,461 @@
+// umap.cu -- the UMAP stages between the distance matrix and the 3-D embedding, batched over clouds.
+//
+// Replaces, inside umap.UMAP(...).fit_transform / .fit / .transform (debug_tda_pipeline.py:96-104,
+// analyze_tda_over_layers.py:38-44,69,72, analyze_adversarial_tda.py:85-93), umap-learn's
+//   fast_knn_indices + smooth_knn_dist      -> knn_smooth_kernel   (one warp per row: top-k + sigma/rho bisection)
+//   compute_membership_strengths + fuzzy union (P + P^T - P o P^T) + make_epochs_per_sample -> fuzzy_kernel
+//   optimize_layout_euclidean               -> sgd_epoch_kernel    (edge-parallel, on-device negative sampling)
+//   noisy_scale_coords / min-max rescale, init_transform          -> small helpers
+// SURVEY.md Appendix A is the specification these kernels follow; oracle/umap_oracle.py restates it on the CPU.
+#include "common.cuh"
+#include "launch_count.cuh"
+#include "../../include/tda_b200.h"
+#include <cmath>
+
+namespace tda {
+namespace umap {
+
+constexpr double kSmoothKTolerance = 1e-5;
+constexpr float kMinKDistScale = 1e-3f;
+
+__device__ __forceinline__ bool pair_less(float d1, int i1, float d2, int i2) { return d1 < d2 || (d1 == d2 && i1 < i2); }
+
+// ------------------------------------------------------------------------------------------------
+// exact kNN (self included, as umap-learn's precomputed-metric path does) fused with smooth_knn_dist.
+// One warp per row.  The running top-k is a sorted list striped over the warp (rank r -> lane r%32, slot r/32).
+template <int KPL>
+__global__ void __launch_bounds__(256) knn_smooth_kernel(const float* __restrict__ D, int n, int m, int k, float local_connectivity,
+                                                         float bandwidth, int n_iter, int* __restrict__ knn_idx,
+                                                         float* __restrict__ knn_dist, float* __restrict__ sigma, float* __restrict__ rho,
+                                                         double* __restrict__ dist_sum) {
+  const int p = blockIdx.y;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* drow = D + ((size_t)p * n + row) * m;
+  float dv[KPL];
+  int iv[KPL];
+#pragma unroll
+  for (int s = 0; s < KPL; ++s) { dv[s] = INFINITY; iv[s] = 0x7fffffff; }
+  const int last_lane = (k - 1) & 31, last_slot = (k - 1) >> 5;
+  float thr_d = INFINITY;
+  int thr_i = 0x7fffffff;
+  for (int j0 = 0; j0 < m; j0 += 32) {
+    const int j = j0 + lane;
+    const float d = j < m ? drow[j] : INFINITY;
+    unsigned cand = __ballot_sync(0xffffffffu, j < m && pair_less(d, j, thr_d, thr_i));
+    while (cand) {
+      const int src = __ffs(cand) - 1;
+      cand &= cand - 1;
+      const float cd = __shfl_sync(0xffffffffu, d, src);
+      const int cj = j0 + src;
+      if (!pair_less(cd, cj, thr_d, thr_i)) continue;  // threshold moved since the ballot
+      // insertion position = number of list entries smaller than the candidate
+      int pos = 0;
+#pragma unroll
+      for (int s = 0; s < KPL; ++s) pos += __popc(__ballot_sync(0xffffffffu, pair_less(dv[s], iv[s], cd, cj)));
+#pragma unroll
+      for (int s = KPL - 1; s >= 0; --s) {
+        const int r = s * 32 + lane;
+        float upd = __shfl_up_sync(0xffffffffu, dv[s], 1);
+        int upi = __shfl_up_sync(0xffffffffu, iv[s], 1);
+        if (s > 0) {
+          const float wd = __shfl_sync(0xffffffffu, dv[s - 1], 31);
+          const int wi = __shfl_sync(0xffffffffu, iv[s - 1], 31);
+          if (lane == 0) { upd = wd; upi = wi; }
+        }
+        if (r == pos) { dv[s] = cd; iv[s] = cj; }
+        else if (r > pos) { dv[s] = upd; iv[s] = upi; }
+      }
+      thr_d = __shfl_sync(0xffffffffu, dv[last_slot], last_lane);
+      thr_i = __shfl_sync(0xffffffffu, iv[last_slot], last_lane);
+    }
+  }
+  // ---- write the neighbour lists (index -1 where the neighbour is at infinite distance: "disconnected")
+  int* oi = knn_idx + ((size_t)p * n + row) * k;
+  float* od = knn_dist + ((size_t)p * n + row) * k;
+  double rsum = 0.0;
+#pragma unroll
+  for (int s = 0; s < KPL; ++s) {
+    const int r = s * 32 + lane;
+    if (r < k) {
+      oi[r] = isinf(dv[s]) ? -1 : iv[s];
+      od[r] = dv[s];
+      rsum += (double)dv[s];
+    }
+  }
+  rsum = warp_sum_f64(rsum);
+  // ---- smooth_knn_dist for this row
+  // rho: distance to the local_connectivity-th nearest neighbour at positive distance (interpolated)
+  int zeros = 0;
+#pragma unroll
+  for (int s = 0; s < KPL; ++s) zeros += __popc(__ballot_sync(0xffffffffu, (s * 32 + lane) < k && !(dv[s] > 0.f)));
+  const int nnz = k - zeros;
+  auto fetch = [&](int r) -> float {  // list entry of rank r (warp uniform argument)
+    float v = 0.f;
+#pragma unroll
+    for (int s = 0; s < KPL; ++s) {
+      const float t = __shfl_sync(0xffffffffu, dv[s], r & 31);
+      if ((r >> 5) == s) v = t;
+    }
+    return v;
+  };
+  float rho_i = 0.f;
+  if ((float)nnz >= local_connectivity) {
+    const int index = (int)floorf(local_connectivity);
+    const float interp = local_connectivity - (float)index;
+    if (index > 0) {
+      rho_i = fetch(zeros + index - 1);
+      if (interp > (float)kSmoothKTolerance) rho_i += interp * (fetch(zeros + index) - fetch(zeros + index - 1));
+    } else {
+      rho_i = interp * fetch(zeros);
+    }
+  } else if (nnz > 0) {
+    rho_i = fetch(k - 1);  // max of the positive entries = last entry of the sorted list
+  }
+  const double target = log2((double)k) * (double)bandwidth;
+  double lo = 0.0, hi = INFINITY, mid = 1.0;
+  for (int it = 0; it < n_iter; ++it) {
+    double psum = 0.0;
+#pragma unroll
+    for (int s = 0; s < KPL; ++s) {
+      const int r = s * 32 + lane;
+      if (r >= 1 && r < k) {
+        const float dd = dv[s] - rho_i;  // float32 subtraction, as in the numba kernel
+        psum += dd > 0.f ? exp(-((double)dd / mid)) : 1.0;
+      }
+    }
+    psum = warp_sum_f64(psum);
+    if (fabs(psum - target) < kSmoothKTolerance) break;
+    if (psum > target) { hi = mid; mid = (lo + hi) / 2.0; }
+    else { lo = mid; if (isinf(hi)) mid *= 2.0; else mid = (lo + hi) / 2.0; }
+  }
+  if (lane == 0) {
+    float sg = (float)mid;
+    if (rho_i > 0.f) {
+      const float mean_i = (float)(rsum / k);
+      if (sg < kMinKDistScale * mean_i) sg = kMinKDistScale * mean_i;
+    }
+    sigma[(size_t)p * n + row] = sg;
+    rho[(size_t)p * n + row] = rho_i;
+    atomicAdd(&dist_sum[p], rsum);
+  }
+}
+
+// rows whose rho is 0 are floored with the mean over the whole [n,k] distance table
+__global__ void sigma_floor_kernel(int n, int k, const float* __restrict__ rho, float* __restrict__ sigma, const double* __restrict__ dist_sum) {
+  const int p = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (!(rho[(size_t)p * n + i] > 0.f)) {
+    const float mean_all = (float)(dist_sum[p] / ((double)n * k));
+    float& s = sigma[(size_t)p * n + i];
+    if (s < kMinKDistScale * mean_all) s = kMinKDistScale * mean_all;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// membership strengths + fuzzy union, written to a fixed slot table: slot (i,t,0) = directed entry i->j,
+// slot (i,t,1) = the transposed entry j->i when i is not in j's own list.  weight 0 = empty slot.
+__device__ __forceinline__ float membership(float d, float rho_i, float sigma_i, bool is_self, bool bipartite) {
+  if (!bipartite && is_self) return 0.f;
+  if (d - rho_i <= 0.f || sigma_i == 0.f) return 1.f;
+  return expf(-((d - rho_i) / sigma_i));
+}
+__global__ void fuzzy_kernel(const int* __restrict__ knn_idx, const float* __restrict__ knn_dist, const float* __restrict__ sigma,
+                             const float* __restrict__ rho, int n, int k, float mix, int* __restrict__ head, int* __restrict__ tail,
+                             float* __restrict__ weight, unsigned int* __restrict__ max_w_bits) {
+  const int p = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  float wmax = 0.f;
+  if (e < n * k) {
+    const int i = e / k;
+    const size_t base = (size_t)p * n;
+    const int* idx = knn_idx + base * k;
+    const float* dist = knn_dist + base * k;
+    const int j = idx[e];
+    const size_t s0 = ((size_t)p * n * k + e) * 2;
+    float w = 0.f;
+    bool found = false;
+    if (j >= 0 && j != i) {
+      const float vij = membership(dist[e], rho[base + i], sigma[base + i], false, false);
+      float vji = 0.f;
+      for (int t = 0; t < k; ++t)
+        if (idx[(size_t)j * k + t] == i) {
+          vji = membership(dist[(size_t)j * k + t], rho[base + j], sigma[base + j], false, false);
+          found = true;
+          break;
+        }
+      const float prod = vij * vji;
+      w = mix * (vij + vji - prod) + (1.f - mix) * prod;
+    }
+    head[s0] = i; tail[s0] = j < 0 ? i : j; weight[s0] = w;
+    head[s0 + 1] = j < 0 ? i : j; tail[s0 + 1] = i; weight[s0 + 1] = found ? 0.f : w;
+    wmax = w;
+  }
+  wmax = warp_max_f32(wmax);
+  if ((threadIdx.x & 31) == 0 && wmax > 0.f) atomicMax(&max_w_bits[p], __float_as_uint(wmax));
+}
+// epochs_per_sample = max_w / w; entries with w < max_w / n_epochs are pruned (eps = -1)
+__global__ void epochs_kernel(const float* __restrict__ weight, int slots, int n_epochs, const unsigned int* __restrict__ max_w_bits,
+                              float* __restrict__ eps) {
+  const int p = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= slots) return;
+  const float mw = __uint_as_float(max_w_bits[p]);
+  const float w = weight[(size_t)p * slots + e];
+  eps[(size_t)p * slots + e] = (w > 0.f && w >= mw / (float)n_epochs) ? mw / w : -1.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SGD: one launch per epoch, one thread per slot of every cloud.  Stateless schedule: an edge with period
+// eps fires at the epochs ceil(q*eps), q = 1,2,...; the negative-sample budget follows umap-learn's
+// epoch_of_next_negative_sample recurrence in closed form.  Updates use float atomics (every update is kept,
+// order is free -- the reference's serial loop is one admissible order).
+__device__ __forceinline__ uint32_t mix32(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+  return (uint32_t)x;
+}
+__device__ __forceinline__ float clip4(float v) { return fminf(fmaxf(v, -4.f), 4.f); }
+
+template <int DIM>
+__global__ void __launch_bounds__(256) sgd_epoch_kernel(float* __restrict__ Yh, const float* __restrict__ Yt_in, const int* __restrict__ head,
+                                                        const int* __restrict__ tail, const float* __restrict__ eps_arr, int slots, int n_head,
+                                                        int n_tail, int epoch, float a, float b, float gamma, float alpha, float nsr,
+                                                        int move_other, uint64_t seed) {
+  const int p = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= slots) return;
+  const float eps = eps_arr[(size_t)p * slots + e];
+  if (!(eps > 0.f)) return;
+  const int q = (int)floorf((float)epoch / eps);
+  if (q < 1 || q <= (int)floorf((float)(epoch - 1) / eps)) return;
+  const int j = head[(size_t)p * slots + e], kk = tail[(size_t)p * slots + e];
+  float* yh = Yh + ((size_t)p * n_head + j) * DIM;
+  float* Yt = move_other ? Yh : const_cast<float*>(Yt_in);
+  float* yt = Yt + ((size_t)p * n_tail + kk) * DIM;
+  float cur[DIM], oth[DIM], delta[DIM];
+  float d2 = 0.f;
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) { cur[d] = yh[d]; oth[d] = yt[d]; delta[d] = 0.f; const float t = cur[d] - oth[d]; d2 += t * t; }
+  float g = 0.f;
+  if (d2 > 0.f) {
+    const float pw = __powf(d2, b - 1.f);
+    g = (-2.f * a * b * pw) / (a * pw * d2 + 1.f);
+  }
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) {
+    const float gd = clip4(g * (cur[d] - oth[d])) * alpha;
+    cur[d] += gd; delta[d] += gd;
+    if (move_other) atomicAdd(&yt[d], -gd);
+  }
+  // negatives owed since the previous firing
+  const float epsn = eps / nsr;
+  int tot = (int)floorf((float)epoch / epsn) - 1;
+  if (q > 1) {
+    const int prev = (int)ceilf((float)(q - 1) * eps);
+    tot -= (int)floorf((float)prev / epsn) - 1;
+  }
+  for (int s = 0; s < tot; ++s) {
+    const uint32_t r = mix32(seed ^ ((uint64_t)p << 52) ^ ((uint64_t)e << 20) ^ ((uint64_t)epoch << 4) ^ (uint64_t)s ^ ((uint64_t)s << 40));
+    const int kn = (int)(r % (uint32_t)n_tail);
+    const float* yn = Yt + ((size_t)p * n_tail + kn) * DIM;
+    float dn = 0.f;
+    float on[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) { on[d] = yn[d]; const float t = cur[d] - on[d]; dn += t * t; }
+    float gn = 0.f;
+    if (dn > 0.f) gn = (2.f * gamma * b) / ((0.001f + dn) * (a * __powf(dn, b) + 1.f));
+    else if (move_other && j == kn) continue;
+    if (gn > 0.f) {
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) {
+        const float gd = clip4(gn * (cur[d] - on[d])) * alpha;
+        cur[d] += gd; delta[d] += gd;
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) atomicAdd(&yh[d], delta[d]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// initialisation helpers
+__device__ __forceinline__ float u01(uint64_t key) { return ((float)(mix32(key) >> 8) + 0.5f) * (1.f / 16777216.f); }
+
+__global__ void init_random_kernel(float* __restrict__ Y, int total, float lo, float hi, uint64_t seed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) Y[i] = lo + (hi - lo) * u01(seed * 0x9E3779B97F4A7C15ull + (uint64_t)i);
+}
+
+// Y <- 10 * minmax( Y * (10 / max|Y|) + N(0, noise) ) per cloud and axis  (umap-learn's noisy_scale_coords
+// followed by the [0,10] rescale of simplicial_set_embedding).  One CTA per cloud.
+__global__ void __launch_bounds__(1024) rescale_kernel(float* __restrict__ Yg, int n, int dim, float noise, uint64_t seed) {
+  __shared__ float s_red[32];
+  __shared__ float s_val[2 * 8 + 1];
+  const int p = blockIdx.x;
+  float* Y = Yg + (size_t)p * n * dim;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  auto block_max = [&](float v) -> float {
+    v = warp_max_f32(v);
+    if ((tid & 31) == 0) s_red[tid >> 5] = v;
+    __syncthreads();
+    float m = -INFINITY;
+    for (int w = 0; w < (nt >> 5); ++w) m = fmaxf(m, s_red[w]);
+    __syncthreads();
+    return m;
+  };
+  float am = 0.f;
+  for (int i = tid; i < n * dim; i += nt) am = fmaxf(am, fabsf(Y[i]));
+  am = block_max(am);
+  const float expansion = am > 0.f ? 10.f / am : 1.f;
+  for (int i = tid; i < n * dim; i += nt) {
+    const uint64_t key = seed * 0xD6E8FEB86659FD93ull + ((uint64_t)p << 40) + (uint64_t)i * 2;
+    const float u1 = u01(key), u2 = u01(key + 1);
+    const float g = sqrtf(-2.f * logf(u1)) * cosf(6.28318530718f * u2);
+    Y[i] = Y[i] * expansion + noise * g;
+  }
+  __syncthreads();
+  for (int d = 0; d < dim; ++d) {
+    float mx = -INFINITY, mn = INFINITY;
+    for (int i = tid; i < n; i += nt) { const float v = Y[(size_t)i * dim + d]; mx = fmaxf(mx, v); mn = fminf(mn, v); }
+    mx = block_max(mx);
+    mn = -block_max(-mn);
+    if (tid == 0) { s_val[2 * d] = mn; s_val[2 * d + 1] = mx; }
+  }
+  __syncthreads();
+  for (int i = tid; i < n * dim; i += nt) {
+    const int d = i % dim;
+    const float mn = s_val[2 * d], mx = s_val[2 * d + 1];
+    Y[i] = mx > mn ? 10.f * (Y[i] - mn) / (mx - mn) : 0.f;
+  }
+}
+
+// init_transform: new point = sum_t w_t * train_embedding[idx_t], w = l1-normalised membership strengths
+__global__ void transform_init_kernel(const int* __restrict__ knn_idx, const float* __restrict__ knn_dist, const float* __restrict__ sigma,
+                                      const float* __restrict__ rho, const float* __restrict__ train, int nq, int ntrain, int k, int dim,
+                                      float* __restrict__ Y, int* __restrict__ head, int* __restrict__ tail, float* __restrict__ weight,
+                                      unsigned int* __restrict__ max_w_bits) {
+  const int p = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  const size_t base = ((size_t)p * nq + i) * k;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float wsum = 0.f, wmax = 0.f;
+  for (int t = 0; t < k; ++t) {
+    const int j = knn_idx[base + t];
+    float w = 0.f;
+    if (j >= 0) w = membership(knn_dist[base + t], rho[(size_t)p * nq + i], sigma[(size_t)p * nq + i], false, true);
+    head[base + t] = i; tail[base + t] = j < 0 ? 0 : j; weight[base + t] = w;
+    wsum += w; wmax = fmaxf(wmax, w);
+    if (j >= 0)
+      for (int d = 0; d < dim; ++d) acc[d] += w * train[((size_t)p * ntrain + j) * dim + d];
+  }
+  for (int d = 0; d < dim; ++d) Y[((size_t)p * nq + i) * dim + d] = wsum > 0.f ? acc[d] / wsum : 0.f;
+  if (wmax > 0.f) atomicMax(&max_w_bits[p], __float_as_uint(wmax));
+}
+
+}  // namespace umap
+}  // namespace tda
+
+using namespace tda;
+using namespace tda::umap;
+
+extern "C" int tda_knn_smooth(const float* D, int n, int m, int batch, int k, float local_connectivity, float bandwidth, int n_iter,
+                              int32_t* knn_idx, float* knn_dist, float* sigma, float* rho, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!D || !knn_idx || !knn_dist || !sigma || !rho || !ws || n <= 0 || m <= 0 || batch <= 0) return set_error(TDA_ERR_INVALID, "tda_knn_smooth: bad arguments");
+  if (k < 1 || k > m) return set_error(TDA_ERR_INVALID, "tda_knn_smooth: k=%d out of range (1..%d)", k, m);
+  if (k > 256) return set_error(TDA_ERR_UNSUPPORTED, "tda_knn_smooth: k=%d > 256", k);
+  if (ws_bytes < sizeof(double) * (size_t)batch) return set_error(TDA_ERR_WORKSPACE, "tda_knn_smooth: workspace too small");
+  double* dist_sum = (double*)ws;
+  TDA_CUDA_CHECK(cudaMemsetAsync(dist_sum, 0, sizeof(double) * batch, stream));
+  dim3 grid((n + 7) / 8, batch);
+  const int kpl = (k + 31) / 32;
+#define TDA_KNN_LAUNCH(KPL) knn_smooth_kernel<KPL><<<grid, 256, 0, stream>>>(D, n, m, k, local_connectivity, bandwidth, n_iter, knn_idx, knn_dist, sigma, rho, dist_sum)
+  if (kpl == 1) TDA_KNN_LAUNCH(1);
+  else if (kpl == 2) TDA_KNN_LAUNCH(2);
+  else if (kpl <= 4) TDA_KNN_LAUNCH(4);
+  else TDA_KNN_LAUNCH(8);
+#undef TDA_KNN_LAUNCH
+  dim3 g2((n + 255) / 256, batch);
+  sigma_floor_kernel<<<g2, 256, 0, stream>>>(n, k, rho, sigma, dist_sum);
+  count_launch(2);
+  TDA_LAUNCH_CHECK();
+  return TDA_OK;
+}
+
+extern "C" int tda_fuzzy_graph(const int32_t* knn_idx, const float* knn_dist, const float* sigma, const float* rho, int n, int k, int batch,
+                               float mix_ratio, int n_epochs, int32_t* head, int32_t* tail, float* weight, float* eps, float* max_weight,
+                               void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!knn_idx || !knn_dist || !sigma || !rho || !head || !tail || !weight || !eps || !max_weight || n <= 0 || k <= 0 || batch <= 0)
+    return set_error(TDA_ERR_INVALID, "tda_fuzzy_graph: bad arguments");
+  TDA_CUDA_CHECK(cudaMemsetAsync(max_weight, 0, sizeof(float) * batch, stream));
+  dim3 g((n * k + 255) / 256, batch);
+  fuzzy_kernel<<<g, 256, 0, stream>>>(knn_idx, knn_dist, sigma, rho, n, k, mix_ratio, head, tail, weight, (unsigned int*)max_weight);
+  dim3 g2((2 * n * k + 255) / 256, batch);
+  epochs_kernel<<<g2, 256, 0, stream>>>(weight, 2 * n * k, n_epochs, (const unsigned int*)max_weight, eps);
+  count_launch(2);
+  TDA_LAUNCH_CHECK();
+  return TDA_OK;
+}
+
+extern "C" int tda_umap_sgd(float* Y, const float* Y_other, const int32_t* head, const int32_t* tail, const float* eps, int slots, int n_head,
+                            int n_tail, int dim, int batch, int n_epochs, float a, float b, float gamma, float alpha0,
+                            float negative_sample_rate, int move_other, uint64_t seed, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!Y || !head || !tail || !eps || slots <= 0 || n_head <= 0 || n_tail <= 0 || batch <= 0 || n_epochs < 0)
+    return set_error(TDA_ERR_INVALID, "tda_umap_sgd: bad arguments");
+  if (!move_other && !Y_other) return set_error(TDA_ERR_INVALID, "tda_umap_sgd: Y_other required when move_other=0");
+  if (dim < 1 || dim > 4) return set_error(TDA_ERR_UNSUPPORTED, "tda_umap_sgd: n_components=%d (supported: 1..4)", dim);
+  dim3 g((slots + 255) / 256, batch);
+  for (int ep = 0; ep < n_epochs; ++ep) {
+    const float alpha = ep == 0 ? alpha0 : alpha0 * (1.f - (float)(ep - 1) / (float)n_epochs);
+#define TDA_SGD_LAUNCH(DIM) sgd_epoch_kernel<DIM><<<g, 256, 0, stream>>>(Y, Y_other, head, tail, eps, slots, n_head, n_tail, ep, a, b, gamma, alpha, negative_sample_rate, move_other, seed)
+    switch (dim) {
+      case 1: TDA_SGD_LAUNCH(1); break;
+      case 2: TDA_SGD_LAUNCH(2); break;
+      case 3: TDA_SGD_LAUNCH(3); break;
+      default: TDA_SGD_LAUNCH(4); break;
+    }
+#undef TDA_SGD_LAUNCH
+  }
+  count_launch(n_epochs);
+  TDA_LAUNCH_CHECK();
+  return TDA_OK;
+}
+
+extern "C" int tda_umap_init_random(float* Y, int n, int dim, int batch, float lo, float hi, uint64_t seed, void* stream_) {
+  if (!Y || n <= 0 || dim <= 0 || batch <= 0) return set_error(TDA_ERR_INVALID, "tda_umap_init_random: bad arguments");
+  const int total = n * dim * batch;
+  init_random_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(Y, total, lo, hi, seed);
+  count_launch();
+  TDA_LAUNCH_CHECK();
+  return TDA_OK;
+}
+
+extern "C" int tda_umap_rescale(float* Y, int n, int dim, int batch, float noise, uint64_t seed, void* stream_) {
+  if (!Y || n <= 0 || dim <= 0 || dim > 8 || batch <= 0) return set_error(TDA_ERR_INVALID, "tda_umap_rescale: bad arguments");
+  rescale_kernel<<<batch, 1024, 0, (cudaStream_t)stream_>>>(Y, n, dim, noise, seed);
+  count_launch();
+  TDA_LAUNCH_CHECK();
+  return TDA_OK;
+}
+
+extern "C" int tda_umap_transform_init(const int32_t* knn_idx, const float* knn_dist, const float* sigma, const float* rho,
+                                       const float* train_embedding, int n_query, int n_train, int k, int dim, int batch, int n_epochs,
+                                       float* Y, int32_t* head, int32_t* tail, float* weight, float* eps, float* max_weight, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!knn_idx || !knn_dist || !sigma || !rho || !train_embedding || !Y || !head || !tail || !weight || !eps || !max_weight || dim > 8)
+    return set_error(TDA_ERR_INVALID, "tda_umap_transform_init: bad arguments");
+  TDA_CUDA_CHECK(cudaMemsetAsync(max_weight, 0, sizeof(float) * batch, stream));
+  dim3 g((n_query + 127) / 128, batch);
+  transform_init_kernel<<<g, 128, 0, stream>>>(knn_idx, knn_dist, sigma, rho, train_embedding, n_query, n_train, k, dim, Y, head, tail, weight,
+                                               (unsigned int*)max_weight);
+  dim3 g2((n_query * k + 255) / 256, batch);
+  epochs_kernel<<<g2, 256, 0, stream>>>(weight, n_query * k, n_epochs, (const unsigned int*)max_weight, eps);
+  count_launch(2);
+  TDA_LAUNCH_CHECK();
+  return TDA_OK;
+}
