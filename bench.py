@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- UMAP + Rips(H0/H1) layers/sec on the C3 workload of BASELINE.json
+("32 layers x 2k tokens x 4096-d, UMAP k=15 then Rips H0/H1"), synthetic activations (tda_multimodal_b200/workloads.py).
+
+  python bench.py --gpus N --steps K --warmup W            this repo's CUDA path (one rank per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...  the CPU restatement of umap-learn + ripser (oracle/), all host cores
+
+A step = one pass of the hot path over one batch: every rank runs the 32-layer sweep (pairwise distances -> exact kNN
++ sigma/rho -> fuzzy graph -> spectral init -> SGD to 3-D -> Rips H0/H1) on its own 32 layers (weak scaling: layer
+sets differ by rank) and the ranks gather the diagrams (NCCL) -- the only cross-GPU traffic of the path.
+`value` times the sweep with the activations already resident in HBM; `e2e` times the same sweep from pinned HOST
+buffers (H2D of the activations and D2H of embeddings + diagrams inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "umap_rips_h0h1_layers_per_sec"
+UNIT = "layers/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--layers", type=int, default=32)
+    ap.add_argument("--points", type=int, default=2000)
+    ap.add_argument("--dim", type=int, default=4096)
+    ap.add_argument("--neighbors", type=int, default=15)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=25.0)
+    return ap.parse_args()
+
+
+def workload_config(a, world):
+    return {"workload": f"C3: {a.layers} layers x {a.points} points x {a.dim}-d synthetic activations per GPU, UMAP(n_neighbors={a.neighbors}, "
+                        f"n_components=3, min_dist=0.1, metric=cosine, 500 epochs) -> ripser(maxdim=1)",
+            "layers_per_gpu": a.layers, "points": a.points, "dim": a.dim, "n_neighbors": a.neighbors,
+            "parallelism": f"layer-sharded x{world}, NCCL gather of diagrams", "l2": "inputs (1.05 GB/step/GPU) larger than L2"}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU side (oracle port of umap-learn + ripser): used by cpu_baseline and by --impl reference
+def _cpu_layer(args):
+    layer, n, d, k, n_layers = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from oracle import umap_oracle as uo, rips as orips
+    from tda_multimodal_b200 import workloads
+    X = workloads.c3_layer(layer, n=n, d=d, n_layers=n_layers)
+    t0 = time.perf_counter()
+    Y = uo.UMAPOracle(n_neighbors=k, n_components=3, min_dist=0.1, metric="cosine", random_state=42).fit_transform(X)
+    t1 = time.perf_counter()
+    orips.ripser(Y, maxdim=1)
+    t2 = time.perf_counter()
+    return layer, t1 - t0, t2 - t1
+
+
+def _cpu_warm():
+    """numba JIT + library load, untimed (tiny cloud)."""
+    from oracle import umap_oracle as uo, rips as orips
+    from tda_multimodal_b200 import workloads
+    X = workloads.c3_layer(0, n=120, d=64)
+    Y = uo.UMAPOracle(n_neighbors=10, n_components=3, metric="cosine", random_state=42).fit_transform(X)
+    orips.ripser(Y, maxdim=1)
+
+
+def cpu_baseline_serial(a, budget_s):
+    """Single core, as the reference runs it (serial `for i in range(32)`, random_state set => serial numba SGD,
+    ripser single-threaded): whole layers of the same workload until the time budget is used."""
+    _cpu_warm()
+    done, t_total, per = 0, 0.0, []
+    for layer in range(a.layers):
+        _, tu, tr = _cpu_layer((layer, a.points, a.dim, a.neighbors, a.layers))
+        done += 1
+        t_total += tu + tr
+        per.append((round(tu, 2), round(tr, 2)))
+        if t_total >= budget_s:
+            break
+    return {"value": done / t_total, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"layers 0..{done - 1} of the {a.layers}-layer C3 workload, serial on one core (oracle/umap_oracle.py numba + oracle/rips_oracle.cpp); "
+                      f"per-layer (umap_s, rips_s) = {per}"}
+
+
+def run_reference(a):
+    """--impl reference: the oracle port on all host cores (one process per layer, layers are independent)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, a.layers))
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs, initializer=_pool_init) as pool:
+        for _ in range(max(1, a.warmup)):
+            pool.map(_warm_job, range(procs))          # warm-up = JIT / library load on every worker (tiny clouds)
+        times = []
+        for _ in range(a.steps):
+            # bounded sample: the first `procs` layers of the workload, one per core, concurrently
+            t0 = time.perf_counter()
+            pool.map(_cpu_layer, [(l, a.points, a.dim, a.neighbors, a.layers) for l in range(procs)])
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = procs * a.steps / total
+    sample = (f"per step: layers 0..{procs - 1} of the C3 workload concurrently, one process per core; warm-up steps run tiny clouds "
+              f"(numba JIT only)")
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "reference", "config": workload_config(a, a.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def _pool_init():
+    os.environ["OMP_NUM_THREADS"] = "1"
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    os.environ["MKL_NUM_THREADS"] = "1"
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+
+
+def _warm_job(_):
+    _cpu_warm()
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, f"/tmp/tda_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in open(self.path):
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return out
+
+
+def algorithmic_work(stage, a, n_layers_done, extra):
+    """Algorithmic bytes / flops of one stage over `n_layers_done` layers (DESIGN.md 'Measurement')."""
+    n, d, k = a.points, a.dim, a.neighbors
+    E = n * (n - 1) // 2
+    L = n_layers_done
+    if stage == "pdist_gemm":
+        return "tensor", 2.0 * L * n * n * d
+    table = {
+        "pdist_prep": L * (4.0 * n * d + 8.0 * n * d),                 # read X, write hi + lo
+        "knn_smooth": L * (4.0 * n * n + 8.0 * n * k + 8.0 * n),       # read D, write idx+dist, sigma+rho
+        "fuzzy_graph": L * (12.0 * n * k + 8.0 * n + 16.0 * 2 * n * k),
+        "spectral_init": L * extra.get("spectral_bytes_per_layer", 0.0),
+        "umap_sgd": extra.get("sgd_bytes", 0.0),
+        "rips_pdist": L * (12.0 * n + 4.0 * n * n),
+        "rips_edge_sort": L * (4.0 * n * n + 16.0 * E + 16.0 * E),     # read dm, radix sort key+payload, rank scatter
+        "rips_h0": L * (4.0 * n * n) * extra.get("boruvka_rounds", 11),
+        "rips_apparent": L * 8.0 * (E - n + 1) * (n - 2),
+        "rips_reduce": 8.0 * extra.get("reduce_keys", 0.0),
+    }
+    return "hbm", table[stage]
+
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    from tda_multimodal_b200 import _lib, pipeline, workloads
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the b200 arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+
+    # this rank's 32 layers (weak scaling: rank r gets layer seeds offset by r * layers), in pinned host memory
+    Xh = torch.empty((a.layers, a.points, a.dim), dtype=torch.float32).pin_memory()
+    workloads.c3_layers(n_layers=a.layers, n=a.points, d=a.dim, seed=3000 + 1000 * rank, out=Xh.numpy())
+    Xd = Xh.to(dev)
+    n_units = a.layers * world
+    my_units = list(range(rank * a.layers, (rank + 1) * a.layers))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        out = pipeline.layer_sweep(Xd, n_neighbors=a.neighbors, return_embedding=True)
+        return gather(out)
+
+    def step_e2e():
+        out = pipeline.layer_sweep_host(Xh, device=dev, n_neighbors=a.neighbors)
+        return gather(out), out
+
+    def gather(out):
+        if world == 1:
+            return [r["dgms"] for r in out["results"]]
+        # contiguous unit ranges per rank: gather with the same two all_gathers, then reorder
+        counts, payload = pipeline.pack_diagrams(out["results"])
+        ct = torch.from_numpy(counts).to(dev)
+        allc = [torch.empty_like(ct) for _ in range(world)]
+        dist.all_gather(allc, ct)
+        rows = max(int(c.sum()) for c in allc)
+        pad = np.zeros((max(rows, 1), 2), np.float32)
+        pad[:payload.shape[0]] = payload
+        pt = torch.from_numpy(pad).to(dev)
+        allp = [torch.empty_like(pt) for _ in range(world)]
+        dist.all_gather(allp, pt)
+        if rank != 0:
+            return None
+        full = []
+        for r in range(world):
+            full += pipeline.unpack_diagrams(allc[r].cpu().numpy(), allp[r].cpu().numpy())
+        return full
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            res = fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), res
+
+    for _ in range(a.warmup):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    L.tda_launch_count_reset()
+    L.tda_stage_timing_reset()
+    L.tda_stage_timing_enable(1)
+    ms_res, dgms = timed(step_resident, a.steps)
+    launches = int(L.tda_launch_count())
+    stages = _lib.stage_times()
+    L.tda_stage_timing_enable(0)
+    ms_e2e, (dg2, out2) = timed(step_e2e, a.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        layers_per_step = a.layers * world
+        value = layers_per_step * a.steps / (ms_res / 1e3)
+        e2e_value = layers_per_step * a.steps / (ms_e2e / 1e3)
+        d2h = int(out2["embedding"].nbytes + sum(sum(d.shape[0] * 8 for d in r["dgms"]) for r in out2["results"]) + 16 * a.layers)
+        # ---- roofline of the dominant stage (timed with CUDA events inside the timed region, rank 0)
+        import json as _json
+        peaks = {}
+        try:
+            peaks = _json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        bf16_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+        peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+        # device-side counters of the last sweep for the reduction's algorithmic bytes
+        extra = {}
+        try:
+            dm = pipeline.pdist_lowdim(torch.from_numpy(out2["embedding"]).to(dev))
+            st = pipeline.rips_batch(dm, maxdim=1, want_stats=True)
+            extra["reduce_keys"] = float(sum(r["stats"]["pushes"] + r["stats"]["pops"] for r in st)) * a.steps
+            extra["rips_stats_sum"] = {k: int(sum(r["stats"][k] for r in st)) for k in ("columns", "apparent", "reduced", "additions", "pushes", "pops")}
+        except Exception as ex:  # stats are optional evidence
+            extra["stats_error"] = repr(ex)
+        n_done = a.layers * a.steps
+        fired = 0.0
+        extra["sgd_bytes"] = 124.0 * 500 * 2 * a.points * a.neighbors * 0.35 * n_done  # ~35% of slots fire per epoch on average
+        tot_ms = sum(v[0] for v in stages.values())
+        dom = max(stages, key=lambda s: stages[s][0])
+        kind, work = algorithmic_work(dom, a, n_done, extra)
+        dom_ms = stages[dom][0]
+        calls = max(1, stages[dom][1])
+        if kind == "tensor":
+            achieved = work / (dom_ms / 1e3) / 1e12
+            peak, unit = bf16_peak / 2.0, "TFLOP/s"     # kind::tf32 issues at half the bf16 rate; useful flops = 1/3 of issued (3xTF32)
+        else:
+            achieved = work / (dom_ms / 1e3) / 1e9
+            peak, unit = hbm_peak, "GB/s"
+        roofline = {"kernel": dom, "bound": kind, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak if peak else None,
+                    "traffic": None, "peak_source": peak_src, "avg_launch_ms": dom_ms / calls, "share_of_device_stage_time": dom_ms / tot_ms if tot_ms else None,
+                    "stages_ms_per_step": {s: round(v[0] / a.steps, 3) for s, v in stages.items()}}
+        if "rips_stats_sum" in extra:
+            roofline["rips_stats_per_step"] = extra["rips_stats_sum"]
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms_res / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": workload_config(a, world),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(Xh.numel() * 4), "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / a.steps},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
+        if world == 1 and not a.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_serial(a, a.cpu_budget_s)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

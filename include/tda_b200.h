@@ -34,6 +34,26 @@ const char* tda_last_error(void);
 int64_t tda_launch_count(void);
 void tda_launch_count_reset(void);
 
+/* Optional stage timer (off by default): when enabled, every entry point brackets its stages with CUDA events on
+ * the stream it launches on; tda_stage_timing_read synchronises those events and returns the accumulated
+ * milliseconds and call counts per stage (arrays of TDA_STAGE_COUNT entries); returns TDA_STAGE_COUNT.
+ * bench.py uses it to time the dominant kernel inside the timed region (roofline.achieved). */
+#define TDA_STAGE_PDIST_PREP 0
+#define TDA_STAGE_PDIST_GEMM 1
+#define TDA_STAGE_KNN_SMOOTH 2
+#define TDA_STAGE_FUZZY 3
+#define TDA_STAGE_SPECTRAL 4
+#define TDA_STAGE_SGD 5
+#define TDA_STAGE_RIPS_PDIST 6
+#define TDA_STAGE_RIPS_SORT 7
+#define TDA_STAGE_RIPS_H0 8
+#define TDA_STAGE_RIPS_APPARENT 9
+#define TDA_STAGE_RIPS_REDUCE 10
+#define TDA_STAGE_COUNT 11
+void tda_stage_timing_enable(int on);
+void tda_stage_timing_reset(void);
+int tda_stage_timing_read(double* ms_out, int64_t* calls_out, int n);
+
 /* ---- pairwise distances on high-dimensional activations (tcgen05 / TMEM / TMA GEMM, 3xTF32) ------
  * Replaces sklearn.metrics.pairwise_distances inside umap-learn's small-data path (metric='cosine';
  * debug_tda_pipeline.py:96-104, analyze_tda_over_layers.py:69,72, analyze_adversarial_tda.py:85-93), inside

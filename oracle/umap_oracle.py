@@ -319,7 +319,7 @@ class UMAPOracle:
         self._knn_indices, self._knn_dists = exact_knn(dmat, k)
         self.graph_, self._sigmas, self._rhos = fuzzy_simplicial_set(self._knn_indices, self._knn_dists, n, k,
                                                                     self.set_op_mix_ratio, self.local_connectivity)
-        graph = self.graph_.tocoo()
+        graph = self.graph_.tocoo(copy=True)  # graph_ itself stays unpruned
         graph.sum_duplicates()
         n_epochs = self.n_epochs if self.n_epochs is not None else (500 if n <= 10000 else 200)
         graph.data[graph.data < (graph.data.max() / float(n_epochs))] = 0.0

@@ -13,6 +13,9 @@ PROTOTYPES = {
     "tda_last_error": (ctypes.c_char_p, []),
     "tda_launch_count": (c_int64, []),
     "tda_launch_count_reset": (None, []),
+    "tda_stage_timing_enable": (None, [c_int]),
+    "tda_stage_timing_reset": (None, []),
+    "tda_stage_timing_read": (c_int, [c_void_p, c_void_p, c_int]),
     "tda_pdist_lowdim": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tda_pdist_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "tda_pdist": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -38,6 +41,17 @@ PROTOTYPES = {
 }
 
 TDA_ERR_CAPACITY = -4
+STAGES = ["pdist_prep", "pdist_gemm", "knn_smooth", "fuzzy_graph", "spectral_init", "umap_sgd", "rips_pdist", "rips_edge_sort",
+          "rips_h0", "rips_apparent", "rips_reduce"]
+
+
+def stage_times():
+    """{stage: (milliseconds, calls)} accumulated since the last reset (synchronises the recorded events)."""
+    import numpy as np
+    ms = np.zeros(len(STAGES), dtype=np.float64)
+    calls = np.zeros(len(STAGES), dtype=np.int64)
+    lib().tda_stage_timing_read(ms.ctypes.data, calls.ctypes.data, len(STAGES))
+    return {s: (float(ms[i]), int(calls[i])) for i, s in enumerate(STAGES)}
 
 
 class TdaError(RuntimeError):

@@ -1,7 +1,8 @@
-// capi.cu -- library-wide pieces of the C ABI (version, error string, launch counter).
+// capi.cu -- library-wide pieces of the C ABI (version, error string, launch counter, stage timer).
 #include "common.cuh"
 #include "launch_count.cuh"
 #include "../../include/tda_b200.h"
+#include <vector>
 
 namespace tda {
 char* tls_error_buffer() {
@@ -12,9 +13,74 @@ int64_t& launch_counter() {
   static thread_local int64_t c = 0;
   return c;
 }
+
+// ---- stage timer: per thread, a list of (stage, start event, stop event); events are pooled and reused
+struct StageRec { int stage; cudaEvent_t e0, e1; };
+struct StageState {
+  bool on = false;
+  std::vector<StageRec> recs;
+  std::vector<cudaEvent_t> pool;
+  double ms[STAGE_COUNT] = {0};
+  int64_t calls[STAGE_COUNT] = {0};
+  int open[STAGE_COUNT];
+  StageState() { for (int i = 0; i < STAGE_COUNT; ++i) open[i] = -1; }
+};
+static StageState& stage_state() {
+  static thread_local StageState s;
+  return s;
+}
+bool stage_timing_on() { return stage_state().on; }
+static cudaEvent_t take_event(StageState& S) {
+  cudaEvent_t e = nullptr;
+  if (!S.pool.empty()) { e = S.pool.back(); S.pool.pop_back(); }
+  else cudaEventCreate(&e);
+  return e;
+}
+void stage_begin(int stage, cudaStream_t s) {
+  StageState& S = stage_state();
+  StageRec r{stage, take_event(S), take_event(S)};
+  cudaEventRecord(r.e0, s);
+  S.open[stage] = (int)S.recs.size();
+  S.recs.push_back(r);
+}
+void stage_end(int stage, cudaStream_t s) {
+  StageState& S = stage_state();
+  if (S.open[stage] < 0) return;
+  cudaEventRecord(S.recs[S.open[stage]].e1, s);
+  S.open[stage] = -1;
+}
+static void stage_collect(StageState& S) {
+  for (StageRec& r : S.recs) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+      S.ms[r.stage] += (double)ms;
+      S.calls[r.stage] += 1;
+    }
+    S.pool.push_back(r.e0);
+    S.pool.push_back(r.e1);
+  }
+  S.recs.clear();
+  (void)cudaGetLastError();
+}
 }  // namespace tda
 
 extern "C" int tda_version(void) { return 100; }
 extern "C" const char* tda_last_error(void) { return tda::tls_error_buffer(); }
 extern "C" int64_t tda_launch_count(void) { return tda::launch_counter(); }
 extern "C" void tda_launch_count_reset(void) { tda::launch_counter() = 0; }
+
+extern "C" void tda_stage_timing_enable(int on) { tda::stage_state().on = on != 0; }
+extern "C" void tda_stage_timing_reset(void) {
+  tda::StageState& S = tda::stage_state();
+  tda::stage_collect(S);
+  for (int i = 0; i < tda::STAGE_COUNT; ++i) { S.ms[i] = 0; S.calls[i] = 0; }
+}
+extern "C" int tda_stage_timing_read(double* ms_out, int64_t* calls_out, int n) {
+  tda::StageState& S = tda::stage_state();
+  tda::stage_collect(S);
+  for (int i = 0; i < n && i < tda::STAGE_COUNT; ++i) {
+    if (ms_out) ms_out[i] = S.ms[i];
+    if (calls_out) calls_out[i] = S.calls[i];
+  }
+  return tda::STAGE_COUNT;
+}

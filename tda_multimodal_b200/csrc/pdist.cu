@@ -416,6 +416,7 @@ extern "C" int tda_pdist(const float* X, const float* Y, int n, int m, int d, in
   if (L.total > ws_bytes) return set_error(TDA_ERR_WORKSPACE, "tda_pdist: workspace %zu < required %zu", ws_bytes, L.total);
   const bool euclid = (metric == TDA_METRIC_SQEUCLIDEAN || metric == TDA_METRIC_EUCLIDEAN);
   const float* mean = nullptr;
+  stage_begin_if(STAGE_PDIST_PREP, stream);
   if (euclid && symmetric) {  // centring is distance preserving and removes the ||x||^2 cancellation of raw activations
     dim3 g((d + 127) / 128, batch);
     col_mean_kernel<<<g, 128, 0, stream>>>(X, n, d, L.mean);
@@ -433,6 +434,7 @@ extern "C" int tda_pdist(const float* X, const float* Y, int n, int m, int d, in
     prep_kernel<<<(unsigned)((size_t)batch * m), 128, 0, stream>>>(Y, m, d, L.dp, metric, nullptr, L.b_hi, L.b_lo, L.norm_b);
     count_launch();
   }
+  stage_end_if(STAGE_PDIST_PREP, stream);
   TDA_LAUNCH_CHECK();
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int rc;
@@ -451,7 +453,10 @@ extern "C" int tda_pdist(const float* X, const float* Y, int n, int m, int d, in
   TDA_CUDA_CHECK(cudaFuncSetAttribute(pdist_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   const long long tiles = (long long)P.tiles_m * P.tiles_n * batch;
   const int grid = (int)(tiles < sms ? tiles : sms);
-  pdist_gemm_kernel<<<grid, kThreads, kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, P);
+  {
+    StageScope st(STAGE_PDIST_GEMM, stream);
+    pdist_gemm_kernel<<<grid, kThreads, kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, P);
+  }
   count_launch();
   TDA_LAUNCH_CHECK();
   return TDA_OK;

@@ -29,10 +29,6 @@ namespace tda {
 namespace rips {
 
 constexpr int kReduceThreads = 256;
-constexpr int kChunk = 512;            // keys per heap chunk
-constexpr uint32_t kNil = 0xffffffffu;
-constexpr int kGenItems = 8;           // cofacets generated per thread per sub-batch (256*8 = 2048 vertices)
-constexpr int kMaxNew = kReduceThreads * kGenItems / kChunk + 2;
 constexpr int kRankDiag = 0x7fffffff;
 
 // stats slots
@@ -278,19 +274,19 @@ __global__ void __launch_bounds__(1024) h0_emit_kernel(const uint32_t* __restric
 // rank(b,v) < r (the first cofacet of the edge in filtration order has the edge as its longest edge),
 // -1 if the lune is empty, -2 for MST edges (negative edges are not columns).
 __global__ void apparent_kernel(const int* __restrict__ rank, const uint32_t* __restrict__ ends, const uint8_t* __restrict__ mst,
-                                const int* __restrict__ Tarr, int n, int64_t E, int* __restrict__ apex, int* __restrict__ blist,
-                                int* __restrict__ bcount, int cap1, unsigned long long* __restrict__ stats) {
+                                const int* __restrict__ Tarr, int n, int64_t E, int* __restrict__ apex, uint2* __restrict__ ea,
+                                int* __restrict__ blist, int* __restrict__ bcount, int cap1, unsigned long long* __restrict__ stats) {
   const int p = blockIdx.y;
   const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int T = Tarr[p];
   if (r >= T) return;
   int* A = apex + (size_t)p * E;
+  const uint32_t e = ends[(size_t)p * E + r];
   if (mst[(size_t)p * E + r]) {
-    if (lane == 0) A[r] = -2;
+    if (lane == 0) { A[r] = -2; ea[(size_t)p * E + r] = make_uint2(e, (uint32_t)-2); }
     return;
   }
-  const uint32_t e = ends[(size_t)p * E + r];
   const int* ra = rank + (size_t)p * n * n + (size_t)(e >> 16) * n;
   const int* rb = rank + (size_t)p * n * n + (size_t)(e & 0xffffu) * n;
   int found = -1;
@@ -302,6 +298,7 @@ __global__ void apparent_kernel(const int* __restrict__ rank, const uint32_t* __
   }
   if (lane == 0) {
     A[r] = found;
+    ea[(size_t)p * E + r] = make_uint2(e, (uint32_t)found);
     if (found < 0) {
       int pos = atomicAdd(&bcount[p], 1);
       if (pos < cap1) blist[(size_t)p * cap1 + pos] = (int)r;
@@ -313,427 +310,261 @@ __global__ void apparent_kernel(const int* __restrict__ rank, const uint32_t* __
 // residual reduction
 //
 // Working column of one edge b with an empty lune = set of triangle keys with odd multiplicity in
-// delta(V), V = edges added so far.  Three levels, all owned by one CTA:
-//   F      : open-addressing hash SET in shared memory holding the keys in [base, fmax]; inserting a key
-//            that is already present removes it (Z/2 cancellation is free); pop-min = block-wide scan.
-//   heap   : monotone radix heap for the keys > fmax: bucket q>=1 holds keys whose highest bit differing
-//            from `base` is q-1, as linked lists of 512-key chunks in a global pool (per-CTA free list +
-//            global bump).  When F runs dry the first non-empty bucket [L,U] is streamed into F
-//            (base=L, fmax=U); when F overflows its upper half is spilled back (fmax lowered).
-// Keys above the horizon H are not stored at all; when everything <= H is consumed the horizon is
-// extended and delta(V) re-enumerated for the new window.
-template <typename K> struct KeyTraits;
-template <> struct KeyTraits<uint32_t> {
-  static constexpr int NB = 33;
-  static __device__ __forceinline__ int bucket(uint32_t x) { return 32 - __clz(x); }
-  static __device__ __forceinline__ uint32_t maxv() { return 0xffffffffu; }
-  static __device__ __forceinline__ uint32_t low_mask(int b) { return b >= 32 ? 0xffffffffu : ((1u << b) - 1u); }
-  static __device__ __forceinline__ uint32_t cas(uint32_t* a, uint32_t c, uint32_t v) { return atomicCAS(a, c, v); }
-};
-template <> struct KeyTraits<uint64_t> {
-  static constexpr int NB = 65;
-  static __device__ __forceinline__ int bucket(uint64_t x) { return 64 - __clzll((long long)x); }
-  static __device__ __forceinline__ uint64_t maxv() { return ~0ull; }
-  static __device__ __forceinline__ uint64_t low_mask(int b) { return b >= 64 ? ~0ull : ((1ull << b) - 1ull); }
-  static __device__ __forceinline__ uint64_t cas(uint64_t* a, uint64_t c, uint64_t v) {
-    return (uint64_t)atomicCAS((unsigned long long*)a, (unsigned long long)c, (unsigned long long)v);
-  }
-};
-
-constexpr int kFCap = 4096;        // slots of the shared-memory front set
-constexpr int kFLoad = 1024;       // largest bucket loaded into F in one go / live keys kept after a spill
-constexpr int kFUsedMax = 1536;    // used slots (live + tombstones) allowed before a 2048-key batch
-constexpr int kFreeCache = 48;
+// delta(V), V = edges added so far.  One CTA owns one cloud at a time and walks its columns in ripser's
+// order.  The column lives in a BITSET over the key space (global memory, one window of `wbits` bits per
+// resident CTA): adding the coboundary of an edge is n-2 fire-and-forget atomic XORs (Z/2 cancellation is
+// free, keys never move), the next pivot is the next set bit.  A one-bit-per-page summary of the bitset sits
+// in shared memory (page = 8192 bits = 1 KB), so the scan skips empty regions and the clean-up after a
+// column touches only dirty pages.  The 2^18 keys just ahead of the scan position (the "near" range) are held in
+// shared memory instead: the chain of pivots is followed there without a global fence or a global read per step,
+// and the range is refilled from the global bitset (and zeroed there) when the scan runs off its end.  If the key
+// space exceeds the window, keys beyond it are dropped and delta(V) is re-enumerated when the window slides.
+constexpr int kPageShift = 13;                 // 8192 bits per page
+constexpr int kPageWords = 1 << (kPageShift - 5);  // 256 words = kReduceThreads
+static_assert(kPageWords == kReduceThreads, "one thread per word of a page");
+constexpr int kNearShift = 18;                 // near range: 2^18 bits = 32 pages = 32 KB of shared memory
+constexpr int kNearWords = 1 << (kNearShift - 5);
+constexpr uint64_t kNearBits = 1ull << kNearShift;
+constexpr uint32_t kScanRows = 8;              // rows of kReduceThreads near words examined per barrier
 
 struct ReduceParams {
-  const int* rank; const uint32_t* ends; const float* sdist; const int* T; const int* apex;
+  const int* rank; const uint32_t* ends; const float* sdist; const int* T; const uint2* ea;  // ea[r] = (endpoints, apex)
   int* blist; const int* bcount;
   int n; int64_t E; int batch; int cap1;
   float* h1_pairs; int64_t* h1_simplex; int32_t* counts;
   // per-CTA scratch
+  uint32_t* bits; uint64_t wbits;           // [grid, wbits/32]  (all zero between columns)
   uint32_t* vbits; int64_t vwords;          // [grid, vwords]
   uint32_t* vlist; int64_t vcap;            // [grid, 2, vcap]
   // per-problem
-  void* hkeys; int* hvals; int hcap;        // [batch, hcap]
+  uint64_t* hkeys; int* hvals; int hcap;    // [batch, hcap]
   uint32_t* vpool; int64_t vpool_cap;       // [batch, vpool_cap]
   int64_t* vstart; int* vlen;               // [batch, cap1]
-  // heap pool (shared)
-  void* pool_keys; uint32_t* pool_next; uint32_t pool_chunks; unsigned int* pool_top;
   int* work_counter; unsigned long long* stats;  // [batch, ST_N]
 };
 
-template <typename K>
 struct ReduceSmem {
-  K F[kFCap];
-  K base, fmax, red[kReduceThreads / 32], red2[kReduceThreads / 32];
-  uint32_t head[KeyTraits<K>::NB], tail[KeyTraits<K>::NB], fill[KeyTraits<K>::NB], count[KeyTraits<K>::NB];
-  uint32_t bcnt[KeyTraits<K>::NB], oldtail[KeyTraits<K>::NB], oldfill[KeyTraits<K>::NB];
-  uint32_t newchunk[KeyTraits<K>::NB][kMaxNew];
-  uint32_t fcache[kFreeCache];
-  uint32_t nzmask[3];
-  uint32_t fcache_n, freehead, vcount, vcount2, vsel, f_used;
-  int f_live;
-  int bc_int, abort_flag, problem;
-  unsigned long long pushes, pops;
+  alignas(16) uint32_t nearw[kNearWords];
+  uint32_t bal[2][kReduceThreads / 32];
+  uint32_t val[2][kReduceThreads / 32];
+  uint32_t vcount, vcount2, vsel;
+  int abort_flag, problem;
+  unsigned long long toggles;
 };
 
-template <typename K>
 struct Reducer {
-  using TR = KeyTraits<K>;
-  static constexpr int NB = TR::NB;
-  static constexpr int kFItems = kFCap / kReduceThreads;
+  static constexpr uint64_t kEmpty = ~0ull;
   const ReduceParams& P;
-  ReduceSmem<K>& S;
-  const int tid;
-  const int* R; const uint32_t* EN; const int* A; int T; int n;
-  K* pool; uint32_t* vbits; uint32_t* vl[2];
-  K* hkeys; int* hvals;
+  ReduceSmem& S;
+  uint32_t* s1;            // page summary (dynamic shared memory), s1words words
+  const int tid, lane, warp;
+  const int* R; const uint32_t* EN; const uint2* EA; int T; int n;
+  uint32_t* bits; uint32_t* vbits; uint32_t* vl0;
+  uint64_t* hkeys; int* hvals;
+  uint64_t wbits; uint32_t npages, s1words;
+  uint64_t wbase;          // first key of the window
+  uint64_t nbase;          // first relative position of the near range (page aligned)
+  uint32_t par;            // parity of the bal/val double buffer
+  unsigned long long my_toggles;
+  unsigned long long n_refills, n_passes;   // diagnostics
 
-  static __device__ __forceinline__ K empty_key() { return TR::maxv(); }
-  static __device__ __forceinline__ K tomb_key() { return TR::maxv() - 1; }
-
-  __device__ Reducer(const ReduceParams& p, ReduceSmem<K>& s) : P(p), S(s), tid(threadIdx.x) {
-    pool = (K*)P.pool_keys;
+  __device__ __forceinline__ Reducer(const ReduceParams& p, ReduceSmem& s, uint32_t* s1_)
+      : P(p), S(s), s1(s1_), tid(threadIdx.x), lane(threadIdx.x & 31), warp(threadIdx.x >> 5) {
     n = P.n;
+    wbits = P.wbits;
+    npages = (uint32_t)(wbits >> kPageShift);
+    s1words = (npages + 31) >> 5;
+    bits = P.bits + (size_t)blockIdx.x * (wbits >> 5);
     vbits = P.vbits + (size_t)blockIdx.x * P.vwords;
-    vl[0] = P.vlist + (size_t)blockIdx.x * 2 * P.vcap;
-    vl[1] = vl[0] + P.vcap;
+    vl0 = P.vlist + (size_t)blockIdx.x * 2 * P.vcap;
+    par = 0;
+    my_toggles = 0;
+    n_refills = n_passes = 0;
   }
 
-  // ---- chunk pool (thread 0 only)
-  __device__ uint32_t alloc_chunk() {
-    if (S.fcache_n) return S.fcache[--S.fcache_n];
-    uint32_t c = S.freehead;
-    if (c != kNil) { S.freehead = P.pool_next[c]; return c; }
-    c = atomicAdd(P.pool_top, 1u);
-    if (c >= P.pool_chunks) { S.abort_flag = TDA_ERR_CAPACITY; return P.pool_chunks; /* trash chunk */ }
-    return c;
-  }
-  __device__ void free_chunk(uint32_t c) {
-    if (c >= P.pool_chunks) return;
-    if (S.fcache_n < (uint32_t)kFreeCache) { S.fcache[S.fcache_n++] = c; return; }
-    P.pool_next[c] = S.freehead;
-    S.freehead = c;
-  }
-
-  __device__ void heap_reset() {
-    if (tid < NB) { S.head[tid] = kNil; S.tail[tid] = kNil; S.fill[tid] = kChunk; S.count[tid] = 0; }
-  }
-  // return every chunk of every bucket to the free list (O(1) per bucket: splice)
-  __device__ void heap_release() {
-    __syncthreads();
-    if (tid == 0)
-      for (int b = 0; b < NB; ++b)
-        if (S.head[b] != kNil && S.head[b] < P.pool_chunks) {
-          uint32_t t = S.tail[b];
-          if (t < P.pool_chunks) { P.pool_next[t] = S.freehead; S.freehead = S.head[b]; }
-        }
-    __syncthreads();
-    heap_reset();
-    __syncthreads();
-  }
-
-  // ---- F: shared-memory front set with toggle semantics
-  __device__ void f_clear() {
-#pragma unroll
-    for (int it = 0; it < kFItems; ++it) S.F[tid + it * kReduceThreads] = empty_key();
-    if (tid == 0) { S.f_used = 0; S.f_live = 0; }
-    __syncthreads();
-  }
-  __device__ __forceinline__ void f_toggle(K key) {
-    uint32_t h = (uint32_t)(((uint64_t)key * 0x9E3779B97F4A7C15ull) >> 40) & (kFCap - 1);
-    for (;;) {
-      K cur = S.F[h];
-      if (cur == key) {
-        if (TR::cas(&S.F[h], key, tomb_key()) == key) { atomicSub(&S.f_live, 1); return; }
-        cur = S.F[h];  // someone else removed it first: keep probing
-      }
-      if (cur == empty_key()) {
-        K prev = TR::cas(&S.F[h], empty_key(), key);
-        if (prev == empty_key()) { atomicAdd(&S.f_used, 1u); atomicAdd(&S.f_live, 1); return; }
-        if (prev == key) continue;  // the same key landed here concurrently: retry this slot (will remove it)
-      }
-      h = (h + 1) & (kFCap - 1);
+  // smallest thread index whose word is non-zero (and that word), or -1; one barrier per call
+  __device__ __forceinline__ int block_first_nonzero(uint32_t w, uint32_t& wout) {
+    const unsigned b = __ballot_sync(0xffffffffu, w != 0);
+    const uint32_t wfirst = __shfl_sync(0xffffffffu, w, b ? __ffs(b) - 1 : 0);
+    if (lane == 0) {
+      S.bal[par][warp] = b;
+      S.val[par][warp] = wfirst;
     }
-  }
-  __device__ K block_min(K v) {
-    v = sizeof(K) == 4 ? (K)warp_min_u32((uint32_t)v) : (K)warp_min_u64((uint64_t)v);
-    if ((tid & 31) == 0) S.red[tid >> 5] = v;
     __syncthreads();
-    K m = S.red[0];
+    int first = -1;
 #pragma unroll
-    for (int w = 1; w < kReduceThreads / 32; ++w) m = S.red[w] < m ? S.red[w] : m;
+    for (int i = kReduceThreads / 32 - 1; i >= 0; --i)
+      if (S.bal[par][i]) { first = i * 32 + __ffs(S.bal[par][i]) - 1; wout = S.val[par][i]; }
+    par ^= 1;
+    return first;
+  }
+
+  // block-wide minimum; one barrier per call
+  __device__ __forceinline__ uint32_t block_min(uint32_t v) {
+    v = __reduce_min_sync(0xffffffffu, v);
+    if (lane == 0) S.bal[par][warp] = v;
     __syncthreads();
+    uint32_t m = S.bal[par][0];
+#pragma unroll
+    for (int i = 1; i < kReduceThreads / 32; ++i) m = min(m, S.bal[par][i]);
+    par ^= 1;
     return m;
   }
-  // smallest live key of F, removed; false if F holds no live key
-  __device__ bool f_popmin(K& out) {
-    if (S.f_live <= 0) return false;
-    K m = tomb_key();
-    int at = -1;
-#pragma unroll
-    for (int it = 0; it < kFItems; ++it) {
-      int i = tid + it * kReduceThreads;
-      K k = S.F[i];
-      if (k < m) { m = k; at = i; }
-    }
-    const K g = block_min(m);
-    if (g >= tomb_key()) return false;
-    if (m == g && at >= 0) { S.F[at] = tomb_key(); S.f_live -= 1; }  // exactly one slot holds a live key
-    __syncthreads();
-    out = g;
-    return true;
-  }
 
-  // ---- push a batch of keys held in registers to the heap (all threads call).
-  // force_bucket: -1 => by radix relative to S.base (keys > fmax >= base)
-  template <int ITEMS>
-  __device__ void push_batch(const K (&keys)[ITEMS], const bool (&valid)[ITEMS], int force_bucket) {
-    int any = 0;
-#pragma unroll
-    for (int it = 0; it < ITEMS; ++it) any |= valid[it] ? 1 : 0;
-    if (tid < NB) S.bcnt[tid] = 0;
-    if (!__syncthreads_or(any)) return;
-    int bk[ITEMS];
-    uint32_t off[ITEMS];
-    const K base = S.base;
-    const unsigned lane_lt = (1u << (tid & 31)) - 1u;
-#pragma unroll
-    for (int it = 0; it < ITEMS; ++it) {
-      // warp-aggregated slot reservation: one shared-memory atomic per distinct bucket per warp
-      bk[it] = valid[it] ? (force_bucket >= 0 ? force_bucket : TR::bucket(keys[it] ^ base)) : -1;
-      unsigned act = __ballot_sync(0xffffffffu, valid[it]);
-      if (act) {
-        unsigned peers = __match_any_sync(0xffffffffu, bk[it]);
-        if (valid[it]) {
-          int leader = __ffs(peers) - 1;
-          uint32_t b0 = 0;
-          if ((tid & 31) == leader) b0 = atomicAdd(&S.bcnt[bk[it]], (uint32_t)__popc(peers));
-          b0 = __shfl_sync(peers, b0, leader);
-          off[it] = b0 + __popc(peers & lane_lt);
-        }
-      }
-    }
-    __syncthreads();
-    if (tid < NB) {
-      if (S.bcnt[tid]) {
-        S.oldtail[tid] = S.tail[tid];
-        S.oldfill[tid] = S.fill[tid];
-        atomicOr(&S.nzmask[tid >> 5], 1u << (tid & 31));
-      }
-    }
-    __syncthreads();
-    if (tid == 0) {
-      unsigned long long added = 0;
-      for (int wq = 0; wq < 3; ++wq) {
-        unsigned msk = S.nzmask[wq];
-        S.nzmask[wq] = 0;
-        while (msk) {
-          int b = wq * 32 + __ffs(msk) - 1;
-          msk &= msk - 1;
-          uint32_t c = S.bcnt[b];
-          added += c;
-          uint32_t total = S.fill[b] + c;
-          uint32_t nnew = total > (uint32_t)kChunk ? (total - kChunk + kChunk - 1) / kChunk : 0;
-          uint32_t prev = S.tail[b];
-          for (uint32_t j = 0; j < nnew; ++j) {
-            uint32_t ch = alloc_chunk();
-            S.newchunk[b][j] = ch;
-            if (prev != kNil && prev < P.pool_chunks) P.pool_next[prev] = ch; else if (prev == kNil) S.head[b] = ch;
-            prev = ch;
-          }
-          if (nnew) { S.tail[b] = prev; S.fill[b] = total - kChunk * nnew; } else S.fill[b] = total;
-          S.count[b] += c;
-        }
-      }
-      S.pushes += added;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int it = 0; it < ITEMS; ++it)
-      if (valid[it]) {
-        int b = bk[it];
-        uint32_t pos = S.oldfill[b] + off[it];
-        uint32_t ch;
-        if (pos < (uint32_t)kChunk) ch = S.oldtail[b];
-        else { pos -= kChunk; ch = S.newchunk[b][pos / kChunk]; pos %= kChunk; }
-        pool[(size_t)ch * kChunk + pos] = keys[it];
-      }
-    __syncthreads();
-  }
-
-  // ---- keep F within its load limits: compact tombstones, spill the upper half to the heap when too many live keys
-  __device__ void f_maintain(uint32_t max_used) {
-    if (S.f_used <= max_used) return;
-    K keep[kFItems];
-    bool live[kFItems];
+  // next set bit of the window at relative position >= pos; false when the window holds none
+  __device__ __forceinline__ bool scan(uint64_t& pos) {
     for (;;) {
-#pragma unroll
-      for (int it = 0; it < kFItems; ++it) {
-        keep[it] = S.F[tid + it * kReduceThreads];
-        live[it] = keep[it] < tomb_key();
-      }
-      const int nlive = S.f_live;
-      __syncthreads();
-      K mid = TR::maxv();
-      if (nlive > kFLoad) {  // spill keys above the midpoint of the live range
-        K mn = TR::maxv(), mx = 0;
-#pragma unroll
-        for (int it = 0; it < kFItems; ++it)
-          if (live[it]) { mn = keep[it] < mn ? keep[it] : mn; mx = keep[it] > mx ? keep[it] : mx; }
-        mn = block_min(mn);
-        mx = ~block_min((K)~mx);
-        mid = mn + (mx - mn) / 2;
-      }
-      f_clear();
-      bool spill[kFItems];
-#pragma unroll
-      for (int it = 0; it < kFItems; ++it) {
-        spill[it] = live[it] && keep[it] > mid;
-        if (live[it] && !spill[it]) f_toggle(keep[it]);
-      }
-      if (nlive > kFLoad) {
-        if (tid == 0) S.fmax = mid;
-        push_batch<kFItems>(keep, spill, -1);
-      }
-      __syncthreads();
-      if (S.f_live <= kFLoad) break;
-    }
-  }
-
-  // ---- refill F from the radix heap; false when nothing is stored at all
-  __device__ bool refill() {
-    for (;;) {
-      if (S.f_live > 0) return true;
-      int b = 0;
-      for (int q = 1; q < NB; ++q)
-        if (S.count[q]) { b = q; break; }
-      if (!b) return false;
-      f_clear();
-      const uint32_t hb = S.head[b], tb = S.tail[b], fb = S.fill[b], cb = S.count[b];
-      if (tid == 0) {  // detach the list; F now covers the bucket's whole key range [L, U]
-        S.head[b] = kNil; S.tail[b] = kNil; S.fill[b] = kChunk; S.count[b] = 0;
-        S.pops += cb;
-        const K old = S.base;
-        S.fmax = old | TR::low_mask(b);
-        S.base = (old & ~TR::low_mask(b)) | ((K)1 << (b - 1));
-      }
-      __syncthreads();
-      for (uint32_t c = hb; c != kNil;) {
-        const uint32_t cnt = (c == tb) ? fb : (uint32_t)kChunk;
-        const uint32_t nxt = (c == tb) ? kNil : P.pool_next[c];
-        const K fmax = S.fmax;  // may have been lowered by a spill while streaming a long list
-        K keys[kChunk / kReduceThreads];
-        bool valid[kChunk / kReduceThreads];
-#pragma unroll
-        for (int it = 0; it < kChunk / kReduceThreads; ++it) {
-          uint32_t i = tid + it * kReduceThreads;
-          valid[it] = false;
-          if (i < cnt) {
-            K k = pool[(size_t)c * kChunk + i];
-            if (k <= fmax) f_toggle(k); else { keys[it] = k; valid[it] = true; }
-          }
+      // near range (shared memory): the word under the cursor first (uniform address, no barrier), then every
+      // thread walks its own column of the word array (conflict free) and the block takes the minimum index
+      while (pos < nbase + kNearBits) {
+        const uint32_t wi = (uint32_t)((pos - nbase) >> 5);
+        const uint32_t w0 = S.nearw[wi] & (0xffffffffu << (pos & 31));
+        if (w0) { pos = nbase + ((uint64_t)wi << 5) + (uint64_t)(__ffs(w0) - 1); return true; }
+        const uint32_t row0 = (wi + 1) / kReduceThreads;
+        uint32_t cand = 0xffffffffu;
+        for (uint32_t r = row0; r < row0 + kScanRows && r < (uint32_t)(kNearWords / kReduceThreads); ++r) {
+          const uint32_t idx = r * kReduceThreads + tid;
+          if (cand == 0xffffffffu && idx > wi && S.nearw[idx] != 0) cand = idx;
         }
-        __syncthreads();
-        if (tid == 0) free_chunk(c);
-        push_batch<kChunk / kReduceThreads>(keys, valid, -1);
-        f_maintain(kFCap - 2 * kChunk);
-        c = nxt;
+        cand = block_min(cand);
+        ++n_passes;
+        if (cand != 0xffffffffu) {
+          const uint32_t w = S.nearw[cand];
+          pos = nbase + ((uint64_t)cand << 5) + (uint64_t)(__ffs(w) - 1);
+          return true;
+        }
+        pos = nbase + ((uint64_t)min((row0 + kScanRows) * kReduceThreads, (uint32_t)kNearWords) << 5);
+      }
+      // near range exhausted: move it to the next dirty page of the global bitset
+      ++n_refills;
+      __threadfence();  // every thread's XORs are performed before anybody reads the bitset
+      __syncthreads();
+      uint32_t page = (uint32_t)((nbase + kNearBits) >> kPageShift);
+      if (page >= npages) return false;
+      uint32_t found_page = 0xffffffffu;
+      for (uint32_t base = page >> 5; base < s1words; base += kReduceThreads) {
+        const uint32_t idx = base + tid;
+        uint32_t w = idx < s1words ? s1[idx] : 0u;
+        if (idx == (page >> 5)) w &= 0xffffffffu << (page & 31);
+        uint32_t wv = 0;
+        const int f = block_first_nonzero(w, wv);
+        if (f >= 0) { found_page = (base + f) * 32 + (__ffs(wv) - 1); break; }
+      }
+      if (found_page == 0xffffffffu || found_page >= npages) { nbase = (uint64_t)npages << kPageShift; return false; }
+      nbase = (uint64_t)found_page << kPageShift;
+      pos = nbase;
+      // move [nbase, nbase + 2^18) from the global bitset to shared memory: 8 x 16-byte loads per thread, all in flight
+      const uint64_t wwords = wbits >> 5;
+      const uint64_t g0 = nbase >> 5;  // multiple of 256 words: 16-byte aligned
+      uint4 buf[kNearWords / 4 / kReduceThreads];
+#pragma unroll
+      for (int j = 0; j < kNearWords / 4 / kReduceThreads; ++j) {
+        const uint64_t g = g0 + ((uint64_t)j * kReduceThreads + tid) * 4;
+        buf[j] = g < wwords ? __ldcg(reinterpret_cast<const uint4*>(bits + g)) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int j = 0; j < kNearWords / 4 / kReduceThreads; ++j) {
+        const uint32_t idx4 = (uint32_t)j * kReduceThreads + tid;
+        const uint64_t g = g0 + (uint64_t)idx4 * 4;
+        reinterpret_cast<uint4*>(S.nearw)[idx4] = buf[j];
+        if (buf[j].x | buf[j].y | buf[j].z | buf[j].w) *reinterpret_cast<uint4*>(bits + g) = make_uint4(0, 0, 0, 0);
+      }
+      if (tid < (1 << (kNearShift - kPageShift))) {
+        const uint32_t pg = found_page + tid;
+        if (pg < npages) atomicAnd(&s1[pg >> 5], ~(1u << (pg & 31)));
       }
       __syncthreads();
     }
   }
 
-  // next pivot: smallest key with odd multiplicity; false when the stored part of the column is empty
-  __device__ bool extract(K& out) {
-    if (!refill()) return false;
-    return f_popmin(out);
+  __device__ __forceinline__ void toggle_key(uint64_t key) {
+    const uint64_t rel = key - wbase;
+    ++my_toggles;
+    if (rel - nbase < kNearBits) {  // (rel >= nbase always: keys below the scan position are never generated)
+      atomicXor(&S.nearw[(rel - nbase) >> 5], 1u << (rel & 31));
+      return;
+    }
+    atomicXor(&bits[rel >> 5], 1u << (rel & 31));
+    const uint32_t page = (uint32_t)(rel >> kPageShift);
+    const uint32_t m = 1u << (page & 31);
+    if (!(s1[page >> 5] & m)) atomicOr(&s1[page >> 5], m);
   }
-
-  // ---- cofacets of edge `re` with key in (lo, hi] -> F / heap
-  __device__ void gen_push(int re, K lo, K hi) {
-    const uint32_t e = EN[re];
+  // cofacets of edge `re` with key in [lo, wbase + wbits): vertices strided over `nthr` threads
+  __device__ __forceinline__ void gen(int re, uint64_t lo, int t0, int nthr) { gen(re, __ldg(&EN[re]), lo, t0, nthr); }
+  __device__ __forceinline__ void gen(int re, uint32_t e, uint64_t lo, int t0, int nthr) {
     const int a = (int)(e >> 16), b = (int)(e & 0xffffu);
     const int* rowa = R + (size_t)a * n;
     const int* rowb = R + (size_t)b * n;
-    for (int v0 = 0; v0 < n; v0 += kReduceThreads * kGenItems) {
-      f_maintain(kFUsedMax);
-      K keys[kGenItems];
-      bool valid[kGenItems];
-      int ra[kGenItems], rb[kGenItems];
+    const uint64_t hi = wbase + wbits;
+    for (int v0 = t0; v0 < n; v0 += nthr * 4) {
+      int ra[4], rb[4];
 #pragma unroll
-      for (int it = 0; it < kGenItems; ++it) {
-        int v = v0 + it * kReduceThreads + tid;
-        ra[it] = v < n ? rowa[v] : kRankDiag;
-        rb[it] = v < n ? rowb[v] : kRankDiag;
+      for (int it = 0; it < 4; ++it) {
+        const int v = v0 + it * nthr;
+        ra[it] = v < n ? __ldg(&rowa[v]) : kRankDiag;
+        rb[it] = v < n ? __ldg(&rowb[v]) : kRankDiag;
       }
-      const K fmax = S.fmax;
 #pragma unroll
-      for (int it = 0; it < kGenItems; ++it) {
-        int v = v0 + it * kReduceThreads + tid;
-        int M = max(re, max(ra[it], rb[it]));
-        valid[it] = false;
+      for (int it = 0; it < 4; ++it) {
+        const int v = v0 + it * nthr;
+        const int M = max(re, max(ra[it], rb[it]));
         if (M < T) {
-          int opp = (M == re) ? v : (M == ra[it] ? b : a);
-          K key = (K)M * (K)n + (K)(n - 1 - opp);
-          if (key > lo && key <= hi) {
-            keys[it] = key;
-            if (key <= fmax) f_toggle(key); else valid[it] = true;
-          }
+          const int opp = (M == re) ? v : (M == ra[it] ? b : a);
+          const uint64_t key = (uint64_t)M * (uint64_t)n + (uint64_t)(n - 1 - opp);
+          if (key >= lo && key < hi) toggle_key(key);
         }
       }
-      push_batch<kGenItems>(keys, valid, -1);
     }
   }
+  // the next scan reads shared memory only (the global XORs are fenced when the near range is refilled)
+  __device__ __forceinline__ void publish() { __syncthreads(); }
 
   // ---- V (the reduction column as a set of edges, by rank)
-  __device__ void v_toggle_single(int re) {  // thread 0
-    uint32_t w = (uint32_t)re >> 5, m = 1u << (re & 31);
-    uint32_t old = atomicXor(&vbits[w], m);
-    if (!(old & m)) {
-      uint32_t pos = S.vcount;
-      if (pos < (uint32_t)P.vcap) { vl[S.vsel][pos] = (uint32_t)re; S.vcount = pos + 1; }
-      else S.abort_flag = TDA_ERR_CAPACITY;
-    }
+  __device__ __forceinline__ uint32_t* vlist(uint32_t sel) const { return vl0 + (size_t)sel * P.vcap; }
+  __device__ __forceinline__ void v_toggle(int re) {  // any single thread; fire-and-forget (no atomic round trip)
+    atomicXor(&vbits[(uint32_t)re >> 5], 1u << (re & 31));
+    const uint32_t pos = atomicAdd(&S.vcount, 1u);  // the list may hold an edge several times: v_compact keeps it once iff its bit is set
+    if (pos < (uint32_t)P.vcap) vlist(S.vsel)[pos] = (uint32_t)re;
+    else S.abort_flag = TDA_ERR_CAPACITY;
   }
   // compact the list: keep each edge whose bit is set exactly once
-  __device__ void v_compact() {
+  __device__ __forceinline__ void v_compact() {
     __syncthreads();
-    const uint32_t nin = S.vcount;
-    const uint32_t* src = vl[S.vsel];
-    uint32_t* dst = vl[S.vsel ^ 1];
+    const uint32_t nin = min(S.vcount, (uint32_t)P.vcap);
+    const uint32_t* src = vlist(S.vsel);
+    uint32_t* dst = vlist(S.vsel ^ 1);
     if (tid == 0) S.vcount2 = 0;
     __syncthreads();
     for (uint32_t i0 = 0; i0 < nin; i0 += kReduceThreads) {
-      uint32_t i = i0 + tid;
+      const uint32_t i = i0 + tid;
       bool keep = false;
       uint32_t e = 0;
       if (i < nin) {
         e = src[i];
-        uint32_t m = 1u << (e & 31);
+        const uint32_t m = 1u << (e & 31);
         keep = (atomicAnd(&vbits[e >> 5], ~m) & m) != 0;
       }
-      unsigned bal = __ballot_sync(0xffffffffu, keep);
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
       uint32_t bs = 0;
-      if ((tid & 31) == 0 && bal) bs = atomicAdd(&S.vcount2, (uint32_t)__popc(bal));
+      if (lane == 0 && bal) bs = atomicAdd(&S.vcount2, (uint32_t)__popc(bal));
       bs = __shfl_sync(0xffffffffu, bs, 0);
-      if (keep) dst[bs + __popc(bal & ((1u << (tid & 31)) - 1))] = e;
+      if (keep) dst[bs + __popc(bal & ((1u << lane) - 1))] = e;
     }
     __syncthreads();
     const uint32_t nout = S.vcount2;
     for (uint32_t i = tid; i < nout; i += kReduceThreads) {
-      uint32_t e = dst[i];
+      const uint32_t e = dst[i];
       atomicOr(&vbits[e >> 5], 1u << (e & 31));
     }
     __syncthreads();
     if (tid == 0) { S.vsel ^= 1; S.vcount = nout; }
     __syncthreads();
   }
-  __device__ void v_clear() {  // after v_compact: clear bits, empty list
+  __device__ __forceinline__ void v_clear() {  // after v_compact: clear bits, empty list
     const uint32_t nin = S.vcount;
-    const uint32_t* src = vl[S.vsel];
+    const uint32_t* src = vlist(S.vsel);
     for (uint32_t i = tid; i < nin; i += kReduceThreads) {
-      uint32_t e = src[i];
+      const uint32_t e = src[i];
       atomicAnd(&vbits[e >> 5], ~(1u << (e & 31)));
     }
     __syncthreads();
@@ -741,25 +572,25 @@ struct Reducer {
     __syncthreads();
   }
 
-  // ---- pivot hash map (thread 0)
-  __device__ int hash_find(K key) {
-    uint32_t h = (uint32_t)((uint64_t)key * 0x9E3779B97F4A7C15ull >> 32) & (uint32_t)(P.hcap - 1);
+  // ---- pivot hash map: probed by every thread redundantly (uniform addresses -> one transaction, no barrier)
+  __device__ __forceinline__ int hash_find(uint64_t key) const {
+    uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32) & (uint32_t)(P.hcap - 1);
     for (;;) {
-      K k = hkeys[h];
+      const uint64_t k = hkeys[h];
       if (k == key) return hvals[h];
-      if (k == TR::maxv()) return -1;
+      if (k == kEmpty) return -1;
       h = (h + 1) & (uint32_t)(P.hcap - 1);
     }
   }
-  __device__ void hash_insert(K key, int val) {
-    uint32_t h = (uint32_t)((uint64_t)key * 0x9E3779B97F4A7C15ull >> 32) & (uint32_t)(P.hcap - 1);
-    while (hkeys[h] != TR::maxv()) h = (h + 1) & (uint32_t)(P.hcap - 1);
+  __device__ __forceinline__ void hash_insert(uint64_t key, int val) {  // thread 0
+    uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32) & (uint32_t)(P.hcap - 1);
+    while (hkeys[h] != kEmpty) h = (h + 1) & (uint32_t)(P.hcap - 1);
     hkeys[h] = key;
     hvals[h] = val;
   }
 
   // sort blist[0..nb) ascending in place (bitonic, global memory)
-  __device__ void sort_blist(int* bl, int nb) {
+  __device__ __forceinline__ void sort_blist(int* bl, int nb) {
     int np2 = 1;
     while (np2 < nb) np2 <<= 1;
     for (int i = nb + tid; i < np2; i += kReduceThreads) bl[i] = 0x7fffffff;  // cap1 is a power of two >= nb
@@ -767,10 +598,10 @@ struct Reducer {
     for (int k = 2; k <= np2; k <<= 1)
       for (int j = k >> 1; j > 0; j >>= 1) {
         for (int i = tid; i < np2; i += kReduceThreads) {
-          int ixj = i ^ j;
+          const int ixj = i ^ j;
           if (ixj > i) {
-            int a = bl[i], b = bl[ixj];
-            bool up = ((i & k) == 0);
+            const int a = bl[i], b = bl[ixj];
+            const bool up = ((i & k) == 0);
             if ((a > b) == up) { bl[i] = b; bl[ixj] = a; }
           }
         }
@@ -778,31 +609,72 @@ struct Reducer {
       }
   }
 
-  __device__ void run_problem(int p) {
+  // add the edges list[0..cnt) (global memory): one warp per edge
+  __device__ __forceinline__ void add_edges(const uint32_t* list, uint32_t cnt, uint64_t lo, bool track_v) {
+    for (uint32_t i = warp; i < cnt; i += kReduceThreads / 32) {
+      const int re = (int)list[i];
+      if (track_v && lane == 0) v_toggle(re);
+      gen(re, lo, lane, 32);
+    }
+  }
+
+  // zero the window again after a column: bits at relative position >= pos may be set
+  __device__ __forceinline__ void clean_window(uint64_t pos, uint32_t nv) {
+    const uint64_t lo = wbase + pos;
+    if ((uint64_t)nv * (uint64_t)n <= 32ull * npages) {
+      // few keys: toggle them back (V holds every edge exactly once after v_compact)
+      add_edges(vlist(S.vsel), nv, lo, false);
+      __threadfence();
+    } else {
+      // many keys: sweep the dirty pages, one warp per page
+      const uint32_t p0 = (uint32_t)(min(nbase + kNearBits, wbits) >> kPageShift);
+      for (uint32_t wbase_i = (p0 >> 5); wbase_i < s1words; wbase_i += kReduceThreads / 32) {
+        const uint32_t wi = wbase_i + warp;
+        uint32_t f = wi < s1words ? s1[wi] : 0u;
+        while (f) {
+          const uint32_t page = wi * 32 + (__ffs(f) - 1);
+          f &= f - 1;
+          uint4* dst = reinterpret_cast<uint4*>(bits + (size_t)page * kPageWords);
+          dst[lane] = make_uint4(0, 0, 0, 0);
+          dst[lane + 32] = make_uint4(0, 0, 0, 0);
+        }
+      }
+      __threadfence();
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < s1words; i += kReduceThreads) s1[i] = 0;
+    for (uint32_t i = tid; i < (uint32_t)kNearWords; i += kReduceThreads) S.nearw[i] = 0;
+    __syncthreads();
+  }
+
+  __device__ __forceinline__ void run_problem(int p) {
     R = P.rank + (size_t)p * n * n;
     EN = P.ends + (size_t)p * P.E;
-    A = P.apex + (size_t)p * P.E;
+    EA = P.ea + (size_t)p * P.E;
     T = P.T[p];
-    hkeys = (K*)P.hkeys + (size_t)p * P.hcap;
+    hkeys = P.hkeys + (size_t)p * P.hcap;
     hvals = P.hvals + (size_t)p * P.hcap;
     const float* SD = P.sdist + (size_t)p * P.E;
     int* bl = P.blist + (size_t)p * P.cap1;
-    int nb = P.bcount[p];
+    const int nb = P.bcount[p];
     unsigned long long* st = P.stats + (size_t)p * ST_N;
     if (nb > P.cap1) {
       if (tid == 0) { P.counts[p * 4 + 3] = TDA_ERR_CAPACITY; P.counts[p * 4 + 1] = 0; }
       return;
     }
     sort_blist(bl, nb);
-    for (int i = tid; i < P.hcap; i += kReduceThreads) hkeys[i] = TR::maxv();
-    if (tid == 0) { S.pushes = 0; S.pops = 0; S.vcount = 0; S.vsel = 0; S.abort_flag = 0; }
-    heap_reset();
+    for (int i = tid; i < P.hcap; i += kReduceThreads) hkeys[i] = kEmpty;
+    for (uint32_t i = tid; i < s1words; i += kReduceThreads) s1[i] = 0;
+    for (uint32_t i = tid; i < (uint32_t)kNearWords; i += kReduceThreads) S.nearw[i] = 0;
+    if (tid == 0) { S.vcount = 0; S.vsel = 0; S.abort_flag = 0; S.toggles = 0; }
+    my_toggles = 0;
+    n_refills = n_passes = 0;
+    __threadfence();
     __syncthreads();
-    const K kmax = (K)T * (K)n - 1;
-    const uint64_t span0 = (uint64_t)max(T / 64, 256) * (uint64_t)n;
+    const uint64_t kmax = (uint64_t)T * (uint64_t)n;  // keys are < kmax
     int nrows = 0;
     int64_t vpool_used = 0;
-    unsigned long long additions = 0, extensions = 0, maxv = 0;
+    unsigned long long additions = 0, slides = 0, maxv = 0, pops = 0;
     long long cyc[6] = {0, 0, 0, 0, 0, 0};
     unsigned long long badd_edges = 0, ext_edges = 0;
     long long t0;
@@ -811,71 +683,64 @@ struct Reducer {
 
     for (int ci = nb - 1; ci >= 0; --ci) {
       const int rbirth = bl[ci];
-      const K start = (K)(rbirth + 1) * (K)n - 1;
-      K H = ((uint64_t)(kmax - start) > span0) ? (K)(start + (K)span0) : kmax;
-      uint64_t span = span0;
-      f_clear();
-      if (tid == 0) { S.base = start; S.fmax = start; v_toggle_single(rbirth); }
-      __syncthreads();
-      gen_push(rbirth, start, H);
+      const uint64_t first = (uint64_t)(rbirth + 1) * (uint64_t)n;  // the lune of rbirth is empty: every cofacet key is >= first
+      wbase = first & ~((1ull << kPageShift) - 1);
+      nbase = 0;
+      uint64_t pos = first - wbase;
+      if (tid == 0) v_toggle(rbirth);
+      gen(rbirth, first, tid, kReduceThreads);
+      publish();
       bool essential = false;
-      K pivot = 0;
+      uint64_t pivot = 0;
       for (;;) {
         if (S.abort_flag) break;
-        K pk;
         t0 = clock64();
-        bool ok = extract(pk);
+        const bool ok = scan(pos);
         cyc[0] += clock64() - t0;
         if (!ok) {
-          if (H >= kmax) { essential = true; break; }
-          // extend the horizon: re-enumerate V for keys in (H, H2]
+          if (wbase + wbits >= kmax) { essential = true; break; }
+          // slide the window (it is all zero now) and re-enumerate delta(V) for the new range
           t0 = clock64();
-          span = span * 4;
-          K H2 = ((uint64_t)(kmax - H) > span) ? (K)(H + (K)span) : kmax;
+          wbase += wbits;
+          nbase = 0;
+          pos = 0;
           v_compact();
-          const uint32_t nv = S.vcount;
-          const uint32_t* list = vl[S.vsel];
-          for (uint32_t i = 0; i < nv; ++i) gen_push((int)list[i], H, H2);
-          H = H2;
-          ++extensions;
-          ext_edges += nv;
+          add_edges(vlist(S.vsel), S.vcount, wbase, false);
+          publish();
+          ++slides;
+          ext_edges += S.vcount;
           cyc[4] += clock64() - t0;
           continue;
         }
-        // owner of the pivot
+        ++pops;
+        const uint64_t pk = wbase + pos;
         t0 = clock64();
-        const int M = (int)(pk / (K)n);
-        const int w = n - 1 - (int)(pk % (K)n);
-        if (tid == 0) {
-          int kind = -1;  // -1 none, -2 apparent, >=0 reduced column id
-          if (A[M] == w) kind = -2; else kind = hash_find(pk);
-          S.bc_int = kind;
-        }
-        __syncthreads();
-        const int owner = S.bc_int;
-        __syncthreads();
+        int M, w;
+        if ((pk >> 32) == 0) { M = (int)((uint32_t)pk / (uint32_t)n); w = n - 1 - (int)((uint32_t)pk - (uint32_t)M * (uint32_t)n); }
+        else { M = (int)(pk / (uint64_t)n); w = n - 1 - (int)(pk % (uint64_t)n); }
+        const uint2 eaM = __ldg(&EA[M]);
+        int owner = -2;  // -1 none, -2 apparent, >=0 reduced column id
+        if ((int)eaM.y != w) owner = hash_find(pk);
         cyc[1] += clock64() - t0;
         if (owner == -1) { pivot = pk; break; }
         ++additions;
         t0 = clock64();
         if (owner == -2) {
-          if (tid == 0) v_toggle_single(M);
-          __syncthreads();
-          gen_push(M, pk, H);
+          if (tid == 0) v_toggle(M);
+          gen(M, eaM.x, pk, tid, kReduceThreads);
+          publish();
           cyc[2] += clock64() - t0;
         } else {
           const int64_t vs = P.vstart[(size_t)p * P.cap1 + owner];
           const int vn = P.vlen[(size_t)p * P.cap1 + owner];
           const uint32_t* ov = P.vpool + (size_t)p * P.vpool_cap + vs;
           if (S.vcount + (uint32_t)vn > (uint32_t)P.vcap) v_compact();
-          for (int i = 0; i < vn; ++i) {
-            int re = (int)ov[i];
-            if (tid == 0) v_toggle_single(re);
-            gen_push(re, pk, H);
-          }
+          add_edges(ov, (uint32_t)vn, pk, true);
+          publish();
           badd_edges += vn;
           cyc[3] += clock64() - t0;
         }
+        pos += 1;  // pk itself was toggled off by the addition
       }
       if (S.abort_flag) break;
       t0 = clock64();
@@ -887,7 +752,7 @@ struct Reducer {
         // store V (all edges, including the column's own) for later additions
         if (vpool_used + nv > P.vpool_cap) { if (tid == 0) S.abort_flag = TDA_ERR_CAPACITY; __syncthreads(); break; }
         uint32_t* dst = P.vpool + (size_t)p * P.vpool_cap + vpool_used;
-        const uint32_t* list = vl[S.vsel];
+        const uint32_t* list = vlist(S.vsel);
         for (uint32_t i = tid; i < nv; i += kReduceThreads) dst[i] = list[i];
         if (tid == 0) {
           P.vstart[(size_t)p * P.cap1 + ci] = vpool_used;
@@ -895,20 +760,23 @@ struct Reducer {
           hash_insert(pivot, ci);
         }
         vpool_used += nv;
+        clean_window(pos, nv);
+      } else {
+        for (uint32_t i = tid; i < s1words; i += kReduceThreads) s1[i] = 0;
       }
       const float birth = SD[rbirth];
       float death = INFINITY;
       int Md = -1, wd = -1;
-      if (!essential) { Md = (int)(pivot / (K)n); wd = n - 1 - (int)(pivot % (K)n); death = SD[Md]; }
+      if (!essential) { Md = (int)(pivot / (uint64_t)n); wd = n - 1 - (int)(pivot % (uint64_t)n); death = SD[Md]; }
       if (essential || death > birth) {
         if (tid == 0) {
           out[2 * nrows] = birth; out[2 * nrows + 1] = death;
           if (outs) {
-            uint32_t e = EN[rbirth];
+            const uint32_t e = EN[rbirth];
             outs[2 * nrows] = edge_index((int)(e >> 16), (int)(e & 0xffffu));
             if (essential) outs[2 * nrows + 1] = -1;
             else {
-              uint32_t em = EN[Md];
+              const uint32_t em = EN[Md];
               int x = (int)(em >> 16), y = (int)(em & 0xffffu), z = wd, t;
               if (x < y) { t = x; x = y; y = t; }
               if (y < z) { t = y; y = z; z = t; }
@@ -919,39 +787,43 @@ struct Reducer {
         }
         ++nrows;
       }
-      v_clear();
-      heap_release();
+      v_clear();   // also makes the hash / vpool writes of thread 0 visible block-wide (barriers inside)
+      __threadfence();
       cyc[5] += clock64() - t0;
     }
     __syncthreads();
-    if (S.abort_flag) {  // leave the scratch clean for the next problem
+    if (S.abort_flag) {  // leave the scratch clean for the next problem: wipe the whole window
       v_compact();
       v_clear();
-      heap_release();
+      for (uint64_t i = tid; i < (wbits >> 5); i += kReduceThreads) bits[i] = 0;
+      for (uint32_t i = tid; i < s1words; i += kReduceThreads) s1[i] = 0;
+      for (uint32_t i = tid; i < (uint32_t)kNearWords; i += kReduceThreads) S.nearw[i] = 0;
+      __threadfence();
+      __syncthreads();
     }
+    atomicAdd(&S.toggles, my_toggles);
+    __syncthreads();
     if (tid == 0) {
       P.counts[p * 4 + 1] = nrows;
       P.counts[p * 4 + 3] = S.abort_flag;
       st[ST_REDUCED] = (unsigned long long)nb;
       st[ST_ADDITIONS] = additions;
-      st[ST_PUSHES] = S.pushes;
-      st[ST_POPS] = S.pops;
-      st[ST_EXTENSIONS] = extensions;
+      st[ST_PUSHES] = S.toggles;
+      st[ST_POPS] = pops;
+      st[ST_EXTENSIONS] = slides + n_refills;
       st[ST_MAXV] = maxv;
       for (int q = 0; q < 6; ++q) st[ST_CYC_EXTRACT + q] = (unsigned long long)cyc[q];
       st[ST_BADD_EDGES] = badd_edges;
-      st[ST_EXT_EDGES] = ext_edges;
+      st[ST_EXT_EDGES] = ext_edges + n_passes;
     }
     __syncthreads();
   }
 };
 
-template <typename K>
-__global__ void __launch_bounds__(kReduceThreads, 1) reduce_kernel(ReduceParams P) {
-  __shared__ ReduceSmem<K> S;
-  Reducer<K> red(P, S);
-  if (threadIdx.x == 0) { S.freehead = kNil; S.fcache_n = 0; S.nzmask[0] = S.nzmask[1] = S.nzmask[2] = 0; }
-  __syncthreads();
+__global__ void __launch_bounds__(kReduceThreads) rips_reduce_kernel(const __grid_constant__ ReduceParams P) {
+  __shared__ ReduceSmem S;
+  extern __shared__ uint32_t s1_dyn[];
+  Reducer red(P, S, s1_dyn);
   for (;;) {
     if (threadIdx.x == 0) S.problem = atomicAdd(P.work_counter, 1);
     __syncthreads();
@@ -981,15 +853,14 @@ struct Layout {
   uint32_t *vals_a, *vals_b;
   void* cub_tmp; size_t cub_bytes;
   int* rank; uint32_t* ends; float* sdist; uint32_t* thresh_bits; int* T;
-  uint8_t* mst; int* mstlist; int* apex; int* blist; int* bcount;
+  uint8_t* mst; int* mstlist; int* apex; uint2* ea; int* blist; int* bcount;
   uint32_t *comp, *parent, *cbest; int* done;
   uint32_t* vbits; int64_t vwords; uint32_t* vlist; int64_t vcap;
-  void* hkeys; int* hvals; int hcap;
+  uint64_t* hkeys; int* hvals; int hcap;
   uint32_t* vpool; int64_t vpool_cap; int64_t* vstart; int* vlen;
-  void* pool_keys; uint32_t* pool_next; uint32_t pool_chunks; unsigned int* pool_top;
+  uint32_t* bits; uint64_t wbits;   // per-CTA key windows
   int* work_counter; unsigned long long* stats;
   int grid; size_t total;
-  bool wide;  // 64-bit triangle keys
 };
 
 static int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
@@ -1000,7 +871,6 @@ static Layout make_layout(void* ws, int n, int batch, int maxdim, int cap1, size
   const int64_t E = (int64_t)n * (n - 1) / 2;
   const int64_t BE = (int64_t)batch * E;
   Carver c(ws, ~size_t(0));
-  L.wide = ((double)E * (double)n >= 4294967295.0);
   L.keys_a = c.take<uint64_t>(BE);
   L.keys_b = c.take<uint64_t>(BE);
   L.vals_a = c.take<uint32_t>(BE);
@@ -1024,6 +894,7 @@ static Layout make_layout(void* ws, int n, int batch, int maxdim, int cap1, size
   L.work_counter = c.take<int>(1);
   if (maxdim >= 1) {
     L.apex = c.take<int>(BE);
+    L.ea = c.take<uint2>(BE);
     L.blist = c.take<int>((int64_t)batch * cap1);
     L.bcount = c.take<int>(batch);
     L.grid = batch < 2 * sm_count ? batch : 2 * sm_count;
@@ -1033,21 +904,23 @@ static Layout make_layout(void* ws, int n, int batch, int maxdim, int cap1, size
     L.vcap = E + 1024;
     L.vlist = c.take<uint32_t>((int64_t)L.grid * 2 * L.vcap);
     L.hcap = next_pow2(2 * cap1);
-    L.hkeys = L.wide ? (void*)c.take<uint64_t>((int64_t)batch * L.hcap) : (void*)c.take<uint32_t>((int64_t)batch * L.hcap);
+    L.hkeys = c.take<uint64_t>((int64_t)batch * L.hcap);
     L.hvals = c.take<int>((int64_t)batch * L.hcap);
-    L.vpool_cap = (int64_t)(pool_bytes / 8 / (size_t)batch / sizeof(uint32_t));
-    if (L.vpool_cap < 4 * (int64_t)cap1) L.vpool_cap = 4 * (int64_t)cap1;
-    L.vpool = c.take<uint32_t>((int64_t)batch * L.vpool_cap);
     L.vstart = c.take<int64_t>((int64_t)batch * cap1);
     L.vlen = c.take<int>((int64_t)batch * cap1);
-    const size_t ksz = L.wide ? 8 : 4;
-    size_t chunks = pool_bytes / (kChunk * ksz);
-    if (chunks < (size_t)L.grid * 80) chunks = (size_t)L.grid * 80;
-    if (chunks > 0x7ffffff0u) chunks = 0x7ffffff0u;
-    L.pool_chunks = (uint32_t)chunks;
-    L.pool_keys = c.take<char>((chunks + 1) * kChunk * ksz);
-    L.pool_next = c.take<uint32_t>(chunks + 1);
-    L.pool_top = c.take<unsigned int>(1);
+    // key windows: the whole key space E*n when it fits in 2^32 bits and in the pool, else a sliding window
+    const uint64_t page = 1ull << kPageShift;
+    uint64_t want = ((uint64_t)E * (uint64_t)n + 32 * page - 1) / (32 * page) * (32 * page);
+    if (want > (1ull << 32)) want = 1ull << 32;
+    uint64_t afford = (uint64_t)(pool_bytes / 2 / (size_t)L.grid) * 8 / (32 * page) * (32 * page);
+    if (afford < 32 * page) afford = 32 * page;
+    L.wbits = want < afford ? want : afford;
+    L.bits = c.take<uint32_t>((size_t)L.grid * (L.wbits >> 5));
+    // reduction columns (V) of finished columns: whatever the pool leaves, at least 4 * cap1 entries per cloud
+    const size_t bits_bytes = (size_t)L.grid * (L.wbits >> 3);
+    L.vpool_cap = pool_bytes > bits_bytes ? (int64_t)((pool_bytes - bits_bytes) / (size_t)batch / sizeof(uint32_t)) : 0;
+    if (L.vpool_cap < 4 * (int64_t)cap1) L.vpool_cap = 4 * (int64_t)cap1;
+    L.vpool = c.take<uint32_t>((int64_t)batch * L.vpool_cap);
   }
   L.total = c.off;
   return L;
@@ -1071,6 +944,7 @@ using namespace tda::rips;
 extern "C" int tda_pdist_lowdim(const float* pts, int n, int d, int batch, float* dm, void* stream) {
   if (!pts || !dm || n <= 0 || d <= 0 || d > 64 || batch <= 0) return set_error(TDA_ERR_INVALID, "tda_pdist_lowdim: bad arguments");
   dim3 block(32, 8), grid((n + 31) / 32, (n + 7) / 8, batch);
+  StageScope st(STAGE_RIPS_PDIST, (cudaStream_t)stream);
   pdist_lowdim_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(pts, n, d, dm);
   count_launch();
   TDA_LAUNCH_CHECK();
@@ -1101,6 +975,7 @@ extern "C" int tda_rips(const float* dm, int n, int batch, int maxdim, float thr
   const int64_t E = (int64_t)n * (n - 1) / 2;
   const int64_t BE = (int64_t)batch * E;
 
+  stage_begin_if(STAGE_RIPS_SORT, stream);
   TDA_CUDA_CHECK(cudaMemsetAsync(L.T, 0, sizeof(int) * batch, stream));
   TDA_CUDA_CHECK(cudaMemsetAsync(L.stats, 0, sizeof(unsigned long long) * batch * ST_N, stream));
   TDA_CUDA_CHECK(cudaMemsetAsync(L.work_counter, 0, sizeof(int), stream));
@@ -1134,8 +1009,10 @@ extern "C" int tda_rips(const float* dm, int n, int batch, int maxdim, float thr
     rank_diag_kernel<<<g, 256, 0, stream>>>(n, L.rank);
     count_launch();
   }
+  stage_end_if(STAGE_RIPS_SORT, stream);
   TDA_CUDA_CHECK(cudaMemsetAsync(L.mst, 0, (size_t)(BE > 0 ? BE : 1), stream));
   {
+    StageScope st(STAGE_RIPS_H0, stream);
     dim3 gi((n + 255) / 256, batch);
     boruvka_init_kernel<<<gi, 256, 0, stream>>>(n, L.comp, L.cbest, L.done);
     count_launch();
@@ -1154,23 +1031,30 @@ extern "C" int tda_rips(const float* dm, int n, int batch, int maxdim, float thr
   }
   if (maxdim >= 1 && E > 0) {
     TDA_CUDA_CHECK(cudaMemsetAsync(L.bcount, 0, sizeof(int) * batch, stream));
-    TDA_CUDA_CHECK(cudaMemsetAsync(L.pool_top, 0, sizeof(unsigned int), stream));
+    TDA_CUDA_CHECK(cudaMemsetAsync(L.bits, 0, (size_t)L.grid * (L.wbits >> 3), stream));
     TDA_CUDA_CHECK(cudaMemsetAsync(L.vbits, 0, sizeof(uint32_t) * (size_t)L.grid * L.vwords, stream));
     dim3 g((unsigned)((E * 32 + 255) / 256), batch);
-    apparent_kernel<<<g, 256, 0, stream>>>(L.rank, L.ends, L.mst, L.T, n, E, L.apex, L.blist, L.bcount, cap1p, L.stats);
+    {
+      StageScope st(STAGE_RIPS_APPARENT, stream);
+      apparent_kernel<<<g, 256, 0, stream>>>(L.rank, L.ends, L.mst, L.T, n, E, L.apex, L.ea, L.blist, L.bcount, cap1p, L.stats);
+    }
     count_launch();
     TDA_LAUNCH_CHECK();
     ReduceParams P;
-    P.rank = L.rank; P.ends = L.ends; P.sdist = L.sdist; P.T = L.T; P.apex = L.apex; P.blist = L.blist; P.bcount = L.bcount;
+    P.rank = L.rank; P.ends = L.ends; P.sdist = L.sdist; P.T = L.T; P.ea = L.ea; P.blist = L.blist; P.bcount = L.bcount;
     P.n = n; P.E = E; P.batch = batch; P.cap1 = cap1p;
     P.h1_pairs = h1_pairs; P.h1_simplex = h1_simplex; P.counts = counts;
     P.vbits = L.vbits; P.vwords = L.vwords; P.vlist = L.vlist; P.vcap = L.vcap;
     P.hkeys = L.hkeys; P.hvals = L.hvals; P.hcap = L.hcap;
+    P.bits = L.bits; P.wbits = L.wbits;
     P.vpool = L.vpool; P.vpool_cap = L.vpool_cap; P.vstart = L.vstart; P.vlen = L.vlen;
-    P.pool_keys = L.pool_keys; P.pool_next = L.pool_next; P.pool_chunks = L.pool_chunks; P.pool_top = L.pool_top;
     P.work_counter = L.work_counter; P.stats = L.stats;
-    if (L.wide) reduce_kernel<uint64_t><<<L.grid, kReduceThreads, 0, stream>>>(P);
-    else reduce_kernel<uint32_t><<<L.grid, kReduceThreads, 0, stream>>>(P);
+    {
+      StageScope st(STAGE_RIPS_REDUCE, stream);
+      const size_t s1_bytes = (size_t)(((L.wbits >> kPageShift) + 31) / 32) * sizeof(uint32_t);
+      TDA_CUDA_CHECK(cudaFuncSetAttribute(rips_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1_bytes));
+      rips_reduce_kernel<<<L.grid, kReduceThreads, s1_bytes, stream>>>(P);
+    }
     count_launch();
     TDA_LAUNCH_CHECK();
     finalize_stats_kernel<<<(batch + 255) / 256, 256, 0, stream>>>(L.T, L.bcount, n, batch, L.stats, counts);

@@ -345,6 +345,7 @@ extern "C" int tda_graph_components(const int32_t* head, const int32_t* tail, co
   if (!head || !tail || !weight || !eps || !comp || !ncomp || !comp_size || !degree || !ws || n <= 0 || batch <= 0)
     return set_error(TDA_ERR_INVALID, "tda_graph_components: bad arguments");
   if (ws_bytes < sizeof(int) * (size_t)batch * n) return set_error(TDA_ERR_WORKSPACE, "tda_graph_components: workspace too small");
+  StageScope st(STAGE_SPECTRAL, stream);
   components_kernel<<<batch, 1024, 0, stream>>>(head, tail, weight, eps, slots, n, (int*)ws, comp, degree, ncomp, comp_size);
   count_launch();
   TDA_LAUNCH_CHECK();
@@ -365,6 +366,7 @@ extern "C" int tda_spectral_embed(const int32_t* head, const int32_t* tail, cons
   P.comp = comp; P.deg = degree; P.ncomp = ncomp; P.csize = comp_size;
   P.Q = L.Q; P.out = Y; P.evals = evals ? evals : L.evals; P.maxcomp = maxcomp; P.min_size = min_size; P.seed = seed;
   dim3 grid(maxcomp, batch);
+  StageScope st(STAGE_SPECTRAL, stream);
   lanczos_kernel<<<grid, kLanczosThreads, 0, stream>>>(P);
   count_launch();
   TDA_LAUNCH_CHECK();

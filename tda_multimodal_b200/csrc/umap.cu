@@ -369,6 +369,7 @@ extern "C" int tda_knn_smooth(const float* D, int n, int m, int batch, int k, fl
   if (k > 256) return set_error(TDA_ERR_UNSUPPORTED, "tda_knn_smooth: k=%d > 256", k);
   if (ws_bytes < sizeof(double) * (size_t)batch) return set_error(TDA_ERR_WORKSPACE, "tda_knn_smooth: workspace too small");
   double* dist_sum = (double*)ws;
+  StageScope st(STAGE_KNN_SMOOTH, stream);
   TDA_CUDA_CHECK(cudaMemsetAsync(dist_sum, 0, sizeof(double) * batch, stream));
   dim3 grid((n + 7) / 8, batch);
   const int kpl = (k + 31) / 32;
@@ -391,6 +392,7 @@ extern "C" int tda_fuzzy_graph(const int32_t* knn_idx, const float* knn_dist, co
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!knn_idx || !knn_dist || !sigma || !rho || !head || !tail || !weight || !eps || !max_weight || n <= 0 || k <= 0 || batch <= 0)
     return set_error(TDA_ERR_INVALID, "tda_fuzzy_graph: bad arguments");
+  StageScope st(STAGE_FUZZY, stream);
   TDA_CUDA_CHECK(cudaMemsetAsync(max_weight, 0, sizeof(float) * batch, stream));
   dim3 g((n * k + 255) / 256, batch);
   fuzzy_kernel<<<g, 256, 0, stream>>>(knn_idx, knn_dist, sigma, rho, n, k, mix_ratio, head, tail, weight, (unsigned int*)max_weight);
@@ -410,6 +412,7 @@ extern "C" int tda_umap_sgd(float* Y, const float* Y_other, const int32_t* head,
   if (!move_other && !Y_other) return set_error(TDA_ERR_INVALID, "tda_umap_sgd: Y_other required when move_other=0");
   if (dim < 1 || dim > 4) return set_error(TDA_ERR_UNSUPPORTED, "tda_umap_sgd: n_components=%d (supported: 1..4)", dim);
   dim3 g((slots + 255) / 256, batch);
+  StageScope st(STAGE_SGD, stream);
   for (int ep = 0; ep < n_epochs; ++ep) {
     const float alpha = ep == 0 ? alpha0 : alpha0 * (1.f - (float)(ep - 1) / (float)n_epochs);
 #define TDA_SGD_LAUNCH(DIM) sgd_epoch_kernel<DIM><<<g, 256, 0, stream>>>(Y, Y_other, head, tail, eps, slots, n_head, n_tail, ep, a, b, gamma, alpha, negative_sample_rate, move_other, seed)

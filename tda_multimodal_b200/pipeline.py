@@ -1,0 +1,128 @@
+"""The per-layer TDA sweep of the reference as ONE batched device pipeline.
+
+Reference: the hot loop ``for i in tqdm(range(N_LAYERS))`` of debug_tda_pipeline.py:92-131 (same body in
+analyze_adversarial_tda.py:82-123): per layer  X[N,hidden] -> umap.UMAP(n_neighbors, n_components=3, min_dist=0.1,
+random_state=42, metric='cosine').fit_transform -> ripser(Y, maxdim=1)['dgms'] -> get_persistence -> stats record.
+The layers are independent (no carried state but the append-only stats list, :131), so here all layers of a
+rank go through each kernel together (batch dimension = layer), and ranks split the layers (layer l -> rank
+l mod G) with a single gather of the diagrams at the end.
+"""
+import numpy as np
+
+from . import _lib
+from .rips import pdist_lowdim, rips_batch
+from .umap_ import umap_fit_batch
+
+
+def get_persistence(dgm):
+    """debug_tda_pipeline.py:79-89 (verbatim semantics): finite persistence values and their max."""
+    if dgm.shape[0] == 0:
+        return np.array([]), 0.0
+    pers = dgm[:, 1] - dgm[:, 0]
+    pers = pers[np.isfinite(pers)]
+    if pers.shape[0] == 0:
+        return np.array([]), 0.0
+    return pers, np.max(pers)
+
+
+def stats_record(layer, dgms):
+    """The H0/H1 fields of one summary_stats.json record, in the reference's key order (debug_tda_pipeline.py:121-131);
+    the two silhouette fields are appended by the caller that has the labels."""
+    h0_pers, max_h0 = get_persistence(dgms[0])
+    h1_pers, max_h1 = get_persistence(dgms[1]) if len(dgms) > 1 else (np.array([]), 0.0)
+    return {"layer": int(layer), "n_h1_features": len(h1_pers), "max_h1_persistence": float(max_h1),
+            "all_h1_persistence_values": h1_pers.tolist(), "n_h0_features": len(dgms[0]) - len(h0_pers),
+            "max_h0_persistence": float(max_h0)}
+
+
+def layer_sweep(X, n_neighbors=15, n_components=3, min_dist=0.1, metric="cosine", random_state=42, maxdim=1, n_epochs=None,
+                return_embedding=True):
+    """UMAP + Rips for a stack of layers resident on the device.  X [L,n,d] float32 CUDA tensor.
+    Returns {'embedding': [L,n,n_components] CUDA tensor, 'results': [L dicts with 'dgms', 'num_edges', 'thresh']}."""
+    _lib.require_cuda()
+    Y = umap_fit_batch(X, n_neighbors=n_neighbors, n_components=n_components, metric=metric, min_dist=min_dist,
+                       random_state=random_state, n_epochs=n_epochs)
+    dm = pdist_lowdim(Y)
+    res = rips_batch(dm, maxdim=maxdim)
+    return {"embedding": Y if return_embedding else None, "results": res}
+
+
+def layer_sweep_host(X_host, device=None, **kw):
+    """The call a user of the reference makes, with HOST buffers: X_host [L,n,d] float32/float64 numpy array or a
+    (pinned) CPU torch tensor.  Copies to the device, runs layer_sweep, returns host results
+    ({'embedding': float32 ndarray [L,n,3], 'results': [...]})."""
+    torch = _lib.require_cuda()
+    Xt = X_host if isinstance(X_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(X_host))
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    Xd = Xt.to(device=dev, dtype=torch.float32, non_blocking=True)
+    out = layer_sweep(Xd, **kw)
+    out["embedding"] = out["embedding"].cpu().numpy() if out["embedding"] is not None else None
+    return out
+
+
+# ---- diagram exchange between ranks ---------------------------------------------------------------------------
+def pack_diagrams(results, maxdim=1):
+    """list of per-unit result dicts -> (counts [U, maxdim+1] int32, payload [sum,2] float32), unit-major, dim-minor."""
+    counts = np.zeros((len(results), maxdim + 1), dtype=np.int32)
+    rows = []
+    for u, r in enumerate(results):
+        for q in range(maxdim + 1):
+            d = np.asarray(r["dgms"][q], dtype=np.float32).reshape(-1, 2)
+            counts[u, q] = d.shape[0]
+            rows.append(d)
+    payload = np.concatenate(rows, axis=0) if rows else np.zeros((0, 2), np.float32)
+    return counts, np.ascontiguousarray(payload, dtype=np.float32)
+
+
+def unpack_diagrams(counts, payload):
+    out, off = [], 0
+    for u in range(counts.shape[0]):
+        dgms = []
+        for q in range(counts.shape[1]):
+            c = int(counts[u, q])
+            dgms.append(payload[off:off + c].astype(np.float64))
+            off += c
+        out.append(dgms)
+    return out
+
+
+def shard_units(n_units, rank, world):
+    """unit u -> rank u mod world."""
+    return list(range(rank, n_units, world))
+
+
+def gather_diagrams(local_units, local_results, n_units, maxdim=1, group=None, device=None):
+    """All ranks contribute the diagrams of their units; every rank gets the full list (unit order).  Two
+    collectives: all_gather of the per-unit counts, all_gather of the padded [pairs,2] payload.  Works on NCCL
+    (device tensors) and on gloo (CPU tensors; used by the CPU tests)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        full = [None] * n_units
+        for u, r in zip(local_units, local_results):
+            full[u] = r["dgms"]
+        return full
+    world = dist.get_world_size(group)
+    backend = dist.get_backend(group)
+    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu"))
+    counts, payload = pack_diagrams(local_results, maxdim)
+    per_rank = (n_units + world - 1) // world
+    cpad = np.zeros((per_rank, maxdim + 1), dtype=np.int32)
+    cpad[:counts.shape[0]] = counts
+    ct = torch.from_numpy(cpad).to(dev)
+    all_counts = [torch.empty_like(ct) for _ in range(world)]
+    dist.all_gather(all_counts, ct, group=group)
+    all_counts = [c.cpu().numpy() for c in all_counts]
+    max_rows = max(int(c.sum()) for c in all_counts)
+    ppad = np.zeros((max(max_rows, 1), 2), dtype=np.float32)
+    ppad[:payload.shape[0]] = payload
+    pt = torch.from_numpy(ppad).to(dev)
+    all_payload = [torch.empty_like(pt) for _ in range(world)]
+    dist.all_gather(all_payload, pt, group=group)
+    full = [None] * n_units
+    for r in range(world):
+        units = shard_units(n_units, r, world)
+        dg = unpack_diagrams(all_counts[r][:len(units)], all_payload[r].cpu().numpy())
+        for u, d in zip(units, dg):
+            full[u] = d
+    return full

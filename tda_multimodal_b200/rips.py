@@ -44,8 +44,15 @@ def rips_batch(dm, maxdim=1, thresh=float("inf"), cap1=None, pool_bytes=None, wa
     B, n, _ = dm.shape
     dev = dm.device
     cap1 = _next_pow2(cap1 or max(64, 4 * n))
-    pool_bytes = int(pool_bytes or max(64 << 20, 64 * n * n * min(B, 8)))
     free_bytes = torch.cuda.mem_get_info(dev)[0]
+    if pool_bytes is None:
+        # half of the pool holds one key window (bitset over the E*n triangle keys, <= 2^32 bits) per resident CTA,
+        # the other half the reduction columns of finished columns; capped so that large batches slide windows instead
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        grid = min(B, 2 * sms)
+        window = min(-(-(n * (n - 1) // 2 * n) // 8), 1 << 29)
+        pool_bytes = max(64 << 20, min(2 * grid * window, int(0.35 * free_bytes)))
+    pool_bytes = int(pool_bytes)
     with torch.cuda.device(dev):
         while True:
             ws_bytes = int(L.tda_rips_workspace_bytes(n, B, maxdim, cap1, pool_bytes))
@@ -60,7 +67,7 @@ def rips_batch(dm, maxdim=1, thresh=float("inf"), cap1=None, pool_bytes=None, wa
                               cap1, _lib.ptr(counts), _lib.ptr(th), _lib.ptr(ws), ws_bytes, pool_bytes, _lib.stream_ptr())
             if code == _lib.TDA_ERR_CAPACITY and pool_bytes < free_bytes // 2:
                 cap1 *= 2
-                pool_bytes *= 4
+                pool_bytes *= 2
                 del ws
                 continue
             _lib.check(code)
