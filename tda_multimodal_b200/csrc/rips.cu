@@ -23,6 +23,8 @@
 #include "../../include/tda_b200.h"
 #include <cub/device/device_radix_sort.cuh>
 #include <cfloat>
+#include <cstdlib>
+#include <cstring>
 #include <cmath>
 
 namespace tda {
@@ -333,7 +335,8 @@ struct ReduceParams {
   int n; int64_t E; int batch; int cap1;
   float* h1_pairs; int64_t* h1_simplex; int32_t* counts;
   // per-CTA scratch
-  uint32_t* bits; uint64_t wbits;           // [grid, wbits/32]  (all zero between columns)
+  uint32_t* bits; uint64_t wbits;           // [grid, wbits/32]  (all zero between columns)   (bitset reducer)
+  uint32_t* xmat; int xw;                   // [grid, n, xw]  V as a symmetric bit matrix    (sweep reducer)
   uint32_t* vbits; int64_t vwords;          // [grid, vwords]
   uint32_t* vlist; int64_t vcap;            // [grid, 2, vcap]
   // per-problem
@@ -834,6 +837,531 @@ __global__ void __launch_bounds__(kReduceThreads) rips_reduce_kernel(const __gri
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// residual reduction, ROW-SWEEP formulation (the default)
+//
+// The same reduction (ripser's order, same pivots, same V's), organised around the rows of the key space instead
+// of around the keys: row M = all triangles whose longest edge has rank M, one bit per opposite vertex.  With
+// X = V as a symmetric n x n bit matrix (x_e = X[a][b]), the working column restricted to row M=(c,d) is
+//        r(M) = ( x_M * 1  ^  X[c][.]  ^  X[d][.] )  &  lune(M),      lune(M) = { w : rank(c,w) < M and rank(d,w) < M }
+// so a row costs a few word-parallel bit operations instead of n scattered atomics per added edge, and rows whose
+// endpoints are not incident to V ("untouched") are zero and are skipped by a streaming filter over the edge list.
+// The column walks the rows upward from its birth edge; inside a row the lowest key is the highest vertex:
+// apparent pivot (w == apex[M]) -> x_M flips, r ^= lune;  pivot owned by a reduced column -> X ^= V_owner and the
+// row is recomputed;  unowned pivot -> death.  Per CTA: 16 warps compute 16 heavy rows at a time (lune words by
+// coalesced rank-row loads + ballot), warp 0 then resolves them in order from shared memory and patches the later
+// rows of the group for every flip, so the dependent chain of pivots costs ~100 cycles per pivot instead of a
+// global-memory round trip per step.
+constexpr int kSweepThreads = 512;
+constexpr int kSweepWarps = kSweepThreads / 32;
+constexpr int kGroupRows = 32;                    // heavy rows resolved per group (one lane of the resolver per row)
+constexpr int kChunkRows = kSweepThreads;         // rows filtered per pass
+enum { SW_DONE = 0, SW_RESTART = 1, SW_REDUCED = 2, SW_DEATH = 3 };
+
+struct SweepSmem {
+  uint2 chunk_ea[kChunkRows];
+  uint32_t heavy[kChunkRows];
+  uint32_t wcnt[kSweepWarps];
+  uint32_t row_rank[2][kGroupRows], row_c[2][kGroupRows], row_d[2][kGroupRows];
+  int row_apex[2][kGroupRows];
+  uint32_t dirty;      // bit s: row s of the current group has a non-zero working row
+  uint32_t nheavy;
+  uint32_t vcount, vcount2, vsel;
+  int abort_flag, problem;
+  int res_status, res_s, res_owner;
+  uint32_t res_w;
+  unsigned long long additions, pivots, heavy_rows, restarts, groups, t_res;
+};
+
+template <int WPL>   // words of a row per lane of the resolver (W <= 32 * WPL)
+struct Sweeper {
+  static constexpr uint64_t kEmpty = ~0ull;
+  static constexpr bool getenv_diag = false;
+  const ReduceParams& P;
+  SweepSmem& S;
+  uint32_t* touched;   // [W]
+  uint32_t* Sr;        // [kGroupRows][W]      working rows of the current group
+  uint32_t* Slm;       // [2][kGroupRows][W]   lune masks, double buffered (the next group's are produced during the resolve)
+  const int tid, lane, warp;
+  const int* R; const uint32_t* EN; const uint2* EA; int T; int n; int W;
+  uint32_t* X; uint32_t* vbits; uint32_t* vl0;
+  uint64_t* hkeys; int* hvals;
+
+  __device__ Sweeper(const ReduceParams& p, SweepSmem& s, uint32_t* dyn)
+      : P(p), S(s), tid(threadIdx.x), lane(threadIdx.x & 31), warp(threadIdx.x >> 5) {
+    n = P.n;
+    W = P.xw;
+    touched = dyn;
+    Sr = dyn + W;
+    Slm = Sr + (size_t)kGroupRows * W;
+    X = P.xmat + (size_t)blockIdx.x * (size_t)n * W;
+    vbits = P.vbits + (size_t)blockIdx.x * P.vwords;
+    vl0 = P.vlist + (size_t)blockIdx.x * 2 * P.vcap;
+  }
+  __device__ __forceinline__ uint32_t* vlist(uint32_t sel) const { return vl0 + (size_t)sel * P.vcap; }
+  __device__ __forceinline__ bool tbit(uint32_t v) const { return (touched[v >> 5] >> (v & 31)) & 1u; }
+
+  // ---- V bookkeeping (same scheme as the bitset reducer: parity bits + a list that may hold duplicates)
+  __device__ __forceinline__ void v_toggle(int re) {
+    atomicXor(&vbits[(uint32_t)re >> 5], 1u << (re & 31));
+    const uint32_t pos = atomicAdd(&S.vcount, 1u);
+    if (pos < (uint32_t)P.vcap) vlist(S.vsel)[pos] = (uint32_t)re;
+    else S.abort_flag = TDA_ERR_CAPACITY;
+  }
+  __device__ __forceinline__ void x_flip(uint32_t c, uint32_t d) {
+    atomicXor(&X[(size_t)c * W + (d >> 5)], 1u << (d & 31));
+    atomicXor(&X[(size_t)d * W + (c >> 5)], 1u << (c & 31));
+  }
+  __device__ __forceinline__ void v_compact() {
+    __syncthreads();
+    const uint32_t nin = min(S.vcount, (uint32_t)P.vcap);
+    const uint32_t* src = vlist(S.vsel);
+    uint32_t* dst = vlist(S.vsel ^ 1);
+    if (tid == 0) S.vcount2 = 0;
+    __syncthreads();
+    for (uint32_t i0 = 0; i0 < nin; i0 += kSweepThreads) {
+      const uint32_t i = i0 + tid;
+      bool keep = false;
+      uint32_t e = 0;
+      if (i < nin) {
+        e = src[i];
+        const uint32_t m = 1u << (e & 31);
+        keep = (atomicAnd(&vbits[e >> 5], ~m) & m) != 0;
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      uint32_t bs = 0;
+      if (lane == 0 && bal) bs = atomicAdd(&S.vcount2, (uint32_t)__popc(bal));
+      bs = __shfl_sync(0xffffffffu, bs, 0);
+      if (keep) dst[bs + __popc(bal & ((1u << lane) - 1))] = e;
+    }
+    __syncthreads();
+    const uint32_t nout = S.vcount2;
+    for (uint32_t i = tid; i < nout; i += kSweepThreads) {
+      const uint32_t e = dst[i];
+      atomicOr(&vbits[e >> 5], 1u << (e & 31));
+    }
+    __syncthreads();
+    if (tid == 0) { S.vsel ^= 1; S.vcount = nout; }
+    __syncthreads();
+  }
+  // after v_compact: clear the parity bits, the X bits of every edge of V and the touched mask; empty the list
+  __device__ __forceinline__ void v_clear() {
+    const uint32_t nin = S.vcount;
+    const uint32_t* src = vlist(S.vsel);
+    for (uint32_t i = tid; i < nin; i += kSweepThreads) {
+      const uint32_t e = src[i];
+      atomicAnd(&vbits[e >> 5], ~(1u << (e & 31)));
+      const uint32_t en = __ldg(&EN[e]);
+      x_flip(en >> 16, en & 0xffffu);
+    }
+    for (int i = tid; i < W; i += kSweepThreads) touched[i] = 0;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) S.vcount = 0;
+    __syncthreads();
+  }
+  __device__ __forceinline__ int hash_find(uint64_t key) const {
+    uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32) & (uint32_t)(P.hcap - 1);
+    for (;;) {
+      const uint64_t k = hkeys[h];
+      if (k == key) return hvals[h];
+      if (k == kEmpty) return -1;
+      h = (h + 1) & (uint32_t)(P.hcap - 1);
+    }
+  }
+  __device__ __forceinline__ void hash_insert(uint64_t key, int val) {  // thread 0
+    uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32) & (uint32_t)(P.hcap - 1);
+    while (hkeys[h] != kEmpty) h = (h + 1) & (uint32_t)(P.hcap - 1);
+    hkeys[h] = key;
+    hvals[h] = val;
+  }
+  __device__ __forceinline__ void sort_blist(int* bl, int nb) {
+    int np2 = 1;
+    while (np2 < nb) np2 <<= 1;
+    for (int i = nb + tid; i < np2; i += kSweepThreads) bl[i] = 0x7fffffff;
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < np2; i += kSweepThreads) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const int a = bl[i], b = bl[ixj];
+            const bool up = ((i & k) == 0);
+            if ((a > b) == up) { bl[i] = b; bl[ixj] = a; }
+          }
+        }
+        __syncthreads();
+      }
+  }
+
+  // ---- lune masks of the heavy rows [i, i + ns) of the chunk at `pos` into buffer `buf`; rows are dealt round-robin to
+  // the warps [wfirst, wfirst + nw).  lune(M=(c,d)) = { w : rank(c,w) < M and rank(d,w) < M }: coalesced rank-row loads
+  // (all of a 32-word block in flight at once) + ballot; independent of V, so it runs ahead of the resolver.
+  __device__ __forceinline__ void produce_lune(int buf, uint32_t pos, uint32_t i, int ns, int wfirst, int nw) {
+    for (int sl = warp - wfirst; sl < ns; sl += nw) {
+      const uint32_t hidx = S.heavy[i + sl];
+      const uint2 ea = S.chunk_ea[hidx];
+      const uint32_t Mrow = pos + hidx;
+      const uint32_t c = ea.x >> 16, d = ea.x & 0xffffu;
+      const int* Rc = R + (size_t)c * n;
+      const int* Rd = R + (size_t)d * n;
+      uint32_t* lm = Slm + ((size_t)buf * kGroupRows + sl) * W;
+      for (int k0 = 0; k0 < W; k0 += 32) {
+        int ra[32], rb[32];
+#pragma unroll
+        for (int kk = 0; kk < 32; ++kk) {
+          const int w = (k0 + kk) * 32 + lane;
+          const bool ok = (k0 + kk) < W && w < n;
+          ra[kk] = ok ? __ldg(&Rc[w]) : kRankDiag;
+          rb[kk] = ok ? __ldg(&Rd[w]) : kRankDiag;
+        }
+        uint32_t lmine = 0;
+#pragma unroll
+        for (int kk = 0; kk < 32; ++kk) {
+          const unsigned word = __ballot_sync(0xffffffffu, ra[kk] < (int)Mrow && rb[kk] < (int)Mrow);
+          if (lane == kk) lmine = word;
+        }
+        if (k0 + lane < W) lm[k0 + lane] = lmine;
+      }
+      if (lane == 0) { S.row_rank[buf][sl] = Mrow; S.row_c[buf][sl] = c; S.row_d[buf][sl] = d; S.row_apex[buf][sl] = (int)ea.y; }
+    }
+  }
+
+  // ---- working rows of the group: r = (x_M ^ X[c] ^ X[d]) & lune, from the CURRENT X (all flips of earlier groups are fenced)
+  __device__ __forceinline__ void form_rows(int buf, int ns) {
+    for (int sl = warp; sl < ns; sl += kSweepWarps) {
+      const uint32_t c = S.row_c[buf][sl], d = S.row_d[buf][sl];
+      const uint32_t* Xc = X + (size_t)c * W;
+      const uint32_t* Xd = X + (size_t)d * W;
+      const uint32_t* lm = Slm + ((size_t)buf * kGroupRows + sl) * W;
+      uint32_t* r = Sr + (size_t)sl * W;
+      const uint32_t xmw = __ldcg(&Xc[d >> 5]);
+      const uint32_t xm = ((xmw >> (d & 31)) & 1u) ? 0xffffffffu : 0u;
+      uint32_t any = 0;
+      for (int k = lane; k < W; k += 32) {
+        const uint32_t v = (xm ^ __ldcg(&Xc[k]) ^ __ldcg(&Xd[k])) & lm[k];
+        r[k] = v;
+        any |= v;
+      }
+      if (__any_sync(0xffffffffu, any != 0) && lane == 0) atomicOr(&S.dirty, 1u << sl);
+    }
+  }
+
+  // ---- warp 0: walk the dirty rows of the group in order.  The current row lives in registers (WPL words per lane);
+  // lane l also watches row l of the group for patches.  Nothing here touches global memory except the pivot hash
+  // look-up of a non-apparent pivot; the flips are written out once per group.
+  __device__ __forceinline__ void resolve(int buf, int ns) {
+    int status = SW_DONE, res_s = 0, res_owner = -1;
+    uint32_t res_w = 0;
+    uint32_t additions = 0, pivots = 0;
+    bool new_touch = false;
+    const uint32_t myc = lane < ns ? S.row_c[buf][lane] : 0xffffffffu;
+    const uint32_t myd = lane < ns ? S.row_d[buf][lane] : 0xffffffffu;
+    const uint32_t myrank = lane < ns ? S.row_rank[buf][lane] : 0u;
+    const int myapex = lane < ns ? S.row_apex[buf][lane] : -3;
+    const uint32_t* lmbase = Slm + (size_t)buf * kGroupRows * W;
+    uint32_t flipmask = 0;   // rows whose edge joined V in this group (at most once per row: its apparent key is unique)
+    uint32_t mask = S.dirty;
+    while (mask && status == SW_DONE) {
+      const int s = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const uint32_t c = __shfl_sync(0xffffffffu, myc, s), d = __shfl_sync(0xffffffffu, myd, s);
+      const int apex = __shfl_sync(0xffffffffu, myapex, s);
+      uint32_t* r = Sr + (size_t)s * W;
+      const uint32_t* lm = lmbase + (size_t)s * W;
+      uint32_t rw[WPL];
+#pragma unroll
+      for (int q = 0; q < WPL; ++q) rw[q] = (lane + 32 * q) < W ? r[lane + 32 * q] : 0u;
+      for (;;) {
+        int best = -1;
+#pragma unroll
+        for (int q = 0; q < WPL; ++q)
+          if (rw[q]) best = (lane + 32 * q) * 32 + 31 - __clz(rw[q]);   // q ascending: the last hit is this lane's highest
+        best = __reduce_max_sync(0xffffffffu, best);
+        if (best < 0) break;
+        ++pivots;
+        if (best == apex) {  // apparent pair (row edge, this triangle): the row's edge joins V; x_M flips, so r ^= lune
+          const bool nt = !tbit(c) || !tbit(d);
+          if (nt) {
+            __syncwarp();
+            if (lane == 0) {
+              touched[c >> 5] |= 1u << (c & 31);
+              touched[d >> 5] |= 1u << (d & 31);
+            }
+            new_touch = true;
+          }
+          flipmask |= 1u << s;
+#pragma unroll
+          for (int q = 0; q < WPL; ++q)
+            if ((lane + 32 * q) < W) rw[q] ^= lm[lane + 32 * q];
+          // later rows of the group that share a vertex with this edge see exactly one bit of X flip
+          bool patched = false;
+          if (lane > s) {
+            int vb = -1;
+            if (myc == c) vb = (int)d; else if (myc == d) vb = (int)c; else if (myd == c) vb = (int)d; else if (myd == d) vb = (int)c;
+            if (vb >= 0) {
+              const uint32_t m = 1u << (vb & 31);
+              if (lmbase[(size_t)lane * W + (vb >> 5)] & m) { Sr[(size_t)lane * W + (vb >> 5)] ^= m; patched = true; }
+            }
+          }
+          mask |= __ballot_sync(0xffffffffu, patched);
+          ++additions;
+          continue;
+        }
+        const uint32_t Mrow = __shfl_sync(0xffffffffu, myrank, s);
+        const uint64_t key = (uint64_t)Mrow * (uint64_t)n + (uint64_t)(n - 1 - best);
+        const int owner = hash_find(key);
+        res_s = s; res_w = (uint32_t)best; res_owner = owner;
+        status = owner < 0 ? SW_DEATH : SW_REDUCED;
+        if (owner >= 0) ++additions;
+        break;
+      }
+      if (status == SW_DONE && new_touch) { status = SW_RESTART; res_s = s; }  // rows skipped as untouched may matter now
+    }
+    __syncwarp();
+    if (flipmask) {  // write the group's flips out: X (both symmetric bits), the parity bit and the list entry, one lane per flip
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&S.vcount, (uint32_t)__popc(flipmask));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if ((flipmask >> lane) & 1u) {
+        atomicXor(&X[(size_t)myc * W + (myd >> 5)], 1u << (myd & 31));
+        atomicXor(&X[(size_t)myd * W + (myc >> 5)], 1u << (myc & 31));
+        atomicXor(&vbits[myrank >> 5], 1u << (myrank & 31));
+        const uint32_t vp = base + __popc(flipmask & ((1u << lane) - 1));
+        if (vp < (uint32_t)P.vcap) vlist(S.vsel)[vp] = myrank;
+        else S.abort_flag = TDA_ERR_CAPACITY;
+      }
+    }
+    if (lane == 0) {
+      S.res_status = status; S.res_s = res_s; S.res_owner = res_owner; S.res_w = res_w;
+      S.additions += additions; S.pivots += pivots;
+      S.dirty = 0;
+    }
+  }
+
+  __device__ __forceinline__ void run_problem(int p) {
+    R = P.rank + (size_t)p * n * n;
+    EN = P.ends + (size_t)p * P.E;
+    EA = P.ea + (size_t)p * P.E;
+    T = P.T[p];
+    hkeys = P.hkeys + (size_t)p * P.hcap;
+    hvals = P.hvals + (size_t)p * P.hcap;
+    const float* SD = P.sdist + (size_t)p * P.E;
+    int* bl = P.blist + (size_t)p * P.cap1;
+    const int nb = P.bcount[p];
+    unsigned long long* st = P.stats + (size_t)p * ST_N;
+    if (nb > P.cap1) {
+      if (tid == 0) { P.counts[p * 4 + 3] = TDA_ERR_CAPACITY; P.counts[p * 4 + 1] = 0; }
+      return;
+    }
+    sort_blist(bl, nb);
+    for (int i = tid; i < P.hcap; i += kSweepThreads) hkeys[i] = kEmpty;
+    for (int i = tid; i < W; i += kSweepThreads) touched[i] = 0;
+    if (tid == 0) {
+      S.vcount = 0; S.vsel = 0; S.abort_flag = 0; S.dirty = 0;
+      S.additions = 0; S.pivots = 0; S.heavy_rows = 0; S.restarts = 0; S.groups = 0; S.t_res = 0;
+    }
+    __threadfence();
+    __syncthreads();
+    int nrows = 0;
+    int64_t vpool_used = 0;
+    unsigned long long maxv = 0, rows_swept = 0, badd_edges = 0;
+    long long cyc[6] = {0, 0, 0, 0, 0, 0};
+    long long t0;
+    float* out = P.h1_pairs + (size_t)p * P.cap1 * 2;
+    int64_t* outs = P.h1_simplex ? P.h1_simplex + (size_t)p * P.cap1 * 2 : nullptr;
+
+    for (int ci = nb - 1; ci >= 0; --ci) {
+      const int rbirth = bl[ci];
+      {  // V = {birth edge}
+        const uint32_t en = __ldg(&EN[rbirth]);
+        const uint32_t c = en >> 16, d = en & 0xffffu;
+        if (tid == 0) {
+          x_flip(c, d);
+          v_toggle(rbirth);
+          touched[c >> 5] |= 1u << (c & 31);
+          touched[d >> 5] |= 1u << (d & 31);
+        }
+        __threadfence();
+        __syncthreads();
+      }
+      bool essential = false;
+      uint64_t pivot = 0;
+      uint32_t pos = (uint32_t)rbirth + 1;
+      for (;;) {
+        if (S.abort_flag) break;
+        if (pos >= (uint32_t)T) { essential = true; break; }
+        // ---- streaming filter over the next kChunkRows rows
+        t0 = clock64();
+        const uint32_t row = pos + tid;
+        bool heavy = false;
+        if (row < (uint32_t)T) {
+          const uint2 ea = __ldg(&EA[row]);
+          S.chunk_ea[tid] = ea;
+          heavy = tbit(ea.x >> 16) || tbit(ea.x & 0xffffu);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, heavy);
+        if (lane == 0) S.wcnt[warp] = __popc(bal);
+        __syncthreads();
+        uint32_t off = 0, total = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < kSweepWarps; ++w2) {
+          const uint32_t cw = S.wcnt[w2];
+          if (w2 < warp) off += cw;
+          total += cw;
+        }
+        if (heavy) S.heavy[off + __popc(bal & ((1u << lane) - 1))] = (uint32_t)tid;
+        __syncthreads();
+        rows_swept += min((uint32_t)kChunkRows, (uint32_t)T - pos);
+        cyc[0] += clock64() - t0;
+        const uint32_t nh = total;
+        uint32_t i = 0;
+        bool restart = false, done = false;
+        uint32_t newpos = pos + kChunkRows;
+        int buf = 0;
+        if (nh) {
+          t0 = clock64();
+          produce_lune(0, pos, 0, (int)min((uint32_t)kGroupRows, nh), 0, kSweepWarps);
+          __syncthreads();
+          cyc[1] += clock64() - t0;
+        }
+        while (i < nh) {
+          const int ns = (int)min((uint32_t)kGroupRows, nh - i);
+          t0 = clock64();
+          form_rows(buf, ns);
+          __syncthreads();
+          cyc[4] += clock64() - t0;
+          t0 = clock64();
+          if (warp == 0) { const long long tr = clock64(); resolve(buf, ns); if (lane == 0) S.t_res += clock64() - tr; }
+          else if (i + ns < nh) produce_lune(buf ^ 1, pos, i + ns, (int)min((uint32_t)kGroupRows, nh - i - ns), 1, kSweepWarps - 1);
+          __threadfence();   // the resolver's X flips are performed before the next group's rows are formed
+          __syncthreads();
+          cyc[2] += clock64() - t0;
+          const int status = S.res_status;
+          const int s = S.res_s;
+          if (tid == 0) { S.groups += 1; S.heavy_rows += (status == SW_DONE) ? ns : s + 1; }
+          if (status == SW_DONE) { i += ns; buf ^= 1; continue; }
+          const uint32_t srow = pos + S.heavy[i + s];
+          if (status == SW_RESTART) { newpos = srow + 1; restart = true; break; }
+          if (status == SW_REDUCED) {
+            t0 = clock64();
+            const int owner = S.res_owner;
+            const int64_t vs = P.vstart[(size_t)p * P.cap1 + owner];
+            const int vn = P.vlen[(size_t)p * P.cap1 + owner];
+            const uint32_t* ov = P.vpool + (size_t)p * P.vpool_cap + vs;
+            if (S.vcount + (uint32_t)vn > (uint32_t)P.vcap) v_compact();
+            for (int q = tid; q < vn; q += kSweepThreads) {
+              const int re = (int)ov[q];
+              const uint32_t en = __ldg(&EN[re]);
+              const uint32_t c = en >> 16, d = en & 0xffffu;
+              x_flip(c, d);
+              v_toggle(re);
+              atomicOr(&touched[c >> 5], 1u << (c & 31));
+              atomicOr(&touched[d >> 5], 1u << (d & 31));
+            }
+            badd_edges += vn;
+            __threadfence();
+            __syncthreads();
+            newpos = srow;  // recompute this row: the pivot just handled is now even, lower vertices may remain
+            restart = true;
+            cyc[3] += clock64() - t0;
+            break;
+          }
+          // SW_DEATH
+          pivot = (uint64_t)srow * (uint64_t)n + (uint64_t)(n - 1 - S.res_w);
+          done = true;
+          break;
+        }
+        if (done) break;
+        if (restart && tid == 0) S.restarts += 1;
+        pos = newpos;
+        __syncthreads();
+      }
+      if (S.abort_flag) break;
+      t0 = clock64();
+      // finalise the column
+      v_compact();
+      const uint32_t nv = S.vcount;
+      if (nv > maxv) maxv = nv;
+      if (!essential) {
+        if (vpool_used + nv > P.vpool_cap) { if (tid == 0) S.abort_flag = TDA_ERR_CAPACITY; __syncthreads(); break; }
+        uint32_t* dst = P.vpool + (size_t)p * P.vpool_cap + vpool_used;
+        const uint32_t* list = vlist(S.vsel);
+        for (uint32_t i = tid; i < nv; i += kSweepThreads) dst[i] = list[i];
+        if (tid == 0) {
+          P.vstart[(size_t)p * P.cap1 + ci] = vpool_used;
+          P.vlen[(size_t)p * P.cap1 + ci] = (int)nv;
+          hash_insert(pivot, ci);
+        }
+        vpool_used += nv;
+      }
+      const float birth = SD[rbirth];
+      float death = INFINITY;
+      int Md = -1, wd = -1;
+      if (!essential) { Md = (int)(pivot / (uint64_t)n); wd = n - 1 - (int)(pivot % (uint64_t)n); death = SD[Md]; }
+      if (essential || death > birth) {
+        if (tid == 0) {
+          out[2 * nrows] = birth; out[2 * nrows + 1] = death;
+          if (outs) {
+            const uint32_t e = EN[rbirth];
+            outs[2 * nrows] = edge_index((int)(e >> 16), (int)(e & 0xffffu));
+            if (essential) outs[2 * nrows + 1] = -1;
+            else {
+              const uint32_t em = EN[Md];
+              int x = (int)(em >> 16), y = (int)(em & 0xffffu), z = wd, t;
+              if (x < y) { t = x; x = y; y = t; }
+              if (y < z) { t = y; y = z; z = t; }
+              if (x < y) { t = x; x = y; y = t; }
+              outs[2 * nrows + 1] = (int64_t)x * (x - 1) * (x - 2) / 6 + (int64_t)y * (y - 1) / 2 + z;
+            }
+          }
+        }
+        ++nrows;
+      }
+      v_clear();
+      cyc[5] += clock64() - t0;
+    }
+    __syncthreads();
+    if (S.abort_flag) {  // leave the scratch clean for the next problem
+      v_compact();
+      v_clear();
+      for (size_t i = tid; i < (size_t)n * W; i += kSweepThreads) X[i] = 0;
+      __threadfence();
+      __syncthreads();
+    }
+    if (tid == 0) {
+      P.counts[p * 4 + 1] = nrows;
+      P.counts[p * 4 + 3] = S.abort_flag;
+      st[ST_REDUCED] = (unsigned long long)nb;
+      st[ST_ADDITIONS] = S.additions;
+      st[ST_PUSHES] = rows_swept;      // rows streamed through the filter
+      st[ST_POPS] = S.pivots;
+      st[ST_EXTENSIONS] = S.restarts;
+      st[ST_MAXV] = getenv_diag ? S.t_res : maxv;
+      for (int q = 0; q < 6; ++q) st[ST_CYC_EXTRACT + q] = (unsigned long long)cyc[q];
+      st[ST_BADD_EDGES] = badd_edges;
+      st[ST_EXT_EDGES] = S.heavy_rows;
+      st[ST_CYC_OWNER] = S.groups;   // (diagnostic) number of row groups
+    }
+    __syncthreads();
+  }
+};
+
+template <int WPL>
+__global__ void __launch_bounds__(kSweepThreads, 1) rips_sweep_kernel(const __grid_constant__ ReduceParams P) {
+  __shared__ SweepSmem S;
+  extern __shared__ uint32_t sweep_dyn[];
+  Sweeper<WPL> sw(P, S, sweep_dyn);
+  for (;;) {
+    if (threadIdx.x == 0) S.problem = atomicAdd(P.work_counter, 1);
+    __syncthreads();
+    const int p = S.problem;
+    __syncthreads();
+    if (p >= P.batch) break;
+    sw.run_problem(p);
+  }
+}
+
 __global__ void finalize_stats_kernel(const int* __restrict__ T, const int* __restrict__ bcount, int n, int batch,
                                       unsigned long long* __restrict__ stats, const int32_t* __restrict__ counts) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -858,16 +1386,24 @@ struct Layout {
   uint32_t* vbits; int64_t vwords; uint32_t* vlist; int64_t vcap;
   uint64_t* hkeys; int* hvals; int hcap;
   uint32_t* vpool; int64_t vpool_cap; int64_t* vstart; int* vlen;
-  uint32_t* bits; uint64_t wbits;   // per-CTA key windows
+  uint32_t* bits; uint64_t wbits;   // per-CTA key windows (bitset reducer)
+  uint32_t* xmat; int xw;           // per-CTA V bit matrix (sweep reducer)
+  bool sweep;
   int* work_counter; unsigned long long* stats;
   int grid; size_t total;
 };
 
 static int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
+static bool use_sweep_reducer() {
+  const char* e = getenv("TDA_RIPS_REDUCER");
+  return !(e && strcmp(e, "bitset") == 0);
+}
+
 static Layout make_layout(void* ws, int n, int batch, int maxdim, int cap1, size_t pool_bytes, int sm_count) {
   Layout L;
   memset(&L, 0, sizeof(L));
+  L.sweep = use_sweep_reducer();
   const int64_t E = (int64_t)n * (n - 1) / 2;
   const int64_t BE = (int64_t)batch * E;
   Carver c(ws, ~size_t(0));
@@ -908,6 +1444,13 @@ static Layout make_layout(void* ws, int n, int batch, int maxdim, int cap1, size
     L.hvals = c.take<int>((int64_t)batch * L.hcap);
     L.vstart = c.take<int64_t>((int64_t)batch * cap1);
     L.vlen = c.take<int>((int64_t)batch * cap1);
+    L.xw = (n + 31) / 32;
+    if (L.sweep) {
+      L.xmat = c.take<uint32_t>((size_t)L.grid * (size_t)n * L.xw);
+      L.vpool_cap = (int64_t)(pool_bytes / (size_t)batch / sizeof(uint32_t));
+      if (L.vpool_cap < 4 * (int64_t)cap1) L.vpool_cap = 4 * (int64_t)cap1;
+      L.vpool = c.take<uint32_t>((int64_t)batch * L.vpool_cap);
+    } else {
     // key windows: the whole key space E*n when it fits in 2^32 bits and in the pool, else a sliding window
     const uint64_t page = 1ull << kPageShift;
     uint64_t want = ((uint64_t)E * (uint64_t)n + 32 * page - 1) / (32 * page) * (32 * page);
@@ -921,6 +1464,7 @@ static Layout make_layout(void* ws, int n, int batch, int maxdim, int cap1, size
     L.vpool_cap = pool_bytes > bits_bytes ? (int64_t)((pool_bytes - bits_bytes) / (size_t)batch / sizeof(uint32_t)) : 0;
     if (L.vpool_cap < 4 * (int64_t)cap1) L.vpool_cap = 4 * (int64_t)cap1;
     L.vpool = c.take<uint32_t>((int64_t)batch * L.vpool_cap);
+    }
   }
   L.total = c.off;
   return L;
@@ -1031,7 +1575,8 @@ extern "C" int tda_rips(const float* dm, int n, int batch, int maxdim, float thr
   }
   if (maxdim >= 1 && E > 0) {
     TDA_CUDA_CHECK(cudaMemsetAsync(L.bcount, 0, sizeof(int) * batch, stream));
-    TDA_CUDA_CHECK(cudaMemsetAsync(L.bits, 0, (size_t)L.grid * (L.wbits >> 3), stream));
+    if (L.sweep) TDA_CUDA_CHECK(cudaMemsetAsync(L.xmat, 0, sizeof(uint32_t) * (size_t)L.grid * (size_t)n * L.xw, stream));
+    else TDA_CUDA_CHECK(cudaMemsetAsync(L.bits, 0, (size_t)L.grid * (L.wbits >> 3), stream));
     TDA_CUDA_CHECK(cudaMemsetAsync(L.vbits, 0, sizeof(uint32_t) * (size_t)L.grid * L.vwords, stream));
     dim3 g((unsigned)((E * 32 + 255) / 256), batch);
     {
@@ -1046,14 +1591,29 @@ extern "C" int tda_rips(const float* dm, int n, int batch, int maxdim, float thr
     P.h1_pairs = h1_pairs; P.h1_simplex = h1_simplex; P.counts = counts;
     P.vbits = L.vbits; P.vwords = L.vwords; P.vlist = L.vlist; P.vcap = L.vcap;
     P.hkeys = L.hkeys; P.hvals = L.hvals; P.hcap = L.hcap;
-    P.bits = L.bits; P.wbits = L.wbits;
+    P.bits = L.bits; P.wbits = L.wbits; P.xmat = L.xmat; P.xw = L.xw;
     P.vpool = L.vpool; P.vpool_cap = L.vpool_cap; P.vstart = L.vstart; P.vlen = L.vlen;
     P.work_counter = L.work_counter; P.stats = L.stats;
     {
       StageScope st(STAGE_RIPS_REDUCE, stream);
-      const size_t s1_bytes = (size_t)(((L.wbits >> kPageShift) + 31) / 32) * sizeof(uint32_t);
-      TDA_CUDA_CHECK(cudaFuncSetAttribute(rips_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1_bytes));
-      rips_reduce_kernel<<<L.grid, kReduceThreads, s1_bytes, stream>>>(P);
+      if (L.sweep) {
+        const size_t dyn = sizeof(uint32_t) * (size_t)L.xw * (1 + 3 * kGroupRows);
+#define TDA_SWEEP_LAUNCH(WPL)                                                                                                 \
+  do {                                                                                                                        \
+    TDA_CUDA_CHECK(cudaFuncSetAttribute(rips_sweep_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));      \
+    rips_sweep_kernel<WPL><<<L.grid, kSweepThreads, dyn, stream>>>(P);                                                        \
+  } while (0)
+        if (L.xw <= 32) TDA_SWEEP_LAUNCH(1);
+        else if (L.xw <= 64) TDA_SWEEP_LAUNCH(2);
+        else if (L.xw <= 128) TDA_SWEEP_LAUNCH(4);
+        else if (L.xw <= 256) TDA_SWEEP_LAUNCH(8);
+        else return set_error(TDA_ERR_UNSUPPORTED, "tda_rips: n=%d > 8192 needs TDA_RIPS_REDUCER=bitset", n);
+#undef TDA_SWEEP_LAUNCH
+      } else {
+        const size_t s1_bytes = (size_t)(((L.wbits >> kPageShift) + 31) / 32) * sizeof(uint32_t);
+        TDA_CUDA_CHECK(cudaFuncSetAttribute(rips_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1_bytes));
+        rips_reduce_kernel<<<L.grid, kReduceThreads, s1_bytes, stream>>>(P);
+      }
     }
     count_launch();
     TDA_LAUNCH_CHECK();

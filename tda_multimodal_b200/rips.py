@@ -4,6 +4,7 @@ debug_tda_pipeline.py:109-110, analyze_tda_over_layers.py:76, analyze_adversaria
 `rips_batch` is the batched device entry (layers x bootstrap resamples in one call); `ripser` mirrors the
 keyword surface and the result dict of ripser.py's `ripser` for a single cloud.
 """
+import os
 import warnings
 
 import numpy as np
@@ -46,12 +47,17 @@ def rips_batch(dm, maxdim=1, thresh=float("inf"), cap1=None, pool_bytes=None, wa
     cap1 = _next_pow2(cap1 or max(64, 4 * n))
     free_bytes = torch.cuda.mem_get_info(dev)[0]
     if pool_bytes is None:
-        # half of the pool holds one key window (bitset over the E*n triangle keys, <= 2^32 bits) per resident CTA,
-        # the other half the reduction columns of finished columns; capped so that large batches slide windows instead
-        sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        grid = min(B, 2 * sms)
-        window = min(-(-(n * (n - 1) // 2 * n) // 8), 1 << 29)
-        pool_bytes = max(64 << 20, min(2 * grid * window, int(0.35 * free_bytes)))
+        E = n * (n - 1) // 2
+        if os.environ.get("TDA_RIPS_REDUCER") == "bitset":
+            # half of the pool holds one key window (bitset over the E*n triangle keys, <= 2^32 bits) per resident CTA,
+            # the other half the reduction columns of finished columns
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            grid = min(B, 2 * sms)
+            window = min(-(-(E * n) // 8), 1 << 29)
+            pool_bytes = max(64 << 20, min(2 * grid * window, int(0.35 * free_bytes)))
+        else:
+            # row-sweep reducer: the pool only stores the reduction columns (edge lists) of finished columns
+            pool_bytes = max(64 << 20, min(B * 16 * E * 4, int(0.35 * free_bytes)))
     pool_bytes = int(pool_bytes)
     with torch.cuda.device(dev):
         while True:
