@@ -865,6 +865,9 @@ struct SweepSmem {
   uint32_t row_rank[2][kGroupRows], row_c[2][kGroupRows], row_d[2][kGroupRows];
   int row_apex[2][kGroupRows];
   uint32_t dirty;      // bit s: row s of the current group has a non-zero working row
+  uint32_t simple;     // bit s: r == lune (the whole row is odd): one apparent pivot clears it -- the common case, since V is a
+                       //        cocycle below the cursor: x_M ^ x_cw ^ x_dw is the same for every w of the lune
+  uint32_t both;       // bit s: both endpoints of row s were already touched when the row was formed
   uint32_t nheavy;
   uint32_t vcount, vcount2, vsel;
   int abort_flag, problem;
@@ -1037,13 +1040,21 @@ struct Sweeper {
       uint32_t* r = Sr + (size_t)sl * W;
       const uint32_t xmw = __ldcg(&Xc[d >> 5]);
       const uint32_t xm = ((xmw >> (d & 31)) & 1u) ? 0xffffffffu : 0u;
-      uint32_t any = 0;
+      uint32_t any = 0, diff = 0;
       for (int k = lane; k < W; k += 32) {
-        const uint32_t v = (xm ^ __ldcg(&Xc[k]) ^ __ldcg(&Xd[k])) & lm[k];
+        const uint32_t l = lm[k];
+        const uint32_t v = (xm ^ __ldcg(&Xc[k]) ^ __ldcg(&Xd[k])) & l;
         r[k] = v;
         any |= v;
+        diff |= v ^ l;
       }
-      if (__any_sync(0xffffffffu, any != 0) && lane == 0) atomicOr(&S.dirty, 1u << sl);
+      const bool nz = __any_sync(0xffffffffu, any != 0);
+      const bool full = !__any_sync(0xffffffffu, diff != 0);
+      if (lane == 0) {
+        if (nz) atomicOr(&S.dirty, 1u << sl);
+        if (nz && full) atomicOr(&S.simple, 1u << sl);
+        if (tbit(c) && tbit(d)) atomicOr(&S.both, 1u << sl);
+      }
     }
   }
 
@@ -1062,10 +1073,30 @@ struct Sweeper {
     const uint32_t* lmbase = Slm + (size_t)buf * kGroupRows * W;
     uint32_t flipmask = 0;   // rows whose edge joined V in this group (at most once per row: its apparent key is unique)
     uint32_t mask = S.dirty;
+    uint32_t fast = S.simple & S.both;   // rows that take the register-only path (until a patch touches them)
     while (mask && status == SW_DONE) {
       const int s = __ffs(mask) - 1;
       mask &= mask - 1;
       const uint32_t c = __shfl_sync(0xffffffffu, myc, s), d = __shfl_sync(0xffffffffu, myd, s);
+      if ((fast >> s) & 1u) {
+        // whole row odd, endpoints already touched: the apparent pivot (M, apex) joins the row's edge to V and clears the row
+        flipmask |= 1u << s;
+        bool patched = false;
+        if (lane > s) {
+          int vb = -1;
+          if (myc == c) vb = (int)d; else if (myc == d) vb = (int)c; else if (myd == c) vb = (int)d; else if (myd == d) vb = (int)c;
+          if (vb >= 0) {
+            const uint32_t m = 1u << (vb & 31);
+            if (lmbase[(size_t)lane * W + (vb >> 5)] & m) { Sr[(size_t)lane * W + (vb >> 5)] ^= m; patched = true; }
+          }
+        }
+        const uint32_t pm = __ballot_sync(0xffffffffu, patched);
+        mask |= pm;
+        fast &= ~pm;
+        ++pivots;
+        ++additions;
+        continue;
+      }
       const int apex = __shfl_sync(0xffffffffu, myapex, s);
       uint32_t* r = Sr + (size_t)s * W;
       const uint32_t* lm = lmbase + (size_t)s * W;
@@ -1104,7 +1135,9 @@ struct Sweeper {
               if (lmbase[(size_t)lane * W + (vb >> 5)] & m) { Sr[(size_t)lane * W + (vb >> 5)] ^= m; patched = true; }
             }
           }
-          mask |= __ballot_sync(0xffffffffu, patched);
+          const uint32_t pm = __ballot_sync(0xffffffffu, patched);
+          mask |= pm;
+          fast &= ~pm;
           ++additions;
           continue;
         }
@@ -1135,7 +1168,7 @@ struct Sweeper {
     if (lane == 0) {
       S.res_status = status; S.res_s = res_s; S.res_owner = res_owner; S.res_w = res_w;
       S.additions += additions; S.pivots += pivots;
-      S.dirty = 0;
+      S.dirty = 0; S.simple = 0; S.both = 0;
     }
   }
 
@@ -1158,7 +1191,7 @@ struct Sweeper {
     for (int i = tid; i < P.hcap; i += kSweepThreads) hkeys[i] = kEmpty;
     for (int i = tid; i < W; i += kSweepThreads) touched[i] = 0;
     if (tid == 0) {
-      S.vcount = 0; S.vsel = 0; S.abort_flag = 0; S.dirty = 0;
+      S.vcount = 0; S.vsel = 0; S.abort_flag = 0; S.dirty = 0; S.simple = 0; S.both = 0;
       S.additions = 0; S.pivots = 0; S.heavy_rows = 0; S.restarts = 0; S.groups = 0; S.t_res = 0;
     }
     __threadfence();
