@@ -337,6 +337,7 @@ struct ReduceParams {
   // per-CTA scratch
   uint32_t* bits; uint64_t wbits;           // [grid, wbits/32]  (all zero between columns)   (bitset reducer)
   uint32_t* xmat; int xw;                   // [grid, n, xw]  V as a symmetric bit matrix    (sweep reducer)
+  uint32_t* pmat;                           // [grid, n, xw]  adjacency bit matrix of the edges below the cursor
   uint32_t* vbits; int64_t vwords;          // [grid, vwords]
   uint32_t* vlist; int64_t vcap;            // [grid, 2, vcap]
   // per-problem
@@ -856,6 +857,7 @@ constexpr int kSweepThreads = 512;
 constexpr int kSweepWarps = kSweepThreads / 32;
 constexpr int kGroupRows = 32;                    // heavy rows resolved per group (one lane of the resolver per row)
 constexpr int kChunkRows = kSweepThreads;         // rows filtered per pass
+constexpr int kDenseThreshold = 64;               // heavy rows in a chunk from which the column switches to the Pm lune path
 enum { SW_DONE = 0, SW_RESTART = 1, SW_REDUCED = 2, SW_DEATH = 3 };
 
 struct SweepSmem {
@@ -888,6 +890,11 @@ struct Sweeper {
   const int tid, lane, warp;
   const int* R; const uint32_t* EN; const uint2* EA; int T; int n; int W;
   uint32_t* X; uint32_t* vbits; uint32_t* vl0;
+  uint32_t* Pm;          // Pm[c] = { w : rank(c,w) < p_pos }  (exact; advanced chunk by chunk, repositioned at column start)
+  uint32_t p_pos; bool p_valid;
+  bool p_mode;           // dense mode: Pm is maintained and the lune masks come from it (else from the rank rows)
+  uint32_t* seen1;       // [W] vertices that occur in the current chunk / in at least two of its rows
+  uint32_t* seen2;
   uint64_t* hkeys; int* hvals;
 
   __device__ Sweeper(const ReduceParams& p, SweepSmem& s, uint32_t* dyn)
@@ -895,9 +902,13 @@ struct Sweeper {
     n = P.n;
     W = P.xw;
     touched = dyn;
-    Sr = dyn + W;
+    seen1 = dyn + W;
+    seen2 = dyn + 2 * W;
+    Sr = dyn + 3 * W;
     Slm = Sr + (size_t)kGroupRows * W;
     X = P.xmat + (size_t)blockIdx.x * (size_t)n * W;
+    Pm = P.pmat + (size_t)blockIdx.x * (size_t)n * W;
+    p_pos = 0; p_valid = false; p_mode = false;
     vbits = P.vbits + (size_t)blockIdx.x * P.vwords;
     vl0 = P.vlist + (size_t)blockIdx.x * 2 * P.vcap;
   }
@@ -997,10 +1008,54 @@ struct Sweeper {
       }
   }
 
-  // ---- lune masks of the heavy rows [i, i + ns) of the chunk at `pos` into buffer `buf`; rows are dealt round-robin to
+  // ---- Pm bookkeeping.  All threads call; ends with the bits performed and a barrier.
+  __device__ __forceinline__ void p_set_rows(uint32_t lo, uint32_t hi, bool set) {  // rows [lo, hi)
+    for (uint32_t row = lo + tid; row < hi; row += kSweepThreads) {
+      const uint32_t en = __ldg(&EA[row]).x;
+      const uint32_t c = en >> 16, d = en & 0xffffu;
+      if (set) {
+        atomicOr(&Pm[(size_t)c * W + (d >> 5)], 1u << (d & 31));
+        atomicOr(&Pm[(size_t)d * W + (c >> 5)], 1u << (c & 31));
+      } else {
+        atomicAnd(&Pm[(size_t)c * W + (d >> 5)], ~(1u << (d & 31)));
+        atomicAnd(&Pm[(size_t)d * W + (c >> 5)], ~(1u << (c & 31)));
+      }
+    }
+  }
+  __device__ __forceinline__ void p_move(uint32_t target) {
+    const uint32_t dist = target > p_pos ? target - p_pos : p_pos - target;
+    if (!p_valid || (uint64_t)dist * 32ull > (uint64_t)n * (uint64_t)n) {
+      // rebuild from the rank matrix: one warp per vertex row, a word per ballot
+      for (int c = warp; c < n; c += kSweepWarps) {
+        const int* Rc = R + (size_t)c * n;
+        for (int k0 = 0; k0 < W; k0 += 32) {
+          uint32_t mine = 0;
+          const int kend = min(32, W - k0);
+#pragma unroll 8
+          for (int kk = 0; kk < kend; ++kk) {
+            const int w = (k0 + kk) * 32 + lane;
+            const int ra = w < n ? __ldg(&Rc[w]) : kRankDiag;
+            const unsigned word = __ballot_sync(0xffffffffu, ra < (int)target);
+            if (lane == kk) mine = word;
+          }
+          if (k0 + lane < W) Pm[(size_t)c * W + k0 + lane] = mine;
+        }
+      }
+      p_valid = true;
+    } else if (target > p_pos) {
+      p_set_rows(p_pos, target, true);
+    } else if (target < p_pos) {
+      p_set_rows(target, p_pos, false);
+    }
+    p_pos = target;
+    __threadfence();
+    __syncthreads();
+  }
+
+  // ---- (sparse mode, Pm not maintained) lune masks of the heavy rows [i, i + ns) of the chunk at `pos` into buffer `buf`; rows are dealt round-robin to
   // the warps [wfirst, wfirst + nw).  lune(M=(c,d)) = { w : rank(c,w) < M and rank(d,w) < M }: coalesced rank-row loads
   // (all of a 32-word block in flight at once) + ballot; independent of V, so it runs ahead of the resolver.
-  __device__ __forceinline__ void produce_lune(int buf, uint32_t pos, uint32_t i, int ns, int wfirst, int nw) {
+  __device__ __forceinline__ void produce_lune_rank(int buf, uint32_t pos, uint32_t i, int ns, int wfirst, int nw) {
     for (int sl = warp - wfirst; sl < ns; sl += nw) {
       const uint32_t hidx = S.heavy[i + sl];
       const uint2 ea = S.chunk_ea[hidx];
@@ -1025,6 +1080,37 @@ struct Sweeper {
           if (lane == kk) lmine = word;
         }
         if (k0 + lane < W) lm[k0 + lane] = lmine;
+      }
+      if (lane == 0) { S.row_rank[buf][sl] = Mrow; S.row_c[buf][sl] = c; S.row_d[buf][sl] = d; S.row_apex[buf][sl] = (int)ea.y; }
+    }
+  }
+
+  // ---- lune masks of the heavy rows [i, i + ns) of the chunk at `pos` into buffer `buf`; rows are dealt round-robin to
+  // the warps [wfirst, wfirst + nw).  lune(M=(c,d)) = { w : rank(c,w) < M and rank(d,w) < M } = Pm_M[c] & Pm_M[d].  Pm has
+  // been advanced to the END of the chunk by the filter, so the chunk's edges that are not below M (the rows after this
+  // one) are taken out again: each lane checks a few of them against c and d.  Independent of V: runs ahead of the resolver.
+  __device__ __forceinline__ void produce_lune(int buf, uint32_t pos, uint32_t i, int ns, int wfirst, int nw) {
+    if (!p_mode) { produce_lune_rank(buf, pos, i, ns, wfirst, nw); return; }
+    const uint32_t nchunk = min((uint32_t)kChunkRows, (uint32_t)T - pos);
+    for (int sl = warp - wfirst; sl < ns; sl += nw) {
+      const uint32_t hidx = S.heavy[i + sl];
+      const uint2 ea = S.chunk_ea[hidx];
+      const uint32_t Mrow = pos + hidx;
+      const uint32_t c = ea.x >> 16, d = ea.x & 0xffffu;
+      const uint32_t* Pc = Pm + (size_t)c * W;
+      const uint32_t* Pd = Pm + (size_t)d * W;
+      uint32_t* lm = Slm + ((size_t)buf * kGroupRows + sl) * W;
+      for (int k = lane; k < W; k += 32) lm[k] = __ldcg(&Pc[k]) & __ldcg(&Pd[k]);
+      __syncwarp();
+      // only vertices that occur in at least two rows of the chunk can need the correction
+      if (((seen2[c >> 5] >> (c & 31)) | (seen2[d >> 5] >> (d & 31))) & 1u)
+      for (uint32_t j = hidx + 1 + lane; j < nchunk; j += 32) {
+        const uint32_t e2 = S.chunk_ea[j].x;
+        const uint32_t c2 = e2 >> 16, d2 = e2 & 0xffffu;
+        int other = -1;
+        if (c2 == c || c2 == d) other = (int)d2;
+        else if (d2 == c || d2 == d) other = (int)c2;
+        if (other >= 0) atomicAnd(&lm[other >> 5], ~(1u << (other & 31)));
       }
       if (lane == 0) { S.row_rank[buf][sl] = Mrow; S.row_c[buf][sl] = c; S.row_d[buf][sl] = d; S.row_apex[buf][sl] = (int)ea.y; }
     }
@@ -1187,6 +1273,7 @@ struct Sweeper {
       if (tid == 0) { P.counts[p * 4 + 3] = TDA_ERR_CAPACITY; P.counts[p * 4 + 1] = 0; }
       return;
     }
+    p_valid = false;   // Pm belongs to the previous cloud's rank matrix
     sort_blist(bl, nb);
     for (int i = tid; i < P.hcap; i += kSweepThreads) hkeys[i] = kEmpty;
     for (int i = tid; i < W; i += kSweepThreads) touched[i] = 0;
@@ -1221,18 +1308,34 @@ struct Sweeper {
       bool essential = false;
       uint64_t pivot = 0;
       uint32_t pos = (uint32_t)rbirth + 1;
+      p_mode = false;
       for (;;) {
         if (S.abort_flag) break;
         if (pos >= (uint32_t)T) { essential = true; break; }
         // ---- streaming filter over the next kChunkRows rows
         t0 = clock64();
+        if (p_mode) {
+          for (int i2 = tid; i2 < 2 * W; i2 += kSweepThreads) seen1[i2] = 0;
+          __syncthreads();
+        }
         const uint32_t row = pos + tid;
         bool heavy = false;
         if (row < (uint32_t)T) {
           const uint2 ea = __ldg(&EA[row]);
           S.chunk_ea[tid] = ea;
-          heavy = tbit(ea.x >> 16) || tbit(ea.x & 0xffffu);
+          const uint32_t c = ea.x >> 16, d = ea.x & 0xffffu;
+          heavy = tbit(c) || tbit(d);
+          if (p_mode) {
+            if (row >= p_pos) {  // the edge enters Pm (exact state = end of this chunk; the lune producer compensates)
+              atomicOr(&Pm[(size_t)c * W + (d >> 5)], 1u << (d & 31));
+              atomicOr(&Pm[(size_t)d * W + (c >> 5)], 1u << (c & 31));
+            }
+            if (atomicOr(&seen1[c >> 5], 1u << (c & 31)) & (1u << (c & 31))) atomicOr(&seen2[c >> 5], 1u << (c & 31));
+            if (atomicOr(&seen1[d >> 5], 1u << (d & 31)) & (1u << (d & 31))) atomicOr(&seen2[d >> 5], 1u << (d & 31));
+          }
         }
+        if (p_mode) p_pos = max(p_pos, min(pos + (uint32_t)kChunkRows, (uint32_t)T));
+        __threadfence();
         const unsigned bal = __ballot_sync(0xffffffffu, heavy);
         if (lane == 0) S.wcnt[warp] = __popc(bal);
         __syncthreads();
@@ -1248,6 +1351,20 @@ struct Sweeper {
         rows_swept += min((uint32_t)kChunkRows, (uint32_t)T - pos);
         cyc[0] += clock64() - t0;
         const uint32_t nh = total;
+        if (!p_mode && nh >= (uint32_t)kDenseThreshold) {
+          // the column has become dense: from here on keep Pm (2 atomics per streamed row) and read the lune masks from
+          // it (1 KB per heavy row instead of two rank rows); bring Pm to the end of this chunk first
+          t0 = clock64();
+          p_move(pos);
+          const uint32_t cend = min(pos + (uint32_t)kChunkRows, (uint32_t)T);
+          p_set_rows(pos, cend, true);
+          p_pos = cend;
+          for (int i2 = tid; i2 < 2 * W; i2 += kSweepThreads) seen1[i2] = 0xffffffffu;  // this chunk: assume every vertex repeats
+          p_mode = true;
+          __threadfence();
+          __syncthreads();
+          cyc[5] += clock64() - t0;
+        }
         uint32_t i = 0;
         bool restart = false, done = false;
         uint32_t newpos = pos + kChunkRows;
@@ -1421,6 +1538,7 @@ struct Layout {
   uint32_t* vpool; int64_t vpool_cap; int64_t* vstart; int* vlen;
   uint32_t* bits; uint64_t wbits;   // per-CTA key windows (bitset reducer)
   uint32_t* xmat; int xw;           // per-CTA V bit matrix (sweep reducer)
+  uint32_t* pmat;                   // per-CTA "edges below the cursor" bit matrix (sweep reducer)
   bool sweep;
   int* work_counter; unsigned long long* stats;
   int grid; size_t total;
@@ -1480,6 +1598,7 @@ static Layout make_layout(void* ws, int n, int batch, int maxdim, int cap1, size
     L.xw = (n + 31) / 32;
     if (L.sweep) {
       L.xmat = c.take<uint32_t>((size_t)L.grid * (size_t)n * L.xw);
+      L.pmat = c.take<uint32_t>((size_t)L.grid * (size_t)n * L.xw);
       L.vpool_cap = (int64_t)(pool_bytes / (size_t)batch / sizeof(uint32_t));
       if (L.vpool_cap < 4 * (int64_t)cap1) L.vpool_cap = 4 * (int64_t)cap1;
       L.vpool = c.take<uint32_t>((int64_t)batch * L.vpool_cap);
@@ -1624,13 +1743,13 @@ extern "C" int tda_rips(const float* dm, int n, int batch, int maxdim, float thr
     P.h1_pairs = h1_pairs; P.h1_simplex = h1_simplex; P.counts = counts;
     P.vbits = L.vbits; P.vwords = L.vwords; P.vlist = L.vlist; P.vcap = L.vcap;
     P.hkeys = L.hkeys; P.hvals = L.hvals; P.hcap = L.hcap;
-    P.bits = L.bits; P.wbits = L.wbits; P.xmat = L.xmat; P.xw = L.xw;
+    P.bits = L.bits; P.wbits = L.wbits; P.xmat = L.xmat; P.xw = L.xw; P.pmat = L.pmat;
     P.vpool = L.vpool; P.vpool_cap = L.vpool_cap; P.vstart = L.vstart; P.vlen = L.vlen;
     P.work_counter = L.work_counter; P.stats = L.stats;
     {
       StageScope st(STAGE_RIPS_REDUCE, stream);
       if (L.sweep) {
-        const size_t dyn = sizeof(uint32_t) * (size_t)L.xw * (1 + 3 * kGroupRows);
+        const size_t dyn = sizeof(uint32_t) * (size_t)L.xw * (3 + 3 * kGroupRows);
 #define TDA_SWEEP_LAUNCH(WPL)                                                                                                 \
   do {                                                                                                                        \
     TDA_CUDA_CHECK(cudaFuncSetAttribute(rips_sweep_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));      \
