@@ -16,7 +16,7 @@ for rep in range(2):
     res = rips.rips_batch(dm, maxdim=1, want_stats=True)
     torch.cuda.synchronize(); dt = time.perf_counter() - t
 print(f"rips_batch {L} clouds: {dt*1e3:.1f} ms")
-keys = ["reduced", "additions", "pushes", "pops", "extensions", "max_v", "cyc_extract", "cyc_owner", "cyc_gen", "cyc_badd", "cyc_ext", "cyc_final", "ext_edges"]
+keys = ["reduced", "additions", "pushes", "pops", "extensions", "max_v", "cyc_extract", "cyc_owner", "cyc_gen", "cyc_badd", "cyc_ext", "cyc_final", "ext_edges", "badd_edges"]
 rows = sorted(range(L), key=lambda p: -(res[p]["stats"]["cyc_extract"] + res[p]["stats"]["cyc_gen"] + res[p]["stats"]["cyc_ext"] + res[p]["stats"]["cyc_final"] + res[p]["stats"]["cyc_badd"]))
 print("cloud " + " ".join(f"{k:>11s}" for k in keys))
 for p in rows[:8] + rows[-2:]:

@@ -866,10 +866,13 @@ struct SweepSmem {
   uint32_t wcnt[kSweepWarps];
   uint32_t row_rank[2][kGroupRows], row_c[2][kGroupRows], row_d[2][kGroupRows];
   int row_apex[2][kGroupRows];
-  uint32_t dirty;      // bit s: row s of the current group has a non-zero working row
-  uint32_t simple;     // bit s: r == lune (the whole row is odd): one apparent pivot clears it -- the common case, since V is a
+  uint32_t dirty[2];   // bit s: row s of the group in this buffer has a non-zero working row
+  uint32_t simple[2];  // bit s: r == lune (the whole row is odd): one apparent pivot clears it -- the common case, since V is a
                        //        cocycle below the cursor: x_M ^ x_cw ^ x_dw is the same for every w of the lune
-  uint32_t both;       // bit s: both endpoints of row s were already touched when the row was formed
+  uint32_t both[2];    // bit s: both endpoints of row s were already touched when the row was formed
+  uint32_t conf[2][kGroupRows];  // conf[.][f] bit l (l > f): rows f and l of the group share a vertex (a flip of f patches l)
+  uint32_t patched;    // rows of the NEXT group that the flips of the group just resolved have changed
+  uint32_t flipmask;   // rows of the group just resolved whose edge joined V
   uint32_t nheavy;
   uint32_t vcount, vcount2, vsel;
   int abort_flag, problem;
@@ -885,16 +888,16 @@ struct Sweeper {
   const ReduceParams& P;
   SweepSmem& S;
   uint32_t* touched;   // [W]
-  uint32_t* Sr;        // [kGroupRows][W]      working rows of the current group
-  uint32_t* Slm;       // [2][kGroupRows][W]   lune masks, double buffered (the next group's are produced during the resolve)
+  uint32_t* Sr;        // [2][kGroupRows][W]   working rows   } double buffered: the next group is produced (from the X of
+  uint32_t* Slm;       // [2][kGroupRows][W]   lune masks     } before this group's flips) while this group is resolved
   const int tid, lane, warp;
   const int* R; const uint32_t* EN; const uint2* EA; int T; int n; int W;
   uint32_t* X; uint32_t* vbits; uint32_t* vl0;
   uint32_t* Pm;          // Pm[c] = { w : rank(c,w) < p_pos }  (exact; advanced chunk by chunk, repositioned at column start)
   uint32_t p_pos; bool p_valid;
   bool p_mode;           // dense mode: Pm is maintained and the lune masks come from it (else from the rank rows)
-  uint32_t* seen1;       // [W] vertices that occur in the current chunk / in at least two of its rows
-  uint32_t* seen2;
+  uint32_t* vhead;       // [n]  dense mode: per vertex, head of the list of endpoint slots of the current chunk's rows
+  uint32_t* vnext;       // [2 * kChunkRows]  slot 2j+side -> next slot of the same vertex (0xffffffff = end)
   uint64_t* hkeys; int* hvals;
 
   __device__ Sweeper(const ReduceParams& p, SweepSmem& s, uint32_t* dyn)
@@ -902,10 +905,10 @@ struct Sweeper {
     n = P.n;
     W = P.xw;
     touched = dyn;
-    seen1 = dyn + W;
-    seen2 = dyn + 2 * W;
-    Sr = dyn + 3 * W;
-    Slm = Sr + (size_t)kGroupRows * W;
+    Sr = dyn + W;
+    Slm = Sr + (size_t)2 * kGroupRows * W;
+    vhead = Slm + (size_t)2 * kGroupRows * W;
+    vnext = vhead + n;
     X = P.xmat + (size_t)blockIdx.x * (size_t)n * W;
     Pm = P.pmat + (size_t)blockIdx.x * (size_t)n * W;
     p_pos = 0; p_valid = false; p_mode = false;
@@ -1052,95 +1055,186 @@ struct Sweeper {
     __syncthreads();
   }
 
-  // ---- (sparse mode, Pm not maintained) lune masks of the heavy rows [i, i + ns) of the chunk at `pos` into buffer `buf`; rows are dealt round-robin to
-  // the warps [wfirst, wfirst + nw).  lune(M=(c,d)) = { w : rank(c,w) < M and rank(d,w) < M }: coalesced rank-row loads
-  // (all of a 32-word block in flight at once) + ballot; independent of V, so it runs ahead of the resolver.
-  __device__ __forceinline__ void produce_lune_rank(int buf, uint32_t pos, uint32_t i, int ns, int wfirst, int nw) {
-    for (int sl = warp - wfirst; sl < ns; sl += nw) {
-      const uint32_t hidx = S.heavy[i + sl];
-      const uint2 ea = S.chunk_ea[hidx];
-      const uint32_t Mrow = pos + hidx;
-      const uint32_t c = ea.x >> 16, d = ea.x & 0xffffu;
-      const int* Rc = R + (size_t)c * n;
-      const int* Rd = R + (size_t)d * n;
-      uint32_t* lm = Slm + ((size_t)buf * kGroupRows + sl) * W;
-      for (int k0 = 0; k0 < W; k0 += 32) {
-        int ra[32], rb[32];
+  // ---- lune(M=(c,d)) = { w : rank(c,w) < M and rank(d,w) < M } of one heavy row (one warp), two ways.
+  // (sparse mode, Pm not maintained) from the two rank rows: coalesced loads, a 32-word block in flight at once, ballot
+  __device__ __forceinline__ void lune_from_ranks(uint32_t* lm, uint32_t c, uint32_t d, uint32_t Mrow) {
+    const int* Rc = R + (size_t)c * n;
+    const int* Rd = R + (size_t)d * n;
+    for (int k0 = 0; k0 < W; k0 += 16) {
+      int ra[16], rb[16];
 #pragma unroll
-        for (int kk = 0; kk < 32; ++kk) {
-          const int w = (k0 + kk) * 32 + lane;
-          const bool ok = (k0 + kk) < W && w < n;
-          ra[kk] = ok ? __ldg(&Rc[w]) : kRankDiag;
-          rb[kk] = ok ? __ldg(&Rd[w]) : kRankDiag;
-        }
-        uint32_t lmine = 0;
-#pragma unroll
-        for (int kk = 0; kk < 32; ++kk) {
-          const unsigned word = __ballot_sync(0xffffffffu, ra[kk] < (int)Mrow && rb[kk] < (int)Mrow);
-          if (lane == kk) lmine = word;
-        }
-        if (k0 + lane < W) lm[k0 + lane] = lmine;
+      for (int kk = 0; kk < 16; ++kk) {
+        const int w = (k0 + kk) * 32 + lane;
+        const bool ok = (k0 + kk) < W && w < n;
+        ra[kk] = ok ? __ldg(&Rc[w]) : kRankDiag;
+        rb[kk] = ok ? __ldg(&Rd[w]) : kRankDiag;
       }
-      if (lane == 0) { S.row_rank[buf][sl] = Mrow; S.row_c[buf][sl] = c; S.row_d[buf][sl] = d; S.row_apex[buf][sl] = (int)ea.y; }
+      uint32_t lmine = 0;
+#pragma unroll
+      for (int kk = 0; kk < 16; ++kk) {
+        const unsigned word = __ballot_sync(0xffffffffu, ra[kk] < (int)Mrow && rb[kk] < (int)Mrow);
+        if (lane == kk) lmine = word;
+      }
+      if (lane < 16 && k0 + lane < W) lm[k0 + lane] = lmine;
+    }
+  }
+  // (dense mode) Pm[c] & Pm[d] (the words `pw`, loaded by the caller).  Pm has been advanced to the END of the chunk by the
+  // filter, so the chunk's edges that are not below M (the rows after this one) are taken out again: lanes 0 and 1 walk the
+  // chunk's per-vertex row lists of c and d (a vertex occurs in ~1.5 rows of a chunk on average).
+  __device__ __forceinline__ void lune_from_pm(uint32_t* lm, const uint32_t (&pw)[WPL], uint32_t c, uint32_t d, uint32_t hidx) {
+#pragma unroll
+    for (int q = 0; q < WPL; ++q)
+      if ((lane + 32 * q) < W) lm[lane + 32 * q] = pw[q];
+    __syncwarp();
+    if (lane < 2) {
+      uint32_t slot = vhead[lane == 0 ? c : d];
+      while (slot != 0xffffffffu) {
+        const uint32_t j = slot >> 1;
+        if (j > hidx) {
+          const uint32_t e2 = S.chunk_ea[j].x;
+          const uint32_t other = (slot & 1u) ? (e2 >> 16) : (e2 & 0xffffu);   // slot side 0 = the row's c endpoint, 1 = its d endpoint
+          atomicAnd(&lm[other >> 5], ~(1u << (other & 31)));
+        }
+        slot = vnext[slot];
+      }
     }
   }
 
-  // ---- lune masks of the heavy rows [i, i + ns) of the chunk at `pos` into buffer `buf`; rows are dealt round-robin to
-  // the warps [wfirst, wfirst + nw).  lune(M=(c,d)) = { w : rank(c,w) < M and rank(d,w) < M } = Pm_M[c] & Pm_M[d].  Pm has
-  // been advanced to the END of the chunk by the filter, so the chunk's edges that are not below M (the rows after this
-  // one) are taken out again: each lane checks a few of them against c and d.  Independent of V: runs ahead of the resolver.
-  __device__ __forceinline__ void produce_lune(int buf, uint32_t pos, uint32_t i, int ns, int wfirst, int nw) {
-    if (!p_mode) { produce_lune_rank(buf, pos, i, ns, wfirst, nw); return; }
-    const uint32_t nchunk = min((uint32_t)kChunkRows, (uint32_t)T - pos);
-    for (int sl = warp - wfirst; sl < ns; sl += nw) {
-      const uint32_t hidx = S.heavy[i + sl];
-      const uint2 ea = S.chunk_ea[hidx];
-      const uint32_t Mrow = pos + hidx;
-      const uint32_t c = ea.x >> 16, d = ea.x & 0xffffu;
-      const uint32_t* Pc = Pm + (size_t)c * W;
-      const uint32_t* Pd = Pm + (size_t)d * W;
-      uint32_t* lm = Slm + ((size_t)buf * kGroupRows + sl) * W;
-      for (int k = lane; k < W; k += 32) lm[k] = __ldcg(&Pc[k]) & __ldcg(&Pd[k]);
-      __syncwarp();
-      // only vertices that occur in at least two rows of the chunk can need the correction
-      if (((seen2[c >> 5] >> (c & 31)) | (seen2[d >> 5] >> (d & 31))) & 1u)
-      for (uint32_t j = hidx + 1 + lane; j < nchunk; j += 32) {
-        const uint32_t e2 = S.chunk_ea[j].x;
-        const uint32_t c2 = e2 >> 16, d2 = e2 & 0xffffu;
-        int other = -1;
-        if (c2 == c || c2 == d) other = (int)d2;
-        else if (d2 == c || d2 == d) other = (int)c2;
-        if (other >= 0) atomicAnd(&lm[other >> 5], ~(1u << (other & 31)));
-      }
-      if (lane == 0) { S.row_rank[buf][sl] = Mrow; S.row_c[buf][sl] = c; S.row_d[buf][sl] = d; S.row_apex[buf][sl] = (int)ea.y; }
-    }
-  }
-
-  // ---- working rows of the group: r = (x_M ^ X[c] ^ X[d]) & lune, from the CURRENT X (all flips of earlier groups are fenced)
-  __device__ __forceinline__ void form_rows(int buf, int ns) {
-    for (int sl = warp; sl < ns; sl += kSweepWarps) {
-      const uint32_t c = S.row_c[buf][sl], d = S.row_d[buf][sl];
-      const uint32_t* Xc = X + (size_t)c * W;
-      const uint32_t* Xd = X + (size_t)d * W;
-      const uint32_t* lm = Slm + ((size_t)buf * kGroupRows + sl) * W;
-      uint32_t* r = Sr + (size_t)sl * W;
-      const uint32_t xmw = __ldcg(&Xc[d >> 5]);
-      const uint32_t xm = ((xmw >> (d & 31)) & 1u) ? 0xffffffffu : 0u;
-      uint32_t any = 0, diff = 0;
-      for (int k = lane; k < W; k += 32) {
-        const uint32_t l = lm[k];
-        const uint32_t v = (xm ^ __ldcg(&Xc[k]) ^ __ldcg(&Xd[k])) & l;
-        r[k] = v;
+  // ---- the heavy rows [i, i + ns) of the chunk at `pos` into buffer `buf`: lune mask, working row
+  // r = (x_M ^ X[c] ^ X[d]) & lune and its class.  Rows are dealt round-robin to the warps [wfirst, wfirst + nw).  X is not
+  // written while a group is being resolved (flips are deferred), so a group produced during the resolve of the previous
+  // one sees the X of before that group's flips; patch_next() applies them afterwards.
+  __device__ __forceinline__ void finish_row(int buf, int sl, uint32_t Mrow, uint2 ea, uint32_t xmw, const uint32_t (&xx)[WPL]) {
+    const uint32_t c = ea.x >> 16, d = ea.x & 0xffffu;
+    const uint32_t* lm = Slm + ((size_t)buf * kGroupRows + sl) * W;
+    uint32_t* r = Sr + ((size_t)buf * kGroupRows + sl) * W;
+    const uint32_t xm = ((xmw >> (d & 31)) & 1u) ? 0xffffffffu : 0u;
+    uint32_t any = 0, diff = 0;
+#pragma unroll
+    for (int q = 0; q < WPL; ++q)
+      if ((lane + 32 * q) < W) {
+        const uint32_t l = lm[lane + 32 * q];
+        const uint32_t v = (xm ^ xx[q]) & l;
+        r[lane + 32 * q] = v;
         any |= v;
         diff |= v ^ l;
       }
-      const bool nz = __any_sync(0xffffffffu, any != 0);
-      const bool full = !__any_sync(0xffffffffu, diff != 0);
-      if (lane == 0) {
-        if (nz) atomicOr(&S.dirty, 1u << sl);
-        if (nz && full) atomicOr(&S.simple, 1u << sl);
-        if (tbit(c) && tbit(d)) atomicOr(&S.both, 1u << sl);
+    const bool nz = __any_sync(0xffffffffu, any != 0);
+    const bool full = !__any_sync(0xffffffffu, diff != 0);
+    if (lane == 0) {
+      S.row_rank[buf][sl] = Mrow; S.row_c[buf][sl] = c; S.row_d[buf][sl] = d; S.row_apex[buf][sl] = (int)ea.y;
+      if (nz) atomicOr(&S.dirty[buf], 1u << sl);
+      if (nz && full) atomicOr(&S.simple[buf], 1u << sl);
+      if (tbit(c) && tbit(d)) atomicOr(&S.both[buf], 1u << sl);
+    }
+  }
+  __device__ __forceinline__ void produce(int buf, uint32_t pos, uint32_t i, int ns, int wfirst, int nw) {
+    constexpr int kMaxMine = 3;   // 32 rows over >= 15 warps
+    if (p_mode) {
+      // dense mode: every global word of all of this warp's rows is requested before any of them is used
+      uint2 ea[kMaxMine];
+      uint32_t xmw[kMaxMine], xx[kMaxMine][WPL], pw[kMaxMine][WPL];
+#pragma unroll
+      for (int t = 0; t < kMaxMine; ++t) {
+        const int sl = warp - wfirst + t * nw;
+        if (sl < ns) {
+          ea[t] = S.chunk_ea[S.heavy[i + sl]];
+          const uint32_t c = ea[t].x >> 16, d = ea[t].x & 0xffffu;
+          const uint32_t* Xc = X + (size_t)c * W;
+          const uint32_t* Xd = X + (size_t)d * W;
+          const uint32_t* Pc = Pm + (size_t)c * W;
+          const uint32_t* Pd = Pm + (size_t)d * W;
+          xmw[t] = __ldcg(&Xc[d >> 5]);
+#pragma unroll
+          for (int q = 0; q < WPL; ++q) {
+            const bool ok = (lane + 32 * q) < W;
+            xx[t][q] = ok ? (__ldcg(&Xc[lane + 32 * q]) ^ __ldcg(&Xd[lane + 32 * q])) : 0u;
+            pw[t][q] = ok ? (__ldcg(&Pc[lane + 32 * q]) & __ldcg(&Pd[lane + 32 * q])) : 0u;
+          }
+        }
       }
+#pragma unroll
+      for (int t = 0; t < kMaxMine; ++t) {
+        const int sl = warp - wfirst + t * nw;
+        if (sl < ns) {
+          const uint32_t hidx = S.heavy[i + sl];
+          uint32_t* lm = Slm + ((size_t)buf * kGroupRows + sl) * W;
+          lune_from_pm(lm, pw[t], ea[t].x >> 16, ea[t].x & 0xffffu, hidx);
+          __syncwarp();
+          finish_row(buf, sl, pos + hidx, ea[t], xmw[t], xx[t]);
+        }
+      }
+      return;
+    }
+    for (int sl = warp - wfirst; sl < ns; sl += nw) {
+      const uint32_t hidx = S.heavy[i + sl];
+      const uint2 ea = S.chunk_ea[hidx];
+      const uint32_t Mrow = pos + hidx;
+      const uint32_t c = ea.x >> 16, d = ea.x & 0xffffu;
+      const uint32_t* Xc = X + (size_t)c * W;
+      const uint32_t* Xd = X + (size_t)d * W;
+      uint32_t* lm = Slm + ((size_t)buf * kGroupRows + sl) * W;
+      const uint32_t xmw = __ldcg(&Xc[d >> 5]);
+      uint32_t xx[WPL];
+#pragma unroll
+      for (int q = 0; q < WPL; ++q) xx[q] = (lane + 32 * q) < W ? (__ldcg(&Xc[lane + 32 * q]) ^ __ldcg(&Xd[lane + 32 * q])) : 0u;
+      lune_from_ranks(lm, c, d, Mrow);
+      __syncwarp();
+      finish_row(buf, sl, Mrow, ea, xmw, xx);
+    }
+  }
+
+  // ---- after a group: its flips go out to global memory (X, the parity bits, the V list), one lane of warp 0 per flip ...
+  __device__ __forceinline__ void write_flips(int buf) {  // warp 0
+    const uint32_t flipmask = S.flipmask;
+    if (!flipmask) return;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&S.vcount, (uint32_t)__popc(flipmask));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if ((flipmask >> lane) & 1u) {
+      const uint32_t c = S.row_c[buf][lane], d = S.row_d[buf][lane], rk = S.row_rank[buf][lane];
+      atomicXor(&X[(size_t)c * W + (d >> 5)], 1u << (d & 31));
+      atomicXor(&X[(size_t)d * W + (c >> 5)], 1u << (c & 31));
+      atomicXor(&vbits[rk >> 5], 1u << (rk & 31));
+      const uint32_t vp = base + __popc(flipmask & ((1u << lane) - 1));
+      if (vp < (uint32_t)P.vcap) vlist(S.vsel)[vp] = rk;
+      else S.abort_flag = TDA_ERR_CAPACITY;
+    }
+  }
+  // ... and are applied to the rows of the next group (produced from the X of before): a flip of edge (c,d) changes exactly one
+  // bit of every row that shares a vertex with it.  All threads: thread t looks at row t%32 and flips t/32, t/32 + 16.
+  __device__ __forceinline__ void patch_next(int buf, int ns_next) {
+    const uint32_t flipmask = S.flipmask;
+    const int l2 = tid & 31;
+    if (!flipmask || l2 >= ns_next) return;
+    const int nb = buf ^ 1;
+    const uint32_t c2 = S.row_c[nb][l2], d2 = S.row_d[nb][l2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int f = (tid >> 5) + h * kSweepWarps;
+      if (!((flipmask >> f) & 1u)) continue;
+      const uint32_t c = S.row_c[buf][f], d = S.row_d[buf][f];
+      int vb = -1;
+      if (c2 == c) vb = (int)d; else if (c2 == d) vb = (int)c; else if (d2 == c) vb = (int)d; else if (d2 == d) vb = (int)c;
+      if (vb >= 0) {
+        const uint32_t m = 1u << (vb & 31);
+        const size_t o = ((size_t)nb * kGroupRows + l2) * W + (vb >> 5);
+        if (Slm[o] & m) { atomicXor(&Sr[o], m); atomicOr(&S.patched, 1u << l2); }
+      }
+    }
+  }
+
+  // ---- which rows of a produced group share a vertex (all threads; same thread layout as patch_next)
+  __device__ __forceinline__ void conflicts(int buf, int ns) {
+    const int l2 = tid & 31;
+    if (l2 >= ns) return;
+    const uint32_t c2 = S.row_c[buf][l2], d2 = S.row_d[buf][l2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int f = (tid >> 5) + h * kSweepWarps;
+      if (f >= l2) continue;
+      const uint32_t c = S.row_c[buf][f], d = S.row_d[buf][f];
+      if (c2 == c || c2 == d || d2 == c || d2 == d) atomicOr(&S.conf[buf][f], 1u << l2);
     }
   }
 
@@ -1157,34 +1251,41 @@ struct Sweeper {
     const uint32_t myrank = lane < ns ? S.row_rank[buf][lane] : 0u;
     const int myapex = lane < ns ? S.row_apex[buf][lane] : -3;
     const uint32_t* lmbase = Slm + (size_t)buf * kGroupRows * W;
+    uint32_t* rbase = Sr + (size_t)buf * kGroupRows * W;
+    const uint32_t patched0 = S.patched;   // rows changed by the previous group's flips: re-examine them from shared memory
     uint32_t flipmask = 0;   // rows whose edge joined V in this group (at most once per row: its apparent key is unique)
-    uint32_t mask = S.dirty;
-    uint32_t fast = S.simple & S.both;   // rows that take the register-only path (until a patch touches them)
+    uint32_t mask = S.dirty[buf] | patched0;
+    uint32_t fast = S.simple[buf] & S.both[buf] & ~patched0;   // rows that take the register-only path (until a patch touches them)
     while (mask && status == SW_DONE) {
       const int s = __ffs(mask) - 1;
       mask &= mask - 1;
-      const uint32_t c = __shfl_sync(0xffffffffu, myc, s), d = __shfl_sync(0xffffffffu, myd, s);
       if ((fast >> s) & 1u) {
         // whole row odd, endpoints already touched: the apparent pivot (M, apex) joins the row's edge to V and clears the row
         flipmask |= 1u << s;
-        bool patched = false;
-        if (lane > s) {
-          int vb = -1;
-          if (myc == c) vb = (int)d; else if (myc == d) vb = (int)c; else if (myd == c) vb = (int)d; else if (myd == d) vb = (int)c;
-          if (vb >= 0) {
-            const uint32_t m = 1u << (vb & 31);
-            if (lmbase[(size_t)lane * W + (vb >> 5)] & m) { Sr[(size_t)lane * W + (vb >> 5)] ^= m; patched = true; }
-          }
-        }
-        const uint32_t pm = __ballot_sync(0xffffffffu, patched);
-        mask |= pm;
-        fast &= ~pm;
         ++pivots;
         ++additions;
+        const uint32_t cm = S.conf[buf][s];   // later rows of the group that share a vertex with this edge (rare)
+        if (cm) {
+          const uint32_t c = __shfl_sync(0xffffffffu, myc, s), d = __shfl_sync(0xffffffffu, myd, s);
+          bool patched = false;
+          if ((cm >> lane) & 1u) {
+            int vb = -1;
+            if (myc == c) vb = (int)d; else if (myc == d) vb = (int)c; else if (myd == c) vb = (int)d; else if (myd == d) vb = (int)c;
+            if (vb >= 0) {
+              const uint32_t m = 1u << (vb & 31);
+              if (lmbase[(size_t)lane * W + (vb >> 5)] & m) { rbase[(size_t)lane * W + (vb >> 5)] ^= m; patched = true; }
+            }
+          }
+          const uint32_t pm = __ballot_sync(0xffffffffu, patched);
+          mask |= pm;
+          fast &= ~pm;
+        }
         continue;
       }
+      const uint32_t c = __shfl_sync(0xffffffffu, myc, s), d = __shfl_sync(0xffffffffu, myd, s);
       const int apex = __shfl_sync(0xffffffffu, myapex, s);
-      uint32_t* r = Sr + (size_t)s * W;
+      const uint32_t cm = S.conf[buf][s];
+      uint32_t* r = rbase + (size_t)s * W;
       const uint32_t* lm = lmbase + (size_t)s * W;
       uint32_t rw[WPL];
 #pragma unroll
@@ -1213,12 +1314,12 @@ struct Sweeper {
             if ((lane + 32 * q) < W) rw[q] ^= lm[lane + 32 * q];
           // later rows of the group that share a vertex with this edge see exactly one bit of X flip
           bool patched = false;
-          if (lane > s) {
+          if ((cm >> lane) & 1u) {
             int vb = -1;
             if (myc == c) vb = (int)d; else if (myc == d) vb = (int)c; else if (myd == c) vb = (int)d; else if (myd == d) vb = (int)c;
             if (vb >= 0) {
               const uint32_t m = 1u << (vb & 31);
-              if (lmbase[(size_t)lane * W + (vb >> 5)] & m) { Sr[(size_t)lane * W + (vb >> 5)] ^= m; patched = true; }
+              if (lmbase[(size_t)lane * W + (vb >> 5)] & m) { rbase[(size_t)lane * W + (vb >> 5)] ^= m; patched = true; }
             }
           }
           const uint32_t pm = __ballot_sync(0xffffffffu, patched);
@@ -1238,23 +1339,14 @@ struct Sweeper {
       if (status == SW_DONE && new_touch) { status = SW_RESTART; res_s = s; }  // rows skipped as untouched may matter now
     }
     __syncwarp();
-    if (flipmask) {  // write the group's flips out: X (both symmetric bits), the parity bit and the list entry, one lane per flip
-      uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(&S.vcount, (uint32_t)__popc(flipmask));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if ((flipmask >> lane) & 1u) {
-        atomicXor(&X[(size_t)myc * W + (myd >> 5)], 1u << (myd & 31));
-        atomicXor(&X[(size_t)myd * W + (myc >> 5)], 1u << (myc & 31));
-        atomicXor(&vbits[myrank >> 5], 1u << (myrank & 31));
-        const uint32_t vp = base + __popc(flipmask & ((1u << lane) - 1));
-        if (vp < (uint32_t)P.vcap) vlist(S.vsel)[vp] = myrank;
-        else S.abort_flag = TDA_ERR_CAPACITY;
-      }
-    }
     if (lane == 0) {
       S.res_status = status; S.res_s = res_s; S.res_owner = res_owner; S.res_w = res_w;
       S.additions += additions; S.pivots += pivots;
-      S.dirty = 0; S.simple = 0; S.both = 0;
+      S.dirty[buf] = 0; S.simple[buf] = 0; S.both[buf] = 0; S.patched = 0;
+      S.flipmask = flipmask;
+    }
+    S.conf[buf][lane] = 0;
+    {
     }
   }
 
@@ -1278,7 +1370,8 @@ struct Sweeper {
     for (int i = tid; i < P.hcap; i += kSweepThreads) hkeys[i] = kEmpty;
     for (int i = tid; i < W; i += kSweepThreads) touched[i] = 0;
     if (tid == 0) {
-      S.vcount = 0; S.vsel = 0; S.abort_flag = 0; S.dirty = 0; S.simple = 0; S.both = 0;
+      S.vcount = 0; S.vsel = 0; S.abort_flag = 0; S.dirty[0] = S.dirty[1] = 0; S.simple[0] = S.simple[1] = 0; S.both[0] = S.both[1] = 0; S.patched = 0; S.flipmask = 0;
+      for (int q = 0; q < kGroupRows; ++q) S.conf[0][q] = S.conf[1][q] = 0;
       S.additions = 0; S.pivots = 0; S.heavy_rows = 0; S.restarts = 0; S.groups = 0; S.t_res = 0;
     }
     __threadfence();
@@ -1315,7 +1408,7 @@ struct Sweeper {
         // ---- streaming filter over the next kChunkRows rows
         t0 = clock64();
         if (p_mode) {
-          for (int i2 = tid; i2 < 2 * W; i2 += kSweepThreads) seen1[i2] = 0;
+          for (int i2 = tid; i2 < n; i2 += kSweepThreads) vhead[i2] = 0xffffffffu;
           __syncthreads();
         }
         const uint32_t row = pos + tid;
@@ -1330,8 +1423,8 @@ struct Sweeper {
               atomicOr(&Pm[(size_t)c * W + (d >> 5)], 1u << (d & 31));
               atomicOr(&Pm[(size_t)d * W + (c >> 5)], 1u << (c & 31));
             }
-            if (atomicOr(&seen1[c >> 5], 1u << (c & 31)) & (1u << (c & 31))) atomicOr(&seen2[c >> 5], 1u << (c & 31));
-            if (atomicOr(&seen1[d >> 5], 1u << (d & 31)) & (1u << (d & 31))) atomicOr(&seen2[d >> 5], 1u << (d & 31));
+            vnext[2 * tid] = atomicExch(&vhead[c], 2u * tid);        // endpoint slots of this row into the per-vertex lists
+            vnext[2 * tid + 1] = atomicExch(&vhead[d], 2u * tid + 1);
           }
         }
         if (p_mode) p_pos = max(p_pos, min(pos + (uint32_t)kChunkRows, (uint32_t)T));
@@ -1359,11 +1452,11 @@ struct Sweeper {
           const uint32_t cend = min(pos + (uint32_t)kChunkRows, (uint32_t)T);
           p_set_rows(pos, cend, true);
           p_pos = cend;
-          for (int i2 = tid; i2 < 2 * W; i2 += kSweepThreads) seen1[i2] = 0xffffffffu;  // this chunk: assume every vertex repeats
           p_mode = true;
           __threadfence();
           __syncthreads();
           cyc[5] += clock64() - t0;
+          continue;   // filter this chunk again in dense mode (builds the per-vertex row lists)
         }
         uint32_t i = 0;
         bool restart = false, done = false;
@@ -1371,26 +1464,32 @@ struct Sweeper {
         int buf = 0;
         if (nh) {
           t0 = clock64();
-          produce_lune(0, pos, 0, (int)min((uint32_t)kGroupRows, nh), 0, kSweepWarps);
+          produce(0, pos, 0, (int)min((uint32_t)kGroupRows, nh), 0, kSweepWarps);
+          __syncthreads();
+          conflicts(0, (int)min((uint32_t)kGroupRows, nh));
           __syncthreads();
           cyc[1] += clock64() - t0;
         }
         while (i < nh) {
           const int ns = (int)min((uint32_t)kGroupRows, nh - i);
+          const int ns_next = (int)min((uint32_t)kGroupRows, nh - i - ns);
           t0 = clock64();
-          form_rows(buf, ns);
-          __syncthreads();
-          cyc[4] += clock64() - t0;
-          t0 = clock64();
-          if (warp == 0) { const long long tr = clock64(); resolve(buf, ns); if (lane == 0) S.t_res += clock64() - tr; }
-          else if (i + ns < nh) produce_lune(buf ^ 1, pos, i + ns, (int)min((uint32_t)kGroupRows, nh - i - ns), 1, kSweepWarps - 1);
-          __threadfence();   // the resolver's X flips are performed before the next group's rows are formed
+          if (warp == 0) resolve(buf, ns);
+          else if (ns_next > 0) produce(buf ^ 1, pos, i + ns, ns_next, 1, kSweepWarps - 1);
           __syncthreads();
           cyc[2] += clock64() - t0;
+          t0 = clock64();
+          if (warp == 0) write_flips(buf);
+          if (S.res_status == SW_DONE && ns_next > 0) { patch_next(buf, ns_next); conflicts(buf ^ 1, ns_next); }
+          __threadfence();   // the flips are performed before anybody reads X again
+          __syncthreads();
+          cyc[4] += clock64() - t0;
           const int status = S.res_status;
           const int s = S.res_s;
           if (tid == 0) { S.groups += 1; S.heavy_rows += (status == SW_DONE) ? ns : s + 1; }
           if (status == SW_DONE) { i += ns; buf ^= 1; continue; }
+          if (tid == 0) { S.dirty[buf ^ 1] = 0; S.simple[buf ^ 1] = 0; S.both[buf ^ 1] = 0; S.patched = 0; }  // the group produced ahead is dropped
+          if (tid < kGroupRows) S.conf[buf ^ 1][tid] = 0;
           const uint32_t srow = pos + S.heavy[i + s];
           if (status == SW_RESTART) { newpos = srow + 1; restart = true; break; }
           if (status == SW_REDUCED) {
@@ -1749,7 +1848,7 @@ extern "C" int tda_rips(const float* dm, int n, int batch, int maxdim, float thr
     {
       StageScope st(STAGE_RIPS_REDUCE, stream);
       if (L.sweep) {
-        const size_t dyn = sizeof(uint32_t) * (size_t)L.xw * (3 + 3 * kGroupRows);
+        const size_t dyn = sizeof(uint32_t) * ((size_t)L.xw * (1 + 4 * kGroupRows) + (size_t)n + 2 * kChunkRows);
 #define TDA_SWEEP_LAUNCH(WPL)                                                                                                 \
   do {                                                                                                                        \
     TDA_CUDA_CHECK(cudaFuncSetAttribute(rips_sweep_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));      \
