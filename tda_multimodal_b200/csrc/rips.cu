@@ -122,11 +122,12 @@ __global__ void rank_diag_kernel(int n, int* __restrict__ rank) {  // n == 1 or 
 // warp per matrix row: smallest rank leaving the row's component -> atomicMin per component) and a
 // one-CTA-per-cloud merge kernel (hook, break 2-cycles, pointer jumping, relabel).
 constexpr uint32_t kNoEdge = 0xffffffffu;
-__global__ void boruvka_init_kernel(int n, uint32_t* __restrict__ comp, uint32_t* __restrict__ cbest, int* __restrict__ done) {
+__global__ void boruvka_init_kernel(int n, uint32_t* __restrict__ comp, uint32_t* __restrict__ cbest, int* __restrict__ done,
+                                    int* __restrict__ mstcount) {
   int p = blockIdx.y;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { comp[(size_t)p * n + i] = i; cbest[(size_t)p * n + i] = kNoEdge; }
-  if (i == 0) done[p] = 0;
+  if (i == 0) { done[p] = 0; mstcount[p] = 0; }
 }
 __global__ void __launch_bounds__(256) boruvka_scan_kernel(const int* __restrict__ rank, const int* __restrict__ Tarr, int n,
                                                            const uint32_t* __restrict__ comp_g, uint32_t* __restrict__ cbest_g,
@@ -150,7 +151,8 @@ __global__ void __launch_bounds__(256) boruvka_scan_kernel(const int* __restrict
 }
 __global__ void __launch_bounds__(1024) boruvka_merge_kernel(const uint32_t* __restrict__ ends, int n, int64_t E, uint32_t* __restrict__ comp_g,
                                                              uint32_t* __restrict__ parent_g, uint32_t* __restrict__ cbest_g,
-                                                             uint8_t* __restrict__ mst, int* __restrict__ done) {
+                                                             uint8_t* __restrict__ mst, int* __restrict__ done,
+                                                             int* __restrict__ mstlist_g, int* __restrict__ mstcount) {
   const int p = blockIdx.x;
   if (done[p]) return;
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -168,6 +170,11 @@ __global__ void __launch_bounds__(1024) boruvka_merge_kernel(const uint32_t* __r
       uint32_t u = e >> 16, v = e & 0xffffu;
       par = comp[u] == (uint32_t)c ? comp[v] : comp[u];
       M[r] = 1;  // both sides may pick the same edge: same value written twice
+      // ... but it enters the MST list once: two components that picked each other did so through this edge; the smaller id lists it
+      if (!(cbest[par] == r && par < (uint32_t)c)) {
+        const int pos = atomicAdd(&mstcount[p], 1);
+        if (pos < n) mstlist_g[(size_t)p * n + pos] = (int)r;
+      }
       merged = 1;
     }
     parent[c] = par;
@@ -193,51 +200,51 @@ __global__ void __launch_bounds__(1024) boruvka_merge_kernel(const uint32_t* __r
   for (int i = tid; i < n; i += nt) { comp[i] = parent[comp[i]]; cbest[i] = kNoEdge; }
 }
 
-// gather the MST ranks, sort them, emit the H0 rows.  One CTA per cloud.
+// sort the MST ranks (collected by the merge kernel), emit the H0 rows.  One CTA per cloud; the list is sorted in shared
+// memory when it fits (n <= 8192), else in place in global memory.
 __global__ void __launch_bounds__(1024) h0_emit_kernel(const uint32_t* __restrict__ ends, const float* __restrict__ sdist,
-                                                       const int* __restrict__ Tarr, int n, int64_t E, const uint8_t* __restrict__ mst,
+                                                       const int* __restrict__ Tarr, int n, int64_t E, const int* __restrict__ mstcount,
                                                        const uint32_t* __restrict__ comp_g, float* __restrict__ h0_pairs,
-                                                       int64_t* __restrict__ h0_simplex, int32_t* __restrict__ counts, int* __restrict__ mstlist_g) {
-  __shared__ int s_zero, s_nmst;
+                                                       int64_t* __restrict__ h0_simplex, int32_t* __restrict__ counts, int* __restrict__ mstlist_g,
+                                                       int use_smem) {
+  extern __shared__ int s_list[];
+  __shared__ int s_zero, s_rows;
+  __shared__ int s_wcnt[32];
   const int p = blockIdx.x;
   const int tid = threadIdx.x, nt = blockDim.x;
   const uint32_t* EN = ends + (size_t)p * E;
   const uint32_t* comp = comp_g + (size_t)p * n;
   const int T = Tarr[p];
-  const uint8_t* M = mst + (size_t)p * E;
-  int* mstlist = mstlist_g + (size_t)p * n;
-  if (tid == 0) { s_nmst = 0; s_zero = 0; }
-  __syncthreads();
-  for (int64_t r = tid; r < T; r += nt)
-    if (M[r]) {
-      int pos = atomicAdd(&s_nmst, 1);
-      if (pos < n) mstlist[pos] = (int)r;
-    }
-  __syncthreads();
-  const int nm = min(s_nmst, n - 1);
+  int* glist = mstlist_g + (size_t)p * n;
+  const int nm = min(mstcount[p], n - 1);
   int np2 = 1;
   while (np2 < nm) np2 <<= 1;
-  if (np2 <= n) {
-    for (int i = nm + tid; i < np2; i += nt) mstlist[i] = 0x7fffffff;
+  int* list = use_smem ? s_list : glist;
+  if (tid == 0) { s_zero = 0; s_rows = 0; }
+  if (use_smem)
+    for (int i = tid; i < nm; i += nt) s_list[i] = glist[i];
+  if (np2 <= n || use_smem) {
+    for (int i = nm + tid; i < np2; i += nt) list[i] = 0x7fffffff;
     __syncthreads();
     for (int k = 2; k <= np2; k <<= 1)
       for (int j = k >> 1; j > 0; j >>= 1) {
         for (int i = tid; i < np2; i += nt) {
-          int ixj = i ^ j;
+          const int ixj = i ^ j;
           if (ixj > i) {
-            int a = mstlist[i], b = mstlist[ixj];
-            bool up = ((i & k) == 0);
-            if ((a > b) == up) { mstlist[i] = b; mstlist[ixj] = a; }
+            const int a = list[i], b = list[ixj];
+            const bool up = ((i & k) == 0);
+            if ((a > b) == up) { list[i] = b; list[ixj] = a; }
           }
         }
         __syncthreads();
       }
-  } else {  // np2 > n only for tiny n: serial insertion sort
+  } else {  // np2 > n only for tiny n without the shared-memory copy: serial insertion sort
+    __syncthreads();
     if (tid == 0)
       for (int i = 1; i < nm; ++i) {
-        int v = mstlist[i], k = i - 1;
-        while (k >= 0 && mstlist[k] > v) { mstlist[k + 1] = mstlist[k]; --k; }
-        mstlist[k + 1] = v;
+        int v = list[i], k = i - 1;
+        while (k >= 0 && list[k] > v) { list[k + 1] = list[k]; --k; }
+        list[k + 1] = v;
       }
     __syncthreads();
   }
@@ -245,28 +252,47 @@ __global__ void __launch_bounds__(1024) h0_emit_kernel(const uint32_t* __restric
   // edges have the smallest ranks, so they are a prefix of the sorted list.
   float* out = h0_pairs + (size_t)p * n * 2;
   int64_t* outs = h0_simplex ? h0_simplex + (size_t)p * n * 2 : nullptr;
+  int zloc = 0;
   for (int k = tid; k < nm; k += nt)
-    if (sdist[(size_t)p * E + mstlist[k]] == 0.f) atomicAdd(&s_zero, 1);
+    if (sdist[(size_t)p * E + list[k]] == 0.f) ++zloc;
+  if (zloc) atomicAdd(&s_zero, zloc);
   __syncthreads();
   const int z = s_zero;
   for (int k = z + tid; k < nm; k += nt) {
-    int r = mstlist[k];
-    int row = k - z;
+    const int r = list[k];
+    const int row = k - z;
     out[2 * row] = 0.f; out[2 * row + 1] = sdist[(size_t)p * E + r];
     if (outs) {
-      uint32_t e = EN[r];
+      const uint32_t e = EN[r];
       outs[2 * row] = -1; outs[2 * row + 1] = edge_index((int)(e >> 16), (int)(e & 0xffffu));
     }
   }
-  if (tid == 0) {
-    int rows = nm - z;
-    for (int i = 0; i < n && rows < n; ++i)
-      if (comp[i] == (uint32_t)i) {  // one essential class per component, reported at its root vertex
-        out[2 * rows] = 0.f; out[2 * rows + 1] = INFINITY;
-        if (outs) { outs[2 * rows] = i; outs[2 * rows + 1] = -1; }
-        ++rows;
+  // one essential class per component, reported at its root vertex, in vertex order (ordered block compaction)
+  int rows = nm - z;
+  for (int base = 0; base < n; base += nt) {
+    const int i = base + tid;
+    const bool isroot = i < n && comp[i] == (uint32_t)i;
+    const unsigned bal = __ballot_sync(0xffffffffu, isroot);
+    if ((tid & 31) == 0) s_wcnt[tid >> 5] = __popc(bal);
+    __syncthreads();
+    int off = 0, total = 0;
+    for (int w = 0; w < (nt >> 5); ++w) {
+      const int cw = s_wcnt[w];
+      if (w < (tid >> 5)) off += cw;
+      total += cw;
+    }
+    if (isroot) {
+      const int row = rows + off + __popc(bal & ((1u << (tid & 31)) - 1));
+      if (row < n) {
+        out[2 * row] = 0.f; out[2 * row + 1] = INFINITY;
+        if (outs) { outs[2 * row] = i; outs[2 * row + 1] = -1; }
       }
-    counts[p * 4 + 0] = rows;
+    }
+    rows += total;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    counts[p * 4 + 0] = min(rows, n);
     counts[p * 4 + 2] = T;
   }
 }
@@ -1630,7 +1656,7 @@ struct Layout {
   uint32_t *vals_a, *vals_b;
   void* cub_tmp; size_t cub_bytes;
   int* rank; uint32_t* ends; float* sdist; uint32_t* thresh_bits; int* T;
-  uint8_t* mst; int* mstlist; int* apex; uint2* ea; int* blist; int* bcount;
+  uint8_t* mst; int* mstlist; int* mstcount; int* apex; uint2* ea; int* blist; int* bcount;
   uint32_t *comp, *parent, *cbest; int* done;
   uint32_t* vbits; int64_t vwords; uint32_t* vlist; int64_t vcap;
   uint64_t* hkeys; int* hvals; int hcap;
@@ -1672,6 +1698,7 @@ static Layout make_layout(void* ws, int n, int batch, int maxdim, int cap1, size
   L.T = c.take<int>(batch);
   L.mst = c.take<uint8_t>(BE);
   L.mstlist = c.take<int>((int64_t)batch * n);
+  L.mstcount = c.take<int>(batch);
   L.comp = c.take<uint32_t>((int64_t)batch * n);
   L.parent = c.take<uint32_t>((int64_t)batch * n);
   L.cbest = c.take<uint32_t>((int64_t)batch * n);
@@ -1809,7 +1836,7 @@ extern "C" int tda_rips(const float* dm, int n, int batch, int maxdim, float thr
   {
     StageScope st(STAGE_RIPS_H0, stream);
     dim3 gi((n + 255) / 256, batch);
-    boruvka_init_kernel<<<gi, 256, 0, stream>>>(n, L.comp, L.cbest, L.done);
+    boruvka_init_kernel<<<gi, 256, 0, stream>>>(n, L.comp, L.cbest, L.done, L.mstcount);
     count_launch();
     int rounds = 1;
     while ((1 << rounds) < n) ++rounds;
@@ -1817,10 +1844,16 @@ extern "C" int tda_rips(const float* dm, int n, int batch, int maxdim, float thr
     dim3 gs((n + 7) / 8, batch);
     for (int r = 0; r < rounds && E > 0; ++r) {
       boruvka_scan_kernel<<<gs, 256, 0, stream>>>(L.rank, L.T, n, L.comp, L.cbest, L.done);
-      boruvka_merge_kernel<<<batch, 1024, 0, stream>>>(L.ends, n, E, L.comp, L.parent, L.cbest, L.mst, L.done);
+      boruvka_merge_kernel<<<batch, 1024, 0, stream>>>(L.ends, n, E, L.comp, L.parent, L.cbest, L.mst, L.done, L.mstlist, L.mstcount);
       count_launch(2);
     }
-    h0_emit_kernel<<<batch, 1024, 0, stream>>>(L.ends, L.sdist, L.T, n, E, L.mst, L.comp, h0_pairs, h0_simplex, counts, L.mstlist);
+    {
+      int np2 = 1;
+      while (np2 < n) np2 <<= 1;
+      const int use_smem = np2 <= 8192;
+      h0_emit_kernel<<<batch, 1024, use_smem ? sizeof(int) * (size_t)np2 : 0, stream>>>(L.ends, L.sdist, L.T, n, E, L.mstcount, L.comp, h0_pairs,
+                                                                                       h0_simplex, counts, L.mstlist, use_smem);
+    }
     count_launch();
     TDA_LAUNCH_CHECK();
   }
