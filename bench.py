@@ -201,7 +201,9 @@ def algorithmic_work(stage, a, n_layers_done, extra):
         "rips_edge_sort": L * (4.0 * n * n + 16.0 * E + 16.0 * E),     # read dm, radix sort key+payload, rank scatter
         "rips_h0": L * (4.0 * n * n) * extra.get("boruvka_rounds", 11),
         "rips_apparent": L * 8.0 * (E - n + 1) * (n - 2),
-        "rips_reduce": 8.0 * extra.get("reduce_keys", 0.0),
+        # row-sweep reducer: 8 B (endpoints, apex) per streamed row; per heavy row two V rows + two lune sources
+        # (adjacency-bitmatrix rows in dense columns: 4 * n/8 B in total)
+        "rips_reduce": 8.0 * extra.get("reduce_rows", 0.0) + 4.0 * (n / 8.0) * extra.get("reduce_heavy_rows", 0.0),
     }
     return "hbm", table[stage]
 
@@ -310,8 +312,11 @@ def run_b200(a):
         try:
             dm = pipeline.pdist_lowdim(torch.from_numpy(out2["embedding"]).to(dev))
             st = pipeline.rips_batch(dm, maxdim=1, want_stats=True)
-            extra["reduce_keys"] = float(sum(r["stats"]["pushes"] + r["stats"]["pops"] for r in st)) * a.steps
-            extra["rips_stats_sum"] = {k: int(sum(r["stats"][k] for r in st)) for k in ("columns", "apparent", "reduced", "additions", "pushes", "pops")}
+            extra["reduce_rows"] = float(sum(r["stats"]["pushes"] for r in st)) * a.steps
+            extra["reduce_heavy_rows"] = float(sum(r["stats"]["ext_edges"] for r in st)) * a.steps
+            names = {"columns": "columns", "apparent": "apparent_pairs", "reduced": "reduced_columns", "additions": "column_additions",
+                     "pushes": "rows_streamed", "ext_edges": "heavy_rows", "pops": "pivots"}
+            extra["rips_stats_sum"] = {v: int(sum(r["stats"][k] for r in st)) for k, v in names.items()}
         except Exception as ex:  # stats are optional evidence
             extra["stats_error"] = repr(ex)
         n_done = a.layers * a.steps

@@ -144,6 +144,12 @@ size_t tda_rips_workspace_bytes(int n, int batch, int maxdim, int cap1, size_t p
 int tda_rips(const float* dm, int n, int batch, int maxdim, float thresh,
              float* h0_pairs, int64_t* h0_simplex, float* h1_pairs, int64_t* h1_simplex, int cap1,
              int32_t* counts, float* thresh_out, void* ws, size_t ws_bytes, size_t pool_bytes, void* stream);
+/* tda_rips_launch: the same work, only enqueued on `stream` (no synchronisation): the caller synchronises the stream and
+ * reads counts[:,3] (0 = ok, TDA_ERR_CAPACITY = that problem overflowed: call again with larger cap1 / pool) itself.  Lets
+ * several batches overlap on different streams (tda_multimodal_b200.pipeline.layer_sweep). */
+int tda_rips_launch(const float* dm, int n, int batch, int maxdim, float thresh,
+                    float* h0_pairs, int64_t* h0_simplex, float* h1_pairs, int64_t* h1_simplex, int cap1,
+                    int32_t* counts, float* thresh_out, void* ws, size_t ws_bytes, size_t pool_bytes, void* stream);
 /* device statistics of the last tda_rips call on this workspace: [batch,16] int64:
  * columns(non-MST edges<=thresh), apparent, reduced, additions, pushes, pops, horizon_extensions, max_V,
  * SM cycles in extract / owner lookup / apparent add / reduced-column add / horizon extension / finalise,

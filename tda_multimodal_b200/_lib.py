@@ -37,6 +37,8 @@ PROTOTYPES = {
     "tda_rips_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_size_t]),
     "tda_rips": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                          c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]),
+    "tda_rips_launch": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]),
     "tda_rips_stats": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_size_t, c_void_p]),
 }
 

@@ -1779,7 +1779,7 @@ extern "C" size_t tda_rips_workspace_bytes(int n, int batch, int maxdim, int cap
   return L.total + 4096;
 }
 
-extern "C" int tda_rips(const float* dm, int n, int batch, int maxdim, float thresh, float* h0_pairs, int64_t* h0_simplex,
+static int rips_enqueue(const float* dm, int n, int batch, int maxdim, float thresh, float* h0_pairs, int64_t* h0_simplex,
                         float* h1_pairs, int64_t* h1_simplex, int cap1, int32_t* counts, float* thresh_out, void* ws,
                         size_t ws_bytes, size_t pool_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -1904,6 +1904,23 @@ extern "C" int tda_rips(const float* dm, int n, int batch, int maxdim, float thr
     finalize_stats_kernel<<<(batch + 255) / 256, 256, 0, stream>>>(L.T, L.bcount, n, batch, L.stats, counts);
     count_launch();
   }
+  return TDA_OK;
+}
+
+extern "C" int tda_rips_launch(const float* dm, int n, int batch, int maxdim, float thresh, float* h0_pairs, int64_t* h0_simplex,
+                               float* h1_pairs, int64_t* h1_simplex, int cap1, int32_t* counts, float* thresh_out, void* ws,
+                               size_t ws_bytes, size_t pool_bytes, void* stream_) {
+  return rips_enqueue(dm, n, batch, maxdim, thresh, h0_pairs, h0_simplex, h1_pairs, h1_simplex, cap1, counts, thresh_out, ws, ws_bytes,
+                      pool_bytes, stream_);
+}
+
+extern "C" int tda_rips(const float* dm, int n, int batch, int maxdim, float thresh, float* h0_pairs, int64_t* h0_simplex,
+                        float* h1_pairs, int64_t* h1_simplex, int cap1, int32_t* counts, float* thresh_out, void* ws,
+                        size_t ws_bytes, size_t pool_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int rc = rips_enqueue(dm, n, batch, maxdim, thresh, h0_pairs, h0_simplex, h1_pairs, h1_simplex, cap1, counts, thresh_out, ws,
+                              ws_bytes, pool_bytes, stream_);
+  if (rc != TDA_OK) return rc;
   // overflow status must be known to the caller
   TDA_CUDA_CHECK(cudaStreamSynchronize(stream));
   {

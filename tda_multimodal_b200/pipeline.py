@@ -7,10 +7,12 @@ The layers are independent (no carried state but the append-only stats list, :13
 rank go through each kernel together (batch dimension = layer), and ranks split the layers (layer l -> rank
 l mod G) with a single gather of the diagrams at the end.
 """
+import os
+
 import numpy as np
 
 from . import _lib
-from .rips import pdist_lowdim, rips_batch
+from .rips import pdist_lowdim, rips_batch, rips_batch_launch
 from .umap_ import umap_fit_batch
 
 
@@ -36,15 +38,60 @@ def stats_record(layer, dgms):
 
 
 def layer_sweep(X, n_neighbors=15, n_components=3, min_dist=0.1, metric="cosine", random_state=42, maxdim=1, n_epochs=None,
-                return_embedding=True):
+                return_embedding=True, chunks=None):
     """UMAP + Rips for a stack of layers resident on the device.  X [L,n,d] float32 CUDA tensor.
-    Returns {'embedding': [L,n,n_components] CUDA tensor, 'results': [L dicts with 'dgms', 'num_edges', 'thresh']}."""
-    _lib.require_cuda()
-    Y = umap_fit_batch(X, n_neighbors=n_neighbors, n_components=n_components, metric=metric, min_dist=min_dist,
-                       random_state=random_state, n_epochs=n_epochs)
-    dm = pdist_lowdim(Y)
-    res = rips_batch(dm, maxdim=maxdim)
-    return {"embedding": Y if return_embedding else None, "results": res}
+    Returns {'embedding': [L,n,n_components] CUDA tensor, 'results': [L dicts with 'dgms', 'num_edges', 'thresh']}.
+
+    The layers are cut into `chunks` groups (default: 2 when L >= 8; env TDA_SWEEP_CHUNKS overrides) that run on their own CUDA streams:
+    the Rips reduction of a group (one SM per cloud, latency bound) overlaps the UMAP stages of the next groups, and the
+    reductions of all groups overlap each other (tda_rips_launch does not synchronise)."""
+    torch = _lib.require_cuda()
+    Lc = X.shape[0]
+    if chunks is None:
+        chunks = int(os.environ.get("TDA_SWEEP_CHUNKS", "0")) or (2 if Lc >= 8 else 1)
+    chunks = max(1, min(int(chunks), Lc))
+    if chunks == 1:
+        Y = umap_fit_batch(X, n_neighbors=n_neighbors, n_components=n_components, metric=metric, min_dist=min_dist,
+                           random_state=random_state, n_epochs=n_epochs)
+        res = rips_batch(pdist_lowdim(Y), maxdim=maxdim)
+        return {"embedding": Y if return_embedding else None, "results": res}
+    cur = torch.cuda.current_stream(X.device)
+    bounds = [(Lc * c) // chunks for c in range(chunks + 1)]
+    streams = _sweep_streams(X.device, chunks)
+    Ys, jobs = [], []
+    for c in range(chunks):
+        st = streams[c]
+        st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            Xc = X[bounds[c]:bounds[c + 1]]
+            Xc.record_stream(st)
+            Y = umap_fit_batch(Xc, n_neighbors=n_neighbors, n_components=n_components, metric=metric, min_dist=min_dist,
+                               random_state=random_state, n_epochs=n_epochs)
+            jobs.append(rips_batch_launch(pdist_lowdim(Y), maxdim=maxdim))
+            Ys.append(Y)
+    res = []
+    for job in jobs:
+        res += job.finish()
+    for st in streams[:chunks]:
+        cur.wait_stream(st)
+    Yall = None
+    if return_embedding:
+        Yall = torch.cat(Ys, dim=0)
+        for Y, st in zip(Ys, streams):
+            Y.record_stream(cur)
+    return {"embedding": Yall, "results": res}
+
+
+_STREAMS = {}
+
+
+def _sweep_streams(device, k):
+    torch = _lib.require_cuda()
+    key = (device.type, device.index)
+    have = _STREAMS.setdefault(key, [])
+    while len(have) < k:
+        have.append(torch.cuda.Stream(device=device))
+    return have
 
 
 def layer_sweep_host(X_host, device=None, **kw):

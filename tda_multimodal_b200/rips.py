@@ -29,19 +29,77 @@ def pdist_lowdim(pts):
     return dm
 
 
-def rips_batch(dm, maxdim=1, thresh=float("inf"), cap1=None, pool_bytes=None, want_simplices=False, want_stats=False):
-    """Persistence of `B` dense distance matrices `dm` [B,n,n] (float32, CUDA).
+_STAT_NAMES = ["columns", "apparent", "reduced", "additions", "pushes", "pops", "extensions", "max_v", "cyc_extract",
+               "cyc_owner", "cyc_gen", "cyc_badd", "cyc_ext", "cyc_final", "badd_edges", "ext_edges"]
 
-    Returns a list of B dicts: {'dgms': [float64 (n_k,2)]*(maxdim+1), 'num_edges': int, 'thresh': float
-    [, 'simplices': [...], 'stats': {...}]}.  Grows cap1 / the column pool and retries when the library
-    reports TDA_ERR_CAPACITY.
-    """
-    torch = _lib.require_cuda()
-    L = _lib.lib()
-    if maxdim > 1:
-        raise NotImplementedError("tda_multimodal_b200: Rips persistence is implemented for maxdim <= 1 in this round")
-    assert dm.is_cuda and dm.dtype == torch.float32 and dm.dim() == 3 and dm.shape[1] == dm.shape[2]
-    dm = dm.contiguous()
+
+class RipsJob:
+    """A batch of Rips problems enqueued on the current CUDA stream (tda_rips_launch).  `finish()` synchronises that
+    stream, checks the per-problem status and returns the list of result dicts; on a capacity overflow it re-runs the
+    batch synchronously with larger buffers."""
+
+    def __init__(self, dm, maxdim, thresh, cap1, pool_bytes, want_simplices, want_stats):
+        torch = _lib.require_cuda()
+        L = _lib.lib()
+        self.dm, self.maxdim, self.thresh = dm, maxdim, float(thresh)
+        self.cap1, self.pool_bytes = cap1, pool_bytes
+        self.want_simplices, self.want_stats = want_simplices, want_stats
+        B, n, _ = dm.shape
+        dev = dm.device
+        self.stream = torch.cuda.current_stream(dev)
+        self.ws_bytes = int(L.tda_rips_workspace_bytes(n, B, maxdim, cap1, pool_bytes))
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self.h0 = torch.empty((B, n, 2), dtype=torch.float32, device=dev)
+        self.h0s = torch.empty((B, n, 2), dtype=torch.int64, device=dev) if want_simplices else None
+        self.h1 = torch.empty((B, cap1, 2), dtype=torch.float32, device=dev) if maxdim >= 1 else None
+        self.h1s = torch.empty((B, cap1, 2), dtype=torch.int64, device=dev) if (want_simplices and maxdim >= 1) else None
+        self.counts = torch.zeros((B, 4), dtype=torch.int32, device=dev)
+        self.th = torch.empty((B,), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.tda_rips_launch(_lib.ptr(dm), n, B, maxdim, self.thresh, _lib.ptr(self.h0), _lib.ptr(self.h0s), _lib.ptr(self.h1),
+                                         _lib.ptr(self.h1s), cap1, _lib.ptr(self.counts), _lib.ptr(self.th), _lib.ptr(self.ws),
+                                         self.ws_bytes, pool_bytes, _lib.stream_ptr()))
+
+    def finish(self):
+        torch = _lib.require_cuda()
+        L = _lib.lib()
+        dm = self.dm
+        B, n, _ = dm.shape
+        self.stream.synchronize()
+        counts_h = self.counts.cpu().numpy()
+        if (counts_h[:, 3] != 0).any():
+            # some problem overflowed cap1 / the column pool: run the whole batch again, synchronously, with larger buffers
+            del self.ws
+            with torch.cuda.stream(self.stream):
+                return rips_batch(dm, maxdim=self.maxdim, thresh=self.thresh, cap1=2 * self.cap1, pool_bytes=2 * self.pool_bytes,
+                                  want_simplices=self.want_simplices, want_stats=self.want_stats)
+        stats = None
+        if self.want_stats and self.maxdim >= 1:
+            stats = np.zeros((B, 16), dtype=np.int64)
+            with torch.cuda.device(dm.device):
+                _lib.check(L.tda_rips_stats(_lib.ptr(self.ws), n, B, self.maxdim, self.cap1, self.pool_bytes, stats.ctypes.data))
+        with torch.cuda.stream(self.stream):
+            h0_h = self.h0.cpu().numpy()
+            h1_h = self.h1.cpu().numpy() if self.h1 is not None else None
+            th_h = self.th.cpu().numpy()
+            h0s_h = self.h0s.cpu().numpy() if self.h0s is not None else None
+            h1s_h = self.h1s.cpu().numpy() if self.h1s is not None else None
+        out = []
+        for p in range(B):
+            c0, c1 = int(counts_h[p, 0]), int(counts_h[p, 1])
+            dgms = [h0_h[p, :c0].astype(np.float64)]
+            if self.maxdim >= 1:
+                dgms.append(h1_h[p, :c1].astype(np.float64))
+            r = {"dgms": dgms, "num_edges": int(counts_h[p, 2]), "thresh": float(th_h[p])}
+            if self.want_simplices:
+                r["simplices"] = [h0s_h[p, :c0]] + ([h1s_h[p, :c1]] if self.maxdim >= 1 else [])
+            if stats is not None:
+                r["stats"] = dict(zip(_STAT_NAMES, stats[p].tolist()))
+            out.append(r)
+        return out
+
+
+def _default_sizes(torch, dm, cap1, pool_bytes):
     B, n, _ = dm.shape
     dev = dm.device
     cap1 = _next_pow2(cap1 or max(64, 4 * n))
@@ -58,7 +116,37 @@ def rips_batch(dm, maxdim=1, thresh=float("inf"), cap1=None, pool_bytes=None, wa
         else:
             # row-sweep reducer: the pool only stores the reduction columns (edge lists) of finished columns
             pool_bytes = max(64 << 20, min(B * 16 * E * 4, int(0.35 * free_bytes)))
-    pool_bytes = int(pool_bytes)
+    return cap1, int(pool_bytes), free_bytes
+
+
+def rips_batch_launch(dm, maxdim=1, thresh=float("inf"), cap1=None, pool_bytes=None, want_simplices=False, want_stats=False):
+    """Enqueue the persistence of `B` dense distance matrices `dm` [B,n,n] (float32, CUDA) on the current stream and return a
+    RipsJob; nothing is synchronised until `job.finish()`."""
+    torch = _lib.require_cuda()
+    if maxdim > 1:
+        raise NotImplementedError("tda_multimodal_b200: Rips persistence is implemented for maxdim <= 1 in this round")
+    assert dm.is_cuda and dm.dtype == torch.float32 and dm.dim() == 3 and dm.shape[1] == dm.shape[2]
+    dm = dm.contiguous()
+    cap1, pool_bytes, _ = _default_sizes(torch, dm, cap1, pool_bytes)
+    return RipsJob(dm, maxdim, thresh, cap1, pool_bytes, want_simplices, want_stats)
+
+
+def rips_batch(dm, maxdim=1, thresh=float("inf"), cap1=None, pool_bytes=None, want_simplices=False, want_stats=False):
+    """Persistence of `B` dense distance matrices `dm` [B,n,n] (float32, CUDA).
+
+    Returns a list of B dicts: {'dgms': [float64 (n_k,2)]*(maxdim+1), 'num_edges': int, 'thresh': float
+    [, 'simplices': [...], 'stats': {...}]}.  Grows cap1 / the column pool and retries when the library
+    reports TDA_ERR_CAPACITY.
+    """
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    if maxdim > 1:
+        raise NotImplementedError("tda_multimodal_b200: Rips persistence is implemented for maxdim <= 1 in this round")
+    assert dm.is_cuda and dm.dtype == torch.float32 and dm.dim() == 3 and dm.shape[1] == dm.shape[2]
+    dm = dm.contiguous()
+    B, n, _ = dm.shape
+    dev = dm.device
+    cap1, pool_bytes, free_bytes = _default_sizes(torch, dm, cap1, pool_bytes)
     with torch.cuda.device(dev):
         while True:
             ws_bytes = int(L.tda_rips_workspace_bytes(n, B, maxdim, cap1, pool_bytes))
@@ -98,8 +186,7 @@ def rips_batch(dm, maxdim=1, thresh=float("inf"), cap1=None, pool_bytes=None, wa
         if want_simplices:
             r["simplices"] = [h0s_h[p, :c0]] + ([h1s_h[p, :c1]] if maxdim >= 1 else [])
         if stats is not None:
-            r["stats"] = dict(zip(["columns", "apparent", "reduced", "additions", "pushes", "pops", "extensions", "max_v", "cyc_extract",
-                                   "cyc_owner", "cyc_gen", "cyc_badd", "cyc_ext", "cyc_final", "badd_edges", "ext_edges"], stats[p].tolist()))
+            r["stats"] = dict(zip(_STAT_NAMES, stats[p].tolist()))
         out.append(r)
     return out
 
