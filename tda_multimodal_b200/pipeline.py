@@ -82,6 +82,27 @@ def layer_sweep(X, n_neighbors=15, n_components=3, min_dist=0.1, metric="cosine"
     return {"embedding": Yall, "results": res}
 
 
+def bootstrap_rips(Y, n_resamples=256, size=1000, seed=4000, layer_ids=None, replace=False, maxdim=1, max_batch=256):
+    """Config C4 of BASELINE.json: for every 3-D cloud Y[l] ([L,n,dim] CUDA tensor, e.g. the UMAP output of layer l),
+    `n_resamples` bootstrap resamples of `size` points -> Rips H0/H1 of each, batched `max_batch` problems per call (the
+    batch dimension of every Rips kernel is the resample).  The reference has no bootstrap code: the semantics are
+    L * n_resamples independent ``ripser(Y_l[idx], maxdim=1)`` calls; index sets come from
+    workloads.c4_resample_indices (seeded per (layer, resample)).  Returns results[l][r] = dict with 'dgms', ..."""
+    torch = _lib.require_cuda()
+    from . import workloads
+    Lc, n, dim = Y.shape
+    layer_ids = list(range(Lc)) if layer_ids is None else list(layer_ids)
+    out = []
+    for li, layer in enumerate(layer_ids):
+        idx = torch.from_numpy(workloads.c4_resample_indices(layer, n, n_resamples, size, seed=seed, replace=replace)).to(Y.device)
+        res = []
+        for r0 in range(0, n_resamples, max_batch):
+            pts = Y[li][idx[r0:r0 + max_batch]].contiguous()      # [b, size, dim]
+            res += rips_batch(pdist_lowdim(pts), maxdim=maxdim)
+        out.append(res)
+    return out
+
+
 _STREAMS = {}
 
 

@@ -132,3 +132,66 @@ def test_large_cloud_properties(torch_cuda):
     perm = rng.permutation(2000)
     r2 = rips.rips_batch(rips.pdist_lowdim(torch.from_numpy(X[perm]).cuda()[None]), maxdim=1)[0]
     assert same_diagram(r2["dgms"][1], d1) and same_diagram(r2["dgms"][0], d0)
+
+
+def test_bootstrap_resamples_match_oracle(torch_cuda):
+    """Config C4 semantics: resamples of one cloud, batched on the GPU == independent oracle calls on the same index sets."""
+    torch = torch_cuda
+    from oracle import rips as orips
+    from tda_multimodal_b200 import pipeline, workloads
+    rng = np.random.default_rng(21)
+    Y = np.stack([torus3d(300, rng), blobs3d(300, rng)])
+    res = pipeline.bootstrap_rips(torch.from_numpy(Y).cuda(), n_resamples=6, size=150, seed=4000, max_batch=4)
+    assert len(res) == 2 and len(res[0]) == 6
+    for l in range(2):
+        idx = workloads.c4_resample_indices(l, 300, 6, 150, seed=4000)
+        for r in range(6):
+            want = orips.ripser(Y[l][idx[r]], maxdim=1)["dgms"]
+            got = res[l][r]["dgms"]
+            assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+
+
+def test_async_jobs_and_chunked_sweep_equal_blocking(torch_cuda):
+    torch = torch_cuda
+    from tda_multimodal_b200 import rips
+    rng = np.random.default_rng(22)
+    X = np.stack([torus3d(200, rng) for _ in range(5)])
+    dm = rips.pdist_lowdim(torch.from_numpy(X).cuda())
+    blocking = rips.rips_batch(dm, maxdim=1)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    s1.wait_stream(torch.cuda.current_stream()); s2.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s1):
+        j1 = rips.rips_batch_launch(dm[:2], maxdim=1)
+    with torch.cuda.stream(s2):
+        j2 = rips.rips_batch_launch(dm[2:], maxdim=1)
+    got = j1.finish() + j2.finish()
+    for a, b in zip(got, blocking):
+        assert np.array_equal(a["dgms"][0], b["dgms"][0]) and np.array_equal(a["dgms"][1], b["dgms"][1])
+    # too small a capacity is detected by finish() and repaired by a synchronous re-run
+    j3 = rips.rips_batch_launch(dm, maxdim=1, cap1=2)
+    got3 = j3.finish()
+    assert all(np.array_equal(a["dgms"][1], b["dgms"][1]) for a, b in zip(got3, blocking))
+
+
+def test_full_size_invariants(torch_cuda):
+    """BASELINE.json sizes (2000-point 3-D clouds): properties that do not need the (slow) oracle -- #H0 rows = n with one
+    infinite bar, H0 deaths ascending = MST weights, H1 births descending, invariance under a permutation of the points and
+    exact equivariance under scaling by a power of two."""
+    torch = torch_cuda
+    from scipy.sparse.csgraph import minimum_spanning_tree
+    from tda_multimodal_b200 import rips
+    rng = np.random.default_rng(33)
+    X = torus3d(2000, rng)
+    perm = rng.permutation(2000)
+    batch = np.stack([X, X[perm], X * np.float32(4.0)])
+    dm = rips.pdist_lowdim(torch.from_numpy(batch).cuda())
+    a, b, c = rips.rips_batch(dm, maxdim=1)
+    d0, d1 = a["dgms"]
+    assert d0.shape == (2000, 2) and np.isinf(d0[-1, 1]) and np.isfinite(d0[:-1, 1]).all() and np.all(np.diff(d0[:-1, 1]) >= 0)
+    mst = np.sort(minimum_spanning_tree(dm[0].double().cpu().numpy()).data)
+    assert np.array_equal(mst.astype(np.float32), d0[:-1, 1].astype(np.float32))
+    assert np.all(np.diff(d1[:, 0]) <= 0) and np.all(d1[:, 1] > d1[:, 0])
+    assert same_diagram(b["dgms"][0], d0) and same_diagram(b["dgms"][1], d1)
+    assert np.array_equal(c["dgms"][0][:-1] / 4.0, d0[:-1]) and same_diagram(c["dgms"][1] / 4.0, d1)
+    pers = np.sort(d1[:, 1] - d1[:, 0])[::-1]
+    assert pers[0] > 2 * pers[2]  # torus R=3, r=1: two dominant classes at most
