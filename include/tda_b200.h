@@ -116,6 +116,14 @@ int tda_spectral_embed(const int32_t* head, const int32_t* tail, const float* we
                        int batch, const int32_t* comp, const int32_t* ncomp, const int32_t* comp_size, const float* degree,
                        int maxcomp, int min_size, uint64_t seed, float* Y, float* evals, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- silhouette ------------------------------------------------------------------------------------
+ * Replaces sklearn.metrics.silhouette_score(point_cloud_low_dim, labels) (debug_tda_pipeline.py:117-118;
+ * analyze_adversarial_tda.py:108-111) on the euclidean distance matrix of the 3-D cloud (tda_pdist_lowdim).
+ *   dm [batch,n,n] float32; labels [batch,n] int32 in [0, n_labels), 2 <= n_labels <= 64; score [batch] float32 (mean
+ *   silhouette coefficient; points of a singleton label contribute 0, as in scikit-learn); ws: 8*batch bytes. */
+int tda_silhouette(const float* dm, const int32_t* labels, int n, int batch, int n_labels, float* score, void* ws, size_t ws_bytes,
+                   void* stream);
+
 /* ---- Rips persistence -------------------------------------------------------------------------
  * Replaces ripser(X, maxdim=1)['dgms'] (debug_tda_pipeline.py:109-110; analyze_tda_over_layers.py:76;
  * analyze_adversarial_tda.py:100-101).

@@ -34,6 +34,7 @@ PROTOTYPES = {
                                      c_void_p, c_void_p, c_size_t, c_void_p]),
     "tda_spectral_embed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_int, c_int, ctypes.c_uint64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tda_silhouette": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tda_rips_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_size_t]),
     "tda_rips": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                          c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]),

@@ -82,6 +82,35 @@ def layer_sweep(X, n_neighbors=15, n_components=3, min_dist=0.1, metric="cosine"
     return {"embedding": Yall, "results": res}
 
 
+def silhouette_score(Y, labels, dm=None):
+    """sklearn.metrics.silhouette_score(Y, labels) (euclidean) as the reference calls it (debug_tda_pipeline.py:117-118) on the
+    GPU.  Y [n,dim] or [B,n,dim] (numpy or CUDA tensor), labels: one sequence of n hashable labels (strings in the reference)
+    shared by all clouds, or [B,n].  Returns a Python float (single cloud) or a float32 numpy array [B]."""
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    single = (Y.ndim == 2)
+    Yt = Y if isinstance(Y, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(Y, dtype=np.float32))
+    Yt = Yt.to(device="cuda", dtype=torch.float32)
+    if single:
+        Yt = Yt[None]
+    B, n, _ = Yt.shape
+    lab = np.asarray(labels)
+    if lab.ndim == 1:
+        lab = np.broadcast_to(lab, (B, n))
+    uniq, inv = np.unique(lab.reshape(-1), return_inverse=True)
+    if not (2 <= len(uniq) <= n - 1):
+        raise ValueError("Number of labels is %d. Valid values are 2 to n_samples - 1 (inclusive)" % len(uniq))
+    lab_d = torch.from_numpy(inv.reshape(B, n).astype(np.int32)).to(Yt.device)
+    if dm is None:
+        dm = pdist_lowdim(Yt.contiguous())
+    score = torch.empty((B,), dtype=torch.float32, device=Yt.device)
+    ws = torch.empty(8 * B, dtype=torch.uint8, device=Yt.device)
+    with torch.cuda.device(Yt.device):
+        _lib.check(L.tda_silhouette(_lib.ptr(dm), _lib.ptr(lab_d), n, B, int(len(uniq)), _lib.ptr(score), _lib.ptr(ws), 8 * B, _lib.stream_ptr()))
+    out = score.cpu().numpy()
+    return float(out[0]) if single else out
+
+
 def bootstrap_rips(Y, n_resamples=256, size=1000, seed=4000, layer_ids=None, replace=False, maxdim=1, max_batch=256):
     """Config C4 of BASELINE.json: for every 3-D cloud Y[l] ([L,n,dim] CUDA tensor, e.g. the UMAP output of layer l),
     `n_resamples` bootstrap resamples of `size` points -> Rips H0/H1 of each, batched `max_batch` problems per call (the
