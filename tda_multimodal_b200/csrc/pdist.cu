@@ -7,14 +7,14 @@
 //
 // Precision: the reference computes in float32 (sgemm).  bf16/tf32 single-pass MMA cannot meet the 1e-5
 // parity bound, so every operand is split x = hi + lo with hi = tf32(x), lo = tf32(x - hi) and the kernel
-// accumulates lo*hi + hi*lo + hi*hi (3xTF32): the K loop simply runs three times over different (A,B)
-// tensor-map pairs.  The tensor core's fp32 accumulate truncates, which biases a 12288-term sum by ~3e-5
+// accumulates lo*hi + hi*lo + hi*hi (3xTF32) from the four operand tiles of every k-block.  The tensor core's fp32 accumulate truncates, which biases a 12288-term sum by ~3e-5
 // (measured), so K is cut into chunks of 128 elements: each chunk is accumulated in TMEM on its own (small
 // partial sums, few truncating adds) and the epilogue warps add the chunks in registers with round-to-nearest.
 // Useful FLOPs = 2*N*M*D, issued FLOPs = 3x that.
 //
 // Kernel structure (one persistent CTA per SM, 192 threads):
-//   warp 0      : TMA producer   (cp.async.bulk.tensor.2d, 128B swizzle, 6-stage mbarrier ring)
+//   warp 0      : TMA producer   (cp.async.bulk.tensor.2d, 128B swizzle, 3-stage mbarrier ring of 64 KB stages:
+//                                 A_hi, A_lo, B_hi, B_lo of one k-block, loaded once for the three products)
 //   warp 1      : MMA issuer     (tcgen05.mma.cta_group::1.kind::tf32, M=128 N=128 K=8; owns TMEM alloc)
 //   warps 2..5  : epilogue       (tcgen05.ld 32x32b.x32 -> distance formula -> global), double-buffered
 //                                 accumulators (2 x 128 TMEM columns) so it overlaps the next tile's K loop
@@ -28,8 +28,10 @@ namespace tda {
 namespace pdist {
 
 constexpr int BM = 128, BN = 128, BK = 32;       // tile; BK floats = 128 bytes = one swizzle row
-constexpr int kStages = 6;
-constexpr int kStageBytes = (BM + BN) * BK * 4;  // 32 KB
+constexpr int kStages = 3;
+constexpr int kTileABytes = BM * BK * 4;         // 16 KB
+constexpr int kTileBBytes = BN * BK * 4;         // 16 KB
+constexpr int kStageBytes = 2 * kTileABytes + 2 * kTileBBytes;  // 64 KB: A_hi, A_lo, B_hi, B_lo of one k-block
 constexpr int kThreads = 192;
 constexpr int kTmemCols = 256;                   // 2 accumulator stages x 128 columns
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
@@ -165,21 +167,18 @@ pdist_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         const int b = t / tiles_per_problem, r = t % tiles_per_problem;
         const int row_a = b * P.n + (r / P.tiles_n) * BM;
         const int row_b = b * P.m + (r % P.tiles_n) * BN;
-        for (int k0 = 0; k0 < P.kblocks; k0 += P.kchunk) {
-          const int k1 = min(k0 + P.kchunk, P.kblocks);
-          for (int pass = 0; pass < 3; ++pass) {
-            const CUtensorMap* ma = pass == 0 ? &map_a_lo : &map_a_hi;   // lo*hi, hi*lo, hi*hi: small terms first
-            const CUtensorMap* mb = pass == 1 ? &map_b_lo : &map_b_hi;
-            for (int kb = k0; kb < k1; ++kb) {
-              mbar_wait(&empty[stage], phase ^ 1);
-              uint8_t* sa = smem + stage * kStageBytes;
-              uint8_t* sb = sa + BM * BK * 4;
-              mbar_expect_tx(&full[stage], kStageBytes);
-              tma_load_2d(ma, &full[stage], sa, kb * BK, row_a);
-              tma_load_2d(mb, &full[stage], sb, kb * BK, row_b);
-              if (++stage == kStages) { stage = 0; phase ^= 1; }
-            }
-          }
+        // every k-block brings its four operand tiles once; the three products of the split are formed from them
+        // (the earlier version re-loaded a tile pair per product: 1.5x the L2 -> shared-memory traffic, which is what
+        // bounds this kernel)
+        for (int kb = 0; kb < P.kblocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* st = smem + stage * kStageBytes;
+          mbar_expect_tx(&full[stage], kStageBytes);
+          tma_load_2d(&map_a_hi, &full[stage], st, kb * BK, row_a);
+          tma_load_2d(&map_a_lo, &full[stage], st + kTileABytes, kb * BK, row_a);
+          tma_load_2d(&map_b_hi, &full[stage], st + 2 * kTileABytes, kb * BK, row_b);
+          tma_load_2d(&map_b_lo, &full[stage], st + 2 * kTileABytes + kTileBBytes, kb * BK, row_b);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -195,17 +194,21 @@ pdist_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         mbar_wait(&tempty[as], aphase ^ 1);  // epilogue has drained this accumulator stage
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
-        const int total_kb = 3 * (min(k0 + P.kchunk, P.kblocks) - k0);
+        const int total_kb = min(k0 + P.kchunk, P.kblocks) - k0;
         for (int it = 0; it < total_kb; ++it) {
           mbar_wait(&full[stage], phase);
           tcgen05_fence_after();
           if (lane == 0) {
-            const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-            const uint32_t sb = sa + BM * BK * 4;
-            const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
+            const uint32_t s0 = smem_u32(smem + stage * kStageBytes);
+            const uint64_t a_hi = make_smem_desc(s0), a_lo = make_smem_desc(s0 + kTileABytes);
+            const uint64_t b_hi = make_smem_desc(s0 + 2 * kTileABytes), b_lo = make_smem_desc(s0 + 2 * kTileABytes + kTileBBytes);
+            // lo*hi, hi*lo, hi*hi (small terms first); advance 8 floats = 32 bytes inside the swizzle row: +2 in the >>4 address field
 #pragma unroll
-            for (int k = 0; k < BK / 8; ++k)  // advance 8 floats = 32 bytes inside the swizzle row: +2 in the >>4 address field
-              tcgen05_mma_tf32(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc, (it | k) != 0);
+            for (int k = 0; k < BK / 8; ++k) tcgen05_mma_tf32(tmem_d, a_lo + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), kIdesc, (it | k) != 0);
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k) tcgen05_mma_tf32(tmem_d, a_hi + (uint64_t)(2 * k), b_lo + (uint64_t)(2 * k), kIdesc, 1);
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k) tcgen05_mma_tf32(tmem_d, a_hi + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), kIdesc, 1);
             tcgen05_commit(&empty[stage]);                       // frees the smem stage once these MMAs retire
             if (it == total_kb - 1) tcgen05_commit(&tfull[as]);  // chunk complete -> epilogue
           }

@@ -1679,7 +1679,7 @@ static bool use_sweep_reducer() {
 static Layout make_layout(void* ws, int n, int batch, int maxdim, int cap1, size_t pool_bytes, int sm_count) {
   Layout L;
   memset(&L, 0, sizeof(L));
-  L.sweep = use_sweep_reducer();
+  L.sweep = use_sweep_reducer() && n <= 8192;   // the row sweep keeps <= 8 words of a row per resolver lane; larger clouds use the key bitset
   const int64_t E = (int64_t)n * (n - 1) / 2;
   const int64_t BE = (int64_t)batch * E;
   Carver c(ws, ~size_t(0));
@@ -1891,7 +1891,7 @@ static int rips_enqueue(const float* dm, int n, int batch, int maxdim, float thr
         else if (L.xw <= 64) TDA_SWEEP_LAUNCH(2);
         else if (L.xw <= 128) TDA_SWEEP_LAUNCH(4);
         else if (L.xw <= 256) TDA_SWEEP_LAUNCH(8);
-        else return set_error(TDA_ERR_UNSUPPORTED, "tda_rips: n=%d > 8192 needs TDA_RIPS_REDUCER=bitset", n);
+        else return set_error(TDA_ERR_UNSUPPORTED, "tda_rips: internal: sweep reducer selected for n=%d", n);
 #undef TDA_SWEEP_LAUNCH
       } else {
         const size_t s1_bytes = (size_t)(((L.wbits >> kPageShift) + 31) / 32) * sizeof(uint32_t);

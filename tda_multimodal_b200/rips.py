@@ -106,7 +106,7 @@ def _default_sizes(torch, dm, cap1, pool_bytes):
     free_bytes = torch.cuda.mem_get_info(dev)[0]
     if pool_bytes is None:
         E = n * (n - 1) // 2
-        if os.environ.get("TDA_RIPS_REDUCER") == "bitset":
+        if os.environ.get("TDA_RIPS_REDUCER") == "bitset" or n > 8192:
             # half of the pool holds one key window (bitset over the E*n triangle keys, <= 2^32 bits) per resident CTA,
             # the other half the reduction columns of finished columns
             sms = torch.cuda.get_device_properties(dev).multi_processor_count
