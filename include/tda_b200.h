@@ -89,10 +89,12 @@ int tda_fuzzy_graph(const int32_t* knn_idx, const float* knn_dist, const float* 
                     float mix_ratio, int n_epochs, int32_t* head, int32_t* tail, float* weight, float* eps, float* max_weight,
                     void* stream);
 /* tda_umap_sgd: optimize_layout_euclidean.  Y [batch,n_head,dim] in/out; Y_other [batch,n_tail,dim] (NULL and
- *   move_other=1 for fit: tail == head embedding); slot table as produced above; dim 1..4. */
+ *   move_other=1 for fit: tail == head embedding); slot table as produced above; dim 1..4.
+ *   ws (optional, 16-byte aligned, >= 16 * batch * (n_head + (move_other ? 0 : n_tail)) bytes): for dim == 3 the embedding is
+ *   padded to float4 there for the duration of the call (one 16-byte load and one vector atomic per point). */
 int tda_umap_sgd(float* Y, const float* Y_other, const int32_t* head, const int32_t* tail, const float* eps, int slots, int n_head,
                  int n_tail, int dim, int batch, int n_epochs, float a, float b, float gamma, float alpha0,
-                 float negative_sample_rate, int move_other, uint64_t seed, void* stream);
+                 float negative_sample_rate, int move_other, uint64_t seed, void* ws, size_t ws_bytes, void* stream);
 int tda_umap_init_random(float* Y, int n, int dim, int batch, float lo, float hi, uint64_t seed, void* stream);
 /* noisy_scale_coords (max|Y| -> 10, + N(0,noise)) followed by the per-axis rescale to [0,10] */
 int tda_umap_rescale(float* Y, int n, int dim, int batch, float noise, uint64_t seed, void* stream);

@@ -24,7 +24,7 @@ PROTOTYPES = {
     "tda_fuzzy_graph": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p]),
     "tda_umap_sgd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
-                             c_float, c_float, c_float, c_float, c_int, ctypes.c_uint64, c_void_p]),
+                             c_float, c_float, c_float, c_float, c_int, ctypes.c_uint64, c_void_p, c_size_t, c_void_p]),
     "tda_umap_init_random": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, ctypes.c_uint64, c_void_p]),
     "tda_umap_rescale": (c_int, [c_void_p, c_int, c_int, c_int, c_float, ctypes.c_uint64, c_void_p]),
     "tda_umap_transform_init": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,

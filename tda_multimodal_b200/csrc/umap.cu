@@ -279,6 +279,77 @@ __global__ void __launch_bounds__(256) sgd_epoch_kernel(float* __restrict__ Yh, 
   for (int d = 0; d < DIM; ++d) atomicAdd(&yh[d], delta[d]);
 }
 
+// 3-D embeddings (the reference's n_components=3) padded to float4: one 16-byte load per point and ONE vector float atomic
+// (red.global.add.v4.f32, sm_90+) per moved endpoint instead of three scalar ones -- the per-epoch kernel is bound by the
+// atomic throughput of L2.  Same schedule, RNG keys and update rule as sgd_epoch_kernel<3>.
+__global__ void pack4_kernel(const float* __restrict__ Y, float4* __restrict__ Y4, size_t npts) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < npts) Y4[i] = make_float4(Y[3 * i], Y[3 * i + 1], Y[3 * i + 2], 0.f);
+}
+__global__ void unpack4_kernel(const float4* __restrict__ Y4, float* __restrict__ Y, size_t npts) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < npts) { const float4 v = Y4[i]; Y[3 * i] = v.x; Y[3 * i + 1] = v.y; Y[3 * i + 2] = v.z; }
+}
+__global__ void __launch_bounds__(256) sgd_epoch_kernel_v4(float4* __restrict__ Yh, float4* __restrict__ Yt, const int* __restrict__ head,
+                                                           const int* __restrict__ tail, const float* __restrict__ eps_arr, int slots, int n_head,
+                                                           int n_tail, int epoch, float a, float b, float gamma, float alpha, float nsr,
+                                                           int move_other, uint64_t seed) {
+  const int p = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= slots) return;
+  const float eps = eps_arr[(size_t)p * slots + e];
+  if (!(eps > 0.f)) return;
+  const int q = (int)floorf((float)epoch / eps);
+  if (q < 1 || q <= (int)floorf((float)(epoch - 1) / eps)) return;
+  const int j = head[(size_t)p * slots + e], kk = tail[(size_t)p * slots + e];
+  float4* yh = Yh + (size_t)p * n_head + j;
+  float4* yt = Yt + (size_t)p * n_tail + kk;
+  const float4 c4 = __ldcg(yh), o4 = __ldcg(yt);
+  float cur[3] = {c4.x, c4.y, c4.z};
+  const float oth[3] = {o4.x, o4.y, o4.z};
+  float delta[3] = {0.f, 0.f, 0.f}, dt[3];
+  float d2 = 0.f;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) { const float t = cur[d] - oth[d]; d2 += t * t; }
+  float g = 0.f;
+  if (d2 > 0.f) {
+    const float pw = __powf(d2, b - 1.f);
+    g = (-2.f * a * b * pw) / (a * pw * d2 + 1.f);
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const float gd = clip4(g * (cur[d] - oth[d])) * alpha;
+    cur[d] += gd; delta[d] += gd; dt[d] = -gd;
+  }
+  if (move_other) atomicAdd(yt, make_float4(dt[0], dt[1], dt[2], 0.f));
+  const float epsn = eps / nsr;
+  int tot = (int)floorf((float)epoch / epsn) - 1;
+  if (q > 1) {
+    const int prev = (int)ceilf((float)(q - 1) * eps);
+    tot -= (int)floorf((float)prev / epsn) - 1;
+  }
+  for (int s = 0; s < tot; ++s) {
+    const uint32_t r = mix32(seed ^ ((uint64_t)p << 52) ^ ((uint64_t)e << 20) ^ ((uint64_t)epoch << 4) ^ (uint64_t)s ^ ((uint64_t)s << 40));
+    const int kn = (int)(r % (uint32_t)n_tail);
+    const float4 n4 = __ldcg(Yt + (size_t)p * n_tail + kn);
+    const float on[3] = {n4.x, n4.y, n4.z};
+    float dn = 0.f;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { const float t = cur[d] - on[d]; dn += t * t; }
+    float gn = 0.f;
+    if (dn > 0.f) gn = (2.f * gamma * b) / ((0.001f + dn) * (a * __powf(dn, b) + 1.f));
+    else if (move_other && j == kn) continue;
+    if (gn > 0.f) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const float gd = clip4(gn * (cur[d] - on[d])) * alpha;
+        cur[d] += gd; delta[d] += gd;
+      }
+    }
+  }
+  atomicAdd(yh, make_float4(delta[0], delta[1], delta[2], 0.f));
+}
+
 // ------------------------------------------------------------------------------------------------
 // initialisation helpers
 __device__ __forceinline__ float u01(uint64_t key) { return ((float)(mix32(key) >> 8) + 0.5f) * (1.f / 16777216.f); }
@@ -405,7 +476,7 @@ extern "C" int tda_fuzzy_graph(const int32_t* knn_idx, const float* knn_dist, co
 
 extern "C" int tda_umap_sgd(float* Y, const float* Y_other, const int32_t* head, const int32_t* tail, const float* eps, int slots, int n_head,
                             int n_tail, int dim, int batch, int n_epochs, float a, float b, float gamma, float alpha0,
-                            float negative_sample_rate, int move_other, uint64_t seed, void* stream_) {
+                            float negative_sample_rate, int move_other, uint64_t seed, void* ws, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!Y || !head || !tail || !eps || slots <= 0 || n_head <= 0 || n_tail <= 0 || batch <= 0 || n_epochs < 0)
     return set_error(TDA_ERR_INVALID, "tda_umap_sgd: bad arguments");
@@ -413,6 +484,22 @@ extern "C" int tda_umap_sgd(float* Y, const float* Y_other, const int32_t* head,
   if (dim < 1 || dim > 4) return set_error(TDA_ERR_UNSUPPORTED, "tda_umap_sgd: n_components=%d (supported: 1..4)", dim);
   dim3 g((slots + 255) / 256, batch);
   StageScope st(STAGE_SGD, stream);
+  const size_t np_h = (size_t)batch * n_head, np_t = move_other ? 0 : (size_t)batch * n_tail;
+  if (dim == 3 && ws && ws_bytes >= sizeof(float4) * (np_h + np_t) && (((uintptr_t)ws) & 15) == 0 && n_epochs > 0) {
+    float4* Yh4 = (float4*)ws;
+    float4* Yt4 = move_other ? Yh4 : Yh4 + np_h;
+    pack4_kernel<<<(unsigned)((np_h + 255) / 256), 256, 0, stream>>>(Y, Yh4, np_h);
+    if (!move_other) pack4_kernel<<<(unsigned)((np_t + 255) / 256), 256, 0, stream>>>(Y_other, Yt4, np_t);
+    for (int ep = 0; ep < n_epochs; ++ep) {
+      const float alpha = ep == 0 ? alpha0 : alpha0 * (1.f - (float)(ep - 1) / (float)n_epochs);
+      sgd_epoch_kernel_v4<<<g, 256, 0, stream>>>(Yh4, Yt4, head, tail, eps, slots, n_head, n_tail, ep, a, b, gamma, alpha, negative_sample_rate,
+                                                 move_other, seed);
+    }
+    unpack4_kernel<<<(unsigned)((np_h + 255) / 256), 256, 0, stream>>>(Yh4, Y, np_h);
+    count_launch(n_epochs + 2 + (move_other ? 0 : 1));
+    TDA_LAUNCH_CHECK();
+    return TDA_OK;
+  }
   for (int ep = 0; ep < n_epochs; ++ep) {
     const float alpha = ep == 0 ? alpha0 : alpha0 * (1.f - (float)(ep - 1) / (float)n_epochs);
 #define TDA_SGD_LAUNCH(DIM) sgd_epoch_kernel<DIM><<<g, 256, 0, stream>>>(Y, Y_other, head, tail, eps, slots, n_head, n_tail, ep, a, b, gamma, alpha, negative_sample_rate, move_other, seed)
