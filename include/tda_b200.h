@@ -160,10 +160,11 @@ int tda_rips(const float* dm, int n, int batch, int maxdim, float thresh,
 int tda_rips_launch(const float* dm, int n, int batch, int maxdim, float thresh,
                     float* h0_pairs, int64_t* h0_simplex, float* h1_pairs, int64_t* h1_simplex, int cap1,
                     int32_t* counts, float* thresh_out, void* ws, size_t ws_bytes, size_t pool_bytes, void* stream);
-/* device statistics of the last tda_rips call on this workspace: [batch,16] int64:
- * columns(non-MST edges<=thresh), apparent, reduced, additions, pushes, pops, horizon_extensions, max_V,
- * SM cycles in extract / owner lookup / apparent add / reduced-column add / horizon extension / finalise,
- * edges re-enumerated by reduced-column adds, edges re-enumerated by horizon extensions */
+/* device statistics of the last tda_rips call on this workspace: [batch,16] int64 (row-sweep reducer):
+ * columns (non-MST edges <= thresh), apparent pairs, reduced columns, column additions, rows streamed through the filter,
+ * pivots, restarts of a chunk (new vertex touched / reduced column added), largest |V|, then SM cycles of CTA thread 0 in:
+ * filter, (number of row groups), resolve||produce phase, reduced-column additions, flip write-out + patch phase,
+ * dense-mode switches; edges added through reduced columns, heavy rows */
 int tda_rips_stats(const void* ws, int n, int batch, int maxdim, int cap1, size_t pool_bytes, int64_t* stats_host);
 
 #ifdef __cplusplus

@@ -904,13 +904,12 @@ struct SweepSmem {
   int abort_flag, problem;
   int res_status, res_s, res_owner;
   uint32_t res_w;
-  unsigned long long additions, pivots, heavy_rows, restarts, groups, t_res;
+  unsigned long long additions, pivots, heavy_rows, restarts, groups;
 };
 
 template <int WPL>   // words of a row per lane of the resolver (W <= 32 * WPL)
 struct Sweeper {
   static constexpr uint64_t kEmpty = ~0ull;
-  static constexpr bool getenv_diag = false;
   const ReduceParams& P;
   SweepSmem& S;
   uint32_t* touched;   // [W]
@@ -1398,7 +1397,7 @@ struct Sweeper {
     if (tid == 0) {
       S.vcount = 0; S.vsel = 0; S.abort_flag = 0; S.dirty[0] = S.dirty[1] = 0; S.simple[0] = S.simple[1] = 0; S.both[0] = S.both[1] = 0; S.patched = 0; S.flipmask = 0;
       for (int q = 0; q < kGroupRows; ++q) S.conf[0][q] = S.conf[1][q] = 0;
-      S.additions = 0; S.pivots = 0; S.heavy_rows = 0; S.restarts = 0; S.groups = 0; S.t_res = 0;
+      S.additions = 0; S.pivots = 0; S.heavy_rows = 0; S.restarts = 0; S.groups = 0;
     }
     __threadfence();
     __syncthreads();
@@ -1612,7 +1611,7 @@ struct Sweeper {
       st[ST_PUSHES] = rows_swept;      // rows streamed through the filter
       st[ST_POPS] = S.pivots;
       st[ST_EXTENSIONS] = S.restarts;
-      st[ST_MAXV] = getenv_diag ? S.t_res : maxv;
+      st[ST_MAXV] = maxv;
       for (int q = 0; q < 6; ++q) st[ST_CYC_EXTRACT + q] = (unsigned long long)cyc[q];
       st[ST_BADD_EDGES] = badd_edges;
       st[ST_EXT_EDGES] = S.heavy_rows;
