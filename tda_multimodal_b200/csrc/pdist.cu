@@ -411,7 +411,7 @@ extern "C" int tda_pdist(const float* X, const float* Y, int n, int m, int d, in
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!X || !D || !ws || n <= 0 || d <= 0 || batch <= 0) return set_error(TDA_ERR_INVALID, "tda_pdist: bad arguments");
   if (metric < TDA_METRIC_SQEUCLIDEAN || metric > TDA_METRIC_DOT) return set_error(TDA_ERR_INVALID, "tda_pdist: unknown metric %d", metric);
-  const bool symmetric = (Y == nullptr || Y == X);
+  const bool symmetric = (Y == nullptr) || (Y == X && m == n);   // (a row block of X against all of X shares X's base pointer)
   if (symmetric) m = n;
   if (m <= 0) return set_error(TDA_ERR_INVALID, "tda_pdist: bad m");
   if ((int64_t)batch * n + BM >= (1ll << 31) || (int64_t)batch * m + BN >= (1ll << 31)) return set_error(TDA_ERR_UNSUPPORTED, "tda_pdist: too many rows");

@@ -111,6 +111,50 @@ def silhouette_score(Y, labels, dm=None):
     return float(out[0]) if single else out
 
 
+def knn_row_sharded(X, k, metric="cosine", rank=None, world=None, group=None, row_block=8192, local_connectivity=1.0):
+    """Exact kNN (+ sigma/rho) of ONE large cloud X [n,d] (CUDA, replicated on every rank) with the rows of the distance
+    matrix sharded over the ranks (config C5 of BASELINE.json): rank r computes rows
+    [r*n/G, (r+1)*n/G) x all columns, `row_block` rows at a time (the n x n matrix is never materialised), then the
+    [n/G, k] index / distance / sigma / rho blocks are exchanged with one all_gather each -- the only traffic of the path.
+    Returns (idx [1,n,k] int32, dist [1,n,k], sigma [1,n], rho [1,n]) on every rank, ready for umap_fit_batch(knn=...).
+    (The sigma floor of rows without a positive neighbour distance uses the mean distance of the row block, not of the
+    whole matrix; such rows only occur for duplicated points.)"""
+    torch = _lib.require_cuda()
+    import torch.distributed as dist
+    from .pdist import pdist
+    from .umap_ import DISCONNECTION_DISTANCES, knn_smooth
+    n = X.shape[0]
+    if rank is None:
+        rank = dist.get_rank(group) if (dist.is_available() and dist.is_initialized()) else 0
+    if world is None:
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    r0, r1 = (n * rank) // world, (n * (rank + 1)) // world
+    disc = float(DISCONNECTION_DISTANCES.get(metric, float("inf")))
+    Xc = X.contiguous()
+    parts = []
+    for b0 in range(r0, r1, row_block):
+        b1 = min(b0 + row_block, r1)
+        D = pdist(Xc[b0:b1][None], Xc[None], metric=metric, disconnect=disc)[0]      # [rows, n]
+        ar = torch.arange(b1 - b0, device=X.device)
+        D[ar, b0 + ar] = 0.0                                                          # the point itself, exactly (sklearn zeroes the diagonal)
+        parts.append(knn_smooth(D[None], k, local_connectivity=local_connectivity))
+        del D
+    local = [torch.cat([p[q][0] for p in parts], dim=0) for q in range(4)]            # idx, dist, sigma, rho of rows [r0, r1)
+    if world == 1 or not (dist.is_available() and dist.is_initialized()):
+        return tuple(t[None] for t in local)      # no process group: the caller gets this rank's rows only
+    # ragged row counts: pad every block to the largest, gather, trim
+    per = [(n * (r + 1)) // world - (n * r) // world for r in range(world)]
+    mx = max(per)
+    out = []
+    for t in local:
+        pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        pad[:t.shape[0]] = t
+        bufs = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(bufs, pad, group=group)
+        out.append(torch.cat([bufs[r][:per[r]] for r in range(world)], dim=0)[None])
+    return tuple(out)
+
+
 def bootstrap_rips(Y, n_resamples=256, size=1000, seed=4000, layer_ids=None, replace=False, maxdim=1, max_batch=256):
     """Config C4 of BASELINE.json: for every 3-D cloud Y[l] ([L,n,dim] CUDA tensor, e.g. the UMAP output of layer l),
     `n_resamples` bootstrap resamples of `size` points -> Rips H0/H1 of each, batched `max_batch` problems per call (the

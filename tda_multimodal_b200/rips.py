@@ -214,6 +214,23 @@ def greedy_permutation_device(dm, n_perm):
     return idx, lambdas
 
 
+def greedy_permutation_points(pts, n_perm):
+    """The same furthest-point sampling straight from the points (euclidean): no n x n matrix (clouds of 1e5 points)."""
+    torch = _lib.require_cuda()
+    n = pts.shape[0]
+    idx = torch.zeros(n_perm, dtype=torch.long, device=pts.device)
+    lambdas = torch.zeros(n_perm, dtype=torch.float32, device=pts.device)
+    P = pts.to(torch.float64)
+    ds = (P - P[0]).square().sum(1).sqrt().to(torch.float32)
+    for i in range(1, n_perm):
+        j = torch.argmax(ds)
+        idx[i] = j
+        lambdas[i - 1] = ds[j]
+        ds = torch.minimum(ds, (P - P[j]).square().sum(1).sqrt().to(torch.float32))
+    lambdas[-1] = ds.max()
+    return idx, lambdas
+
+
 def ripser(X, maxdim=1, thresh=np.inf, coeff=2, distance_matrix=False, do_cocycles=False, metric="euclidean", n_perm=None):
     """Drop-in for ``ripser.ripser`` (ripser.py): same arguments, same result keys; `dgms` are float64
     ``(n_k, 2)`` arrays (debug_tda_pipeline.py:124-127 json-dumps np.max of them, which needs float64)."""
@@ -244,6 +261,15 @@ def ripser(X, maxdim=1, thresh=np.inf, coeff=2, distance_matrix=False, do_cocycl
         if n_perm < 0:
             raise ValueError("Should be a strictly positive number of points in the greedy permutation")
     Xd = _as_cuda_f32(X)
+    if (n_perm is not None and n_perm < n and not distance_matrix and metric == "euclidean" and shape[1] <= 64 and n > 4096):
+        # large cloud + landmarks: sample from the points, build only the landmark matrix (and landmark-to-all distances)
+        idx_t, lambdas = greedy_permutation_points(Xd, n_perm)
+        dm = pdist_lowdim(Xd[idx_t][None])[0]
+        dperm2all = torch.cdist(Xd[idx_t].double(), Xd.double()).to(torch.float32)
+        res = rips_batch(dm[None], maxdim=maxdim, thresh=float(thresh))[0]
+        return {"dgms": res["dgms"], "cocycles": [[] for _ in range(maxdim + 1)], "num_edges": res["num_edges"],
+                "dperm2all": dperm2all if is_tensor else dperm2all.cpu().numpy(), "idx_perm": idx_t.cpu().numpy(),
+                "r_cover": float(lambdas[-1])}
     if distance_matrix:
         dm = Xd
     elif metric == "euclidean" and shape[1] <= 64:

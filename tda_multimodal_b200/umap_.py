@@ -178,8 +178,10 @@ def spectral_init(X, head, tail, weight, eps, n, dim, seed, metric):
 
 def umap_fit_batch(X, n_neighbors=15, n_components=2, metric="euclidean", n_epochs=None, learning_rate=1.0, init="spectral",
                    min_dist=0.1, spread=1.0, set_op_mix_ratio=1.0, local_connectivity=1.0, repulsion_strength=1.0,
-                   negative_sample_rate=5, random_state=None, a=None, b=None, return_state=False):
-    """fit_transform of B clouds at once.  X [B,n,d] float32 CUDA tensor -> embedding [B,n,n_components] (CUDA)."""
+                   negative_sample_rate=5, random_state=None, a=None, b=None, return_state=False, knn=None):
+    """fit_transform of B clouds at once.  X [B,n,d] float32 CUDA tensor -> embedding [B,n,n_components] (CUDA).
+    `knn` = (idx [B,n,k] int32, dist, sigma, rho) skips the distance / kNN stages (e.g. the row-sharded exact kNN of
+    pipeline.knn_row_sharded for clouds whose distance matrix should not be materialised on one GPU)."""
     torch = _lib.require_cuda()
     L = _lib.lib()
     assert X.is_cuda and X.dim() == 3
@@ -194,9 +196,13 @@ def umap_fit_batch(X, n_neighbors=15, n_components=2, metric="euclidean", n_epoc
         a, b = find_ab_params(spread, min_dist)
     seed = _seed_from(random_state)
     n_ep = int(n_epochs) if n_epochs is not None else (500 if n <= 10000 else 200)
-    D = distance_matrix(X, metric=metric)
-    idx, dist, sigma, rho = knn_smooth(D, k, local_connectivity=local_connectivity)
-    del D
+    if knn is None:
+        D = distance_matrix(X, metric=metric)
+        idx, dist, sigma, rho = knn_smooth(D, k, local_connectivity=local_connectivity)
+        del D
+    else:
+        idx, dist, sigma, rho = (t.contiguous() for t in knn)
+        assert idx.shape == (B, n, k), "knn must hold n_neighbors entries per point (self included)"
     # umap-learn prunes with max(n_epochs, default) > 10 semantics: weights below max/n_epochs are dropped
     head, tail, weight, eps = fuzzy_graph(idx, dist, sigma, rho, n_ep if n_ep > 10 else (500 if n <= 10000 else 200), set_op_mix_ratio)
     with torch.cuda.device(dev):

@@ -101,3 +101,43 @@ def test_workload_generators_are_seeded():
     assert idx.shape == (4, 100) and all(len(set(r)) == 100 for r in idx)
     c1 = workloads.c1_activations(n_layers=2, d=32)
     assert len(c1) == 48 and sum(v["metadata"]["type"] == "bound" for v in c1.values()) == 36
+
+
+def test_persim_plot_diagrams_with_stub_matplotlib(monkeypatch):
+    """persim.plot_diagrams(dgms, show=False) as the reference calls it (debug_tda_pipeline.py:140).  matplotlib is not in the
+    image, so a recording stub stands in for pyplot: what is checked is that the shim accepts ripser-style dgms (float64,
+    inf deaths, empty H1) and draws one scatter per dimension plus the diagonal and the infinity line."""
+    import types
+    calls = {"scatter": [], "plot": [], "legend": 0}
+
+    class Ax:
+        def plot(self, *a, **k): calls["plot"].append((a, k))
+        def scatter(self, x, y, *a, **k): calls["scatter"].append((np.asarray(x), np.asarray(y), k.get("label")))
+        def set_xlabel(self, *_): pass
+        def set_ylabel(self, *_): pass
+        def set_xlim(self, *_): pass
+        def set_ylim(self, *_): pass
+        def set_aspect(self, *_): pass
+        def set_title(self, *_): pass
+        def legend(self, **_): calls["legend"] += 1
+
+    ax = Ax()
+    plt = types.ModuleType("matplotlib.pyplot")
+    plt.gca = lambda: ax
+    plt.show = lambda: None
+    mpl = types.ModuleType("matplotlib")
+    mpl.pyplot = plt
+    monkeypatch.setitem(sys.modules, "matplotlib", mpl)
+    monkeypatch.setitem(sys.modules, "matplotlib.pyplot", plt)
+    monkeypatch.syspath_prepend(os.path.join(ROOT, "shims"))
+    sys.modules.pop("persim", None)
+    import persim
+    h0 = np.array([[0, 0.5], [0, 1.25], [0, np.inf]])
+    h1 = np.array([[1.0, 1.5]])
+    persim.plot_diagrams([h0, h1], show=False)
+    assert len(calls["scatter"]) == 2 and calls["scatter"][0][2] == "$H_{0}$" and calls["legend"] == 1
+    assert np.isfinite(calls["scatter"][0][1]).all()          # the infinite bar is drawn on the infinity line
+    assert len(calls["plot"]) == 2                            # diagonal + infinity line
+    persim.plot_diagrams([h0, np.zeros((0, 2))], show=False)  # empty H1 (happens on the reference's own clouds)
+    assert persim.bottleneck(h1, h1) == 0.0
+    sys.modules.pop("persim", None)
