@@ -1313,8 +1313,36 @@ struct Sweeper {
       uint32_t* r = rbase + (size_t)s * W;
       const uint32_t* lm = lmbase + (size_t)s * W;
       uint32_t rw[WPL];
+      uint32_t anyw = 0, diffw = 0;
 #pragma unroll
-      for (int q = 0; q < WPL; ++q) rw[q] = (lane + 32 * q) < W ? r[lane + 32 * q] : 0u;
+      for (int q = 0; q < WPL; ++q) {
+        const bool ok = (lane + 32 * q) < W;
+        rw[q] = ok ? r[lane + 32 * q] : 0u;
+        anyw |= rw[q];
+        diffw |= rw[q] ^ (ok ? lm[lane + 32 * q] : 0u);
+      }
+      // a row that was patched (or formed before its endpoints were touched) is usually all-or-nothing again: re-test its class
+      if (!__any_sync(0xffffffffu, anyw != 0)) continue;
+      if (!__any_sync(0xffffffffu, diffw != 0) && tbit(c) && tbit(d)) {
+        flipmask |= 1u << s;
+        ++pivots;
+        ++additions;
+        if (cm) {
+          bool patched = false;
+          if ((cm >> lane) & 1u) {
+            int vb = -1;
+            if (myc == c) vb = (int)d; else if (myc == d) vb = (int)c; else if (myd == c) vb = (int)d; else if (myd == d) vb = (int)c;
+            if (vb >= 0) {
+              const uint32_t m = 1u << (vb & 31);
+              if (lmbase[(size_t)lane * W + (vb >> 5)] & m) { rbase[(size_t)lane * W + (vb >> 5)] ^= m; patched = true; }
+            }
+          }
+          const uint32_t pm = __ballot_sync(0xffffffffu, patched);
+          mask |= pm;
+          fast &= ~pm;
+        }
+        continue;
+      }
       for (;;) {
         int best = -1;
 #pragma unroll
