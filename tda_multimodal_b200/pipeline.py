@@ -47,24 +47,31 @@ def layer_sweep(X, n_neighbors=15, n_components=3, min_dist=0.1, metric="cosine"
     reductions of all groups overlap each other (tda_rips_launch does not synchronise)."""
     torch = _lib.require_cuda()
     Lc = X.shape[0]
+    on_host = not X.is_cuda     # a (pinned) host tensor: every chunk copies its own layers on its own stream, so the copy of
+    dev = torch.device("cuda", torch.cuda.current_device()) if on_host else X.device   # one chunk overlaps the compute of another
     if chunks is None:
         chunks = int(os.environ.get("TDA_SWEEP_CHUNKS", "0")) or (2 if Lc >= 8 else 1)
     chunks = max(1, min(int(chunks), Lc))
     if chunks == 1:
+        if on_host:
+            X = X.to(device=dev, dtype=torch.float32, non_blocking=True)
         Y = umap_fit_batch(X, n_neighbors=n_neighbors, n_components=n_components, metric=metric, min_dist=min_dist,
                            random_state=random_state, n_epochs=n_epochs)
         res = rips_batch(pdist_lowdim(Y), maxdim=maxdim)
         return {"embedding": Y if return_embedding else None, "results": res}
-    cur = torch.cuda.current_stream(X.device)
+    cur = torch.cuda.current_stream(dev)
     bounds = [(Lc * c) // chunks for c in range(chunks + 1)]
-    streams = _sweep_streams(X.device, chunks)
+    streams = _sweep_streams(dev, chunks)
     Ys, jobs = [], []
     for c in range(chunks):
         st = streams[c]
         st.wait_stream(cur)
         with torch.cuda.stream(st):
             Xc = X[bounds[c]:bounds[c + 1]]
-            Xc.record_stream(st)
+            if on_host:
+                Xc = Xc.to(device=dev, dtype=torch.float32, non_blocking=True)
+            else:
+                Xc.record_stream(st)
             Y = umap_fit_batch(Xc, n_neighbors=n_neighbors, n_components=n_components, metric=metric, min_dist=min_dist,
                                random_state=random_state, n_epochs=n_epochs)
             jobs.append(rips_batch_launch(pdist_lowdim(Y), maxdim=maxdim))
@@ -194,9 +201,11 @@ def layer_sweep_host(X_host, device=None, **kw):
     ({'embedding': float32 ndarray [L,n,3], 'results': [...]})."""
     torch = _lib.require_cuda()
     Xt = X_host if isinstance(X_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(X_host))
+    if Xt.dtype != torch.float32:
+        Xt = Xt.to(torch.float32)     # check_array(dtype=float32) of umap-learn, on the host
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
-    Xd = Xt.to(device=dev, dtype=torch.float32, non_blocking=True)
-    out = layer_sweep(Xd, **kw)
+    with torch.cuda.device(dev):
+        out = layer_sweep(Xt, **kw)
     out["embedding"] = out["embedding"].cpu().numpy() if out["embedding"] is not None else None
     return out
 
