@@ -1234,9 +1234,7 @@ struct Sweeper {
     if (!flipmask || l2 >= ns_next) return;
     const int nb = buf ^ 1;
     const uint32_t c2 = S.row_c[nb][l2], d2 = S.row_d[nb][l2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int f = (tid >> 5) + h * kSweepWarps;
+    for (int f = tid >> 5; f < kGroupRows; f += kSweepWarps) {
       if (!((flipmask >> f) & 1u)) continue;
       const uint32_t c = S.row_c[buf][f], d = S.row_d[buf][f];
       int vb = -1;
@@ -1254,9 +1252,7 @@ struct Sweeper {
     const int l2 = tid & 31;
     if (l2 >= ns) return;
     const uint32_t c2 = S.row_c[buf][l2], d2 = S.row_d[buf][l2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int f = (tid >> 5) + h * kSweepWarps;
+    for (int f = tid >> 5; f < kGroupRows; f += kSweepWarps) {
       if (f >= l2) continue;
       const uint32_t c = S.row_c[buf][f], d = S.row_d[buf][f];
       if (c2 == c || c2 == d || d2 == c || d2 == d) atomicOr(&S.conf[buf][f], 1u << l2);
