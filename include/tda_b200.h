@@ -160,6 +160,15 @@ int tda_rips(const float* dm, int n, int batch, int maxdim, float thresh,
 int tda_rips_launch(const float* dm, int n, int batch, int maxdim, float thresh,
                     float* h0_pairs, int64_t* h0_simplex, float* h1_pairs, int64_t* h1_simplex, int cap1,
                     int32_t* counts, float* thresh_out, void* ws, size_t ws_bytes, size_t pool_bytes, void* stream);
+/* tda_rips_h2: H2 (optional `maxdim=2` of ripser(X, maxdim)) on top of a FINISHED tda_rips(maxdim=1) call: `ws1` is that
+ * call's workspace (with the same n, batch, cap1, pool_bytes1), which still holds the rank matrix and the H1 pivots (clearing).
+ * Triangles in an apparent pair with a tetrahedron are skipped in parallel, the residual triangle columns are reduced like the
+ * H1 columns (implicit cohomology over Z/2, working column = bitset over tetrahedron keys).  n <= 1024.
+ *   h2_pairs [batch,cap2,2] float32 (birth, death), death > birth; counts2 [batch,4] int32: -, n_h2 rows, -, status;
+ *   cap2 a power of two; returns TDA_ERR_CAPACITY (after synchronising) if a problem overflowed cap2 or the pool. */
+size_t tda_rips_h2_workspace_bytes(int n, int batch, int cap2, size_t pool_bytes);
+int tda_rips_h2(const void* ws1, int n, int batch, int cap1, size_t pool_bytes1, float* h2_pairs, int cap2, int32_t* counts2,
+                void* ws2, size_t ws2_bytes, size_t pool_bytes2, void* stream);
 /* device statistics of the last tda_rips call on this workspace: [batch,16] int64 (row-sweep reducer):
  * columns (non-MST edges <= thresh), apparent pairs, reduced columns, column additions, rows streamed through the filter,
  * pivots, restarts of a chunk (new vertex touched / reduced column added), largest |V|, then SM cycles of CTA thread 0 in:

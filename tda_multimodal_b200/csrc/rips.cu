@@ -23,6 +23,7 @@
 #include "../../include/tda_b200.h"
 #include <cub/device/device_radix_sort.cuh>
 #include <cfloat>
+#include <vector>
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
@@ -371,6 +372,7 @@ struct ReduceParams {
   uint32_t* vpool; int64_t vpool_cap;       // [batch, vpool_cap]
   int64_t* vstart; int* vlen;               // [batch, cap1]
   int* work_counter; unsigned long long* stats;  // [batch, ST_N]
+  const short* apex4;                       // (H2) [batch, E*n] per triangle key: the vertex of its apparent cofacet, or -1
 };
 
 struct ReduceSmem {
@@ -382,6 +384,11 @@ struct ReduceSmem {
   unsigned long long toggles;
 };
 
+// DIM = 1: columns are edges (by rank), rows triangles, key = rank(longest edge) * n + (n-1-opposite vertex)          (H1)
+// DIM = 2: columns are triangles (by that key), rows tetrahedra, key = rank(longest edge) * n^2 + (n-1-p) * n + (n-1-q), p > q
+//          the two vertices off the longest edge.  Ascending key order refines the diameter, faces precede cofaces: a valid
+//          simplex-wise filtration, so the (birth, death) values of the diagram do not depend on the tie-break.        (H2)
+template <int DIM>
 struct Reducer {
   static constexpr uint64_t kEmpty = ~0ull;
   const ReduceParams& P;
@@ -520,7 +527,35 @@ struct Reducer {
     if (!(s1[page >> 5] & m)) atomicOr(&s1[page >> 5], m);
   }
   // cofacets of edge `re` with key in [lo, wbase + wbits): vertices strided over `nthr` threads
-  __device__ __forceinline__ void gen(int re, uint64_t lo, int t0, int nthr) { gen(re, __ldg(&EN[re]), lo, t0, nthr); }
+  __device__ __forceinline__ void gen(int re, uint64_t lo, int t0, int nthr) {
+    if constexpr (DIM == 1) gen(re, __ldg(&EN[re]), lo, t0, nthr);
+    else gen_tri((uint32_t)re, lo, t0, nthr);
+  }
+  // cofacets (tetrahedra) of the triangle with key k3 = M * n + (n-1-w)
+  __device__ __forceinline__ void gen_tri(uint32_t k3, uint64_t lo, int t0, int nthr) {
+    const int M = (int)(k3 / (uint32_t)n);
+    const int w = n - 1 - (int)(k3 - (uint32_t)M * (uint32_t)n);
+    const uint32_t e = __ldg(&EN[M]);
+    const int x = (int)(e >> 16), y = (int)(e & 0xffffu);
+    const int* rowx = R + (size_t)x * n;
+    const int* rowy = R + (size_t)y * n;
+    const int* roww = R + (size_t)w * n;
+    const uint64_t hi = wbase + wbits;
+    const uint64_t n2 = (uint64_t)n * (uint64_t)n;
+    for (int v = t0; v < n; v += nthr) {
+      const int rx = __ldg(&rowx[v]), ry = __ldg(&rowy[v]), rw = __ldg(&roww[v]);   // v in {x,y,w}: kRankDiag -> skipped below
+      const int M4 = max(max(M, rx), max(ry, rw));
+      if (M4 >= T) continue;
+      int p2, q2;   // the two vertices off the longest edge
+      if (M4 == M) { p2 = w; q2 = v; }
+      else if (M4 == rx) { p2 = y; q2 = w; }
+      else if (M4 == ry) { p2 = x; q2 = w; }
+      else { p2 = x; q2 = y; }
+      const int hi_v = max(p2, q2), lo_v = min(p2, q2);
+      const uint64_t key = (uint64_t)M4 * n2 + (uint64_t)(n - 1 - hi_v) * (uint64_t)n + (uint64_t)(n - 1 - lo_v);
+      if (key >= lo && key < hi) toggle_key(key);
+    }
+  }
   __device__ __forceinline__ void gen(int re, uint32_t e, uint64_t lo, int t0, int nthr) {
     const int a = (int)(e >> 16), b = (int)(e & 0xffffu);
     const int* rowa = R + (size_t)a * n;
@@ -701,7 +736,9 @@ struct Reducer {
     n_refills = n_passes = 0;
     __threadfence();
     __syncthreads();
-    const uint64_t kmax = (uint64_t)T * (uint64_t)n;  // keys are < kmax
+    const uint64_t n2 = (uint64_t)n * (uint64_t)n;
+    const short* A4 = DIM == 2 ? P.apex4 + (size_t)p * (size_t)P.E * (size_t)n : nullptr;
+    const uint64_t kmax = DIM == 1 ? (uint64_t)T * (uint64_t)n : (uint64_t)T * n2;  // keys are < kmax
     int nrows = 0;
     int64_t vpool_used = 0;
     unsigned long long additions = 0, slides = 0, maxv = 0, pops = 0;
@@ -712,8 +749,9 @@ struct Reducer {
     int64_t* outs = P.h1_simplex ? P.h1_simplex + (size_t)p * P.cap1 * 2 : nullptr;
 
     for (int ci = nb - 1; ci >= 0; --ci) {
-      const int rbirth = bl[ci];
-      const uint64_t first = (uint64_t)(rbirth + 1) * (uint64_t)n;  // the lune of rbirth is empty: every cofacet key is >= first
+      const int rbirth = bl[ci];   // DIM 1: rank of the birth edge; DIM 2: key of the birth triangle
+      // DIM 1: the lune of rbirth is empty, every cofacet key is >= (rbirth+1)*n.  DIM 2: a cofacet's longest edge is >= the triangle's
+      const uint64_t first = DIM == 1 ? (uint64_t)(rbirth + 1) * (uint64_t)n : (uint64_t)((uint32_t)rbirth / (uint32_t)n) * n2;
       wbase = first & ~((1ull << kPageShift) - 1);
       nbase = 0;
       uint64_t pos = first - wbase;
@@ -746,18 +784,30 @@ struct Reducer {
         const uint64_t pk = wbase + pos;
         t0 = clock64();
         int M, w;
-        if ((pk >> 32) == 0) { M = (int)((uint32_t)pk / (uint32_t)n); w = n - 1 - (int)((uint32_t)pk - (uint32_t)M * (uint32_t)n); }
-        else { M = (int)(pk / (uint64_t)n); w = n - 1 - (int)(pk % (uint64_t)n); }
-        const uint2 eaM = __ldg(&EA[M]);
+        uint2 eaM = make_uint2(0, 0);
         int owner = -2;  // -1 none, -2 apparent, >=0 reduced column id
-        if ((int)eaM.y != w) owner = hash_find(pk);
+        if constexpr (DIM == 1) {
+          if ((pk >> 32) == 0) { M = (int)((uint32_t)pk / (uint32_t)n); w = n - 1 - (int)((uint32_t)pk - (uint32_t)M * (uint32_t)n); }
+          else { M = (int)(pk / (uint64_t)n); w = n - 1 - (int)(pk % (uint64_t)n); }
+          eaM = __ldg(&EA[M]);
+          if ((int)eaM.y != w) owner = hash_find(pk);
+        } else {
+          // tetrahedron (M4; p > q): its youngest facet is the triangle (M4, q); the pair is apparent iff that triangle's first
+          // cofacet is this tetrahedron, i.e. apex4[(M4, q)] == p.  M holds the facet's key, the column that owns the pivot.
+          const uint64_t M4 = pk / n2, rem = pk - M4 * n2;
+          const int pv = n - 1 - (int)(rem / (uint64_t)n), qv = n - 1 - (int)(rem % (uint64_t)n);
+          M = (int)(M4 * (uint64_t)n + (uint64_t)(n - 1 - qv));
+          w = pv;
+          if ((int)A4[M] != pv) owner = hash_find(pk);
+        }
         cyc[1] += clock64() - t0;
         if (owner == -1) { pivot = pk; break; }
         ++additions;
         t0 = clock64();
         if (owner == -2) {
           if (tid == 0) v_toggle(M);
-          gen(M, eaM.x, pk, tid, kReduceThreads);
+          if constexpr (DIM == 1) gen(M, eaM.x, pk, tid, kReduceThreads);
+          else gen_tri((uint32_t)M, pk, tid, kReduceThreads);
           publish();
           cyc[2] += clock64() - t0;
         } else {
@@ -794,14 +844,18 @@ struct Reducer {
       } else {
         for (uint32_t i = tid; i < s1words; i += kReduceThreads) s1[i] = 0;
       }
-      const float birth = SD[rbirth];
+      const float birth = DIM == 1 ? SD[rbirth] : SD[(uint32_t)rbirth / (uint32_t)n];
       float death = INFINITY;
       int Md = -1, wd = -1;
-      if (!essential) { Md = (int)(pivot / (uint64_t)n); wd = n - 1 - (int)(pivot % (uint64_t)n); death = SD[Md]; }
+      if (!essential) {
+        if constexpr (DIM == 1) { Md = (int)(pivot / (uint64_t)n); wd = n - 1 - (int)(pivot % (uint64_t)n); }
+        else Md = (int)(pivot / n2);
+        death = SD[Md];
+      }
       if (essential || death > birth) {
         if (tid == 0) {
           out[2 * nrows] = birth; out[2 * nrows + 1] = death;
-          if (outs) {
+          if (DIM == 1 && outs) {
             const uint32_t e = EN[rbirth];
             outs[2 * nrows] = edge_index((int)(e >> 16), (int)(e & 0xffffu));
             if (essential) outs[2 * nrows + 1] = -1;
@@ -850,10 +904,11 @@ struct Reducer {
   }
 };
 
+template <int DIM>
 __global__ void __launch_bounds__(kReduceThreads) rips_reduce_kernel(const __grid_constant__ ReduceParams P) {
   __shared__ ReduceSmem S;
   extern __shared__ uint32_t s1_dyn[];
-  Reducer red(P, S, s1_dyn);
+  Reducer<DIM> red(P, S, s1_dyn);
   for (;;) {
     if (threadIdx.x == 0) S.problem = atomicAdd(P.work_counter, 1);
     __syncthreads();
@@ -1660,6 +1715,83 @@ __global__ void __launch_bounds__(kSweepThreads, 1) rips_sweep_kernel(const __gr
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// H2 pre-pass (runs after the H1 stage on the same rank matrix)
+//  h2_clear_kernel    : bitset of the triangles that are H1 death simplices (apparent pairs (r, apex[r]) and the pivots of the
+//                       reduced H1 columns): they are not H2 columns (clearing)
+//  h2_apparent_kernel : one warp per edge M walks the triangles (M, w), w in lune(M): apex4 = the largest vertex v > w of the lune
+//                       with rank(w,v) < M, i.e. the oldest cofacet of the triangle has the same diameter and the triangle is
+//                       its youngest facet -- an apparent (zero-persistence) pair; triangles that are neither cleared nor
+//                       apparent are the residual H2 columns.
+__global__ void h2_clear_kernel(const uint2* __restrict__ ea, const int* __restrict__ Tarr, const uint64_t* __restrict__ hkeys, int hcap,
+                                int n, int64_t E, uint32_t* __restrict__ cbits, int64_t cwords) {
+  const int p = blockIdx.y;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t* cb = cbits + (size_t)p * cwords;
+  if (t < Tarr[p]) {
+    const int apex = (int)ea[(size_t)p * E + t].y;   // -2 for MST edges, -1 for an empty lune
+    if (apex >= 0) {
+      const uint64_t k = (uint64_t)t * (uint64_t)n + (uint64_t)(n - 1 - apex);
+      atomicOr(&cb[k >> 5], 1u << (k & 31));
+    }
+  }
+  if (t < hcap) {
+    const uint64_t k = hkeys[(size_t)p * hcap + t];
+    if (k != ~0ull) atomicOr(&cb[k >> 5], 1u << (k & 31));
+  }
+}
+
+constexpr int kH2MaxWords = 32;   // n <= 1024
+__global__ void __launch_bounds__(256) h2_apparent_kernel(const int* __restrict__ rank, const uint32_t* __restrict__ ends, const int* __restrict__ Tarr,
+                                                          int n, int64_t E, const uint32_t* __restrict__ cbits, int64_t cwords,
+                                                          short* __restrict__ apex4, int* __restrict__ blist2, int* __restrict__ bcount2, int cap2) {
+  const int p = blockIdx.y;
+  const int64_t M = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (M >= Tarr[p]) return;
+  const int W = (n + 31) >> 5;
+  const int* R = rank + (size_t)p * n * n;
+  const uint32_t e = ends[(size_t)p * E + M];
+  const int x = (int)(e >> 16), y = (int)(e & 0xffffu);
+  const int* Rx = R + (size_t)x * n;
+  const int* Ry = R + (size_t)y * n;
+  uint32_t lunew = 0;   // lane k holds word k of the lune mask
+  for (int k = 0; k < W; ++k) {
+    const int v = 32 * k + lane;
+    const bool in = v < n && Rx[v] < (int)M && Ry[v] < (int)M;
+    const unsigned b = __ballot_sync(0xffffffffu, in);
+    if (lane == k) lunew = b;
+  }
+  const uint32_t* cb = cbits + (size_t)p * cwords;
+  short* A4 = apex4 + (size_t)p * (size_t)E * (size_t)n;
+  for (int k = W - 1; k >= 0; --k) {
+    uint32_t word = __shfl_sync(0xffffffffu, lunew, k);
+    while (word) {
+      const int bit = 31 - __clz(word);
+      word &= ~(1u << bit);
+      const int w = 32 * k + bit;
+      const int* Rw = R + (size_t)w * n;
+      int found = -1;
+      for (int k2 = W - 1; k2 >= (w >> 5); --k2) {
+        const uint32_t lw = __shfl_sync(0xffffffffu, lunew, k2);
+        const int v = 32 * k2 + lane;
+        const bool ok = ((lw >> lane) & 1u) && v > w && Rw[v] < (int)M;
+        const unsigned b = __ballot_sync(0xffffffffu, ok);
+        if (b) { found = 32 * k2 + 31 - __clz(b); break; }
+      }
+      if (lane == 0) {
+        const uint64_t k3 = (uint64_t)M * (uint64_t)n + (uint64_t)(n - 1 - w);
+        A4[k3] = (short)found;
+        const bool cleared = (cb[k3 >> 5] >> (k3 & 31)) & 1u;
+        if (!cleared && found < 0) {
+          const int pos = atomicAdd(&bcount2[p], 1);
+          if (pos < cap2) blist2[(size_t)p * cap2 + pos] = (int)k3;
+        }
+      }
+    }
+  }
+}
+
 __global__ void finalize_stats_kernel(const int* __restrict__ T, const int* __restrict__ bcount, int n, int batch,
                                       unsigned long long* __restrict__ stats, const int32_t* __restrict__ counts) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1918,8 +2050,8 @@ static int rips_enqueue(const float* dm, int n, int batch, int maxdim, float thr
 #undef TDA_SWEEP_LAUNCH
       } else {
         const size_t s1_bytes = (size_t)(((L.wbits >> kPageShift) + 31) / 32) * sizeof(uint32_t);
-        TDA_CUDA_CHECK(cudaFuncSetAttribute(rips_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1_bytes));
-        rips_reduce_kernel<<<L.grid, kReduceThreads, s1_bytes, stream>>>(P);
+        TDA_CUDA_CHECK(cudaFuncSetAttribute(rips_reduce_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1_bytes));
+        rips_reduce_kernel<1><<<L.grid, kReduceThreads, s1_bytes, stream>>>(P);
       }
     }
     count_launch();
@@ -1962,5 +2094,124 @@ extern "C" int tda_rips_stats(const void* ws, int n, int batch, int maxdim, int 
   if (!ws || !stats_host) return set_error(TDA_ERR_INVALID, "tda_rips_stats: bad arguments");
   Layout L = make_layout((void*)ws, n, batch, maxdim, next_pow2(cap1), pool_bytes, sm_count_cached());
   TDA_CUDA_CHECK(cudaMemcpy(stats_host, L.stats, sizeof(int64_t) * ST_N * batch, cudaMemcpyDeviceToHost));
+  return TDA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// H2 on top of a finished H1 run
+namespace tda {
+namespace rips {
+struct Layout2 {
+  uint32_t* cbits; int64_t cwords; short* apex4; int* blist2; int* bcount2;
+  uint64_t* hkeys; int* hvals; int hcap; int64_t* vstart; int* vlen; uint32_t* vpool; int64_t vpool_cap;
+  uint32_t* bits; uint64_t wbits; uint32_t* vbits; int64_t vwords; uint32_t* vlist; int64_t vcap;
+  int* work_counter; unsigned long long* stats;
+  int grid; size_t total;
+};
+static Layout2 make_layout2(void* ws, int n, int batch, int cap2, size_t pool_bytes, int sm_count) {
+  Layout2 L;
+  memset(&L, 0, sizeof(L));
+  const int64_t E = (int64_t)n * (n - 1) / 2;
+  const int64_t K3 = E * n;   // triangle key space
+  Carver c(ws, ~size_t(0));
+  L.cwords = (K3 + 31) / 32 + 1;
+  L.cbits = c.take<uint32_t>((size_t)batch * L.cwords);
+  L.apex4 = c.take<short>((size_t)batch * K3);
+  L.blist2 = c.take<int>((size_t)batch * cap2);
+  L.bcount2 = c.take<int>(batch);
+  L.hcap = next_pow2(2 * cap2);
+  L.hkeys = c.take<uint64_t>((size_t)batch * L.hcap);
+  L.hvals = c.take<int>((size_t)batch * L.hcap);
+  L.vstart = c.take<int64_t>((size_t)batch * cap2);
+  L.vlen = c.take<int>((size_t)batch * cap2);
+  L.stats = c.take<unsigned long long>((size_t)batch * ST_N);
+  L.work_counter = c.take<int>(1);
+  L.grid = batch < 2 * sm_count ? batch : 2 * sm_count;
+  if (L.grid < 1) L.grid = 1;
+  L.vwords = L.cwords;
+  L.vbits = c.take<uint32_t>((size_t)L.grid * L.vwords);
+  L.vcap = (K3 < (int64_t)(16 << 20) ? K3 : (int64_t)(16 << 20)) + 1024;
+  L.vlist = c.take<uint32_t>((size_t)L.grid * 2 * L.vcap);
+  const uint64_t page = 1ull << kPageShift;
+  const double want_d = (double)E * (double)n * (double)n;
+  uint64_t want = want_d >= 4294967296.0 ? (1ull << 32) : (((uint64_t)want_d + 32 * page - 1) / (32 * page) * (32 * page));
+  if (want > (1ull << 32)) want = 1ull << 32;
+  uint64_t afford = (uint64_t)(pool_bytes / 2 / (size_t)L.grid) * 8 / (32 * page) * (32 * page);
+  if (afford < 32 * page) afford = 32 * page;
+  L.wbits = want < afford ? want : afford;
+  L.bits = c.take<uint32_t>((size_t)L.grid * (L.wbits >> 5));
+  const size_t bits_bytes = (size_t)L.grid * (L.wbits >> 3);
+  L.vpool_cap = pool_bytes > bits_bytes ? (int64_t)((pool_bytes - bits_bytes) / (size_t)batch / sizeof(uint32_t)) : 0;
+  if (L.vpool_cap < 4 * (int64_t)cap2) L.vpool_cap = 4 * (int64_t)cap2;
+  L.vpool = c.take<uint32_t>((size_t)batch * L.vpool_cap);
+  L.total = c.off;
+  return L;
+}
+}  // namespace rips
+}  // namespace tda
+
+extern "C" size_t tda_rips_h2_workspace_bytes(int n, int batch, int cap2, size_t pool_bytes) {
+  if (n <= 0 || batch <= 0 || cap2 <= 0) return 0;
+  return make_layout2(nullptr, n, batch, next_pow2(cap2), pool_bytes, 148).total + 4096;
+}
+
+extern "C" int tda_rips_h2(const void* ws1, int n, int batch, int cap1, size_t pool_bytes1, float* h2_pairs, int cap2, int32_t* counts2,
+                           void* ws2, size_t ws2_bytes, size_t pool_bytes2, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!ws1 || !h2_pairs || !counts2 || !ws2 || n <= 0 || batch <= 0 || cap2 <= 0) return set_error(TDA_ERR_INVALID, "tda_rips_h2: bad arguments");
+  if (n > 32 * kH2MaxWords) return set_error(TDA_ERR_UNSUPPORTED, "tda_rips_h2: n=%d > %d (H2 is implemented for small clouds)", n, 32 * kH2MaxWords);
+  if (next_pow2(cap2) != cap2) return set_error(TDA_ERR_INVALID, "tda_rips_h2: cap2 must be a power of two");
+  if (batch > 65535) return set_error(TDA_ERR_INVALID, "tda_rips_h2: batch > 65535");
+  const int sms = sm_count_cached();
+  Layout L1 = make_layout((void*)ws1, n, batch, 1, next_pow2(cap1), pool_bytes1, sms);
+  Layout2 L = make_layout2(ws2, n, batch, cap2, pool_bytes2, sms);
+  if (L.total > ws2_bytes) return set_error(TDA_ERR_WORKSPACE, "tda_rips_h2: workspace %zu < required %zu", ws2_bytes, L.total);
+  const int64_t E = (int64_t)n * (n - 1) / 2;
+  if (E == 0) { TDA_CUDA_CHECK(cudaMemsetAsync(counts2, 0, sizeof(int32_t) * 4 * batch, stream)); return TDA_OK; }
+  const int64_t K3 = E * n;
+  TDA_CUDA_CHECK(cudaMemsetAsync(counts2, 0, sizeof(int32_t) * 4 * batch, stream));
+  TDA_CUDA_CHECK(cudaMemsetAsync(L.cbits, 0, sizeof(uint32_t) * (size_t)batch * L.cwords, stream));
+  TDA_CUDA_CHECK(cudaMemsetAsync(L.apex4, 0xff, sizeof(short) * (size_t)batch * K3, stream));
+  TDA_CUDA_CHECK(cudaMemsetAsync(L.bcount2, 0, sizeof(int) * batch, stream));
+  TDA_CUDA_CHECK(cudaMemsetAsync(L.work_counter, 0, sizeof(int), stream));
+  TDA_CUDA_CHECK(cudaMemsetAsync(L.stats, 0, sizeof(unsigned long long) * batch * ST_N, stream));
+  TDA_CUDA_CHECK(cudaMemsetAsync(L.vbits, 0, sizeof(uint32_t) * (size_t)L.grid * L.vwords, stream));
+  TDA_CUDA_CHECK(cudaMemsetAsync(L.bits, 0, (size_t)L.grid * (L.wbits >> 3), stream));
+  {
+    const int64_t work = E > L1.hcap ? E : L1.hcap;
+    dim3 g((unsigned)((work + 255) / 256), batch);
+    h2_clear_kernel<<<g, 256, 0, stream>>>(L1.ea, L1.T, L1.hkeys, L1.hcap, n, E, L.cbits, L.cwords);
+    dim3 g2((unsigned)((E * 32 + 255) / 256), batch);
+    h2_apparent_kernel<<<g2, 256, 0, stream>>>(L1.rank, L1.ends, L1.T, n, E, L.cbits, L.cwords, L.apex4, L.blist2, L.bcount2, cap2);
+    count_launch(2);
+    TDA_LAUNCH_CHECK();
+  }
+  ReduceParams P;
+  memset(&P, 0, sizeof(P));
+  P.rank = L1.rank; P.ends = L1.ends; P.sdist = L1.sdist; P.T = L1.T; P.ea = L1.ea;
+  P.blist = L.blist2; P.bcount = L.bcount2;
+  P.n = n; P.E = E; P.batch = batch; P.cap1 = cap2;
+  P.h1_pairs = h2_pairs; P.h1_simplex = nullptr; P.counts = counts2;
+  P.bits = L.bits; P.wbits = L.wbits;
+  P.vbits = L.vbits; P.vwords = L.vwords; P.vlist = L.vlist; P.vcap = L.vcap;
+  P.hkeys = L.hkeys; P.hvals = L.hvals; P.hcap = L.hcap;
+  P.vpool = L.vpool; P.vpool_cap = L.vpool_cap; P.vstart = L.vstart; P.vlen = L.vlen;
+  P.work_counter = L.work_counter; P.stats = L.stats;
+  P.apex4 = L.apex4;
+  {
+    const size_t s1_bytes = (size_t)(((L.wbits >> kPageShift) + 31) / 32) * sizeof(uint32_t);
+    TDA_CUDA_CHECK(cudaFuncSetAttribute(rips_reduce_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1_bytes));
+    rips_reduce_kernel<2><<<L.grid, kReduceThreads, s1_bytes, stream>>>(P);
+    count_launch();
+    TDA_LAUNCH_CHECK();
+  }
+  TDA_CUDA_CHECK(cudaStreamSynchronize(stream));
+  {
+    std::vector<int32_t> hc((size_t)batch * 4);
+    TDA_CUDA_CHECK(cudaMemcpy(hc.data(), counts2, sizeof(int32_t) * 4 * batch, cudaMemcpyDeviceToHost));
+    for (int p = 0; p < batch; ++p)
+      if (hc[p * 4 + 3] != 0)
+        return set_error(TDA_ERR_CAPACITY, "tda_rips_h2: problem %d overflowed (cap2=%d or pool %zu bytes); retry with larger sizes", p, cap2, pool_bytes2);
+  }
   return TDA_OK;
 }

@@ -124,7 +124,7 @@ def rips_batch_launch(dm, maxdim=1, thresh=float("inf"), cap1=None, pool_bytes=N
     RipsJob; nothing is synchronised until `job.finish()`."""
     torch = _lib.require_cuda()
     if maxdim > 1:
-        raise NotImplementedError("tda_multimodal_b200: Rips persistence is implemented for maxdim <= 1 in this round")
+        raise NotImplementedError("tda_multimodal_b200: asynchronous Rips jobs cover maxdim <= 1 (use rips_batch for maxdim=2)")
     assert dm.is_cuda and dm.dtype == torch.float32 and dm.dim() == 3 and dm.shape[1] == dm.shape[2]
     dm = dm.contiguous()
     cap1, pool_bytes, _ = _default_sizes(torch, dm, cap1, pool_bytes)
@@ -140,12 +140,16 @@ def rips_batch(dm, maxdim=1, thresh=float("inf"), cap1=None, pool_bytes=None, wa
     """
     torch = _lib.require_cuda()
     L = _lib.lib()
-    if maxdim > 1:
-        raise NotImplementedError("tda_multimodal_b200: Rips persistence is implemented for maxdim <= 1 in this round")
+    if maxdim > 2:
+        raise NotImplementedError("tda_multimodal_b200: Rips persistence is implemented for maxdim <= 2")
     assert dm.is_cuda and dm.dtype == torch.float32 and dm.dim() == 3 and dm.shape[1] == dm.shape[2]
     dm = dm.contiguous()
     B, n, _ = dm.shape
     dev = dm.device
+    if maxdim == 2 and n > 1024:
+        raise NotImplementedError("tda_multimodal_b200: maxdim=2 is implemented for clouds of at most 1024 points")
+    want_h2 = maxdim == 2
+    maxdim = min(maxdim, 1)    # the library's H0/H1 stage; H2 runs on top of its workspace
     cap1, pool_bytes, free_bytes = _default_sizes(torch, dm, cap1, pool_bytes)
     with torch.cuda.device(dev):
         while True:
@@ -170,6 +174,26 @@ def rips_batch(dm, maxdim=1, thresh=float("inf"), cap1=None, pool_bytes=None, wa
         if want_stats and maxdim >= 1:
             stats = np.zeros((B, 16), dtype=np.int64)
             _lib.check(L.tda_rips_stats(_lib.ptr(ws), n, B, maxdim, cap1, pool_bytes, stats.ctypes.data))
+        h2_h = c2_h = None
+        if want_h2:
+            E = n * (n - 1) // 2
+            cap2 = _next_pow2(max(1024, 32 * n))
+            pool2 = max(64 << 20, min(2 * min(B, 296) * min(-(-(E * n * n) // 8), 1 << 29), int(0.35 * free_bytes)))
+            while True:
+                ws2_bytes = int(L.tda_rips_h2_workspace_bytes(n, B, cap2, pool2))
+                ws2 = torch.empty(ws2_bytes, dtype=torch.uint8, device=dev)
+                h2 = torch.empty((B, cap2, 2), dtype=torch.float32, device=dev)
+                c2 = torch.zeros((B, 4), dtype=torch.int32, device=dev)
+                code = L.tda_rips_h2(_lib.ptr(ws), n, B, cap1, pool_bytes, _lib.ptr(h2), cap2, _lib.ptr(c2), _lib.ptr(ws2), ws2_bytes, pool2,
+                                     _lib.stream_ptr())
+                if code == _lib.TDA_ERR_CAPACITY and pool2 < free_bytes // 2:
+                    cap2 *= 4
+                    pool2 *= 2
+                    del ws2
+                    continue
+                _lib.check(code)
+                break
+            h2_h, c2_h = h2.cpu().numpy(), c2.cpu().numpy()
     counts_h = counts.cpu().numpy()
     h0_h = h0.cpu().numpy()
     h1_h = h1.cpu().numpy() if h1 is not None else None
@@ -182,6 +206,8 @@ def rips_batch(dm, maxdim=1, thresh=float("inf"), cap1=None, pool_bytes=None, wa
         dgms = [h0_h[p, :c0].astype(np.float64)]
         if maxdim >= 1:
             dgms.append(h1_h[p, :c1].astype(np.float64))
+        if want_h2:
+            dgms.append(h2_h[p, :int(c2_h[p, 1])].astype(np.float64))
         r = {"dgms": dgms, "num_edges": int(counts_h[p, 2]), "thresh": float(th_h[p])}
         if want_simplices:
             r["simplices"] = [h0s_h[p, :c0]] + ([h1s_h[p, :c1]] if maxdim >= 1 else [])

@@ -1,0 +1,58 @@
+"""GPU parity: H2 (ripser(X, maxdim=2)) vs the CPU oracle.  H2 rows are compared as multisets of (birth, death) values: the
+tie-break among tetrahedra of equal diameter is free (any simplex-wise refinement gives the same diagram values)."""
+import numpy as np
+import pytest
+
+from tests.helpers import blobs3d, same_diagram, torus3d
+
+pytestmark = pytest.mark.gpu
+
+
+def sphere(n, rng, noise=0.03):
+    v = rng.normal(size=(n, 3))
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    return (v + rng.normal(0, noise, v.shape)).astype(np.float32)
+
+
+@pytest.mark.parametrize("gen,n,seed", [(sphere, 60, 0), (sphere, 120, 1), (blobs3d, 100, 2), (torus3d, 150, 3)])
+def test_h2_matches_oracle(gen, n, seed):
+    from oracle import rips as orips
+    from tda_multimodal_b200 import rips
+    X = gen(n, np.random.default_rng(seed))
+    want = orips.ripser(X, maxdim=2)["dgms"]
+    got = rips.ripser(X, maxdim=2)
+    assert len(got["dgms"]) == 3 and len(got["cocycles"]) == 3
+    d = got["dgms"]
+    assert np.array_equal(d[0], want[0]) and np.array_equal(d[1], want[1])          # H0 / H1 unchanged
+    assert d[2].dtype == np.float64 and same_diagram(d[2], want[2]), (len(d[2]), len(want[2]))
+    assert np.all(d[2][:, 1] > d[2][:, 0])
+
+
+def test_h2_sphere_has_one_dominant_void_and_batches():
+    import torch
+    from tda_multimodal_b200 import rips
+    rng = np.random.default_rng(7)
+    X = np.stack([sphere(200, rng, 0.02), sphere(200, rng, 0.02) * 2.0])
+    dm = rips.pdist_lowdim(torch.from_numpy(X.astype(np.float32)).cuda())
+    res = rips.rips_batch(dm, maxdim=2)
+    for b in range(2):
+        d2 = res[b]["dgms"][2]
+        pers = np.sort(d2[:, 1] - d2[:, 0])[::-1]
+        assert pers[0] > 0.3 * (b + 1) and (len(pers) == 1 or pers[0] > 3 * pers[1])
+    assert np.allclose(res[1]["dgms"][2], 2.0 * res[0]["dgms"][2]) or len(res[1]["dgms"][2]) > 0
+
+
+def test_h2_on_reference_size_cloud_and_limits():
+    """The reference's own cloud size (36 points): maxdim=2 through the shim signature; large clouds are refused loudly."""
+    from oracle import rips as orips
+    from tda_multimodal_b200 import rips
+    from tests.helpers import load_ref_rips_golden
+    clouds, _ = load_ref_rips_golden()
+    for i in (0, 25):
+        got = rips.ripser(clouds[i], maxdim=2)["dgms"]
+        want = orips.ripser(clouds[i], maxdim=2)["dgms"]
+        assert np.array_equal(got[1], want[1]) and same_diagram(got[2], want[2])
+    with pytest.raises(NotImplementedError):
+        rips.ripser(np.zeros((1100, 3), np.float32), maxdim=2)
+    with pytest.raises(NotImplementedError):
+        rips.ripser(clouds[0], maxdim=3)
