@@ -163,7 +163,7 @@ int tda_rips_launch(const float* dm, int n, int batch, int maxdim, float thresh,
 /* tda_rips_h2: H2 (optional `maxdim=2` of ripser(X, maxdim)) on top of a FINISHED tda_rips(maxdim=1) call: `ws1` is that
  * call's workspace (with the same n, batch, cap1, pool_bytes1), which still holds the rank matrix and the H1 pivots (clearing).
  * Triangles in an apparent pair with a tetrahedron are skipped in parallel, the residual triangle columns are reduced like the
- * H1 columns (implicit cohomology over Z/2, working column = bitset over tetrahedron keys).  n <= 1024.
+ * H1 columns (implicit cohomology over Z/2, working column = bitset over tetrahedron keys).  n <= 2048 (triangle keys E*n < 2^32).
  *   h2_pairs [batch,cap2,2] float32 (birth, death), death > birth; counts2 [batch,4] int32: -, n_h2 rows, -, status;
  *   cap2 a power of two; returns TDA_ERR_CAPACITY (after synchronising) if a problem overflowed cap2 or the pool. */
 size_t tda_rips_h2_workspace_bytes(int n, int batch, int cap2, size_t pool_bytes);

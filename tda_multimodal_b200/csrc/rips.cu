@@ -655,10 +655,10 @@ struct Reducer {
   }
 
   // sort blist[0..nb) ascending in place (bitonic, global memory)
-  __device__ __forceinline__ void sort_blist(int* bl, int nb) {
+  __device__ __forceinline__ void sort_blist(int* bl, int nb) {   // (triangle keys of DIM 2 are compared as unsigned)
     int np2 = 1;
     while (np2 < nb) np2 <<= 1;
-    for (int i = nb + tid; i < np2; i += kReduceThreads) bl[i] = 0x7fffffff;  // cap1 is a power of two >= nb
+    for (int i = nb + tid; i < np2; i += kReduceThreads) bl[i] = DIM == 1 ? 0x7fffffff : (int)0xffffffffu;  // cap1 is a power of two >= nb
     __syncthreads();
     for (int k = 2; k <= np2; k <<= 1)
       for (int j = k >> 1; j > 0; j >>= 1) {
@@ -667,7 +667,8 @@ struct Reducer {
           if (ixj > i) {
             const int a = bl[i], b = bl[ixj];
             const bool up = ((i & k) == 0);
-            if ((a > b) == up) { bl[i] = b; bl[ixj] = a; }
+            const bool gt = DIM == 1 ? (a > b) : ((uint32_t)a > (uint32_t)b);
+            if (gt == up) { bl[i] = b; bl[ixj] = a; }
           }
         }
         __syncthreads();
@@ -798,7 +799,7 @@ struct Reducer {
           const int pv = n - 1 - (int)(rem / (uint64_t)n), qv = n - 1 - (int)(rem % (uint64_t)n);
           M = (int)(M4 * (uint64_t)n + (uint64_t)(n - 1 - qv));
           w = pv;
-          if ((int)A4[M] != pv) owner = hash_find(pk);
+          if ((int)A4[(uint32_t)M] != pv) owner = hash_find(pk);
         }
         cyc[1] += clock64() - t0;
         if (owner == -1) { pivot = pk; break; }
@@ -1741,7 +1742,7 @@ __global__ void h2_clear_kernel(const uint2* __restrict__ ea, const int* __restr
   }
 }
 
-constexpr int kH2MaxWords = 32;   // n <= 1024
+constexpr int kH2MaxWords = 64;   // n <= 2048 (two lune words per lane; triangle keys E*n < 2^32)
 __global__ void __launch_bounds__(256) h2_apparent_kernel(const int* __restrict__ rank, const uint32_t* __restrict__ ends, const int* __restrict__ Tarr,
                                                           int n, int64_t E, const uint32_t* __restrict__ cbits, int64_t cwords,
                                                           short* __restrict__ apex4, int* __restrict__ blist2, int* __restrict__ bcount2, int cap2) {
@@ -1755,17 +1756,21 @@ __global__ void __launch_bounds__(256) h2_apparent_kernel(const int* __restrict_
   const int x = (int)(e >> 16), y = (int)(e & 0xffffu);
   const int* Rx = R + (size_t)x * n;
   const int* Ry = R + (size_t)y * n;
-  uint32_t lunew = 0;   // lane k holds word k of the lune mask
+  uint32_t lunew0 = 0, lunew1 = 0;   // lane k holds words k and k + 32 of the lune mask
   for (int k = 0; k < W; ++k) {
     const int v = 32 * k + lane;
     const bool in = v < n && Rx[v] < (int)M && Ry[v] < (int)M;
     const unsigned b = __ballot_sync(0xffffffffu, in);
-    if (lane == k) lunew = b;
+    if (lane == (k & 31)) { if (k < 32) lunew0 = b; else lunew1 = b; }
   }
+  auto lune_word = [&](int k) -> uint32_t {   // warp-uniform k
+    const uint32_t a0 = __shfl_sync(0xffffffffu, lunew0, k & 31), a1 = __shfl_sync(0xffffffffu, lunew1, k & 31);
+    return k < 32 ? a0 : a1;
+  };
   const uint32_t* cb = cbits + (size_t)p * cwords;
   short* A4 = apex4 + (size_t)p * (size_t)E * (size_t)n;
   for (int k = W - 1; k >= 0; --k) {
-    uint32_t word = __shfl_sync(0xffffffffu, lunew, k);
+    uint32_t word = lune_word(k);
     while (word) {
       const int bit = 31 - __clz(word);
       word &= ~(1u << bit);
@@ -1773,7 +1778,7 @@ __global__ void __launch_bounds__(256) h2_apparent_kernel(const int* __restrict_
       const int* Rw = R + (size_t)w * n;
       int found = -1;
       for (int k2 = W - 1; k2 >= (w >> 5); --k2) {
-        const uint32_t lw = __shfl_sync(0xffffffffu, lunew, k2);
+        const uint32_t lw = lune_word(k2);
         const int v = 32 * k2 + lane;
         const bool ok = ((lw >> lane) & 1u) && v > w && Rw[v] < (int)M;
         const unsigned b = __ballot_sync(0xffffffffu, ok);

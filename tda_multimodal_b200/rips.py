@@ -146,8 +146,8 @@ def rips_batch(dm, maxdim=1, thresh=float("inf"), cap1=None, pool_bytes=None, wa
     dm = dm.contiguous()
     B, n, _ = dm.shape
     dev = dm.device
-    if maxdim == 2 and n > 1024:
-        raise NotImplementedError("tda_multimodal_b200: maxdim=2 is implemented for clouds of at most 1024 points")
+    if maxdim == 2 and n > 2048:
+        raise NotImplementedError("tda_multimodal_b200: maxdim=2 is implemented for clouds of at most 2048 points")
     want_h2 = maxdim == 2
     maxdim = min(maxdim, 1)    # the library's H0/H1 stage; H2 runs on top of its workspace
     cap1, pool_bytes, free_bytes = _default_sizes(torch, dm, cap1, pool_bytes)

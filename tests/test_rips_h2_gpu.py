@@ -53,6 +53,6 @@ def test_h2_on_reference_size_cloud_and_limits():
         want = orips.ripser(clouds[i], maxdim=2)["dgms"]
         assert np.array_equal(got[1], want[1]) and same_diagram(got[2], want[2])
     with pytest.raises(NotImplementedError):
-        rips.ripser(np.zeros((1100, 3), np.float32), maxdim=2)
+        rips.ripser(np.zeros((2100, 3), np.float32), maxdim=2)
     with pytest.raises(NotImplementedError):
         rips.ripser(clouds[0], maxdim=3)
