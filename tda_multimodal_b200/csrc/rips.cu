@@ -41,7 +41,6 @@ enum { ST_COLUMNS = 0, ST_APPARENT, ST_REDUCED, ST_ADDITIONS, ST_PUSHES, ST_POPS
 // ------------------------------------------------------------------------------------------------
 // low-dimensional euclidean distance matrix (ripser.py front end)
 __global__ void pdist_lowdim_kernel(const float* __restrict__ pts, int n, int d, float* __restrict__ dm) {
-  extern __shared__ float sp[];  // [n_tile_i + n_tile_j][d] not needed: d is tiny, read directly
   int p = blockIdx.z;
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   int i = blockIdx.y * blockDim.y + threadIdx.y;
