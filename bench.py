@@ -26,12 +26,15 @@ if ROOT not in sys.path:
 
 METRIC = "umap_rips_h0h1_layers_per_sec"
 UNIT = "layers/s"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the round's `ncu --set full` capture of this command
+# (profiles/r01_final_ncu_full_summary.csv; 16 clouds of 2000 points per launch): static evidence, not measured by this run
+NCU_TRAFFIC_BYTES = {"rips_reduce": 1.05e9, "pdist_gemm": 3.16e9}
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--layers", type=int, default=32)
@@ -338,8 +341,9 @@ def run_b200(a):
         else:
             achieved = work / (dom_ms / 1e3) / 1e9
             peak, unit = hbm_peak, "GB/s"
+        default_shape = (a.layers, a.points, a.dim) == (32, 2000, 4096)
         roofline = {"kernel": dom, "bound": kind, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak if peak else None,
-                    "traffic": None, "peak_source": peak_src, "avg_launch_ms": dom_ms / calls, "share_of_device_stage_time": dom_ms / tot_ms if tot_ms else None,
+                    "traffic": NCU_TRAFFIC_BYTES.get(dom) if default_shape else None, "peak_source": peak_src, "avg_launch_ms": dom_ms / calls, "share_of_device_stage_time": dom_ms / tot_ms if tot_ms else None,
                     "stages_ms_per_step": {s: round(v[0] / a.steps, 3) for s, v in stages.items()}}
         if "rips_stats_sum" in extra:
             roofline["rips_stats_per_step"] = extra["rips_stats_sum"]
