@@ -111,7 +111,7 @@ int tda_umap_transform_init(const int32_t* knn_idx, const float* knn_dist, const
  *   symmetric normalised Laplacian (Lanczos, full reorthogonalisation), written as unit vectors into the component's
  *   rows of Y [batch,n,dim]; evals [batch,maxcomp,4] (eigenvalues of D^-1/2 W D^-1/2) or NULL.
  */
-size_t tda_spectral_workspace_bytes(int n, int batch, int maxcomp);
+size_t tda_spectral_workspace_bytes(int n, int batch, int maxcomp, int slots);
 int tda_graph_components(const int32_t* head, const int32_t* tail, const float* weight, const float* eps, int slots, int n, int batch,
                          int32_t* comp, int32_t* ncomp, int32_t* comp_size, float* degree, void* ws, size_t ws_bytes, void* stream);
 int tda_spectral_embed(const int32_t* head, const int32_t* tail, const float* weight, const float* eps, int slots, int n, int dim,

@@ -101,6 +101,8 @@ struct LanczosParams {
   float* Q;        // [batch, maxcomp, kMaxKrylov + 2, n]
   float* out;      // [batch, n, dim] eigenvectors (rows of other components untouched)
   float* evals;    // [batch, maxcomp, kMaxDim]
+  int4* entries;   // [batch, slots]  (head, tail, weight / sqrt(deg_h deg_t), -) of the live slots, one segment per component
+  int* ent_count;  // [batch]         segment allocation cursor
   int maxcomp; int min_size; uint64_t seed;
 };
 
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(kLanczosThreads) lanczos_kernel(LanczosParams 
   __shared__ float s_red[kLanczosThreads / 32];
   __shared__ double s_lam[kMaxDim];
   __shared__ double s_vec[kMaxDim][kMaxKrylov];
-  __shared__ int s_m;
+  __shared__ int s_m, s_base, s_cursor;
   const int p = blockIdx.y, c = blockIdx.x;
   if (c >= P.ncomp[p]) return;
   const int n = P.n, dim = P.dim;
@@ -160,34 +162,73 @@ __global__ void __launch_bounds__(kLanczosThreads) lanczos_kernel(LanczosParams 
   for (int i = tid; i < n; i += kLanczosThreads) q0[i] /= nrm;
   __syncthreads();
 
+  // the component's live slots, compacted once with their matrix entry: the 96 sparse matrix-vector products then stream 16 bytes
+  // per entry with independent loads instead of chasing eps -> head/tail -> deg per slot
+  int4* ent = P.entries + (size_t)p * P.slots;
+  int my_cnt = 0;
+  for (int e = tid; e < P.slots; e += kLanczosThreads)
+    if (eps[e] > 0.f && comp[head[e]] == c) ++my_cnt;
+  const int cnt = (int)(block_sum((float)my_cnt) + 0.5f);   // (exact: counts are far below 2^24)
+  if (tid == 0) { s_base = atomicAdd(&P.ent_count[p], cnt); s_cursor = 0; }
+  __syncthreads();
+  ent += s_base;
+  for (int e0 = 0; e0 < P.slots; e0 += kLanczosThreads) {
+    const int e = e0 + tid;
+    int h = 0, t = 0;
+    bool ok = false;
+    if (e < P.slots && eps[e] > 0.f) { h = head[e]; t = tail[e]; ok = comp[h] == c; }
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    int wbase = 0;
+    if (lane == 0 && bal) wbase = atomicAdd(&s_cursor, __popc(bal));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (ok) ent[wbase + __popc(bal & ((1u << lane) - 1))] = make_int4(h, t, __float_as_int(weight[e] * rsqrtf(deg[h] * deg[t])), 0);
+  }
+  __syncthreads();
+
   int meff = m;
   for (int j = 0; j < m; ++j) {
     const float* qj = q0 + (size_t)j * n;
     float* w = q0 + (size_t)(j + 1) * n;  // becomes q_{j+1}
     for (int i = tid; i < n; i += kLanczosThreads) w[i] = 0.f;
     __syncthreads();
-    for (int e = tid; e < P.slots; e += kLanczosThreads)
-      if (eps[e] > 0.f) {
-        const int h = head[e], t = tail[e];
-        if (comp[h] == c) atomicAdd(&w[h], weight[e] * rsqrtf(deg[h] * deg[t]) * qj[t]);
-      }
+#pragma unroll 4
+    for (int k = tid; k < cnt; k += kLanczosThreads) {
+      const int4 E = ent[k];
+      atomicAdd(&w[E.x], __int_as_float(E.z) * qj[E.y]);
+    }
     __syncthreads();
     // classical Gram-Schmidt, twice, against u1 and q_0..q_j; the first pass's coefficient on q_j is alpha_j
     for (int pass = 0; pass < 2; ++pass) {
       for (int v = warp; v <= j + 1; v += nwarps) {  // v = 0: u1, v = 1..j+1: q_{v-1}
         const float* qv = Q + (size_t)v * n;
-        float s = 0.f;
-        for (int i = lane; i < n; i += 32) s += w[i] * qv[i];
-        s = warp_sum_f32(s);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // four independent chains: the loop is bound by the L2 latency of Q
+        int i = lane;
+        for (; i + 96 < n; i += 128) {
+          s0 += w[i] * qv[i]; s1 += w[i + 32] * qv[i + 32]; s2 += w[i + 64] * qv[i + 64]; s3 += w[i + 96] * qv[i + 96];
+        }
+        for (; i < n; i += 32) s0 += w[i] * qv[i];
+        float s = warp_sum_f32((s0 + s1) + (s2 + s3));
         if (lane == 0) s_coef[v] = s;
       }
       __syncthreads();
       if (pass == 0 && tid == 0) s_alpha[j] = (double)s_coef[j + 1];
       else if (pass == 1 && tid == 0) s_alpha[j] += (double)s_coef[j + 1];
-      for (int i = tid; i < n; i += kLanczosThreads) {
-        float v = w[i];
-        for (int t = 0; t <= j + 1; ++t) v -= s_coef[t] * Q[(size_t)t * n + i];
-        w[i] = v;
+      for (int i0 = tid; i0 < n; i0 += 4 * kLanczosThreads) {   // four elements per thread and four vectors per trip in flight
+        const int i1 = i0 + kLanczosThreads, i2 = i0 + 2 * kLanczosThreads, i3 = i0 + 3 * kLanczosThreads;
+        float v0 = w[i0], v1 = i1 < n ? w[i1] : 0.f, v2 = i2 < n ? w[i2] : 0.f, v3 = i3 < n ? w[i3] : 0.f;
+#pragma unroll 4
+        for (int t = 0; t <= j + 1; ++t) {
+          const float c = s_coef[t];
+          const float* q = Q + (size_t)t * n;
+          v0 -= c * q[i0];
+          if (i1 < n) v1 -= c * q[i1];
+          if (i2 < n) v2 -= c * q[i2];
+          if (i3 < n) v3 -= c * q[i3];
+        }
+        w[i0] = v0;
+        if (i1 < n) w[i1] = v1;
+        if (i2 < n) w[i2] = v2;
+        if (i3 < n) w[i3] = v3;
       }
       __syncthreads();
     }
@@ -312,9 +353,10 @@ __global__ void __launch_bounds__(kLanczosThreads) lanczos_kernel(LanczosParams 
 struct Layout {
   int *label, *comp, *ncomp, *csize;
   float *deg, *Q, *evals;
+  int4* entries; int* ent_count;
   size_t total;
 };
-static Layout make_layout(void* ws, int n, int batch, int maxcomp) {
+static Layout make_layout(void* ws, int n, int batch, int maxcomp, int slots) {
   Layout L;
   Carver c(ws, ~size_t(0));
   L.label = c.take<int>((size_t)batch * n);
@@ -324,6 +366,8 @@ static Layout make_layout(void* ws, int n, int batch, int maxcomp) {
   L.deg = c.take<float>((size_t)batch * n);
   L.evals = c.take<float>((size_t)batch * (maxcomp > 0 ? maxcomp : 1) * kMaxDim);
   L.Q = c.take<float>((size_t)batch * (maxcomp > 0 ? maxcomp : 0) * (kMaxKrylov + 2) * n);
+  L.entries = c.take<int4>((size_t)batch * (slots > 0 ? slots : 0));
+  L.ent_count = c.take<int>(batch);
   L.total = c.off;
   return L;
 }
@@ -334,9 +378,9 @@ static Layout make_layout(void* ws, int n, int batch, int maxcomp) {
 using namespace tda;
 using namespace tda::spectral;
 
-extern "C" size_t tda_spectral_workspace_bytes(int n, int batch, int maxcomp) {
-  if (n <= 0 || batch <= 0 || maxcomp < 0) return 0;
-  return make_layout(nullptr, n, batch, maxcomp).total + 1024;
+extern "C" size_t tda_spectral_workspace_bytes(int n, int batch, int maxcomp, int slots) {
+  if (n <= 0 || batch <= 0 || maxcomp < 0 || slots < 0) return 0;
+  return make_layout(nullptr, n, batch, maxcomp, slots).total + 1024;
 }
 
 extern "C" int tda_graph_components(const int32_t* head, const int32_t* tail, const float* weight, const float* eps, int slots, int n, int batch,
@@ -359,12 +403,13 @@ extern "C" int tda_spectral_embed(const int32_t* head, const int32_t* tail, cons
   if (!head || !tail || !weight || !eps || !comp || !ncomp || !comp_size || !degree || !Y || !ws || n <= 0 || batch <= 0 || maxcomp <= 0)
     return set_error(TDA_ERR_INVALID, "tda_spectral_embed: bad arguments");
   if (dim < 1 || dim > kMaxDim) return set_error(TDA_ERR_UNSUPPORTED, "tda_spectral_embed: dim=%d (supported 1..%d)", dim, kMaxDim);
-  Layout L = make_layout(ws, n, batch, maxcomp);
+  Layout L = make_layout(ws, n, batch, maxcomp, slots);
   if (L.total > ws_bytes) return set_error(TDA_ERR_WORKSPACE, "tda_spectral_embed: workspace %zu < required %zu", ws_bytes, L.total);
+  TDA_CUDA_CHECK(cudaMemsetAsync(L.ent_count, 0, sizeof(int) * batch, stream));
   LanczosParams P;
   P.head = head; P.tail = tail; P.weight = weight; P.eps = eps; P.slots = slots; P.n = n; P.dim = dim;
   P.comp = comp; P.deg = degree; P.ncomp = ncomp; P.csize = comp_size;
-  P.Q = L.Q; P.out = Y; P.evals = evals ? evals : L.evals; P.maxcomp = maxcomp; P.min_size = min_size; P.seed = seed;
+  P.Q = L.Q; P.entries = L.entries; P.ent_count = L.ent_count; P.out = Y; P.evals = evals ? evals : L.evals; P.maxcomp = maxcomp; P.min_size = min_size; P.seed = seed;
   dim3 grid(maxcomp, batch);
   StageScope st(STAGE_SPECTRAL, stream);
   lanczos_kernel<<<grid, kLanczosThreads, 0, stream>>>(P);

@@ -141,7 +141,7 @@ def spectral_init(X, head, tail, weight, eps, n, dim, seed, metric):
         ncomp_h = ncomp.cpu().numpy()
         maxcomp = int(ncomp_h.max())
         min_size = 1 if maxcomp == 1 else max(2 * dim, dim + 2)
-        ws_bytes = int(L.tda_spectral_workspace_bytes(n, B, maxcomp))
+        ws_bytes = int(L.tda_spectral_workspace_bytes(n, B, maxcomp, slots))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         _lib.check(L.tda_spectral_embed(_lib.ptr(head), _lib.ptr(tail), _lib.ptr(weight), _lib.ptr(eps), slots, n, dim, B, _lib.ptr(comp),
                                         _lib.ptr(ncomp), _lib.ptr(csize), _lib.ptr(deg), maxcomp, min_size, int(seed), _lib.ptr(Y), None,

@@ -130,7 +130,7 @@ def test_components_and_spectral_vs_scipy(torch_cuda):
     np.testing.assert_allclose(deg[0].cpu().numpy(), np.asarray(G.sum(1)).ravel(), rtol=1e-5)
     # eigenvectors of every large component: residual of A v = lambda v and agreement of lambda with ARPACK
     maxcomp = nc
-    ws_bytes = int(L.tda_spectral_workspace_bytes(n, 1, maxcomp))
+    ws_bytes = int(L.tda_spectral_workspace_bytes(n, 1, maxcomp, head.shape[1]))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
     Y = torch.zeros((1, n, dim), dtype=torch.float32, device="cuda")
     ev = torch.zeros((1, maxcomp, 4), dtype=torch.float32, device="cuda")
