@@ -345,6 +345,16 @@ def run_b200(a):
         roofline = {"kernel": dom, "bound": kind, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak if peak else None,
                     "traffic": NCU_TRAFFIC_BYTES.get(dom) if default_shape else None, "peak_source": peak_src, "avg_launch_ms": dom_ms / calls, "share_of_device_stage_time": dom_ms / tot_ms if tot_ms else None,
                     "stages_ms_per_step": {s: round(v[0] / a.steps, 3) for s, v in stages.items()}}
+        # the two kernel-level figures BASELINE.json's metric names next to layers/s, from the same stage timers
+        secondary = {}
+        if stages.get("pdist_gemm", (0, 0))[0] > 0:
+            secondary["pdist_useful_tflops"] = algorithmic_work("pdist_gemm", a, n_done, extra)[1] / (stages["pdist_gemm"][0] / 1e3) / 1e12
+            secondary["pdist_issued_tflops_3xtf32"] = 3.0 * secondary["pdist_useful_tflops"]
+            secondary["pdist_frac_of_tf32_peak_issued"] = secondary["pdist_issued_tflops_3xtf32"] / (bf16_peak / 2.0)
+        if stages.get("knn_smooth", (0, 0))[0] > 0:
+            secondary["knn_hbm_gbs"] = algorithmic_work("knn_smooth", a, n_done, extra)[1] / (stages["knn_smooth"][0] / 1e3) / 1e9
+            secondary["knn_frac_of_hbm_peak"] = secondary["knn_hbm_gbs"] / hbm_peak
+        roofline["secondary"] = secondary
         if "rips_stats_sum" in extra:
             roofline["rips_stats_per_step"] = extra["rips_stats_sum"]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,

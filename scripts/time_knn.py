@@ -1,0 +1,28 @@
+"""kNN + sigma/rho kernel alone (tda_knn_smooth) on C3-shaped distance matrices: HBM GB/s against the measured copy peak.
+Every timed launch reads matrices that are not in L2 (the batch is larger than L2 and a 512 MB buffer is written in between)."""
+import sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from tda_multimodal_b200 import umap_, workloads
+peak = 6543.7
+try:
+    peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    pass
+k = 15
+X = torch.from_numpy(workloads.c3_layers(n_layers=8, n=2000, d=4096)).cuda()
+D8 = umap_.distance_matrix(X, metric="cosine")
+flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+for B in (8, 16, 32):
+    D = D8.repeat(B // 8, 1, 1).contiguous()
+    n = D.shape[1]
+    for _ in range(3): umap_.knn_smooth(D, k)
+    ts = []
+    for _ in range(10):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); umap_.knn_smooth(D, k); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sorted(ts)[len(ts) // 2]
+    by = B * (4.0 * n * n + 8.0 * n * k + 8.0 * n)
+    print(f"knn_smooth B={B} n={n} k={k}: median {ms:.3f} ms (min {min(ts):.3f})  {by/ms/1e6:.0f} GB/s = {by/ms/1e6/peak:.2f} of measured HBM peak {peak:.0f} GB/s (call = memset + knn kernel + sigma floor kernel + 4 torch.empty)", flush=True)

@@ -347,6 +347,15 @@ __global__ void apparent_kernel(const int* __restrict__ rank, const uint32_t* __
 // shared memory instead: the chain of pivots is followed there without a global fence or a global read per step,
 // and the range is refilled from the global bitset (and zeroed there) when the scan runs off its end.  If the key
 // space exceeds the window, keys beyond it are dropped and delta(V) is re-enumerated when the window slides.
+// -DTDA_BOUNDS_CHECK: every indexed access of the reducer is checked; the first violations are printed (device printf) and
+// the access is skipped, so a bad index can be located without compute-sanitizer
+#ifdef TDA_BOUNDS_CHECK
+#define TDA_BC(cond, what, a, b)                                                                                              \
+  ((cond) ? true : (printf("TDA_BOUNDS %s: %lld %lld (block %d thread %d line %d)\n", what, (long long)(a), (long long)(b), \
+                           (int)blockIdx.x, (int)threadIdx.x, __LINE__), false))
+#else
+#define TDA_BC(cond, what, a, b) true
+#endif
 constexpr int kPageShift = 13;                 // 8192 bits per page
 constexpr int kPageWords = 1 << (kPageShift - 5);  // 256 words = kReduceThreads
 static_assert(kPageWords == kReduceThreads, "one thread per word of a page");
@@ -520,6 +529,7 @@ struct Reducer {
       atomicXor(&S.nearw[(rel - nbase) >> 5], 1u << (rel & 31));
       return;
     }
+    if (!TDA_BC(rel < wbits, "toggle_key rel/wbits", rel, wbits)) return;
     atomicXor(&bits[rel >> 5], 1u << (rel & 31));
     const uint32_t page = (uint32_t)(rel >> kPageShift);
     const uint32_t m = 1u << (page & 31);
@@ -534,6 +544,7 @@ struct Reducer {
   __device__ __forceinline__ void gen_tri(uint32_t k3, uint64_t lo, int t0, int nthr) {
     const int M = (int)(k3 / (uint32_t)n);
     const int w = n - 1 - (int)(k3 - (uint32_t)M * (uint32_t)n);
+    if (!TDA_BC(M >= 0 && M < T, "gen_tri M/T", M, T)) return;
     const uint32_t e = __ldg(&EN[M]);
     const int x = (int)(e >> 16), y = (int)(e & 0xffffu);
     const int* rowx = R + (size_t)x * n;
@@ -586,6 +597,7 @@ struct Reducer {
   // ---- V (the reduction column as a set of edges, by rank)
   __device__ __forceinline__ uint32_t* vlist(uint32_t sel) const { return vl0 + (size_t)sel * P.vcap; }
   __device__ __forceinline__ void v_toggle(int re) {  // any single thread; fire-and-forget (no atomic round trip)
+    if (!TDA_BC((int64_t)((uint32_t)re >> 5) < P.vwords, "v_toggle word/vwords", (uint32_t)re >> 5, P.vwords)) return;
     atomicXor(&vbits[(uint32_t)re >> 5], 1u << (re & 31));
     const uint32_t pos = atomicAdd(&S.vcount, 1u);  // the list may hold an edge several times: v_compact keeps it once iff its bit is set
     if (pos < (uint32_t)P.vcap) vlist(S.vsel)[pos] = (uint32_t)re;
@@ -699,6 +711,7 @@ struct Reducer {
         while (f) {
           const uint32_t page = wi * 32 + (__ffs(f) - 1);
           f &= f - 1;
+          if (!TDA_BC(page < npages, "clean page/npages", page, npages)) continue;
           uint4* dst = reinterpret_cast<uint4*>(bits + (size_t)page * kPageWords);
           dst[lane] = make_uint4(0, 0, 0, 0);
           dst[lane + 32] = make_uint4(0, 0, 0, 0);
@@ -798,6 +811,7 @@ struct Reducer {
           const int pv = n - 1 - (int)(rem / (uint64_t)n), qv = n - 1 - (int)(rem % (uint64_t)n);
           M = (int)(M4 * (uint64_t)n + (uint64_t)(n - 1 - qv));
           w = pv;
+          if (!TDA_BC((uint64_t)(uint32_t)M < (uint64_t)P.E * (uint64_t)n && M4 < (uint64_t)T, "pivot facet key/M4", (uint32_t)M, M4)) { S.abort_flag = TDA_ERR_INVALID; break; }
           if ((int)A4[(uint32_t)M] != pv) owner = hash_find(pk);
         }
         cyc[1] += clock64() - t0;
@@ -811,8 +825,10 @@ struct Reducer {
           publish();
           cyc[2] += clock64() - t0;
         } else {
+          if (!TDA_BC(owner < P.cap1, "owner/cap1", owner, P.cap1)) { S.abort_flag = TDA_ERR_INVALID; break; }
           const int64_t vs = P.vstart[(size_t)p * P.cap1 + owner];
           const int vn = P.vlen[(size_t)p * P.cap1 + owner];
+          if (!TDA_BC(vs >= 0 && vn >= 0 && vs + vn <= P.vpool_cap, "vstart+vlen/vpool_cap", vs, vn)) { S.abort_flag = TDA_ERR_INVALID; break; }
           const uint32_t* ov = P.vpool + (size_t)p * P.vpool_cap + vs;
           if (S.vcount + (uint32_t)vn > (uint32_t)P.vcap) v_compact();
           add_edges(ov, (uint32_t)vn, pk, true);
@@ -853,7 +869,7 @@ struct Reducer {
         death = SD[Md];
       }
       if (essential || death > birth) {
-        if (tid == 0) {
+        if (tid == 0 && TDA_BC(nrows < P.cap1, "nrows/cap1", nrows, P.cap1)) {
           out[2 * nrows] = birth; out[2 * nrows + 1] = death;
           if (DIM == 1 && outs) {
             const uint32_t e = EN[rbirth];
@@ -1732,12 +1748,12 @@ __global__ void h2_clear_kernel(const uint2* __restrict__ ea, const int* __restr
     const int apex = (int)ea[(size_t)p * E + t].y;   // -2 for MST edges, -1 for an empty lune
     if (apex >= 0) {
       const uint64_t k = (uint64_t)t * (uint64_t)n + (uint64_t)(n - 1 - apex);
-      atomicOr(&cb[k >> 5], 1u << (k & 31));
+      if (TDA_BC(apex < n, "h2_clear apex/n", apex, n)) atomicOr(&cb[k >> 5], 1u << (k & 31));
     }
   }
   if (t < hcap) {
     const uint64_t k = hkeys[(size_t)p * hcap + t];
-    if (k != ~0ull) atomicOr(&cb[k >> 5], 1u << (k & 31));
+    if (k != ~0ull && TDA_BC((int64_t)(k >> 5) < cwords, "h2_clear pivot key/cwords", k, cwords)) atomicOr(&cb[k >> 5], 1u << (k & 31));
   }
 }
 
@@ -2040,9 +2056,18 @@ static int rips_enqueue(const float* dm, int n, int batch, int maxdim, float thr
     {
       StageScope st(STAGE_RIPS_REDUCE, stream);
       if (L.sweep) {
-        const size_t dyn = sizeof(uint32_t) * ((size_t)L.xw * (1 + 4 * kGroupRows) + (size_t)n + 2 * kChunkRows);
+        // TDA_SWEEP_EXCLUSIVE=1: ask for all of the SM's shared memory, so that no CTA of a kernel running on another stream
+        // (UMAP SGD of the next chunk ...) shares the SM -- and the issue slots -- with the latency-bound resolver warp
+        static const bool exclusive = [] { const char* e = getenv("TDA_SWEEP_EXCLUSIVE"); return e && e[0] == '1'; }();
+        size_t dyn = sizeof(uint32_t) * ((size_t)L.xw * (1 + 4 * kGroupRows) + (size_t)n + 2 * kChunkRows);
 #define TDA_SWEEP_LAUNCH(WPL)                                                                                                 \
   do {                                                                                                                        \
+    if (exclusive) {                                                                                                          \
+      cudaFuncAttributes fa;                                                                                                  \
+      TDA_CUDA_CHECK(cudaFuncGetAttributes(&fa, rips_sweep_kernel<WPL>));                                                     \
+      const size_t room = (size_t)227 * 1024 - fa.sharedSizeBytes;                                                            \
+      if (dyn < room) dyn = room;                                                                                             \
+    }                                                                                                                         \
     TDA_CUDA_CHECK(cudaFuncSetAttribute(rips_sweep_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));      \
     rips_sweep_kernel<WPL><<<L.grid, kSweepThreads, dyn, stream>>>(P);                                                        \
   } while (0)
@@ -2184,9 +2209,13 @@ extern "C" int tda_rips_h2(const void* ws1, int n, int batch, int cap1, size_t p
   {
     const int64_t work = E > L1.hcap ? E : L1.hcap;
     dim3 g((unsigned)((work + 255) / 256), batch);
+    static const bool debug_sync = getenv("TDA_DEBUG_SYNC") != nullptr;   // locate a faulting kernel: synchronise after each one
+    if (debug_sync) TDA_CUDA_CHECK(cudaStreamSynchronize(stream));
     h2_clear_kernel<<<g, 256, 0, stream>>>(L1.ea, L1.T, L1.hkeys, L1.hcap, n, E, L.cbits, L.cwords);
+    if (debug_sync) TDA_CUDA_CHECK(cudaStreamSynchronize(stream));
     dim3 g2((unsigned)((E * 32 + 255) / 256), batch);
     h2_apparent_kernel<<<g2, 256, 0, stream>>>(L1.rank, L1.ends, L1.T, n, E, L.cbits, L.cwords, L.apex4, L.blist2, L.bcount2, cap2);
+    if (debug_sync) TDA_CUDA_CHECK(cudaStreamSynchronize(stream));
     count_launch(2);
     TDA_LAUNCH_CHECK();
   }

@@ -22,33 +22,28 @@ __device__ __forceinline__ bool pair_less(float d1, int i1, float d2, int i2) { 
 
 // ------------------------------------------------------------------------------------------------
 // exact kNN (self included, as umap-learn's precomputed-metric path does) fused with smooth_knn_dist.
-// One warp per row.  The running top-k is a sorted list striped over the warp (rank r -> lane r%32, slot r/32).
+// The running top-k of a row is a sorted list striped over a warp (rank r -> lane r%32, slot r/32); ties go to the
+// smaller index (numpy's stable argsort), so the result does not depend on the order candidates are offered in.
 template <int KPL>
-__global__ void __launch_bounds__(256) knn_smooth_kernel(const float* __restrict__ D, int n, int m, int k, float local_connectivity,
-                                                         float bandwidth, int n_iter, int* __restrict__ knn_idx,
-                                                         float* __restrict__ knn_dist, float* __restrict__ sigma, float* __restrict__ rho,
-                                                         double* __restrict__ dist_sum) {
-  const int p = blockIdx.y;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= n) return;
-  const float* drow = D + ((size_t)p * n + row) * m;
+struct TopK {
   float dv[KPL];
   int iv[KPL];
+  float thr_d;   // current k-th smallest (d, index): only candidates below it can enter
+  int thr_i;
+  __device__ __forceinline__ void init() {
 #pragma unroll
-  for (int s = 0; s < KPL; ++s) { dv[s] = INFINITY; iv[s] = 0x7fffffff; }
-  const int last_lane = (k - 1) & 31, last_slot = (k - 1) >> 5;
-  float thr_d = INFINITY;
-  int thr_i = 0x7fffffff;
-  for (int j0 = 0; j0 < m; j0 += 32) {
-    const int j = j0 + lane;
-    const float d = j < m ? drow[j] : INFINITY;
-    unsigned cand = __ballot_sync(0xffffffffu, j < m && pair_less(d, j, thr_d, thr_i));
+    for (int s = 0; s < KPL; ++s) { dv[s] = INFINITY; iv[s] = 0x7fffffff; }
+    thr_d = INFINITY;
+    thr_i = 0x7fffffff;
+  }
+  // every lane offers one candidate (d, j); `ok` false = nothing to offer
+  __device__ __forceinline__ void offer(float d, int j, bool ok, int lane, int last_lane, int last_slot) {
+    unsigned cand = __ballot_sync(0xffffffffu, ok && pair_less(d, j, thr_d, thr_i));
     while (cand) {
       const int src = __ffs(cand) - 1;
       cand &= cand - 1;
       const float cd = __shfl_sync(0xffffffffu, d, src);
-      const int cj = j0 + src;
+      const int cj = __shfl_sync(0xffffffffu, j, src);
       if (!pair_less(cd, cj, thr_d, thr_i)) continue;  // threshold moved since the ballot
       // insertion position = number of list entries smaller than the candidate
       int pos = 0;
@@ -67,10 +62,205 @@ __global__ void __launch_bounds__(256) knn_smooth_kernel(const float* __restrict
         if (r == pos) { dv[s] = cd; iv[s] = cj; }
         else if (r > pos) { dv[s] = upd; iv[s] = upi; }
       }
-      thr_d = __shfl_sync(0xffffffffu, dv[last_slot], last_lane);
-      thr_i = __shfl_sync(0xffffffffu, iv[last_slot], last_lane);
+      float td = dv[0];
+      int ti = iv[0];
+#pragma unroll
+      for (int s = 1; s < KPL; ++s)
+        if (s == last_slot) { td = dv[s]; ti = iv[s]; }
+      thr_d = __shfl_sync(0xffffffffu, td, last_lane);
+      thr_i = __shfl_sync(0xffffffffu, ti, last_lane);
     }
   }
+};
+
+// Streams ROWS rows of D through their top-k lists.  Every lane keeps kKnnVecLoads 16-byte loads per row in flight
+// (2 KB per row per warp and iteration; streaming, evict-first) and the warp looks at a batch only when some lane holds a
+// value not above the row's current threshold -- after the first few hundred columns almost never.
+constexpr int kKnnVecLoads = 4;
+constexpr int kKnnScalarLoads = 8;
+template <int KPL, int ROWS>
+__device__ __forceinline__ void knn_stream_rows(const float* const (&drow)[ROWS], const bool (&live)[ROWS], int m, int k, int lane,
+                                                TopK<KPL> (&tk)[ROWS]) {
+  const int last_lane = (k - 1) & 31, last_slot = (k - 1) >> 5;
+  bool vec = (m & 3) == 0;
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) vec = vec && ((reinterpret_cast<uintptr_t>(drow[r]) & 15) == 0);
+  if (vec) {
+    const int m4 = m >> 2;
+    for (int q0 = 0; q0 < m4; q0 += 32 * kKnnVecLoads) {
+      float4 v[ROWS][kKnnVecLoads];
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+        for (int u = 0; u < kKnnVecLoads; ++u) {
+          const int q = q0 + u * 32 + lane;
+          v[r][u] = (live[r] && q < m4) ? __ldcs(reinterpret_cast<const float4*>(drow[r]) + q) : make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+        }
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        float lmin = INFINITY;
+#pragma unroll
+        for (int u = 0; u < kKnnVecLoads; ++u) lmin = fminf(lmin, fminf(fminf(v[r][u].x, v[r][u].y), fminf(v[r][u].z, v[r][u].w)));
+        if (live[r] && __any_sync(0xffffffffu, lmin <= tk[r].thr_d)) {
+#pragma unroll
+          for (int u = 0; u < kKnnVecLoads; ++u) {
+            const int q = q0 + u * 32 + lane;
+            const bool ok = q < m4;
+            tk[r].offer(v[r][u].x, 4 * q + 0, ok, lane, last_lane, last_slot);
+            tk[r].offer(v[r][u].y, 4 * q + 1, ok, lane, last_lane, last_slot);
+            tk[r].offer(v[r][u].z, 4 * q + 2, ok, lane, last_lane, last_slot);
+            tk[r].offer(v[r][u].w, 4 * q + 3, ok, lane, last_lane, last_slot);
+          }
+        }
+      }
+    }
+  } else {
+    for (int j0 = 0; j0 < m; j0 += 32 * kKnnScalarLoads) {
+      float v[ROWS][kKnnScalarLoads];
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+        for (int u = 0; u < kKnnScalarLoads; ++u) {
+          const int j = j0 + u * 32 + lane;
+          v[r][u] = (live[r] && j < m) ? __ldcs(drow[r] + j) : INFINITY;
+        }
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        float lmin = INFINITY;
+#pragma unroll
+        for (int u = 0; u < kKnnScalarLoads; ++u) lmin = fminf(lmin, v[r][u]);
+        if (live[r] && __any_sync(0xffffffffu, lmin <= tk[r].thr_d)) {
+#pragma unroll
+          for (int u = 0; u < kKnnScalarLoads; ++u) {
+            const int j = j0 + u * 32 + lane;
+            tk[r].offer(v[r][u], j, j < m, lane, last_lane, last_slot);
+          }
+        }
+      }
+    }
+  }
+}
+
+// k <= 16: one warp per PAIR of rows.  Both rows stream together (twice the loads in flight); afterwards row A's list
+// sits on lanes 0..15 and row B's on lanes 16..31, so the sigma bisection runs on full warps.  Each bisection step is
+// first evaluated in fp32 (MUFU ex2); the fp64 sum of the numba kernel is only formed when the fp32 one is within
+// kScreenBand of the target, i.e. when fp32 could decide the comparison or the convergence test differently (its error
+// is < 1e-5: 15 terms of |x| e^-|x| * 2^-22), so lo/mid/hi follow exactly the fp64 sequence.
+constexpr float kScreenBand = 1e-3f;
+__global__ void __launch_bounds__(128) knn_smooth_pair_kernel(const float* __restrict__ D, int n, int m, int k, float local_connectivity,
+                                                              float bandwidth, int n_iter, int* __restrict__ knn_idx,
+                                                              float* __restrict__ knn_dist, float* __restrict__ sigma,
+                                                              float* __restrict__ rho, double* __restrict__ dist_sum) {
+  const int p = blockIdx.y;
+  const int row0 = 2 * (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+  const int lane = threadIdx.x & 31;
+  if (row0 >= n) return;
+  const float* drow[2] = {D + ((size_t)p * n + row0) * m, D + ((size_t)p * n + min(row0 + 1, n - 1)) * m};
+  const bool live[2] = {true, row0 + 1 < n};
+  TopK<1> tk[2];
+  tk[0].init();
+  tk[1].init();
+  knn_stream_rows<1, 2>(drow, live, m, k, lane, tk);
+  // ---- pack: lanes 0..15 = row A ranks 0..15, lanes 16..31 = row B ranks 0..15
+  const int half = lane >> 4, hl = lane & 15;
+  const float dB = __shfl_sync(0xffffffffu, tk[1].dv[0], hl);
+  const int iB = __shfl_sync(0xffffffffu, tk[1].iv[0], hl);
+  const float d = half ? dB : tk[0].dv[0];
+  const int ix = half ? iB : tk[0].iv[0];
+  const int row = row0 + half;
+  const bool row_ok = row < n;
+  const bool in_list = hl < k;
+  if (row_ok && in_list) {
+    knn_idx[((size_t)p * n + row) * k + hl] = isinf(d) ? -1 : ix;
+    knn_dist[((size_t)p * n + row) * k + hl] = d;
+  }
+  double rsum = in_list ? (double)d : 0.0;
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) rsum += __shfl_xor_sync(0xffffffffu, rsum, o);
+  // ---- rho: distance to the local_connectivity-th nearest neighbour at positive distance (interpolated)
+  const unsigned zb = __ballot_sync(0xffffffffu, in_list && !(d > 0.f));
+  const int zeros = __popc((zb >> (16 * half)) & 0xffffu);
+  const int nnz = k - zeros;
+  const int index = (int)floorf(local_connectivity);
+  const float interp = local_connectivity - (float)index;
+  const float f_prev = __shfl_sync(0xffffffffu, d, min(max(zeros + index - 1, 0), 15), 16);
+  const float f_next = __shfl_sync(0xffffffffu, d, min(zeros + index, 15), 16);
+  const float f_first = __shfl_sync(0xffffffffu, d, min(zeros, 15), 16);
+  const float f_last = __shfl_sync(0xffffffffu, d, k - 1, 16);
+  float rho_i = 0.f;
+  if ((float)nnz >= local_connectivity) {
+    if (index > 0) {
+      rho_i = f_prev;
+      if (interp > (float)kSmoothKTolerance) rho_i += interp * (f_next - f_prev);
+    } else {
+      rho_i = interp * f_first;
+    }
+  } else if (nnz > 0) {
+    rho_i = f_last;  // max of the positive entries = last entry of the sorted list
+  }
+  // ---- sigma: umap-learn's bisection, two rows per warp
+  const double target = log2((double)k) * (double)bandwidth;
+  const float targetf = (float)target;
+  const bool term = hl >= 1 && in_list;
+  const float dd = d - rho_i;  // float32 subtraction, as in the numba kernel
+  double lo = 0.0, hi = INFINITY, mid = 1.0;
+  bool done = !row_ok;
+  for (int it = 0; it < n_iter; ++it) {
+    if (__all_sync(0xffffffffu, done)) break;
+    float e32 = 0.f;
+    if (term) e32 = dd > 0.f ? __expf(-__fdividef(dd, (float)mid)) : 1.f;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) e32 += __shfl_xor_sync(0xffffffffu, e32, o);
+    const bool close = !done && !(fabsf(e32 - targetf) >= kScreenBand);  // NaN counts as close
+    double psum = (double)e32;
+    if (__any_sync(0xffffffffu, close)) {
+      double e64 = 0.0;
+      if (term) e64 = dd > 0.f ? exp(-((double)dd / mid)) : 1.0;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) e64 += __shfl_xor_sync(0xffffffffu, e64, o);
+      if (close) psum = e64;
+    }
+    if (!done) {
+      if (close && fabs(psum - target) < kSmoothKTolerance) {
+        done = true;
+      } else if (psum > target) {
+        hi = mid;
+        mid = (lo + hi) / 2.0;
+      } else {
+        lo = mid;
+        if (isinf(hi)) mid *= 2.0; else mid = (lo + hi) / 2.0;
+      }
+    }
+  }
+  if (hl == 0 && row_ok) {
+    float sg = (float)mid;
+    if (rho_i > 0.f) {
+      const float mean_i = (float)(rsum / k);
+      if (sg < kMinKDistScale * mean_i) sg = kMinKDistScale * mean_i;
+    }
+    sigma[(size_t)p * n + row] = sg;
+    rho[(size_t)p * n + row] = rho_i;
+    atomicAdd(&dist_sum[p], rsum);
+  }
+}
+
+// general k (up to 256): one warp per row, list of KPL entries per lane.
+template <int KPL>
+__global__ void __launch_bounds__(256) knn_smooth_kernel(const float* __restrict__ D, int n, int m, int k, float local_connectivity,
+                                                         float bandwidth, int n_iter, int* __restrict__ knn_idx,
+                                                         float* __restrict__ knn_dist, float* __restrict__ sigma, float* __restrict__ rho,
+                                                         double* __restrict__ dist_sum) {
+  const int p = blockIdx.y;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* drows[1] = {D + ((size_t)p * n + row) * m};
+  const bool lives[1] = {true};
+  TopK<KPL> tks[1];
+  tks[0].init();
+  knn_stream_rows<KPL, 1>(drows, lives, m, k, lane, tks);
+  float (&dv)[KPL] = tks[0].dv;
+  int (&iv)[KPL] = tks[0].iv;
   // ---- write the neighbour lists (index -1 where the neighbour is at infinite distance: "disconnected")
   int* oi = knn_idx + ((size_t)p * n + row) * k;
   float* od = knn_dist + ((size_t)p * n + row) * k;
@@ -471,7 +661,10 @@ extern "C" int tda_knn_smooth(const float* D, int n, int m, int batch, int k, fl
   dim3 grid((n + 7) / 8, batch);
   const int kpl = (k + 31) / 32;
 #define TDA_KNN_LAUNCH(KPL) knn_smooth_kernel<KPL><<<grid, 256, 0, stream>>>(D, n, m, k, local_connectivity, bandwidth, n_iter, knn_idx, knn_dist, sigma, rho, dist_sum)
-  if (kpl == 1) TDA_KNN_LAUNCH(1);
+  if (k <= 16) {
+    dim3 gp((n + 7) / 8, batch);  // 4 warps x 2 rows per CTA
+    knn_smooth_pair_kernel<<<gp, 128, 0, stream>>>(D, n, m, k, local_connectivity, bandwidth, n_iter, knn_idx, knn_dist, sigma, rho, dist_sum);
+  } else if (kpl == 1) TDA_KNN_LAUNCH(1);
   else if (kpl == 2) TDA_KNN_LAUNCH(2);
   else if (kpl <= 4) TDA_KNN_LAUNCH(4);
   else TDA_KNN_LAUNCH(8);

@@ -26,7 +26,9 @@ def torch_cuda():
     return torch
 
 
-@pytest.mark.parametrize("n,k,metric", [(500, 15, "cosine"), (36, 6, "cosine"), (300, 40, "euclidean"), (130, 129, "cosine")])
+@pytest.mark.parametrize("n,k,metric", [(500, 15, "cosine"), (36, 6, "cosine"), (300, 40, "euclidean"), (130, 129, "cosine"),
+                                        (501, 15, "cosine"), (37, 2, "euclidean"), (131, 16, "cosine"), (203, 17, "euclidean"),
+                                        (1028, 15, "cosine")])
 def test_knn_smooth_matches_oracle(torch_cuda, n, k, metric):
     torch = torch_cuda
     from oracle import umap_oracle as uo
@@ -48,6 +50,30 @@ def test_knn_smooth_matches_oracle(torch_cuda, n, k, metric):
     psum = np.exp(-np.maximum(dd[:, 1:] - r[:, None], 0) / s[:, None]).sum(1)
     floored = s <= 1e-3 * dd.mean(1) * (1 + 1e-6)
     assert np.all((np.abs(psum - np.log2(k)) < 1e-3) | floored)
+
+
+@pytest.mark.parametrize("rows,cols,k,batch", [(301, 500, 15, 3), (64, 2000, 15, 2), (77, 333, 8, 2), (50, 402, 20, 2)])
+def test_knn_smooth_batched_rectangular(torch_cuda, rows, cols, k, batch):
+    """Row pairs / odd row counts / vector and scalar loads / several problems per launch (the transform and row-block
+    callers pass rectangular blocks): indices, distances, rho exact; sigma equal to a float64 host replay of the bisection."""
+    torch = torch_cuda
+    from oracle import umap_oracle as uo
+    from tda_multimodal_b200 import umap_
+    rng = np.random.default_rng(rows * 7 + cols)
+    dmat = rng.random((batch, rows, cols), dtype=np.float32)
+    dmat[:, :, 0][:, ::5] = 0.0          # some zero distances (rho skips them)
+    dmat[0, 3, :] = np.inf               # a row with fewer than k finite entries
+    dmat[0, 3, 5:9] = [0.5, 0.25, 0.75, 0.125]
+    dmat[1, 7, 10:14] = 0.3              # ties: smaller column first
+    idx, dist, sigma, rho = umap_.knn_smooth(torch.from_numpy(dmat).cuda(), k)
+    for b in range(batch):
+        oidx, odist = uo.exact_knn(dmat[b], k)
+        osig, orho = uo.smooth_knn_dist(odist, float(k))
+        assert np.array_equal(idx[b].cpu().numpy(), oidx)
+        assert np.array_equal(dist[b].cpu().numpy(), odist)
+        assert np.array_equal(rho[b].cpu().numpy(), orho)
+        fin = np.isfinite(odist).all(1)
+        np.testing.assert_allclose(sigma[b].cpu().numpy()[fin], osig[fin], rtol=1e-6)
 
 
 def test_knn_from_tensor_core_distances(torch_cuda):
