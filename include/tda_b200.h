@@ -165,10 +165,12 @@ int tda_rips_launch(const float* dm, int n, int batch, int maxdim, float thresh,
  * Triangles in an apparent pair with a tetrahedron are skipped in parallel, the residual triangle columns are reduced like the
  * H1 columns (implicit cohomology over Z/2, working column = bitset over tetrahedron keys).  n <= 2048 (triangle keys E*n < 2^32).
  *   h2_pairs [batch,cap2,2] float32 (birth, death), death > birth; counts2 [batch,4] int32: -, n_h2 rows, -, status;
- *   cap2 a power of two; returns TDA_ERR_CAPACITY (after synchronising) if a problem overflowed cap2 or the pool. */
-size_t tda_rips_h2_workspace_bytes(int n, int batch, int cap2, size_t pool_bytes);
+ *   cap2 a power of two; returns TDA_ERR_CAPACITY (after synchronising) if a problem overflowed cap2 or the pool.
+ *   far_bytes: room for the far buckets (tetrahedron keys beyond the 2^32-bit window of the working column wait there, one
+ *   region per window and resident CTA, until the window reaches them); 0 = none (later windows are re-enumerated instead). */
+size_t tda_rips_h2_workspace_bytes(int n, int batch, int cap2, size_t pool_bytes, size_t far_bytes);
 int tda_rips_h2(const void* ws1, int n, int batch, int cap1, size_t pool_bytes1, float* h2_pairs, int cap2, int32_t* counts2,
-                void* ws2, size_t ws2_bytes, size_t pool_bytes2, void* stream);
+                void* ws2, size_t ws2_bytes, size_t pool_bytes2, size_t far_bytes, void* stream);
 /* device statistics of the last tda_rips call on this workspace: [batch,16] int64 (row-sweep reducer):
  * columns (non-MST edges <= thresh), apparent pairs, reduced columns, column additions, rows streamed through the filter,
  * pivots, restarts of a chunk (new vertex touched / reduced column added), largest |V|, then SM cycles of CTA thread 0 in:

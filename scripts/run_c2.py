@@ -6,7 +6,7 @@ import numpy as np, torch
 from tda_multimodal_b200 import rips, workloads
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
 X = workloads.c2_torus(n=n)
-for rep in range(2):
+for rep in range(int(os.environ.get("C2_REPS", "1"))):
     torch.cuda.synchronize(); t = time.perf_counter()
     r = rips.ripser(X, maxdim=2)
     torch.cuda.synchronize(); dt = time.perf_counter() - t

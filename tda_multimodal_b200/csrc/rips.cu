@@ -346,7 +346,12 @@ __global__ void apparent_kernel(const int* __restrict__ rank, const uint32_t* __
 // column touches only dirty pages.  The 2^18 keys just ahead of the scan position (the "near" range) are held in
 // shared memory instead: the chain of pivots is followed there without a global fence or a global read per step,
 // and the range is refilled from the global bitset (and zeroed there) when the scan runs off its end.  If the key
-// space exceeds the window, keys beyond it are dropped and delta(V) is re-enumerated when the window slides.
+// space exceeds the window (H2 of more than ~300 points: E * n^2 tetrahedron keys), a key beyond the window is appended to the
+// FAR BUCKET of the window it belongs to (fixed region per window, counter in shared memory); when the scan runs off the
+// window it jumps to the next non-empty bucket and toggles that bucket's keys into the (all-zero) bitset, so every key is
+// written once and read once however many windows a column crosses.  Only if a bucket overflows does the column fall back to
+// re-enumerating delta(V) for each later window (the first version of this reducer did that for every slide:
+// C2 at n = 2000 crossed up to 1.8 k windows per column and did not finish).
 // -DTDA_BOUNDS_CHECK: every indexed access of the reducer is checked; the first violations are printed (device printf) and
 // the access is skipped, so a bad index can be located without compute-sanitizer
 #ifdef TDA_BOUNDS_CHECK
@@ -363,6 +368,7 @@ constexpr int kNearShift = 18;                 // near range: 2^18 bits = 32 pag
 constexpr int kNearWords = 1 << (kNearShift - 5);
 constexpr uint64_t kNearBits = 1ull << kNearShift;
 constexpr uint32_t kScanRows = 8;              // rows of kReduceThreads near words examined per barrier
+constexpr uint32_t kMaxFarBuckets = 8192;      // fill counters of the far buckets live in shared memory (32 KB at most)
 
 struct ReduceParams {
   const int* rank; const uint32_t* ends; const float* sdist; const int* T; const uint2* ea;  // ea[r] = (endpoints, apex)
@@ -381,6 +387,9 @@ struct ReduceParams {
   int64_t* vstart; int* vlen;               // [batch, cap1]
   int* work_counter; unsigned long long* stats;  // [batch, ST_N]
   const short* apex4;                       // (H2) [batch, E*n] per triangle key: the vertex of its apparent cofacet, or -1
+  // far buckets (key space larger than one window): keys beyond the window wait in the bucket of their window instead of
+  // being re-enumerated from V when the window gets there.  [grid, far_cap] keys; nbk = most windows a column can see
+  uint64_t* far; uint64_t far_cap; uint32_t nbk;
 };
 
 struct ReduceSmem {
@@ -389,6 +398,7 @@ struct ReduceSmem {
   uint32_t val[2][kReduceThreads / 32];
   uint32_t vcount, vcount2, vsel;
   int abort_flag, problem;
+  int far_overflow;        // a bucket of this column ran out of room: its later windows are re-enumerated from V instead
   unsigned long long toggles;
 };
 
@@ -410,6 +420,12 @@ struct Reducer {
   uint64_t wbase;          // first key of the window
   uint64_t nbase;          // first relative position of the near range (page aligned)
   uint32_t par;            // parity of the bal/val double buffer
+  uint64_t* far; uint32_t* fcnt;   // far buckets of this CTA, their fill counters (dynamic shared memory, after s1)
+  uint64_t* foff;                  // start of every bucket's region (dynamic shared memory): regions grow with the window index,
+                                   // because a cofacet's longest edge is the max of several ranks (density ~ x^2 over the key space)
+  uint64_t wbase0;                 // first window of the current column
+  uint32_t cur_b, ncol_b;          // current window / number of windows of the current column
+  bool far_on;
   unsigned long long my_toggles;
   unsigned long long n_refills, n_passes;   // diagnostics
 
@@ -425,6 +441,20 @@ struct Reducer {
     par = 0;
     my_toggles = 0;
     n_refills = n_passes = 0;
+    far = P.far ? P.far + (size_t)blockIdx.x * P.far_cap : nullptr;
+    fcnt = s1 + s1words;
+    foff = reinterpret_cast<uint64_t*>(s1 + ((s1words + P.nbk + 1) & ~1u));
+    wbase0 = 0; cur_b = 0; ncol_b = 1; far_on = false;
+  }
+
+  // a key beyond the current window: park it in the bucket of its window
+  __device__ __forceinline__ void far_append(uint64_t key) {
+    const uint32_t b = (uint32_t)((key - wbase0) / wbits);
+    if (!TDA_BC(b > cur_b && b < ncol_b, "far_append bucket/ncol_b", b, ncol_b)) return;
+    const uint32_t slot = atomicAdd(&fcnt[b], 1u);
+    const uint64_t o0 = foff[b];
+    if ((uint64_t)slot < foff[b + 1] - o0) far[o0 + slot] = key;
+    else S.far_overflow = 1;
   }
 
   // smallest thread index whose word is non-zero (and that word), or -1; one barrier per call
@@ -552,18 +582,37 @@ struct Reducer {
     const int* roww = R + (size_t)w * n;
     const uint64_t hi = wbase + wbits;
     const uint64_t n2 = (uint64_t)n * (uint64_t)n;
-    for (int v = t0; v < n; v += nthr) {
-      const int rx = __ldg(&rowx[v]), ry = __ldg(&rowy[v]), rw = __ldg(&roww[v]);   // v in {x,y,w}: kRankDiag -> skipped below
-      const int M4 = max(max(M, rx), max(ry, rw));
-      if (M4 >= T) continue;
-      int p2, q2;   // the two vertices off the longest edge
-      if (M4 == M) { p2 = w; q2 = v; }
-      else if (M4 == rx) { p2 = y; q2 = w; }
-      else if (M4 == ry) { p2 = x; q2 = w; }
-      else { p2 = x; q2 = y; }
-      const int hi_v = max(p2, q2), lo_v = min(p2, q2);
-      const uint64_t key = (uint64_t)M4 * n2 + (uint64_t)(n - 1 - hi_v) * (uint64_t)n + (uint64_t)(n - 1 - lo_v);
-      if (key >= lo && key < hi) toggle_key(key);
+    // the three rank rows are read once each and never again (L2 latency per element): keep kTriLoads vertices per thread in
+    // flight -- one warp per triangle walks n/32 vertices, which cost 25 k cycles per triangle with one load group at a time
+    constexpr int kTriLoads = 8;
+    for (int v0 = t0; v0 < n; v0 += nthr * kTriLoads) {
+      int rxs[kTriLoads], rys[kTriLoads], rws[kTriLoads];
+#pragma unroll
+      for (int u = 0; u < kTriLoads; ++u) {
+        const int v = v0 + u * nthr;
+        const bool in = v < n;
+        rxs[u] = in ? __ldg(&rowx[v]) : kRankDiag;   // (v in {x,y,w}: kRankDiag as well -> skipped below)
+        rys[u] = in ? __ldg(&rowy[v]) : kRankDiag;
+        rws[u] = in ? __ldg(&roww[v]) : kRankDiag;
+      }
+#pragma unroll
+      for (int u = 0; u < kTriLoads; ++u) {
+        const int v = v0 + u * nthr;
+        const int rx = rxs[u], ry = rys[u], rw = rws[u];
+        const int M4 = max(max(M, rx), max(ry, rw));
+        if (M4 >= T) continue;
+        int p2, q2;   // the two vertices off the longest edge
+        if (M4 == M) { p2 = w; q2 = v; }
+        else if (M4 == rx) { p2 = y; q2 = w; }
+        else if (M4 == ry) { p2 = x; q2 = w; }
+        else { p2 = x; q2 = y; }
+        const int hi_v = max(p2, q2), lo_v = min(p2, q2);
+        const uint64_t key = (uint64_t)M4 * n2 + (uint64_t)(n - 1 - hi_v) * (uint64_t)n + (uint64_t)(n - 1 - lo_v);
+        if (key >= lo) {
+          if (key < hi) toggle_key(key);
+          else if (far_on) far_append(key);
+        }
+      }
     }
   }
   __device__ __forceinline__ void gen(int re, uint32_t e, uint64_t lo, int t0, int nthr) {
@@ -586,13 +635,19 @@ struct Reducer {
         if (M < T) {
           const int opp = (M == re) ? v : (M == ra[it] ? b : a);
           const uint64_t key = (uint64_t)M * (uint64_t)n + (uint64_t)(n - 1 - opp);
-          if (key >= lo && key < hi) toggle_key(key);
+          if (key >= lo) {
+            if (key < hi) toggle_key(key);
+            else if (far_on) far_append(key);
+          }
         }
       }
     }
   }
   // the next scan reads shared memory only (the global XORs are fenced when the near range is refilled)
-  __device__ __forceinline__ void publish() { __syncthreads(); }
+  // The fence is required: the toggles are fire-and-forget RED operations, and without it a batch of two clouds (two CTAs
+  // reducing at the same time) faulted in about one run of five (an illegal address a few columns later); bar.sync alone
+  // does not wait for them.  160 repetitions are clean with it (scripts/h2_flaky.py).
+  __device__ __forceinline__ void publish() { __threadfence(); __syncthreads(); }
 
   // ---- V (the reduction column as a set of edges, by rank)
   __device__ __forceinline__ uint32_t* vlist(uint32_t sel) const { return vl0 + (size_t)sel * P.vcap; }
@@ -756,7 +811,7 @@ struct Reducer {
     int64_t vpool_used = 0;
     unsigned long long additions = 0, slides = 0, maxv = 0, pops = 0;
     long long cyc[6] = {0, 0, 0, 0, 0, 0};
-    unsigned long long badd_edges = 0, ext_edges = 0;
+    unsigned long long badd_edges = 0, ext_edges = 0, far_keys = 0;
     long long t0;
     float* out = P.h1_pairs + (size_t)p * P.cap1 * 2;
     int64_t* outs = P.h1_simplex ? P.h1_simplex + (size_t)p * P.cap1 * 2 : nullptr;
@@ -768,6 +823,25 @@ struct Reducer {
       wbase = first & ~((1ull << kPageShift) - 1);
       nbase = 0;
       uint64_t pos = first - wbase;
+      wbase0 = wbase;
+      cur_b = 0;
+      ncol_b = (uint32_t)((kmax - wbase0 + wbits - 1) / wbits);
+      far_on = far != nullptr && ncol_b > 1 && ncol_b <= P.nbk;
+      if (far_on) {
+        // region of bucket b: 30 % of the room split evenly, 70 % in proportion to x^3 over the part of the key space the
+        // column can still reach (x = rank of the longest edge / T)
+        const double x0 = (double)wbase0 / (double)kmax, x03 = x0 * x0 * x0, den = 1.0 - x03;
+        for (uint32_t b = tid; b <= ncol_b; b += kReduceThreads) {
+          double xb = ((double)wbase0 + (double)b * (double)wbits) / (double)kmax;
+          if (xb > 1.0) xb = 1.0;
+          const double cubic = den > 1e-9 ? (xb * xb * xb - x03) / den : (double)b / (double)ncol_b;
+          const double f = 0.3 * (double)b / (double)ncol_b + 0.7 * cubic;
+          foff[b] = b == ncol_b ? P.far_cap : (uint64_t)((double)P.far_cap * (f < 1.0 ? f : 1.0));
+        }
+        for (uint32_t b = tid; b < ncol_b; b += kReduceThreads) fcnt[b] = 0;
+        if (tid == 0) S.far_overflow = 0;
+        __syncthreads();
+      }
       if (tid == 0) v_toggle(rbirth);
       gen(rbirth, first, tid, kReduceThreads);
       publish();
@@ -779,6 +853,28 @@ struct Reducer {
         const bool ok = scan(pos);
         cyc[0] += clock64() - t0;
         if (!ok) {
+          if (far_on && S.far_overflow) far_on = false;   // (uniform: written before the barriers inside scan())
+          if (far_on) {
+            // jump to the next window that holds parked keys and toggle them in (the bitset is all zero now)
+            t0 = clock64();
+            uint32_t cand = 0xffffffffu;
+            for (uint32_t b = cur_b + 1 + tid; b < ncol_b; b += kReduceThreads)
+              if (fcnt[b]) { cand = b; break; }
+            cand = block_min(cand);
+            if (cand == 0xffffffffu) { essential = true; break; }
+            cur_b = cand;
+            wbase = wbase0 + (uint64_t)cand * wbits;
+            nbase = 0;
+            pos = 0;
+            const uint32_t cnt = fcnt[cand];
+            const uint64_t* src = far + foff[cand];
+            for (uint32_t i = tid; i < cnt; i += kReduceThreads) toggle_key(src[i]);
+            publish();
+            ++slides;
+            far_keys += cnt;
+            cyc[4] += clock64() - t0;
+            continue;
+          }
           if (wbase + wbits >= kmax) { essential = true; break; }
           // slide the window (it is all zero now) and re-enumerate delta(V) for the new range
           t0 = clock64();
@@ -841,6 +937,7 @@ struct Reducer {
       if (S.abort_flag) break;
       t0 = clock64();
       // finalise the column
+      far_on = false;   // (clean_window re-enumerates delta(V) inside the last window only)
       v_compact();
       const uint32_t nv = S.vcount;
       if (nv > maxv) maxv = nv;
@@ -914,7 +1011,7 @@ struct Reducer {
       st[ST_MAXV] = maxv;
       for (int q = 0; q < 6; ++q) st[ST_CYC_EXTRACT + q] = (unsigned long long)cyc[q];
       st[ST_BADD_EDGES] = badd_edges;
-      st[ST_EXT_EDGES] = ext_edges + n_passes;
+      st[ST_EXT_EDGES] = ext_edges + n_passes + far_keys;
     }
     __syncthreads();
   }
@@ -2053,6 +2150,7 @@ static int rips_enqueue(const float* dm, int n, int batch, int maxdim, float thr
     P.bits = L.bits; P.wbits = L.wbits; P.xmat = L.xmat; P.xw = L.xw; P.pmat = L.pmat;
     P.vpool = L.vpool; P.vpool_cap = L.vpool_cap; P.vstart = L.vstart; P.vlen = L.vlen;
     P.work_counter = L.work_counter; P.stats = L.stats;
+    P.apex4 = nullptr; P.far = nullptr; P.far_cap = 0; P.nbk = 0;
     {
       StageScope st(STAGE_RIPS_REDUCE, stream);
       if (L.sweep) {
@@ -2135,9 +2233,10 @@ struct Layout2 {
   uint64_t* hkeys; int* hvals; int hcap; int64_t* vstart; int* vlen; uint32_t* vpool; int64_t vpool_cap;
   uint32_t* bits; uint64_t wbits; uint32_t* vbits; int64_t vwords; uint32_t* vlist; int64_t vcap;
   int* work_counter; unsigned long long* stats;
+  uint64_t* far; uint64_t far_cap; uint32_t nbk;
   int grid; size_t total;
 };
-static Layout2 make_layout2(void* ws, int n, int batch, int cap2, size_t pool_bytes, int sm_count) {
+static Layout2 make_layout2(void* ws, int n, int batch, int cap2, size_t pool_bytes, size_t far_bytes, int sm_count) {
   Layout2 L;
   memset(&L, 0, sizeof(L));
   const int64_t E = (int64_t)n * (n - 1) / 2;
@@ -2173,19 +2272,24 @@ static Layout2 make_layout2(void* ws, int n, int batch, int cap2, size_t pool_by
   L.vpool_cap = pool_bytes > bits_bytes ? (int64_t)((pool_bytes - bits_bytes) / (size_t)batch / sizeof(uint32_t)) : 0;
   if (L.vpool_cap < 4 * (int64_t)cap2) L.vpool_cap = 4 * (int64_t)cap2;
   L.vpool = c.take<uint32_t>((size_t)batch * L.vpool_cap);
+  // far buckets: one region per window of the key space and resident CTA (only when the key space exceeds the window)
+  L.nbk = want_d > (double)L.wbits ? (uint32_t)(want_d / (double)L.wbits) + 2 : 0;
+  L.far_cap = L.nbk ? (uint64_t)(far_bytes / (size_t)L.grid / sizeof(uint64_t)) : 0;
+  if (L.nbk > kMaxFarBuckets || L.far_cap < 256ull * L.nbk) { L.nbk = 0; L.far_cap = 0; }   // too many windows / no room: re-enumerate
+  L.far = L.far_cap ? c.take<uint64_t>((size_t)L.grid * L.far_cap) : nullptr;
   L.total = c.off;
   return L;
 }
 }  // namespace rips
 }  // namespace tda
 
-extern "C" size_t tda_rips_h2_workspace_bytes(int n, int batch, int cap2, size_t pool_bytes) {
+extern "C" size_t tda_rips_h2_workspace_bytes(int n, int batch, int cap2, size_t pool_bytes, size_t far_bytes) {
   if (n <= 0 || batch <= 0 || cap2 <= 0) return 0;
-  return make_layout2(nullptr, n, batch, next_pow2(cap2), pool_bytes, 148).total + 4096;
+  return make_layout2(nullptr, n, batch, next_pow2(cap2), pool_bytes, far_bytes, 148).total + 4096;
 }
 
 extern "C" int tda_rips_h2(const void* ws1, int n, int batch, int cap1, size_t pool_bytes1, float* h2_pairs, int cap2, int32_t* counts2,
-                           void* ws2, size_t ws2_bytes, size_t pool_bytes2, void* stream_) {
+                           void* ws2, size_t ws2_bytes, size_t pool_bytes2, size_t far_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!ws1 || !h2_pairs || !counts2 || !ws2 || n <= 0 || batch <= 0 || cap2 <= 0) return set_error(TDA_ERR_INVALID, "tda_rips_h2: bad arguments");
   if (n > 32 * kH2MaxWords) return set_error(TDA_ERR_UNSUPPORTED, "tda_rips_h2: n=%d > %d (H2 is implemented for small clouds)", n, 32 * kH2MaxWords);
@@ -2193,7 +2297,7 @@ extern "C" int tda_rips_h2(const void* ws1, int n, int batch, int cap1, size_t p
   if (batch > 65535) return set_error(TDA_ERR_INVALID, "tda_rips_h2: batch > 65535");
   const int sms = sm_count_cached();
   Layout L1 = make_layout((void*)ws1, n, batch, 1, next_pow2(cap1), pool_bytes1, sms);
-  Layout2 L = make_layout2(ws2, n, batch, cap2, pool_bytes2, sms);
+  Layout2 L = make_layout2(ws2, n, batch, cap2, pool_bytes2, far_bytes, sms);
   if (L.total > ws2_bytes) return set_error(TDA_ERR_WORKSPACE, "tda_rips_h2: workspace %zu < required %zu", ws2_bytes, L.total);
   const int64_t E = (int64_t)n * (n - 1) / 2;
   if (E == 0) { TDA_CUDA_CHECK(cudaMemsetAsync(counts2, 0, sizeof(int32_t) * 4 * batch, stream)); return TDA_OK; }
@@ -2231,8 +2335,10 @@ extern "C" int tda_rips_h2(const void* ws1, int n, int batch, int cap1, size_t p
   P.vpool = L.vpool; P.vpool_cap = L.vpool_cap; P.vstart = L.vstart; P.vlen = L.vlen;
   P.work_counter = L.work_counter; P.stats = L.stats;
   P.apex4 = L.apex4;
+  P.far = L.far; P.far_cap = L.far_cap; P.nbk = L.nbk;
   {
-    const size_t s1_bytes = (size_t)(((L.wbits >> kPageShift) + 31) / 32) * sizeof(uint32_t);
+    // page summary, then (far buckets) nbk fill counters and nbk + 1 region offsets
+    const size_t s1_bytes = ((size_t)(((L.wbits >> kPageShift) + 31) / 32) + (size_t)L.nbk + 2) * sizeof(uint32_t) + ((size_t)L.nbk + 1) * sizeof(uint64_t);
     TDA_CUDA_CHECK(cudaFuncSetAttribute(rips_reduce_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1_bytes));
     rips_reduce_kernel<2><<<L.grid, kReduceThreads, s1_bytes, stream>>>(P);
     count_launch();
@@ -2242,6 +2348,21 @@ extern "C" int tda_rips_h2(const void* ws1, int n, int batch, int cap1, size_t p
   {
     std::vector<int32_t> hc((size_t)batch * 4);
     TDA_CUDA_CHECK(cudaMemcpy(hc.data(), counts2, sizeof(int32_t) * 4 * batch, cudaMemcpyDeviceToHost));
+    if (getenv("TDA_H2_STATS")) {   // device counters of the H2 reduction, one line per problem (diagnostics)
+      std::vector<unsigned long long> hs((size_t)batch * ST_N);
+      std::vector<int> hb(batch);
+      TDA_CUDA_CHECK(cudaMemcpy(hs.data(), L.stats, sizeof(unsigned long long) * ST_N * batch, cudaMemcpyDeviceToHost));
+      TDA_CUDA_CHECK(cudaMemcpy(hb.data(), L.bcount2, sizeof(int) * batch, cudaMemcpyDeviceToHost));
+      for (int p = 0; p < batch; ++p) {
+        const unsigned long long* q = hs.data() + (size_t)p * ST_N;
+        fprintf(stderr, "tda_rips_h2 stats p=%d n=%d: residual columns %d (cap2 %d), additions %llu, toggles %llu, pivots %llu, slides+refills %llu, max|V| %llu, "
+                        "Mcycles scan %.1f owner %.1f apparent-add %.1f column-add %.1f slide %.1f finalise %.1f, edges via columns %llu, far keys+passes %llu, "
+                        "windows %u far_cap %llu wbits %llu\n",
+                p, n, hb[p], cap2, q[ST_ADDITIONS], q[ST_PUSHES], q[ST_POPS], q[ST_EXTENSIONS], q[ST_MAXV], q[ST_CYC_EXTRACT] / 1e6, q[ST_CYC_OWNER] / 1e6,
+                q[ST_CYC_GEN] / 1e6, q[ST_CYC_BADD] / 1e6, q[ST_CYC_EXT] / 1e6, q[ST_CYC_FINAL] / 1e6, q[ST_BADD_EDGES], q[ST_EXT_EDGES], L.nbk,
+                (unsigned long long)L.far_cap, (unsigned long long)L.wbits);
+      }
+    }
     for (int p = 0; p < batch; ++p)
       if (hc[p * 4 + 3] != 0)
         return set_error(TDA_ERR_CAPACITY, "tda_rips_h2: problem %d overflowed (cap2=%d or pool %zu bytes); retry with larger sizes", p, cap2, pool_bytes2);

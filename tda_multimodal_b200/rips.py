@@ -177,15 +177,20 @@ def rips_batch(dm, maxdim=1, thresh=float("inf"), cap1=None, pool_bytes=None, wa
         h2_h = c2_h = None
         if want_h2:
             E = n * (n - 1) // 2
-            cap2 = _next_pow2(max(1024, 32 * n))
+            cap2 = _next_pow2(max(1024, 32 * n, n * n // 8))   # residual triangle columns: ~7 k at n=500, ~3e5 expected at n=2000
             pool2 = max(64 << 20, min(2 * min(B, 296) * min(-(-(E * n * n) // 8), 1 << 29), int(0.35 * free_bytes)))
+            pool2 = int(os.environ.get("TDA_H2_POOL_BYTES", "0")) or pool2
+            # tetrahedron keys beyond one 2^32-bit window of the working column (n > ~300) are parked in far buckets, 8 B per key
+            far2 = int(os.environ.get("TDA_H2_FAR_BYTES", "-1"))
+            if far2 < 0:
+                far2 = 0 if E * n * n <= (1 << 32) else min(int(0.4 * free_bytes), min(B, 296) * (64 << 30))
             while True:
-                ws2_bytes = int(L.tda_rips_h2_workspace_bytes(n, B, cap2, pool2))
+                ws2_bytes = int(L.tda_rips_h2_workspace_bytes(n, B, cap2, pool2, far2))
                 ws2 = torch.empty(ws2_bytes, dtype=torch.uint8, device=dev)
                 h2 = torch.empty((B, cap2, 2), dtype=torch.float32, device=dev)
                 c2 = torch.zeros((B, 4), dtype=torch.int32, device=dev)
                 code = L.tda_rips_h2(_lib.ptr(ws), n, B, cap1, pool_bytes, _lib.ptr(h2), cap2, _lib.ptr(c2), _lib.ptr(ws2), ws2_bytes, pool2,
-                                     _lib.stream_ptr())
+                                     far2, _lib.stream_ptr())
                 if code == _lib.TDA_ERR_CAPACITY and pool2 < free_bytes // 2:
                     cap2 *= 4
                     pool2 *= 2

@@ -28,6 +28,26 @@ def test_h2_matches_oracle(gen, n, seed):
     assert np.all(d[2][:, 1] > d[2][:, 0])
 
 
+@pytest.mark.parametrize("far_bytes", [64 << 20, 64 << 10, 0])
+def test_h2_many_windows_far_buckets_match_oracle(monkeypatch, far_bytes):
+    """A tetrahedron key space of many windows (forced by a 4 MB pool: ~15 windows of 2^24 keys at n=150), as config C2 has at
+    n=2000 with 2^32-bit windows: keys beyond the window are parked in far buckets (64 MB: never overflow; 64 KB: buckets of a
+    few hundred keys overflow and the column falls back to re-enumerating its later windows; 0: no buckets at all)."""
+    from oracle import rips as orips
+    from tda_multimodal_b200 import rips
+    monkeypatch.setenv("TDA_H2_POOL_BYTES", str(4 << 20))
+    monkeypatch.setenv("TDA_H2_FAR_BYTES", str(far_bytes))
+    X = np.stack([torus3d(150, np.random.default_rng(11)), sphere(150, np.random.default_rng(12), 0.05)])
+    import torch
+    dm = rips.pdist_lowdim(torch.from_numpy(X.astype(np.float32)).cuda())
+    res = rips.rips_batch(dm, maxdim=2)
+    for b in range(2):
+        want = orips.ripser(X[b], maxdim=2)["dgms"]
+        d = res[b]["dgms"]
+        assert np.array_equal(d[0], want[0]) and np.array_equal(d[1], want[1])
+        assert same_diagram(d[2], want[2]), (far_bytes, b, len(d[2]), len(want[2]))
+
+
 def test_h2_sphere_has_one_dominant_void_and_batches():
     import torch
     from tda_multimodal_b200 import rips
