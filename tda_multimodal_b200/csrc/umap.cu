@@ -141,107 +141,257 @@ __device__ __forceinline__ void knn_stream_rows(const float* const (&drow)[ROWS]
   }
 }
 
-// k <= 16: one warp per PAIR of rows.  Both rows stream together (twice the loads in flight); afterwards row A's list
-// sits on lanes 0..15 and row B's on lanes 16..31, so the sigma bisection runs on full warps.  Each bisection step is
-// first evaluated in fp32 (MUFU ex2); the fp64 sum of the numba kernel is only formed when the fp32 one is within
-// kScreenBand of the target, i.e. when fp32 could decide the comparison or the convergence test differently (its error
-// is < 1e-5: 15 terms of |x| e^-|x| * 2^-22), so lo/mid/hi follow exactly the fp64 sequence.
-constexpr float kScreenBand = 1e-3f;
-__global__ void __launch_bounds__(128) knn_smooth_pair_kernel(const float* __restrict__ D, int n, int m, int k, float local_connectivity,
-                                                              float bandwidth, int n_iter, int* __restrict__ knn_idx,
-                                                              float* __restrict__ knn_dist, float* __restrict__ sigma,
-                                                              float* __restrict__ rho, double* __restrict__ dist_sum) {
-  const int p = blockIdx.y;
-  const int row0 = 2 * (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
-  const int lane = threadIdx.x & 31;
-  if (row0 >= n) return;
-  const float* drow[2] = {D + ((size_t)p * n + row0) * m, D + ((size_t)p * n + min(row0 + 1, n - 1)) * m};
-  const bool live[2] = {true, row0 + 1 < n};
-  TopK<1> tk[2];
-  tk[0].init();
-  tk[1].init();
-  knn_stream_rows<1, 2>(drow, live, m, k, lane, tk);
-  // ---- pack: lanes 0..15 = row A ranks 0..15, lanes 16..31 = row B ranks 0..15
-  const int half = lane >> 4, hl = lane & 15;
-  const float dB = __shfl_sync(0xffffffffu, tk[1].dv[0], hl);
-  const int iB = __shfl_sync(0xffffffffu, tk[1].iv[0], hl);
-  const float d = half ? dB : tk[0].dv[0];
-  const int ix = half ? iB : tk[0].iv[0];
-  const int row = row0 + half;
-  const bool row_ok = row < n;
-  const bool in_list = hl < k;
-  if (row_ok && in_list) {
-    knn_idx[((size_t)p * n + row) * k + hl] = isinf(d) ? -1 : ix;
-    knn_dist[((size_t)p * n + row) * k + hl] = d;
-  }
-  double rsum = in_list ? (double)d : 0.0;
+// ---- k <= 16: the C3 / C5 case ----------------------------------------------------------------------------------
+// A CTA of 4 warps owns 32 rows.  SELECTION (warp per row, 8 rows one after the other): the row is read once, in chunks of
+// 2048 columns held in registers (16 x 16-byte streaming loads per lane in flight).  The k-th smallest of the 32 lane minima
+// of a chunk bounds the row's k-th smallest from above, so only the few columns not above that bound (about 25 of 2000)
+// are candidates; they are pushed into a small shared-memory buffer and merged into the sorted best-k list (one 64-bit key
+// (distance, column) per lane) by a bitonic sort across the warp -- about a fifth of the instructions of an insertion per
+// candidate.  A row whose buffer overflows (ties, infinite distances) is redone with the insertion list.
+// BISECTION (all 128 threads, 4 threads per row): every step is evaluated in fp32 first (MUFU ex2); fp32 decides a step
+// only when it is at least kScreenBand away from the target (its error is < 1e-5: 15 terms of |x| e^-|x| * 2^-22), a row
+// that comes closer is parked, and the parked rows finish with the numba kernel's fp64 sum from exactly that state, so
+// lo/mid/hi follow the fp64 sequence.
+constexpr float kScreenBand = 1e-4f;
+constexpr int kBlkWarps = 4, kBlkRows = 32, kBlkRowsPerWarp = kBlkRows / kBlkWarps;
+constexpr int kBlkLoads = 16;                       // float4 per lane and chunk
+constexpr int kBlkChunk = 32 * 4 * kBlkLoads;       // 2048 columns
+constexpr int kBlkCand = 64;                        // candidate buffer per warp
+constexpr unsigned long long kKeyMax = ~0ull;
+
+__device__ __forceinline__ unsigned long long knn_key(float d, int j) {
+  d += 0.0f;                                        // -0 -> +0: equal distances must tie (the smaller column wins)
+  const uint32_t b = __float_as_uint(d);
+  const uint32_t o = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  return ((unsigned long long)o << 32) | (uint32_t)j;
+}
+__device__ __forceinline__ float knn_key_dist(unsigned long long key) {
+  const uint32_t o = (uint32_t)(key >> 32);
+  return __uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o);
+}
+template <typename T>
+__device__ __forceinline__ T warp_sort_asc(T v, int lane) {   // bitonic sort of one value per lane, ascending with the lane
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) rsum += __shfl_xor_sync(0xffffffffu, rsum, o);
-  // ---- rho: distance to the local_connectivity-th nearest neighbour at positive distance (interpolated)
-  const unsigned zb = __ballot_sync(0xffffffffu, in_list && !(d > 0.f));
-  const int zeros = __popc((zb >> (16 * half)) & 0xffffu);
-  const int nnz = k - zeros;
+  for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      const T o = __shfl_xor_sync(0xffffffffu, v, j);
+      const bool keep_min = ((lane & j) == 0) == ((lane & k2) == 0);
+      const T mn = v < o ? v : o, mx = v < o ? o : v;
+      v = keep_min ? mn : mx;
+    }
+  }
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_merge_bitonic(T v, int lane) {   // v bitonic across the lanes -> ascending
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) {
+    const T o = __shfl_xor_sync(0xffffffffu, v, j);
+    const T mn = v < o ? v : o, mx = v < o ? o : v;
+    v = ((lane & j) == 0) ? mn : mx;
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(kBlkWarps * 32) knn_smooth_block_kernel(const float* __restrict__ D, int n, int m, int k, float local_connectivity,
+                                                                            float bandwidth, int n_iter, int* __restrict__ knn_idx,
+                                                                            float* __restrict__ knn_dist, float* __restrict__ sigma,
+                                                                            float* __restrict__ rho, double* __restrict__ dist_sum) {
+  __shared__ unsigned long long s_cand[kBlkWarps][kBlkCand];
+  __shared__ uint32_t s_cnt[kBlkWarps];
+  __shared__ float s_kd[kBlkRows][16];
+  __shared__ float s_rho[kBlkRows];
+  __shared__ double s_rsum[kBlkRows];
+  const int p = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row_base = blockIdx.x * kBlkRows;
   const int index = (int)floorf(local_connectivity);
   const float interp = local_connectivity - (float)index;
-  const float f_prev = __shfl_sync(0xffffffffu, d, min(max(zeros + index - 1, 0), 15), 16);
-  const float f_next = __shfl_sync(0xffffffffu, d, min(zeros + index, 15), 16);
-  const float f_first = __shfl_sync(0xffffffffu, d, min(zeros, 15), 16);
-  const float f_last = __shfl_sync(0xffffffffu, d, k - 1, 16);
-  float rho_i = 0.f;
-  if ((float)nnz >= local_connectivity) {
-    if (index > 0) {
-      rho_i = f_prev;
-      if (interp > (float)kSmoothKTolerance) rho_i += interp * (f_next - f_prev);
-    } else {
-      rho_i = interp * f_first;
+
+  for (int ri = 0; ri < kBlkRowsPerWarp; ++ri) {
+    const int rl = warp * kBlkRowsPerWarp + ri;
+    const int row = row_base + rl;
+    if (row >= n) break;                               // (warp uniform)
+    const float* drow = D + ((size_t)p * n + row) * m;
+    const bool vec = ((m & 3) == 0) && ((reinterpret_cast<uintptr_t>(drow) & 15) == 0);
+    unsigned long long best = kKeyMax;                 // lane r: r-th smallest (distance, column) so far; kKeyMax beyond k
+    float tau = INFINITY;
+    bool overflow = false;
+    if (lane == 0) s_cnt[warp] = 0;
+    __syncwarp();
+    for (int c0 = 0; c0 < m && !overflow; c0 += kBlkChunk) {
+      float4 v[kBlkLoads];
+      if (vec) {
+#pragma unroll
+        for (int u = 0; u < kBlkLoads; ++u) {
+          const int e = c0 + (u * 32 + lane) * 4;
+          v[u] = e < m ? __ldcs(reinterpret_cast<const float4*>(drow + e)) : make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < kBlkLoads; ++u) {
+          const int e = c0 + (u * 32 + lane) * 4;
+          v[u].x = e + 0 < m ? __ldcs(drow + e + 0) : INFINITY;
+          v[u].y = e + 1 < m ? __ldcs(drow + e + 1) : INFINITY;
+          v[u].z = e + 2 < m ? __ldcs(drow + e + 2) : INFINITY;
+          v[u].w = e + 3 < m ? __ldcs(drow + e + 3) : INFINITY;
+        }
+      }
+      float lmin = INFINITY;
+#pragma unroll
+      for (int u = 0; u < kBlkLoads; ++u) lmin = fminf(lmin, fminf(fminf(v[u].x, v[u].y), fminf(v[u].z, v[u].w)));
+      const float sorted_min = warp_sort_asc<float>(lmin, lane);
+      tau = fminf(tau, __shfl_sync(0xffffffffu, sorted_min, k - 1));
+      // candidates: everything not above the bound (ties included; the merge orders them by column)
+#pragma unroll
+      for (int u = 0; u < kBlkLoads; ++u) {
+        const int e = c0 + (u * 32 + lane) * 4;
+        const float dd[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (dd[c] <= tau && e + c < m) {
+            const uint32_t pos = atomicAdd(&s_cnt[warp], 1u);
+            if (pos < (uint32_t)kBlkCand) s_cand[warp][pos] = knn_key(dd[c], e + c);
+          }
+        }
+      }
+      __syncwarp();
+      const uint32_t cnt = s_cnt[warp];
+      if (cnt > (uint32_t)kBlkCand) { overflow = true; break; }
+      const bool last = c0 + kBlkChunk >= m;
+      if (cnt >= 32u || last) {
+        unsigned long long a = (uint32_t)lane < cnt ? s_cand[warp][lane] : kKeyMax;
+        a = warp_sort_asc<unsigned long long>(a, lane);
+        if (cnt > 32u) {
+          unsigned long long b = (uint32_t)(32 + lane) < cnt ? s_cand[warp][32 + lane] : kKeyMax;
+          b = warp_sort_asc<unsigned long long>(b, lane);
+          const unsigned long long br = __shfl_sync(0xffffffffu, b, 31 - lane);
+          a = warp_merge_bitonic<unsigned long long>(a < br ? a : br, lane);   // the 32 smallest of a and b
+        }
+        // the 16 smallest candidates (lanes 0..15, ascending) against the best list reversed on lanes 16..31: bitonic
+        const unsigned long long rev = __shfl_sync(0xffffffffu, best, 31 - lane);
+        const unsigned long long w = warp_merge_bitonic<unsigned long long>(lane < 16 ? a : rev, lane);
+        best = lane < k ? w : kKeyMax;
+        const unsigned long long kth = __shfl_sync(0xffffffffu, best, k - 1);
+        if (kth != kKeyMax) tau = fminf(tau, knn_key_dist(kth));
+        __syncwarp();
+        if (lane == 0) s_cnt[warp] = 0;
+        __syncwarp();
+      }
     }
-  } else if (nnz > 0) {
-    rho_i = f_last;  // max of the positive entries = last entry of the sorted list
+    float d;
+    int ix;
+    if (overflow) {
+      // many equal / infinite distances: the insertion list handles any input
+      const float* drows[1] = {drow};
+      const bool lives[1] = {true};
+      TopK<1> tks[1];
+      tks[0].init();
+      knn_stream_rows<1, 1>(drows, lives, m, k, lane, tks);
+      d = tks[0].dv[0];
+      ix = tks[0].iv[0];
+    } else {
+      d = lane < k ? knn_key_dist(best) : INFINITY;
+      ix = (int)(uint32_t)best;
+    }
+    const bool in_list = lane < k;
+    if (in_list) {
+      knn_idx[((size_t)p * n + row) * k + lane] = isinf(d) ? -1 : ix;
+      knn_dist[((size_t)p * n + row) * k + lane] = d;
+    }
+    const double rsum = warp_sum_f64(in_list ? (double)d : 0.0);
+    // rho: distance to the local_connectivity-th nearest neighbour at positive distance (interpolated)
+    const int zeros = __popc(__ballot_sync(0xffffffffu, in_list && !(d > 0.f)));
+    const int nnz = k - zeros;
+    const float f_prev = __shfl_sync(0xffffffffu, d, min(max(zeros + index - 1, 0), 31));
+    const float f_next = __shfl_sync(0xffffffffu, d, min(zeros + index, 31));
+    const float f_first = __shfl_sync(0xffffffffu, d, min(zeros, 31));
+    const float f_last = __shfl_sync(0xffffffffu, d, k - 1);
+    float rho_i = 0.f;
+    if ((float)nnz >= local_connectivity) {
+      if (index > 0) {
+        rho_i = f_prev;
+        if (interp > (float)kSmoothKTolerance) rho_i += interp * (f_next - f_prev);
+      } else {
+        rho_i = interp * f_first;
+      }
+    } else if (nnz > 0) {
+      rho_i = f_last;  // max of the positive entries = last entry of the sorted list
+    }
+    if (lane < 16) s_kd[rl][lane] = d;                 // (lanes >= k hold +inf)
+    if (lane == 0) { s_rho[rl] = rho_i; s_rsum[rl] = rsum; }
   }
-  // ---- sigma: umap-learn's bisection, two rows per warp
+  __syncthreads();
+
+  // ---- sigma: umap-learn's bisection, 4 threads per row (terms q+1, q+5, q+9, q+13 of the row's list)
+  const int rl = threadIdx.x >> 2, q = threadIdx.x & 3;
+  const int row = row_base + rl;
+  const bool row_ok = row < n;
+  const float rho_i = row_ok ? s_rho[rl] : 0.f;
+  float dd[4];
+  bool term[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int j = 1 + q + 4 * t;
+    term[t] = row_ok && j < k;
+    dd[t] = term[t] ? s_kd[rl][j] - rho_i : 0.f;       // float32 subtraction, as in the numba kernel
+  }
   const double target = log2((double)k) * (double)bandwidth;
   const float targetf = (float)target;
-  const bool term = hl >= 1 && in_list;
-  const float dd = d - rho_i;  // float32 subtraction, as in the numba kernel
   double lo = 0.0, hi = INFINITY, mid = 1.0;
-  bool done = !row_ok;
-  for (int it = 0; it < n_iter; ++it) {
-    if (__all_sync(0xffffffffu, done)) break;
+  int it = 0;                                          // bisection steps this row has taken
+  int state = row_ok ? 0 : 2;                          // 0: fp32 screening, 1: parked (needs fp64), 2: done
+  for (int step = 0; step < n_iter; ++step) {
+    if (__all_sync(0xffffffffu, state != 0)) break;
+    const float midf = (float)mid;
     float e32 = 0.f;
-    if (term) e32 = dd > 0.f ? __expf(-__fdividef(dd, (float)mid)) : 1.f;
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) e32 += __shfl_xor_sync(0xffffffffu, e32, o);
-    const bool close = !done && !(fabsf(e32 - targetf) >= kScreenBand);  // NaN counts as close
-    double psum = (double)e32;
-    if (__any_sync(0xffffffffu, close)) {
-      double e64 = 0.0;
-      if (term) e64 = dd > 0.f ? exp(-((double)dd / mid)) : 1.0;
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) e64 += __shfl_xor_sync(0xffffffffu, e64, o);
-      if (close) psum = e64;
-    }
-    if (!done) {
-      if (close && fabs(psum - target) < kSmoothKTolerance) {
-        done = true;
-      } else if (psum > target) {
-        hi = mid;
-        mid = (lo + hi) / 2.0;
+    for (int t = 0; t < 4; ++t)
+      if (term[t]) e32 += dd[t] > 0.f ? __expf(-__fdividef(dd[t], midf)) : 1.f;
+    e32 += __shfl_xor_sync(0xffffffffu, e32, 1);
+    e32 += __shfl_xor_sync(0xffffffffu, e32, 2);
+    if (state == 0) {
+      if (!(fabsf(e32 - targetf) >= kScreenBand)) {    // too close for fp32 (NaN counts as close): redo this step in fp64
+        state = 1;
       } else {
-        lo = mid;
-        if (isinf(hi)) mid *= 2.0; else mid = (lo + hi) / 2.0;
+        if (e32 > targetf) { hi = mid; mid = (lo + hi) / 2.0; }
+        else { lo = mid; if (isinf(hi)) mid *= 2.0; else mid = (lo + hi) / 2.0; }
+        if (++it >= n_iter) state = 2;
       }
     }
   }
-  if (hl == 0 && row_ok) {
+  for (;;) {
+    if (__all_sync(0xffffffffu, state == 2)) break;
+    double e64 = 0.0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (term[t]) e64 += dd[t] > 0.f ? exp(-((double)dd[t] / mid)) : 1.0;
+    e64 += __shfl_xor_sync(0xffffffffu, e64, 1);
+    e64 += __shfl_xor_sync(0xffffffffu, e64, 2);
+    if (state != 2) {
+      if (fabs(e64 - target) < kSmoothKTolerance) {
+        state = 2;
+      } else {
+        if (e64 > target) { hi = mid; mid = (lo + hi) / 2.0; }
+        else { lo = mid; if (isinf(hi)) mid *= 2.0; else mid = (lo + hi) / 2.0; }
+        if (++it >= n_iter) state = 2;
+      }
+    }
+  }
+  double rs = 0.0;
+  if (q == 0 && row_ok) {
+    rs = s_rsum[rl];
     float sg = (float)mid;
     if (rho_i > 0.f) {
-      const float mean_i = (float)(rsum / k);
+      const float mean_i = (float)(rs / k);
       if (sg < kMinKDistScale * mean_i) sg = kMinKDistScale * mean_i;
     }
     sigma[(size_t)p * n + row] = sg;
     rho[(size_t)p * n + row] = rho_i;
-    atomicAdd(&dist_sum[p], rsum);
   }
+  rs = warp_sum_f64(rs);
+  if (lane == 0 && rs != 0.0) atomicAdd(&dist_sum[p], rs);
 }
 
 // general k (up to 256): one warp per row, list of KPL entries per lane.
@@ -662,8 +812,8 @@ extern "C" int tda_knn_smooth(const float* D, int n, int m, int batch, int k, fl
   const int kpl = (k + 31) / 32;
 #define TDA_KNN_LAUNCH(KPL) knn_smooth_kernel<KPL><<<grid, 256, 0, stream>>>(D, n, m, k, local_connectivity, bandwidth, n_iter, knn_idx, knn_dist, sigma, rho, dist_sum)
   if (k <= 16) {
-    dim3 gp((n + 7) / 8, batch);  // 4 warps x 2 rows per CTA
-    knn_smooth_pair_kernel<<<gp, 128, 0, stream>>>(D, n, m, k, local_connectivity, bandwidth, n_iter, knn_idx, knn_dist, sigma, rho, dist_sum);
+    dim3 gp((n + kBlkRows - 1) / kBlkRows, batch);  // 4 warps, 32 rows per CTA
+    knn_smooth_block_kernel<<<gp, kBlkWarps * 32, 0, stream>>>(D, n, m, k, local_connectivity, bandwidth, n_iter, knn_idx, knn_dist, sigma, rho, dist_sum);
   } else if (kpl == 1) TDA_KNN_LAUNCH(1);
   else if (kpl == 2) TDA_KNN_LAUNCH(2);
   else if (kpl <= 4) TDA_KNN_LAUNCH(4);

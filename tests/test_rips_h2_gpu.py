@@ -48,6 +48,33 @@ def test_h2_many_windows_far_buckets_match_oracle(monkeypatch, far_bytes):
         assert same_diagram(d[2], want[2]), (far_bytes, b, len(d[2]), len(want[2]))
 
 
+def test_c2_torus_600_matches_oracle_golden():
+    """Config C2 of BASELINE.json (noisy flat torus in 4096-d, raw distance matrix, maxdim=2) at n=600 against the CPU oracle's
+    diagrams (tests/golden/c2_torus_n600_dgms.npz, made by tests/golden/make_c2_golden.py).  The GPU distances come from the
+    3xTF32 tensor-core GEMM, the oracle's from float64, so the diagrams are compared by bottleneck distance: north_star's bound
+    is 1e-4 x diameter.  The tetrahedron key space spans 15 windows here: the far buckets run with their default sizes."""
+    import os, sys
+    from tda_multimodal_b200 import rips, workloads
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "shims"))
+    try:
+        from persim import bottleneck
+    finally:
+        sys.path.pop(0)
+    gold = np.load(os.path.join(root, "tests", "golden", "c2_torus_n600_dgms.npz"))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = rips.ripser(workloads.c2_torus(n=600), maxdim=2)["dgms"]
+    tol = 1e-4 * float(gold["diameter"])
+    for q, name in enumerate(("h0", "h1", "h2")):
+        assert len(got[q]) > 0
+        assert bottleneck(got[q], gold[name]) <= tol, (name, len(got[q]), len(gold[name]))
+    p2 = np.sort(got[2][:, 1] - got[2][:, 0])[::-1]
+    p1 = np.sort(got[1][:, 1] - got[1][:, 0])[::-1]
+    assert p2[0] > 10 * p2[1] and p1[1] > 3 * p1[2]          # the torus: one void, two long loops
+
+
 def test_h2_sphere_has_one_dominant_void_and_batches():
     import torch
     from tda_multimodal_b200 import rips
