@@ -27,8 +27,8 @@ if ROOT not in sys.path:
 METRIC = "umap_rips_h0h1_layers_per_sec"
 UNIT = "layers/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the round's `ncu --set full` capture of this command
-# (profiles/r01_final_ncu_full_summary.csv; 16 clouds of 2000 points per launch): static evidence, not measured by this run
-NCU_TRAFFIC_BYTES = {"rips_reduce": 1.05e9, "pdist_gemm": 3.16e9}
+# (profiles/r01b_ncu_full_summary.csv; 16 clouds of 2000 points per launch): static evidence, not measured by this run
+NCU_TRAFFIC_BYTES = {"rips_reduce": 1.09e9, "pdist_gemm": 3.0e9, "knn_smooth": 0.26e9}
 
 
 def parse():

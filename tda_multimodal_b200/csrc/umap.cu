@@ -11,6 +11,7 @@
 #include "launch_count.cuh"
 #include "../../include/tda_b200.h"
 #include <cmath>
+#include <cstdlib>
 
 namespace tda {
 namespace umap {
@@ -154,8 +155,6 @@ __device__ __forceinline__ void knn_stream_rows(const float* const (&drow)[ROWS]
 // lo/mid/hi follow the fp64 sequence.
 constexpr float kScreenBand = 1e-4f;
 constexpr int kBlkWarps = 4, kBlkRows = 32, kBlkRowsPerWarp = kBlkRows / kBlkWarps;
-constexpr int kBlkLoads = 16;                       // float4 per lane and chunk
-constexpr int kBlkChunk = 32 * 4 * kBlkLoads;       // 2048 columns
 constexpr int kBlkCand = 64;                        // candidate buffer per warp
 constexpr unsigned long long kKeyMax = ~0ull;
 
@@ -194,10 +193,12 @@ __device__ __forceinline__ T warp_merge_bitonic(T v, int lane) {   // v bitonic 
   return v;
 }
 
+template <int kBlkLoads>                            // 16-byte loads per lane and chunk: a chunk is 128 * kBlkLoads columns
 __global__ void __launch_bounds__(kBlkWarps * 32) knn_smooth_block_kernel(const float* __restrict__ D, int n, int m, int k, float local_connectivity,
                                                                             float bandwidth, int n_iter, int* __restrict__ knn_idx,
                                                                             float* __restrict__ knn_dist, float* __restrict__ sigma,
                                                                             float* __restrict__ rho, double* __restrict__ dist_sum) {
+  constexpr int kBlkChunk = 32 * 4 * kBlkLoads;
   __shared__ unsigned long long s_cand[kBlkWarps][kBlkCand];
   __shared__ uint32_t s_cnt[kBlkWarps];
   __shared__ float s_kd[kBlkRows][16];
@@ -222,20 +223,21 @@ __global__ void __launch_bounds__(kBlkWarps * 32) knn_smooth_block_kernel(const 
     __syncwarp();
     for (int c0 = 0; c0 < m && !overflow; c0 += kBlkChunk) {
       float4 v[kBlkLoads];
+      const float kPad = __int_as_float(0x7fc00000);   // columns past the end are NaN: fminf skips them and "<= tau" is false
       if (vec) {
 #pragma unroll
         for (int u = 0; u < kBlkLoads; ++u) {
           const int e = c0 + (u * 32 + lane) * 4;
-          v[u] = e < m ? __ldcs(reinterpret_cast<const float4*>(drow + e)) : make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+          v[u] = e < m ? __ldcs(reinterpret_cast<const float4*>(drow + e)) : make_float4(kPad, kPad, kPad, kPad);
         }
       } else {
 #pragma unroll
         for (int u = 0; u < kBlkLoads; ++u) {
           const int e = c0 + (u * 32 + lane) * 4;
-          v[u].x = e + 0 < m ? __ldcs(drow + e + 0) : INFINITY;
-          v[u].y = e + 1 < m ? __ldcs(drow + e + 1) : INFINITY;
-          v[u].z = e + 2 < m ? __ldcs(drow + e + 2) : INFINITY;
-          v[u].w = e + 3 < m ? __ldcs(drow + e + 3) : INFINITY;
+          v[u].x = e + 0 < m ? __ldcs(drow + e + 0) : kPad;
+          v[u].y = e + 1 < m ? __ldcs(drow + e + 1) : kPad;
+          v[u].z = e + 2 < m ? __ldcs(drow + e + 2) : kPad;
+          v[u].w = e + 3 < m ? __ldcs(drow + e + 3) : kPad;
         }
       }
       float lmin = INFINITY;
@@ -250,7 +252,7 @@ __global__ void __launch_bounds__(kBlkWarps * 32) knn_smooth_block_kernel(const 
         const float dd[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          if (dd[c] <= tau && e + c < m) {
+          if (dd[c] <= tau) {
             const uint32_t pos = atomicAdd(&s_cnt[warp], 1u);
             if (pos < (uint32_t)kBlkCand) s_cand[warp][pos] = knn_key(dd[c], e + c);
           }
@@ -813,7 +815,9 @@ extern "C" int tda_knn_smooth(const float* D, int n, int m, int batch, int k, fl
 #define TDA_KNN_LAUNCH(KPL) knn_smooth_kernel<KPL><<<grid, 256, 0, stream>>>(D, n, m, k, local_connectivity, bandwidth, n_iter, knn_idx, knn_dist, sigma, rho, dist_sum)
   if (k <= 16) {
     dim3 gp((n + kBlkRows - 1) / kBlkRows, batch);  // 4 warps, 32 rows per CTA
-    knn_smooth_block_kernel<<<gp, kBlkWarps * 32, 0, stream>>>(D, n, m, k, local_connectivity, bandwidth, n_iter, knn_idx, knn_dist, sigma, rho, dist_sum);
+    static const int loads = [] { const char* e = getenv("TDA_KNN_LOADS"); return e ? atoi(e) : 8; }();
+    if (loads == 8) knn_smooth_block_kernel<8><<<gp, kBlkWarps * 32, 0, stream>>>(D, n, m, k, local_connectivity, bandwidth, n_iter, knn_idx, knn_dist, sigma, rho, dist_sum);
+    else knn_smooth_block_kernel<16><<<gp, kBlkWarps * 32, 0, stream>>>(D, n, m, k, local_connectivity, bandwidth, n_iter, knn_idx, knn_dist, sigma, rho, dist_sum);
   } else if (kpl == 1) TDA_KNN_LAUNCH(1);
   else if (kpl == 2) TDA_KNN_LAUNCH(2);
   else if (kpl <= 4) TDA_KNN_LAUNCH(4);
