@@ -637,6 +637,7 @@ __global__ void unpack4_kernel(const float4* __restrict__ Y4, float* __restrict_
 // queues the ones that fire (ballot compaction into shared memory), then works through the queue with full warps.
 constexpr int kSgdSlotsPerLane = 8;
 constexpr int kSgdWarps = 8;
+constexpr int kSgdNegBatch = 6;   // negative_sample_rate 5 owes 4..6 samples per firing
 __global__ void __launch_bounds__(kSgdWarps * 32) sgd_epoch_kernel_v4(float4* __restrict__ Yh, float4* __restrict__ Yt, const int* __restrict__ head,
                                                                       const int* __restrict__ tail, const float* __restrict__ eps_arr, int slots,
                                                                       int n_head, int n_tail, int epoch, float a, float b, float gamma, float alpha,
@@ -669,6 +670,23 @@ __global__ void __launch_bounds__(kSgdWarps * 32) sgd_epoch_kernel_v4(float4* __
     const float eps = eps_arr[(size_t)p * slots + e];
     const int q = (int)floorf((float)epoch / eps);
     const int j = head[(size_t)p * slots + e], kk = tail[(size_t)p * slots + e];
+    // negatives owed since the previous firing
+    const float epsn = eps / nsr;
+    int tot = (int)floorf((float)epoch / epsn) - 1;
+    if (q > 1) {
+      const int prev = (int)ceilf((float)(q - 1) * eps);
+      tot -= (int)floorf((float)prev / epsn) - 1;
+    }
+    // The negative samples' addresses depend on (slot, epoch, s) only: the first kSgdNegBatch of them are requested here,
+    // together with the two endpoints, instead of one L2 round trip per sample inside the dependent update chain.
+    float4 n4[kSgdNegBatch];
+#pragma unroll
+    for (int u = 0; u < kSgdNegBatch; ++u) {
+      if (u < tot) {
+        const uint32_t r = mix32(seed ^ ((uint64_t)p << 52) ^ ((uint64_t)e << 20) ^ ((uint64_t)epoch << 4) ^ (uint64_t)u ^ ((uint64_t)u << 40));
+        n4[u] = __ldcg(Yt + (size_t)p * n_tail + (int)(r % (uint32_t)n_tail));
+      }
+    }
     float4* yh = Yh + (size_t)p * n_head + j;
     float4* yt = Yt + (size_t)p * n_tail + kk;
     const float4 c4 = __ldcg(yh), o4 = __ldcg(yt);
@@ -689,30 +707,28 @@ __global__ void __launch_bounds__(kSgdWarps * 32) sgd_epoch_kernel_v4(float4* __
       cur[d] += gd; delta[d] += gd; dt[d] = -gd;
     }
     if (move_other) atomicAdd(yt, make_float4(dt[0], dt[1], dt[2], 0.f));
-    const float epsn = eps / nsr;
-    int tot = (int)floorf((float)epoch / epsn) - 1;
-    if (q > 1) {
-      const int prev = (int)ceilf((float)(q - 1) * eps);
-      tot -= (int)floorf((float)prev / epsn) - 1;
-    }
-    for (int s = 0; s < tot; ++s) {
-      const uint32_t r = mix32(seed ^ ((uint64_t)p << 52) ^ ((uint64_t)e << 20) ^ ((uint64_t)epoch << 4) ^ (uint64_t)s ^ ((uint64_t)s << 40));
-      const int kn = (int)(r % (uint32_t)n_tail);
-      const float4 n4 = __ldcg(Yt + (size_t)p * n_tail + kn);
-      const float on[3] = {n4.x, n4.y, n4.z};
+    auto repel = [&](const float4& nn) {   // (a negative at zero distance gives no update, whichever vertex it is)
+      const float on[3] = {nn.x, nn.y, nn.z};
       float dn = 0.f;
 #pragma unroll
       for (int d = 0; d < 3; ++d) { const float t = cur[d] - on[d]; dn += t * t; }
-      float gn = 0.f;
-      if (dn > 0.f) gn = (2.f * gamma * b) / ((0.001f + dn) * (a * __powf(dn, b) + 1.f));
-      else if (move_other && j == kn) continue;
-      if (gn > 0.f) {
+      if (dn > 0.f) {
+        const float gn = (2.f * gamma * b) / ((0.001f + dn) * (a * __powf(dn, b) + 1.f));
+        if (gn > 0.f) {
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          const float gd = clip4(gn * (cur[d] - on[d])) * alpha;
-          cur[d] += gd; delta[d] += gd;
+          for (int d = 0; d < 3; ++d) {
+            const float gd = clip4(gn * (cur[d] - on[d])) * alpha;
+            cur[d] += gd; delta[d] += gd;
+          }
         }
       }
+    };
+#pragma unroll
+    for (int u = 0; u < kSgdNegBatch; ++u)
+      if (u < tot) repel(n4[u]);
+    for (int sidx = kSgdNegBatch; sidx < tot; ++sidx) {   // (only with a larger negative_sample_rate)
+      const uint32_t r = mix32(seed ^ ((uint64_t)p << 52) ^ ((uint64_t)e << 20) ^ ((uint64_t)epoch << 4) ^ (uint64_t)sidx ^ ((uint64_t)sidx << 40));
+      repel(__ldcg(Yt + (size_t)p * n_tail + (int)(r % (uint32_t)n_tail)));
     }
     atomicAdd(yh, make_float4(delta[0], delta[1], delta[2], 0.f));
   }
