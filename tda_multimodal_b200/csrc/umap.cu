@@ -734,6 +734,112 @@ __global__ void __launch_bounds__(kSgdWarps * 32) sgd_epoch_kernel_v4(float4* __
   }
 }
 
+// EXPERIMENT (off unless TDA_SGD_CLOUD=1): one CTA per cloud, the whole optimisation in ONE launch -- the embedding (16 B
+// per point) lives in shared memory, updates are shared-memory float atomics, epochs are separated by __syncthreads(), and
+// nothing but the read-only slot table (eps, head, tail) leaves the SM.  Same schedule, RNG keys and update rule as the
+// per-epoch kernel (tests/test_umap_gpu.py: trustworthiness 0.99315 vs 0.99313 on 8 clouds).  Measured on the C3 sweep: 64 ms
+// per 16 clouds x 500 epochs against 15.5 ms for the per-epoch kernel -- a cloud fires ~21 k edges per epoch at ~300
+// instructions each (six __powf), which is ~50 us of issue time on ONE SM, while the per-epoch kernel spreads the same work
+// over all 148 SMs and pays L2 atomics instead (shared-memory float add is a CAS loop, ATOMS.CAST.SPIN, on sm_100a).
+// The design that would win is a cluster of 8 CTAs per cloud with the embedding in distributed shared memory.
+constexpr int kSgdCloudThreads = 1024;
+constexpr int kSgdCloudWarps = kSgdCloudThreads / 32;
+constexpr int kSgdCloudMinBatch = 8;
+constexpr size_t kSgdCloudMaxBytes = 160 * 1024;
+__global__ void __launch_bounds__(kSgdCloudThreads, 1) sgd_cloud_kernel(float4* __restrict__ Y4, const int* __restrict__ head, const int* __restrict__ tail,
+                                                                        const float* __restrict__ eps_arr, int slots, int n, int n_epochs, float a,
+                                                                        float b, float gamma, float alpha0, float nsr, uint64_t seed) {
+  extern __shared__ float4 s_y[];                       // [n] the cloud's embedding
+  __shared__ int s_queue[kSgdCloudWarps][kSgdSlotsPerLane * 32];
+  const int p = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4* Yg = Y4 + (size_t)p * n;
+  for (int i = threadIdx.x; i < n; i += kSgdCloudThreads) s_y[i] = Yg[i];
+  __syncthreads();
+  const float* ep_p = eps_arr + (size_t)p * slots;
+  const int* hd_p = head + (size_t)p * slots;
+  const int* tl_p = tail + (size_t)p * slots;
+  int* queue = s_queue[warp];
+  constexpr int kChunk = kSgdSlotsPerLane * 32;
+  for (int epoch = 0; epoch < n_epochs; ++epoch) {
+    const float alpha = epoch == 0 ? alpha0 : alpha0 * (1.f - (float)(epoch - 1) / (float)n_epochs);
+    for (int base = warp * kChunk; base < slots; base += kSgdCloudWarps * kChunk) {
+      int count = 0;
+#pragma unroll
+      for (int i = 0; i < kSgdSlotsPerLane; ++i) {
+        const int e = base + i * 32 + lane;
+        bool fire = false;
+        if (e < slots) {
+          const float eps = __ldg(&ep_p[e]);
+          if (eps > 0.f) {
+            const int q = (int)floorf((float)epoch / eps);
+            fire = !(q < 1 || q <= (int)floorf((float)(epoch - 1) / eps));
+          }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, fire);
+        if (fire) queue[count + __popc(bal & ((1u << lane) - 1))] = e;
+        count += __popc(bal);
+      }
+      __syncwarp();
+      for (int qi = lane; qi < count; qi += 32) {
+        const int e = queue[qi];
+        const float eps = __ldg(&ep_p[e]);
+        const int q = (int)floorf((float)epoch / eps);
+        const int j = __ldg(&hd_p[e]), kk = __ldg(&tl_p[e]);
+        const float epsn = eps / nsr;
+        int tot = (int)floorf((float)epoch / epsn) - 1;
+        if (q > 1) {
+          const int prev = (int)ceilf((float)(q - 1) * eps);
+          tot -= (int)floorf((float)prev / epsn) - 1;
+        }
+        const float4 c4 = s_y[j], o4 = s_y[kk];
+        float cur[3] = {c4.x, c4.y, c4.z};
+        const float oth[3] = {o4.x, o4.y, o4.z};
+        float delta[3] = {0.f, 0.f, 0.f};
+        float d2 = 0.f;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { const float t = cur[d] - oth[d]; d2 += t * t; }
+        float g = 0.f;
+        if (d2 > 0.f) {
+          const float pw = __powf(d2, b - 1.f);
+          g = (-2.f * a * b * pw) / (a * pw * d2 + 1.f);
+        }
+        float* yt = reinterpret_cast<float*>(&s_y[kk]);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const float gd = clip4(g * (cur[d] - oth[d])) * alpha;
+          cur[d] += gd; delta[d] += gd;
+          atomicAdd(&yt[d], -gd);
+        }
+        for (int sidx = 0; sidx < tot; ++sidx) {
+          const uint32_t r = mix32(seed ^ ((uint64_t)p << 52) ^ ((uint64_t)e << 20) ^ ((uint64_t)epoch << 4) ^ (uint64_t)sidx ^ ((uint64_t)sidx << 40));
+          const float4 nn = s_y[(int)(r % (uint32_t)n)];
+          const float on[3] = {nn.x, nn.y, nn.z};
+          float dn = 0.f;
+#pragma unroll
+          for (int d = 0; d < 3; ++d) { const float t = cur[d] - on[d]; dn += t * t; }
+          if (dn > 0.f) {
+            const float gn = (2.f * gamma * b) / ((0.001f + dn) * (a * __powf(dn, b) + 1.f));
+            if (gn > 0.f) {
+#pragma unroll
+              for (int d = 0; d < 3; ++d) {
+                const float gd = clip4(gn * (cur[d] - on[d])) * alpha;
+                cur[d] += gd; delta[d] += gd;
+              }
+            }
+          }
+        }
+        float* yh = reinterpret_cast<float*>(&s_y[j]);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) atomicAdd(&yh[d], delta[d]);
+      }
+      __syncwarp();   // the queue is reused by the next chunk
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < n; i += kSgdCloudThreads) Yg[i] = s_y[i];
+}
+
 // ------------------------------------------------------------------------------------------------
 // initialisation helpers
 __device__ __forceinline__ float u01(uint64_t key) { return ((float)(mix32(key) >> 8) + 0.5f) * (1.f / 16777216.f); }
@@ -878,6 +984,19 @@ extern "C" int tda_umap_sgd(float* Y, const float* Y_other, const int32_t* head,
     float4* Yh4 = (float4*)ws;
     float4* Yt4 = move_other ? Yh4 : Yh4 + np_h;
     pack4_kernel<<<(unsigned)((np_h + 255) / 256), 256, 0, stream>>>(Y, Yh4, np_h);
+    // TDA_SGD_CLOUD=1: one CTA per cloud with the embedding in shared memory, all epochs in one launch (see sgd_cloud_kernel)
+    const char* cloud_env = getenv("TDA_SGD_CLOUD");
+    const bool cloud_mode = cloud_env && cloud_env[0] == '1';
+    const size_t cloud_bytes = sizeof(float4) * (size_t)n_head;
+    if (cloud_mode && move_other && n_head == n_tail && batch >= kSgdCloudMinBatch && cloud_bytes <= kSgdCloudMaxBytes) {
+      TDA_CUDA_CHECK(cudaFuncSetAttribute(sgd_cloud_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cloud_bytes));
+      sgd_cloud_kernel<<<batch, kSgdCloudThreads, cloud_bytes, stream>>>(Yh4, head, tail, eps, slots, n_head, n_epochs, a, b, gamma, alpha0,
+                                                                         negative_sample_rate, seed);
+      unpack4_kernel<<<(unsigned)((np_h + 255) / 256), 256, 0, stream>>>(Yh4, Y, np_h);
+      count_launch(3);
+      TDA_LAUNCH_CHECK();
+      return TDA_OK;
+    }
     if (!move_other) pack4_kernel<<<(unsigned)((np_t + 255) / 256), 256, 0, stream>>>(Y_other, Yt4, np_t);
     for (int ep = 0; ep < n_epochs; ++ep) {
       const float alpha = ep == 0 ? alpha0 : alpha0 * (1.f - (float)(ep - 1) / (float)n_epochs);

@@ -202,6 +202,28 @@ def test_fit_transform_trustworthiness_vs_oracle(torch_cuda, kind, n, k):
     assert um.graph_.shape == (n, n) and um._sigmas.shape == (n,) and um.embedding_ is Yg
 
 
+def test_sgd_cloud_kernel_matches_epoch_kernel(torch_cuda, monkeypatch):
+    """The one-launch SGD (one CTA per cloud, embedding in shared memory, TDA_SGD_CLOUD=1) against the launch-per-epoch kernel
+    on a batch of 8 clouds: same schedule and RNG keys, only the order of the float updates differs -- both embeddings must be
+    finite, inside the clip box, equally trustworthy, and different from their common initialisation."""
+    torch = torch_cuda
+    from tda_multimodal_b200 import umap_
+    rng = np.random.default_rng(91)
+    X = np.stack([activations(400, 128, rng, kind="torus" if i % 2 else "clusters") for i in range(8)])
+    Xd = torch.from_numpy(X).cuda()
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("TDA_SGD_CLOUD", mode)
+        Y = umap_.umap_fit_batch(Xd, n_neighbors=15, n_components=3, metric="cosine", random_state=42).cpu().numpy()
+        assert Y.shape == (8, 400, 3) and np.isfinite(Y).all() and np.abs(Y).max() < 100
+        out[mode] = Y
+    t0 = [_trust(X[i], out["0"][i], "cosine") for i in range(8)]
+    t1 = [_trust(X[i], out["1"][i], "cosine") for i in range(8)]
+    assert min(t1) > 0.8 and np.mean(t1) >= np.mean(t0) - 0.02, (t0, t1)
+    rel = np.linalg.norm(out["0"] - out["1"], axis=2).mean() / np.linalg.norm(out["0"] - out["0"].mean(1, keepdims=True), axis=2).mean()
+    print("mean point displacement between the two kernels / cloud radius:", rel, "trust", np.mean(t0), np.mean(t1))
+
+
 def test_downstream_diagrams_clusters(torch_cuda):
     """Downstream-diagram parity (north_star: UMAP is compared by trustworthiness and by the diagrams that follow):
     5 well separated clusters in 512-d -> UMAP 3-D -> Rips.  Both implementations must see exactly 4 dominant H0
