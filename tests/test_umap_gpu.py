@@ -52,7 +52,8 @@ def test_knn_smooth_matches_oracle(torch_cuda, n, k, metric):
     assert np.all((np.abs(psum - np.log2(k)) < 1e-3) | floored)
 
 
-@pytest.mark.parametrize("rows,cols,k,batch", [(301, 500, 15, 3), (64, 2000, 15, 2), (77, 333, 8, 2), (50, 402, 20, 2)])
+@pytest.mark.parametrize("rows,cols,k,batch", [(301, 500, 15, 3), (64, 2000, 15, 2), (77, 333, 8, 2), (50, 402, 20, 2),
+                                               (40, 5000, 15, 1), (33, 3001, 10, 2), (20, 20000, 16, 1)])
 def test_knn_smooth_batched_rectangular(torch_cuda, rows, cols, k, batch):
     """Row pairs / odd row counts / vector and scalar loads / several problems per launch (the transform and row-block
     callers pass rectangular blocks): indices, distances, rho exact; sigma equal to a float64 host replay of the bisection."""
