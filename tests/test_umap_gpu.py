@@ -65,7 +65,7 @@ def test_knn_smooth_batched_rectangular(torch_cuda, rows, cols, k, batch):
     dmat[:, :, 0][:, ::5] = 0.0          # some zero distances (rho skips them)
     dmat[0, 3, :] = np.inf               # a row with fewer than k finite entries
     dmat[0, 3, 5:9] = [0.5, 0.25, 0.75, 0.125]
-    dmat[1, 7, 10:14] = 0.3              # ties: smaller column first
+    dmat[batch - 1, 7, 10:14] = 0.3      # ties: smaller column first
     idx, dist, sigma, rho = umap_.knn_smooth(torch.from_numpy(dmat).cuda(), k)
     for b in range(batch):
         oidx, odist = uo.exact_knn(dmat[b], k)
