@@ -41,6 +41,7 @@ def _lib():
         lib.rips_oracle_thresh.restype = ctypes.c_float
         lib.rips_oracle_thresh.argtypes = [ctypes.c_void_p]
         lib.rips_oracle_stats.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        lib.rips_oracle_dep_stats.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         lib.rips_oracle_free.argtypes = [ctypes.c_void_p]
         _LIB = lib
     return _LIB
@@ -91,7 +92,11 @@ def rips_dm(dm, maxdim=1, thresh=np.inf, with_simplices=False, with_stats=False)
             simp.append(s)
             st = np.zeros(7, dtype=np.int64)
             lib.rips_oracle_stats(h, q, st.ctypes.data)
-            stats.append(dict(zip(["columns", "emergent", "reduced", "additions", "pops", "max_v", "cofacets"], st.tolist())))
+            rec = dict(zip(["columns", "emergent", "reduced", "additions", "pops", "max_v", "cofacets"], st.tolist()))
+            dp = np.zeros(3, dtype=np.int64)
+            lib.rips_oracle_dep_stats(h, q, dp.ctypes.data)
+            rec.update(dict(zip(["dep_total_steps", "dep_critical_steps", "dep_depth"], dp.tolist())))
+            stats.append(rec)
         out = {"dgms": dgms, "num_edges": int(lib.rips_oracle_num_edges(h)), "thresh": float(lib.rips_oracle_thresh(h))}
         if with_simplices:
             out["simplices"] = simp

@@ -65,6 +65,9 @@ struct Binom {
 
 struct Stats {
   int64_t columns[3], emergent[3], reduced[3], additions[3], pops[3], max_v[3], cofacets[3];
+  // dependency structure of the reduced (non-emergent) columns: cost of a column = its pivot steps (additions + 1); a column
+  // depends on every reduced column it adds.  total = sum of costs, critical = heaviest dependency chain, depth = its length.
+  int64_t dep_total[3], dep_critical[3], dep_depth[3];
 };
 
 struct Rips {
@@ -234,8 +237,10 @@ struct Rips {
     std::vector<std::vector<idx_t>> V(columns.size());  // reduction columns (excluding the column itself)
     st.columns[dim] = (int64_t)columns.size();
     std::vector<Simplex> buf;
+    std::vector<int64_t> chain(columns.size(), 0), depth(columns.size(), 0);   // 0 = emergent column (no work to wait for)
     for (size_t j = 0; j < columns.size(); ++j) {
       const Simplex col = columns[j];
+      int64_t steps = 1, dep_chain = 0, dep_depth = 0;
       Heap work;           // working coboundary
       std::vector<idx_t> vcol;  // working reduction column entries (with multiplicity)
       Simplex pivot{0, -1};
@@ -271,6 +276,9 @@ struct Rips {
         if (it != pivot_col.end()) {
           size_t a = (size_t)it->second;
           ++st.additions[dim];
+          ++steps;
+          if (chain[a] > dep_chain) dep_chain = chain[a];
+          if (depth[a] > dep_depth) dep_depth = depth[a];
           // add column a: its own coboundary plus the coboundaries of its reduction column
           auto add_simplex = [&](idx_t sidx) {
             vcol.push_back(sidx);
@@ -301,6 +309,13 @@ struct Rips {
           a = b;
         }
         st.max_v[dim] = std::max<int64_t>(st.max_v[dim], (int64_t)V[j].size());
+        if (!emergent) {
+          chain[j] = steps + dep_chain;
+          depth[j] = 1 + dep_depth;
+          st.dep_total[dim] += steps;
+          st.dep_critical[dim] = std::max(st.dep_critical[dim], chain[j]);
+          st.dep_depth[dim] = std::max(st.dep_depth[dim], depth[j]);
+        }
         break;
       }
     }
@@ -332,6 +347,11 @@ void rips_oracle_stats(void* h, int dim, int64_t* out) {
   Rips* r = (Rips*)h;
   out[0] = r->st.columns[dim]; out[1] = r->st.emergent[dim]; out[2] = r->st.reduced[dim];
   out[3] = r->st.additions[dim]; out[4] = r->st.pops[dim]; out[5] = r->st.max_v[dim]; out[6] = r->st.cofacets[dim];
+}
+// dependency statistics of the reduced columns of one dimension: total pivot steps, heaviest dependency chain, its length
+void rips_oracle_dep_stats(void* h, int dim, int64_t* out) {
+  Rips* r = (Rips*)h;
+  out[0] = r->st.dep_total[dim]; out[1] = r->st.dep_critical[dim]; out[2] = r->st.dep_depth[dim];
 }
 void rips_oracle_free(void* h) { delete (Rips*)h; }
 
