@@ -135,3 +135,31 @@ def ripser(X, maxdim=1, thresh=np.inf, coeff=2, distance_matrix=False, do_cocycl
     res.update({"cocycles": [[] for _ in range(maxdim + 1)], "dperm2all": dperm2all,
                 "idx_perm": idx_perm, "r_cover": r_cover})
     return res
+
+
+_MODEL = None
+
+
+def model_h1(dm):
+    """H1 diagram of a float32 distance matrix by the "propagate, then verify" model (oracle/rips_propagate_model.cpp): a CPU
+    study of the next GPU reducer, checked against `rips_dm` in tests/test_oracle_golden.py.  Returns (pairs [k,2] float64 in
+    processing order, stats dict)."""
+    global _MODEL
+    if _MODEL is None:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "librips_model.so")
+        if not os.path.exists(path):
+            subprocess.check_call(["make", "-C", os.path.dirname(path)])
+        lib = ctypes.CDLL(path)
+        lib.rips_model_h1.restype = ctypes.c_int64
+        lib.rips_model_h1.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+        _MODEL = lib
+    dm = np.ascontiguousarray(dm, dtype=np.float32)
+    n = dm.shape[0]
+    cap = max(16, n * n // 4)
+    out = np.zeros((cap, 2), dtype=np.float64)
+    st = np.zeros(10, dtype=np.int64)
+    k = int(_MODEL.rips_model_h1(dm.ctypes.data, n, out.ctypes.data, cap, st.ctypes.data))
+    if k < 0:
+        raise RuntimeError("model_h1: pair buffer too small")
+    names = ["residual_columns", "apparent_edges", "events", "propagated_flips", "heavy_rows_verified", "max_v", "passes", "apparent_graph_depth", "incremental_flips", "heavy_rows_in_v"]
+    return out[:k].copy(), dict(zip(names, st.tolist()))

@@ -1,0 +1,173 @@
+// oracle/rips_propagate_model.cpp -- TEST INFRASTRUCTURE ONLY: a CPU model of a "propagate, then verify" formulation of the
+// residual H1 reduction, written to check the idea against the ripser restatement (rips_oracle.cpp) before it becomes a
+// kernel.  Never on the product path.
+//
+// Setting (as in csrc/rips.cu): edges in ripser's filtration order get ranks 0..T-1; a non-MST edge M=(c,d) whose lune
+// {w : rank(c,w) < M, rank(d,w) < M} is not empty is in an apparent pair with the triangle (M, apex(M)), apex = the largest
+// lune vertex; the other non-MST edges are the residual columns, reduced in descending rank order.  Triangle keys
+// (M, w) ascend with M and, inside a row M, with descending w.
+//
+// Observation the model rests on: when the reduction of a column reaches row M of an apparent edge, the entry at the apex
+// decides whether column M is added, and after that step x_M = x_(c,apex) ^ x_(d,apex) whatever x_M was before (x_e = 1 iff
+// edge e is in the reduction column V).  So the tens of thousands of apparent-pair additions of a long column are a forward
+// substitution along a STATIC graph (two parents per apparent edge) whose depth is ~30 on the C3 clouds, not a chain of
+// dependent pivots.  The model therefore repeats, per column:
+//   propagate  x_M = x_pa(M) ^ x_pb(M) for every apparent edge above the cursor (speculative view),
+//   verify     the rows above the cursor in order: r(M) = { w in lune(M) : x_M ^ x_(c,w) ^ x_(d,w) = 1 }; the first non-empty
+//              row holds the next NON-apparent pivot (M, max r(M)),
+//   event      pivot owned by an earlier column j -> V ^= V_j, cursor = M, again;  unowned -> death;  no row -> essential.
+// Everything below the cursor is final (the coboundary of V_j vanishes below its pivot).
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <numeric>
+#include <unordered_map>
+#include <vector>
+
+namespace {
+struct Model {
+  int n; int64_t T;
+  std::vector<int> R;                 // [n*n] rank, INT_MAX above the threshold / on the diagonal
+  std::vector<int> ea, eb;            // endpoints by rank (ea > eb)
+  std::vector<float> len;             // length by rank
+  std::vector<int> apex, pa, pb;      // per rank: apex (-1 none, -2 MST), parents of an apparent edge
+};
+}  // namespace
+
+extern "C" {
+
+// dist: n*n float32, symmetric, zero diagonal.  pairs_out: [cap,2] doubles (birth, death; death = inf for essential classes),
+// in processing order, zero-persistence pairs dropped (as ripser does).  stats: [10] int64: residual columns, apparent edges,
+// events (additions of reduced columns), propagated flips (every pass recomputes the view from the cursor), heavy rows verified,
+// largest |V|, propagate passes, depth of the apparent graph, flips an INCREMENTAL propagation would do (edges whose view
+// value differs from the previous pass of the same column), rows verified whose own edge is in V.
+// Returns the number of pairs (or -1 if cap is too small).
+int64_t rips_model_h1(const float* dist, int n, double* pairs_out, int64_t cap, int64_t* stats) {
+  Model m; m.n = n;
+  const int64_t E = (int64_t)n * (n - 1) / 2;
+  std::vector<float> elen(E); std::vector<int> ia(E), ib(E);
+  { int64_t q = 0; for (int i = 1; i < n; ++i) for (int j = 0; j < i; ++j) { elen[q] = dist[(size_t)i * n + j]; ia[q] = i; ib[q] = j; ++q; } }
+  float thr = INFINITY;
+  for (int i = 0; i < n; ++i) { float mx = 0.f; for (int j = 0; j < n; ++j) if (j != i) mx = std::max(mx, dist[(size_t)i * n + j]); thr = std::min(thr, mx); }
+  std::vector<int64_t> ord(E); std::iota(ord.begin(), ord.end(), 0);
+  std::sort(ord.begin(), ord.end(), [&](int64_t x, int64_t y) { return elen[x] < elen[y] || (elen[x] == elen[y] && x > y); });
+  int64_t T = 0; while (T < E && elen[ord[T]] <= thr) ++T;
+  m.T = T;
+  m.R.assign((size_t)n * n, 0x7fffffff);
+  m.ea.resize(T); m.eb.resize(T); m.len.resize(T);
+  for (int64_t r = 0; r < T; ++r) { const int a = ia[ord[r]], b = ib[ord[r]]; m.ea[r] = a; m.eb[r] = b; m.len[r] = elen[ord[r]]; m.R[(size_t)a * n + b] = m.R[(size_t)b * n + a] = (int)r; }
+  // MST, apex, parents, depth of the apparent graph
+  std::vector<int> uf(n); std::iota(uf.begin(), uf.end(), 0);
+  auto find = [&](int x) { while (uf[x] != x) { uf[x] = uf[uf[x]]; x = uf[x]; } return x; };
+  m.apex.assign(T, -1); m.pa.assign(T, -1); m.pb.assign(T, -1);
+  std::vector<int> depth(T, 0); int maxdepth = 0; int64_t n_app = 0;
+  std::vector<int64_t> residual;
+  for (int64_t r = 0; r < T; ++r) {
+    const int a = m.ea[r], b = m.eb[r];
+    const int ra = find(a), rb = find(b);
+    if (ra != rb) { uf[ra] = rb; m.apex[r] = -2; continue; }
+    const int* Ra = &m.R[(size_t)a * n]; const int* Rb = &m.R[(size_t)b * n];
+    int ap = -1; for (int w = n - 1; w >= 0; --w) if (Ra[w] < r && Rb[w] < r) { ap = w; break; }
+    m.apex[r] = ap;
+    if (ap < 0) { residual.push_back(r); continue; }
+    ++n_app; m.pa[r] = Ra[ap]; m.pb[r] = Rb[ap];
+    depth[r] = 1 + std::max(depth[m.pa[r]], depth[m.pb[r]]); maxdepth = std::max(maxdepth, depth[r]);
+  }
+  const int W = (n + 63) / 64;
+  std::vector<uint8_t> xr(T, 0), xs(T, 0);
+  std::vector<uint64_t> X((size_t)n * W, 0), lune(W);
+  std::vector<uint8_t> touched(n, 0);
+  std::unordered_map<int64_t, int> owner;              // pivot key -> index into Vs
+  std::vector<std::vector<int>> Vs;
+  int64_t n_pairs = 0, events = 0, flips = 0, heavy = 0, maxv = 0, passes = 0, delta_flips = 0, heavy_in_v = 0;
+  std::vector<uint8_t> xprev(T, 0);
+  std::vector<int64_t> prev_list;
+  auto toggle_view = [&](int64_t e) {                  // xs[e] ^= 1 with the vertex bit matrix kept in step
+    xs[e] ^= 1; const int a = m.ea[e], b = m.eb[e];
+    X[(size_t)a * W + (b >> 6)] ^= 1ull << (b & 63); X[(size_t)b * W + (a >> 6)] ^= 1ull << (a & 63);
+    touched[a] = touched[b] = 1;
+  };
+  for (int64_t ci = (int64_t)residual.size() - 1; ci >= 0; --ci) {
+    const int64_t b = residual[ci];
+    std::vector<int64_t> real_set;                     // edges with xr = 1 (for the clean-up)
+    auto toggle_real = [&](int64_t e) { xr[e] ^= 1; if (xr[e]) real_set.push_back(e); };
+    toggle_real(b);
+    int64_t M0 = b; int w_last = n;                    // rows <= M0 settled; in row M0 only vertices below w_last remain
+    std::vector<int64_t> view_set;                     // edges with xs = 1 at some point (for the clean-up)
+    bool essential = false; int64_t pivM = -1; int pivw = -1;
+    for (;;) {
+      // ---- propagate: the speculative view above the cursor
+      for (int64_t e : view_set) if (xs[e]) toggle_view(e);
+      view_set.clear();
+      std::fill(touched.begin(), touched.end(), 0);
+      ++passes;
+      for (int64_t e : real_set) if (xr[e] && !xs[e]) { toggle_view(e); view_set.push_back(e); }
+      for (int64_t M = M0 + 1; M < T; ++M) {
+        if (m.apex[M] < 0) continue;
+        const uint8_t want = xs[m.pa[M]] ^ xs[m.pb[M]];
+        if (want != xs[M]) { toggle_view(M); view_set.push_back(M); ++flips; }
+      }
+      {  // what an incremental propagation would have touched: the symmetric difference with the previous pass
+        for (int64_t e : view_set) if (xs[e] != xprev[e]) { ++delta_flips; xprev[e] = xs[e]; }
+        for (int64_t e : prev_list) if (xs[e] != xprev[e]) { ++delta_flips; xprev[e] = xs[e]; }
+        prev_list = view_set;
+      }
+      // ---- verify rows in order
+      pivM = -1;
+      for (int64_t M = M0; M < T && pivM < 0; ++M) {
+        if (m.apex[M] == -2) continue;                 // MST edge: empty lune
+        const int c = m.ea[M], d = m.eb[M];
+        if (!touched[c] && !touched[d]) continue;
+        ++heavy;
+        heavy_in_v += xs[M];
+        const int* Rc = &m.R[(size_t)c * n]; const int* Rd = &m.R[(size_t)d * n];
+        const int wtop = M == M0 ? w_last - 1 : n - 1;
+        for (int w = wtop; w >= 0; --w) {
+          if (!(Rc[w] < M && Rd[w] < M)) continue;
+          const int bit = (int)xs[M] ^ (int)((X[(size_t)c * W + (w >> 6)] >> (w & 63)) & 1) ^ (int)((X[(size_t)d * W + (w >> 6)] >> (w & 63)) & 1);
+          if (bit) { pivM = M; pivw = w; break; }
+        }
+      }
+      if (pivM < 0) { essential = true; break; }
+      // rows up to pivM are settled: the view becomes real there
+      for (int64_t e : view_set) if (e <= pivM && xs[e] != xr[e]) toggle_real(e);
+      const int64_t key = pivM * (int64_t)n + (n - 1 - pivw);
+      auto it = owner.find(key);
+      if (it == owner.end()) break;                    // death
+      ++events;
+      for (int e : Vs[it->second]) toggle_real(e);
+      M0 = pivM; w_last = pivw;
+    }
+    // V of this column = the real set
+    std::vector<int> V;
+    for (int64_t e : real_set) if (xr[e]) { V.push_back((int)e); xr[e] = 0; }
+    std::sort(V.begin(), V.end()); V.erase(std::unique(V.begin(), V.end()), V.end());
+    maxv = std::max<int64_t>(maxv, (int64_t)V.size());
+    for (int64_t e : view_set) if (xs[e]) toggle_view(e);
+    for (int64_t e : real_set) if (xs[e]) toggle_view(e);
+    for (int64_t e : prev_list) xprev[e] = 0;
+    for (int64_t e : view_set) xprev[e] = 0;
+    prev_list.clear();
+    const float birth = m.len[b];
+    if (essential) {
+      if (n_pairs >= cap) return -1;
+      pairs_out[2 * n_pairs] = birth; pairs_out[2 * n_pairs + 1] = INFINITY; ++n_pairs;
+    } else {
+      const float death = m.len[pivM];
+      owner.emplace(pivM * (int64_t)n + (n - 1 - pivw), (int)Vs.size());
+      Vs.push_back(std::move(V));
+      if (death > birth) {
+        if (n_pairs >= cap) return -1;
+        pairs_out[2 * n_pairs] = birth; pairs_out[2 * n_pairs + 1] = death; ++n_pairs;
+      }
+    }
+  }
+  if (stats) {
+    stats[0] = (int64_t)residual.size(); stats[1] = n_app; stats[2] = events; stats[3] = flips; stats[4] = heavy; stats[5] = maxv;
+    stats[6] = passes; stats[7] = maxdepth; stats[8] = delta_flips; stats[9] = heavy_in_v;
+  }
+  return n_pairs;
+}
+
+}  // extern "C"

@@ -1,0 +1,31 @@
+"""CPU: the "propagate, then verify" model of the residual H1 reduction (oracle/rips_propagate_model.cpp, an algorithm study
+for the next GPU reducer: apparent-pair additions as a forward substitution over a static two-parent graph, non-apparent
+pivots found by verifying rows in order) must give the ripser restatement's H1 diagram -- same pairs, same order -- on the
+reference's 32 shipped clouds and on random clouds."""
+import numpy as np
+import pytest
+
+from oracle import rips as orips
+from tests.helpers import blobs3d, circle2d, load_ref_rips_golden, torus3d
+
+
+def test_model_equals_oracle_on_reference_clouds():
+    clouds, _ = load_ref_rips_golden()
+    for c in clouds:
+        dm = orips.euclidean_dm_f32(c)
+        want = orips.rips_dm(dm, maxdim=1)["dgms"][1]
+        got, st = orips.model_h1(dm)
+        assert np.array_equal(got, want)
+        assert st["residual_columns"] >= len(want)
+
+
+@pytest.mark.parametrize("gen,n,seed", [(torus3d, 150, 1), (blobs3d, 220, 2), (circle2d, 90, 3), (torus3d, 400, 4)])
+def test_model_equals_oracle_on_random_clouds(gen, n, seed):
+    X = gen(n, np.random.default_rng(seed))
+    dm = orips.euclidean_dm_f32(X)
+    want = orips.rips_dm(dm, maxdim=1, with_stats=True)
+    got, st = orips.model_h1(dm)
+    assert np.array_equal(got, want["dgms"][1])
+    assert st["residual_columns"] == want["stats"][1]["reduced"]
+    # the apparent-pair additions of the sequential algorithm became a substitution of depth << their number
+    assert st["apparent_graph_depth"] < 64
