@@ -140,10 +140,11 @@ def ripser(X, maxdim=1, thresh=np.inf, coeff=2, distance_matrix=False, do_cocycl
 _MODEL = None
 
 
-def model_h1(dm):
-    """H1 diagram of a float32 distance matrix by the "propagate, then verify" model (oracle/rips_propagate_model.cpp): a CPU
-    study of the next GPU reducer, checked against `rips_dm` in tests/test_oracle_golden.py.  Returns (pairs [k,2] float64 in
-    processing order, stats dict)."""
+def model_h1(dm, window=None):
+    """H1 diagram of a float32 distance matrix by the "substitute, then verify" model (oracle/rips_propagate_model.cpp): a CPU
+    study of the next GPU reducer, checked against `rips_dm` in tests/test_reduction_model_cpu.py.  window=None: the whole view
+    above the cursor is propagated on every pass; window=k: the kernel-shaped variant (windows of k ranks: substitute, verify,
+    undo above the first failing row).  Returns (pairs [k,2] float64 in processing order, stats dict)."""
     global _MODEL
     if _MODEL is None:
         path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "librips_model.so")
@@ -152,14 +153,21 @@ def model_h1(dm):
         lib = ctypes.CDLL(path)
         lib.rips_model_h1.restype = ctypes.c_int64
         lib.rips_model_h1.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+        lib.rips_model_h1_windowed.restype = ctypes.c_int64
+        lib.rips_model_h1_windowed.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
         _MODEL = lib
     dm = np.ascontiguousarray(dm, dtype=np.float32)
     n = dm.shape[0]
     cap = max(16, n * n // 4)
     out = np.zeros((cap, 2), dtype=np.float64)
     st = np.zeros(10, dtype=np.int64)
-    k = int(_MODEL.rips_model_h1(dm.ctypes.data, n, out.ctypes.data, cap, st.ctypes.data))
+    if window is None:
+        k = int(_MODEL.rips_model_h1(dm.ctypes.data, n, out.ctypes.data, cap, st.ctypes.data))
+        names = ["residual_columns", "apparent_edges", "events", "propagated_flips", "heavy_rows_verified", "max_v", "passes", "apparent_graph_depth",
+                 "incremental_flips", "heavy_rows_in_v"]
+    else:
+        k = int(_MODEL.rips_model_h1_windowed(dm.ctypes.data, n, int(window), out.ctypes.data, cap, st.ctypes.data))
+        names = ["residual_columns", "apparent_edges", "events", "flips", "flips_undone", "heavy_rows_verified", "max_v", "windows"]
     if k < 0:
         raise RuntimeError("model_h1: pair buffer too small")
-    names = ["residual_columns", "apparent_edges", "events", "propagated_flips", "heavy_rows_verified", "max_v", "passes", "apparent_graph_depth", "incremental_flips", "heavy_rows_in_v"]
-    return out[:k].copy(), dict(zip(names, st.tolist()))
+    return out[:k].copy(), dict(zip(names, st[:len(names)].tolist()))

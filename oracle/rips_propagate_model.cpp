@@ -35,16 +35,10 @@ struct Model {
 };
 }  // namespace
 
-extern "C" {
-
-// dist: n*n float32, symmetric, zero diagonal.  pairs_out: [cap,2] doubles (birth, death; death = inf for essential classes),
-// in processing order, zero-persistence pairs dropped (as ripser does).  stats: [10] int64: residual columns, apparent edges,
-// events (additions of reduced columns), propagated flips (every pass recomputes the view from the cursor), heavy rows verified,
-// largest |V|, propagate passes, depth of the apparent graph, flips an INCREMENTAL propagation would do (edges whose view
-// value differs from the previous pass of the same column), rows verified whose own edge is in V.
-// Returns the number of pairs (or -1 if cap is too small).
-int64_t rips_model_h1(const float* dist, int n, double* pairs_out, int64_t cap, int64_t* stats) {
-  Model m; m.n = n;
+namespace {
+// edges in filtration order, ranks, MST flags, apex and the two parent edges of every apparent edge
+static void build_model(Model& m, const float* dist, int n, std::vector<int64_t>& residual, int64_t& n_app, int& maxdepth) {
+  m.n = n;
   const int64_t E = (int64_t)n * (n - 1) / 2;
   std::vector<float> elen(E); std::vector<int> ia(E), ib(E);
   { int64_t q = 0; for (int i = 1; i < n; ++i) for (int j = 0; j < i; ++j) { elen[q] = dist[(size_t)i * n + j]; ia[q] = i; ib[q] = j; ++q; } }
@@ -57,12 +51,10 @@ int64_t rips_model_h1(const float* dist, int n, double* pairs_out, int64_t cap, 
   m.R.assign((size_t)n * n, 0x7fffffff);
   m.ea.resize(T); m.eb.resize(T); m.len.resize(T);
   for (int64_t r = 0; r < T; ++r) { const int a = ia[ord[r]], b = ib[ord[r]]; m.ea[r] = a; m.eb[r] = b; m.len[r] = elen[ord[r]]; m.R[(size_t)a * n + b] = m.R[(size_t)b * n + a] = (int)r; }
-  // MST, apex, parents, depth of the apparent graph
   std::vector<int> uf(n); std::iota(uf.begin(), uf.end(), 0);
   auto find = [&](int x) { while (uf[x] != x) { uf[x] = uf[uf[x]]; x = uf[x]; } return x; };
   m.apex.assign(T, -1); m.pa.assign(T, -1); m.pb.assign(T, -1);
-  std::vector<int> depth(T, 0); int maxdepth = 0; int64_t n_app = 0;
-  std::vector<int64_t> residual;
+  std::vector<int> depth(T, 0); maxdepth = 0; n_app = 0;
   for (int64_t r = 0; r < T; ++r) {
     const int a = m.ea[r], b = m.eb[r];
     const int ra = find(a), rb = find(b);
@@ -74,6 +66,22 @@ int64_t rips_model_h1(const float* dist, int n, double* pairs_out, int64_t cap, 
     ++n_app; m.pa[r] = Ra[ap]; m.pb[r] = Rb[ap];
     depth[r] = 1 + std::max(depth[m.pa[r]], depth[m.pb[r]]); maxdepth = std::max(maxdepth, depth[r]);
   }
+}
+}  // namespace
+
+extern "C" {
+
+// dist: n*n float32, symmetric, zero diagonal.  pairs_out: [cap,2] doubles (birth, death; death = inf for essential classes),
+// in processing order, zero-persistence pairs dropped (as ripser does).  stats: [10] int64: residual columns, apparent edges,
+// events (additions of reduced columns), propagated flips (every pass recomputes the view from the cursor), heavy rows verified,
+// largest |V|, propagate passes, depth of the apparent graph, flips an INCREMENTAL propagation would do (edges whose view
+// value differs from the previous pass of the same column), rows verified whose own edge is in V.
+// Returns the number of pairs (or -1 if cap is too small).
+int64_t rips_model_h1(const float* dist, int n, double* pairs_out, int64_t cap, int64_t* stats) {
+  Model m;
+  std::vector<int64_t> residual; int64_t n_app = 0; int maxdepth = 0;
+  build_model(m, dist, n, residual, n_app, maxdepth);
+  const int64_t T = m.T;
   const int W = (n + 63) / 64;
   std::vector<uint8_t> xr(T, 0), xs(T, 0);
   std::vector<uint64_t> X((size_t)n * W, 0), lune(W);
@@ -166,6 +174,105 @@ int64_t rips_model_h1(const float* dist, int n, double* pairs_out, int64_t cap, 
   if (stats) {
     stats[0] = (int64_t)residual.size(); stats[1] = n_app; stats[2] = events; stats[3] = flips; stats[4] = heavy; stats[5] = maxv;
     stats[6] = passes; stats[7] = maxdepth; stats[8] = delta_flips; stats[9] = heavy_in_v;
+  }
+  return n_pairs;
+}
+
+
+// The same reduction organised the way the sweep kernel would run it: the rows above the cursor are
+// taken in windows of `window` consecutive ranks.  Per window: (A) substitution x_M = x_pa ^ x_pb for the apparent rows whose
+// endpoints V touches, flips applied to X at once; (B) every row of the window verified against that X -- a flip of a LATER row
+// cannot show up in an earlier row, its edge is outside that row's lune; (C) at the first non-empty row the flips above it are
+// undone and the event is handled (owned pivot: V ^= V_j, resume in that row below the pivot vertex; unowned: death).
+// stats: [8] residual columns, apparent edges, events, flips, flips undone, heavy rows verified, largest |V|, windows visited.
+int64_t rips_model_h1_windowed(const float* dist, int n, int window, double* pairs_out, int64_t cap, int64_t* stats) {
+  Model m;
+  std::vector<int64_t> residual; int64_t n_app = 0; int maxdepth = 0;
+  build_model(m, dist, n, residual, n_app, maxdepth);
+  const int64_t T = m.T;
+  const int W = (n + 63) / 64;
+  if (window < 1) window = 1;
+  std::vector<uint8_t> x(T, 0);
+  std::vector<uint64_t> X((size_t)n * W, 0);
+  std::vector<uint8_t> touched(n, 0);
+  std::unordered_map<int64_t, int> owner;
+  std::vector<std::vector<int>> Vs;
+  int64_t n_pairs = 0, events = 0, flips = 0, undone = 0, heavy = 0, maxv = 0, windows = 0;
+  std::vector<int64_t> members;                        // every edge whose x was ever set in this column (clean-up, V)
+  auto toggle = [&](int64_t e) {
+    x[e] ^= 1; const int a = m.ea[e], b = m.eb[e];
+    X[(size_t)a * W + (b >> 6)] ^= 1ull << (b & 63); X[(size_t)b * W + (a >> 6)] ^= 1ull << (a & 63);
+    touched[a] = touched[b] = 1;
+    if (x[e]) members.push_back(e);
+  };
+  for (int64_t ci = (int64_t)residual.size() - 1; ci >= 0; --ci) {
+    const int64_t b = residual[ci];
+    members.clear();
+    std::fill(touched.begin(), touched.end(), 0);
+    toggle(b);
+    int64_t lo = b + 1;          // first row of the next window
+    int64_t resume_row = -1; int resume_w = 0;   // after an owned pivot: that row again, below the pivot vertex, no substitution
+    bool essential = false; int64_t pivM = -1; int pivw = -1;
+    for (;;) {
+      const int64_t first = resume_row >= 0 ? resume_row : lo;
+      if (first >= T) { essential = true; break; }
+      const int64_t hi = std::min<int64_t>(T, first + window);
+      ++windows;
+      // (A) substitution
+      std::vector<int64_t> flipped;
+      for (int64_t M = first; M < hi; ++M) {
+        if (M == resume_row || m.apex[M] < 0) continue;
+        const int c = m.ea[M], d = m.eb[M];
+        if (!touched[c] && !touched[d]) continue;
+        const uint8_t want = x[m.pa[M]] ^ x[m.pb[M]];
+        if (want != x[M]) { toggle(M); flipped.push_back(M); ++flips; }
+      }
+      // (B) verification against the X that already holds every flip of the window
+      pivM = -1;
+      for (int64_t M = first; M < hi && pivM < 0; ++M) {
+        if (m.apex[M] == -2) continue;
+        const int c = m.ea[M], d = m.eb[M];
+        if (!touched[c] && !touched[d]) continue;
+        ++heavy;
+        const int* Rc = &m.R[(size_t)c * n]; const int* Rd = &m.R[(size_t)d * n];
+        const int wtop = M == resume_row ? resume_w - 1 : n - 1;
+        for (int w = wtop; w >= 0; --w) {
+          if (!(Rc[w] < M && Rd[w] < M)) continue;
+          const int bit = (int)x[M] ^ (int)((X[(size_t)c * W + (w >> 6)] >> (w & 63)) & 1) ^ (int)((X[(size_t)d * W + (w >> 6)] >> (w & 63)) & 1);
+          if (bit) { pivM = M; pivw = w; break; }
+        }
+      }
+      if (pivM < 0) { lo = hi; resume_row = -1; continue; }
+      // (C) event: undo the flips above the failing row
+      for (int64_t e : flipped) if (e > pivM) { toggle(e); ++undone; }
+      const int64_t key = pivM * (int64_t)n + (n - 1 - pivw);
+      auto it = owner.find(key);
+      if (it == owner.end()) break;                    // death
+      ++events;
+      for (int e : Vs[it->second]) toggle(e);
+      resume_row = pivM; resume_w = pivw; lo = pivM + 1;
+    }
+    std::vector<int> V;
+    for (int64_t e : members) if (x[e]) { V.push_back((int)e); toggle(e); }
+    std::sort(V.begin(), V.end()); V.erase(std::unique(V.begin(), V.end()), V.end());
+    maxv = std::max<int64_t>(maxv, (int64_t)V.size());
+    const float birth = m.len[b];
+    if (essential) {
+      if (n_pairs >= cap) return -1;
+      pairs_out[2 * n_pairs] = birth; pairs_out[2 * n_pairs + 1] = INFINITY; ++n_pairs;
+    } else {
+      const float death = m.len[pivM];
+      owner.emplace(pivM * (int64_t)n + (n - 1 - pivw), (int)Vs.size());
+      Vs.push_back(std::move(V));
+      if (death > birth) {
+        if (n_pairs >= cap) return -1;
+        pairs_out[2 * n_pairs] = birth; pairs_out[2 * n_pairs + 1] = death; ++n_pairs;
+      }
+    }
+  }
+  if (stats) {
+    stats[0] = (int64_t)residual.size(); stats[1] = n_app; stats[2] = events; stats[3] = flips; stats[4] = undone; stats[5] = heavy;
+    stats[6] = maxv; stats[7] = windows;
   }
   return n_pairs;
 }

@@ -29,3 +29,20 @@ def test_model_equals_oracle_on_random_clouds(gen, n, seed):
     assert st["residual_columns"] == want["stats"][1]["reduced"]
     # the apparent-pair additions of the sequential algorithm became a substitution of depth << their number
     assert st["apparent_graph_depth"] < 64
+
+
+@pytest.mark.parametrize("window", [1, 7, 64, 512, 1 << 30])
+def test_windowed_model_equals_oracle(window):
+    """The kernel-shaped variant: substitution and verification per window of ranks, flips above the first failing row undone.
+    Any window size must give the same pairs (window 1 is the sequential algorithm, 2^30 one window per pass)."""
+    clouds, _ = load_ref_rips_golden()
+    for c in clouds[::4]:
+        dm = orips.euclidean_dm_f32(c)
+        got, _ = orips.model_h1(dm, window=window)
+        assert np.array_equal(got, orips.rips_dm(dm, maxdim=1)["dgms"][1])
+    for gen, n, seed in [(torus3d, 160, 5), (blobs3d, 250, 6), (torus3d, 420, 7)]:
+        dm = orips.euclidean_dm_f32(gen(n, np.random.default_rng(seed)))
+        want = orips.rips_dm(dm, maxdim=1, with_stats=True)
+        got, st = orips.model_h1(dm, window=window)
+        assert np.array_equal(got, want["dgms"][1]), (window, n)
+        assert st["residual_columns"] == want["stats"][1]["reduced"]
