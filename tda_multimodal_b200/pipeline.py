@@ -276,3 +276,74 @@ def gather_diagrams(local_units, local_results, n_units, maxdim=1, group=None, d
         for u, d in zip(units, dg):
             full[u] = d
     return full
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fit once / transform many (analyze_tda_over_layers.py:67-72): all layers depend on ONE fit, so the fit runs on one rank,
+# the fitted state is broadcast, and the transforms shard by layer.
+FITTED_STATE_KEYS = ("raw_data", "embedding", "scalars")
+
+
+def pack_fitted_state(raw_data, embedding, a, b, n_neighbors):
+    """The three tensors a rank needs to run UMAP.transform: training data [n,d] f32, its embedding [n,dim] f32, and
+    (a, b, n_neighbors, n, d, dim) as one float64 vector."""
+    import torch
+    raw = raw_data.reshape(raw_data.shape[-2], raw_data.shape[-1]).to(torch.float32).contiguous()
+    emb = embedding.reshape(embedding.shape[-2], embedding.shape[-1]).to(torch.float32).contiguous()
+    sc = torch.tensor([float(a), float(b), float(n_neighbors), float(raw.shape[0]), float(raw.shape[1]), float(emb.shape[1])], dtype=torch.float64)
+    return {"raw_data": raw, "embedding": emb, "scalars": sc}
+
+
+def broadcast_fitted_state(state, src=0, group=None, device=None):
+    """`state` = pack_fitted_state(...) on rank `src`, None elsewhere.  Every rank returns the same dict (tensors on `device`:
+    the current CUDA device under NCCL, the CPU under gloo).  Two broadcasts: the shape/scalar vector, then data + embedding
+    as one flat float32 buffer."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return state
+    rank = dist.get_rank(group)
+    backend = dist.get_backend(group)
+    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu"))
+    sc = state["scalars"].to(dev) if rank == src else torch.zeros(6, dtype=torch.float64, device=dev)
+    dist.broadcast(sc, src=src, group=group)
+    n, d, dim = int(sc[3].item()), int(sc[4].item()), int(sc[5].item())
+    flat = torch.empty(n * d + n * dim, dtype=torch.float32, device=dev)
+    if rank == src:
+        flat[:n * d] = state["raw_data"].to(dev).reshape(-1)
+        flat[n * d:] = state["embedding"].to(dev).reshape(-1)
+    dist.broadcast(flat, src=src, group=group)
+    return {"raw_data": flat[:n * d].reshape(n, d), "embedding": flat[n * d:].reshape(n, dim), "scalars": sc.cpu()}
+
+
+def fit_once_transform_many(X_layers, fit_layer=0, n_neighbors=15, n_components=3, min_dist=0.1, metric="cosine", random_state=42,
+                            maxdim=1, group=None):
+    """analyze_tda_over_layers.py:56-77 over the ranks: UMAP is fitted on layer `fit_layer` by rank 0, its state is broadcast,
+    rank r transforms layers r, r+G, ... (the fit layer returns the stored embedding, as umap-learn does for its own training
+    data) and runs Rips on each; the diagrams are gathered.  X_layers [L,n,d] float32 CUDA tensor (replicated, or only this
+    rank's layers filled in).  Returns (embeddings of this rank's layers {layer: [n,dim] CUDA tensor}, diagrams of ALL layers)."""
+    torch = _lib.require_cuda()
+    import torch.distributed as dist
+    from .umap_ import UMAP, find_ab_params, umap_transform_batch
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    rank = dist.get_rank(group) if multi else 0
+    world = dist.get_world_size(group) if multi else 1
+    L = X_layers.shape[0]
+    state = None
+    if rank == 0:
+        um = UMAP(n_neighbors=n_neighbors, n_components=n_components, min_dist=min_dist, metric=metric, random_state=random_state)
+        um.fit(X_layers[fit_layer])
+        state = pack_fitted_state(um._raw_data[0], um._embedding_dev[0], um._a, um._b, um._n_neighbors)
+    state = broadcast_fitted_state(state, src=0, group=group)
+    a, b, k = float(state["scalars"][0]), float(state["scalars"][1]), int(state["scalars"][2])
+    mine = shard_units(L, rank, world)
+    emb, results = {}, []
+    for l in mine:
+        if l == fit_layer:
+            Y = state["embedding"]
+        else:
+            Y = umap_transform_batch(X_layers[l][None].to(torch.float32), state["raw_data"][None], state["embedding"][None], k, metric=metric,
+                                     a=a, b=b, seed=42)[0]
+        emb[l] = Y
+        results.append(rips_batch(pdist_lowdim(Y[None].contiguous()), maxdim=maxdim)[0])
+    return emb, gather_diagrams(mine, results, L, maxdim=maxdim, group=group)

@@ -55,3 +55,43 @@ def test_single_process_passthrough():
     from tda_multimodal_b200 import pipeline
     full = pipeline.gather_diagrams([0, 1, 2], [_fake_result(u) for u in range(3)], 3)
     assert all(np.array_equal(full[u][1], _fake_result(u)["dgms"][1]) for u in range(3))
+
+
+def _bcast_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from tda_multimodal_b200 import pipeline
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(5)
+    raw, emb = torch.randn(37, 16, generator=g), torch.randn(37, 3, generator=g)
+    state = pipeline.pack_fitted_state(raw[None], emb[None], 1.577, 0.895, 15) if rank == 0 else None
+    got = pipeline.broadcast_fitted_state(state, src=0)
+    ok = torch.equal(got["raw_data"], raw) and torch.equal(got["embedding"], emb)
+    ok = ok and [float(v) for v in got["scalars"]] == [1.577, 0.895, 15.0, 37.0, 16.0, 3.0]
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_fitted_state_broadcast():
+    """analyze_tda_over_layers.py: one fit, many transforms -- the fitted state (training data, embedding, a, b, k) reaches
+    every rank unchanged (world size 2, gloo); the transforms themselves are GPU work."""
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_bcast_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert ret[0] and ret[1]
+    sys.path.insert(0, ROOT)
+    import torch
+    from tda_multimodal_b200 import pipeline
+    st = pipeline.pack_fitted_state(torch.zeros(1, 4, 2), torch.zeros(1, 4, 3), 1.0, 1.0, 3)
+    assert pipeline.broadcast_fitted_state(st) is st       # single process: passthrough
