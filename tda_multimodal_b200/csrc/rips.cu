@@ -390,6 +390,7 @@ struct ReduceParams {
   // far buckets (key space larger than one window): keys beyond the window wait in the bucket of their window instead of
   // being re-enumerated from V when the window gets there.  [grid, far_cap] keys; nbk = most windows a column can see
   uint64_t* far; uint64_t far_cap; uint32_t nbk;
+  int verify_mode;                          // sweep reducer: substitute-then-verify instead of the sequential resolver (opt-in)
 };
 
 struct ReduceSmem {
@@ -1073,9 +1074,15 @@ struct SweepSmem {
   int res_status, res_s, res_owner;
   uint32_t res_w;
   unsigned long long additions, pivots, heavy_rows, restarts, groups;
+  // substitute-then-verify mode
+  uint32_t sub_done[kChunkRows / 32];   // chunk rows whose x is final for this pass (all but the heavy apparent rows not yet substituted)
+  uint16_t fliprow[kChunkRows];         // chunk-local rows whose edge was flipped since the chunk started (for the undo)
+  uint32_t nflip;
+  uint32_t new_touch;                   // a flip touched a vertex that V did not touch before: filter the chunk again
+  int fail_w;                           // highest vertex of the first non-empty row
 };
 
-template <int WPL>   // words of a row per lane of the resolver (W <= 32 * WPL)
+template <int WPL, bool VERIFY = false>   // WPL: words of a row per lane of the resolver (W <= 32 * WPL); VERIFY: substitute-then-verify
 struct Sweeper {
   static constexpr uint64_t kEmpty = ~0ull;
   const ReduceParams& P;
@@ -1618,6 +1625,7 @@ struct Sweeper {
       bool essential = false;
       uint64_t pivot = 0;
       uint32_t pos = (uint32_t)rbirth + 1;
+      uint32_t vchunk_pos = 0xffffffffu;   // (verify mode) start of the chunk the flip list belongs to
       p_mode = false;
       for (;;) {
         if (S.abort_flag) break;
@@ -1674,6 +1682,154 @@ struct Sweeper {
           __syncthreads();
           cyc[5] += clock64() - t0;
           continue;   // filter this chunk again in dense mode (builds the per-vertex row lists)
+        }
+        if constexpr (VERIFY) {
+          // ---- substitute, then verify (CPU model: oracle/rips_propagate_model.cpp, windowed variant).
+          // (A) substitution: for an apparent row M=(c,d) with apex a the reduction ends with x_M = x_(c,a) ^ x_(d,a), whatever
+          //     happened before; one thread per heavy row, a row whose parent edge is a row of this chunk waits for it.
+          if (pos != vchunk_pos) {
+            vchunk_pos = pos;
+            if (tid == 0) S.nflip = 0;
+          }
+          if (tid < kChunkRows / 32) S.sub_done[tid] = 0xffffffffu;
+          if (tid == 0) S.new_touch = 0;
+          __syncthreads();
+          t0 = clock64();
+          int apex_j = -3, dep_a = -1, dep_b = -1;
+          uint32_t hj = 0, cj = 0, dj = 0;
+          bool pending = false;
+          if ((uint32_t)tid < nh) {
+            hj = S.heavy[tid];
+            const uint2 eaj = S.chunk_ea[hj];
+            cj = eaj.x >> 16; dj = eaj.x & 0xffffu;
+            apex_j = (int)eaj.y;
+            if (apex_j >= 0) {
+              const int ra = __ldg(&R[(size_t)cj * n + apex_j]), rb = __ldg(&R[(size_t)dj * n + apex_j]);
+              if (ra >= (int)pos) dep_a = ra - (int)pos;
+              if (rb >= (int)pos) dep_b = rb - (int)pos;
+              pending = true;
+              atomicAnd(&S.sub_done[hj >> 5], ~(1u << (hj & 31)));
+            }
+          }
+          __syncthreads();
+          for (;;) {
+            bool can = pending;
+            if (can && dep_a >= 0) can = (S.sub_done[dep_a >> 5] >> (dep_a & 31)) & 1u;
+            if (can && dep_b >= 0) can = (S.sub_done[dep_b >> 5] >> (dep_b & 31)) & 1u;
+            if (can) {
+              const uint32_t xa = (__ldcg(&X[(size_t)cj * W + ((uint32_t)apex_j >> 5)]) >> (apex_j & 31)) & 1u;
+              const uint32_t xb = (__ldcg(&X[(size_t)dj * W + ((uint32_t)apex_j >> 5)]) >> (apex_j & 31)) & 1u;
+              const uint32_t cur = (__ldcg(&X[(size_t)cj * W + (dj >> 5)]) >> (dj & 31)) & 1u;
+              if ((xa ^ xb) != cur) {
+                x_flip(cj, dj);
+                v_toggle((int)(pos + hj));
+                const uint32_t oc = atomicOr(&touched[cj >> 5], 1u << (cj & 31));
+                const uint32_t od = atomicOr(&touched[dj >> 5], 1u << (dj & 31));
+                if (!((oc >> (cj & 31)) & 1u) || !((od >> (dj & 31)) & 1u)) S.new_touch = 1;
+                const uint32_t fi = atomicAdd(&S.nflip, 1u);
+                if (fi < (uint32_t)kChunkRows) S.fliprow[fi] = (uint16_t)hj;
+                else S.abort_flag = TDA_ERR_CAPACITY;   // (a row flips at most once per pass; repeated passes could exceed the list)
+              }
+              pending = false;
+            }
+            __threadfence();   // the flips are performed before another thread reads these X words
+            __syncthreads();
+            if (can) atomicOr(&S.sub_done[hj >> 5], 1u << (hj & 31));
+            if (__syncthreads_count(pending) == 0) break;
+          }
+          cyc[2] += clock64() - t0;
+          if (S.new_touch) {   // rows filtered out as untouched may matter now: filter this chunk again (substitution is idempotent)
+            if (tid == 0) S.restarts += 1;
+            __syncthreads();
+            continue;
+          }
+          // (B) verification: every heavy row, formed from the X that holds all the flips of the chunk, must be empty
+          t0 = clock64();
+          bool failed = false;
+          uint32_t fi0 = 0;
+          int fs = 0;
+          for (uint32_t i0 = 0; i0 < nh && !failed; i0 += kGroupRows) {
+            const int ns = (int)min((uint32_t)kGroupRows, nh - i0);
+            produce(0, pos, i0, ns, 0, kSweepWarps);
+            __syncthreads();
+            const uint32_t dirty = S.dirty[0];
+            if (dirty) {
+              failed = true; fi0 = i0; fs = __ffs(dirty) - 1;
+              if (warp == 0) {   // the first non-empty row: its highest vertex is the next non-apparent pivot
+                const uint32_t* r = Sr + (size_t)fs * W;
+                int best = -1;
+#pragma unroll
+                for (int q = 0; q < WPL; ++q) {
+                  const uint32_t rwq = (lane + 32 * q) < W ? r[lane + 32 * q] : 0u;
+                  if (rwq) best = (lane + 32 * q) * 32 + 31 - __clz(rwq);
+                }
+                best = __reduce_max_sync(0xffffffffu, best);
+                if (lane == 0) S.fail_w = best;
+              }
+            }
+            __syncthreads();
+            if (tid == 0) { S.dirty[0] = 0; S.simple[0] = 0; S.both[0] = 0; S.groups += 1; S.heavy_rows += failed ? (uint32_t)(fs + 1) : (uint32_t)ns; }
+            __syncthreads();
+          }
+          cyc[1] += clock64() - t0;
+          if (!failed) {
+            if (tid == 0) S.additions += S.nflip;
+            pos += kChunkRows;
+            __syncthreads();
+            continue;
+          }
+          // (C) event at row srow: the flips above it are undone (they were made with an X that the event changes)
+          t0 = clock64();
+          const uint32_t srow = pos + S.heavy[fi0 + fs];
+          const int fw = S.fail_w;
+          const uint32_t nfl = min(S.nflip, (uint32_t)kChunkRows);
+          uint32_t kept = 0;
+          for (uint32_t f = tid; f < nfl; f += kSweepThreads) {
+            const uint32_t hf = S.fliprow[f];
+            if (pos + hf > srow) {
+              const uint2 eaf = S.chunk_ea[hf];
+              x_flip(eaf.x >> 16, eaf.x & 0xffffu);
+              v_toggle((int)(pos + hf));
+            } else {
+              ++kept;
+            }
+          }
+          (void)kept;
+          __syncthreads();
+          if (tid == 0) {
+            uint32_t k2 = 0;
+            for (uint32_t f = 0; f < nfl; ++f) k2 += (pos + S.fliprow[f] <= srow) ? 1u : 0u;
+            S.additions += k2;
+            S.pivots += 1;
+          }
+          __threadfence();
+          __syncthreads();
+          const uint64_t fkey = (uint64_t)srow * (uint64_t)n + (uint64_t)(n - 1 - fw);
+          const int fowner = hash_find(fkey);
+          if (fowner < 0) { pivot = fkey; cyc[4] += clock64() - t0; break; }   // death
+          {
+            const int64_t vs = P.vstart[(size_t)p * P.cap1 + fowner];
+            const int vn = P.vlen[(size_t)p * P.cap1 + fowner];
+            const uint32_t* ov = P.vpool + (size_t)p * P.vpool_cap + vs;
+            if (S.vcount + (uint32_t)vn > (uint32_t)P.vcap) v_compact();
+            for (int q = tid; q < vn; q += kSweepThreads) {
+              const int re = (int)ov[q];
+              const uint32_t en = __ldg(&EN[re]);
+              const uint32_t c = en >> 16, d = en & 0xffffu;
+              x_flip(c, d);
+              v_toggle(re);
+              atomicOr(&touched[c >> 5], 1u << (c & 31));
+              atomicOr(&touched[d >> 5], 1u << (d & 31));
+            }
+            badd_edges += vn;
+            if (tid == 0) { S.additions += 1; S.restarts += 1; }
+            __threadfence();
+            __syncthreads();
+          }
+          pos = srow;   // this row again: the pivot just handled is even now, lower vertices may remain (its substitution is a no-op)
+          cyc[3] += clock64() - t0;
+          __syncthreads();
+          continue;
         }
         uint32_t i = 0;
         bool restart = false, done = false;
@@ -1813,11 +1969,11 @@ struct Sweeper {
   }
 };
 
-template <int WPL>
+template <int WPL, bool VERIFY = false>
 __global__ void __launch_bounds__(kSweepThreads, 1) rips_sweep_kernel(const __grid_constant__ ReduceParams P) {
   __shared__ SweepSmem S;
   extern __shared__ uint32_t sweep_dyn[];
-  Sweeper<WPL> sw(P, S, sweep_dyn);
+  Sweeper<WPL, VERIFY> sw(P, S, sweep_dyn);
   for (;;) {
     if (threadIdx.x == 0) S.problem = atomicAdd(P.work_counter, 1);
     __syncthreads();
@@ -2152,22 +2308,31 @@ static int rips_enqueue(const float* dm, int n, int batch, int maxdim, float thr
     P.work_counter = L.work_counter; P.stats = L.stats;
     P.apex4 = nullptr; P.far = nullptr; P.far_cap = 0; P.nbk = 0;
     {
+      const char* e = getenv("TDA_RIPS_REDUCER");   // "verify": substitute-then-verify inside the sweep kernel (not yet the default)
+      P.verify_mode = (e && strcmp(e, "verify") == 0) ? 1 : 0;
+    }
+    {
       StageScope st(STAGE_RIPS_REDUCE, stream);
       if (L.sweep) {
         // TDA_SWEEP_EXCLUSIVE=1: ask for all of the SM's shared memory, so that no CTA of a kernel running on another stream
         // (UMAP SGD of the next chunk ...) shares the SM -- and the issue slots -- with the latency-bound resolver warp
         static const bool exclusive = [] { const char* e = getenv("TDA_SWEEP_EXCLUSIVE"); return e && e[0] == '1'; }();
         size_t dyn = sizeof(uint32_t) * ((size_t)L.xw * (1 + 4 * kGroupRows) + (size_t)n + 2 * kChunkRows);
-#define TDA_SWEEP_LAUNCH(WPL)                                                                                                 \
+#define TDA_SWEEP_LAUNCH_K(KERNEL)                                                                                            \
   do {                                                                                                                        \
     if (exclusive) {                                                                                                          \
       cudaFuncAttributes fa;                                                                                                  \
-      TDA_CUDA_CHECK(cudaFuncGetAttributes(&fa, rips_sweep_kernel<WPL>));                                                     \
+      TDA_CUDA_CHECK(cudaFuncGetAttributes(&fa, KERNEL));                                                                     \
       const size_t room = (size_t)227 * 1024 - fa.sharedSizeBytes;                                                            \
       if (dyn < room) dyn = room;                                                                                             \
     }                                                                                                                         \
-    TDA_CUDA_CHECK(cudaFuncSetAttribute(rips_sweep_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));      \
-    rips_sweep_kernel<WPL><<<L.grid, kSweepThreads, dyn, stream>>>(P);                                                        \
+    TDA_CUDA_CHECK(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));                      \
+    KERNEL<<<L.grid, kSweepThreads, dyn, stream>>>(P);                                                                        \
+  } while (0)
+#define TDA_SWEEP_LAUNCH(WPL)                                                                                                 \
+  do {                                                                                                                        \
+    if (P.verify_mode) TDA_SWEEP_LAUNCH_K((rips_sweep_kernel<WPL, true>));                                                    \
+    else TDA_SWEEP_LAUNCH_K((rips_sweep_kernel<WPL, false>));                                                                 \
   } while (0)
         if (L.xw <= 32) TDA_SWEEP_LAUNCH(1);
         else if (L.xw <= 64) TDA_SWEEP_LAUNCH(2);
@@ -2175,6 +2340,7 @@ static int rips_enqueue(const float* dm, int n, int batch, int maxdim, float thr
         else if (L.xw <= 256) TDA_SWEEP_LAUNCH(8);
         else return set_error(TDA_ERR_UNSUPPORTED, "tda_rips: internal: sweep reducer selected for n=%d", n);
 #undef TDA_SWEEP_LAUNCH
+#undef TDA_SWEEP_LAUNCH_K
       } else {
         const size_t s1_bytes = (size_t)(((L.wbits >> kPageShift) + 31) / 32) * sizeof(uint32_t);
         TDA_CUDA_CHECK(cudaFuncSetAttribute(rips_reduce_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1_bytes));
