@@ -140,7 +140,7 @@ def ripser(X, maxdim=1, thresh=np.inf, coeff=2, distance_matrix=False, do_cocycl
 _MODEL = None
 
 
-def model_h1(dm, window=None):
+def model_h1(dm, window=None, kernel_steps=False):
     """H1 diagram of a float32 distance matrix by the "substitute, then verify" model (oracle/rips_propagate_model.cpp): a CPU
     study of the next GPU reducer, checked against `rips_dm` in tests/test_reduction_model_cpu.py.  window=None: the whole view
     above the cursor is propagated on every pass; window=k: the kernel-shaped variant (windows of k ranks: substitute, verify,
@@ -155,6 +155,8 @@ def model_h1(dm, window=None):
         lib.rips_model_h1.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
         lib.rips_model_h1_windowed.restype = ctypes.c_int64
         lib.rips_model_h1_windowed.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+        lib.rips_model_h1_kernel.restype = ctypes.c_int64
+        lib.rips_model_h1_kernel.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
         _MODEL = lib
     dm = np.ascontiguousarray(dm, dtype=np.float32)
     n = dm.shape[0]
@@ -165,6 +167,11 @@ def model_h1(dm, window=None):
         k = int(_MODEL.rips_model_h1(dm.ctypes.data, n, out.ctypes.data, cap, st.ctypes.data))
         names = ["residual_columns", "apparent_edges", "events", "propagated_flips", "heavy_rows_verified", "max_v", "passes", "apparent_graph_depth",
                  "incremental_flips", "heavy_rows_in_v"]
+    elif kernel_steps:   # the control flow of Sweeper<WPL, VERIFY=true> (csrc/rips.cu), chunk = window
+        k = int(_MODEL.rips_model_h1_kernel(dm.ctypes.data, n, int(window), out.ctypes.data, cap, st.ctypes.data))
+        names = ["residual_columns", "apparent_edges", "events", "flips", "flips_undone", "heavy_rows_verified", "refilter_passes", "rounds"]
+        if k == -2:
+            raise RuntimeError("model_h1: substitution made no progress")
     else:
         k = int(_MODEL.rips_model_h1_windowed(dm.ctypes.data, n, int(window), out.ctypes.data, cap, st.ctypes.data))
         names = ["residual_columns", "apparent_edges", "events", "flips", "flips_undone", "heavy_rows_verified", "max_v", "windows"]

@@ -277,4 +277,126 @@ int64_t rips_model_h1_windowed(const float* dist, int n, int window, double* pai
   return n_pairs;
 }
 
+
+// The windowed variant again, but step for step as Sweeper<WPL, VERIFY=true> (csrc/rips.cu) does it, so that the kernel's
+// control flow is checked on the CPU too: the chunk's heavy rows are fixed by a filter at the start of a pass; the
+// substitution runs in rounds (a row waits until the parent edges that are rows of the same chunk are done; rows that are
+// not heavy count as done); a flip that touches a new vertex makes the whole chunk be filtered and substituted again
+// (substitution is idempotent); every recorded flip above the failing row is undone, even if a row was recorded twice.
+// stats: [8] residual columns, apparent edges, events, flips, flips undone, heavy rows verified, re-filter passes, rounds.
+int64_t rips_model_h1_kernel(const float* dist, int n, int chunk, double* pairs_out, int64_t cap, int64_t* stats) {
+  Model m;
+  std::vector<int64_t> residual; int64_t n_app = 0; int maxdepth = 0;
+  build_model(m, dist, n, residual, n_app, maxdepth);
+  const int64_t T = m.T;
+  const int W = (n + 63) / 64;
+  if (chunk < 1) chunk = 1;
+  std::vector<uint8_t> x(T, 0);
+  std::vector<uint64_t> X((size_t)n * W, 0);
+  std::vector<uint8_t> touched(n, 0);
+  std::unordered_map<int64_t, int> owner;
+  std::vector<std::vector<int>> Vs;
+  int64_t n_pairs = 0, events = 0, flips = 0, undone = 0, heavy_rows = 0, refilters = 0, rounds = 0;
+  std::vector<int64_t> members;
+  auto xbit = [&](int a, int b) { return (int)((X[(size_t)a * W + (b >> 6)] >> (b & 63)) & 1); };
+  auto flip = [&](int64_t e) {   // x_flip + v_toggle
+    x[e] ^= 1; const int a = m.ea[e], b = m.eb[e];
+    X[(size_t)a * W + (b >> 6)] ^= 1ull << (b & 63); X[(size_t)b * W + (a >> 6)] ^= 1ull << (a & 63);
+    if (x[e]) members.push_back(e);
+  };
+  for (int64_t ci = (int64_t)residual.size() - 1; ci >= 0; --ci) {
+    const int64_t b = residual[ci];
+    members.clear();
+    std::fill(touched.begin(), touched.end(), 0);
+    flip(b); touched[m.ea[b]] = touched[m.eb[b]] = 1;
+    int64_t pos = b + 1, vchunk_pos = -1;
+    std::vector<int64_t> fliplist;
+    bool essential = false; int64_t pivM = -1; int pivw = -1;
+    for (;;) {
+      if (pos >= T) { essential = true; break; }
+      const int64_t hi = std::min<int64_t>(T, pos + chunk);
+      // filter
+      std::vector<int64_t> heavy;
+      for (int64_t M = pos; M < hi; ++M) if (touched[m.ea[M]] || touched[m.eb[M]]) heavy.push_back(M);
+      if (pos != vchunk_pos) { vchunk_pos = pos; fliplist.clear(); }
+      // (A) substitution in rounds
+      std::vector<uint8_t> done((size_t)(hi - pos), 1), pending(heavy.size(), 0);
+      for (size_t h = 0; h < heavy.size(); ++h) if (m.apex[heavy[h]] >= 0) { pending[h] = 1; done[heavy[h] - pos] = 0; }
+      bool new_touch = false;
+      for (;;) {
+        ++rounds;
+        std::vector<size_t> can;
+        for (size_t h = 0; h < heavy.size(); ++h) {
+          if (!pending[h]) continue;
+          const int64_t M = heavy[h];
+          const int64_t ra = m.pa[M], rb = m.pb[M];
+          if (ra >= pos && !done[ra - pos]) continue;
+          if (rb >= pos && !done[rb - pos]) continue;
+          can.push_back(h);
+        }
+        for (size_t h : can) {
+          const int64_t M = heavy[h];
+          const int c = m.ea[M], d = m.eb[M], a = m.apex[M];
+          const int want = xbit(c, a) ^ xbit(d, a), cur = xbit(c, d);
+          if (want != cur) {
+            flip(M); ++flips;
+            if (!touched[c] || !touched[d]) new_touch = true;
+            touched[c] = touched[d] = 1;
+            fliplist.push_back(M);
+          }
+          pending[h] = 0;
+        }
+        for (size_t h : can) done[heavy[h] - pos] = 1;
+        bool left = false; for (uint8_t q : pending) left |= q != 0;
+        if (!left) break;
+        if (can.empty()) return -2;   // no progress: the dependency order is broken
+      }
+      if (new_touch) { ++refilters; continue; }
+      // (B) verification of the heavy rows in order
+      pivM = -1;
+      for (int64_t M : heavy) {
+        ++heavy_rows;
+        if (m.apex[M] == -2) continue;
+        const int c = m.ea[M], d = m.eb[M];
+        const int* Rc = &m.R[(size_t)c * n]; const int* Rd = &m.R[(size_t)d * n];
+        for (int w = n - 1; w >= 0; --w) {
+          if (!(Rc[w] < M && Rd[w] < M)) continue;
+          if (x[M] ^ xbit(c, w) ^ xbit(d, w)) { pivM = M; pivw = w; break; }
+        }
+        if (pivM >= 0) break;
+      }
+      if (pivM < 0) { pos = hi; continue; }
+      // (C) event
+      for (int64_t e : fliplist) if (e > pivM) { flip(e); ++undone; }
+      const int64_t key = pivM * (int64_t)n + (n - 1 - pivw);
+      auto it = owner.find(key);
+      if (it == owner.end()) break;                    // death
+      ++events;
+      for (int e : Vs[it->second]) { flip(e); touched[m.ea[e]] = touched[m.eb[e]] = 1; }
+      pos = pivM;
+    }
+    std::vector<int> V;
+    for (int64_t e : members) if (x[e]) { V.push_back((int)e); flip(e); }
+    std::sort(V.begin(), V.end()); V.erase(std::unique(V.begin(), V.end()), V.end());
+    const float birth = m.len[b];
+    if (essential) {
+      if (n_pairs >= cap) return -1;
+      pairs_out[2 * n_pairs] = birth; pairs_out[2 * n_pairs + 1] = INFINITY; ++n_pairs;
+    } else {
+      const float death = m.len[pivM];
+      owner.emplace(pivM * (int64_t)n + (n - 1 - pivw), (int)Vs.size());
+      Vs.push_back(std::move(V));
+      if (death > birth) {
+        if (n_pairs >= cap) return -1;
+        pairs_out[2 * n_pairs] = birth; pairs_out[2 * n_pairs + 1] = death; ++n_pairs;
+      }
+    }
+  }
+  if (stats) {
+    stats[0] = (int64_t)residual.size(); stats[1] = n_app; stats[2] = events; stats[3] = flips; stats[4] = undone; stats[5] = heavy_rows;
+    stats[6] = refilters; stats[7] = rounds;
+  }
+  return n_pairs;
+}
+
 }  // extern "C"

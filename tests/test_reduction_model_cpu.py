@@ -46,3 +46,19 @@ def test_windowed_model_equals_oracle(window):
         got, st = orips.model_h1(dm, window=window)
         assert np.array_equal(got, want["dgms"][1]), (window, n)
         assert st["residual_columns"] == want["stats"][1]["reduced"]
+
+
+@pytest.mark.parametrize("chunk", [4, 32, 512])
+def test_kernel_step_model_equals_oracle(chunk):
+    """The control flow of the GPU variant (Sweeper<WPL, VERIFY=true> in csrc/rips.cu), replayed on the CPU: heavy rows fixed by
+    a filter per pass, substitution in dependency rounds, a whole-chunk re-filter when a flip touches a new vertex, undo of every
+    recorded flip above the failing row."""
+    clouds, _ = load_ref_rips_golden()
+    for c in clouds[::5]:
+        dm = orips.euclidean_dm_f32(c)
+        got, _ = orips.model_h1(dm, window=chunk, kernel_steps=True)
+        assert np.array_equal(got, orips.rips_dm(dm, maxdim=1)["dgms"][1])
+    for gen, n, seed in [(torus3d, 170, 8), (blobs3d, 260, 9), (circle2d, 120, 10), (torus3d, 450, 11)]:
+        dm = orips.euclidean_dm_f32(gen(n, np.random.default_rng(seed)))
+        got, st = orips.model_h1(dm, window=chunk, kernel_steps=True)
+        assert np.array_equal(got, orips.rips_dm(dm, maxdim=1)["dgms"][1]), (chunk, n, st)
