@@ -6,7 +6,7 @@
 set -u
 mkdir -p gpurun_out
 export TDA_TEST_UNVALIDATED=1
-timeout 300 python -m pytest tests/test_zz_verify_reducer_gpu.py tests/test_zz_fit_once_gpu.py -q 2>&1 | tail -15 | tee gpurun_out/unvalidated_tests.log
+timeout 400 python -m pytest tests/test_zz_verify_reducer_gpu.py tests/test_zz_fit_once_gpu.py tests/test_rips_h2_gpu.py -q 2>&1 | tail -15 | tee gpurun_out/unvalidated_tests.log
 # the default reducer's own parity tests, run with the new reducer selected (bit-exact diagrams + simplex pairs)
 TDA_RIPS_REDUCER=verify timeout 300 python -m pytest tests/test_rips_gpu.py -q -x 2>&1 | tail -5 | tee gpurun_out/verify_on_default_tests.log
 for mode in sweep verify; do
