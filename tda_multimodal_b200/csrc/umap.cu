@@ -734,6 +734,135 @@ __global__ void __launch_bounds__(kSgdWarps * 32) sgd_epoch_kernel_v4(float4* __
   }
 }
 
+// EXPERIMENT (off unless TDA_SGD_AGG=1; written after the round's GPU minutes were spent: compiled, never run): the per-epoch
+// kernel with the updates of the slot block's own vertex summed in the warp.  The slot table is row-major -- the 2k slots of
+// source vertex i are consecutive, k with head i and k with tail i (fuzzy_kernel) -- so every fired slot of a block moves
+// vertex i; a segmented shuffle reduction over the (queue-ordered, hence contiguous) lanes of the same block leaves one vector
+// RED per block for vertex i plus one per fired edge for the far endpoint: ~1.1 instead of 2 atomics per fired edge, on a
+// stage that is bound by the L2 atomic rate.  Same schedule, RNG keys and update rule; fit (move_other) only.
+__global__ void __launch_bounds__(kSgdWarps * 32) sgd_epoch_kernel_v4_agg(float4* __restrict__ Y, const int* __restrict__ head,
+                                                                          const int* __restrict__ tail, const float* __restrict__ eps_arr, int slots,
+                                                                          int n, int twok, int epoch, float a, float b, float gamma, float alpha,
+                                                                          float nsr, uint64_t seed) {
+  __shared__ int s_queue[kSgdWarps][kSgdSlotsPerLane * 32];
+  const int p = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int base = (blockIdx.x * kSgdWarps + warp) * (kSgdSlotsPerLane * 32);
+  if (base >= slots) return;
+  int* queue = s_queue[warp];
+  int count = 0;
+#pragma unroll
+  for (int i = 0; i < kSgdSlotsPerLane; ++i) {
+    const int e = base + i * 32 + lane;
+    bool fire = false;
+    if (e < slots) {
+      const float eps = eps_arr[(size_t)p * slots + e];
+      if (eps > 0.f) {
+        const int q = (int)floorf((float)epoch / eps);
+        fire = !(q < 1 || q <= (int)floorf((float)(epoch - 1) / eps));
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, fire);
+    if (fire) queue[count + __popc(bal & ((1u << lane) - 1))] = e;
+    count += __popc(bal);
+  }
+  __syncwarp();
+  float4* Yp = Y + (size_t)p * n;
+  for (int q0 = 0; q0 < count; q0 += 32) {   // (warp uniform: every lane takes part in the shuffles)
+    const int qi = q0 + lane;
+    const bool act = qi < count;
+    int own = -1 - lane;                     // vertex of the slot block (distinct negative keys for idle lanes)
+    float own_upd[3] = {0.f, 0.f, 0.f};
+    if (act) {
+      const int e = queue[qi];
+      const float eps = eps_arr[(size_t)p * slots + e];
+      const int q = (int)floorf((float)epoch / eps);
+      const int j = head[(size_t)p * slots + e], kk = tail[(size_t)p * slots + e];
+      const float epsn = eps / nsr;
+      int tot = (int)floorf((float)epoch / epsn) - 1;
+      if (q > 1) {
+        const int prev = (int)ceilf((float)(q - 1) * eps);
+        tot -= (int)floorf((float)prev / epsn) - 1;
+      }
+      float4 n4[kSgdNegBatch];
+#pragma unroll
+      for (int u = 0; u < kSgdNegBatch; ++u) {
+        if (u < tot) {
+          const uint32_t r = mix32(seed ^ ((uint64_t)p << 52) ^ ((uint64_t)e << 20) ^ ((uint64_t)epoch << 4) ^ (uint64_t)u ^ ((uint64_t)u << 40));
+          n4[u] = __ldcg(Yp + (int)(r % (uint32_t)n));
+        }
+      }
+      const float4 c4 = __ldcg(Yp + j), o4 = __ldcg(Yp + kk);
+      float cur[3] = {c4.x, c4.y, c4.z};
+      const float oth[3] = {o4.x, o4.y, o4.z};
+      float delta[3] = {0.f, 0.f, 0.f}, dt[3];
+      float d2 = 0.f;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) { const float t = cur[d] - oth[d]; d2 += t * t; }
+      float g = 0.f;
+      if (d2 > 0.f) {
+        const float pw = __powf(d2, b - 1.f);
+        g = (-2.f * a * b * pw) / (a * pw * d2 + 1.f);
+      }
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const float gd = clip4(g * (cur[d] - oth[d])) * alpha;
+        cur[d] += gd; delta[d] += gd; dt[d] = -gd;
+      }
+      auto repel = [&](const float4& nn) {
+        const float on[3] = {nn.x, nn.y, nn.z};
+        float dn = 0.f;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { const float t = cur[d] - on[d]; dn += t * t; }
+        if (dn > 0.f) {
+          const float gn = (2.f * gamma * b) / ((0.001f + dn) * (a * __powf(dn, b) + 1.f));
+          if (gn > 0.f) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              const float gd = clip4(gn * (cur[d] - on[d])) * alpha;
+              cur[d] += gd; delta[d] += gd;
+            }
+          }
+        }
+      };
+#pragma unroll
+      for (int u = 0; u < kSgdNegBatch; ++u)
+        if (u < tot) repel(n4[u]);
+      for (int sidx = kSgdNegBatch; sidx < tot; ++sidx) {
+        const uint32_t r = mix32(seed ^ ((uint64_t)p << 52) ^ ((uint64_t)e << 20) ^ ((uint64_t)epoch << 4) ^ (uint64_t)sidx ^ ((uint64_t)sidx << 40));
+        repel(__ldcg(Yp + (int)(r % (uint32_t)n)));
+      }
+      // the block's own vertex collects in the warp, the far endpoint is updated directly
+      const int blk = e / twok;
+      if (j == blk) {
+        own = blk;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) own_upd[d] = delta[d];
+        atomicAdd(Yp + kk, make_float4(dt[0], dt[1], dt[2], 0.f));
+      } else if (kk == blk) {
+        own = blk;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) own_upd[d] = dt[d];
+        atomicAdd(Yp + j, make_float4(delta[0], delta[1], delta[2], 0.f));
+      } else {   // (not produced by fuzzy_kernel; handled like the plain kernel)
+        atomicAdd(Yp + kk, make_float4(dt[0], dt[1], dt[2], 0.f));
+        atomicAdd(Yp + j, make_float4(delta[0], delta[1], delta[2], 0.f));
+      }
+    }
+    // segmented inclusive sum over equal keys (contiguous lanes), last lane of a segment writes
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int ko = __shfl_up_sync(0xffffffffu, own, off);
+      const float v0 = __shfl_up_sync(0xffffffffu, own_upd[0], off);
+      const float v1 = __shfl_up_sync(0xffffffffu, own_upd[1], off);
+      const float v2 = __shfl_up_sync(0xffffffffu, own_upd[2], off);
+      if (lane >= off && ko == own) { own_upd[0] += v0; own_upd[1] += v1; own_upd[2] += v2; }
+    }
+    const int knext = __shfl_down_sync(0xffffffffu, own, 1);
+    if (own >= 0 && (lane == 31 || knext != own)) atomicAdd(Yp + own, make_float4(own_upd[0], own_upd[1], own_upd[2], 0.f));
+  }
+}
+
 // EXPERIMENT (off unless TDA_SGD_CLOUD=1): one CTA per cloud, the whole optimisation in ONE launch -- the embedding (16 B
 // per point) lives in shared memory, updates are shared-memory float atomics, epochs are separated by __syncthreads(), and
 // nothing but the read-only slot table (eps, head, tail) leaves the SM.  Same schedule, RNG keys and update rule as the
@@ -998,10 +1127,17 @@ extern "C" int tda_umap_sgd(float* Y, const float* Y_other, const int32_t* head,
       return TDA_OK;
     }
     if (!move_other) pack4_kernel<<<(unsigned)((np_t + 255) / 256), 256, 0, stream>>>(Y_other, Yt4, np_t);
+    const char* agg_env = getenv("TDA_SGD_AGG");
+    const bool agg_mode = agg_env && agg_env[0] == '1' && move_other && n_head == n_tail && slots % n_head == 0 && (slots / n_head) % 2 == 0;
     for (int ep = 0; ep < n_epochs; ++ep) {
       const float alpha = ep == 0 ? alpha0 : alpha0 * (1.f - (float)(ep - 1) / (float)n_epochs);
       const int per_block = kSgdWarps * kSgdSlotsPerLane * 32;
       dim3 g4((slots + per_block - 1) / per_block, batch);
+      if (agg_mode) {
+        sgd_epoch_kernel_v4_agg<<<g4, kSgdWarps * 32, 0, stream>>>(Yh4, head, tail, eps, slots, n_head, slots / n_head, ep, a, b, gamma, alpha,
+                                                                   negative_sample_rate, seed);
+        continue;
+      }
       sgd_epoch_kernel_v4<<<g4, kSgdWarps * 32, 0, stream>>>(Yh4, Yt4, head, tail, eps, slots, n_head, n_tail, ep, a, b, gamma, alpha,
                                                              negative_sample_rate, move_other, seed);
     }

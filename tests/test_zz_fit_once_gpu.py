@@ -25,3 +25,20 @@ def test_fit_once_transform_many_single_rank():
         want = orips.ripser(Y, maxdim=1)["dgms"]
         assert np.array_equal(dgms[l][0], want[0]) and np.array_equal(dgms[l][1], want[1])
     assert trustworthiness(X[0].cpu().numpy(), emb[0].cpu().numpy(), n_neighbors=10, metric="cosine") > 0.85
+
+
+def test_sgd_aggregated_atomics_matches_plain_kernel(monkeypatch):
+    """TDA_SGD_AGG=1 (updates of a slot block's own vertex summed in the warp: ~1.1 instead of 2 atomics per fired edge) against
+    the plain per-epoch kernel: same schedule and samples, so the embeddings must be equally trustworthy."""
+    import torch
+    from sklearn.manifold import trustworthiness
+    from tda_multimodal_b200 import umap_, workloads
+    X = workloads.c3_layers(layers=[0, 5, 20, 31], n=500, d=256)
+    Xd = torch.from_numpy(X).cuda()
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("TDA_SGD_AGG", mode)
+        Y = umap_.umap_fit_batch(Xd, n_neighbors=15, n_components=3, metric="cosine", random_state=42).cpu().numpy()
+        assert np.isfinite(Y).all() and np.abs(Y).max() < 100
+        out[mode] = [trustworthiness(X[i], Y[i], n_neighbors=10, metric="cosine") for i in range(4)]
+    assert min(out["1"]) > 0.8 and np.mean(out["1"]) >= np.mean(out["0"]) - 0.02, out
