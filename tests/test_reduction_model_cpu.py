@@ -62,3 +62,26 @@ def test_kernel_step_model_equals_oracle(chunk):
         dm = orips.euclidean_dm_f32(gen(n, np.random.default_rng(seed)))
         got, st = orips.model_h1(dm, window=chunk, kernel_steps=True)
         assert np.array_equal(got, orips.rips_dm(dm, maxdim=1)["dgms"][1]), (chunk, n, st)
+
+
+def test_models_on_ties_and_duplicates():
+    """Grid points (many equal edge lengths, duplicate points), circles and rounded Gaussians: all three model variants against
+    the oracle (values compared as multisets where equal diameters leave the pair order open)."""
+    rng = np.random.default_rng(123)
+    for trial in range(80):
+        n, dim = int(rng.integers(5, 70)), int(rng.integers(1, 4))
+        kind = trial % 4
+        if kind == 0:
+            X = rng.normal(size=(n, dim)).astype(np.float32)
+        elif kind == 1:
+            X = rng.integers(0, 5, size=(n, dim)).astype(np.float32)
+        elif kind == 2:
+            t = rng.uniform(0, 2 * np.pi, n)
+            X = np.c_[np.cos(t), np.sin(t)].astype(np.float32)
+        else:
+            X = np.round(rng.normal(size=(n, dim)) * 3).astype(np.float32) / 3
+        dm = orips.euclidean_dm_f32(X)
+        want = sorted(map(tuple, orips.rips_dm(dm, maxdim=1)["dgms"][1]))
+        for kw in (dict(), dict(window=16), dict(window=8, kernel_steps=True), dict(window=512, kernel_steps=True)):
+            got, _ = orips.model_h1(dm, **kw)
+            assert sorted(map(tuple, got)) == want, (trial, kind, n, kw)
