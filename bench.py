@@ -320,11 +320,11 @@ def run_b200(a):
         try:
             dm = pipeline.pdist_lowdim(torch.from_numpy(out2["embedding"]).to(dev))
             st = pipeline.rips_batch(dm, maxdim=1, want_stats=True)
-            extra["reduce_rows"] = float(sum(r["stats"]["pushes"] for r in st)) * a.steps
-            extra["reduce_heavy_rows"] = float(sum(r["stats"]["ext_edges"] for r in st)) * a.steps
-            names = {"columns": "columns", "apparent": "apparent_pairs", "reduced": "reduced_columns", "additions": "column_additions",
-                     "pushes": "rows_streamed", "ext_edges": "heavy_rows", "pops": "pivots"}
-            extra["rips_stats_sum"] = {v: int(sum(r["stats"][k] for r in st)) for k, v in names.items()}
+            rows_key = "rows_substituted" if "rows_substituted" in st[0]["stats"] else "rows_streamed"
+            extra["reduce_rows"] = float(sum(r["stats"][rows_key] for r in st)) * a.steps
+            extra["reduce_heavy_rows"] = float(sum(r["stats"]["heavy_rows"] for r in st)) * a.steps
+            extra["rips_stats_sum"] = {k: int(sum(r["stats"][k] for r in st)) for k in st[0]["stats"] if not k.startswith(("cyc_", "spare", "max_v"))}
+            extra["rips_reducer"] = _lib.rips_reducer()
         except Exception as ex:  # stats are optional evidence
             extra["stats_error"] = repr(ex)
         n_done = a.layers * a.steps

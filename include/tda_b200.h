@@ -12,7 +12,8 @@
  *  - all problems of one call have the same shape; `batch` = number of independent problems
  *    (layers x bootstrap resamples), laid out contiguously [batch, ...];
  *  - return value 0 = success, negative = error (tda_last_error() gives the text; thread local);
- *  - the library keeps no global state besides the error string; scratch memory is the caller's
+ *  - the library keeps no global state besides the thread-local error string / launch counter / stage timer and the
+ *    process-wide tuning options of tda_set_option (it reads no environment variables); scratch memory is the caller's
  *    workspace `ws` (size from the matching *_workspace_bytes call).
  */
 #ifndef TDA_B200_H
@@ -33,6 +34,14 @@ const char* tda_last_error(void);
 /* number of kernels launched by this library in the calling thread since the last reset (bench.py gpu_launches) */
 int64_t tda_launch_count(void);
 void tda_launch_count_reset(void);
+/* Tuning options (process-wide integers; defaults in parentheses).  Unknown names return TDA_ERR_INVALID / -1.
+ *   rips_reducer (0): residual H1 reducer -- 0 "sweep2" substitute by rank + verify by window, 1 row sweep with a sequential
+ *                     resolver warp, 2 row sweep substitute-then-verify per 512-row chunk, 3 key bitset (any n)
+ *   rips_w0 (1024), rips_wsparse (8192), rips_wmax (32768), rips_dense_min (64), rips_dense_div (8): sweep2 window schedule
+ *   sweep_exclusive (0), sgd_mode (0: per-epoch kernel, 1: one CTA per cloud, 2: warp-aggregated), knn_loads (8),
+ *   debug_sync (0), h2_stats (0) */
+int tda_set_option(const char* name, long long value);
+long long tda_get_option(const char* name);
 
 /* Optional stage timer (off by default): when enabled, every entry point brackets its stages with CUDA events on
  * the stream it launches on; tda_stage_timing_read synchronises those events and returns the accumulated
@@ -139,7 +148,8 @@ int tda_pdist_lowdim(const float* pts, int n, int d, int batch, float* dm, void*
 /* tda_rips: Vietoris-Rips persistence (Z/2) of `batch` dense distance matrices, H0 and H1.
  *   dm      [batch,n,n] float32 symmetric, zero diagonal
  *   thresh  +inf => per-problem enclosing radius min_i max_j dm (ripser's default)
- *   maxdim  0 or 1 (2 is not implemented in this round: returns TDA_ERR_UNSUPPORTED)
+ *   maxdim  0 or 1 (H2 is the separate call tda_rips_h2 on top of a finished maxdim=1 run; maxdim >= 2 here returns
+ *           TDA_ERR_UNSUPPORTED)
  *   h0_pairs [batch,n,2] float32: rows (0,death) ascending, then one (0,+inf) per component
  *   h0_simplex [batch,n,2] int64 or NULL: (birth vertex or -1, death edge index i(i-1)/2+j or -1)
  *   h1_pairs [batch,cap1,2] float32: (birth,death) in ripser's emission order (birth descending)
@@ -171,11 +181,14 @@ int tda_rips_launch(const float* dm, int n, int batch, int maxdim, float thresh,
 size_t tda_rips_h2_workspace_bytes(int n, int batch, int cap2, size_t pool_bytes, size_t far_bytes);
 int tda_rips_h2(const void* ws1, int n, int batch, int cap1, size_t pool_bytes1, float* h2_pairs, int cap2, int32_t* counts2,
                 void* ws2, size_t ws2_bytes, size_t pool_bytes2, size_t far_bytes, void* stream);
-/* device statistics of the last tda_rips call on this workspace: [batch,16] int64 (row-sweep reducer):
- * columns (non-MST edges <= thresh), apparent pairs, reduced columns, column additions, rows streamed through the filter,
- * pivots, restarts of a chunk (new vertex touched / reduced column added), largest |V|, then SM cycles of CTA thread 0 in:
- * filter, (number of row groups), resolve||produce phase, reduced-column additions, flip write-out + patch phase,
- * dense-mode switches; edges added through reduced columns, heavy rows */
+/* device statistics of the last tda_rips call on this workspace: [batch, TDA_RIPS_STATS] int64.  For the default reducer (sweep2):
+ *  0 columns (non-MST edges <= thresh), 1 apparent pairs, 2 reduced columns, 3 column additions (flips kept + reduced columns
+ *  added), 4 rows substituted, 5 non-apparent pivots (events + deaths), 6 windows, 7 largest |V|, 8..13 SM cycles of CTA
+ *  thread 0 in: substitution round 1, later rounds, apply + heavy lists, verification, decision + events, Pm moves + column
+ *  finalisation; 14 edges added through reduced columns, 15 heavy rows verified, 16 substitution rounds after the first,
+ *  17 rows handled in those rounds, 18 rows of Pm moved, 19 columns that went dense, 20 spurious stops, 21 flips undone.
+ *  (reducers 1-3 fill 0..15 with their own counters: rows streamed, pivots, restarts, ...) */
+#define TDA_RIPS_STATS 24
 int tda_rips_stats(const void* ws, int n, int batch, int maxdim, int cap1, size_t pool_bytes, int64_t* stats_host);
 
 #ifdef __cplusplus

@@ -140,7 +140,7 @@ def ripser(X, maxdim=1, thresh=np.inf, coeff=2, distance_matrix=False, do_cocycl
 _MODEL = None
 
 
-def model_h1(dm, window=None, kernel_steps=False):
+def model_h1(dm, window=None, kernel_steps=False, pend=None, percol=False, modes=None):
     """H1 diagram of a float32 distance matrix by the "substitute, then verify" model (oracle/rips_propagate_model.cpp): a CPU
     study of the next GPU reducer, checked against `rips_dm` in tests/test_reduction_model_cpu.py.  window=None: the whole view
     above the cursor is propagated on every pass; window=k: the kernel-shaped variant (windows of k ranks: substitute, verify,
@@ -157,12 +157,38 @@ def model_h1(dm, window=None, kernel_steps=False):
         lib.rips_model_h1_windowed.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
         lib.rips_model_h1_kernel.restype = ctypes.c_int64
         lib.rips_model_h1_kernel.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+        lib.rips_model_h1_pend.restype = ctypes.c_int64
+        lib.rips_model_h1_pend.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                           ctypes.c_void_p, ctypes.c_int64]
+        lib.rips_model_h1_modes.restype = ctypes.c_int64
+        lib.rips_model_h1_modes.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 6 + [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
         _MODEL = lib
     dm = np.ascontiguousarray(dm, dtype=np.float32)
     n = dm.shape[0]
     cap = max(16, n * n // 4)
     out = np.zeros((cap, 2), dtype=np.float64)
-    st = np.zeros(10, dtype=np.int64)
+    st = np.zeros(16, dtype=np.int64)
+    if modes is not None:   # (w0, wsparse, wmax, dense_min, dense_div): the two-mode control flow of Sweeper2 (csrc/rips.cu)
+        k = int(_MODEL.rips_model_h1_modes(dm.ctypes.data, n, *[int(v) for v in modes], out.ctypes.data, cap, st.ctypes.data))
+        names = ["residual_columns", "apparent_edges", "events", "flips", "flips_undone", "heavy_rows_verified", "windows", "rounds",
+                 "spurious_rows", "rows_substituted", "rows_in_late_rounds", "pm_rows_moved", "dense_columns", "exact_row_checks"]
+        if k < 0:
+            raise RuntimeError(f"model_h1: modes model failed ({k})")
+        return out[:k].copy(), dict(zip(names, st[:len(names)].tolist()))
+    if pend is not None:   # (w0, wmax): growing windows, substitution over all apparent rows, superset-mask verification (the cluster reducer)
+        pc = np.zeros((n * n // 4 + 16, 6), dtype=np.int64) if percol else None
+        k = int(_MODEL.rips_model_h1_pend(dm.ctypes.data, n, int(pend[0]), int(pend[1]), out.ctypes.data, cap, st.ctypes.data,
+                                          pc.ctypes.data if percol else None, len(pc) if percol else 0))
+        names = ["residual_columns", "apparent_edges", "events", "flips", "flips_undone", "heavy_rows_verified", "windows", "rounds",
+                 "spurious_stops", "rows_substituted", "max_window", "pm_rows_moved"]
+        if k == -2:
+            raise RuntimeError("model_h1: substitution made no progress")
+        if k < 0:
+            raise RuntimeError("model_h1: pair buffer too small")
+        stats = dict(zip(names, st[:len(names)].tolist()))
+        if percol:
+            stats["columns"] = pc[:stats["residual_columns"]].copy()
+        return out[:k].copy(), stats
     if window is None:
         k = int(_MODEL.rips_model_h1(dm.ctypes.data, n, out.ctypes.data, cap, st.ctypes.data))
         names = ["residual_columns", "apparent_edges", "events", "propagated_flips", "heavy_rows_verified", "max_v", "passes", "apparent_graph_depth",

@@ -399,4 +399,306 @@ int64_t rips_model_h1_kernel(const float* dist, int n, int chunk, double* pairs_
   return n_pairs;
 }
 
+
+// The formulation the cluster reducer (csrc/rips.cu, ClusterSweeper) implements.  Differences to the kernel-step model above:
+//   * windows grow (w0, doubling up to wmax after every clean window, back to w0 after a failure);
+//   * the substitution runs over EVERY apparent row of the window (x by rank: x_M = x[pa] ^ x[pb]; no touched filter, no
+//     re-filter passes), in rounds: a row waits for a parent that is an apparent row of the same window;
+//   * verification uses the SUPERSET mask Pend[c] & Pend[d] (Pend = adjacency of all edges below the window's end) instead of
+//     the exact lune.  If the window leaves V a cocycle of the complex at the window's end, every row passes; a failing bit
+//     (row M, vertex w) under the superset mask belongs to the triangle {c, d, w} whose own row max(M, rank(c,w), rank(d,w))
+//     lies in the window, so the smallest failing row Mf bounds the first true failure from below.  The flips above Mf are
+//     undone and row Mf is verified with its exact lune: non-empty -> event at (Mf, highest vertex); empty -> rows <= Mf are
+//     settled (spurious stop) and the sweep continues behind it.
+// stats: [12] residual columns, apparent edges, events, flips, flips undone, heavy rows verified, windows, substitution rounds,
+//             spurious stops, rows substituted, largest window reached, rows of Pm moved (set/cleared)
+// percol (optional): [cap_cols, 6] per residual column in processing order: birth rank, last row reached, windows, rounds,
+//             heavy rows, events
+int64_t rips_model_h1_pend(const float* dist, int n, int w0, int wmax, double* pairs_out, int64_t cap, int64_t* stats,
+                           int64_t* percol, int64_t cap_cols) {
+  Model m;
+  std::vector<int64_t> residual; int64_t n_app = 0; int maxdepth = 0;
+  build_model(m, dist, n, residual, n_app, maxdepth);
+  const int64_t T = m.T;
+  const int W = (n + 63) / 64;
+  if (w0 < 1) w0 = 1;
+  if (wmax < w0) wmax = w0;
+  std::vector<uint8_t> x(T, 0);
+  std::vector<uint64_t> X((size_t)n * W, 0), Pm((size_t)n * W, 0);
+  int64_t p_pos = 0;   // Pm = adjacency of the edges with rank < p_pos
+  std::vector<uint8_t> touched(n, 0);
+  std::unordered_map<int64_t, int> owner;
+  std::vector<std::vector<int>> Vs;
+  int64_t n_pairs = 0, events = 0, flips = 0, undone = 0, heavy_rows = 0, windows = 0, rounds = 0, spurious = 0, subst_rows = 0, maxwin = 0, pm_moved = 0;
+  std::vector<int64_t> members;
+  auto flip = [&](int64_t e) {
+    x[e] ^= 1; const int a = m.ea[e], b = m.eb[e];
+    X[(size_t)a * W + (b >> 6)] ^= 1ull << (b & 63); X[(size_t)b * W + (a >> 6)] ^= 1ull << (a & 63);
+    touched[a] = touched[b] = 1;
+    if (x[e]) members.push_back(e);
+  };
+  auto p_move = [&](int64_t target) {
+    while (p_pos < target) { const int a = m.ea[p_pos], b = m.eb[p_pos]; Pm[(size_t)a * W + (b >> 6)] |= 1ull << (b & 63); Pm[(size_t)b * W + (a >> 6)] |= 1ull << (a & 63); ++p_pos; ++pm_moved; }
+    while (p_pos > target) { --p_pos; const int a = m.ea[p_pos], b = m.eb[p_pos]; Pm[(size_t)a * W + (b >> 6)] &= ~(1ull << (b & 63)); Pm[(size_t)b * W + (a >> 6)] &= ~(1ull << (a & 63)); ++pm_moved; }
+  };
+  int64_t col_no = 0;
+  for (int64_t ci = (int64_t)residual.size() - 1; ci >= 0; --ci, ++col_no) {
+    const int64_t b = residual[ci];
+    members.clear();
+    std::fill(touched.begin(), touched.end(), 0);
+    flip(b);
+    int64_t pos = b + 1;
+    int64_t win = w0;
+    bool essential = false; int64_t pivM = -1; int pivw = -1;
+    int64_t c_windows = 0, c_rounds = 0, c_heavy = 0, c_events = 0;
+    for (;;) {
+      if (pos >= T) { essential = true; break; }
+      const int64_t hi = std::min<int64_t>(T, pos + win);
+      ++windows; ++c_windows; maxwin = std::max(maxwin, hi - pos);
+      // (A) substitution over every apparent row of the window, in dependency rounds
+      std::vector<int64_t> fliplist;
+      {
+        std::vector<uint8_t> done((size_t)(hi - pos), 0);
+        std::vector<int64_t> pending;
+        for (int64_t M = pos; M < hi; ++M) { if (m.apex[M] < 0) done[M - pos] = 1; else pending.push_back(M); }
+        subst_rows += (int64_t)pending.size();
+        while (!pending.empty()) {
+          ++rounds; ++c_rounds;
+          std::vector<int64_t> can, wait;
+          for (int64_t M : pending) {
+            const int64_t ra = m.pa[M], rb = m.pb[M];
+            if ((ra >= pos && !done[ra - pos]) || (rb >= pos && !done[rb - pos])) wait.push_back(M); else can.push_back(M);
+          }
+          if (can.empty()) return -2;
+          for (int64_t M : can) {
+            const uint8_t want = x[m.pa[M]] ^ x[m.pb[M]];
+            if (want != x[M]) { flip(M); ++flips; fliplist.push_back(M); }
+          }
+          for (int64_t M : can) done[M - pos] = 1;
+          pending.swap(wait);
+        }
+      }
+      // (B) verification of the heavy apparent rows against the superset mask Pend[c] & Pend[d]
+      p_move(hi);
+      int64_t Mf = -1;
+      for (int64_t M = pos; M < hi; ++M) {
+        if (m.apex[M] < 0) continue;
+        const int c = m.ea[M], d = m.eb[M];
+        if (!touched[c] && !touched[d]) continue;
+        ++heavy_rows; ++c_heavy;
+        const uint64_t xm = x[M] ? ~0ull : 0ull;
+        bool bad = false;
+        for (int k = 0; k < W && !bad; ++k)
+          bad = ((xm ^ X[(size_t)c * W + k] ^ X[(size_t)d * W + k]) & Pm[(size_t)c * W + k] & Pm[(size_t)d * W + k]) != 0;
+        if (bad) { Mf = M; break; }   // (the kernel takes the minimum over all failing rows; in order, the first one is it)
+      }
+      if (Mf < 0) { pos = hi; win = std::min<int64_t>(2 * win, wmax); continue; }
+      // (C) stop at Mf: undo the flips above it, verify the row exactly
+      for (int64_t e : fliplist) if (e > Mf) { flip(e); ++undone; }
+      win = w0;
+      {
+        const int c = m.ea[Mf], d = m.eb[Mf];
+        const int* Rc = &m.R[(size_t)c * n]; const int* Rd = &m.R[(size_t)d * n];
+        pivM = -1;
+        for (int w = n - 1; w >= 0; --w) {
+          if (!(Rc[w] < Mf && Rd[w] < Mf)) continue;
+          const int bit = (int)x[Mf] ^ (int)((X[(size_t)c * W + (w >> 6)] >> (w & 63)) & 1) ^ (int)((X[(size_t)d * W + (w >> 6)] >> (w & 63)) & 1);
+          if (bit) { pivM = Mf; pivw = w; break; }
+        }
+      }
+      if (pivM < 0) { ++spurious; pos = Mf + 1; continue; }
+      const int64_t key = pivM * (int64_t)n + (n - 1 - pivw);
+      auto it = owner.find(key);
+      if (it == owner.end()) break;   // death
+      ++events; ++c_events;
+      for (int e : Vs[it->second]) flip(e);
+      pos = pivM;   // this row again (its substitution is a no-op; the handled vertex is even now)
+    }
+    if (percol && col_no < cap_cols) {
+      int64_t* o = percol + col_no * 6;
+      o[0] = b; o[1] = essential ? T : pivM; o[2] = c_windows; o[3] = c_rounds; o[4] = c_heavy; o[5] = c_events;
+    }
+    std::vector<int> V;
+    for (int64_t e : members) if (x[e]) { V.push_back((int)e); flip(e); }
+    std::sort(V.begin(), V.end()); V.erase(std::unique(V.begin(), V.end()), V.end());
+    maxwin = std::max<int64_t>(maxwin, 0);
+    const float birth = m.len[b];
+    if (essential) {
+      if (n_pairs >= cap) return -1;
+      pairs_out[2 * n_pairs] = birth; pairs_out[2 * n_pairs + 1] = INFINITY; ++n_pairs;
+    } else {
+      const float death = m.len[pivM];
+      owner.emplace(pivM * (int64_t)n + (n - 1 - pivw), (int)Vs.size());
+      Vs.push_back(std::move(V));
+      if (death > birth) {
+        if (n_pairs >= cap) return -1;
+        pairs_out[2 * n_pairs] = birth; pairs_out[2 * n_pairs + 1] = death; ++n_pairs;
+      }
+    }
+  }
+  if (stats) {
+    stats[0] = (int64_t)residual.size(); stats[1] = n_app; stats[2] = events; stats[3] = flips; stats[4] = undone; stats[5] = heavy_rows;
+    stats[6] = windows; stats[7] = rounds; stats[8] = spurious; stats[9] = subst_rows; stats[10] = maxwin; stats[11] = pm_moved;
+  }
+  return n_pairs;
+}
+
+
+// rips_model_h1_pend with the two modes of the kernel (csrc/rips.cu, Sweeper2):
+//   sparse mode (every column starts in it): windows w0, doubling up to wsparse; exact lunes from the rank rows, so the first
+//       failing (row, vertex) of the window is the event; after an event the window size falls back to w0;
+//   dense mode (entered when a window holds >= max(dense_min, rows / dense_div) heavy rows): Pm is moved to the window's end and
+//       the superset mask is used; windows double up to wmax; the failing rows are examined in ascending order with the exact
+//       lune until one is a true failure (the others are spurious stops: nothing is undone, nothing re-substituted); after an
+//       event the window keeps its END (Pm only ever moves forward inside a column) and restarts at the event's row.
+// stats: [14] residual columns, apparent edges, events, flips, flips undone, heavy rows verified, windows, substitution rounds,
+//             spurious rows examined, rows substituted, rows handled in rounds >= 2, rows of Pm moved, dense columns, exact row checks
+int64_t rips_model_h1_modes(const float* dist, int n, int w0, int wsparse, int wmax, int dense_min, int dense_div, double* pairs_out,
+                            int64_t cap, int64_t* stats) {
+  Model m;
+  std::vector<int64_t> residual; int64_t n_app = 0; int maxdepth = 0;
+  build_model(m, dist, n, residual, n_app, maxdepth);
+  const int64_t T = m.T;
+  const int W = (n + 63) / 64;
+  std::vector<uint8_t> x(T, 0);
+  std::vector<uint64_t> X((size_t)n * W, 0), Pm((size_t)n * W, 0);
+  int64_t p_pos = 0;
+  std::vector<uint8_t> touched(n, 0);
+  std::unordered_map<int64_t, int> owner;
+  std::vector<std::vector<int>> Vs;
+  int64_t n_pairs = 0, events = 0, flips = 0, undone = 0, heavy_rows = 0, windows = 0, rounds = 0, spurious = 0, subst_rows = 0, late_rows = 0, pm_moved = 0,
+          dense_cols = 0, exact_checks = 0;
+  std::vector<int64_t> members;
+  auto flip = [&](int64_t e) {
+    x[e] ^= 1; const int a = m.ea[e], b = m.eb[e];
+    X[(size_t)a * W + (b >> 6)] ^= 1ull << (b & 63); X[(size_t)b * W + (a >> 6)] ^= 1ull << (a & 63);
+    touched[a] = touched[b] = 1;
+    if (x[e]) members.push_back(e);
+  };
+  auto p_move = [&](int64_t target) {
+    const int64_t dist_rows = target > p_pos ? target - p_pos : p_pos - target;
+    if (dist_rows * 32 > (int64_t)n * n) {   // rebuild from the rank matrix (counted as n*n/32 rows)
+      std::fill(Pm.begin(), Pm.end(), 0);
+      for (int64_t r = 0; r < target; ++r) { const int a = m.ea[r], b = m.eb[r]; Pm[(size_t)a * W + (b >> 6)] |= 1ull << (b & 63); Pm[(size_t)b * W + (a >> 6)] |= 1ull << (a & 63); }
+      p_pos = target; pm_moved += (int64_t)n * n / 32;
+      return;
+    }
+    while (p_pos < target) { const int a = m.ea[p_pos], b = m.eb[p_pos]; Pm[(size_t)a * W + (b >> 6)] |= 1ull << (b & 63); Pm[(size_t)b * W + (a >> 6)] |= 1ull << (a & 63); ++p_pos; ++pm_moved; }
+    while (p_pos > target) { --p_pos; const int a = m.ea[p_pos], b = m.eb[p_pos]; Pm[(size_t)a * W + (b >> 6)] &= ~(1ull << (b & 63)); Pm[(size_t)b * W + (a >> 6)] &= ~(1ull << (a & 63)); ++pm_moved; }
+  };
+  // exact check of row M: highest failing vertex, or -1
+  auto exact_row = [&](int64_t M) {
+    ++exact_checks;
+    const int c = m.ea[M], d = m.eb[M];
+    const int* Rc = &m.R[(size_t)c * n]; const int* Rd = &m.R[(size_t)d * n];
+    for (int w = n - 1; w >= 0; --w) {
+      if (!(Rc[w] < M && Rd[w] < M)) continue;
+      const int bit = (int)x[M] ^ (int)((X[(size_t)c * W + (w >> 6)] >> (w & 63)) & 1) ^ (int)((X[(size_t)d * W + (w >> 6)] >> (w & 63)) & 1);
+      if (bit) return w;
+    }
+    return -1;
+  };
+  for (int64_t ci = (int64_t)residual.size() - 1; ci >= 0; --ci) {
+    const int64_t b = residual[ci];
+    members.clear();
+    std::fill(touched.begin(), touched.end(), 0);
+    flip(b);
+    int64_t pos = b + 1, win = w0, hi = -1;   // hi >= 0: the window's end is kept (dense mode after an event)
+    bool dense = false;
+    bool essential = false; int64_t pivM = -1; int pivw = -1;
+    for (;;) {
+      if (pos >= T) { essential = true; break; }
+      if (hi < 0 || hi <= pos) hi = std::min<int64_t>(T, pos + win);
+      ++windows;
+      const size_t mark = members.size();   // (the kernel: position in the V list where this window's flips start)
+      std::vector<int64_t> fliplist;
+      {
+        std::vector<uint8_t> done((size_t)(hi - pos), 0);
+        std::vector<int64_t> pending;
+        for (int64_t M = pos; M < hi; ++M) if (m.apex[M] >= 0) pending.push_back(M);
+        subst_rows += (int64_t)pending.size();
+        bool first = true;
+        while (!pending.empty()) {
+          ++rounds;
+          if (!first) late_rows += (int64_t)pending.size();
+          first = false;
+          std::vector<int64_t> can, wait;
+          for (int64_t M : pending) {
+            const int64_t ra = m.pa[M], rb = m.pb[M];
+            const bool wa = ra >= pos && m.apex[ra] >= 0 && !done[ra - pos], wb = rb >= pos && m.apex[rb] >= 0 && !done[rb - pos];
+            if (wa || wb) wait.push_back(M); else can.push_back(M);
+          }
+          if (can.empty()) return -2;
+          for (int64_t M : can) {
+            const uint8_t want = x[m.pa[M]] ^ x[m.pb[M]];
+            if (want != x[M]) { flip(M); ++flips; fliplist.push_back(M); }
+          }
+          for (int64_t M : can) done[M - pos] = 1;
+          pending.swap(wait);
+        }
+      }
+      (void)mark;
+      // heavy rows of the window
+      std::vector<int64_t> heavy;
+      for (int64_t M = pos; M < hi; ++M) if (m.apex[M] >= 0 && (touched[m.ea[M]] || touched[m.eb[M]])) heavy.push_back(M);
+      if (!dense && (int64_t)heavy.size() >= std::max<int64_t>(dense_min, (hi - pos) / dense_div)) { dense = true; ++dense_cols; }
+      heavy_rows += (int64_t)heavy.size();
+      int64_t evM = -1; int evw = -1;
+      if (!dense) {
+        for (int64_t M : heavy) { const int w = exact_row(M); --exact_checks; if (w >= 0) { evM = M; evw = w; break; } }
+      } else {
+        p_move(hi);
+        std::vector<int64_t> failing;
+        for (int64_t M : heavy) {
+          const int c = m.ea[M], d = m.eb[M];
+          const uint64_t xm = x[M] ? ~0ull : 0ull;
+          bool bad = false;
+          for (int k = 0; k < W && !bad; ++k)
+            bad = ((xm ^ X[(size_t)c * W + k] ^ X[(size_t)d * W + k]) & Pm[(size_t)c * W + k] & Pm[(size_t)d * W + k]) != 0;
+          if (bad) failing.push_back(M);
+        }
+        for (int64_t M : failing) {   // ascending
+          const int w = exact_row(M);
+          if (w >= 0) { evM = M; evw = w; break; }
+          ++spurious;
+        }
+        // all spurious is impossible: a failing bit under the superset mask is a true failure of a row of this window
+        if (!failing.empty() && evM < 0) return -3;
+      }
+      if (evM < 0) { pos = hi; hi = -1; win = std::min<int64_t>(2 * win, dense ? wmax : wsparse); continue; }
+      for (int64_t e : fliplist) if (e > evM) { flip(e); ++undone; }
+      pivM = evM; pivw = evw;
+      const int64_t key = pivM * (int64_t)n + (n - 1 - pivw);
+      auto it = owner.find(key);
+      if (it == owner.end()) break;   // death
+      ++events;
+      for (int e : Vs[it->second]) flip(e);
+      pos = pivM;
+      if (!dense) { win = w0; hi = -1; }
+    }
+    std::vector<int> V;
+    for (int64_t e : members) if (x[e]) { V.push_back((int)e); flip(e); }
+    std::sort(V.begin(), V.end()); V.erase(std::unique(V.begin(), V.end()), V.end());
+    const float birth = m.len[b];
+    if (essential) {
+      if (n_pairs >= cap) return -1;
+      pairs_out[2 * n_pairs] = birth; pairs_out[2 * n_pairs + 1] = INFINITY; ++n_pairs;
+    } else {
+      const float death = m.len[pivM];
+      owner.emplace(pivM * (int64_t)n + (n - 1 - pivw), (int)Vs.size());
+      Vs.push_back(std::move(V));
+      if (death > birth) {
+        if (n_pairs >= cap) return -1;
+        pairs_out[2 * n_pairs] = birth; pairs_out[2 * n_pairs + 1] = death; ++n_pairs;
+      }
+    }
+  }
+  if (stats) {
+    stats[0] = (int64_t)residual.size(); stats[1] = n_app; stats[2] = events; stats[3] = flips; stats[4] = undone; stats[5] = heavy_rows;
+    stats[6] = windows; stats[7] = rounds; stats[8] = spurious; stats[9] = subst_rows; stats[10] = late_rows; stats[11] = pm_moved;
+    stats[12] = dense_cols; stats[13] = exact_checks;
+  }
+  return n_pairs;
+}
+
 }  // extern "C"

@@ -13,6 +13,8 @@ PROTOTYPES = {
     "tda_last_error": (ctypes.c_char_p, []),
     "tda_launch_count": (c_int64, []),
     "tda_launch_count_reset": (None, []),
+    "tda_set_option": (c_int, [ctypes.c_char_p, ctypes.c_longlong]),
+    "tda_get_option": (ctypes.c_longlong, [ctypes.c_char_p]),
     "tda_stage_timing_enable": (None, [c_int]),
     "tda_stage_timing_reset": (None, []),
     "tda_stage_timing_read": (c_int, [c_void_p, c_void_p, c_int]),
@@ -46,6 +48,34 @@ PROTOTYPES = {
 }
 
 TDA_ERR_CAPACITY = -4
+RIPS_STATS = 24   # TDA_RIPS_STATS
+
+# The library itself reads no environment variables; this host glue maps the historical TDA_* variables onto
+# tda_set_option when the library is loaded (scripts/ and the A/B runs in profiles/ use them).
+_REDUCERS = {"sweep2": 0, "sweep": 1, "verify": 2, "bitset": 3}
+_ENV_OPTIONS = {
+    "TDA_RIPS_REDUCER": ("rips_reducer", lambda v: _REDUCERS[v]),
+    "TDA_RIPS_W0": ("rips_w0", int), "TDA_RIPS_WSPARSE": ("rips_wsparse", int), "TDA_RIPS_WMAX": ("rips_wmax", int),
+    "TDA_RIPS_DENSE_MIN": ("rips_dense_min", int), "TDA_RIPS_DENSE_DIV": ("rips_dense_div", int),
+    "TDA_SWEEP_EXCLUSIVE": ("sweep_exclusive", int),
+    "TDA_SGD_CLOUD": ("sgd_mode", lambda v: 1 if v == "1" else 0),
+    "TDA_SGD_AGG": ("sgd_mode", lambda v: 2 if v == "1" else 0),
+    "TDA_SGD_MODE": ("sgd_mode", int),
+    "TDA_KNN_LOADS": ("knn_loads", int), "TDA_DEBUG_SYNC": ("debug_sync", lambda v: 1), "TDA_H2_STATS": ("h2_stats", lambda v: 1),
+}
+
+
+def set_option(name, value):
+    """Process-wide tuning option of the library (include/tda_b200.h: tda_set_option)."""
+    check(lib().tda_set_option(name.encode(), int(value)))
+
+
+def get_option(name):
+    return int(lib().tda_get_option(name.encode()))
+
+
+def rips_reducer():
+    return {v: k for k, v in _REDUCERS.items()}[get_option("rips_reducer")]
 STAGES = ["pdist_prep", "pdist_gemm", "knn_smooth", "fuzzy_graph", "spectral_init", "umap_sgd", "rips_pdist", "rips_edge_sort",
           "rips_h0", "rips_apparent", "rips_reduce"]
 
@@ -82,6 +112,10 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         _lib = l
+        for env, (opt, conv) in _ENV_OPTIONS.items():
+            v = os.environ.get(env)
+            if v not in (None, ""):
+                check(l.tda_set_option(opt.encode(), int(conv(v))))
     return _lib
 
 

@@ -62,9 +62,43 @@ static void stage_collect(StageState& S) {
   S.recs.clear();
   (void)cudaGetLastError();
 }
+
+// ---- tuning options (process-wide; the library reads no environment variables)
+struct OptionDef { const char* name; long long value; };
+static OptionDef g_options[] = {
+    {"rips_reducer", 0},       // 0 sweep2 (substitute by rank, verify by window; default), 1 row sweep with sequential resolver, 2 row sweep substitute-then-verify, 3 key bitset
+    {"rips_w0", 1024},         // sweep2: first window of a column (rows)
+    {"rips_wsparse", 8192},    // sweep2: largest window in sparse mode
+    {"rips_wmax", 32768},      // sweep2: largest window in dense mode (<= 65472)
+    {"rips_dense_min", 64},    // sweep2: a window with >= max(dense_min, rows / dense_div) heavy rows switches the column to dense mode
+    {"rips_dense_div", 8},
+    {"sweep_exclusive", 0},    // reducers 1/2: ask for the whole shared memory of the SM
+    {"sgd_mode", 0},           // 0 per-epoch kernel (float4 atomics), 1 one CTA per cloud, 2 warp-aggregated per-epoch kernel
+    {"knn_loads", 8},          // 16-byte loads per lane in flight in the k <= 16 kNN kernel (8 or 16)
+    {"debug_sync", 0},         // synchronise after every kernel of tda_rips_h2 (fault location)
+    {"h2_stats", 0},           // print the H2 reducer's device counters to stderr
+};
+long long option(const char* name) {
+  for (const OptionDef& o : g_options)
+    if (strcmp(o.name, name) == 0) return o.value;
+  return 0;
+}
 }  // namespace tda
 
-extern "C" int tda_version(void) { return 100; }
+extern "C" int tda_set_option(const char* name, long long value) {
+  if (!name) return tda::set_error(tda::TDA_ERR_INVALID, "tda_set_option: null name");
+  for (tda::OptionDef& o : tda::g_options)
+    if (strcmp(o.name, name) == 0) { o.value = value; return tda::TDA_OK; }
+  return tda::set_error(tda::TDA_ERR_INVALID, "tda_set_option: unknown option '%s'", name);
+}
+extern "C" long long tda_get_option(const char* name) {
+  if (!name) return -1;
+  for (const tda::OptionDef& o : tda::g_options)
+    if (strcmp(o.name, name) == 0) return o.value;
+  return -1;
+}
+
+extern "C" int tda_version(void) { return 200; }
 extern "C" const char* tda_last_error(void) { return tda::tls_error_buffer(); }
 extern "C" int64_t tda_launch_count(void) { return tda::launch_counter(); }
 extern "C" void tda_launch_count_reset(void) { tda::launch_counter() = 0; }

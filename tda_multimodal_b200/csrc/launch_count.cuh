@@ -6,6 +6,7 @@
 namespace tda {
 int64_t& launch_counter();  // defined in capi.cu
 inline void count_launch(int k = 1) { launch_counter() += k; }
+long long option(const char* name);  // tuning options set through tda_set_option (capi.cu)
 
 // stage ids (keep in sync with include/tda_b200.h TDA_STAGE_*)
 enum Stage : int {

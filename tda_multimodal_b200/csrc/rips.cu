@@ -10,10 +10,12 @@
 //                               every non-MST edge with an apex is a zero-persistence apparent pair whose
 //                               coboundary column never needs reducing.
 //   4. residual reduction     : only edges with an EMPTY lune (relative-neighbourhood-graph edges that are
-//                               not in the MST) are reduced, by implicit persistent cohomology over Z/2:
-//                               the working column is a monotone radix heap of triangle keys in a chunked
-//                               global-memory pool, pivots owned by apparent pairs are recognised in O(1)
-//                               from the apex table, pivots owned by reduced columns through a hash map.
+//                               not in the MST) are reduced, by implicit persistent cohomology over Z/2.
+//                               Default: rips_sweep2.cuh (apparent-pair additions as a forward substitution by
+//                               rank, windows verified against the cocycle condition); older reducers kept for
+//                               comparison: the row sweep with a resolver warp / per-chunk verify (Sweeper) and
+//                               the key bitset (Reducer<1>, any n; Reducer<2> is the H2 reducer).  Pivots owned by
+//                               reduced columns are found through a hash map.
 //
 // A triangle is keyed by (rank of its longest edge, opposite vertex): key = M*n + (n-1-w).  Ascending key
 // order refines (diameter asc) and puts faces before cofaces, so it is a valid simplex-wise filtration; the
@@ -36,7 +38,9 @@ constexpr int kRankDiag = 0x7fffffff;
 
 // stats slots
 enum { ST_COLUMNS = 0, ST_APPARENT, ST_REDUCED, ST_ADDITIONS, ST_PUSHES, ST_POPS, ST_EXTENSIONS, ST_MAXV,
-       ST_CYC_EXTRACT, ST_CYC_OWNER, ST_CYC_GEN, ST_CYC_BADD, ST_CYC_EXT, ST_CYC_FINAL, ST_BADD_EDGES, ST_EXT_EDGES, ST_N };
+       ST_CYC_EXTRACT, ST_CYC_OWNER, ST_CYC_GEN, ST_CYC_BADD, ST_CYC_EXT, ST_CYC_FINAL, ST_BADD_EDGES, ST_EXT_EDGES,
+       ST_S2_ROUNDS, ST_S2_LATE, ST_S2_PM, ST_S2_DENSE, ST_S2_SPURIOUS, ST_S2_UNDONE, ST_SPARE0, ST_SPARE1, ST_N };
+static_assert(ST_N == TDA_RIPS_STATS, "stats slots");
 
 // ------------------------------------------------------------------------------------------------
 // low-dimensional euclidean distance matrix (ripser.py front end)
@@ -391,6 +395,10 @@ struct ReduceParams {
   // being re-enumerated from V when the window gets there.  [grid, far_cap] keys; nbk = most windows a column can see
   uint64_t* far; uint64_t far_cap; uint32_t nbk;
   int verify_mode;                          // sweep reducer: substitute-then-verify instead of the sequential resolver (opt-in)
+  // sweep2 reducer (rips_sweep2.cuh)
+  const uint2* par;                         // [batch, E] parents of the apparent edges (rank | apparent << 31)
+  uint2* s2_pend; uint2* s2_heavy; uint32_t* s2_fail;   // per-CTA spill lists: [grid, 2, wmax + 64], [grid, wmax + 64], [grid, kS2FailCap]
+  int s2_w0, s2_wsparse, s2_wmax, s2_dense_min, s2_dense_div;
 };
 
 struct ReduceSmem {
@@ -1984,6 +1992,8 @@ __global__ void __launch_bounds__(kSweepThreads, 1) rips_sweep_kernel(const __gr
   }
 }
 
+#include "rips_sweep2.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // H2 pre-pass (runs after the H1 stage on the same rank matrix)
 //  h2_clear_kernel    : bitset of the triangles that are H1 death simplices (apparent pairs (r, apex[r]) and the pivots of the
@@ -2092,22 +2102,30 @@ struct Layout {
   uint32_t* bits; uint64_t wbits;   // per-CTA key windows (bitset reducer)
   uint32_t* xmat; int xw;           // per-CTA V bit matrix (sweep reducer)
   uint32_t* pmat;                   // per-CTA "edges below the cursor" bit matrix (sweep reducer)
-  bool sweep;
+  bool sweep;                       // one of the row-sweep reducers (X / Pm bit matrices) rather than the key bitset
+  int reducer;                      // 0 sweep2, 1 sweep (resolver), 2 sweep (verify), 3 bitset
+  uint2* par;                       // parents of the apparent edges (sweep2)
+  uint2* s2_pend; uint2* s2_heavy; uint32_t* s2_fail; int s2_wmax;
   int* work_counter; unsigned long long* stats;
   int grid; size_t total;
 };
 
 static int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
-static bool use_sweep_reducer() {
-  const char* e = getenv("TDA_RIPS_REDUCER");
-  return !(e && strcmp(e, "bitset") == 0);
+static int s2_wmax_option() {
+  long long w = option("rips_wmax");
+  if (w < 64) w = 64;
+  if (w > kS2MaxWindow) w = kS2MaxWindow;
+  return (int)(w & ~31ll);
 }
 
 static Layout make_layout(void* ws, int n, int batch, int maxdim, int cap1, size_t pool_bytes, int sm_count) {
   Layout L;
   memset(&L, 0, sizeof(L));
-  L.sweep = use_sweep_reducer() && n <= 8192;   // the row sweep keeps <= 8 words of a row per resolver lane; larger clouds use the key bitset
+  L.reducer = (int)option("rips_reducer");
+  if (L.reducer < 0 || L.reducer > 3) L.reducer = 0;
+  if ((L.reducer == 1 || L.reducer == 2) && n > 8192) L.reducer = 0;   // the resolver keeps <= 8 words of a row per lane
+  L.sweep = L.reducer != 3;
   const int64_t E = (int64_t)n * (n - 1) / 2;
   const int64_t BE = (int64_t)batch * E;
   Carver c(ws, ~size_t(0));
@@ -2149,7 +2167,14 @@ static Layout make_layout(void* ws, int n, int batch, int maxdim, int cap1, size
     L.hvals = c.take<int>((int64_t)batch * L.hcap);
     L.vstart = c.take<int64_t>((int64_t)batch * cap1);
     L.vlen = c.take<int>((int64_t)batch * cap1);
-    L.xw = (n + 31) / 32;
+    L.xw = ((n + 31) / 32 + 1) & ~1;   // even: rows of X / Pm are 8-byte aligned
+    if (L.reducer == 0) {
+      L.par = c.take<uint2>(BE);
+      L.s2_wmax = s2_wmax_option();
+      L.s2_pend = c.take<uint2>((size_t)L.grid * 2 * (size_t)(L.s2_wmax + 64));
+      L.s2_heavy = c.take<uint2>((size_t)L.grid * (size_t)(L.s2_wmax + 64));
+      L.s2_fail = c.take<uint32_t>((size_t)L.grid * kS2FailCap);
+    }
     if (L.sweep) {
       L.xmat = c.take<uint32_t>((size_t)L.grid * (size_t)n * L.xw);
       L.pmat = c.take<uint32_t>((size_t)L.grid * (size_t)n * L.xw);
@@ -2307,16 +2332,37 @@ static int rips_enqueue(const float* dm, int n, int batch, int maxdim, float thr
     P.vpool = L.vpool; P.vpool_cap = L.vpool_cap; P.vstart = L.vstart; P.vlen = L.vlen;
     P.work_counter = L.work_counter; P.stats = L.stats;
     P.apex4 = nullptr; P.far = nullptr; P.far_cap = 0; P.nbk = 0;
-    {
-      const char* e = getenv("TDA_RIPS_REDUCER");   // "verify": substitute-then-verify inside the sweep kernel (not yet the default)
-      P.verify_mode = (e && strcmp(e, "verify") == 0) ? 1 : 0;
+    P.verify_mode = L.reducer == 2 ? 1 : 0;
+    P.par = L.par; P.s2_pend = L.s2_pend; P.s2_heavy = L.s2_heavy; P.s2_fail = L.s2_fail;
+    P.s2_wmax = L.s2_wmax;
+    P.s2_w0 = (int)option("rips_w0");
+    if (P.s2_w0 < 32) P.s2_w0 = 32;
+    if (P.s2_w0 > P.s2_wmax) P.s2_w0 = P.s2_wmax;
+    P.s2_wsparse = (int)option("rips_wsparse");
+    if (P.s2_wsparse < P.s2_w0) P.s2_wsparse = P.s2_w0;
+    if (P.s2_wsparse > P.s2_wmax) P.s2_wsparse = P.s2_wmax;
+    P.s2_dense_min = (int)option("rips_dense_min");
+    if (P.s2_dense_min < 1) P.s2_dense_min = 1;
+    P.s2_dense_div = (int)option("rips_dense_div");
+    if (P.s2_dense_div < 1) P.s2_dense_div = 1;
+    if (L.reducer == 0) {
+      StageScope st(STAGE_RIPS_APPARENT, stream);
+      dim3 gp((unsigned)((E + 255) / 256), batch);
+      parents_kernel<<<gp, 256, 0, stream>>>(L.rank, L.ea, L.T, n, E, L.par);
+      count_launch();
+      TDA_LAUNCH_CHECK();
     }
     {
       StageScope st(STAGE_RIPS_REDUCE, stream);
-      if (L.sweep) {
+      if (L.reducer == 0) {
+        const size_t dyn = Sweeper2::dyn_bytes(L.xw, L.s2_wmax);
+        if (dyn > (size_t)200 * 1024) return set_error(TDA_ERR_UNSUPPORTED, "tda_rips: sweep2 needs %zu bytes of shared memory (n=%d, rips_wmax=%d)", dyn, n, L.s2_wmax);
+        TDA_CUDA_CHECK(cudaFuncSetAttribute(rips_sweep2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        rips_sweep2_kernel<<<L.grid, kS2Threads, dyn, stream>>>(P);
+      } else if (L.sweep) {
         // TDA_SWEEP_EXCLUSIVE=1: ask for all of the SM's shared memory, so that no CTA of a kernel running on another stream
         // (UMAP SGD of the next chunk ...) shares the SM -- and the issue slots -- with the latency-bound resolver warp
-        static const bool exclusive = [] { const char* e = getenv("TDA_SWEEP_EXCLUSIVE"); return e && e[0] == '1'; }();
+        const bool exclusive = option("sweep_exclusive") != 0;
         size_t dyn = sizeof(uint32_t) * ((size_t)L.xw * (1 + 4 * kGroupRows) + (size_t)n + 2 * kChunkRows);
 #define TDA_SWEEP_LAUNCH_K(KERNEL)                                                                                            \
   do {                                                                                                                        \
@@ -2479,7 +2525,7 @@ extern "C" int tda_rips_h2(const void* ws1, int n, int batch, int cap1, size_t p
   {
     const int64_t work = E > L1.hcap ? E : L1.hcap;
     dim3 g((unsigned)((work + 255) / 256), batch);
-    static const bool debug_sync = getenv("TDA_DEBUG_SYNC") != nullptr;   // locate a faulting kernel: synchronise after each one
+    const bool debug_sync = option("debug_sync") != 0;   // locate a faulting kernel: synchronise after each one
     if (debug_sync) TDA_CUDA_CHECK(cudaStreamSynchronize(stream));
     h2_clear_kernel<<<g, 256, 0, stream>>>(L1.ea, L1.T, L1.hkeys, L1.hcap, n, E, L.cbits, L.cwords);
     if (debug_sync) TDA_CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -2514,7 +2560,7 @@ extern "C" int tda_rips_h2(const void* ws1, int n, int batch, int cap1, size_t p
   {
     std::vector<int32_t> hc((size_t)batch * 4);
     TDA_CUDA_CHECK(cudaMemcpy(hc.data(), counts2, sizeof(int32_t) * 4 * batch, cudaMemcpyDeviceToHost));
-    if (getenv("TDA_H2_STATS")) {   // device counters of the H2 reduction, one line per problem (diagnostics)
+    if (option("h2_stats")) {   // device counters of the H2 reduction, one line per problem (diagnostics)
       std::vector<unsigned long long> hs((size_t)batch * ST_N);
       std::vector<int> hb(batch);
       TDA_CUDA_CHECK(cudaMemcpy(hs.data(), L.stats, sizeof(unsigned long long) * ST_N * batch, cudaMemcpyDeviceToHost));

@@ -1,0 +1,760 @@
+// rips_sweep2.cuh -- residual H1 reduction, "substitute by rank, verify by window" (the default reducer; included by rips.cu).
+//
+// Same reduction as ripser's (same column order, same pivots), organised so that nothing in it is a chain of dependent pivots
+// (CPU model, checked pair for pair against the ripser restatement: oracle/rips_propagate_model.cpp, rips_model_h1_modes):
+//
+//  * x_e = 1 iff edge e (by rank) is in the reduction column V.  When the sweep passes row M of an apparent edge M=(c,d) with
+//    apex a, the reduction ends with  x_M = x_(c,a) ^ x_(d,a)  whatever it was before: the apparent-pair additions are a forward
+//    SUBSTITUTION over a static graph (two parent edges per apparent edge, `par`, written by parents_kernel).  A window of rows
+//    [pos, hi) is substituted in rounds: round 1 takes every row whose parents are final (below the window, or rows that the
+//    substitution does not change), the later rounds run in shared memory on the few rows that wait for a row of the window.
+//  * verification: V must be a cocycle of the complex below the cursor, i.e. every row (x_M ^ X[c] ^ X[d]) & lune(M) must be
+//    empty (X = V as a symmetric bit matrix).  Only rows with a touched endpoint can fail ("heavy" rows).
+//      sparse mode : the lune comes from the two rank rows (exact); the smallest failing key of the window is the event.
+//      dense mode  : (>= 1/8 of a window heavy) the mask is Pend[c] & Pend[d], Pend = adjacency of ALL edges below the window's
+//                    end, kept as a bit matrix that only moves forward inside a column.  If the window leaves V a cocycle of
+//                    the complex at its end, every row passes; a failing bit (M, w) under this superset mask belongs to the
+//                    triangle {c,d,w}, whose own row lies in the window, so the failing rows in ascending order, re-checked
+//                    with the exact lune, give the first true failure (the others are spurious stops: nothing to undo).
+//  * event (M*, w*): the flips above M* are undone; unowned pivot -> death of the column; pivot owned by a reduced column j ->
+//    V ^= V_j and the sweep resumes at row M* (whose substitution is then a no-op).
+//  * windows grow (w0, doubling) while they are clean and shrink back after an event (sparse mode); in dense mode the window
+//    keeps its end after an event.
+//
+// One CTA per cloud at a time (dynamic work counter).  All per-window passes are warp-per-32-rows with coalesced 8-byte loads
+// of the row tables; global x bits are rewritten one word per 32 rows without atomics.
+
+constexpr int kS2Threads = 512;
+constexpr int kS2Warps = kS2Threads / 32;
+constexpr int kS2ListSmem = 2048;      // entries of the pending / heavy lists kept in shared memory (the rest spills to global scratch)
+constexpr int kS2FailCap = 4096;       // failing rows of a dense window that are recorded (more: fall back to the minimum alone)
+constexpr int kS2MaxRounds = 4096;     // substitution rounds per window (depth of the apparent graph is ~30): beyond -> internal error
+constexpr int kS2MaxWindow = 65472;    // rows of a window (16-bit local indices in the pending entries)
+constexpr int kS2Batch = 4;            // heavy rows a warp verifies at once (dense mode)
+enum { TDA_ERR_INTERNAL_S2 = -6 };
+
+struct Sweep2Smem {
+  uint32_t vcount, vcount2, vsel;
+  int abort_flag, problem;
+  uint32_t npend[3];
+  uint32_t nheavy, nfail, fail_row, cand, newtouch;
+  unsigned long long fail_key;
+  int ev_w;
+  unsigned long long st[16];
+};
+enum { S2_WINDOWS = 0, S2_ROUNDS, S2_HEAVY, S2_FLIPS, S2_UNDONE, S2_EVENTS, S2_SPURIOUS, S2_SUBST, S2_LATE, S2_PM, S2_DENSE, S2_EXACT, S2_DEATHS };
+
+struct Sweeper2 {
+  static constexpr uint64_t kEmpty = ~0ull;
+  static constexpr unsigned kFull = 0xffffffffu;
+  const ReduceParams& P;
+  Sweep2Smem& S;
+  uint32_t *touched, *tnew, *xs, *done;
+  uint2 *pend_s, *heavy_s;     // [2][kS2ListSmem], [kS2ListSmem]
+  const int tid, lane, warp;
+  const int* R; const uint32_t* EN; const uint2* EA; const uint2* PAR; int T; int n; int W;
+  uint32_t *X, *Pm, *vbits, *vl0;
+  uint2 *pend_g, *heavy_g; uint32_t* fail_g;
+  uint32_t p_pos; bool p_valid;
+  uint64_t* hkeys; int* hvals;
+
+  __device__ Sweeper2(const ReduceParams& p, Sweep2Smem& s, uint32_t* dyn)
+      : P(p), S(s), tid(threadIdx.x), lane(threadIdx.x & 31), warp(threadIdx.x >> 5) {
+    n = P.n;
+    W = P.xw;
+    const int nw = P.s2_wmax / 32 + 4;
+    touched = dyn;
+    tnew = touched + W;
+    xs = tnew + W;
+    done = xs + nw;
+    pend_s = reinterpret_cast<uint2*>(done + nw + ((2 * W + 2 * nw) & 1));   // 8-byte aligned
+    heavy_s = pend_s + 2 * kS2ListSmem;
+    X = P.xmat + (size_t)blockIdx.x * (size_t)n * W;
+    Pm = P.pmat + (size_t)blockIdx.x * (size_t)n * W;
+    p_pos = 0; p_valid = false;
+    vbits = P.vbits + (size_t)blockIdx.x * P.vwords;
+    vl0 = P.vlist + (size_t)blockIdx.x * 2 * P.vcap;
+    pend_g = P.s2_pend + (size_t)blockIdx.x * 2 * (size_t)(P.s2_wmax + 64);
+    heavy_g = P.s2_heavy + (size_t)blockIdx.x * (size_t)(P.s2_wmax + 64);
+    fail_g = P.s2_fail + (size_t)blockIdx.x * kS2FailCap;
+  }
+  static __host__ __device__ size_t dyn_bytes(int W, int wmax) {
+    const int nw = wmax / 32 + 4;
+    return sizeof(uint32_t) * (size_t)(2 * W + 2 * nw + 2) + sizeof(uint2) * (size_t)(3 * kS2ListSmem);
+  }
+  __device__ __forceinline__ uint32_t* vlist(uint32_t sel) const { return vl0 + (size_t)sel * P.vcap; }
+  __device__ __forceinline__ bool tbit(uint32_t v) const { return (touched[v >> 5] >> (v & 31)) & 1u; }
+  __device__ __forceinline__ bool tnewbit(uint32_t v) const { return (tnew[v >> 5] >> (v & 31)) & 1u; }
+  __device__ __forceinline__ uint32_t xg(uint32_t e) const { return (__ldcg(&vbits[e >> 5]) >> (e & 31)) & 1u; }
+  __device__ __forceinline__ uint2* pend_ref(int buf, uint32_t i) const {
+    return i < (uint32_t)kS2ListSmem ? &pend_s[(size_t)buf * kS2ListSmem + i] : &pend_g[(size_t)buf * (P.s2_wmax + 64) + (i - kS2ListSmem)];
+  }
+  __device__ __forceinline__ uint2* heavy_ref(uint32_t i) const { return i < (uint32_t)kS2ListSmem ? &heavy_s[i] : &heavy_g[i - kS2ListSmem]; }
+  __device__ __forceinline__ void fail(int code) { S.abort_flag = code; }
+
+  __device__ __forceinline__ void x_flip(uint32_t c, uint32_t d) {
+    atomicXor(&X[(size_t)c * W + (d >> 5)], 1u << (d & 31));
+    atomicXor(&X[(size_t)d * W + (c >> 5)], 1u << (c & 31));
+  }
+  __device__ __forceinline__ void touch(uint32_t v) {
+    const uint32_t m = 1u << (v & 31);
+    if (!(touched[v >> 5] & m)) {
+      const uint32_t old = atomicOr(&touched[v >> 5], m);
+      if (!(old & m)) { atomicOr(&tnew[v >> 5], m); S.newtouch = 1; }
+    }
+  }
+  // edge e=(c,d) toggles in V: x bit, X, touched, V list (any thread; duplicates in the list are fine, v_compact drops them)
+  __device__ __forceinline__ void toggle_edge(uint32_t e, uint32_t c, uint32_t d, bool append) {
+    atomicXor(&vbits[e >> 5], 1u << (e & 31));
+    x_flip(c, d);
+    touch(c); touch(d);
+    if (append) {
+      const uint32_t pos = atomicAdd(&S.vcount, 1u);
+      if (pos < (uint32_t)P.vcap) vlist(S.vsel)[pos] = e;
+      else fail(TDA_ERR_CAPACITY);
+    }
+  }
+  // V list -> the distinct edges with x = 1 (x bits are exact; the list may hold an edge several times or with x = 0)
+  __device__ __forceinline__ void v_compact() {
+    __syncthreads();
+    const uint32_t nin = min(S.vcount, (uint32_t)P.vcap);
+    const uint32_t* src = vlist(S.vsel);
+    uint32_t* dst = vlist(S.vsel ^ 1);
+    if (tid == 0) S.vcount2 = 0;
+    __threadfence();
+    __syncthreads();
+    for (uint32_t i0 = 0; i0 < nin; i0 += kS2Threads) {
+      const uint32_t i = i0 + tid;
+      bool keep = false;
+      uint32_t e = 0;
+      if (i < nin) {
+        e = src[i];
+        const uint32_t m = 1u << (e & 31);
+        keep = (atomicAnd(&vbits[e >> 5], ~m) & m) != 0;
+      }
+      const unsigned bal = __ballot_sync(kFull, keep);
+      uint32_t bs = 0;
+      if (lane == 0 && bal) bs = atomicAdd(&S.vcount2, (uint32_t)__popc(bal));
+      bs = __shfl_sync(kFull, bs, 0);
+      if (keep) dst[bs + __popc(bal & ((1u << lane) - 1))] = e;
+    }
+    __threadfence();
+    __syncthreads();
+    const uint32_t nout = S.vcount2;
+    for (uint32_t i = tid; i < nout; i += kS2Threads) {
+      const uint32_t e = dst[i];
+      atomicOr(&vbits[e >> 5], 1u << (e & 31));
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) { S.vsel ^= 1; S.vcount = nout; }
+    __syncthreads();
+  }
+  // after v_compact: x bits, X bits and the touched mask back to zero; the list empty
+  __device__ __forceinline__ void v_clear() {
+    const uint32_t nin = S.vcount;
+    const uint32_t* src = vlist(S.vsel);
+    for (uint32_t i = tid; i < nin; i += kS2Threads) {
+      const uint32_t e = src[i];
+      atomicAnd(&vbits[e >> 5], ~(1u << (e & 31)));
+      const uint32_t en = __ldg(&EN[e]);
+      x_flip(en >> 16, en & 0xffffu);
+    }
+    for (int i = tid; i < W; i += kS2Threads) { touched[i] = 0; tnew[i] = 0; }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) S.vcount = 0;
+    __syncthreads();
+  }
+  __device__ __forceinline__ int hash_find(uint64_t key) const {
+    uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32) & (uint32_t)(P.hcap - 1);
+    for (;;) {
+      const uint64_t k = __ldcg(&hkeys[h]);
+      if (k == key) return __ldcg(&hvals[h]);
+      if (k == kEmpty) return -1;
+      h = (h + 1) & (uint32_t)(P.hcap - 1);
+    }
+  }
+  __device__ __forceinline__ void hash_insert(uint64_t key, int val) {  // thread 0
+    uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32) & (uint32_t)(P.hcap - 1);
+    while (__ldcg(&hkeys[h]) != kEmpty) h = (h + 1) & (uint32_t)(P.hcap - 1);
+    __stcg(&hvals[h], val);
+    __stcg(&hkeys[h], key);
+  }
+  __device__ __forceinline__ void sort_blist(int* bl, int nb) {
+    int np2 = 1;
+    while (np2 < nb) np2 <<= 1;
+    for (int i = nb + tid; i < np2; i += kS2Threads) bl[i] = 0x7fffffff;
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < np2; i += kS2Threads) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const int a = bl[i], b = bl[ixj];
+            const bool up = ((i & k) == 0);
+            if ((a > b) == up) { bl[i] = b; bl[ixj] = a; }
+          }
+        }
+        __syncthreads();
+      }
+  }
+
+  // ---- Pm = adjacency bit matrix of the edges with rank < p_pos.  All threads; ends with the bits performed and a barrier.
+  __device__ __forceinline__ void p_set_rows(uint32_t lo, uint32_t hi, bool set) {
+    for (uint32_t row = lo + tid; row < hi; row += kS2Threads) {
+      const uint32_t en = __ldg(&EN[row]);
+      const uint32_t c = en >> 16, d = en & 0xffffu;
+      if (set) {
+        atomicOr(&Pm[(size_t)c * W + (d >> 5)], 1u << (d & 31));
+        atomicOr(&Pm[(size_t)d * W + (c >> 5)], 1u << (c & 31));
+      } else {
+        atomicAnd(&Pm[(size_t)c * W + (d >> 5)], ~(1u << (d & 31)));
+        atomicAnd(&Pm[(size_t)d * W + (c >> 5)], ~(1u << (c & 31)));
+      }
+    }
+  }
+  __device__ __forceinline__ void p_move(uint32_t target) {
+    const uint32_t dist = target > p_pos ? target - p_pos : p_pos - target;
+    if (!p_valid || (uint64_t)dist * 32ull > (uint64_t)n * (uint64_t)n) {
+      // rebuild from the rank matrix: one warp per vertex row, a word per ballot
+      for (int c = warp; c < n; c += kS2Warps) {
+        const int* Rc = R + (size_t)c * n;
+        for (int k0 = 0; k0 < W; k0 += 32) {
+          uint32_t mine = 0;
+          const int kend = min(32, W - k0);
+#pragma unroll 8
+          for (int kk = 0; kk < kend; ++kk) {
+            const int w = (k0 + kk) * 32 + lane;
+            const int ra = w < n ? __ldg(&Rc[w]) : kRankDiag;
+            const unsigned word = __ballot_sync(kFull, ra < (int)target);
+            if (lane == kk) mine = word;
+          }
+          if (k0 + lane < W) __stcg(&Pm[(size_t)c * W + k0 + lane], mine);
+        }
+      }
+      p_valid = true;
+      if (tid == 0) S.st[S2_PM] += (unsigned long long)n * n / 32;
+    } else if (target > p_pos) {
+      p_set_rows(p_pos, target, true);
+      if (tid == 0) S.st[S2_PM] += dist;
+    } else if (target < p_pos) {
+      p_set_rows(target, p_pos, false);
+      if (tid == 0) S.st[S2_PM] += dist;
+    }
+    p_pos = target;
+    __threadfence();
+    __syncthreads();
+  }
+
+  // ---- one row with its exact lune { w : rank(c,w) < M and rank(d,w) < M } (one warp): the highest failing vertex, or -1
+  __device__ __forceinline__ int exact_row(uint32_t M, uint32_t c, uint32_t d, uint32_t xm) const {
+    const int* Rc = R + (size_t)c * n;
+    const int* Rd = R + (size_t)d * n;
+    const uint32_t* Xc = X + (size_t)c * W;
+    const uint32_t* Xd = X + (size_t)d * W;
+    int best = -1;
+    for (int k0 = 0; k0 < W; k0 += 32) {   // 32 words = 1024 vertices per block; lane kk ends up with the lune word k0 + kk
+      const int kend = min(32, W - k0);
+      const int k = k0 + lane;
+      const uint32_t xx = k < W ? (__ldcg(&Xc[k]) ^ __ldcg(&Xd[k])) : 0u;
+      uint32_t lmine = 0;
+      for (int kk0 = 0; kk0 < kend; kk0 += 8) {
+        int ra[8], rb[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int w = (k0 + kk0 + u) * 32 + lane;
+          const bool ok = (kk0 + u) < kend && w < n;
+          ra[u] = ok ? __ldg(&Rc[w]) : kRankDiag;
+          rb[u] = ok ? __ldg(&Rd[w]) : kRankDiag;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const unsigned word = __ballot_sync(kFull, ra[u] < (int)M && rb[u] < (int)M);
+          if (lane == kk0 + u) lmine = word;
+        }
+      }
+      const uint32_t v = (xm ^ xx) & lmine;
+      if (v) best = k * 32 + 31 - __clz(v);
+    }
+    return __reduce_max_sync(kFull, best);
+  }
+
+  // ---- appends one entry per flagged lane to a list (warp-aggregated); returns nothing.  `cnt` in shared memory
+  template <typename Ref>
+  __device__ __forceinline__ void warp_append(bool flag, uint2 ent, uint32_t* cnt, Ref ref) {
+    const unsigned bal = __ballot_sync(kFull, flag);
+    if (!bal) return;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(cnt, (uint32_t)__popc(bal));
+    base = __shfl_sync(kFull, base, 0);
+    if (flag) *ref(base + __popc(bal & ((1u << lane) - 1))) = ent;
+  }
+
+  __device__ __forceinline__ void run_problem(int p) {
+    R = P.rank + (size_t)p * n * n;
+    EN = P.ends + (size_t)p * P.E;
+    EA = P.ea + (size_t)p * P.E;
+    PAR = P.par + (size_t)p * P.E;
+    T = P.T[p];
+    hkeys = P.hkeys + (size_t)p * P.hcap;
+    hvals = P.hvals + (size_t)p * P.hcap;
+    const float* SD = P.sdist + (size_t)p * P.E;
+    int* bl = P.blist + (size_t)p * P.cap1;
+    const int nb = P.bcount[p];
+    unsigned long long* st = P.stats + (size_t)p * ST_N;
+    if (nb > P.cap1) {
+      if (tid == 0) { P.counts[p * 4 + 3] = TDA_ERR_CAPACITY; P.counts[p * 4 + 1] = 0; }
+      return;
+    }
+    p_valid = false;   // Pm belongs to the previous cloud's rank matrix
+    sort_blist(bl, nb);
+    for (int i = tid; i < P.hcap; i += kS2Threads) hkeys[i] = kEmpty;
+    for (int i = tid; i < W; i += kS2Threads) { touched[i] = 0; tnew[i] = 0; }
+    if (tid == 0) {
+      S.vcount = 0; S.vsel = 0; S.abort_flag = 0;
+      for (int q = 0; q < 16; ++q) S.st[q] = 0;
+    }
+    __threadfence();
+    __syncthreads();
+    int nrows = 0;
+    int64_t vpool_used = 0;
+    unsigned long long maxv = 0, badd_edges = 0;
+    long long cyc[6] = {0, 0, 0, 0, 0, 0};
+    long long t0;
+    float* out = P.h1_pairs + (size_t)p * P.cap1 * 2;
+    int64_t* outs = P.h1_simplex ? P.h1_simplex + (size_t)p * P.cap1 * 2 : nullptr;
+    const uint32_t w0 = (uint32_t)P.s2_w0, wsparse = (uint32_t)P.s2_wsparse, wmax = (uint32_t)P.s2_wmax;
+    const uint32_t gw = (uint32_t)(P.s2_wmax + 64);
+
+    for (int ci = nb - 1; ci >= 0; --ci) {
+      const int rbirth = bl[ci];
+      {  // V = {birth edge}
+        const uint32_t en = __ldg(&EN[rbirth]);
+        if (tid == 0) toggle_edge((uint32_t)rbirth, en >> 16, en & 0xffffu, true);
+        __threadfence();
+        __syncthreads();
+      }
+      bool essential = false, dense = false, keep_hi = false;
+      uint64_t pivot = 0;
+      uint32_t pos = (uint32_t)rbirth + 1, win = w0, hi = 0;
+      unsigned long long guard = 0;
+      const unsigned long long guard_max = 64ull + 8ull * ((unsigned long long)T / max(1u, w0) + 1ull) + 4ull * (unsigned long long)nb;
+      for (;;) {
+        if (S.abort_flag) break;
+        if (pos >= (uint32_t)T) { essential = true; break; }
+        if (++guard > guard_max + (unsigned long long)T) { if (tid == 0) fail(TDA_ERR_INTERNAL_S2); __syncthreads(); break; }
+        if (!keep_hi || hi <= pos) {
+          hi = (pos + win + 31u) & ~31u;
+          if (hi > (uint32_t)T) hi = (uint32_t)T;
+        }
+        keep_hi = false;
+        if (S.vcount + (hi - pos) + 64u > (uint32_t)P.vcap) {
+          v_compact();
+          if (S.vcount + (hi - pos) + 64u > (uint32_t)P.vcap) { if (tid == 0) fail(TDA_ERR_CAPACITY); __syncthreads(); break; }
+        }
+        const uint32_t g0 = pos >> 5, g1 = (hi + 31u) >> 5;
+        const uint32_t base_row = g0 << 5;
+        if (tid == 0) {
+          S.npend[0] = S.npend[1] = S.npend[2] = 0; S.nheavy = 0; S.nfail = 0; S.fail_row = 0xffffffffu; S.cand = 0xffffffffu;
+          S.fail_key = ~0ull; S.newtouch = 0; S.ev_w = -1;
+          S.st[S2_WINDOWS] += 1; S.st[S2_SUBST] += hi - pos;
+        }
+        for (int i = tid; i < W; i += kS2Threads) tnew[i] = 0;
+        __syncthreads();
+        const uint32_t vmark = S.vcount;
+        t0 = clock64();
+        // ---- substitution, round 1: every row of the window, one warp per 32 consecutive ranks
+        for (uint32_t g = g0 + warp; g < g1; g += kS2Warps) {
+          const uint32_t row = (g << 5) + lane;
+          const bool inwin = row >= pos && row < hi;
+          const uint32_t xold = __ldcg(&vbits[g]);
+          uint2 ea = make_uint2(0u, 0xffffffffu);
+          if (inwin) ea = __ldg(&EA[row]);
+          const bool app = inwin && (int)ea.y >= 0;
+          uint2 par = make_uint2(0u, 0u);
+          if (app) par = __ldg(&PAR[row]);
+          const uint32_t pa = par.x & 0x7fffffffu, pb = par.y & 0x7fffffffu;
+          const bool depA = app && (par.x >> 31) && pa >= pos;   // the parent is an apparent row of this window: not final yet
+          const bool depB = app && (par.y >> 31) && pb >= pos;
+          const uint32_t c = ea.x >> 16, d = ea.x & 0xffffu, a = ea.y;
+          uint32_t base = 0;
+          bool heavy = false;
+          if (app) {
+            const bool tc = tbit(c), td = tbit(d), ta = tbit(a);
+            heavy = tc || td;
+            // a final parent edge with x = 1 has both endpoints touched (touched = as of the start of the window)
+            if (!depA && ta && tc) base ^= xg(pa);
+            if (!depB && ta && td) base ^= xg(pb);
+          }
+          const bool computed = app && !depA && !depB;
+          const unsigned bapp = __ballot_sync(kFull, app);
+          const unsigned bone = __ballot_sync(kFull, computed && base);
+          const unsigned bdone = __ballot_sync(kFull, computed);
+          if (lane == 0) { xs[g - g0] = (xold & ~bapp) | bone; done[g - g0] = bdone; }
+          const bool pend = app && (depA || depB);
+          const uint2 pent = make_uint2((row - base_row) | (base << 31) | ((depA ? 1u : 0u) << 30) | ((depB ? 1u : 0u) << 29),
+                                        (depA ? (pa - base_row) : 0u) | ((depB ? (pb - base_row) : 0u) << 16));
+          warp_append(pend, pent, &S.npend[0], [&](uint32_t i) { return pend_ref(0, i); });
+          warp_append(heavy, make_uint2(row, ea.x), &S.nheavy, [&](uint32_t i) { return heavy_ref(i); });
+        }
+        __threadfence();
+        __syncthreads();
+        cyc[0] += clock64() - t0;
+        t0 = clock64();
+        // ---- later rounds: rows that wait for rows of the window; shared memory only (+ the spill part of the list)
+        {
+          int r = 0;
+          for (;;) {
+            const uint32_t np = S.npend[r % 3];
+            if (np == 0) break;
+            if (r >= kS2MaxRounds) { if (tid == 0) fail(TDA_ERR_INTERNAL_S2); break; }
+            if (tid == 0) { S.npend[(r + 2) % 3] = 0; S.st[S2_ROUNDS] += 1; S.st[S2_LATE] += np; }
+            const int rb = r & 1, wb = rb ^ 1;
+            const uint32_t np_pad = (np + 31u) & ~31u;
+            for (uint32_t i = tid; i < np_pad; i += kS2Threads) {
+              const bool have = i < np;
+              uint2 ent = make_uint2(0u, 0u);
+              if (have) ent = *pend_ref(rb, i);
+              const uint32_t rl = ent.x & 0x00ffffffu, base = ent.x >> 31;
+              const bool hasA = (ent.x >> 30) & 1u, hasB = (ent.x >> 29) & 1u;
+              const uint32_t pal = ent.y & 0xffffu, pbl = ent.y >> 16;
+              const volatile uint32_t* vdone = done;
+              const volatile uint32_t* vxs = xs;
+              const bool okA = !hasA || ((vdone[pal >> 5] >> (pal & 31)) & 1u);
+              const bool okB = !hasB || ((vdone[pbl >> 5] >> (pbl & 31)) & 1u);
+              const bool ready = have && okA && okB;
+              if (ready) {
+                uint32_t v = base;
+                if (hasA) v ^= (vxs[pal >> 5] >> (pal & 31)) & 1u;
+                if (hasB) v ^= (vxs[pbl >> 5] >> (pbl & 31)) & 1u;
+                if (v) atomicOr(&xs[rl >> 5], 1u << (rl & 31));
+                __threadfence_block();
+                atomicOr(&done[rl >> 5], 1u << (rl & 31));
+              }
+              warp_append(have && !ready, ent, &S.npend[(r + 1) % 3], [&](uint32_t j) { return pend_ref(wb, j); });
+            }
+            __threadfence();
+            __syncthreads();
+            if (S.npend[(r + 1) % 3] == np) { if (tid == 0) fail(TDA_ERR_INTERNAL_S2); __syncthreads(); break; }   // no progress: broken order
+            ++r;
+          }
+        }
+        __syncthreads();
+        if (S.abort_flag) break;
+        cyc[1] += clock64() - t0;
+        t0 = clock64();
+        // ---- apply: the rows whose x changed flip in X / the V list; the global x words are rewritten (one owner per word)
+        for (uint32_t g = g0 + warp; g < g1; g += kS2Warps) {
+          const uint32_t xold = __ldcg(&vbits[g]);
+          const uint32_t xnew = xs[g - g0];
+          const uint32_t diff = xold ^ xnew;
+          if (diff) {
+            uint32_t vb = 0;
+            if (lane == 0) { __stcg(&vbits[g], xnew); vb = atomicAdd(&S.vcount, (uint32_t)__popc(diff)); }
+            vb = __shfl_sync(kFull, vb, 0);
+            if ((diff >> lane) & 1u) {
+              const uint32_t row = (g << 5) + lane;
+              const uint32_t en = __ldg(&EA[row]).x;
+              const uint32_t c = en >> 16, d = en & 0xffffu;
+              x_flip(c, d);
+              touch(c); touch(d);
+              const uint32_t vp = vb + __popc(diff & ((1u << lane) - 1));
+              if (vp < (uint32_t)P.vcap) vlist(S.vsel)[vp] = row;
+              else fail(TDA_ERR_CAPACITY);
+            }
+          }
+        }
+        __threadfence();
+        __syncthreads();
+        if (S.abort_flag) break;
+        if (tid == 0) S.st[S2_FLIPS] += S.vcount - vmark;
+        // rows that became heavy through a vertex touched in this window
+        if (S.newtouch) {
+          for (uint32_t g = g0 + warp; g < g1; g += kS2Warps) {
+            const uint32_t row = (g << 5) + lane;
+            const bool inwin = row >= pos && row < hi;
+            uint2 ea = make_uint2(0u, 0xffffffffu);
+            if (inwin) ea = __ldg(&EA[row]);
+            const uint32_t c = ea.x >> 16, d = ea.x & 0xffffu;
+            bool h = false;
+            if (inwin && (int)ea.y >= 0) {
+              const bool oc = tbit(c) && !tnewbit(c), od = tbit(d) && !tnewbit(d);
+              h = !(oc || od) && (tbit(c) || tbit(d));
+            }
+            warp_append(h, make_uint2(row, ea.x), &S.nheavy, [&](uint32_t i) { return heavy_ref(i); });
+          }
+          __threadfence();
+          __syncthreads();
+        }
+        cyc[2] += clock64() - t0;
+        const uint32_t nh = S.nheavy;
+        if (!dense && nh >= max((uint32_t)P.s2_dense_min, (hi - pos) / (uint32_t)P.s2_dense_div)) {
+          dense = true;
+          if (tid == 0) S.st[S2_DENSE] += 1;
+        }
+        if (tid == 0) S.st[S2_HEAVY] += nh;
+        t0 = clock64();
+        if (dense) p_move(hi);
+        cyc[5] += clock64() - t0;
+        t0 = clock64();
+        // ---- verification of the heavy rows
+        if (!dense) {
+          for (uint32_t i = warp; i < nh; i += kS2Warps) {
+            const uint2 ent = *heavy_ref(i);
+            const uint32_t M = ent.x, c = ent.y >> 16, d = ent.y & 0xffffu;
+            const uint32_t xm = xg(M) ? 0xffffffffu : 0u;
+            const int w = exact_row(M, c, d, xm);
+            if (w >= 0 && lane == 0) atomicMin(&S.fail_key, (unsigned long long)M * (unsigned long long)n + (unsigned long long)(n - 1 - w));
+          }
+        } else {
+          for (uint32_t i0 = warp * kS2Batch; i0 < nh; i0 += kS2Warps * kS2Batch) {
+            uint32_t Mr[kS2Batch], xmw[kS2Batch];
+            const uint32_t *Xc[kS2Batch], *Xd[kS2Batch], *Pc[kS2Batch], *Pd[kS2Batch];
+#pragma unroll
+            for (int b = 0; b < kS2Batch; ++b) {
+              const uint32_t i = i0 + b;
+              uint2 ent = make_uint2(0u, 0u);
+              if (i < nh) ent = *heavy_ref(i);
+              Mr[b] = i < nh ? ent.x : 0xffffffffu;
+              const uint32_t c = ent.y >> 16, d = ent.y & 0xffffu;
+              Xc[b] = X + (size_t)c * W; Xd[b] = X + (size_t)d * W; Pc[b] = Pm + (size_t)c * W; Pd[b] = Pm + (size_t)d * W;
+              xmw[b] = i < nh ? __ldcg(&vbits[ent.x >> 5]) : 0u;
+            }
+            uint32_t any[kS2Batch];
+#pragma unroll
+            for (int b = 0; b < kS2Batch; ++b) any[b] = 0;
+            for (int k = 2 * lane; k < W; k += 64) {   // W is even, rows are 8-byte aligned
+              uint2 a[kS2Batch][4];
+#pragma unroll
+              for (int b = 0; b < kS2Batch; ++b) {
+                a[b][0] = __ldcg(reinterpret_cast<const uint2*>(Xc[b] + k));
+                a[b][1] = __ldcg(reinterpret_cast<const uint2*>(Xd[b] + k));
+                a[b][2] = __ldcg(reinterpret_cast<const uint2*>(Pc[b] + k));
+                a[b][3] = __ldcg(reinterpret_cast<const uint2*>(Pd[b] + k));
+              }
+#pragma unroll
+              for (int b = 0; b < kS2Batch; ++b) {
+                const uint32_t xm = (Mr[b] != 0xffffffffu && ((xmw[b] >> (Mr[b] & 31)) & 1u)) ? 0xffffffffu : 0u;
+                any[b] |= ((xm ^ a[b][0].x ^ a[b][1].x) & a[b][2].x & a[b][3].x) | ((xm ^ a[b][0].y ^ a[b][1].y) & a[b][2].y & a[b][3].y);
+              }
+            }
+#pragma unroll
+            for (int b = 0; b < kS2Batch; ++b) {
+              const bool bad = __any_sync(kFull, any[b] != 0) && Mr[b] != 0xffffffffu;
+              if (bad && lane == 0) {
+                atomicMin(&S.fail_row, Mr[b]);
+                const uint32_t fi = atomicAdd(&S.nfail, 1u);
+                if (fi < (uint32_t)kS2FailCap) fail_g[fi] = Mr[b];
+              }
+            }
+          }
+        }
+        __threadfence();
+        __syncthreads();
+        cyc[3] += clock64() - t0;
+        t0 = clock64();
+        // ---- decision
+        uint32_t evM = 0xffffffffu;
+        int evw = -1;
+        if (!dense) {
+          const unsigned long long fk = S.fail_key;
+          if (fk != ~0ull) { evM = (uint32_t)(fk / (unsigned long long)n); evw = n - 1 - (int)(fk % (unsigned long long)n); }
+        } else if (S.nfail) {
+          // the failing rows in ascending order, each re-checked with its exact lune, until one is a true failure
+          const uint32_t nf = S.nfail;
+          uint32_t last = 0;   // rows <= last have been examined (row ranks here are >= pos >= 1)
+          bool first = true;
+          for (;;) {
+            uint32_t cand;
+            if (nf <= (uint32_t)kS2FailCap) {
+              uint32_t mine = 0xffffffffu;
+              for (uint32_t i = tid; i < nf; i += kS2Threads) {
+                const uint32_t v = __ldcg(&fail_g[i]);
+                if ((first || v > last) && v < mine) mine = v;
+              }
+              mine = warp_min_u32(mine);
+              if (lane == 0 && mine != 0xffffffffu) atomicMin(&S.cand, mine);
+              __syncthreads();
+              cand = S.cand;
+            } else {
+              cand = first ? S.fail_row : 0xffffffffu;   // the list overflowed: only the minimum is known
+            }
+            if (cand == 0xffffffffu) break;
+            if (warp == 0) {
+              const uint32_t en = __ldg(&EA[cand]).x;
+              const uint32_t xm = xg(cand) ? 0xffffffffu : 0u;
+              const int w = exact_row(cand, en >> 16, en & 0xffffu, xm);
+              if (lane == 0) { S.ev_w = w; S.cand = 0xffffffffu; S.st[S2_EXACT] += 1; }
+            }
+            __syncthreads();
+            const int w = S.ev_w;
+            if (w >= 0) { evM = cand; evw = w; break; }
+            if (tid == 0) S.st[S2_SPURIOUS] += 1;
+            last = cand; first = false;
+            __syncthreads();
+          }
+          if (evM == 0xffffffffu) {
+            if (nf <= (uint32_t)kS2FailCap) { if (tid == 0) fail(TDA_ERR_INTERNAL_S2); __syncthreads(); break; }   // cannot happen (see the header)
+            // overflowed list, spurious minimum: rows <= last are settled; same window again from behind it (nothing to undo)
+            pos = last + 1; keep_hi = true;
+            cyc[4] += clock64() - t0;
+            continue;
+          }
+        }
+        if (evM == 0xffffffffu) {   // clean window
+          pos = hi;
+          win = min(2u * win, dense ? wmax : wsparse);
+          cyc[4] += clock64() - t0;
+          continue;
+        }
+        // ---- event at (evM, evw): undo the flips above the row
+        {
+          const uint32_t vend = min(S.vcount, (uint32_t)P.vcap);
+          const uint32_t* vl = vlist(S.vsel);
+          uint32_t und = 0;
+          for (uint32_t f = vmark + tid; f < vend; f += kS2Threads) {
+            const uint32_t e = vl[f];
+            if (e > evM) {
+              const uint32_t en = __ldg(&EN[e]);
+              atomicXor(&vbits[e >> 5], 1u << (e & 31));
+              x_flip(en >> 16, en & 0xffffu);
+              ++und;
+            }
+          }
+          if (und) atomicAdd(&S.st[S2_UNDONE], (unsigned long long)und);
+        }
+        __threadfence();
+        __syncthreads();
+        const uint64_t fkey = (uint64_t)evM * (uint64_t)n + (uint64_t)(n - 1 - evw);
+        const int owner = hash_find(fkey);
+        if (owner < 0) { pivot = fkey; if (tid == 0) S.st[S2_DEATHS] += 1; cyc[4] += clock64() - t0; break; }   // death
+        {
+          const int64_t vs = P.vstart[(size_t)p * P.cap1 + owner];
+          const int vn = P.vlen[(size_t)p * P.cap1 + owner];
+          const uint32_t* ov = P.vpool + (size_t)p * P.vpool_cap + vs;
+          if (S.vcount + (uint32_t)vn + 64u > (uint32_t)P.vcap) v_compact();
+          for (int q = tid; q < vn; q += kS2Threads) {
+            const uint32_t re = ov[q];
+            const uint32_t en = __ldg(&EN[re]);
+            toggle_edge(re, en >> 16, en & 0xffffu, true);
+          }
+          badd_edges += vn;
+          if (tid == 0) S.st[S2_EVENTS] += 1;
+          __threadfence();
+          __syncthreads();
+        }
+        pos = evM;   // this row again: its substitution is a no-op now, the handled vertex is even, lower vertices may remain
+        if (dense) keep_hi = true;
+        else win = w0;
+        cyc[4] += clock64() - t0;
+      }
+      if (S.abort_flag) break;
+      t0 = clock64();
+      // ---- finalise the column
+      v_compact();
+      const uint32_t nv = S.vcount;
+      if (nv > maxv) maxv = nv;
+      if (!essential) {
+        if (vpool_used + nv > P.vpool_cap) { if (tid == 0) fail(TDA_ERR_CAPACITY); __syncthreads(); break; }
+        uint32_t* dst = P.vpool + (size_t)p * P.vpool_cap + vpool_used;
+        const uint32_t* list = vlist(S.vsel);
+        for (uint32_t i = tid; i < nv; i += kS2Threads) dst[i] = list[i];
+        if (tid == 0) {
+          P.vstart[(size_t)p * P.cap1 + ci] = vpool_used;
+          P.vlen[(size_t)p * P.cap1 + ci] = (int)nv;
+          hash_insert(pivot, ci);
+        }
+        vpool_used += nv;
+      }
+      const float birth = SD[rbirth];
+      float death = INFINITY;
+      int Md = -1, wd = -1;
+      if (!essential) { Md = (int)(pivot / (uint64_t)n); wd = n - 1 - (int)(pivot % (uint64_t)n); death = SD[Md]; }
+      if (essential || death > birth) {
+        if (tid == 0) {
+          out[2 * nrows] = birth; out[2 * nrows + 1] = death;
+          if (outs) {
+            const uint32_t e = EN[rbirth];
+            outs[2 * nrows] = edge_index((int)(e >> 16), (int)(e & 0xffffu));
+            if (essential) outs[2 * nrows + 1] = -1;
+            else {
+              const uint32_t em = EN[Md];
+              int x = (int)(em >> 16), y = (int)(em & 0xffffu), z = wd, t;
+              if (x < y) { t = x; x = y; y = t; }
+              if (y < z) { t = y; y = z; z = t; }
+              if (x < y) { t = x; x = y; y = t; }
+              outs[2 * nrows + 1] = (int64_t)x * (x - 1) * (x - 2) / 6 + (int64_t)y * (y - 1) / 2 + z;
+            }
+          }
+        }
+        ++nrows;
+      }
+      v_clear();
+      cyc[5] += clock64() - t0;
+    }
+    __syncthreads();
+    if (S.abort_flag) {  // leave the scratch clean for the next problem
+      __syncthreads();
+      for (size_t i = tid; i < (size_t)n * W; i += kS2Threads) X[i] = 0;
+      for (size_t i = tid; i < (size_t)P.vwords; i += kS2Threads) vbits[i] = 0;
+      for (int i = tid; i < W; i += kS2Threads) { touched[i] = 0; tnew[i] = 0; }
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) S.vcount = 0;
+    }
+    if (tid == 0) {
+      P.counts[p * 4 + 1] = nrows;
+      P.counts[p * 4 + 3] = S.abort_flag;
+      st[ST_REDUCED] = (unsigned long long)nb;
+      st[ST_ADDITIONS] = S.st[S2_FLIPS] - S.st[S2_UNDONE] + S.st[S2_EVENTS];
+      st[ST_PUSHES] = S.st[S2_SUBST];        // rows substituted
+      st[ST_POPS] = S.st[S2_EVENTS] + S.st[S2_DEATHS];   // non-apparent pivots
+      st[ST_EXTENSIONS] = S.st[S2_WINDOWS];
+      st[ST_MAXV] = maxv;
+      for (int q = 0; q < 6; ++q) st[ST_CYC_EXTRACT + q] = (unsigned long long)cyc[q];
+      st[ST_BADD_EDGES] = badd_edges;
+      st[ST_EXT_EDGES] = S.st[S2_HEAVY];
+      st[ST_S2_ROUNDS] = S.st[S2_ROUNDS];
+      st[ST_S2_LATE] = S.st[S2_LATE];
+      st[ST_S2_PM] = S.st[S2_PM];
+      st[ST_S2_DENSE] = S.st[S2_DENSE];
+      st[ST_S2_SPURIOUS] = S.st[S2_SPURIOUS];
+      st[ST_S2_UNDONE] = S.st[S2_UNDONE];
+    }
+    __syncthreads();
+    (void)gw;
+  }
+};
+
+__global__ void __launch_bounds__(kS2Threads, 1) rips_sweep2_kernel(const __grid_constant__ ReduceParams P) {
+  __shared__ Sweep2Smem S;
+  extern __shared__ __align__(16) uint32_t sweep2_dyn[];
+  Sweeper2 sw(P, S, sweep2_dyn);
+  for (;;) {
+    if (threadIdx.x == 0) S.problem = atomicAdd(P.work_counter, 1);
+    __syncthreads();
+    const int p = S.problem;
+    __syncthreads();
+    if (p >= P.batch) break;
+    sw.run_problem(p);
+  }
+}
+
+// parents of the apparent edges: par[M] = (rank(c,apex) | apparent?<<31, rank(d,apex) | apparent?<<31)
+__global__ void parents_kernel(const int* __restrict__ rank, const uint2* __restrict__ ea, const int* __restrict__ Tarr, int n, int64_t E,
+                               uint2* __restrict__ par) {
+  const int p = blockIdx.y;
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= Tarr[p]) return;
+  const uint2 e = ea[(size_t)p * E + r];
+  const int a = (int)e.y;
+  uint2 o = make_uint2(0u, 0u);
+  if (a >= 0) {
+    const int* Rp = rank + (size_t)p * n * n;
+    const uint32_t pa = (uint32_t)Rp[(size_t)(e.x >> 16) * n + a], pb = (uint32_t)Rp[(size_t)(e.x & 0xffffu) * n + a];
+    const uint32_t fa = (int)ea[(size_t)p * E + pa].y >= 0 ? 1u : 0u, fb = (int)ea[(size_t)p * E + pb].y >= 0 ? 1u : 0u;
+    o = make_uint2(pa | (fa << 31), pb | (fb << 31));
+  }
+  par[(size_t)p * E + r] = o;
+}

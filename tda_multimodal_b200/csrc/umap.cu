@@ -1066,7 +1066,7 @@ extern "C" int tda_knn_smooth(const float* D, int n, int m, int batch, int k, fl
 #define TDA_KNN_LAUNCH(KPL) knn_smooth_kernel<KPL><<<grid, 256, 0, stream>>>(D, n, m, k, local_connectivity, bandwidth, n_iter, knn_idx, knn_dist, sigma, rho, dist_sum)
   if (k <= 16) {
     dim3 gp((n + kBlkRows - 1) / kBlkRows, batch);  // 4 warps, 32 rows per CTA
-    static const int loads = [] { const char* e = getenv("TDA_KNN_LOADS"); return e ? atoi(e) : 8; }();
+    const int loads = (int)option("knn_loads");
     if (loads == 8) knn_smooth_block_kernel<8><<<gp, kBlkWarps * 32, 0, stream>>>(D, n, m, k, local_connectivity, bandwidth, n_iter, knn_idx, knn_dist, sigma, rho, dist_sum);
     else knn_smooth_block_kernel<16><<<gp, kBlkWarps * 32, 0, stream>>>(D, n, m, k, local_connectivity, bandwidth, n_iter, knn_idx, knn_dist, sigma, rho, dist_sum);
   } else if (kpl == 1) TDA_KNN_LAUNCH(1);
@@ -1114,8 +1114,8 @@ extern "C" int tda_umap_sgd(float* Y, const float* Y_other, const int32_t* head,
     float4* Yt4 = move_other ? Yh4 : Yh4 + np_h;
     pack4_kernel<<<(unsigned)((np_h + 255) / 256), 256, 0, stream>>>(Y, Yh4, np_h);
     // TDA_SGD_CLOUD=1: one CTA per cloud with the embedding in shared memory, all epochs in one launch (see sgd_cloud_kernel)
-    const char* cloud_env = getenv("TDA_SGD_CLOUD");
-    const bool cloud_mode = cloud_env && cloud_env[0] == '1';
+    const int sgd_mode = (int)option("sgd_mode");
+    const bool cloud_mode = sgd_mode == 1;
     const size_t cloud_bytes = sizeof(float4) * (size_t)n_head;
     if (cloud_mode && move_other && n_head == n_tail && batch >= kSgdCloudMinBatch && cloud_bytes <= kSgdCloudMaxBytes) {
       TDA_CUDA_CHECK(cudaFuncSetAttribute(sgd_cloud_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cloud_bytes));
@@ -1127,8 +1127,7 @@ extern "C" int tda_umap_sgd(float* Y, const float* Y_other, const int32_t* head,
       return TDA_OK;
     }
     if (!move_other) pack4_kernel<<<(unsigned)((np_t + 255) / 256), 256, 0, stream>>>(Y_other, Yt4, np_t);
-    const char* agg_env = getenv("TDA_SGD_AGG");
-    const bool agg_mode = agg_env && agg_env[0] == '1' && move_other && n_head == n_tail && slots % n_head == 0 && (slots / n_head) % 2 == 0;
+    const bool agg_mode = sgd_mode == 2 && move_other && n_head == n_tail && slots % n_head == 0 && (slots / n_head) % 2 == 0;
     for (int ep = 0; ep < n_epochs; ++ep) {
       const float alpha = ep == 0 ? alpha0 : alpha0 * (1.f - (float)(ep - 1) / (float)n_epochs);
       const int per_block = kSgdWarps * kSgdSlotsPerLane * 32;

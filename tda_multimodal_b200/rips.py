@@ -29,8 +29,17 @@ def pdist_lowdim(pts):
     return dm
 
 
-_STAT_NAMES = ["columns", "apparent", "reduced", "additions", "pushes", "pops", "extensions", "max_v", "cyc_extract",
-               "cyc_owner", "cyc_gen", "cyc_badd", "cyc_ext", "cyc_final", "badd_edges", "ext_edges"]
+# names of the device counters per reducer (include/tda_b200.h: tda_rips_stats)
+_STAT_NAMES = {
+    "sweep2": ["columns", "apparent", "reduced", "additions", "rows_substituted", "pivots", "windows", "max_v", "cyc_round1", "cyc_late_rounds",
+               "cyc_apply", "cyc_verify", "cyc_events", "cyc_pm_finalise", "edges_via_columns", "heavy_rows", "late_rounds", "late_rows",
+               "pm_rows_moved", "dense_columns", "spurious_stops", "flips_undone", "spare0", "spare1"],
+    "sweep": ["columns", "apparent", "reduced", "additions", "rows_streamed", "pivots", "restarts", "max_v", "cyc_filter", "row_groups",
+              "cyc_resolve", "cyc_column_add", "cyc_flip_patch", "cyc_dense_final", "edges_via_columns", "heavy_rows"],
+    "bitset": ["columns", "apparent", "reduced", "additions", "toggles", "pivots", "slides", "max_v", "cyc_scan", "cyc_owner", "cyc_gen",
+               "cyc_column_add", "cyc_slide", "cyc_final", "edges_via_columns", "far_keys"],
+}
+_STAT_NAMES["verify"] = _STAT_NAMES["sweep"]
 
 
 class RipsJob:
@@ -75,7 +84,7 @@ class RipsJob:
                                   want_simplices=self.want_simplices, want_stats=self.want_stats)
         stats = None
         if self.want_stats and self.maxdim >= 1:
-            stats = np.zeros((B, 16), dtype=np.int64)
+            stats = np.zeros((B, _lib.RIPS_STATS), dtype=np.int64)
             with torch.cuda.device(dm.device):
                 _lib.check(L.tda_rips_stats(_lib.ptr(self.ws), n, B, self.maxdim, self.cap1, self.pool_bytes, stats.ctypes.data))
         with torch.cuda.stream(self.stream):
@@ -94,7 +103,8 @@ class RipsJob:
             if self.want_simplices:
                 r["simplices"] = [h0s_h[p, :c0]] + ([h1s_h[p, :c1]] if self.maxdim >= 1 else [])
             if stats is not None:
-                r["stats"] = dict(zip(_STAT_NAMES, stats[p].tolist()))
+                names = _STAT_NAMES["bitset" if n > 8192 and _lib.rips_reducer() in ("sweep", "verify") else _lib.rips_reducer()]
+                r["stats"] = dict(zip(names, stats[p].tolist()))
             out.append(r)
         return out
 
@@ -106,7 +116,7 @@ def _default_sizes(torch, dm, cap1, pool_bytes):
     free_bytes = torch.cuda.mem_get_info(dev)[0]
     if pool_bytes is None:
         E = n * (n - 1) // 2
-        if os.environ.get("TDA_RIPS_REDUCER") == "bitset" or n > 8192:
+        if _lib.rips_reducer() == "bitset":
             # half of the pool holds one key window (bitset over the E*n triangle keys, <= 2^32 bits) per resident CTA,
             # the other half the reduction columns of finished columns
             sms = torch.cuda.get_device_properties(dev).multi_processor_count
@@ -172,7 +182,7 @@ def rips_batch(dm, maxdim=1, thresh=float("inf"), cap1=None, pool_bytes=None, wa
             break
         stats = None
         if want_stats and maxdim >= 1:
-            stats = np.zeros((B, 16), dtype=np.int64)
+            stats = np.zeros((B, _lib.RIPS_STATS), dtype=np.int64)
             _lib.check(L.tda_rips_stats(_lib.ptr(ws), n, B, maxdim, cap1, pool_bytes, stats.ctypes.data))
         h2_h = c2_h = None
         if want_h2:

@@ -15,3 +15,18 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture
+def tda_option():
+    """set_option(name, value) for the duration of a test (process-wide library options, restored afterwards)."""
+    from tda_multimodal_b200 import _lib
+    saved = {}
+
+    def setter(name, value):
+        if name not in saved:
+            saved[name] = _lib.get_option(name)
+        _lib.set_option(name, value)
+    yield setter
+    for k, v in saved.items():
+        _lib.set_option(k, v)

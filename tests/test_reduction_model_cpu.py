@@ -85,3 +85,19 @@ def test_models_on_ties_and_duplicates():
         for kw in (dict(), dict(window=16), dict(window=8, kernel_steps=True), dict(window=512, kernel_steps=True)):
             got, _ = orips.model_h1(dm, **kw)
             assert sorted(map(tuple, got)) == want, (trial, kind, n, kw)
+
+
+@pytest.mark.parametrize("cfg", [(1, 1, 1, 1, 8), (4, 16, 64, 2, 8), (32, 64, 64, 1, 1000000), (512, 8192, 65536, 64, 8)])
+def test_two_mode_model_equals_oracle(cfg):
+    """The control flow of the default GPU reducer (csrc/rips_sweep2.cuh): growing windows, substitution of every apparent row by
+    rank in dependency rounds, sparse mode (exact lunes) / dense mode (superset mask Pend[c] & Pend[d], failing rows re-checked in
+    ascending order with the exact lune, window end kept after an event).  cfg = (w0, wsparse, wmax, dense_min, dense_div)."""
+    clouds, _ = load_ref_rips_golden()
+    for c in clouds[::4]:
+        dm = orips.euclidean_dm_f32(c)
+        got, _ = orips.model_h1(dm, modes=cfg)
+        assert np.array_equal(got, orips.rips_dm(dm, maxdim=1)["dgms"][1])
+    for gen, n, seed in [(torus3d, 160, 5), (blobs3d, 250, 6), (circle2d, 120, 10), (torus3d, 420, 7)]:
+        dm = orips.euclidean_dm_f32(gen(n, np.random.default_rng(seed)))
+        got, st = orips.model_h1(dm, modes=cfg)
+        assert np.array_equal(got, orips.rips_dm(dm, maxdim=1)["dgms"][1]), (cfg, n, st)

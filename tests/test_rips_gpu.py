@@ -195,21 +195,3 @@ def test_full_size_invariants(torch_cuda):
     assert np.array_equal(c["dgms"][0][:-1] / 4.0, d0[:-1]) and same_diagram(c["dgms"][1] / 4.0, d1)
     pers = np.sort(d1[:, 1] - d1[:, 0])[::-1]
     assert pers[0] > 2 * pers[2]  # torus R=3, r=1: two dominant classes at most
-
-
-def test_bitset_reducer_fallback_matches(torch_cuda):
-    """The key-bitset reducer (used for n > 8192, selectable with TDA_RIPS_REDUCER=bitset) gives the same diagrams."""
-    import os, subprocess, sys, json
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    code = (
-        "import sys, json, numpy as np; sys.path.insert(0, %r)\n"
-        "from tests.helpers import torus3d\n"
-        "from tda_multimodal_b200 import rips\n"
-        "X = torus3d(500, np.random.default_rng(12))\n"
-        "d = rips.ripser(X, maxdim=1)['dgms']\n"
-        "print(json.dumps([d[0].tolist(), d[1].tolist()]))\n" % root)
-    outs = []
-    for mode in ("sweep", "bitset"):
-        env = dict(os.environ, TDA_RIPS_REDUCER=mode)
-        outs.append(json.loads(subprocess.check_output([sys.executable, "-c", code], env=env, text=True).strip().splitlines()[-1]))
-    assert outs[0] == outs[1] and len(outs[0][1]) > 5

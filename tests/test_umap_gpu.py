@@ -203,7 +203,7 @@ def test_fit_transform_trustworthiness_vs_oracle(torch_cuda, kind, n, k):
     assert um.graph_.shape == (n, n) and um._sigmas.shape == (n,) and um.embedding_ is Yg
 
 
-def test_sgd_cloud_kernel_matches_epoch_kernel(torch_cuda, monkeypatch):
+def test_sgd_cloud_kernel_matches_epoch_kernel(torch_cuda, tda_option):
     """The one-launch SGD (one CTA per cloud, embedding in shared memory, TDA_SGD_CLOUD=1) against the launch-per-epoch kernel
     on a batch of 8 clouds: same schedule and RNG keys, only the order of the float updates differs -- both embeddings must be
     finite, inside the clip box, equally trustworthy, and different from their common initialisation."""
@@ -214,7 +214,7 @@ def test_sgd_cloud_kernel_matches_epoch_kernel(torch_cuda, monkeypatch):
     Xd = torch.from_numpy(X).cuda()
     out = {}
     for mode in ("0", "1"):
-        monkeypatch.setenv("TDA_SGD_CLOUD", mode)
+        tda_option("sgd_mode", int(mode))
         Y = umap_.umap_fit_batch(Xd, n_neighbors=15, n_components=3, metric="cosine", random_state=42).cpu().numpy()
         assert Y.shape == (8, 400, 3) and np.isfinite(Y).all() and np.abs(Y).max() < 100
         out[mode] = Y
