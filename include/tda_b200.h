@@ -38,8 +38,10 @@ void tda_launch_count_reset(void);
  *   rips_reducer (0): residual H1 reducer -- 0 "sweep2" substitute by rank + verify by window, 1 row sweep with a sequential
  *                     resolver warp, 2 row sweep substitute-then-verify per 512-row chunk, 3 key bitset (any n)
  *   rips_w0 (1024), rips_wsparse (8192), rips_wmax (32768), rips_dense_min (64), rips_dense_div (8): sweep2 window schedule
- *   sweep_exclusive (0), sgd_mode (0: per-epoch kernel, 1: one CTA per cloud, 2: warp-aggregated), knn_loads (8),
- *   debug_sync (0), h2_stats (0) */
+ *   sgd_mode (0): 0 deterministic SGD (thread-block cluster per cloud for fit, warp per point for transform; bit-reproducible
+ *                 for a given seed), 3 per-epoch kernels with float atomics (used anyway for n > 8192 or n_components != 3)
+ *   sgd_cluster (4): CTAs per cloud of the deterministic fit kernel;  sweep_exclusive (0), knn_loads (8), debug_sync (0),
+ *   h2_stats (0) */
 int tda_set_option(const char* name, long long value);
 long long tda_get_option(const char* name);
 
@@ -99,8 +101,11 @@ int tda_fuzzy_graph(const int32_t* knn_idx, const float* knn_dist, const float* 
                     void* stream);
 /* tda_umap_sgd: optimize_layout_euclidean.  Y [batch,n_head,dim] in/out; Y_other [batch,n_tail,dim] (NULL and
  *   move_other=1 for fit: tail == head embedding); slot table as produced above; dim 1..4.
- *   ws (optional, 16-byte aligned, >= 16 * batch * (n_head + (move_other ? 0 : n_tail)) bytes): for dim == 3 the embedding is
- *   padded to float4 there for the duration of the call (one 16-byte load and one vector atomic per point). */
+ *   ws (256-byte aligned, tda_umap_sgd_workspace_bytes): the per-vertex adjacency of the deterministic fit kernel, or the
+ *   float4-padded embeddings of the per-epoch kernels.  With dim == 3 and option sgd_mode == 0 the result is bit-reproducible for
+ *   a given seed (all gradients of an epoch are evaluated on the positions of the epoch's start, every vertex sums its own
+ *   displacement in a fixed order); without ws, for n > 8192 or other dims the per-epoch kernels with float atomics run. */
+size_t tda_umap_sgd_workspace_bytes(int slots, int n_head, int n_tail, int dim, int batch, int move_other);
 int tda_umap_sgd(float* Y, const float* Y_other, const int32_t* head, const int32_t* tail, const float* eps, int slots, int n_head,
                  int n_tail, int dim, int batch, int n_epochs, float a, float b, float gamma, float alpha0,
                  float negative_sample_rate, int move_other, uint64_t seed, void* ws, size_t ws_bytes, void* stream);

@@ -1,11 +1,19 @@
 #!/bin/bash
-# sweep2 reducer: parity tests, then bench A/B against the old reducers.  gpurun --timeout 1200 -- 'bash scripts/gpu_check_sweep2.sh'
+# sweep2 reducer: parity tests, per-cloud statistics, bench A/B against the old reducers.
 set -u
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_rips_reducers_gpu.py -x -q 2>&1 | tail -15 | tee gpurun_out/sweep2_tests.log
-timeout 600 python -m pytest tests/test_rips_gpu.py tests/test_rips_h2_gpu.py -x -q 2>&1 | tail -8 | tee gpurun_out/sweep2_rips_tests.log
-for mode in sweep2 verify; do
+timeout 900 python -m pytest tests/test_rips_reducers_gpu.py -x -q 2>&1 | tail -5 | tee gpurun_out/sweep2_tests.log
+timeout 300 python scripts/rips_stats_c3.py 32 2>&1 | tee gpurun_out/sweep2_stats.log
+TDA_RIPS_W0=2048 TDA_RIPS_WSPARSE=16384 timeout 300 python scripts/rips_stats_c3.py 32 2>&1 | tail -4 | tee gpurun_out/sweep2_stats_w2048.log
+for mode in sweep2; do
   TDA_RIPS_REDUCER=$mode timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/bench_s2_$mode.json 2> gpurun_out/bench_s2_$mode.err
-  tail -c 1500 gpurun_out/bench_s2_$mode.json
-  echo
+  python - "$mode" <<'PY'
+import json, sys
+mode = sys.argv[1]
+try:
+    d = json.loads(open(f"gpurun_out/bench_s2_{mode}.json").read().strip().splitlines()[-1])
+    print(mode, "layers/s", round(d["value"], 1), "e2e", round(d["e2e"]["value"], 1), "ms/step", round(d["ms_per_step"], 1), d["roofline"]["stages_ms_per_step"])
+except Exception as ex:
+    print(mode, "bench failed:", ex); print(open(f"gpurun_out/bench_s2_{mode}.err").read()[-3000:])
+PY
 done

@@ -27,6 +27,7 @@ PROTOTYPES = {
                                 c_void_p, c_void_p, c_void_p, c_void_p]),
     "tda_umap_sgd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                              c_float, c_float, c_float, c_float, c_int, ctypes.c_uint64, c_void_p, c_size_t, c_void_p]),
+    "tda_umap_sgd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "tda_umap_init_random": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, ctypes.c_uint64, c_void_p]),
     "tda_umap_rescale": (c_int, [c_void_p, c_int, c_int, c_int, c_float, ctypes.c_uint64, c_void_p]),
     "tda_umap_transform_init": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
@@ -58,9 +59,7 @@ _ENV_OPTIONS = {
     "TDA_RIPS_W0": ("rips_w0", int), "TDA_RIPS_WSPARSE": ("rips_wsparse", int), "TDA_RIPS_WMAX": ("rips_wmax", int),
     "TDA_RIPS_DENSE_MIN": ("rips_dense_min", int), "TDA_RIPS_DENSE_DIV": ("rips_dense_div", int),
     "TDA_SWEEP_EXCLUSIVE": ("sweep_exclusive", int),
-    "TDA_SGD_CLOUD": ("sgd_mode", lambda v: 1 if v == "1" else 0),
-    "TDA_SGD_AGG": ("sgd_mode", lambda v: 2 if v == "1" else 0),
-    "TDA_SGD_MODE": ("sgd_mode", int),
+    "TDA_SGD_MODE": ("sgd_mode", int), "TDA_SGD_CLUSTER": ("sgd_cluster", int),
     "TDA_KNN_LOADS": ("knn_loads", int), "TDA_DEBUG_SYNC": ("debug_sync", lambda v: 1), "TDA_H2_STATS": ("h2_stats", lambda v: 1),
 }
 

@@ -73,7 +73,8 @@ static OptionDef g_options[] = {
     {"rips_dense_min", 64},    // sweep2: a window with >= max(dense_min, rows / dense_div) heavy rows switches the column to dense mode
     {"rips_dense_div", 8},
     {"sweep_exclusive", 0},    // reducers 1/2: ask for the whole shared memory of the SM
-    {"sgd_mode", 0},           // 0 per-epoch kernel (float4 atomics), 1 one CTA per cloud, 2 warp-aggregated per-epoch kernel
+    {"sgd_mode", 0},           // 0 deterministic kernels (cluster per cloud for fit, warp per point for transform), 3 per-epoch kernels with float atomics
+    {"sgd_cluster", 4},        // CTAs per cloud of the deterministic fit kernel (1, 2, 4 or 8)
     {"knn_loads", 8},          // 16-byte loads per lane in flight in the k <= 16 kNN kernel (8 or 16)
     {"debug_sync", 0},         // synchronise after every kernel of tda_rips_h2 (fault location)
     {"h2_stats", 0},           // print the H2 reducer's device counters to stderr

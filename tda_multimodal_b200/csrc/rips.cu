@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(256) boruvka_scan_kernel(const int* __restrict
 __global__ void __launch_bounds__(1024) boruvka_merge_kernel(const uint32_t* __restrict__ ends, int n, int64_t E, uint32_t* __restrict__ comp_g,
                                                              uint32_t* __restrict__ parent_g, uint32_t* __restrict__ cbest_g,
                                                              uint8_t* __restrict__ mst, int* __restrict__ done,
-                                                             int* __restrict__ mstlist_g, int* __restrict__ mstcount) {
+                                                             int* __restrict__ mstlist_g, int mst_stride, int* __restrict__ mstcount) {
   const int p = blockIdx.x;
   if (done[p]) return;
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(1024) boruvka_merge_kernel(const uint32_t* __r
       // ... but it enters the MST list once: two components that picked each other did so through this edge; the smaller id lists it
       if (!(cbest[par] == r && par < (uint32_t)c)) {
         const int pos = atomicAdd(&mstcount[p], 1);
-        if (pos < n) mstlist_g[(size_t)p * n + pos] = (int)r;
+        if (pos < n) mstlist_g[(size_t)p * mst_stride + pos] = (int)r;
       }
       merged = 1;
     }
@@ -205,12 +205,12 @@ __global__ void __launch_bounds__(1024) boruvka_merge_kernel(const uint32_t* __r
 }
 
 // sort the MST ranks (collected by the merge kernel), emit the H0 rows.  One CTA per cloud; the list is sorted in shared
-// memory when it fits (n <= 8192), else in place in global memory.
+// memory when it fits (n <= 8192), else in place in global memory (the per-problem list is padded to a power of two).
 __global__ void __launch_bounds__(1024) h0_emit_kernel(const uint32_t* __restrict__ ends, const float* __restrict__ sdist,
                                                        const int* __restrict__ Tarr, int n, int64_t E, const int* __restrict__ mstcount,
                                                        const uint32_t* __restrict__ comp_g, float* __restrict__ h0_pairs,
                                                        int64_t* __restrict__ h0_simplex, int32_t* __restrict__ counts, int* __restrict__ mstlist_g,
-                                                       int use_smem) {
+                                                       int mst_stride, int use_smem) {
   extern __shared__ int s_list[];
   __shared__ int s_zero, s_rows;
   __shared__ int s_wcnt[32];
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(1024) h0_emit_kernel(const uint32_t* __restric
   const uint32_t* EN = ends + (size_t)p * E;
   const uint32_t* comp = comp_g + (size_t)p * n;
   const int T = Tarr[p];
-  int* glist = mstlist_g + (size_t)p * n;
+  int* glist = mstlist_g + (size_t)p * mst_stride;
   const int nm = min(mstcount[p], n - 1);
   int np2 = 1;
   while (np2 < nm) np2 <<= 1;
@@ -227,31 +227,22 @@ __global__ void __launch_bounds__(1024) h0_emit_kernel(const uint32_t* __restric
   if (tid == 0) { s_zero = 0; s_rows = 0; }
   if (use_smem)
     for (int i = tid; i < nm; i += nt) s_list[i] = glist[i];
-  if (np2 <= n || use_smem) {
-    for (int i = nm + tid; i < np2; i += nt) list[i] = 0x7fffffff;
-    __syncthreads();
-    for (int k = 2; k <= np2; k <<= 1)
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int i = tid; i < np2; i += nt) {
-          const int ixj = i ^ j;
-          if (ixj > i) {
-            const int a = list[i], b = list[ixj];
-            const bool up = ((i & k) == 0);
-            if ((a > b) == up) { list[i] = b; list[ixj] = a; }
-          }
+  // bitonic sort of the list padded to a power of two (the per-problem list holds next_pow2(n) entries)
+  for (int i = nm + tid; i < np2; i += nt) list[i] = 0x7fffffff;
+  __syncthreads();
+  for (int k = 2; k <= np2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < np2; i += nt) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const int a = list[i], b = list[ixj];
+          const bool up = ((i & k) == 0);
+          if ((a > b) == up) { list[i] = b; list[ixj] = a; }
         }
-        __syncthreads();
       }
-  } else {  // np2 > n only for tiny n without the shared-memory copy: serial insertion sort
-    __syncthreads();
-    if (tid == 0)
-      for (int i = 1; i < nm; ++i) {
-        int v = list[i], k = i - 1;
-        while (k >= 0 && list[k] > v) { list[k + 1] = list[k]; --k; }
-        list[k + 1] = v;
-      }
-    __syncthreads();
-  }
+      if (!use_smem) __threadfence_block();
+      __syncthreads();
+    }
   // rows: (0, d) for d != 0 ascending, then one (0, inf) per remaining component.  Zero-length merging
   // edges have the smallest ranks, so they are a prefix of the sorted list.
   float* out = h0_pairs + (size_t)p * n * 2;
@@ -397,7 +388,7 @@ struct ReduceParams {
   int verify_mode;                          // sweep reducer: substitute-then-verify instead of the sequential resolver (opt-in)
   // sweep2 reducer (rips_sweep2.cuh)
   const uint2* par;                         // [batch, E] parents of the apparent edges (rank | apparent << 31)
-  uint2* s2_pend; uint2* s2_heavy; uint32_t* s2_fail;   // per-CTA spill lists: [grid, 2, wmax + 64], [grid, wmax + 64], [grid, kS2FailCap]
+  uint2* s2_pend; uint2* s2_heavy;          // per-CTA spill lists: [grid, 2, wmax + 64], [grid, wmax + 64]
   int s2_w0, s2_wsparse, s2_wmax, s2_dense_min, s2_dense_div;
 };
 
@@ -2105,7 +2096,7 @@ struct Layout {
   bool sweep;                       // one of the row-sweep reducers (X / Pm bit matrices) rather than the key bitset
   int reducer;                      // 0 sweep2, 1 sweep (resolver), 2 sweep (verify), 3 bitset
   uint2* par;                       // parents of the apparent edges (sweep2)
-  uint2* s2_pend; uint2* s2_heavy; uint32_t* s2_fail; int s2_wmax;
+  uint2* s2_pend; uint2* s2_heavy; int s2_wmax;
   int* work_counter; unsigned long long* stats;
   int grid; size_t total;
 };
@@ -2143,7 +2134,7 @@ static Layout make_layout(void* ws, int n, int batch, int maxdim, int cap1, size
   L.thresh_bits = c.take<uint32_t>(batch);
   L.T = c.take<int>(batch);
   L.mst = c.take<uint8_t>(BE);
-  L.mstlist = c.take<int>((int64_t)batch * n);
+  L.mstlist = c.take<int>((int64_t)batch * next_pow2(n));
   L.mstcount = c.take<int>(batch);
   L.comp = c.take<uint32_t>((int64_t)batch * n);
   L.parent = c.take<uint32_t>((int64_t)batch * n);
@@ -2173,7 +2164,6 @@ static Layout make_layout(void* ws, int n, int batch, int maxdim, int cap1, size
       L.s2_wmax = s2_wmax_option();
       L.s2_pend = c.take<uint2>((size_t)L.grid * 2 * (size_t)(L.s2_wmax + 64));
       L.s2_heavy = c.take<uint2>((size_t)L.grid * (size_t)(L.s2_wmax + 64));
-      L.s2_fail = c.take<uint32_t>((size_t)L.grid * kS2FailCap);
     }
     if (L.sweep) {
       L.xmat = c.take<uint32_t>((size_t)L.grid * (size_t)n * L.xw);
@@ -2297,7 +2287,7 @@ static int rips_enqueue(const float* dm, int n, int batch, int maxdim, float thr
     dim3 gs((n + 7) / 8, batch);
     for (int r = 0; r < rounds && E > 0; ++r) {
       boruvka_scan_kernel<<<gs, 256, 0, stream>>>(L.rank, L.T, n, L.comp, L.cbest, L.done);
-      boruvka_merge_kernel<<<batch, 1024, 0, stream>>>(L.ends, n, E, L.comp, L.parent, L.cbest, L.mst, L.done, L.mstlist, L.mstcount);
+      boruvka_merge_kernel<<<batch, 1024, 0, stream>>>(L.ends, n, E, L.comp, L.parent, L.cbest, L.mst, L.done, L.mstlist, next_pow2(n), L.mstcount);
       count_launch(2);
     }
     {
@@ -2305,7 +2295,7 @@ static int rips_enqueue(const float* dm, int n, int batch, int maxdim, float thr
       while (np2 < n) np2 <<= 1;
       const int use_smem = np2 <= 8192;
       h0_emit_kernel<<<batch, 1024, use_smem ? sizeof(int) * (size_t)np2 : 0, stream>>>(L.ends, L.sdist, L.T, n, E, L.mstcount, L.comp, h0_pairs,
-                                                                                       h0_simplex, counts, L.mstlist, use_smem);
+                                                                                       h0_simplex, counts, L.mstlist, np2, use_smem);
     }
     count_launch();
     TDA_LAUNCH_CHECK();
@@ -2333,7 +2323,7 @@ static int rips_enqueue(const float* dm, int n, int batch, int maxdim, float thr
     P.work_counter = L.work_counter; P.stats = L.stats;
     P.apex4 = nullptr; P.far = nullptr; P.far_cap = 0; P.nbk = 0;
     P.verify_mode = L.reducer == 2 ? 1 : 0;
-    P.par = L.par; P.s2_pend = L.s2_pend; P.s2_heavy = L.s2_heavy; P.s2_fail = L.s2_fail;
+    P.par = L.par; P.s2_pend = L.s2_pend; P.s2_heavy = L.s2_heavy;
     P.s2_wmax = L.s2_wmax;
     P.s2_w0 = (int)option("rips_w0");
     if (P.s2_w0 < 32) P.s2_w0 = 32;

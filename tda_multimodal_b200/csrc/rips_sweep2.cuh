@@ -27,10 +27,11 @@
 constexpr int kS2Threads = 512;
 constexpr int kS2Warps = kS2Threads / 32;
 constexpr int kS2ListSmem = 2048;      // entries of the pending / heavy lists kept in shared memory (the rest spills to global scratch)
-constexpr int kS2FailCap = 4096;       // failing rows of a dense window that are recorded (more: fall back to the minimum alone)
 constexpr int kS2MaxRounds = 4096;     // substitution rounds per window (depth of the apparent graph is ~30): beyond -> internal error
 constexpr int kS2MaxWindow = 65472;    // rows of a window (16-bit local indices in the pending entries)
-constexpr int kS2Batch = 4;            // heavy rows a warp verifies at once (dense mode)
+constexpr int kS2Batch = 4;            // heavy rows a warp verifies at once
+constexpr int kS2Unroll = 4;           // 32-row groups a warp keeps in flight in the first substitution round
+constexpr int kS2ProbeMax = 256;       // candidate bits of a row up to which they are probed one by one (more: the whole lune at once)
 enum { TDA_ERR_INTERNAL_S2 = -6 };
 
 struct Sweep2Smem {
@@ -49,12 +50,12 @@ struct Sweeper2 {
   static constexpr unsigned kFull = 0xffffffffu;
   const ReduceParams& P;
   Sweep2Smem& S;
-  uint32_t *touched, *tnew, *xs, *done;
+  uint32_t *touched, *tnew, *xs, *xo, *done;
   uint2 *pend_s, *heavy_s;     // [2][kS2ListSmem], [kS2ListSmem]
   const int tid, lane, warp;
   const int* R; const uint32_t* EN; const uint2* EA; const uint2* PAR; int T; int n; int W;
   uint32_t *X, *Pm, *vbits, *vl0;
-  uint2 *pend_g, *heavy_g; uint32_t* fail_g;
+  uint2 *pend_g, *heavy_g;
   uint32_t p_pos; bool p_valid;
   uint64_t* hkeys; int* hvals;
 
@@ -66,8 +67,9 @@ struct Sweeper2 {
     touched = dyn;
     tnew = touched + W;
     xs = tnew + W;
-    done = xs + nw;
-    pend_s = reinterpret_cast<uint2*>(done + nw + ((2 * W + 2 * nw) & 1));   // 8-byte aligned
+    xo = xs + nw;
+    done = xo + nw;
+    pend_s = reinterpret_cast<uint2*>(done + nw + ((2 * W + 3 * nw) & 1));   // 8-byte aligned
     heavy_s = pend_s + 2 * kS2ListSmem;
     X = P.xmat + (size_t)blockIdx.x * (size_t)n * W;
     Pm = P.pmat + (size_t)blockIdx.x * (size_t)n * W;
@@ -76,11 +78,10 @@ struct Sweeper2 {
     vl0 = P.vlist + (size_t)blockIdx.x * 2 * P.vcap;
     pend_g = P.s2_pend + (size_t)blockIdx.x * 2 * (size_t)(P.s2_wmax + 64);
     heavy_g = P.s2_heavy + (size_t)blockIdx.x * (size_t)(P.s2_wmax + 64);
-    fail_g = P.s2_fail + (size_t)blockIdx.x * kS2FailCap;
   }
   static __host__ __device__ size_t dyn_bytes(int W, int wmax) {
     const int nw = wmax / 32 + 4;
-    return sizeof(uint32_t) * (size_t)(2 * W + 2 * nw + 2) + sizeof(uint2) * (size_t)(3 * kS2ListSmem);
+    return sizeof(uint32_t) * (size_t)(2 * W + 3 * nw + 2) + sizeof(uint2) * (size_t)(3 * kS2ListSmem);
   }
   __device__ __forceinline__ uint32_t* vlist(uint32_t sel) const { return vl0 + (size_t)sel * P.vcap; }
   __device__ __forceinline__ bool tbit(uint32_t v) const { return (touched[v >> 5] >> (v & 31)) & 1u; }
@@ -202,15 +203,21 @@ struct Sweeper2 {
 
   // ---- Pm = adjacency bit matrix of the edges with rank < p_pos.  All threads; ends with the bits performed and a barrier.
   __device__ __forceinline__ void p_set_rows(uint32_t lo, uint32_t hi, bool set) {
-    for (uint32_t row = lo + tid; row < hi; row += kS2Threads) {
-      const uint32_t en = __ldg(&EN[row]);
-      const uint32_t c = en >> 16, d = en & 0xffffu;
-      if (set) {
-        atomicOr(&Pm[(size_t)c * W + (d >> 5)], 1u << (d & 31));
-        atomicOr(&Pm[(size_t)d * W + (c >> 5)], 1u << (c & 31));
-      } else {
-        atomicAnd(&Pm[(size_t)c * W + (d >> 5)], ~(1u << (d & 31)));
-        atomicAnd(&Pm[(size_t)d * W + (c >> 5)], ~(1u << (c & 31)));
+    for (uint32_t row0 = lo + tid; row0 < hi; row0 += 4 * kS2Threads) {
+      uint32_t en[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const uint32_t row = row0 + u * kS2Threads; en[u] = row < hi ? __ldg(&EN[row]) : 0xffffffffu; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (en[u] == 0xffffffffu) continue;
+        const uint32_t c = en[u] >> 16, d = en[u] & 0xffffu;
+        if (set) {
+          atomicOr(&Pm[(size_t)c * W + (d >> 5)], 1u << (d & 31));
+          atomicOr(&Pm[(size_t)d * W + (c >> 5)], 1u << (c & 31));
+        } else {
+          atomicAnd(&Pm[(size_t)c * W + (d >> 5)], ~(1u << (d & 31)));
+          atomicAnd(&Pm[(size_t)d * W + (c >> 5)], ~(1u << (c & 31)));
+        }
       }
     }
   }
@@ -364,41 +371,59 @@ struct Sweeper2 {
         __syncthreads();
         const uint32_t vmark = S.vcount;
         t0 = clock64();
-        // ---- substitution, round 1: every row of the window, one warp per 32 consecutive ranks
-        for (uint32_t g = g0 + warp; g < g1; g += kS2Warps) {
-          const uint32_t row = (g << 5) + lane;
-          const bool inwin = row >= pos && row < hi;
-          const uint32_t xold = __ldcg(&vbits[g]);
-          uint2 ea = make_uint2(0u, 0xffffffffu);
-          if (inwin) ea = __ldg(&EA[row]);
-          const bool app = inwin && (int)ea.y >= 0;
-          uint2 par = make_uint2(0u, 0u);
-          if (app) par = __ldg(&PAR[row]);
-          const uint32_t pa = par.x & 0x7fffffffu, pb = par.y & 0x7fffffffu;
-          const bool depA = app && (par.x >> 31) && pa >= pos;   // the parent is an apparent row of this window: not final yet
-          const bool depB = app && (par.y >> 31) && pb >= pos;
-          const uint32_t c = ea.x >> 16, d = ea.x & 0xffffu, a = ea.y;
-          uint32_t base = 0;
-          bool heavy = false;
-          if (app) {
-            const bool tc = tbit(c), td = tbit(d), ta = tbit(a);
-            heavy = tc || td;
-            // a final parent edge with x = 1 has both endpoints touched (touched = as of the start of the window)
-            if (!depA && ta && tc) base ^= xg(pa);
-            if (!depB && ta && td) base ^= xg(pb);
+        // ---- substitution, round 1: every row of the window, one warp per 32 consecutive ranks, kS2Unroll groups in flight
+        for (uint32_t gb = g0 + warp * kS2Unroll; gb < g1; gb += kS2Warps * kS2Unroll) {
+          uint32_t xold[kS2Unroll];
+          uint2 ea[kS2Unroll], par[kS2Unroll];
+#pragma unroll
+          for (int u = 0; u < kS2Unroll; ++u) {
+            const uint32_t g = gb + u;
+            const uint32_t row = (g << 5) + lane;
+            const bool inwin = g < g1 && row >= pos && row < hi;
+            xold[u] = g < g1 ? __ldcg(&vbits[g]) : 0u;
+            ea[u] = make_uint2(0u, 0xffffffffu);
+            par[u] = make_uint2(0u, 0u);
+            if (inwin) { ea[u] = __ldg(&EA[row]); par[u] = __ldg(&PAR[row]); }
           }
-          const bool computed = app && !depA && !depB;
-          const unsigned bapp = __ballot_sync(kFull, app);
-          const unsigned bone = __ballot_sync(kFull, computed && base);
-          const unsigned bdone = __ballot_sync(kFull, computed);
-          if (lane == 0) { xs[g - g0] = (xold & ~bapp) | bone; done[g - g0] = bdone; }
-          const bool pend = app && (depA || depB);
-          const uint2 pent = make_uint2((row - base_row) | (base << 31) | ((depA ? 1u : 0u) << 30) | ((depB ? 1u : 0u) << 29),
-                                        (depA ? (pa - base_row) : 0u) | ((depB ? (pb - base_row) : 0u) << 16));
-          warp_append(pend, pent, &S.npend[0], [&](uint32_t i) { return pend_ref(0, i); });
-          warp_append(heavy, make_uint2(row, ea.x), &S.nheavy, [&](uint32_t i) { return heavy_ref(i); });
+          uint32_t base[kS2Unroll];
+#pragma unroll
+          for (int u = 0; u < kS2Unroll; ++u) {
+            base[u] = 0;
+            if ((int)ea[u].y >= 0) {
+              const uint32_t pa = par[u].x & 0x7fffffffu, pb = par[u].y & 0x7fffffffu;
+              const bool depA = (par[u].x >> 31) && pa >= pos, depB = (par[u].y >> 31) && pb >= pos;
+              const uint32_t c = ea[u].x >> 16, d = ea[u].x & 0xffffu, a = ea[u].y;
+              const bool tc = tbit(c), td = tbit(d), ta = tbit(a);
+              // a final parent edge with x = 1 has both endpoints touched (touched = as of the start of the window)
+              uint32_t xa = 0, xb = 0;
+              if (!depA && ta && tc) xa = __ldcg(&vbits[pa >> 5]) >> (pa & 31);
+              if (!depB && ta && td) xb = __ldcg(&vbits[pb >> 5]) >> (pb & 31);
+              base[u] = (xa ^ xb) & 1u;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kS2Unroll; ++u) {
+            const uint32_t g = gb + u;
+            if (g >= g1) break;
+            const uint32_t row = (g << 5) + lane;
+            const bool app = (int)ea[u].y >= 0;   // (rows outside the window carry apex = -1)
+            const uint32_t pa = par[u].x & 0x7fffffffu, pb = par[u].y & 0x7fffffffu;
+            const bool depA = app && (par[u].x >> 31) && pa >= pos;   // the parent is an apparent row of this window: not final yet
+            const bool depB = app && (par[u].y >> 31) && pb >= pos;
+            const uint32_t c = ea[u].x >> 16, d = ea[u].x & 0xffffu;
+            const bool heavy = app && (tbit(c) || tbit(d));
+            const bool computed = app && !depA && !depB;
+            const unsigned bapp = __ballot_sync(kFull, app);
+            const unsigned bone = __ballot_sync(kFull, computed && base[u]);
+            const unsigned bdone = __ballot_sync(kFull, computed);
+            if (lane == 0) { xo[g - g0] = xold[u]; xs[g - g0] = (xold[u] & ~bapp) | bone; done[g - g0] = bdone; }
+            const bool pend = app && (depA || depB);
+            const uint2 pent = make_uint2((row - base_row) | (base[u] << 31) | ((depA ? 1u : 0u) << 30) | ((depB ? 1u : 0u) << 29),
+                                          (depA ? (pa - base_row) : 0u) | ((depB ? (pb - base_row) : 0u) << 16));
+            warp_append(pend, pent, &S.npend[0], [&](uint32_t i) { return pend_ref(0, i); });
+            warp_append(heavy, make_uint2(row, ea[u].x), &S.nheavy, [&](uint32_t i) { return heavy_ref(i); });
+          }
         }
-        __threadfence();
         __syncthreads();
         cyc[0] += clock64() - t0;
         t0 = clock64();
@@ -434,7 +459,6 @@ struct Sweeper2 {
               }
               warp_append(have && !ready, ent, &S.npend[(r + 1) % 3], [&](uint32_t j) { return pend_ref(wb, j); });
             }
-            __threadfence();
             __syncthreads();
             if (S.npend[(r + 1) % 3] == np) { if (tid == 0) fail(TDA_ERR_INTERNAL_S2); __syncthreads(); break; }   // no progress: broken order
             ++r;
@@ -445,27 +469,30 @@ struct Sweeper2 {
         cyc[1] += clock64() - t0;
         t0 = clock64();
         // ---- apply: the rows whose x changed flip in X / the V list; the global x words are rewritten (one owner per word)
-        for (uint32_t g = g0 + warp; g < g1; g += kS2Warps) {
-          const uint32_t xold = __ldcg(&vbits[g]);
-          const uint32_t xnew = xs[g - g0];
-          const uint32_t diff = xold ^ xnew;
-          if (diff) {
-            uint32_t vb = 0;
-            if (lane == 0) { __stcg(&vbits[g], xnew); vb = atomicAdd(&S.vcount, (uint32_t)__popc(diff)); }
-            vb = __shfl_sync(kFull, vb, 0);
-            if ((diff >> lane) & 1u) {
-              const uint32_t row = (g << 5) + lane;
-              const uint32_t en = __ldg(&EA[row]).x;
-              const uint32_t c = en >> 16, d = en & 0xffffu;
-              x_flip(c, d);
-              touch(c); touch(d);
-              const uint32_t vp = vb + __popc(diff & ((1u << lane) - 1));
-              if (vp < (uint32_t)P.vcap) vlist(S.vsel)[vp] = row;
-              else fail(TDA_ERR_CAPACITY);
+        {
+          bool flipped = false;
+          for (uint32_t g = g0 + warp; g < g1; g += kS2Warps) {
+            const uint32_t xnew = xs[g - g0];
+            const uint32_t diff = xo[g - g0] ^ xnew;
+            if (diff) {
+              uint32_t vb = 0;
+              if (lane == 0) { __stcg(&vbits[g], xnew); vb = atomicAdd(&S.vcount, (uint32_t)__popc(diff)); }
+              vb = __shfl_sync(kFull, vb, 0);
+              if ((diff >> lane) & 1u) {
+                const uint32_t row = (g << 5) + lane;
+                const uint32_t en = __ldg(&EA[row]).x;
+                const uint32_t c = en >> 16, d = en & 0xffffu;
+                x_flip(c, d);
+                touch(c); touch(d);
+                const uint32_t vp = vb + __popc(diff & ((1u << lane) - 1));
+                if (vp < (uint32_t)P.vcap) vlist(S.vsel)[vp] = row;
+                else fail(TDA_ERR_CAPACITY);
+              }
+              flipped = true;
             }
           }
+          if (flipped) __threadfence();   // the flips are REDs: performed before anybody reads X after the barrier
         }
-        __threadfence();
         __syncthreads();
         if (S.abort_flag) break;
         if (tid == 0) S.st[S2_FLIPS] += S.vcount - vmark;
@@ -484,7 +511,6 @@ struct Sweeper2 {
             }
             warp_append(h, make_uint2(row, ea.x), &S.nheavy, [&](uint32_t i) { return heavy_ref(i); });
           }
-          __threadfence();
           __syncthreads();
         }
         cyc[2] += clock64() - t0;
@@ -498,109 +524,93 @@ struct Sweeper2 {
         if (dense) p_move(hi);
         cyc[5] += clock64() - t0;
         t0 = clock64();
-        // ---- verification of the heavy rows
-        if (!dense) {
-          for (uint32_t i = warp; i < nh; i += kS2Warps) {
-            const uint2 ent = *heavy_ref(i);
-            const uint32_t M = ent.x, c = ent.y >> 16, d = ent.y & 0xffffu;
-            const uint32_t xm = xg(M) ? 0xffffffffu : 0u;
-            const int w = exact_row(M, c, d, xm);
-            if (w >= 0 && lane == 0) atomicMin(&S.fail_key, (unsigned long long)M * (unsigned long long)n + (unsigned long long)(n - 1 - w));
+        // ---- verification of the heavy rows, kS2Batch rows per warp in flight.  Candidate bits of a row: (x_M ^ X[c] ^ X[d]), in
+        // dense mode masked with Pend[c] & Pend[d]; a candidate w is a true failure iff rank(c,w) < M and rank(d,w) < M (two
+        // probes of the rank matrix).  The smallest true failing key of the window is the event.
+        for (uint32_t i0 = warp * kS2Batch; i0 < nh; i0 += kS2Warps * kS2Batch) {
+          uint32_t Mr[kS2Batch], cd[kS2Batch], xm[kS2Batch];
+#pragma unroll
+          for (int b = 0; b < kS2Batch; ++b) {
+            const uint32_t i = i0 + b;
+            uint2 ent = make_uint2(0xffffffffu, 0u);
+            if (i < nh) ent = *heavy_ref(i);
+            Mr[b] = ent.x; cd[b] = ent.y;
+            const uint32_t rl = ent.x - base_row;
+            xm[b] = (i < nh && ((xs[rl >> 5] >> (rl & 31)) & 1u)) ? 0xffffffffu : 0u;
           }
-        } else {
-          for (uint32_t i0 = warp * kS2Batch; i0 < nh; i0 += kS2Warps * kS2Batch) {
-            uint32_t Mr[kS2Batch], xmw[kS2Batch];
-            const uint32_t *Xc[kS2Batch], *Xd[kS2Batch], *Pc[kS2Batch], *Pd[kS2Batch];
+          for (int k0 = 0; k0 < W; k0 += 64) {   // W is even, rows are 8-byte aligned; the loop is warp-uniform
+            const int k = k0 + 2 * lane;
+            const bool kin = k < W;
+            uint2 cw[kS2Batch];
 #pragma unroll
             for (int b = 0; b < kS2Batch; ++b) {
-              const uint32_t i = i0 + b;
-              uint2 ent = make_uint2(0u, 0u);
-              if (i < nh) ent = *heavy_ref(i);
-              Mr[b] = i < nh ? ent.x : 0xffffffffu;
-              const uint32_t c = ent.y >> 16, d = ent.y & 0xffffu;
-              Xc[b] = X + (size_t)c * W; Xd[b] = X + (size_t)d * W; Pc[b] = Pm + (size_t)c * W; Pd[b] = Pm + (size_t)d * W;
-              xmw[b] = i < nh ? __ldcg(&vbits[ent.x >> 5]) : 0u;
-            }
-            uint32_t any[kS2Batch];
-#pragma unroll
-            for (int b = 0; b < kS2Batch; ++b) any[b] = 0;
-            for (int k = 2 * lane; k < W; k += 64) {   // W is even, rows are 8-byte aligned
-              uint2 a[kS2Batch][4];
-#pragma unroll
-              for (int b = 0; b < kS2Batch; ++b) {
-                a[b][0] = __ldcg(reinterpret_cast<const uint2*>(Xc[b] + k));
-                a[b][1] = __ldcg(reinterpret_cast<const uint2*>(Xd[b] + k));
-                a[b][2] = __ldcg(reinterpret_cast<const uint2*>(Pc[b] + k));
-                a[b][3] = __ldcg(reinterpret_cast<const uint2*>(Pd[b] + k));
-              }
-#pragma unroll
-              for (int b = 0; b < kS2Batch; ++b) {
-                const uint32_t xm = (Mr[b] != 0xffffffffu && ((xmw[b] >> (Mr[b] & 31)) & 1u)) ? 0xffffffffu : 0u;
-                any[b] |= ((xm ^ a[b][0].x ^ a[b][1].x) & a[b][2].x & a[b][3].x) | ((xm ^ a[b][0].y ^ a[b][1].y) & a[b][2].y & a[b][3].y);
+              const uint32_t c = cd[b] >> 16, d = cd[b] & 0xffffu;
+              cw[b] = make_uint2(0u, 0u);
+              if (kin) {
+                const uint2 xc = __ldcg(reinterpret_cast<const uint2*>(X + (size_t)c * W + k));
+                const uint2 xd = __ldcg(reinterpret_cast<const uint2*>(X + (size_t)d * W + k));
+                cw[b] = make_uint2(xm[b] ^ xc.x ^ xd.x, xm[b] ^ xc.y ^ xd.y);
+                if (dense) {
+                  const uint2 pc = __ldcg(reinterpret_cast<const uint2*>(Pm + (size_t)c * W + k));
+                  const uint2 pd = __ldcg(reinterpret_cast<const uint2*>(Pm + (size_t)d * W + k));
+                  cw[b].x &= pc.x & pd.x; cw[b].y &= pc.y & pd.y;
+                }
               }
             }
 #pragma unroll
             for (int b = 0; b < kS2Batch; ++b) {
-              const bool bad = __any_sync(kFull, any[b] != 0) && Mr[b] != 0xffffffffu;
-              if (bad && lane == 0) {
-                atomicMin(&S.fail_row, Mr[b]);
-                const uint32_t fi = atomicAdd(&S.nfail, 1u);
-                if (fi < (uint32_t)kS2FailCap) fail_g[fi] = Mr[b];
+              if (Mr[b] == 0xffffffffu) continue;
+              const bool any = __any_sync(kFull, (cw[b].x | cw[b].y) != 0);
+              if (!any) continue;
+              const uint32_t c = cd[b] >> 16, d = cd[b] & 0xffffu;
+              // a later row than the best failure found so far cannot be the event (one lane reads: the test must be warp-uniform)
+              unsigned long long fk_now = 0;
+              if (lane == 0) fk_now = *(volatile unsigned long long*)&S.fail_key;
+              fk_now = __shfl_sync(kFull, fk_now, 0);
+              if ((unsigned long long)Mr[b] * (unsigned long long)n > fk_now) continue;
+              const int npop = __reduce_add_sync(kFull, (unsigned)(__popc(cw[b].x) + __popc(cw[b].y)));
+              int best = -1;
+              if (npop <= kS2ProbeMax) {
+                // probe this lane's candidates from the highest vertex down; the first true one is this lane's highest
+                const int* Rc = R + (size_t)c * n;
+                const int* Rd = R + (size_t)d * n;
+                uint32_t wy = cw[b].y, wx = cw[b].x;
+                while (wy) {
+                  const int bit = 31 - __clz(wy);
+                  wy &= ~(1u << bit);
+                  const int w = (k + 1) * 32 + bit;
+                  if (w < n && __ldg(&Rc[w]) < (int)Mr[b] && __ldg(&Rd[w]) < (int)Mr[b]) { best = w; wy = 0; wx = 0; }
+                }
+                while (wx) {
+                  const int bit = 31 - __clz(wx);
+                  wx &= ~(1u << bit);
+                  const int w = k * 32 + bit;
+                  if (w < n && __ldg(&Rc[w]) < (int)Mr[b] && __ldg(&Rd[w]) < (int)Mr[b]) { best = w; wx = 0; }
+                }
+                best = __reduce_max_sync(kFull, best);
+              } else {
+                best = exact_row(Mr[b], c, d, xm[b]);   // (dense candidate set: the whole lune at once, coalesced)
               }
+              if (best >= 0 && lane == 0) {
+                const unsigned long long key = (unsigned long long)Mr[b] * (unsigned long long)n + (unsigned long long)(n - 1 - best);
+                const unsigned long long old = atomicMin(&S.fail_key, key);
+                // several 64-word slices of the same row (n > 2048): keep the highest vertex = the smallest key (atomicMin does)
+                (void)old;
+              }
+              if (lane == 0) S.nfail = 1;
             }
           }
         }
-        __threadfence();
         __syncthreads();
         cyc[3] += clock64() - t0;
         t0 = clock64();
         // ---- decision
         uint32_t evM = 0xffffffffu;
         int evw = -1;
-        if (!dense) {
+        {
           const unsigned long long fk = S.fail_key;
           if (fk != ~0ull) { evM = (uint32_t)(fk / (unsigned long long)n); evw = n - 1 - (int)(fk % (unsigned long long)n); }
-        } else if (S.nfail) {
-          // the failing rows in ascending order, each re-checked with its exact lune, until one is a true failure
-          const uint32_t nf = S.nfail;
-          uint32_t last = 0;   // rows <= last have been examined (row ranks here are >= pos >= 1)
-          bool first = true;
-          for (;;) {
-            uint32_t cand;
-            if (nf <= (uint32_t)kS2FailCap) {
-              uint32_t mine = 0xffffffffu;
-              for (uint32_t i = tid; i < nf; i += kS2Threads) {
-                const uint32_t v = __ldcg(&fail_g[i]);
-                if ((first || v > last) && v < mine) mine = v;
-              }
-              mine = warp_min_u32(mine);
-              if (lane == 0 && mine != 0xffffffffu) atomicMin(&S.cand, mine);
-              __syncthreads();
-              cand = S.cand;
-            } else {
-              cand = first ? S.fail_row : 0xffffffffu;   // the list overflowed: only the minimum is known
-            }
-            if (cand == 0xffffffffu) break;
-            if (warp == 0) {
-              const uint32_t en = __ldg(&EA[cand]).x;
-              const uint32_t xm = xg(cand) ? 0xffffffffu : 0u;
-              const int w = exact_row(cand, en >> 16, en & 0xffffu, xm);
-              if (lane == 0) { S.ev_w = w; S.cand = 0xffffffffu; S.st[S2_EXACT] += 1; }
-            }
-            __syncthreads();
-            const int w = S.ev_w;
-            if (w >= 0) { evM = cand; evw = w; break; }
-            if (tid == 0) S.st[S2_SPURIOUS] += 1;
-            last = cand; first = false;
-            __syncthreads();
-          }
-          if (evM == 0xffffffffu) {
-            if (nf <= (uint32_t)kS2FailCap) { if (tid == 0) fail(TDA_ERR_INTERNAL_S2); __syncthreads(); break; }   // cannot happen (see the header)
-            // overflowed list, spurious minimum: rows <= last are settled; same window again from behind it (nothing to undo)
-            pos = last + 1; keep_hi = true;
-            cyc[4] += clock64() - t0;
-            continue;
-          }
+          if (tid == 0 && S.nfail && fk == ~0ull) S.st[S2_SPURIOUS] += 1;   // candidate bits, none of them true: a clean window
         }
         if (evM == 0xffffffffu) {   // clean window
           pos = hi;

@@ -734,239 +734,310 @@ __global__ void __launch_bounds__(kSgdWarps * 32) sgd_epoch_kernel_v4(float4* __
   }
 }
 
-// EXPERIMENT (off unless TDA_SGD_AGG=1; written after the round's GPU minutes were spent: compiled, never run): the per-epoch
-// kernel with the updates of the slot block's own vertex summed in the warp.  The slot table is row-major -- the 2k slots of
-// source vertex i are consecutive, k with head i and k with tail i (fuzzy_kernel) -- so every fired slot of a block moves
-// vertex i; a segmented shuffle reduction over the (queue-ordered, hence contiguous) lanes of the same block leaves one vector
-// RED per block for vertex i plus one per fired edge for the far endpoint: ~1.1 instead of 2 atomics per fired edge, on a
-// stage that is bound by the L2 atomic rate.  Same schedule, RNG keys and update rule; fit (move_other) only.
-__global__ void __launch_bounds__(kSgdWarps * 32) sgd_epoch_kernel_v4_agg(float4* __restrict__ Y, const int* __restrict__ head,
-                                                                          const int* __restrict__ tail, const float* __restrict__ eps_arr, int slots,
-                                                                          int n, int twok, int epoch, float a, float b, float gamma, float alpha,
-                                                                          float nsr, uint64_t seed) {
-  __shared__ int s_queue[kSgdWarps][kSgdSlotsPerLane * 32];
-  const int p = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int base = (blockIdx.x * kSgdWarps + warp) * (kSgdSlotsPerLane * 32);
-  if (base >= slots) return;
-  int* queue = s_queue[warp];
-  int count = 0;
+// ------------------------------------------------------------------------------------------------
+// Deterministic SGD for fit (the default for clouds that fit in shared memory): no atomics, all epochs in ONE launch.
+//
+// The fuzzy graph is symmetric with bit-identical weights in both directions (fuzzy_kernel: vij + vji - vij*vji), so the
+// directed entries i->j and j->i have the same period eps and fire in the same epochs.  With all gradients of an epoch
+// evaluated on the positions of the epoch's start (what a thread-per-slot kernel does up to scheduling order), vertex i gets
+// from an edge {i,j} that fires:   g (its own entry, as head)  +  the negative-sample steps of that entry  +  g again (the
+// twin entry j->i moves its tail by -g(j,i) = +g(i,j)).  Each vertex therefore needs only ITS OWN adjacency list (CSR by
+// head, sgd_adj_kernel), computes its whole displacement itself and writes its new position: nothing is shared, the sum over
+// a vertex's fired entries is taken in list order, the result is bit-reproducible for a given seed (the reference passes
+// random_state=42 for exactly that; debug_tda_pipeline.py:100).
+// A cloud is owned by a thread-block CLUSTER: every CTA keeps the whole embedding (double buffered, float4) and its slice of
+// the adjacency in shared memory, moves its own vertices and stores the new positions into every CTA's next buffer through
+// distributed shared memory; one cluster barrier per epoch.
+constexpr int kAdjThreads = 1024;
+__global__ void __launch_bounds__(kAdjThreads) sgd_adj_kernel(const int* __restrict__ head, const int* __restrict__ tail, const float* __restrict__ eps_arr,
+                                                              int slots, int n, int* __restrict__ adj_off, uint2* __restrict__ adj_ent,
+                                                              int* __restrict__ adj_maxdeg) {
+  extern __shared__ int s_adj[];   // cnt[n], off[n + 1]
+  int* cnt = s_adj;
+  int* off = s_adj + n;
+  __shared__ int s_part[kAdjThreads / 32];
+  __shared__ int s_maxdeg;
+  const int p = blockIdx.x, tid = threadIdx.x;
+  const int* H = head + (size_t)p * slots;
+  const int* Tl = tail + (size_t)p * slots;
+  const float* EP = eps_arr + (size_t)p * slots;
+  uint2* ent = adj_ent + (size_t)p * slots;
+  for (int i = tid; i < n; i += kAdjThreads) cnt[i] = 0;
+  if (tid == 0) s_maxdeg = 0;
+  __syncthreads();
+  for (int e = tid; e < slots; e += kAdjThreads)
+    if (EP[e] > 0.f) atomicAdd(&cnt[H[e]], 1);
+  __syncthreads();
+  // exclusive scan of cnt -> off (each thread a contiguous chunk)
+  const int per = (n + kAdjThreads - 1) / kAdjThreads;
+  const int lo = min(tid * per, n), hi = min(lo + per, n);
+  int sum = 0, mx = 0;
+  for (int i = lo; i < hi; ++i) { sum += cnt[i]; mx = max(mx, cnt[i]); }
+  int incl = sum;
 #pragma unroll
-  for (int i = 0; i < kSgdSlotsPerLane; ++i) {
-    const int e = base + i * 32 + lane;
-    bool fire = false;
-    if (e < slots) {
-      const float eps = eps_arr[(size_t)p * slots + e];
-      if (eps > 0.f) {
-        const int q = (int)floorf((float)epoch / eps);
-        fire = !(q < 1 || q <= (int)floorf((float)(epoch - 1) / eps));
-      }
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += t; }
+  if ((tid & 31) == 31) s_part[tid >> 5] = incl;
+  if (mx) atomicMax(&s_maxdeg, mx);
+  __syncthreads();
+  int base = incl - sum;
+  for (int w = 0; w < (tid >> 5); ++w) base += s_part[w];
+  for (int i = lo; i < hi; ++i) { off[i] = base; base += cnt[i]; }
+  if (hi == n && lo < n) off[n] = base;
+  if (n == 0 && tid == 0) off[0] = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += kAdjThreads) cnt[i] = off[i];   // fill cursors
+  __syncthreads();
+  for (int e = tid; e < slots; e += kAdjThreads) {
+    const float ep = EP[e];
+    if (ep > 0.f) {
+      const int pos = atomicAdd(&cnt[H[e]], 1);
+      ent[pos] = make_uint2(__float_as_uint(ep), (uint32_t)Tl[e] | ((uint32_t)H[e] << 16));   // n <= 8192: 16 bits each
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, fire);
-    if (fire) queue[count + __popc(bal & ((1u << lane) - 1))] = e;
-    count += __popc(bal);
   }
-  __syncwarp();
-  float4* Yp = Y + (size_t)p * n;
-  for (int q0 = 0; q0 < count; q0 += 32) {   // (warp uniform: every lane takes part in the shuffles)
-    const int qi = q0 + lane;
-    const bool act = qi < count;
-    int own = -1 - lane;                     // vertex of the slot block (distinct negative keys for idle lanes)
-    float own_upd[3] = {0.f, 0.f, 0.f};
-    if (act) {
-      const int e = queue[qi];
-      const float eps = eps_arr[(size_t)p * slots + e];
-      const int q = (int)floorf((float)epoch / eps);
-      const int j = head[(size_t)p * slots + e], kk = tail[(size_t)p * slots + e];
-      const float epsn = eps / nsr;
-      int tot = (int)floorf((float)epoch / epsn) - 1;
-      if (q > 1) {
-        const int prev = (int)ceilf((float)(q - 1) * eps);
-        tot -= (int)floorf((float)prev / epsn) - 1;
-      }
-      float4 n4[kSgdNegBatch];
+  __threadfence_block();
+  __syncthreads();
+  // the fill order depends on scheduling: sort every list by neighbour id (a vertex has each neighbour once)
+  for (int v = tid; v < n; v += kAdjThreads) {
+    const int a0 = off[v], a1 = off[v + 1];
+    for (int i = a0 + 1; i < a1; ++i) {
+      const uint2 x = ent[i];
+      int k = i - 1;
+      while (k >= a0 && (ent[k].y & 0xffffu) > (x.y & 0xffffu)) { ent[k + 1] = ent[k]; --k; }
+      ent[k + 1] = x;
+    }
+  }
+  for (int i = tid; i <= n; i += kAdjThreads) adj_off[(size_t)p * (n + 1) + i] = off[i];
+  if (tid == 0) adj_maxdeg[p] = s_maxdeg;
+}
+
+constexpr int kClThreads = 512;
+constexpr int kClWarps = kClThreads / 32;
+constexpr int kClQueue = 512;     // fired entries a warp queues before it works through them (a tile of 32 vertices usually fires ~150)
+constexpr int kClMaxCluster = 8;
+
+struct SgdForce {
+  float a, b, gamma, nsr;
+  // attractive step of entry (v -> t) on the epoch's positions; returns the step taken by v
+  __device__ __forceinline__ float3 attract(const float4& yv, const float4& yt, float alpha) const {
+    const float dx = yv.x - yt.x, dy = yv.y - yt.y, dz = yv.z - yt.z;
+    const float d2 = dx * dx + dy * dy + dz * dz;
+    float g = 0.f;
+    if (d2 > 0.f) {
+      const float pw = __powf(d2, b - 1.f);
+      g = (-2.f * a * b * pw) / (a * pw * d2 + 1.f);
+    }
+    return make_float3(clip4(g * dx) * alpha, clip4(g * dy) * alpha, clip4(g * dz) * alpha);
+  }
+  __device__ __forceinline__ void repel(float3& cur, const float4& yn, float alpha) const {
+    const float dx = cur.x - yn.x, dy = cur.y - yn.y, dz = cur.z - yn.z;
+    const float dn = dx * dx + dy * dy + dz * dz;
+    if (dn > 0.f) {   // (a negative at zero distance gives no update, whichever vertex it is)
+      const float gn = (2.f * gamma * b) / ((0.001f + dn) * (a * __powf(dn, b) + 1.f));
+      if (gn > 0.f) { cur.x += clip4(gn * dx) * alpha; cur.y += clip4(gn * dy) * alpha; cur.z += clip4(gn * dz) * alpha; }
+    }
+  }
+  // does an entry of period eps fire in `epoch` (it fires when floor(epoch / eps) steps up; approximate division: the schedule is
+  // this kernel's own definition, evaluated the same way everywhere) ...
+  __device__ __forceinline__ bool fires(float eps, int epoch, int& q) const {
+    q = (int)floorf(__fdividef((float)epoch, eps));
+    return q >= 1 && q > (int)floorf(__fdividef((float)(epoch - 1), eps));
+  }
+  // ... and how many negative samples it owes since its previous firing
+  __device__ __forceinline__ int negatives(float eps, int epoch, int q) const {
+    const float epsn = __fdividef(eps, nsr);
+    int tot = (int)floorf(__fdividef((float)epoch, epsn)) - 1;
+    if (q > 1) {
+      const int prev = (int)ceilf((float)(q - 1) * eps);
+      tot -= (int)floorf(__fdividef((float)prev, epsn)) - 1;
+    }
+    return tot;
+  }
+};
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t dsmem_addr(const void* smem_ptr, uint32_t rank) {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_ptr), r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void dsmem_store_f4(uint32_t addr, const float4& v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// grid = batch * C CTAs, cluster (C,1,1); dynamic shared memory: Yb[2][n] float4, soff[nown + 1], sent[own entries] (optional),
+// per warp: queue[kClQueue] + acc[32] float4
+__global__ void __launch_bounds__(kClThreads, 1) sgd_cluster_kernel(float* __restrict__ Y, const int* __restrict__ adj_off, const uint2* __restrict__ adj_ent,
+                                                                    int slots, int n, int n_epochs, SgdForce F, float alpha0, uint64_t seed,
+                                                                    int max_own_ent) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const uint32_t C = cluster_nctarank(), cr = cluster_ctarank();
+  const int p = blockIdx.x / (int)C;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int v0 = (int)(((long long)n * cr) / C), v1 = (int)(((long long)n * (cr + 1)) / C);
+  const int nown = v1 - v0;
+  const int nown_max = (n + (int)C - 1) / (int)C + 1;
+  float4* Yb = reinterpret_cast<float4*>(s_raw);
+  float4* acc_all = Yb + 2 * (size_t)n;
+  uint32_t* queue_all = reinterpret_cast<uint32_t*>(acc_all + kClWarps * 32);
+  int* soff = reinterpret_cast<int*>(queue_all + kClWarps * kClQueue);
+  uint2* sent = reinterpret_cast<uint2*>(soff + ((nown_max + 2) & ~1));
+  const int* goff = adj_off + (size_t)p * (n + 1);
+  const uint2* gent = adj_ent + (size_t)p * slots;
+  float* Yg = Y + (size_t)p * n * 3;
+  for (int i = tid; i < n; i += kClThreads) Yb[i] = make_float4(Yg[3 * i], Yg[3 * i + 1], Yg[3 * i + 2], 0.f);
+  for (int i = tid; i <= nown; i += kClThreads) soff[i] = goff[v0 + i];
+  __syncthreads();
+  const int e0 = soff[0], ne = soff[nown] - e0;
+  const bool ent_in_smem = ne <= max_own_ent;
+  if (ent_in_smem)
+    for (int i = tid; i < ne; i += kClThreads) sent[i] = gent[e0 + i];
+  const uint2* ent = ent_in_smem ? sent : gent + e0;   // entry i of this CTA's slice
+  float4* acc = acc_all + warp * 32;
+  uint32_t* queue = queue_all + warp * kClQueue;
+  uint32_t remote[kClMaxCluster];
 #pragma unroll
-      for (int u = 0; u < kSgdNegBatch; ++u) {
-        if (u < tot) {
-          const uint32_t r = mix32(seed ^ ((uint64_t)p << 52) ^ ((uint64_t)e << 20) ^ ((uint64_t)epoch << 4) ^ (uint64_t)u ^ ((uint64_t)u << 40));
-          n4[u] = __ldcg(Yp + (int)(r % (uint32_t)n));
-        }
-      }
-      const float4 c4 = __ldcg(Yp + j), o4 = __ldcg(Yp + kk);
-      float cur[3] = {c4.x, c4.y, c4.z};
-      const float oth[3] = {o4.x, o4.y, o4.z};
-      float delta[3] = {0.f, 0.f, 0.f}, dt[3];
-      float d2 = 0.f;
-#pragma unroll
-      for (int d = 0; d < 3; ++d) { const float t = cur[d] - oth[d]; d2 += t * t; }
-      float g = 0.f;
-      if (d2 > 0.f) {
-        const float pw = __powf(d2, b - 1.f);
-        g = (-2.f * a * b * pw) / (a * pw * d2 + 1.f);
-      }
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const float gd = clip4(g * (cur[d] - oth[d])) * alpha;
-        cur[d] += gd; delta[d] += gd; dt[d] = -gd;
-      }
-      auto repel = [&](const float4& nn) {
-        const float on[3] = {nn.x, nn.y, nn.z};
-        float dn = 0.f;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) { const float t = cur[d] - on[d]; dn += t * t; }
-        if (dn > 0.f) {
-          const float gn = (2.f * gamma * b) / ((0.001f + dn) * (a * __powf(dn, b) + 1.f));
-          if (gn > 0.f) {
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-              const float gd = clip4(gn * (cur[d] - on[d])) * alpha;
-              cur[d] += gd; delta[d] += gd;
+  for (int r = 0; r < kClMaxCluster; ++r) remote[r] = r < (int)C ? dsmem_addr(Yb, (uint32_t)r) : 0u;
+  cluster_sync_all();   // every CTA of the cluster has its buffers up before anybody stores into them
+
+  for (int ep = 0; ep < n_epochs; ++ep) {
+    const float alpha = ep == 0 ? alpha0 : alpha0 * (1.f - (float)(ep - 1) / (float)n_epochs);
+    const float4* src = Yb + (size_t)(ep & 1) * n;
+    const uint32_t dst_off = (uint32_t)(((ep + 1) & 1) * n) * 16u;
+    const uint32_t key_ep = hash32((uint32_t)seed ^ (uint32_t)(seed >> 32) ^ hash32((uint32_t)p * 0x27d4eb2fu + (uint32_t)ep));
+    // tiles of 32 consecutive owned vertices, dealt round robin to the warps
+    for (int tv = warp * 32; tv < nown; tv += kClWarps * 32) {
+      const int cnt = min(32, nown - tv);
+      const int ebase = soff[tv] - e0;
+      acc[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncwarp();
+      int qn = 0;
+      // phase 2 (called whenever the queue may overflow, and at the end): full warps over the queued (= fired) entries; the
+      // displacement of each, summed per vertex in queue (= list) order
+      auto drain = [&]() {
+        __syncwarp();
+        for (int q0 = 0; q0 < qn; q0 += 32) {
+          const int qi = q0 + lane;
+          float3 dl = make_float3(0.f, 0.f, 0.f);
+          int vi = -1 - lane;   // distinct dummy keys for idle lanes
+          if (qi < qn) {
+            const int i = ebase + (int)queue[qi];
+            const uint2 en = ent[i];
+            const float eps = __uint_as_float(en.x);
+            const int v = (int)(en.y >> 16);
+            vi = v - (v0 + tv);
+            int q;
+            F.fires(eps, ep, q);
+            const int tot = F.negatives(eps, ep, q);
+            const float4 yv = src[v], yt = src[en.y & 0xffffu];
+            const float3 g1 = F.attract(yv, yt, alpha);
+            float3 cur = make_float3(yv.x + g1.x, yv.y + g1.y, yv.z + g1.z);
+            const uint32_t key = hash32(key_ep + (uint32_t)(e0 + i) * 0x9E3779B1u);
+            for (int sidx = 0; sidx < tot; ++sidx) {
+              const uint32_t r = hash32(key + (uint32_t)sidx * 0x85ebca6bu);
+              F.repel(cur, src[__umulhi(r, (uint32_t)n)], alpha);
             }
+            dl = make_float3((cur.x - yv.x) + g1.x, (cur.y - yv.y) + g1.y, (cur.z - yv.z) + g1.z);
           }
+          // segmented inclusive scan over the lanes (segments = runs of equal vi), the last lane of a run owns its sum
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const float tx = __shfl_up_sync(0xffffffffu, dl.x, o), ty = __shfl_up_sync(0xffffffffu, dl.y, o), tz = __shfl_up_sync(0xffffffffu, dl.z, o);
+            const int tvi = __shfl_up_sync(0xffffffffu, vi, o);
+            if (lane >= o && tvi == vi) { dl.x += tx; dl.y += ty; dl.z += tz; }
+          }
+          const int nvi = __shfl_down_sync(0xffffffffu, vi, 1);
+          if (qi < qn && (lane == 31 || nvi != vi)) {
+            float4 t = acc[vi];
+            t.x += dl.x; t.y += dl.y; t.z += dl.z;
+            acc[vi] = t;
+          }
+          __syncwarp();
         }
+        qn = 0;
       };
-#pragma unroll
-      for (int u = 0; u < kSgdNegBatch; ++u)
-        if (u < tot) repel(n4[u]);
-      for (int sidx = kSgdNegBatch; sidx < tot; ++sidx) {
-        const uint32_t r = mix32(seed ^ ((uint64_t)p << 52) ^ ((uint64_t)e << 20) ^ ((uint64_t)epoch << 4) ^ (uint64_t)sidx ^ ((uint64_t)sidx << 40));
-        repel(__ldcg(Yp + (int)(r % (uint32_t)n)));
+      // phase 1: which entries of the tile fire (lanes over the tile's contiguous entry range: the queue stays in list order)
+      const int eend = soff[tv + cnt] - e0;
+      for (int i0 = ebase; i0 < eend; i0 += 32) {
+        if (qn + 32 > kClQueue) drain();
+        const int i = i0 + lane;
+        bool fire = false;
+        int q;
+        if (i < eend) fire = F.fires(__uint_as_float(ent[i].x), ep, q);
+        const unsigned bal = __ballot_sync(0xffffffffu, fire);
+        if (fire) queue[qn + __popc(bal & ((1u << lane) - 1))] = (uint32_t)(i - ebase);
+        qn += __popc(bal);
       }
-      // the block's own vertex collects in the warp, the far endpoint is updated directly
-      const int blk = e / twok;
-      if (j == blk) {
-        own = blk;
+      drain();
+      // phase 3: new positions of the tile's vertices into the next buffer of every CTA of the cluster
+      if (lane < cnt) {
+        const int v = v0 + tv + lane;
+        const float4 y = src[v], d = acc[lane];
+        const float4 yn = make_float4(y.x + d.x, y.y + d.y, y.z + d.z, 0.f);
 #pragma unroll
-        for (int d = 0; d < 3; ++d) own_upd[d] = delta[d];
-        atomicAdd(Yp + kk, make_float4(dt[0], dt[1], dt[2], 0.f));
-      } else if (kk == blk) {
-        own = blk;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) own_upd[d] = dt[d];
-        atomicAdd(Yp + j, make_float4(delta[0], delta[1], delta[2], 0.f));
-      } else {   // (not produced by fuzzy_kernel; handled like the plain kernel)
-        atomicAdd(Yp + kk, make_float4(dt[0], dt[1], dt[2], 0.f));
-        atomicAdd(Yp + j, make_float4(delta[0], delta[1], delta[2], 0.f));
+        for (int r = 0; r < kClMaxCluster; ++r)
+          if (r < (int)C) dsmem_store_f4(remote[r] + dst_off + (uint32_t)v * 16u, yn);
       }
+      __syncwarp();
     }
-    // segmented inclusive sum over equal keys (contiguous lanes), last lane of a segment writes
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const int ko = __shfl_up_sync(0xffffffffu, own, off);
-      const float v0 = __shfl_up_sync(0xffffffffu, own_upd[0], off);
-      const float v1 = __shfl_up_sync(0xffffffffu, own_upd[1], off);
-      const float v2 = __shfl_up_sync(0xffffffffu, own_upd[2], off);
-      if (lane >= off && ko == own) { own_upd[0] += v0; own_upd[1] += v1; own_upd[2] += v2; }
-    }
-    const int knext = __shfl_down_sync(0xffffffffu, own, 1);
-    if (own >= 0 && (lane == 31 || knext != own)) atomicAdd(Yp + own, make_float4(own_upd[0], own_upd[1], own_upd[2], 0.f));
+    cluster_sync_all();
+  }
+  const float4* fin = Yb + (size_t)(n_epochs & 1) * n;
+  for (int i = tid; i < nown; i += kClThreads) {
+    const float4 y = fin[v0 + i];
+    Yg[3 * (v0 + i)] = y.x; Yg[3 * (v0 + i) + 1] = y.y; Yg[3 * (v0 + i) + 2] = y.z;
   }
 }
 
-// EXPERIMENT (off unless TDA_SGD_CLOUD=1): one CTA per cloud, the whole optimisation in ONE launch -- the embedding (16 B
-// per point) lives in shared memory, updates are shared-memory float atomics, epochs are separated by __syncthreads(), and
-// nothing but the read-only slot table (eps, head, tail) leaves the SM.  Same schedule, RNG keys and update rule as the
-// per-epoch kernel (tests/test_umap_gpu.py: trustworthiness 0.99315 vs 0.99313 on 8 clouds).  Measured on the C3 sweep: 64 ms
-// per 16 clouds x 500 epochs against 15.5 ms for the per-epoch kernel -- a cloud fires ~21 k edges per epoch at ~300
-// instructions each (six __powf), which is ~50 us of issue time on ONE SM, while the per-epoch kernel spreads the same work
-// over all 148 SMs and pays L2 atomics instead (shared-memory float add is a CAS loop, ATOMS.CAST.SPIN, on sm_100a).
-// The design that would win is a cluster of 8 CTAs per cloud with the embedding in distributed shared memory.
-constexpr int kSgdCloudThreads = 1024;
-constexpr int kSgdCloudWarps = kSgdCloudThreads / 32;
-constexpr int kSgdCloudMinBatch = 8;
-constexpr size_t kSgdCloudMaxBytes = 160 * 1024;
-__global__ void __launch_bounds__(kSgdCloudThreads, 1) sgd_cloud_kernel(float4* __restrict__ Y4, const int* __restrict__ head, const int* __restrict__ tail,
-                                                                        const float* __restrict__ eps_arr, int slots, int n, int n_epochs, float a,
-                                                                        float b, float gamma, float alpha0, float nsr, uint64_t seed) {
-  extern __shared__ float4 s_y[];                       // [n] the cloud's embedding
-  __shared__ int s_queue[kSgdCloudWarps][kSgdSlotsPerLane * 32];
-  const int p = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4* Yg = Y4 + (size_t)p * n;
-  for (int i = threadIdx.x; i < n; i += kSgdCloudThreads) s_y[i] = Yg[i];
-  __syncthreads();
-  const float* ep_p = eps_arr + (size_t)p * slots;
-  const int* hd_p = head + (size_t)p * slots;
-  const int* tl_p = tail + (size_t)p * slots;
-  int* queue = s_queue[warp];
-  constexpr int kChunk = kSgdSlotsPerLane * 32;
-  for (int epoch = 0; epoch < n_epochs; ++epoch) {
-    const float alpha = epoch == 0 ? alpha0 : alpha0 * (1.f - (float)(epoch - 1) / (float)n_epochs);
-    for (int base = warp * kChunk; base < slots; base += kSgdCloudWarps * kChunk) {
-      int count = 0;
-#pragma unroll
-      for (int i = 0; i < kSgdSlotsPerLane; ++i) {
-        const int e = base + i * 32 + lane;
-        bool fire = false;
-        if (e < slots) {
-          const float eps = __ldg(&ep_p[e]);
-          if (eps > 0.f) {
-            const int q = (int)floorf((float)epoch / eps);
-            fire = !(q < 1 || q <= (int)floorf((float)(epoch - 1) / eps));
-          }
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, fire);
-        if (fire) queue[count + __popc(bal & ((1u << lane) - 1))] = e;
-        count += __popc(bal);
-      }
-      __syncwarp();
-      for (int qi = lane; qi < count; qi += 32) {
-        const int e = queue[qi];
-        const float eps = __ldg(&ep_p[e]);
-        const int q = (int)floorf((float)epoch / eps);
-        const int j = __ldg(&hd_p[e]), kk = __ldg(&tl_p[e]);
-        const float epsn = eps / nsr;
-        int tot = (int)floorf((float)epoch / epsn) - 1;
-        if (q > 1) {
-          const int prev = (int)ceilf((float)(q - 1) * eps);
-          tot -= (int)floorf((float)prev / epsn) - 1;
-        }
-        const float4 c4 = s_y[j], o4 = s_y[kk];
-        float cur[3] = {c4.x, c4.y, c4.z};
-        const float oth[3] = {o4.x, o4.y, o4.z};
-        float delta[3] = {0.f, 0.f, 0.f};
-        float d2 = 0.f;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) { const float t = cur[d] - oth[d]; d2 += t * t; }
-        float g = 0.f;
-        if (d2 > 0.f) {
-          const float pw = __powf(d2, b - 1.f);
-          g = (-2.f * a * b * pw) / (a * pw * d2 + 1.f);
-        }
-        float* yt = reinterpret_cast<float*>(&s_y[kk]);
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          const float gd = clip4(g * (cur[d] - oth[d])) * alpha;
-          cur[d] += gd; delta[d] += gd;
-          atomicAdd(&yt[d], -gd);
-        }
+// transform (move_other = 0): a query point only ever reads the fixed training embedding, so it is optimised on its own -- one
+// warp per query point, lanes over its k entries, all epochs in registers; no atomics, deterministic.
+__global__ void __launch_bounds__(256) sgd_transform_kernel(float* __restrict__ Y, const float* __restrict__ Yt, const int* __restrict__ tail,
+                                                            const float* __restrict__ eps_arr, int k, int n_query, int n_train, int n_epochs,
+                                                            SgdForce F, float alpha0, uint64_t seed) {
+  const int p = blockIdx.y;
+  const int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (v >= n_query) return;
+  const float* T3 = Yt + (size_t)p * n_train * 3;
+  float* yq = Y + ((size_t)p * n_query + v) * 3;
+  float4 cur = make_float4(yq[0], yq[1], yq[2], 0.f);
+  const size_t sbase = (size_t)p * n_query * k + (size_t)v * k;
+  for (int ep = 0; ep < n_epochs; ++ep) {
+    const float alpha = ep == 0 ? alpha0 : alpha0 * (1.f - (float)(ep - 1) / (float)n_epochs);
+    float3 dl = make_float3(0.f, 0.f, 0.f);
+    const uint32_t key_ep = hash32((uint32_t)seed ^ (uint32_t)(seed >> 32) ^ hash32((uint32_t)p * 0x27d4eb2fu + (uint32_t)ep));
+    for (int t = lane; t < k; t += 32) {
+      const float eps = eps_arr[sbase + t];
+      int q;
+      if (eps > 0.f && F.fires(eps, ep, q)) {
+        const int tot = F.negatives(eps, ep, q);
+        const int j = tail[sbase + t];
+        const float4 yt = make_float4(__ldg(&T3[3 * j]), __ldg(&T3[3 * j + 1]), __ldg(&T3[3 * j + 2]), 0.f);
+        const float3 g1 = F.attract(cur, yt, alpha);
+        float3 c = make_float3(cur.x + g1.x, cur.y + g1.y, cur.z + g1.z);
+        const uint32_t key = hash32(key_ep + (uint32_t)(sbase + t) * 0x9E3779B1u);
         for (int sidx = 0; sidx < tot; ++sidx) {
-          const uint32_t r = mix32(seed ^ ((uint64_t)p << 52) ^ ((uint64_t)e << 20) ^ ((uint64_t)epoch << 4) ^ (uint64_t)sidx ^ ((uint64_t)sidx << 40));
-          const float4 nn = s_y[(int)(r % (uint32_t)n)];
-          const float on[3] = {nn.x, nn.y, nn.z};
-          float dn = 0.f;
-#pragma unroll
-          for (int d = 0; d < 3; ++d) { const float t = cur[d] - on[d]; dn += t * t; }
-          if (dn > 0.f) {
-            const float gn = (2.f * gamma * b) / ((0.001f + dn) * (a * __powf(dn, b) + 1.f));
-            if (gn > 0.f) {
-#pragma unroll
-              for (int d = 0; d < 3; ++d) {
-                const float gd = clip4(gn * (cur[d] - on[d])) * alpha;
-                cur[d] += gd; delta[d] += gd;
-              }
-            }
-          }
+          const uint32_t r = hash32(key + (uint32_t)sidx * 0x85ebca6bu);
+          const int kn = (int)__umulhi(r, (uint32_t)n_train);
+          F.repel(c, make_float4(__ldg(&T3[3 * kn]), __ldg(&T3[3 * kn + 1]), __ldg(&T3[3 * kn + 2]), 0.f), alpha);
         }
-        float* yh = reinterpret_cast<float*>(&s_y[j]);
-#pragma unroll
-        for (int d = 0; d < 3; ++d) atomicAdd(&yh[d], delta[d]);
+        dl.x += c.x - cur.x; dl.y += c.y - cur.y; dl.z += c.z - cur.z;
       }
-      __syncwarp();   // the queue is reused by the next chunk
     }
-    __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      dl.x += __shfl_xor_sync(0xffffffffu, dl.x, o); dl.y += __shfl_xor_sync(0xffffffffu, dl.y, o); dl.z += __shfl_xor_sync(0xffffffffu, dl.z, o);
+    }
+    cur.x += dl.x; cur.y += dl.y; cur.z += dl.z;
   }
-  for (int i = threadIdx.x; i < n; i += kSgdCloudThreads) Yg[i] = s_y[i];
+  if (lane == 0) { yq[0] = cur.x; yq[1] = cur.y; yq[2] = cur.z; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1098,6 +1169,19 @@ extern "C" int tda_fuzzy_graph(const int32_t* knn_idx, const float* knn_dist, co
   return TDA_OK;
 }
 
+// workspace of tda_umap_sgd: the float4-padded embeddings of the per-epoch kernels, or the per-vertex adjacency (CSR by head:
+// offsets, (eps, neighbour) entries, largest degree) of the deterministic cluster kernel -- whichever is larger
+static size_t sgd_adj_bytes(int slots, int n, int batch) {
+  return (((size_t)batch * (n + 1) * sizeof(int) + 255) & ~(size_t)255) + (((size_t)batch * slots * sizeof(uint2) + 255) & ~(size_t)255) +
+         (((size_t)batch * sizeof(int) + 255) & ~(size_t)255);
+}
+extern "C" size_t tda_umap_sgd_workspace_bytes(int slots, int n_head, int n_tail, int dim, int batch, int move_other) {
+  if (slots <= 0 || n_head <= 0 || batch <= 0) return 0;
+  size_t b = sizeof(float4) * (size_t)batch * ((size_t)n_head + (move_other ? 0 : (size_t)n_tail));
+  if (dim == 3 && move_other) b = b > sgd_adj_bytes(slots, n_head, batch) ? b : sgd_adj_bytes(slots, n_head, batch);
+  return b + 256;
+}
+
 extern "C" int tda_umap_sgd(float* Y, const float* Y_other, const int32_t* head, const int32_t* tail, const float* eps, int slots, int n_head,
                             int n_tail, int dim, int batch, int n_epochs, float a, float b, float gamma, float alpha0,
                             float negative_sample_rate, int move_other, uint64_t seed, void* ws, size_t ws_bytes, void* stream_) {
@@ -1108,35 +1192,70 @@ extern "C" int tda_umap_sgd(float* Y, const float* Y_other, const int32_t* head,
   if (dim < 1 || dim > 4) return set_error(TDA_ERR_UNSUPPORTED, "tda_umap_sgd: n_components=%d (supported: 1..4)", dim);
   dim3 g((slots + 255) / 256, batch);
   StageScope st(STAGE_SGD, stream);
-  const size_t np_h = (size_t)batch * n_head, np_t = move_other ? 0 : (size_t)batch * n_tail;
-  if (dim == 3 && ws && ws_bytes >= sizeof(float4) * (np_h + np_t) && (((uintptr_t)ws) & 15) == 0 && n_epochs > 0) {
-    float4* Yh4 = (float4*)ws;
-    float4* Yt4 = move_other ? Yh4 : Yh4 + np_h;
-    pack4_kernel<<<(unsigned)((np_h + 255) / 256), 256, 0, stream>>>(Y, Yh4, np_h);
-    // TDA_SGD_CLOUD=1: one CTA per cloud with the embedding in shared memory, all epochs in one launch (see sgd_cloud_kernel)
-    const int sgd_mode = (int)option("sgd_mode");
-    const bool cloud_mode = sgd_mode == 1;
-    const size_t cloud_bytes = sizeof(float4) * (size_t)n_head;
-    if (cloud_mode && move_other && n_head == n_tail && batch >= kSgdCloudMinBatch && cloud_bytes <= kSgdCloudMaxBytes) {
-      TDA_CUDA_CHECK(cudaFuncSetAttribute(sgd_cloud_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cloud_bytes));
-      sgd_cloud_kernel<<<batch, kSgdCloudThreads, cloud_bytes, stream>>>(Yh4, head, tail, eps, slots, n_head, n_epochs, a, b, gamma, alpha0,
-                                                                         negative_sample_rate, seed);
-      unpack4_kernel<<<(unsigned)((np_h + 255) / 256), 256, 0, stream>>>(Yh4, Y, np_h);
-      count_launch(3);
+  const int sgd_mode = (int)option("sgd_mode");
+  SgdForce F;
+  F.a = a; F.b = b; F.gamma = gamma; F.nsr = negative_sample_rate;
+  if (n_epochs == 0) return TDA_OK;
+  // ---- deterministic paths (sgd_mode 0): cluster kernel for fit, warp-per-point kernel for transform
+  if (sgd_mode == 0 && dim == 3 && !move_other && slots % n_head == 0 && batch <= 65535) {
+    dim3 gt((n_head + 7) / 8, batch);
+    sgd_transform_kernel<<<gt, 256, 0, stream>>>(Y, Y_other, tail, eps, slots / n_head, n_head, n_tail, n_epochs, F, alpha0, seed);
+    count_launch();
+    TDA_LAUNCH_CHECK();
+    return TDA_OK;
+  }
+  if (sgd_mode == 0 && dim == 3 && move_other && n_head == n_tail && n_head <= 8192 && ws && ws_bytes >= sgd_adj_bytes(slots, n_head, batch) &&
+      (((uintptr_t)ws) & 255) == 0) {
+    const int n = n_head;
+    int C = (int)option("sgd_cluster");
+    if (C != 1 && C != 2 && C != 4 && C != 8) C = 4;
+    const int nown_max = (n + C - 1) / C + 1;
+    const size_t base = sizeof(float4) * 2 * (size_t)n + sizeof(float4) * kClWarps * 32 + sizeof(uint32_t) * kClWarps * kClQueue +
+                        sizeof(int) * (size_t)((nown_max + 2) & ~1);
+    const size_t smem_max = (size_t)224 * 1024;
+    if (base + 1024 <= smem_max) {
+      Carver c(ws, ws_bytes);
+      int* adj_off = c.take<int>((size_t)batch * (n + 1));
+      uint2* adj_ent = c.take<uint2>((size_t)batch * slots);
+      int* adj_maxdeg = c.take<int>(batch);
+      const size_t adj_smem = sizeof(int) * (size_t)(2 * n + 1);
+      TDA_CUDA_CHECK(cudaFuncSetAttribute(sgd_adj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adj_smem));
+      sgd_adj_kernel<<<batch, kAdjThreads, adj_smem, stream>>>(head, tail, eps, slots, n, adj_off, adj_ent, adj_maxdeg);
+      // the CTA's slice of the adjacency goes to shared memory when it fits into what the embedding buffers leave
+      size_t cap_ent = (smem_max - base) / sizeof(uint2);
+      const size_t want_ent = (size_t)slots / C + (size_t)slots / (2 * C) + 64;   // 1.5x the mean slice (the kernel checks its actual size)
+      if (cap_ent > want_ent) cap_ent = want_ent;
+      const size_t dyn = base + cap_ent * sizeof(uint2);
+      TDA_CUDA_CHECK(cudaFuncSetAttribute(sgd_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3((unsigned)(batch * C), 1, 1);
+      cfg.blockDim = dim3(kClThreads, 1, 1);
+      cfg.dynamicSmemBytes = dyn;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      TDA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sgd_cluster_kernel, Y, (const int*)adj_off, (const uint2*)adj_ent, slots, n, n_epochs, F, alpha0, seed,
+                                        (int)cap_ent));
+      count_launch(2);
       TDA_LAUNCH_CHECK();
       return TDA_OK;
     }
+  }
+  // ---- per-epoch kernels with float atomics (large clouds, other dimensions, sgd_mode 3): not reproducible run to run
+  const size_t np_h = (size_t)batch * n_head, np_t = move_other ? 0 : (size_t)batch * n_tail;
+  if (dim == 3 && ws && ws_bytes >= sizeof(float4) * (np_h + np_t) && (((uintptr_t)ws) & 15) == 0) {
+    float4* Yh4 = (float4*)ws;
+    float4* Yt4 = move_other ? Yh4 : Yh4 + np_h;
+    pack4_kernel<<<(unsigned)((np_h + 255) / 256), 256, 0, stream>>>(Y, Yh4, np_h);
     if (!move_other) pack4_kernel<<<(unsigned)((np_t + 255) / 256), 256, 0, stream>>>(Y_other, Yt4, np_t);
-    const bool agg_mode = sgd_mode == 2 && move_other && n_head == n_tail && slots % n_head == 0 && (slots / n_head) % 2 == 0;
     for (int ep = 0; ep < n_epochs; ++ep) {
       const float alpha = ep == 0 ? alpha0 : alpha0 * (1.f - (float)(ep - 1) / (float)n_epochs);
       const int per_block = kSgdWarps * kSgdSlotsPerLane * 32;
       dim3 g4((slots + per_block - 1) / per_block, batch);
-      if (agg_mode) {
-        sgd_epoch_kernel_v4_agg<<<g4, kSgdWarps * 32, 0, stream>>>(Yh4, head, tail, eps, slots, n_head, slots / n_head, ep, a, b, gamma, alpha,
-                                                                   negative_sample_rate, seed);
-        continue;
-      }
       sgd_epoch_kernel_v4<<<g4, kSgdWarps * 32, 0, stream>>>(Yh4, Yt4, head, tail, eps, slots, n_head, n_tail, ep, a, b, gamma, alpha,
                                                              negative_sample_rate, move_other, seed);
     }

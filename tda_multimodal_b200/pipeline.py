@@ -105,8 +105,10 @@ def silhouette_score(Y, labels, dm=None):
     if lab.ndim == 1:
         lab = np.broadcast_to(lab, (B, n))
     uniq, inv = np.unique(lab.reshape(-1), return_inverse=True)
-    if not (2 <= len(uniq) <= n - 1):
-        raise ValueError("Number of labels is %d. Valid values are 2 to n_samples - 1 (inclusive)" % len(uniq))
+    for b in range(B):   # scikit-learn's check_number_of_labels, per cloud
+        nl = len(np.unique(lab[b]))
+        if not (2 <= nl <= n - 1):
+            raise ValueError("Number of labels is %d. Valid values are 2 to n_samples - 1 (inclusive)" % nl)
     lab_d = torch.from_numpy(inv.reshape(B, n).astype(np.int32)).to(Yt.device)
     if dm is None:
         dm = pdist_lowdim(Yt.contiguous())
@@ -295,9 +297,9 @@ def pack_fitted_state(raw_data, embedding, a, b, n_neighbors):
 
 
 def broadcast_fitted_state(state, src=0, group=None, device=None):
-    """`state` = pack_fitted_state(...) on rank `src`, None elsewhere.  Every rank returns the same dict (tensors on `device`:
-    the current CUDA device under NCCL, the CPU under gloo).  Two broadcasts: the shape/scalar vector, then data + embedding
-    as one flat float32 buffer."""
+    """`state` = pack_fitted_state(...) on rank `src` OF THE GROUP, None elsewhere.  Every rank returns the same dict (tensors on
+    `device`: the current CUDA device under NCCL, the CPU under gloo).  Two broadcasts: the shape/scalar vector, then data +
+    embedding as one flat float32 buffer."""
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
@@ -305,20 +307,22 @@ def broadcast_fitted_state(state, src=0, group=None, device=None):
     rank = dist.get_rank(group)
     backend = dist.get_backend(group)
     dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu"))
+    gsrc = dist.get_global_rank(group, src) if group is not None else src   # dist.broadcast takes the GLOBAL rank of the source
     sc = state["scalars"].to(dev) if rank == src else torch.zeros(6, dtype=torch.float64, device=dev)
-    dist.broadcast(sc, src=src, group=group)
+    dist.broadcast(sc, src=gsrc, group=group)
     n, d, dim = int(sc[3].item()), int(sc[4].item()), int(sc[5].item())
     flat = torch.empty(n * d + n * dim, dtype=torch.float32, device=dev)
     if rank == src:
         flat[:n * d] = state["raw_data"].to(dev).reshape(-1)
         flat[n * d:] = state["embedding"].to(dev).reshape(-1)
-    dist.broadcast(flat, src=src, group=group)
+    dist.broadcast(flat, src=gsrc, group=group)
     return {"raw_data": flat[:n * d].reshape(n, d), "embedding": flat[n * d:].reshape(n, dim), "scalars": sc.cpu()}
 
 
-def fit_once_transform_many(X_layers, fit_layer=0, n_neighbors=15, n_components=3, min_dist=0.1, metric="cosine", random_state=42,
+def fit_once_transform_many(X_layers, fit_layer=-1, n_neighbors=15, n_components=3, min_dist=0.1, metric="cosine", random_state=42,
                             maxdim=1, group=None):
-    """analyze_tda_over_layers.py:56-77 over the ranks: UMAP is fitted on layer `fit_layer` by rank 0, its state is broadcast,
+    """analyze_tda_over_layers.py:56-77 over the ranks: UMAP is fitted on layer `fit_layer` (default: the last one, as
+    analyze_tda_over_layers.py:68 does) by rank 0, its state is broadcast,
     rank r transforms layers r, r+G, ... (the fit layer returns the stored embedding, as umap-learn does for its own training
     data) and runs Rips on each; the diagrams are gathered.  X_layers [L,n,d] float32 CUDA tensor (replicated, or only this
     rank's layers filled in).  Returns (embeddings of this rank's layers {layer: [n,dim] CUDA tensor}, diagrams of ALL layers)."""
@@ -329,6 +333,7 @@ def fit_once_transform_many(X_layers, fit_layer=0, n_neighbors=15, n_components=
     rank = dist.get_rank(group) if multi else 0
     world = dist.get_world_size(group) if multi else 1
     L = X_layers.shape[0]
+    fit_layer = fit_layer % L
     state = None
     if rank == 0:
         um = UMAP(n_neighbors=n_neighbors, n_components=n_components, min_dist=min_dist, metric=metric, random_state=random_state)

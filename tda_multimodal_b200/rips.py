@@ -25,7 +25,8 @@ def pdist_lowdim(pts):
     L = _lib.lib()
     B, n, d = pts.shape
     dm = torch.empty((B, n, n), dtype=torch.float32, device=pts.device)
-    _lib.check(L.tda_pdist_lowdim(_lib.ptr(pts), n, d, B, _lib.ptr(dm), _lib.stream_ptr()))
+    with torch.cuda.device(pts.device):
+        _lib.check(L.tda_pdist_lowdim(_lib.ptr(pts), n, d, B, _lib.ptr(dm), _lib.stream_ptr()))
     return dm
 
 
@@ -227,7 +228,7 @@ def rips_batch(dm, maxdim=1, thresh=float("inf"), cap1=None, pool_bytes=None, wa
         if want_simplices:
             r["simplices"] = [h0s_h[p, :c0]] + ([h1s_h[p, :c1]] if maxdim >= 1 else [])
         if stats is not None:
-            r["stats"] = dict(zip(_STAT_NAMES, stats[p].tolist()))
+            r["stats"] = dict(zip(_STAT_NAMES[_lib.rips_reducer()], stats[p].tolist()))
         out.append(r)
     return out
 

@@ -218,10 +218,10 @@ def umap_fit_batch(X, n_neighbors=15, n_components=2, metric="euclidean", n_epoc
             Y = Y0.to(torch.float32).reshape(B, n, n_components).contiguous().clone()
             _lib.check(L.tda_umap_rescale(_lib.ptr(Y), n, n_components, B, 0.0, seed + 1, _lib.stream_ptr()))
         init_embedding = Y.clone() if return_state else None
-        ws4 = torch.empty((B * n, 4), dtype=torch.float32, device=dev)   # float4-padded embedding for the vector-atomic SGD
+        ws_sgd = torch.empty(int(L.tda_umap_sgd_workspace_bytes(head.shape[1], n, n, n_components, B, 1)), dtype=torch.uint8, device=dev)
         _lib.check(L.tda_umap_sgd(_lib.ptr(Y), None, _lib.ptr(head), _lib.ptr(tail), _lib.ptr(eps), head.shape[1], n, n, n_components, B,
                                   n_ep, float(a), float(b), float(repulsion_strength), float(learning_rate), float(negative_sample_rate), 1,
-                                  seed + 2, _lib.ptr(ws4), ws4.numel() * 4, _lib.stream_ptr()))
+                                  seed + 2, _lib.ptr(ws_sgd), ws_sgd.numel(), _lib.stream_ptr()))
     if return_state:
         return Y, {"knn_indices": idx, "knn_dists": dist, "sigmas": sigma, "rhos": rho, "head": head, "tail": tail, "weight": weight,
                    "eps": eps, "a": a, "b": b, "n_neighbors": k, "n_epochs": n_ep, "init": init_embedding, "seed": seed}
@@ -257,10 +257,10 @@ def umap_transform_batch(Xq, Xtrain, train_embedding, n_neighbors, metric="eucli
         _lib.check(L.tda_umap_transform_init(_lib.ptr(idx), _lib.ptr(dist), _lib.ptr(sigma), _lib.ptr(rho), _lib.ptr(te), m, n, k, dim, B,
                                              n_ep, _lib.ptr(Y), _lib.ptr(head), _lib.ptr(tail), _lib.ptr(weight), _lib.ptr(eps),
                                              _lib.ptr(maxw), _lib.stream_ptr()))
-        ws4 = torch.empty((B * (m + n), 4), dtype=torch.float32, device=dev)
+        ws_sgd = torch.empty(int(L.tda_umap_sgd_workspace_bytes(slots, m, n, dim, B, 0)), dtype=torch.uint8, device=dev)
         _lib.check(L.tda_umap_sgd(_lib.ptr(Y), _lib.ptr(te), _lib.ptr(head), _lib.ptr(tail), _lib.ptr(eps), slots, m, n, dim, B, n_ep,
                                   float(a), float(b), float(repulsion_strength), float(learning_rate) / 4.0, float(negative_sample_rate), 0,
-                                  int(seed), _lib.ptr(ws4), ws4.numel() * 4, _lib.stream_ptr()))
+                                  int(seed), _lib.ptr(ws_sgd), ws_sgd.numel(), _lib.stream_ptr()))
     return Y
 
 

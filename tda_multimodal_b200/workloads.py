@@ -60,6 +60,41 @@ def c1_activations(seed=1000, n_layers=32, d=4096, metadata=None):
     return out
 
 
+def adversarial_activations(seed=6000, n_layers=32, d=4096):
+    """Inputs of experiments/adversarial_compositional_binding/analyze_adversarial_tda.py:34-48: {id: {'metadata': {...},
+    'activations': {'layer_i': vec}}} with the four conditions of generate_adversarial_metadata.py:39-108 (36 matched, 180
+    colour-mismatch, 180 shape-mismatch, 324 both-mismatch samples).  Latent = image (colour, shape) angles plus a text
+    component whose weight grows with the layer."""
+    from itertools import product
+    colors = ["red", "green", "blue", "yellow", "cyan", "magenta"]
+    shapes = ["cube", "sphere", "pyramid", "cone", "torus", "cylinder"]
+    meta = []
+    for ic, ish in product(colors, shapes):
+        base = f"{ic}_{ish}"
+        meta.append(dict(id=f"{base}_matched", condition="matched", img_color=ic, img_shape=ish, txt_color=ic, txt_shape=ish))
+        meta += [dict(id=f"{base}_color_{tc}", condition="color_mismatch", img_color=ic, img_shape=ish, txt_color=tc, txt_shape=ish)
+                 for tc in colors if tc != ic]
+        meta += [dict(id=f"{base}_shape_{ts}", condition="shape_mismatch", img_color=ic, img_shape=ish, txt_color=ic, txt_shape=ts)
+                 for ts in shapes if ts != ish]
+        oc, osh = [c for c in colors if c != ic][:3], [s_ for s_ in shapes if s_ != ish][:3]
+        meta += [dict(id=f"{base}_both_{tc}_{ts}", condition="both_mismatch", img_color=ic, img_shape=ish, txt_color=tc, txt_shape=ts)
+                 for tc, ts in product(oc, osh)]
+    out = {m["id"]: {"metadata": m, "activations": {}} for m in meta}
+    ang = lambda vals, v: 2 * np.pi * vals.index(v) / len(vals)
+    for layer in range(n_layers):
+        rng = np.random.default_rng(seed + layer)
+        mix = layer / max(1, n_layers - 1)
+        z = np.zeros((len(meta), 8))
+        for r, m in enumerate(meta):
+            a1, a2 = ang(colors, m["img_color"]), ang(shapes, m["img_shape"])
+            b1, b2 = ang(colors, m["txt_color"]), ang(shapes, m["txt_shape"])
+            z[r] = [np.cos(a1), np.sin(a1), np.cos(a2), np.sin(a2), mix * np.cos(b1), mix * np.sin(b1), mix * np.cos(b2), mix * np.sin(b2)]
+        X = _embed(z + rng.normal(0, 0.05, z.shape), d, rng, noise=0.05 / np.sqrt(d) * 4, scale=8.0 * (1 + layer / 8), offset=0.4)
+        for r, m in enumerate(meta):
+            out[m["id"]]["activations"][f"layer_{layer}"] = X[r].copy()
+    return out
+
+
 def c2_torus(seed=2000, n=2000, d=4096, sigma=0.02):
     """C2: noisy S1 x S1 torus, n points embedded in d dimensions (ripser on the raw distance matrix)."""
     rng = np.random.default_rng(seed)

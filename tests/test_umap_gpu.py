@@ -203,26 +203,63 @@ def test_fit_transform_trustworthiness_vs_oracle(torch_cuda, kind, n, k):
     assert um.graph_.shape == (n, n) and um._sigmas.shape == (n,) and um.embedding_ is Yg
 
 
-def test_sgd_cloud_kernel_matches_epoch_kernel(torch_cuda, tda_option):
-    """The one-launch SGD (one CTA per cloud, embedding in shared memory, TDA_SGD_CLOUD=1) against the launch-per-epoch kernel
-    on a batch of 8 clouds: same schedule and RNG keys, only the order of the float updates differs -- both embeddings must be
-    finite, inside the clip box, equally trustworthy, and different from their common initialisation."""
+def test_sgd_deterministic_kernel_matches_atomic_kernel(torch_cuda, tda_option):
+    """The default SGD (sgd_mode 0: a thread-block cluster per cloud, every vertex sums its own displacement in list order, no
+    atomics, all epochs in one launch) against the per-epoch kernels with float atomics (sgd_mode 3) on a batch of 8 clouds:
+    same schedule and update rule, so both embeddings must be finite, inside the clip box and equally trustworthy -- and the
+    default one must be BIT-IDENTICAL from run to run (random_state=42 reproduces, as in the reference; debug_tda_pipeline.py:100)."""
     torch = torch_cuda
     from tda_multimodal_b200 import umap_
     rng = np.random.default_rng(91)
     X = np.stack([activations(400, 128, rng, kind="torus" if i % 2 else "clusters") for i in range(8)])
     Xd = torch.from_numpy(X).cuda()
     out = {}
-    for mode in ("0", "1"):
-        tda_option("sgd_mode", int(mode))
+    for mode in (0, 3, 0):
+        tda_option("sgd_mode", mode)
         Y = umap_.umap_fit_batch(Xd, n_neighbors=15, n_components=3, metric="cosine", random_state=42).cpu().numpy()
         assert Y.shape == (8, 400, 3) and np.isfinite(Y).all() and np.abs(Y).max() < 100
+        if mode == 0 and 0 in out:
+            assert np.array_equal(out[0], Y), "deterministic SGD differs between two runs with the same seed"
         out[mode] = Y
-    t0 = [_trust(X[i], out["0"][i], "cosine") for i in range(8)]
-    t1 = [_trust(X[i], out["1"][i], "cosine") for i in range(8)]
-    assert min(t1) > 0.8 and np.mean(t1) >= np.mean(t0) - 0.02, (t0, t1)
-    rel = np.linalg.norm(out["0"] - out["1"], axis=2).mean() / np.linalg.norm(out["0"] - out["0"].mean(1, keepdims=True), axis=2).mean()
-    print("mean point displacement between the two kernels / cloud radius:", rel, "trust", np.mean(t0), np.mean(t1))
+    t0 = [_trust(X[i], out[0][i], "cosine") for i in range(8)]
+    t3 = [_trust(X[i], out[3][i], "cosine") for i in range(8)]
+    assert min(t0) > 0.8 and np.mean(t0) >= np.mean(t3) - 0.02, (t0, t3)
+    rel = np.linalg.norm(out[0] - out[3], axis=2).mean() / np.linalg.norm(out[3] - out[3].mean(1, keepdims=True), axis=2).mean()
+    print("mean point displacement between the two kernels / cloud radius:", rel, "trust", np.mean(t0), np.mean(t3))
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 8])
+def test_sgd_cluster_sizes_agree(torch_cuda, tda_option, cluster):
+    """The deterministic kernel partitions the vertices over the CTAs of a cluster; the partition must not change a single bit."""
+    torch = torch_cuda
+    from tda_multimodal_b200 import umap_
+    rng = np.random.default_rng(17)
+    Xd = torch.from_numpy(np.stack([activations(333, 64, rng, kind="torus") for _ in range(3)])).cuda()
+    tda_option("sgd_cluster", 4)
+    want = umap_.umap_fit_batch(Xd, n_neighbors=10, n_components=3, metric="cosine", random_state=7).cpu().numpy()
+    tda_option("sgd_cluster", cluster)
+    got = umap_.umap_fit_batch(Xd, n_neighbors=10, n_components=3, metric="cosine", random_state=7).cpu().numpy()
+    assert np.array_equal(got, want)
+
+
+def test_transform_deterministic_and_equals_atomic_kernel(torch_cuda, tda_option):
+    """transform(): the warp-per-point kernel (sgd_mode 0) gives bit-identical results run to run and the same quality as the
+    per-epoch atomic kernel (both optimise every query point against the fixed training embedding)."""
+    torch = torch_cuda
+    from tda_multimodal_b200 import umap_
+    rng = np.random.default_rng(5)
+    Xtr, Xq = activations(500, 96, rng, kind="torus"), activations(200, 96, np.random.default_rng(6), kind="torus")
+    um = umap_.UMAP(n_neighbors=15, n_components=3, metric="cosine", random_state=42).fit(Xtr)
+    out = {}
+    for mode in (0, 3, 0):
+        tda_option("sgd_mode", mode)
+        Yq = um.transform(Xq)
+        assert Yq.shape == (200, 3) and np.isfinite(Yq).all()
+        if mode == 0 and 0 in out:
+            assert np.array_equal(out[0], Yq)
+        out[mode] = Yq
+    rad = np.linalg.norm(um.embedding_ - um.embedding_.mean(0), axis=1).mean()
+    assert np.median(np.linalg.norm(out[0] - out[3], axis=1)) < 0.25 * rad
 
 
 def test_downstream_diagrams_clusters(torch_cuda):
