@@ -38,6 +38,7 @@ void tda_launch_count_reset(void);
  *   rips_reducer (0): residual H1 reducer -- 0 "sweep2" substitute by rank + verify by window, 1 row sweep with a sequential
  *                     resolver warp, 2 row sweep substitute-then-verify per 512-row chunk, 3 key bitset (any n)
  *   rips_w0 (1024), rips_wsparse (8192), rips_wmax (32768), rips_dense_min (64), rips_dense_div (8): sweep2 window schedule
+ *   rips_cluster (4): CTAs of the thread-block cluster that reduces one cloud (sweep2)
  *   sgd_mode (0): 0 deterministic SGD (thread-block cluster per cloud for fit, warp per point for transform; bit-reproducible
  *                 for a given seed), 3 per-epoch kernels with float atomics (used anyway for n > 8192 or n_components != 3)
  *   sgd_cluster (4): CTAs per cloud of the deterministic fit kernel;  sweep_exclusive (0), knn_loads (8), debug_sync (0),
@@ -120,7 +121,7 @@ int tda_umap_transform_init(const int32_t* knn_idx, const float* knn_dist, const
 /* spectral initialisation (umap-learn spectral_layout / multi_component_layout):
  *  tda_graph_components: connected components of the pruned graph (entries with eps > 0); comp [batch,n] ids numbered
  *   by smallest member vertex (scipy order), ncomp [batch], comp_size [batch,n] (first ncomp entries), degree [batch,n];
- *   ws: 4*batch*n bytes.
+ *   ws: 12*batch*n bytes, 8-byte aligned (degrees are accumulated in 64-bit fixed point: order independent, reproducible).
  *  tda_spectral_embed: for every component with >= min_size vertices, the `dim` non-trivial bottom eigenvectors of the
  *   symmetric normalised Laplacian (Lanczos, full reorthogonalisation), written as unit vectors into the component's
  *   rows of Y [batch,n,dim]; evals [batch,maxcomp,4] (eigenvalues of D^-1/2 W D^-1/2) or NULL.
@@ -191,7 +192,8 @@ int tda_rips_h2(const void* ws1, int n, int batch, int cap1, size_t pool_bytes1,
  *  added), 4 rows substituted, 5 non-apparent pivots (events + deaths), 6 windows, 7 largest |V|, 8..13 SM cycles of CTA
  *  thread 0 in: substitution round 1, later rounds, apply + heavy lists, verification, decision + events, Pm moves + column
  *  finalisation; 14 edges added through reduced columns, 15 heavy rows verified, 16 substitution rounds after the first,
- *  17 rows handled in those rounds, 18 rows of Pm moved, 19 columns that went dense, 20 spurious stops, 21 flips undone.
+ *  17 rows handled in those rounds, 18 rows of Pm moved, 19 columns that went dense, 20 spurious stops, 21 flips undone,
+ *  22 SM cycles thread 0 spent in cluster barriers (part of 8..13), 23 number of those barriers.
  *  (reducers 1-3 fill 0..15 with their own counters: rows streamed, pivots, restarts, ...) */
 #define TDA_RIPS_STATS 24
 int tda_rips_stats(const void* ws, int n, int batch, int maxdim, int cap1, size_t pool_bytes, int64_t* stats_host);

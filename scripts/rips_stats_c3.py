@@ -15,6 +15,7 @@ for rep in range(3):
     torch.cuda.synchronize(); dt = time.perf_counter() - t
 print(f"reducer {_lib.rips_reducer()}: rips_batch {L} clouds: {dt*1e3:.1f} ms (whole Rips stage incl. sort / H0 / apparent pairs / D2H)")
 keys = [k for k in res[0]["stats"] if not k.startswith("spare")]
+keys = [k for k in keys if k not in ("columns", "apparent", "edges_via_columns", "max_v")]
 cyc = [k for k in keys if k.startswith("cyc_")]
 rows = sorted(range(L), key=lambda p: -sum(res[p]["stats"][k] for k in cyc))
 print("cloud " + " ".join(f"{k[:13]:>13s}" for k in keys) + "   total_Mcyc")

@@ -2348,7 +2348,27 @@ static int rips_enqueue(const float* dm, int n, int batch, int maxdim, float thr
         const size_t dyn = Sweeper2::dyn_bytes(L.xw, L.s2_wmax);
         if (dyn > (size_t)200 * 1024) return set_error(TDA_ERR_UNSUPPORTED, "tda_rips: sweep2 needs %zu bytes of shared memory (n=%d, rips_wmax=%d)", dyn, n, L.s2_wmax);
         TDA_CUDA_CHECK(cudaFuncSetAttribute(rips_sweep2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-        rips_sweep2_kernel<<<L.grid, kS2Threads, dyn, stream>>>(P);
+        // one thread-block cluster per cloud at a time: cluster size from the option, shrunk for big batches (more clouds than
+        // clusters fit on the machine: rather one cloud per SM) 
+        int C = (int)option("rips_cluster");
+        if (C != 1 && C != 2 && C != 4 && C != 8) C = 4;
+        while (C > 1 && (long long)batch * C > 2ll * sms) C >>= 1;
+        int nclusters = sms / C;
+        if (nclusters > batch) nclusters = batch;
+        if (nclusters > L.grid) nclusters = L.grid;
+        if (nclusters < 1) nclusters = 1;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)(nclusters * C), 1, 1);
+        cfg.blockDim = dim3(kS2Threads, 1, 1);
+        cfg.dynamicSmemBytes = dyn;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        TDA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, rips_sweep2_kernel, P));
       } else if (L.sweep) {
         // TDA_SWEEP_EXCLUSIVE=1: ask for all of the SM's shared memory, so that no CTA of a kernel running on another stream
         // (UMAP SGD of the next chunk ...) shares the SM -- and the issue slots -- with the latency-bound resolver warp

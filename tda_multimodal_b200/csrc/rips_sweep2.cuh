@@ -9,23 +9,29 @@
 //    [pos, hi) is substituted in rounds: round 1 takes every row whose parents are final (below the window, or rows that the
 //    substitution does not change), the later rounds run in shared memory on the few rows that wait for a row of the window.
 //  * verification: V must be a cocycle of the complex below the cursor, i.e. every row (x_M ^ X[c] ^ X[d]) & lune(M) must be
-//    empty (X = V as a symmetric bit matrix).  Only rows with a touched endpoint can fail ("heavy" rows).
-//      sparse mode : the lune comes from the two rank rows (exact); the smallest failing key of the window is the event.
-//      dense mode  : (>= 1/8 of a window heavy) the mask is Pend[c] & Pend[d], Pend = adjacency of ALL edges below the window's
-//                    end, kept as a bit matrix that only moves forward inside a column.  If the window leaves V a cocycle of
-//                    the complex at its end, every row passes; a failing bit (M, w) under this superset mask belongs to the
-//                    triangle {c,d,w}, whose own row lies in the window, so the failing rows in ascending order, re-checked
-//                    with the exact lune, give the first true failure (the others are spurious stops: nothing to undo).
+//    empty (X = V as a symmetric bit matrix).  Only rows with a touched endpoint can fail ("heavy" rows).  The candidate bits
+//    of a row are (x_M ^ X[c] ^ X[d]); a candidate w is a true failure iff rank(c,w) < M and rank(d,w) < M (two probes).
+//      sparse mode : few candidates per row; they are probed directly.
+//      dense mode  : (>= 1/8 of a window heavy) the candidates are first masked with Pend[c] & Pend[d], Pend = adjacency of ALL
+//                    edges below the window's end, kept as a bit matrix that only moves forward inside a column.  If the window
+//                    leaves V a cocycle of the complex at its end, every row passes; a surviving bit (M, w) belongs to the
+//                    triangle {c,d,w}, whose own row lies in the window, so probing the survivors finds the first true failure.
+//    The smallest true failing key of the window is the event.
 //  * event (M*, w*): the flips above M* are undone; unowned pivot -> death of the column; pivot owned by a reduced column j ->
 //    V ^= V_j and the sweep resumes at row M* (whose substitution is then a no-op).
 //  * windows grow (w0, doubling) while they are clean and shrink back after an event (sparse mode); in dense mode the window
 //    keeps its end after an event.
 //
-// One CTA per cloud at a time (dynamic work counter).  All per-window passes are warp-per-32-rows with coalesced 8-byte loads
-// of the row tables; global x bits are rewritten one word per 32 rows without atomics.
+// One thread-block CLUSTER per cloud at a time (dynamic work counter): every pass over the rows / heavy rows of a window is dealt
+// to the warps of all CTAs of the cluster (the passes are bound by L2 / HBM latency: more warps = more loads in flight).  The
+// window's bookkeeping (x words, done bits, pending and heavy lists, counters) lives in the shared memory of CTA 0 and is reached
+// by the other CTAs through distributed shared memory; the touched-vertex bitmaps are replicated.  X, Pm, the x bits by rank and
+// the V list are global (L2-resident).  All per-window passes are warp-per-32-rows with coalesced 8-byte loads of the row tables;
+// global x bits are rewritten one word per 32 rows without atomics.
 
 constexpr int kS2Threads = 512;
 constexpr int kS2Warps = kS2Threads / 32;
+constexpr int kS2MaxCluster = 8;
 constexpr int kS2ListSmem = 2048;      // entries of the pending / heavy lists kept in shared memory (the rest spills to global scratch)
 constexpr int kS2MaxRounds = 4096;     // substitution rounds per window (depth of the apparent graph is ~30): beyond -> internal error
 constexpr int kS2MaxWindow = 65472;    // rows of a window (16-bit local indices in the pending entries)
@@ -38,50 +44,77 @@ struct Sweep2Smem {
   uint32_t vcount, vcount2, vsel;
   int abort_flag, problem;
   uint32_t npend[3];
-  uint32_t nheavy, nfail, fail_row, cand, newtouch;
-  unsigned long long fail_key;
-  int ev_w;
+  uint32_t nheavy, nfail, newtouch, nundone;
+  uint32_t fail_key;           // smallest failing key of the window: (row - base_row) * n + (n - 1 - vertex), 32 bits (< 65536 * n)
   unsigned long long st[16];
 };
 enum { S2_WINDOWS = 0, S2_ROUNDS, S2_HEAVY, S2_FLIPS, S2_UNDONE, S2_EVENTS, S2_SPURIOUS, S2_SUBST, S2_LATE, S2_PM, S2_DENSE, S2_EXACT, S2_DEATHS };
+
+__device__ __forceinline__ uint32_t s2_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t s2_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t s2_clusterid() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+// generic pointer to the same shared-memory object in CTA `rank` of the cluster
+template <typename T>
+__device__ __forceinline__ T* s2_map(T* p, uint32_t rank) {
+  uint64_t out;
+  asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"((uint64_t)p), "r"(rank));
+  return reinterpret_cast<T*>(out);
+}
 
 struct Sweeper2 {
   static constexpr uint64_t kEmpty = ~0ull;
   static constexpr unsigned kFull = 0xffffffffu;
   const ReduceParams& P;
-  Sweep2Smem& S;
-  uint32_t *touched, *tnew, *xs, *xo, *done;
-  uint2 *pend_s, *heavy_s;     // [2][kS2ListSmem], [kS2ListSmem]
+  Sweep2Smem& S;               // CTA 0's control block (remote for the other CTAs)
+  uint32_t *touched, *tnew;    // this CTA's copies of the touched-vertex bitmaps
+  uint32_t *xs, *xo, *done;    // CTA 0's window bitmaps
+  uint2 *pend_s, *heavy_s;     // CTA 0's lists: [2][kS2ListSmem], [kS2ListSmem]
   const int tid, lane, warp;
+  const uint32_t crank, csize;
+  const int gtid, gwarp, nthreads, nwarps;   // cluster-wide thread / warp ids and counts
+  const int slot;                           // scratch slot of this cluster
   const int* R; const uint32_t* EN; const uint2* EA; const uint2* PAR; int T; int n; int W;
   uint32_t *X, *Pm, *vbits, *vl0;
   uint2 *pend_g, *heavy_g;
   uint32_t p_pos; bool p_valid;
   uint64_t* hkeys; int* hvals;
+  long long cyc_sync; unsigned long long n_sync;   // (diagnostics) cycles this thread spent in cluster barriers, and their number
 
-  __device__ Sweeper2(const ReduceParams& p, Sweep2Smem& s, uint32_t* dyn)
-      : P(p), S(s), tid(threadIdx.x), lane(threadIdx.x & 31), warp(threadIdx.x >> 5) {
+  __device__ Sweeper2(const ReduceParams& p, Sweep2Smem& s_local, uint32_t* dyn)
+      : P(p), S(*s2_map(&s_local, 0)), tid(threadIdx.x), lane(threadIdx.x & 31), warp(threadIdx.x >> 5), crank(s2_ctarank()), csize(s2_nctarank()),
+        gtid((int)(s2_ctarank() * kS2Threads + threadIdx.x)), gwarp((int)(s2_ctarank() * kS2Warps + (threadIdx.x >> 5))),
+        nthreads((int)(s2_nctarank() * kS2Threads)), nwarps((int)(s2_nctarank() * kS2Warps)), slot((int)s2_clusterid()) {
     n = P.n;
     W = P.xw;
     const int nw = P.s2_wmax / 32 + 4;
     touched = dyn;
     tnew = touched + W;
-    xs = tnew + W;
+    uint32_t* dyn0 = s2_map(dyn, 0);
+    xs = dyn0 + 2 * W;
     xo = xs + nw;
     done = xo + nw;
     pend_s = reinterpret_cast<uint2*>(done + nw + ((2 * W + 3 * nw) & 1));   // 8-byte aligned
     heavy_s = pend_s + 2 * kS2ListSmem;
-    X = P.xmat + (size_t)blockIdx.x * (size_t)n * W;
-    Pm = P.pmat + (size_t)blockIdx.x * (size_t)n * W;
+    X = P.xmat + (size_t)slot * (size_t)n * W;
+    Pm = P.pmat + (size_t)slot * (size_t)n * W;
     p_pos = 0; p_valid = false;
-    vbits = P.vbits + (size_t)blockIdx.x * P.vwords;
-    vl0 = P.vlist + (size_t)blockIdx.x * 2 * P.vcap;
-    pend_g = P.s2_pend + (size_t)blockIdx.x * 2 * (size_t)(P.s2_wmax + 64);
-    heavy_g = P.s2_heavy + (size_t)blockIdx.x * (size_t)(P.s2_wmax + 64);
+    cyc_sync = 0; n_sync = 0;
+    vbits = P.vbits + (size_t)slot * P.vwords;
+    vl0 = P.vlist + (size_t)slot * 2 * P.vcap;
+    pend_g = P.s2_pend + (size_t)slot * 2 * (size_t)(P.s2_wmax + 64);
+    heavy_g = P.s2_heavy + (size_t)slot * (size_t)(P.s2_wmax + 64);
   }
   static __host__ __device__ size_t dyn_bytes(int W, int wmax) {
     const int nw = wmax / 32 + 4;
     return sizeof(uint32_t) * (size_t)(2 * W + 3 * nw + 2) + sizeof(uint2) * (size_t)(3 * kS2ListSmem);
+  }
+  // barrier over the cluster (release / acquire: shared-memory and global writes of every CTA are visible afterwards)
+  __device__ __forceinline__ void csync() {
+    const long long t = clock64();
+    if (csize > 1) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    else __syncthreads();
+    cyc_sync += clock64() - t;
+    ++n_sync;
   }
   __device__ __forceinline__ uint32_t* vlist(uint32_t sel) const { return vl0 + (size_t)sel * P.vcap; }
   __device__ __forceinline__ bool tbit(uint32_t v) const { return (touched[v >> 5] >> (v & 31)) & 1u; }
@@ -97,39 +130,46 @@ struct Sweeper2 {
     atomicXor(&X[(size_t)c * W + (d >> 5)], 1u << (d & 31));
     atomicXor(&X[(size_t)d * W + (c >> 5)], 1u << (c & 31));
   }
+  // vertex v becomes touched: in every CTA's bitmap (the new-in-this-window bitmap tnew sits W words behind touched)
   __device__ __forceinline__ void touch(uint32_t v) {
     const uint32_t m = 1u << (v & 31);
     if (!(touched[v >> 5] & m)) {
       const uint32_t old = atomicOr(&touched[v >> 5], m);
-      if (!(old & m)) { atomicOr(&tnew[v >> 5], m); S.newtouch = 1; }
+      if (!(old & m)) {
+        for (uint32_t r = 0; r < csize; ++r) {
+          uint32_t* tr = s2_map(touched, r);
+          if (r != crank) atomicOr(&tr[v >> 5], m);
+          atomicOr(&tr[W + (v >> 5)], m);
+        }
+        S.newtouch = 1;
+      }
     }
   }
   // edge e=(c,d) toggles in V: x bit, X, touched, V list (any thread; duplicates in the list are fine, v_compact drops them)
-  __device__ __forceinline__ void toggle_edge(uint32_t e, uint32_t c, uint32_t d, bool append) {
+  __device__ __forceinline__ void toggle_edge(uint32_t e, uint32_t c, uint32_t d) {
     atomicXor(&vbits[e >> 5], 1u << (e & 31));
     x_flip(c, d);
     touch(c); touch(d);
-    if (append) {
-      const uint32_t pos = atomicAdd(&S.vcount, 1u);
-      if (pos < (uint32_t)P.vcap) vlist(S.vsel)[pos] = e;
-      else fail(TDA_ERR_CAPACITY);
-    }
+    const uint32_t pos = atomicAdd(&S.vcount, 1u);
+    if (pos < (uint32_t)P.vcap) vlist(S.vsel)[pos] = e;
+    else fail(TDA_ERR_CAPACITY);
   }
   // V list -> the distinct edges with x = 1 (x bits are exact; the list may hold an edge several times or with x = 0)
   __device__ __forceinline__ void v_compact() {
-    __syncthreads();
+    csync();
     const uint32_t nin = min(S.vcount, (uint32_t)P.vcap);
-    const uint32_t* src = vlist(S.vsel);
-    uint32_t* dst = vlist(S.vsel ^ 1);
-    if (tid == 0) S.vcount2 = 0;
-    __threadfence();
-    __syncthreads();
-    for (uint32_t i0 = 0; i0 < nin; i0 += kS2Threads) {
-      const uint32_t i = i0 + tid;
+    const uint32_t sel = S.vsel;
+    const uint32_t* src = vlist(sel);
+    uint32_t* dst = vlist(sel ^ 1);
+    csync();
+    if (gtid == 0) S.vcount2 = 0;
+    csync();
+    for (uint32_t i0 = 0; i0 < nin; i0 += (uint32_t)nthreads) {
+      const uint32_t i = i0 + (uint32_t)gtid;
       bool keep = false;
       uint32_t e = 0;
       if (i < nin) {
-        e = src[i];
+        e = __ldcg(&src[i]);
         const uint32_t m = 1u << (e & 31);
         keep = (atomicAnd(&vbits[e >> 5], ~m) & m) != 0;
       }
@@ -137,35 +177,35 @@ struct Sweeper2 {
       uint32_t bs = 0;
       if (lane == 0 && bal) bs = atomicAdd(&S.vcount2, (uint32_t)__popc(bal));
       bs = __shfl_sync(kFull, bs, 0);
-      if (keep) dst[bs + __popc(bal & ((1u << lane) - 1))] = e;
+      if (keep) __stcg(&dst[bs + __popc(bal & ((1u << lane) - 1))], e);
     }
     __threadfence();
-    __syncthreads();
+    csync();
     const uint32_t nout = S.vcount2;
-    for (uint32_t i = tid; i < nout; i += kS2Threads) {
-      const uint32_t e = dst[i];
+    for (uint32_t i = (uint32_t)gtid; i < nout; i += (uint32_t)nthreads) {
+      const uint32_t e = __ldcg(&dst[i]);
       atomicOr(&vbits[e >> 5], 1u << (e & 31));
     }
     __threadfence();
-    __syncthreads();
-    if (tid == 0) { S.vsel ^= 1; S.vcount = nout; }
-    __syncthreads();
+    csync();
+    if (gtid == 0) { S.vsel = sel ^ 1; S.vcount = nout; }
+    csync();
   }
-  // after v_compact: x bits, X bits and the touched mask back to zero; the list empty
+  // after v_compact: x bits, X bits and the touched masks back to zero; the list empty
   __device__ __forceinline__ void v_clear() {
     const uint32_t nin = S.vcount;
     const uint32_t* src = vlist(S.vsel);
-    for (uint32_t i = tid; i < nin; i += kS2Threads) {
-      const uint32_t e = src[i];
+    for (uint32_t i = (uint32_t)gtid; i < nin; i += (uint32_t)nthreads) {
+      const uint32_t e = __ldcg(&src[i]);
       atomicAnd(&vbits[e >> 5], ~(1u << (e & 31)));
       const uint32_t en = __ldg(&EN[e]);
       x_flip(en >> 16, en & 0xffffu);
     }
     for (int i = tid; i < W; i += kS2Threads) { touched[i] = 0; tnew[i] = 0; }
     __threadfence();
-    __syncthreads();
-    if (tid == 0) S.vcount = 0;
-    __syncthreads();
+    csync();
+    if (gtid == 0) S.vcount = 0;
+    csync();
   }
   __device__ __forceinline__ int hash_find(uint64_t key) const {
     uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32) & (uint32_t)(P.hcap - 1);
@@ -176,37 +216,42 @@ struct Sweeper2 {
       h = (h + 1) & (uint32_t)(P.hcap - 1);
     }
   }
-  __device__ __forceinline__ void hash_insert(uint64_t key, int val) {  // thread 0
+  __device__ __forceinline__ void hash_insert(uint64_t key, int val) {  // one thread
     uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32) & (uint32_t)(P.hcap - 1);
     while (__ldcg(&hkeys[h]) != kEmpty) h = (h + 1) & (uint32_t)(P.hcap - 1);
     __stcg(&hvals[h], val);
     __stcg(&hkeys[h], key);
+    __threadfence();
   }
+  // CTA 0 sorts the birth list (global memory, bitonic)
   __device__ __forceinline__ void sort_blist(int* bl, int nb) {
-    int np2 = 1;
-    while (np2 < nb) np2 <<= 1;
-    for (int i = nb + tid; i < np2; i += kS2Threads) bl[i] = 0x7fffffff;
-    __syncthreads();
-    for (int k = 2; k <= np2; k <<= 1)
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int i = tid; i < np2; i += kS2Threads) {
-          const int ixj = i ^ j;
-          if (ixj > i) {
-            const int a = bl[i], b = bl[ixj];
-            const bool up = ((i & k) == 0);
-            if ((a > b) == up) { bl[i] = b; bl[ixj] = a; }
+    if (crank == 0) {
+      int np2 = 1;
+      while (np2 < nb) np2 <<= 1;
+      for (int i = nb + tid; i < np2; i += kS2Threads) bl[i] = 0x7fffffff;
+      __syncthreads();
+      for (int k = 2; k <= np2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int i = tid; i < np2; i += kS2Threads) {
+            const int ixj = i ^ j;
+            if (ixj > i) {
+              const int a = bl[i], b = bl[ixj];
+              const bool up = ((i & k) == 0);
+              if ((a > b) == up) { bl[i] = b; bl[ixj] = a; }
+            }
           }
+          __syncthreads();
         }
-        __syncthreads();
-      }
+      __threadfence();
+    }
   }
 
-  // ---- Pm = adjacency bit matrix of the edges with rank < p_pos.  All threads; ends with the bits performed and a barrier.
+  // ---- Pm = adjacency bit matrix of the edges with rank < p_pos.  All threads of the cluster; ends with the bits performed and a barrier.
   __device__ __forceinline__ void p_set_rows(uint32_t lo, uint32_t hi, bool set) {
-    for (uint32_t row0 = lo + tid; row0 < hi; row0 += 4 * kS2Threads) {
+    for (uint32_t row0 = lo + (uint32_t)gtid; row0 < hi; row0 += 4u * (uint32_t)nthreads) {
       uint32_t en[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { const uint32_t row = row0 + u * kS2Threads; en[u] = row < hi ? __ldg(&EN[row]) : 0xffffffffu; }
+      for (int u = 0; u < 4; ++u) { const uint32_t row = row0 + (uint32_t)(u * nthreads); en[u] = row < hi ? __ldg(&EN[row]) : 0xffffffffu; }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         if (en[u] == 0xffffffffu) continue;
@@ -225,7 +270,7 @@ struct Sweeper2 {
     const uint32_t dist = target > p_pos ? target - p_pos : p_pos - target;
     if (!p_valid || (uint64_t)dist * 32ull > (uint64_t)n * (uint64_t)n) {
       // rebuild from the rank matrix: one warp per vertex row, a word per ballot
-      for (int c = warp; c < n; c += kS2Warps) {
+      for (int c = gwarp; c < n; c += nwarps) {
         const int* Rc = R + (size_t)c * n;
         for (int k0 = 0; k0 < W; k0 += 32) {
           uint32_t mine = 0;
@@ -241,17 +286,17 @@ struct Sweeper2 {
         }
       }
       p_valid = true;
-      if (tid == 0) S.st[S2_PM] += (unsigned long long)n * n / 32;
+      if (gtid == 0) S.st[S2_PM] += (unsigned long long)n * n / 32;
     } else if (target > p_pos) {
       p_set_rows(p_pos, target, true);
-      if (tid == 0) S.st[S2_PM] += dist;
+      if (gtid == 0) S.st[S2_PM] += dist;
     } else if (target < p_pos) {
       p_set_rows(target, p_pos, false);
-      if (tid == 0) S.st[S2_PM] += dist;
+      if (gtid == 0) S.st[S2_PM] += dist;
     }
     p_pos = target;
     __threadfence();
-    __syncthreads();
+    csync();
   }
 
   // ---- one row with its exact lune { w : rank(c,w) < M and rank(d,w) < M } (one warp): the highest failing vertex, or -1
@@ -266,17 +311,17 @@ struct Sweeper2 {
       const int k = k0 + lane;
       const uint32_t xx = k < W ? (__ldcg(&Xc[k]) ^ __ldcg(&Xd[k])) : 0u;
       uint32_t lmine = 0;
-      for (int kk0 = 0; kk0 < kend; kk0 += 8) {
-        int ra[8], rb[8];
+      for (int kk0 = 0; kk0 < kend; kk0 += 16) {
+        int ra[16], rb[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 16; ++u) {
           const int w = (k0 + kk0 + u) * 32 + lane;
           const bool ok = (kk0 + u) < kend && w < n;
           ra[u] = ok ? __ldg(&Rc[w]) : kRankDiag;
           rb[u] = ok ? __ldg(&Rd[w]) : kRankDiag;
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 16; ++u) {
           const unsigned word = __ballot_sync(kFull, ra[u] < (int)M && rb[u] < (int)M);
           if (lane == kk0 + u) lmine = word;
         }
@@ -287,7 +332,7 @@ struct Sweeper2 {
     return __reduce_max_sync(kFull, best);
   }
 
-  // ---- appends one entry per flagged lane to a list (warp-aggregated); returns nothing.  `cnt` in shared memory
+  // ---- appends one entry per flagged lane to a list (warp-aggregated).  `cnt` lives in CTA 0's shared memory
   template <typename Ref>
   __device__ __forceinline__ void warp_append(bool flag, uint2 ent, uint32_t* cnt, Ref ref) {
     const unsigned bal = __ballot_sync(kFull, flag);
@@ -311,46 +356,45 @@ struct Sweeper2 {
     const int nb = P.bcount[p];
     unsigned long long* st = P.stats + (size_t)p * ST_N;
     if (nb > P.cap1) {
-      if (tid == 0) { P.counts[p * 4 + 3] = TDA_ERR_CAPACITY; P.counts[p * 4 + 1] = 0; }
+      if (gtid == 0) { P.counts[p * 4 + 3] = TDA_ERR_CAPACITY; P.counts[p * 4 + 1] = 0; }
       return;
     }
     p_valid = false;   // Pm belongs to the previous cloud's rank matrix
     sort_blist(bl, nb);
-    for (int i = tid; i < P.hcap; i += kS2Threads) hkeys[i] = kEmpty;
+    for (int i = gtid; i < P.hcap; i += nthreads) __stcg(&hkeys[i], kEmpty);
     for (int i = tid; i < W; i += kS2Threads) { touched[i] = 0; tnew[i] = 0; }
-    if (tid == 0) {
-      S.vcount = 0; S.vsel = 0; S.abort_flag = 0;
+    if (gtid == 0) {
+      S.vcount = 0; S.vsel = 0; S.abort_flag = 0; S.nundone = 0;
       for (int q = 0; q < 16; ++q) S.st[q] = 0;
     }
     __threadfence();
-    __syncthreads();
+    csync();
     int nrows = 0;
     int64_t vpool_used = 0;
     unsigned long long maxv = 0, badd_edges = 0;
     long long cyc[6] = {0, 0, 0, 0, 0, 0};
     long long t0;
+    cyc_sync = 0; n_sync = 0;
     float* out = P.h1_pairs + (size_t)p * P.cap1 * 2;
     int64_t* outs = P.h1_simplex ? P.h1_simplex + (size_t)p * P.cap1 * 2 : nullptr;
     const uint32_t w0 = (uint32_t)P.s2_w0, wsparse = (uint32_t)P.s2_wsparse, wmax = (uint32_t)P.s2_wmax;
-    const uint32_t gw = (uint32_t)(P.s2_wmax + 64);
 
     for (int ci = nb - 1; ci >= 0; --ci) {
-      const int rbirth = bl[ci];
+      const int rbirth = __ldcg(&bl[ci]);
       {  // V = {birth edge}
         const uint32_t en = __ldg(&EN[rbirth]);
-        if (tid == 0) toggle_edge((uint32_t)rbirth, en >> 16, en & 0xffffu, true);
-        __threadfence();
-        __syncthreads();
+        if (gtid == 0) { toggle_edge((uint32_t)rbirth, en >> 16, en & 0xffffu); __threadfence(); }
+        csync();
       }
       bool essential = false, dense = false, keep_hi = false;
       uint64_t pivot = 0;
       uint32_t pos = (uint32_t)rbirth + 1, win = w0, hi = 0;
       unsigned long long guard = 0;
-      const unsigned long long guard_max = 64ull + 8ull * ((unsigned long long)T / max(1u, w0) + 1ull) + 4ull * (unsigned long long)nb;
+      const unsigned long long guard_max = 1024ull + 4ull * ((unsigned long long)T / max(1u, w0) + 1ull) + 64ull * (unsigned long long)nb;
       for (;;) {
         if (S.abort_flag) break;
         if (pos >= (uint32_t)T) { essential = true; break; }
-        if (++guard > guard_max + (unsigned long long)T) { if (tid == 0) fail(TDA_ERR_INTERNAL_S2); __syncthreads(); break; }
+        if (++guard > guard_max) { csync(); if (gtid == 0) fail(TDA_ERR_INTERNAL_S2); csync(); break; }
         if (!keep_hi || hi <= pos) {
           hi = (pos + win + 31u) & ~31u;
           if (hi > (uint32_t)T) hi = (uint32_t)T;
@@ -358,21 +402,22 @@ struct Sweeper2 {
         keep_hi = false;
         if (S.vcount + (hi - pos) + 64u > (uint32_t)P.vcap) {
           v_compact();
-          if (S.vcount + (hi - pos) + 64u > (uint32_t)P.vcap) { if (tid == 0) fail(TDA_ERR_CAPACITY); __syncthreads(); break; }
+          if (S.vcount + (hi - pos) + 64u > (uint32_t)P.vcap) { csync(); if (gtid == 0) fail(TDA_ERR_CAPACITY); csync(); break; }
         }
         const uint32_t g0 = pos >> 5, g1 = (hi + 31u) >> 5;
         const uint32_t base_row = g0 << 5;
-        if (tid == 0) {
-          S.npend[0] = S.npend[1] = S.npend[2] = 0; S.nheavy = 0; S.nfail = 0; S.fail_row = 0xffffffffu; S.cand = 0xffffffffu;
-          S.fail_key = ~0ull; S.newtouch = 0; S.ev_w = -1;
+        const uint32_t vmark = S.vcount;
+        csync();   // everybody has read the control block of the previous window
+        if (gtid == 0) {
+          S.npend[0] = S.npend[1] = S.npend[2] = 0; S.nheavy = 0; S.nfail = 0;
+          S.fail_key = 0xffffffffu; S.newtouch = 0;
           S.st[S2_WINDOWS] += 1; S.st[S2_SUBST] += hi - pos;
         }
         for (int i = tid; i < W; i += kS2Threads) tnew[i] = 0;
-        __syncthreads();
-        const uint32_t vmark = S.vcount;
+        csync();
         t0 = clock64();
         // ---- substitution, round 1: every row of the window, one warp per 32 consecutive ranks, kS2Unroll groups in flight
-        for (uint32_t gb = g0 + warp * kS2Unroll; gb < g1; gb += kS2Warps * kS2Unroll) {
+        for (uint32_t gb = g0 + (uint32_t)gwarp * kS2Unroll; gb < g1; gb += (uint32_t)nwarps * kS2Unroll) {
           uint32_t xold[kS2Unroll];
           uint2 ea[kS2Unroll], par[kS2Unroll];
 #pragma unroll
@@ -424,11 +469,11 @@ struct Sweeper2 {
             warp_append(heavy, make_uint2(row, ea[u].x), &S.nheavy, [&](uint32_t i) { return heavy_ref(i); });
           }
         }
-        __syncthreads();
+        csync();
         cyc[0] += clock64() - t0;
         t0 = clock64();
-        // ---- later rounds: rows that wait for rows of the window; shared memory only (+ the spill part of the list)
-        {
+        // ---- later rounds (CTA 0 alone): rows that wait for rows of the window; shared memory only (+ the spill part of the list)
+        if (crank == 0 && S.npend[0] != 0) {
           int r = 0;
           for (;;) {
             const uint32_t np = S.npend[r % 3];
@@ -464,14 +509,14 @@ struct Sweeper2 {
             ++r;
           }
         }
-        __syncthreads();
+        csync();
         if (S.abort_flag) break;
         cyc[1] += clock64() - t0;
         t0 = clock64();
         // ---- apply: the rows whose x changed flip in X / the V list; the global x words are rewritten (one owner per word)
         {
           bool flipped = false;
-          for (uint32_t g = g0 + warp; g < g1; g += kS2Warps) {
+          for (uint32_t g = g0 + (uint32_t)gwarp; g < g1; g += (uint32_t)nwarps) {
             const uint32_t xnew = xs[g - g0];
             const uint32_t diff = xo[g - g0] ^ xnew;
             if (diff) {
@@ -485,7 +530,7 @@ struct Sweeper2 {
                 x_flip(c, d);
                 touch(c); touch(d);
                 const uint32_t vp = vb + __popc(diff & ((1u << lane) - 1));
-                if (vp < (uint32_t)P.vcap) vlist(S.vsel)[vp] = row;
+                if (vp < (uint32_t)P.vcap) __stcg(&vlist(S.vsel)[vp], row);
                 else fail(TDA_ERR_CAPACITY);
               }
               flipped = true;
@@ -493,12 +538,12 @@ struct Sweeper2 {
           }
           if (flipped) __threadfence();   // the flips are REDs: performed before anybody reads X after the barrier
         }
-        __syncthreads();
+        csync();
         if (S.abort_flag) break;
-        if (tid == 0) S.st[S2_FLIPS] += S.vcount - vmark;
+        if (gtid == 0) { S.st[S2_FLIPS] += S.vcount - vmark; S.st[S2_UNDONE] += S.nundone; S.nundone = 0; }
         // rows that became heavy through a vertex touched in this window
         if (S.newtouch) {
-          for (uint32_t g = g0 + warp; g < g1; g += kS2Warps) {
+          for (uint32_t g = g0 + (uint32_t)gwarp; g < g1; g += (uint32_t)nwarps) {
             const uint32_t row = (g << 5) + lane;
             const bool inwin = row >= pos && row < hi;
             uint2 ea = make_uint2(0u, 0xffffffffu);
@@ -511,23 +556,21 @@ struct Sweeper2 {
             }
             warp_append(h, make_uint2(row, ea.x), &S.nheavy, [&](uint32_t i) { return heavy_ref(i); });
           }
-          __syncthreads();
+          csync();
         }
         cyc[2] += clock64() - t0;
         const uint32_t nh = S.nheavy;
         if (!dense && nh >= max((uint32_t)P.s2_dense_min, (hi - pos) / (uint32_t)P.s2_dense_div)) {
           dense = true;
-          if (tid == 0) S.st[S2_DENSE] += 1;
+          if (gtid == 0) S.st[S2_DENSE] += 1;
         }
-        if (tid == 0) S.st[S2_HEAVY] += nh;
+        if (gtid == 0) S.st[S2_HEAVY] += nh;
         t0 = clock64();
         if (dense) p_move(hi);
         cyc[5] += clock64() - t0;
         t0 = clock64();
-        // ---- verification of the heavy rows, kS2Batch rows per warp in flight.  Candidate bits of a row: (x_M ^ X[c] ^ X[d]), in
-        // dense mode masked with Pend[c] & Pend[d]; a candidate w is a true failure iff rank(c,w) < M and rank(d,w) < M (two
-        // probes of the rank matrix).  The smallest true failing key of the window is the event.
-        for (uint32_t i0 = warp * kS2Batch; i0 < nh; i0 += kS2Warps * kS2Batch) {
+        // ---- verification of the heavy rows, kS2Batch rows per warp in flight (see the header)
+        for (uint32_t i0 = (uint32_t)gwarp * kS2Batch; i0 < nh; i0 += (uint32_t)nwarps * kS2Batch) {
           uint32_t Mr[kS2Batch], cd[kS2Batch], xm[kS2Batch];
 #pragma unroll
           for (int b = 0; b < kS2Batch; ++b) {
@@ -535,8 +578,11 @@ struct Sweeper2 {
             uint2 ent = make_uint2(0xffffffffu, 0u);
             if (i < nh) ent = *heavy_ref(i);
             Mr[b] = ent.x; cd[b] = ent.y;
-            const uint32_t rl = ent.x - base_row;
-            xm[b] = (i < nh && ((xs[rl >> 5] >> (rl & 31)) & 1u)) ? 0xffffffffu : 0u;
+          }
+#pragma unroll
+          for (int b = 0; b < kS2Batch; ++b) {
+            const uint32_t rl = Mr[b] - base_row;
+            xm[b] = (Mr[b] != 0xffffffffu && ((xs[rl >> 5] >> (rl & 31)) & 1u)) ? 0xffffffffu : 0u;
           }
           for (int k0 = 0; k0 < W; k0 += 64) {   // W is even, rows are 8-byte aligned; the loop is warp-uniform
             const int k = k0 + 2 * lane;
@@ -557,60 +603,74 @@ struct Sweeper2 {
                 }
               }
             }
+            // which rows of the batch have candidates, and few enough to probe them one by one: all their probes go out together
+            int best[kS2Batch];
+            bool big[kS2Batch];
+#pragma unroll
+            for (int b = 0; b < kS2Batch; ++b) {
+              best[b] = -1;
+              big[b] = false;
+              if (Mr[b] == 0xffffffffu) { cw[b] = make_uint2(0u, 0u); continue; }
+              if (!__any_sync(kFull, (cw[b].x | cw[b].y) != 0)) continue;
+              if (lane == 0) S.nfail = 1;
+              const int npop = __reduce_add_sync(kFull, (unsigned)(__popc(cw[b].x) + __popc(cw[b].y)));
+              if (npop > kS2ProbeMax) { big[b] = true; cw[b] = make_uint2(0u, 0u); }
+            }
+            // probe this lane's candidates from the highest vertex down (the 64 bits of the lane's two words as one number); the
+            // first true one is this lane's highest.  The loop runs while any row of the batch has an unprobed candidate here;
+            // the probes of all rows of the batch go out together.
+            unsigned long long cand[kS2Batch];
+#pragma unroll
+            for (int b = 0; b < kS2Batch; ++b) cand[b] = ((unsigned long long)cw[b].y << 32) | (unsigned long long)cw[b].x;
+            for (;;) {
+              int w[kS2Batch];
+              bool any = false;
+#pragma unroll
+              for (int b = 0; b < kS2Batch; ++b) {
+                w[b] = -1;
+                if (cand[b]) {
+                  const int bit = 63 - __clzll((long long)cand[b]);
+                  cand[b] &= ~(1ull << bit);
+                  w[b] = k * 32 + bit;
+                  any = true;
+                }
+              }
+              if (!any) break;
+              int ra[kS2Batch], rb[kS2Batch];
+#pragma unroll
+              for (int b = 0; b < kS2Batch; ++b) {
+                ra[b] = rb[b] = kRankDiag;
+                if (w[b] >= 0 && w[b] < n) {
+                  ra[b] = __ldg(&R[(size_t)(cd[b] >> 16) * n + w[b]]);
+                  rb[b] = __ldg(&R[(size_t)(cd[b] & 0xffffu) * n + w[b]]);
+                }
+              }
+#pragma unroll
+              for (int b = 0; b < kS2Batch; ++b)
+                if (w[b] >= 0 && ra[b] < (int)Mr[b] && rb[b] < (int)Mr[b]) {
+                  best[b] = w[b];   // candidates are taken in descending order: the first true one is the highest
+                  cand[b] = 0;
+                }
+            }
 #pragma unroll
             for (int b = 0; b < kS2Batch; ++b) {
               if (Mr[b] == 0xffffffffu) continue;
-              const bool any = __any_sync(kFull, (cw[b].x | cw[b].y) != 0);
-              if (!any) continue;
-              const uint32_t c = cd[b] >> 16, d = cd[b] & 0xffffu;
-              // a later row than the best failure found so far cannot be the event (one lane reads: the test must be warp-uniform)
-              unsigned long long fk_now = 0;
-              if (lane == 0) fk_now = *(volatile unsigned long long*)&S.fail_key;
-              fk_now = __shfl_sync(kFull, fk_now, 0);
-              if ((unsigned long long)Mr[b] * (unsigned long long)n > fk_now) continue;
-              const int npop = __reduce_add_sync(kFull, (unsigned)(__popc(cw[b].x) + __popc(cw[b].y)));
-              int best = -1;
-              if (npop <= kS2ProbeMax) {
-                // probe this lane's candidates from the highest vertex down; the first true one is this lane's highest
-                const int* Rc = R + (size_t)c * n;
-                const int* Rd = R + (size_t)d * n;
-                uint32_t wy = cw[b].y, wx = cw[b].x;
-                while (wy) {
-                  const int bit = 31 - __clz(wy);
-                  wy &= ~(1u << bit);
-                  const int w = (k + 1) * 32 + bit;
-                  if (w < n && __ldg(&Rc[w]) < (int)Mr[b] && __ldg(&Rd[w]) < (int)Mr[b]) { best = w; wy = 0; wx = 0; }
-                }
-                while (wx) {
-                  const int bit = 31 - __clz(wx);
-                  wx &= ~(1u << bit);
-                  const int w = k * 32 + bit;
-                  if (w < n && __ldg(&Rc[w]) < (int)Mr[b] && __ldg(&Rd[w]) < (int)Mr[b]) { best = w; wx = 0; }
-                }
-                best = __reduce_max_sync(kFull, best);
-              } else {
-                best = exact_row(Mr[b], c, d, xm[b]);   // (dense candidate set: the whole lune at once, coalesced)
-              }
-              if (best >= 0 && lane == 0) {
-                const unsigned long long key = (unsigned long long)Mr[b] * (unsigned long long)n + (unsigned long long)(n - 1 - best);
-                const unsigned long long old = atomicMin(&S.fail_key, key);
-                // several 64-word slices of the same row (n > 2048): keep the highest vertex = the smallest key (atomicMin does)
-                (void)old;
-              }
-              if (lane == 0) S.nfail = 1;
+              int bb = __reduce_max_sync(kFull, best[b]);
+              if (big[b]) bb = exact_row(Mr[b], cd[b] >> 16, cd[b] & 0xffffu, xm[b]);   // (dense candidate set: the whole lune at once, coalesced)
+              if (bb >= 0 && lane == 0) atomicMin(&S.fail_key, (Mr[b] - base_row) * (uint32_t)n + (uint32_t)(n - 1 - bb));
             }
           }
         }
-        __syncthreads();
+        csync();
         cyc[3] += clock64() - t0;
         t0 = clock64();
         // ---- decision
         uint32_t evM = 0xffffffffu;
         int evw = -1;
         {
-          const unsigned long long fk = S.fail_key;
-          if (fk != ~0ull) { evM = (uint32_t)(fk / (unsigned long long)n); evw = n - 1 - (int)(fk % (unsigned long long)n); }
-          if (tid == 0 && S.nfail && fk == ~0ull) S.st[S2_SPURIOUS] += 1;   // candidate bits, none of them true: a clean window
+          const uint32_t fk = S.fail_key;
+          if (fk != 0xffffffffu) { evM = base_row + fk / (uint32_t)n; evw = n - 1 - (int)(fk % (uint32_t)n); }
+          if (gtid == 0 && S.nfail && fk == 0xffffffffu) S.st[S2_SPURIOUS] += 1;   // candidate bits, none of them true: a clean window
         }
         if (evM == 0xffffffffu) {   // clean window
           pos = hi;
@@ -623,8 +683,8 @@ struct Sweeper2 {
           const uint32_t vend = min(S.vcount, (uint32_t)P.vcap);
           const uint32_t* vl = vlist(S.vsel);
           uint32_t und = 0;
-          for (uint32_t f = vmark + tid; f < vend; f += kS2Threads) {
-            const uint32_t e = vl[f];
+          for (uint32_t f = vmark + (uint32_t)gtid; f < vend; f += (uint32_t)nthreads) {
+            const uint32_t e = __ldcg(&vl[f]);
             if (e > evM) {
               const uint32_t en = __ldg(&EN[e]);
               atomicXor(&vbits[e >> 5], 1u << (e & 31));
@@ -632,27 +692,28 @@ struct Sweeper2 {
               ++und;
             }
           }
-          if (und) atomicAdd(&S.st[S2_UNDONE], (unsigned long long)und);
+          if (und) { atomicAdd(&S.nundone, und); __threadfence(); }
         }
-        __threadfence();
-        __syncthreads();
+        csync();
         const uint64_t fkey = (uint64_t)evM * (uint64_t)n + (uint64_t)(n - 1 - evw);
         const int owner = hash_find(fkey);
-        if (owner < 0) { pivot = fkey; if (tid == 0) S.st[S2_DEATHS] += 1; cyc[4] += clock64() - t0; break; }   // death
+        if (owner < 0) { pivot = fkey; if (gtid == 0) S.st[S2_DEATHS] += 1; cyc[4] += clock64() - t0; break; }   // death
         {
-          const int64_t vs = P.vstart[(size_t)p * P.cap1 + owner];
-          const int vn = P.vlen[(size_t)p * P.cap1 + owner];
+          const int64_t vs = __ldcg(&P.vstart[(size_t)p * P.cap1 + owner]);
+          const int vn = __ldcg(&P.vlen[(size_t)p * P.cap1 + owner]);
           const uint32_t* ov = P.vpool + (size_t)p * P.vpool_cap + vs;
           if (S.vcount + (uint32_t)vn + 64u > (uint32_t)P.vcap) v_compact();
-          for (int q = tid; q < vn; q += kS2Threads) {
-            const uint32_t re = ov[q];
+          bool any = false;
+          for (int q = gtid; q < vn; q += nthreads) {
+            const uint32_t re = __ldcg(&ov[q]);
             const uint32_t en = __ldg(&EN[re]);
-            toggle_edge(re, en >> 16, en & 0xffffu, true);
+            toggle_edge(re, en >> 16, en & 0xffffu);
+            any = true;
           }
           badd_edges += vn;
-          if (tid == 0) S.st[S2_EVENTS] += 1;
-          __threadfence();
-          __syncthreads();
+          if (gtid == 0) S.st[S2_EVENTS] += 1;
+          if (any) __threadfence();
+          csync();
         }
         pos = evM;   // this row again: its substitution is a no-op now, the handled vertex is even, lower vertices may remain
         if (dense) keep_hi = true;
@@ -666,13 +727,13 @@ struct Sweeper2 {
       const uint32_t nv = S.vcount;
       if (nv > maxv) maxv = nv;
       if (!essential) {
-        if (vpool_used + nv > P.vpool_cap) { if (tid == 0) fail(TDA_ERR_CAPACITY); __syncthreads(); break; }
+        if (vpool_used + nv > P.vpool_cap) { csync(); if (gtid == 0) fail(TDA_ERR_CAPACITY); csync(); break; }
         uint32_t* dst = P.vpool + (size_t)p * P.vpool_cap + vpool_used;
         const uint32_t* list = vlist(S.vsel);
-        for (uint32_t i = tid; i < nv; i += kS2Threads) dst[i] = list[i];
-        if (tid == 0) {
-          P.vstart[(size_t)p * P.cap1 + ci] = vpool_used;
-          P.vlen[(size_t)p * P.cap1 + ci] = (int)nv;
+        for (uint32_t i = (uint32_t)gtid; i < nv; i += (uint32_t)nthreads) __stcg(&dst[i], __ldcg(&list[i]));
+        if (gtid == 0) {
+          __stcg(&P.vstart[(size_t)p * P.cap1 + ci], (int64_t)vpool_used);
+          __stcg(&P.vlen[(size_t)p * P.cap1 + ci], (int)nv);
           hash_insert(pivot, ci);
         }
         vpool_used += nv;
@@ -682,7 +743,7 @@ struct Sweeper2 {
       int Md = -1, wd = -1;
       if (!essential) { Md = (int)(pivot / (uint64_t)n); wd = n - 1 - (int)(pivot % (uint64_t)n); death = SD[Md]; }
       if (essential || death > birth) {
-        if (tid == 0) {
+        if (gtid == 0) {
           out[2 * nrows] = birth; out[2 * nrows + 1] = death;
           if (outs) {
             const uint32_t e = EN[rbirth];
@@ -703,17 +764,16 @@ struct Sweeper2 {
       v_clear();
       cyc[5] += clock64() - t0;
     }
-    __syncthreads();
+    csync();
     if (S.abort_flag) {  // leave the scratch clean for the next problem
-      __syncthreads();
-      for (size_t i = tid; i < (size_t)n * W; i += kS2Threads) X[i] = 0;
-      for (size_t i = tid; i < (size_t)P.vwords; i += kS2Threads) vbits[i] = 0;
+      for (size_t i = (size_t)gtid; i < (size_t)n * W; i += (size_t)nthreads) X[i] = 0;
+      for (size_t i = (size_t)gtid; i < (size_t)P.vwords; i += (size_t)nthreads) vbits[i] = 0;
       for (int i = tid; i < W; i += kS2Threads) { touched[i] = 0; tnew[i] = 0; }
       __threadfence();
-      __syncthreads();
-      if (tid == 0) S.vcount = 0;
+      csync();
+      if (gtid == 0) S.vcount = 0;
     }
-    if (tid == 0) {
+    if (gtid == 0) {
       P.counts[p * 4 + 1] = nrows;
       P.counts[p * 4 + 3] = S.abort_flag;
       st[ST_REDUCED] = (unsigned long long)nb;
@@ -731,24 +791,28 @@ struct Sweeper2 {
       st[ST_S2_DENSE] = S.st[S2_DENSE];
       st[ST_S2_SPURIOUS] = S.st[S2_SPURIOUS];
       st[ST_S2_UNDONE] = S.st[S2_UNDONE];
+      st[ST_SPARE0] = (unsigned long long)cyc_sync;
+      st[ST_SPARE1] = n_sync;
     }
-    __syncthreads();
-    (void)gw;
+    csync();
   }
 };
 
+// grid = clusters * cluster size (launch attribute); one cluster per cloud at a time
 __global__ void __launch_bounds__(kS2Threads, 1) rips_sweep2_kernel(const __grid_constant__ ReduceParams P) {
   __shared__ Sweep2Smem S;
   extern __shared__ __align__(16) uint32_t sweep2_dyn[];
   Sweeper2 sw(P, S, sweep2_dyn);
+  sw.csync();   // every CTA of the cluster is up before anybody touches its shared memory
   for (;;) {
-    if (threadIdx.x == 0) S.problem = atomicAdd(P.work_counter, 1);
-    __syncthreads();
-    const int p = S.problem;
-    __syncthreads();
+    if (sw.gtid == 0) sw.S.problem = atomicAdd(P.work_counter, 1);
+    sw.csync();
+    const int p = sw.S.problem;
+    sw.csync();
     if (p >= P.batch) break;
     sw.run_problem(p);
   }
+  sw.csync();   // no CTA leaves while another may still reach into its shared memory
 }
 
 // parents of the apparent edges: par[M] = (rank(c,apex) | apparent?<<31, rank(d,apex) | apparent?<<31)

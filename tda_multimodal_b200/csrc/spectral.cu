@@ -24,12 +24,13 @@ namespace spectral {
 constexpr int kMaxKrylov = 96;
 constexpr int kLanczosThreads = 512;
 constexpr int kMaxDim = 4;
+constexpr double kFixScale = 1099511627776.0;   // 2^40
 
 // one CTA per cloud
 __global__ void __launch_bounds__(1024) components_kernel(const int* __restrict__ head_g, const int* __restrict__ tail_g,
                                                           const float* __restrict__ weight_g, const float* __restrict__ eps_g, int slots, int n,
-                                                          int* __restrict__ label_g, int* __restrict__ comp_g, float* __restrict__ deg_g,
-                                                          int* __restrict__ ncomp_g, int* __restrict__ csize_g) {
+                                                          int* __restrict__ label_g, unsigned long long* __restrict__ degfix_g, int* __restrict__ comp_g,
+                                                          float* __restrict__ deg_g, int* __restrict__ ncomp_g, int* __restrict__ csize_g) {
   __shared__ int s_scan[1024];
   __shared__ int s_carry;
   const int p = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
@@ -41,10 +42,15 @@ __global__ void __launch_bounds__(1024) components_kernel(const int* __restrict_
   int* comp = comp_g + (size_t)p * n;
   float* deg = deg_g + (size_t)p * n;
   int* csize = csize_g + (size_t)p * n;
-  for (int i = tid; i < n; i += nt) { label[i] = i; deg[i] = 0.f; csize[i] = 0; }
+  // degrees are summed in 2^-40 fixed point: integer atomics are associative, so the sum does not depend on the order the slots
+  // arrive in (float atomics made the whole initialisation irreproducible from run to run)
+  unsigned long long* degfix = degfix_g + (size_t)p * n;
+  for (int i = tid; i < n; i += nt) { label[i] = i; degfix[i] = 0ull; csize[i] = 0; }
   __syncthreads();
   for (int e = tid; e < slots; e += nt)
-    if (eps[e] > 0.f) atomicAdd(&deg[head[e]], weight[e]);
+    if (eps[e] > 0.f) atomicAdd(&degfix[head[e]], (unsigned long long)((double)weight[e] * kFixScale));
+  __syncthreads();
+  for (int i = tid; i < n; i += nt) deg[i] = (float)((double)degfix[i] * (1.0 / kFixScale));
   for (int round = 0; round < 4 * 1024; ++round) {
     int changed = 0;
     for (int e = tid; e < slots; e += nt)
@@ -103,6 +109,7 @@ struct LanczosParams {
   float* evals;    // [batch, maxcomp, kMaxDim]
   int4* entries;   // [batch, slots]  (head, tail, weight / sqrt(deg_h deg_t), -) of the live slots, one segment per component
   int* ent_count;  // [batch]         segment allocation cursor
+  unsigned long long* wfix;   // [batch, maxcomp, n]  sparse matrix-vector product accumulated in 2^-40 fixed point (order independent)
   int maxcomp; int min_size; uint64_t seed;
 };
 
@@ -128,6 +135,7 @@ __global__ void __launch_bounds__(kLanczosThreads) lanczos_kernel(LanczosParams 
   float* Q = P.Q + ((size_t)p * P.maxcomp + c) * (size_t)(kMaxKrylov + 2) * n;
   float* u1 = Q;            // trivial eigenvector, normalised
   float* q0 = Q + n;        // Lanczos vectors q_0 ..
+  unsigned long long* wfix = P.wfix + ((size_t)p * P.maxcomp + c) * (size_t)n;
   const int m = min(kMaxKrylov, nc - 1);
 
   auto block_sum = [&](float v) -> float {
@@ -189,13 +197,16 @@ __global__ void __launch_bounds__(kLanczosThreads) lanczos_kernel(LanczosParams 
   for (int j = 0; j < m; ++j) {
     const float* qj = q0 + (size_t)j * n;
     float* w = q0 + (size_t)(j + 1) * n;  // becomes q_{j+1}
-    for (int i = tid; i < n; i += kLanczosThreads) w[i] = 0.f;
+    for (int i = tid; i < n; i += kLanczosThreads) wfix[i] = 0ull;
     __syncthreads();
 #pragma unroll 4
     for (int k = tid; k < cnt; k += kLanczosThreads) {
       const int4 E = ent[k];
-      atomicAdd(&w[E.x], __int_as_float(E.z) * qj[E.y]);
+      const long long v = __double2ll_rn((double)(__int_as_float(E.z) * qj[E.y]) * kFixScale);
+      atomicAdd(&wfix[E.x], (unsigned long long)v);   // two's complement: signed sums wrap correctly
     }
+    __syncthreads();
+    for (int i = tid; i < n; i += kLanczosThreads) w[i] = (float)((double)(long long)wfix[i] * (1.0 / kFixScale));
     __syncthreads();
     // classical Gram-Schmidt, twice, against u1 and q_0..q_j; the first pass's coefficient on q_j is alpha_j
     for (int pass = 0; pass < 2; ++pass) {
@@ -353,7 +364,7 @@ __global__ void __launch_bounds__(kLanczosThreads) lanczos_kernel(LanczosParams 
 struct Layout {
   int *label, *comp, *ncomp, *csize;
   float *deg, *Q, *evals;
-  int4* entries; int* ent_count;
+  int4* entries; int* ent_count; unsigned long long* wfix;
   size_t total;
 };
 static Layout make_layout(void* ws, int n, int batch, int maxcomp, int slots) {
@@ -368,6 +379,7 @@ static Layout make_layout(void* ws, int n, int batch, int maxcomp, int slots) {
   L.Q = c.take<float>((size_t)batch * (maxcomp > 0 ? maxcomp : 0) * (kMaxKrylov + 2) * n);
   L.entries = c.take<int4>((size_t)batch * (slots > 0 ? slots : 0));
   L.ent_count = c.take<int>(batch);
+  L.wfix = c.take<unsigned long long>((size_t)batch * (maxcomp > 0 ? maxcomp : 0) * n);
   L.total = c.off;
   return L;
 }
@@ -388,9 +400,11 @@ extern "C" int tda_graph_components(const int32_t* head, const int32_t* tail, co
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!head || !tail || !weight || !eps || !comp || !ncomp || !comp_size || !degree || !ws || n <= 0 || batch <= 0)
     return set_error(TDA_ERR_INVALID, "tda_graph_components: bad arguments");
-  if (ws_bytes < sizeof(int) * (size_t)batch * n) return set_error(TDA_ERR_WORKSPACE, "tda_graph_components: workspace too small");
+  if (ws_bytes < 12 * (size_t)batch * n) return set_error(TDA_ERR_WORKSPACE, "tda_graph_components: workspace too small (12 * batch * n bytes)");
+  if ((((uintptr_t)ws) & 7) != 0) return set_error(TDA_ERR_INVALID, "tda_graph_components: workspace must be 8-byte aligned");
   StageScope st(STAGE_SPECTRAL, stream);
-  components_kernel<<<batch, 1024, 0, stream>>>(head, tail, weight, eps, slots, n, (int*)ws, comp, degree, ncomp, comp_size);
+  unsigned long long* degfix = (unsigned long long*)ws;
+  components_kernel<<<batch, 1024, 0, stream>>>(head, tail, weight, eps, slots, n, (int*)(degfix + (size_t)batch * n), degfix, comp, degree, ncomp, comp_size);
   count_launch();
   TDA_LAUNCH_CHECK();
   return TDA_OK;
@@ -409,7 +423,7 @@ extern "C" int tda_spectral_embed(const int32_t* head, const int32_t* tail, cons
   LanczosParams P;
   P.head = head; P.tail = tail; P.weight = weight; P.eps = eps; P.slots = slots; P.n = n; P.dim = dim;
   P.comp = comp; P.deg = degree; P.ncomp = ncomp; P.csize = comp_size;
-  P.Q = L.Q; P.entries = L.entries; P.ent_count = L.ent_count; P.out = Y; P.evals = evals ? evals : L.evals; P.maxcomp = maxcomp; P.min_size = min_size; P.seed = seed;
+  P.Q = L.Q; P.entries = L.entries; P.ent_count = L.ent_count; P.wfix = L.wfix; P.out = Y; P.evals = evals ? evals : L.evals; P.maxcomp = maxcomp; P.min_size = min_size; P.seed = seed;
   dim3 grid(maxcomp, batch);
   StageScope st(STAGE_SPECTRAL, stream);
   lanczos_kernel<<<grid, kLanczosThreads, 0, stream>>>(P);

@@ -810,10 +810,11 @@ __global__ void __launch_bounds__(kAdjThreads) sgd_adj_kernel(const int* __restr
   if (tid == 0) adj_maxdeg[p] = s_maxdeg;
 }
 
-constexpr int kClThreads = 512;
+constexpr int kClThreads = 1024;
 constexpr int kClWarps = kClThreads / 32;
-constexpr int kClQueue = 512;     // fired entries a warp queues before it works through them (a tile of 32 vertices usually fires ~150)
+constexpr int kClQueue = 256;     // fired entries a warp queues before it works through them (a tile of 32 vertices usually fires ~150)
 constexpr int kClMaxCluster = 8;
+constexpr int kClTile = 16;       // vertices per warp task (more, smaller tasks: the kernel is bound by the latency of one warp's chain)
 
 struct SgdForce {
   float a, b, gamma, nsr;
@@ -886,7 +887,7 @@ __global__ void __launch_bounds__(kClThreads, 1) sgd_cluster_kernel(float* __res
   const int nown_max = (n + (int)C - 1) / (int)C + 1;
   float4* Yb = reinterpret_cast<float4*>(s_raw);
   float4* acc_all = Yb + 2 * (size_t)n;
-  uint32_t* queue_all = reinterpret_cast<uint32_t*>(acc_all + kClWarps * 32);
+  uint32_t* queue_all = reinterpret_cast<uint32_t*>(acc_all + kClWarps * kClTile);
   int* soff = reinterpret_cast<int*>(queue_all + kClWarps * kClQueue);
   uint2* sent = reinterpret_cast<uint2*>(soff + ((nown_max + 2) & ~1));
   const int* goff = adj_off + (size_t)p * (n + 1);
@@ -900,7 +901,7 @@ __global__ void __launch_bounds__(kClThreads, 1) sgd_cluster_kernel(float* __res
   if (ent_in_smem)
     for (int i = tid; i < ne; i += kClThreads) sent[i] = gent[e0 + i];
   const uint2* ent = ent_in_smem ? sent : gent + e0;   // entry i of this CTA's slice
-  float4* acc = acc_all + warp * 32;
+  float4* acc = acc_all + warp * kClTile;
   uint32_t* queue = queue_all + warp * kClQueue;
   uint32_t remote[kClMaxCluster];
 #pragma unroll
@@ -912,11 +913,11 @@ __global__ void __launch_bounds__(kClThreads, 1) sgd_cluster_kernel(float* __res
     const float4* src = Yb + (size_t)(ep & 1) * n;
     const uint32_t dst_off = (uint32_t)(((ep + 1) & 1) * n) * 16u;
     const uint32_t key_ep = hash32((uint32_t)seed ^ (uint32_t)(seed >> 32) ^ hash32((uint32_t)p * 0x27d4eb2fu + (uint32_t)ep));
-    // tiles of 32 consecutive owned vertices, dealt round robin to the warps
-    for (int tv = warp * 32; tv < nown; tv += kClWarps * 32) {
-      const int cnt = min(32, nown - tv);
+    // tiles of kClTile consecutive owned vertices, dealt round robin to the warps
+    for (int tv = warp * kClTile; tv < nown; tv += kClWarps * kClTile) {
+      const int cnt = min(kClTile, nown - tv);
       const int ebase = soff[tv] - e0;
-      acc[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lane < kClTile) acc[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
       __syncwarp();
       int qn = 0;
       // phase 2 (called whenever the queue may overflow, and at the end): full warps over the queued (= fired) entries; the
@@ -1210,7 +1211,7 @@ extern "C" int tda_umap_sgd(float* Y, const float* Y_other, const int32_t* head,
     int C = (int)option("sgd_cluster");
     if (C != 1 && C != 2 && C != 4 && C != 8) C = 4;
     const int nown_max = (n + C - 1) / C + 1;
-    const size_t base = sizeof(float4) * 2 * (size_t)n + sizeof(float4) * kClWarps * 32 + sizeof(uint32_t) * kClWarps * kClQueue +
+    const size_t base = sizeof(float4) * 2 * (size_t)n + sizeof(float4) * kClWarps * kClTile + sizeof(uint32_t) * kClWarps * kClQueue +
                         sizeof(int) * (size_t)((nown_max + 2) & ~1);
     const size_t smem_max = (size_t)224 * 1024;
     if (base + 1024 <= smem_max) {

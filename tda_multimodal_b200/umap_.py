@@ -133,11 +133,11 @@ def spectral_init(X, head, tail, weight, eps, n, dim, seed, metric):
     ncomp = torch.empty((B,), dtype=torch.int32, device=dev)
     csize = torch.empty((B, n), dtype=torch.int32, device=dev)
     deg = torch.empty((B, n), dtype=torch.float32, device=dev)
-    ws0 = torch.empty(4 * B * n, dtype=torch.uint8, device=dev)
+    ws0 = torch.empty(12 * B * n, dtype=torch.uint8, device=dev)
     Y = torch.zeros((B, n, dim), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         _lib.check(L.tda_graph_components(_lib.ptr(head), _lib.ptr(tail), _lib.ptr(weight), _lib.ptr(eps), slots, n, B, _lib.ptr(comp),
-                                          _lib.ptr(ncomp), _lib.ptr(csize), _lib.ptr(deg), _lib.ptr(ws0), 4 * B * n, _lib.stream_ptr()))
+                                          _lib.ptr(ncomp), _lib.ptr(csize), _lib.ptr(deg), _lib.ptr(ws0), 12 * B * n, _lib.stream_ptr()))
         ncomp_h = ncomp.cpu().numpy()
         maxcomp = int(ncomp_h.max())
         min_size = 1 if maxcomp == 1 else max(2 * dim, dim + 2)

@@ -97,3 +97,12 @@ def test_sweep2_batch_of_bench_size_clouds_equals_sweep(tda_option):
     for a, b in zip(out["sweep2"], out["sweep"]):
         assert np.array_equal(a["dgms"][1], b["dgms"][1]) and np.array_equal(a["simplices"][1], b["simplices"][1])
         assert np.array_equal(a["dgms"][0], b["dgms"][0])
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 8])
+@pytest.mark.parametrize("gen,n,seed", [(torus3d, 500, 31), (blobs3d, 1200, 32)])
+def test_sweep2_cluster_sizes(tda_option, cluster, gen, n, seed):
+    """sweep2 deals every pass over a window to the warps of a thread-block cluster (default 4 CTAs per cloud); any cluster size
+    must give the oracle's pairs."""
+    got = _check(gen(n, np.random.default_rng(seed)), "sweep2", tda_option, rips_cluster=cluster, rips_w0=256, rips_dense_min=16)
+    assert got["stats"]["windows"] > 0

@@ -145,9 +145,9 @@ def test_components_and_spectral_vs_scipy(torch_cuda):
     ncomp = torch.empty((1,), dtype=torch.int32, device="cuda")
     csize = torch.empty((1, n), dtype=torch.int32, device="cuda")
     deg = torch.empty((1, n), dtype=torch.float32, device="cuda")
-    ws0 = torch.empty(4 * n, dtype=torch.uint8, device="cuda")
+    ws0 = torch.empty(12 * n, dtype=torch.uint8, device="cuda")
     _lib.check(L.tda_graph_components(_lib.ptr(head), _lib.ptr(tail), _lib.ptr(weight), _lib.ptr(eps), head.shape[1], n, 1, _lib.ptr(comp),
-                                      _lib.ptr(ncomp), _lib.ptr(csize), _lib.ptr(deg), _lib.ptr(ws0), 4 * n, _lib.stream_ptr()))
+                                      _lib.ptr(ncomp), _lib.ptr(csize), _lib.ptr(deg), _lib.ptr(ws0), 12 * n, _lib.stream_ptr()))
     h, t, w, e = (a[0].cpu().numpy() for a in (head, tail, weight, eps))
     keep = e > 0
     G = scipy.sparse.coo_matrix((w[keep].astype(np.float64), (h[keep], t[keep])), shape=(n, n)).tocsr()
