@@ -39,6 +39,7 @@ void tda_launch_count_reset(void);
  *                     resolver warp, 2 row sweep substitute-then-verify per 512-row chunk, 3 key bitset (any n)
  *   rips_w0 (1024), rips_wsparse (8192), rips_wmax (32768), rips_dense_min (64), rips_dense_div (8): sweep2 window schedule
  *   rips_cluster (4): CTAs of the thread-block cluster that reduces one cloud (sweep2)
+ *   rips_warp_engine (1): sweep2 reduces every column by a single warp first (speculatively, committed in ripser's order); 0: windows only
  *   sgd_mode (0): 0 deterministic SGD (thread-block cluster per cloud for fit, warp per point for transform; bit-reproducible
  *                 for a given seed), 3 per-epoch kernels with float atomics (used anyway for n > 8192 or n_components != 3)
  *   sgd_cluster (4): CTAs per cloud of the deterministic fit kernel;  sweep_exclusive (0), knn_loads (8), debug_sync (0),
@@ -190,9 +191,9 @@ int tda_rips_h2(const void* ws1, int n, int batch, int cap1, size_t pool_bytes1,
 /* device statistics of the last tda_rips call on this workspace: [batch, TDA_RIPS_STATS] int64.  For the default reducer (sweep2):
  *  0 columns (non-MST edges <= thresh), 1 apparent pairs, 2 reduced columns, 3 column additions (flips kept + reduced columns
  *  added), 4 rows substituted, 5 non-apparent pivots (events + deaths), 6 windows, 7 largest |V|, 8..13 SM cycles of CTA
- *  thread 0 in: substitution round 1, later rounds, apply + heavy lists, verification, decision + events, Pm moves + column
- *  finalisation; 14 edges added through reduced columns, 15 heavy rows verified, 16 substitution rounds after the first,
- *  17 rows handled in those rounds, 18 rows of Pm moved, 19 columns that went dense, 20 spurious stops, 21 flips undone,
+ *  thread 0 in: the warp stage (every column by one warp), the commit loop, and in the windows of the cluster engine: substitution,
+ *  verification, decision + events, Pm moves + column finalisation; 14 edges added through reduced columns, 15 heavy rows verified, 16 substitution rounds after the first,
+ *  17 rows handled in those rounds, 18 rows of Pm moved, 19 columns that went dense, 20 columns the commit loop resumed (tentative pivot owned), 21 columns handed to the cluster engine,
  *  22 SM cycles thread 0 spent in cluster barriers (part of 8..13), 23 number of those barriers.
  *  (reducers 1-3 fill 0..15 with their own counters: rows streamed, pivots, restarts, ...) */
 #define TDA_RIPS_STATS 24

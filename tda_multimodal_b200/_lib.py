@@ -58,7 +58,7 @@ _ENV_OPTIONS = {
     "TDA_RIPS_REDUCER": ("rips_reducer", lambda v: _REDUCERS[v]),
     "TDA_RIPS_W0": ("rips_w0", int), "TDA_RIPS_WSPARSE": ("rips_wsparse", int), "TDA_RIPS_WMAX": ("rips_wmax", int),
     "TDA_RIPS_DENSE_MIN": ("rips_dense_min", int), "TDA_RIPS_DENSE_DIV": ("rips_dense_div", int),
-    "TDA_RIPS_CLUSTER": ("rips_cluster", int), "TDA_SWEEP_EXCLUSIVE": ("sweep_exclusive", int),
+    "TDA_RIPS_CLUSTER": ("rips_cluster", int), "TDA_RIPS_WARP_ENGINE": ("rips_warp_engine", int), "TDA_SWEEP_EXCLUSIVE": ("sweep_exclusive", int),
     "TDA_SGD_MODE": ("sgd_mode", int), "TDA_SGD_CLUSTER": ("sgd_cluster", int),
     "TDA_KNN_LOADS": ("knn_loads", int), "TDA_DEBUG_SYNC": ("debug_sync", lambda v: 1), "TDA_H2_STATS": ("h2_stats", lambda v: 1),
 }

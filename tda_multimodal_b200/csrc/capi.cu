@@ -72,6 +72,7 @@ static OptionDef g_options[] = {
     {"rips_wmax", 32768},      // sweep2: largest window in dense mode (<= 65472)
     {"rips_dense_min", 64},    // sweep2: a window with >= max(dense_min, rows / dense_div) heavy rows switches the column to dense mode
     {"rips_dense_div", 8},
+    {"rips_warp_engine", 1},   // sweep2: short columns are reduced by single warps first, speculatively, and committed in order
     {"rips_cluster", 4},       // sweep2: CTAs per cloud (thread-block cluster: 1, 2, 4 or 8; halved while batch * cluster > 2 * SMs)
     {"sweep_exclusive", 0},    // reducers 1/2: ask for the whole shared memory of the SM
     {"sgd_mode", 0},           // 0 deterministic kernels (cluster per cloud for fit, warp per point for transform), 3 per-epoch kernels with float atomics

@@ -39,6 +39,12 @@ constexpr int kS2Batch = 4;            // heavy rows a warp verifies at once
 constexpr int kS2Unroll = 4;           // 32-row groups a warp keeps in flight in the first substitution round
 constexpr int kS2ProbeMax = 256;       // candidate bits of a row up to which they are probed one by one (more: the whole lune at once)
 enum { TDA_ERR_INTERNAL_S2 = -6 };
+// warp engine (short, sparse columns: one warp per column, V in the lanes)
+constexpr int kWcMaxV = 32;            // edges of V a warp holds (one per lane); more -> the column goes to the cluster engine
+constexpr int kWcRec = 40;             // words of a column record: status, pos, key lo, key hi, nv, -, -, -, 32 edge ranks
+constexpr uint32_t kWcMaxRows = 1u << 18;   // rows a warp sweeps before it hands the column over
+constexpr uint32_t kWcMaxHeavy = 2048;      // heavy rows a warp handles before it hands the column over
+enum { WC_NONE = 0, WC_DEATH = 1, WC_ESSENTIAL = 2, WC_BIG = 3 };
 
 struct Sweep2Smem {
   uint32_t vcount, vcount2, vsel;
@@ -46,6 +52,13 @@ struct Sweep2Smem {
   uint32_t npend[3];
   uint32_t nheavy, nfail, newtouch, nundone;
   uint32_t fail_key;           // smallest failing key of the window: (row - base_row) * n + (n - 1 - vertex), 32 bits (< 65536 * n)
+  // column bookkeeping shared by the warp engine (stage A / commit loop) and the cluster engine
+  int nrows;                   // H1 rows written so far
+  int next_col;                // stage A: next column to hand to a warp;  commit loop: next column to commit
+  int big_ci;                  // commit loop -> cluster engine: the column to reduce with windows (-1: all columns are done)
+  long long vpool_used;
+  unsigned long long maxv, badd;
+  unsigned long long wc_cols, wc_resumed, wc_big, wc_rows, wc_heavy, wc_scans;   // warp engine counters
   unsigned long long st[16];
 };
 enum { S2_WINDOWS = 0, S2_ROUNDS, S2_HEAVY, S2_FLIPS, S2_UNDONE, S2_EVENTS, S2_SPURIOUS, S2_SUBST, S2_LATE, S2_PM, S2_DENSE, S2_EXACT, S2_DEATHS };
@@ -76,6 +89,8 @@ struct Sweeper2 {
   const int* R; const uint32_t* EN; const uint2* EA; const uint2* PAR; int T; int n; int W;
   uint32_t *X, *Pm, *vbits, *vl0;
   uint2 *pend_g, *heavy_g;
+  uint32_t* wcd;               // this warp's vertex bitmap (warp engine), W words of this CTA's shared memory
+  uint32_t* recs;              // tentative column records of this cluster's cloud: [cap1][kWcRec] words (global)
   uint32_t p_pos; bool p_valid;
   uint64_t* hkeys; int* hvals;
   long long cyc_sync; unsigned long long n_sync;   // (diagnostics) cycles this thread spent in cluster barriers, and their number
@@ -95,6 +110,10 @@ struct Sweeper2 {
     done = xo + nw;
     pend_s = reinterpret_cast<uint2*>(done + nw + ((2 * W + 3 * nw) & 1));   // 8-byte aligned
     heavy_s = pend_s + 2 * kS2ListSmem;
+    {
+      uint2* pend_local = reinterpret_cast<uint2*>(dyn + 2 * W + 3 * nw + ((2 * W + 3 * nw) & 1));
+      wcd = reinterpret_cast<uint32_t*>(pend_local + 3 * kS2ListSmem) + (size_t)warp * W;
+    }
     X = P.xmat + (size_t)slot * (size_t)n * W;
     Pm = P.pmat + (size_t)slot * (size_t)n * W;
     p_pos = 0; p_valid = false;
@@ -103,10 +122,11 @@ struct Sweeper2 {
     vl0 = P.vlist + (size_t)slot * 2 * P.vcap;
     pend_g = P.s2_pend + (size_t)slot * 2 * (size_t)(P.s2_wmax + 64);
     heavy_g = P.s2_heavy + (size_t)slot * (size_t)(P.s2_wmax + 64);
+    recs = P.s2_rec + (size_t)slot * (size_t)P.cap1 * kWcRec;
   }
   static __host__ __device__ size_t dyn_bytes(int W, int wmax) {
     const int nw = wmax / 32 + 4;
-    return sizeof(uint32_t) * (size_t)(2 * W + 3 * nw + 2) + sizeof(uint2) * (size_t)(3 * kS2ListSmem);
+    return sizeof(uint32_t) * (size_t)(2 * W + 3 * nw + 2) + sizeof(uint2) * (size_t)(3 * kS2ListSmem) + sizeof(uint32_t) * (size_t)kS2Warps * W;
   }
   // barrier over the cluster (release / acquire: shared-memory and global writes of every CTA are visible afterwards)
   __device__ __forceinline__ void csync() {
@@ -343,52 +363,243 @@ struct Sweeper2 {
     if (flag) *ref(base + __popc(bal & ((1u << lane) - 1))) = ent;
   }
 
-  __device__ __forceinline__ void run_problem(int p) {
-    R = P.rank + (size_t)p * n * n;
-    EN = P.ends + (size_t)p * P.E;
-    EA = P.ea + (size_t)p * P.E;
-    PAR = P.par + (size_t)p * P.E;
-    T = P.T[p];
-    hkeys = P.hkeys + (size_t)p * P.hcap;
-    hvals = P.hvals + (size_t)p * P.hcap;
+  // =================================================================================================================
+  // Warp engine: one warp reduces one column whose V stays small (<= 32 edges, one per lane: rank `vr`, endpoints `ven`).
+  // The rows are taken strictly in order, 32 at a time; a row matters only if one of its endpoints is an endpoint of an edge of V
+  // ("heavy").  For a heavy apparent row M=(c,d): substitution x_M = [pa in V] ^ [pb in V] (toggle M in V if it differs), then
+  // the row is verified at once: candidates w with x_cw ^ x_dw ^ x_M = 1 come from the edges of V at c and d (x_M = 0: probed
+  // one by one) or are the whole lune minus those (x_M = 1: one scan of the two rank rows).  The first failing (M, w) ends the
+  // sweep: a tentative death (stage A, no look-up) or, with `owned` look-ups (commit loop), the owner's V is added and the row
+  // verified again.  Columns that outgrow the warp (V, rows, heavy rows) are handed to the cluster engine with their state.
+  struct WcState { uint32_t vr, ven; int nv; };
+  __device__ __forceinline__ bool wc_in(const WcState& v, uint32_t r) const { return __ballot_sync(kFull, lane < v.nv && v.vr == r) != 0; }
+  __device__ __forceinline__ bool wc_toggle(WcState& v, uint32_t r, uint32_t en) const {
+    const unsigned hit = __ballot_sync(kFull, lane < v.nv && v.vr == r);
+    if (hit) {   // remove: the last edge moves into its lane
+      const int l = __ffs(hit) - 1;
+      const uint32_t lr = __shfl_sync(kFull, v.vr, v.nv - 1), le = __shfl_sync(kFull, v.ven, v.nv - 1);
+      if (lane == l) { v.vr = lr; v.ven = le; }
+      --v.nv;
+      return true;
+    }
+    if (v.nv >= kWcMaxV) return false;
+    if (lane == v.nv) { v.vr = r; v.ven = en; }
+    ++v.nv;
+    return true;
+  }
+  // this lane's edge of V as seen from row (c,d) (not the row's own edge `M`): the vertex w with (c,w) or (d,w) in V, or -1
+  __device__ __forceinline__ int wc_candidate(const WcState& v, uint32_t c, uint32_t d, uint32_t M) const {
+    if (lane >= v.nv || v.vr == M) return -1;
+    const uint32_t a = v.ven >> 16, b = v.ven & 0xffffu;
+    if (a == c) return (int)b;
+    if (b == c) return (int)a;
+    if (a == d) return (int)b;
+    if (b == d) return (int)a;
+    return -1;
+  }
+  // highest failing vertex of row M=(c,d) for the column V, or -1
+  __device__ __forceinline__ int wc_verify(const WcState& v, uint32_t M, uint32_t c, uint32_t d, bool xm, uint32_t& scans) const {
+    const int w = wc_candidate(v, c, d, M);
+    if (!xm) {
+      // x_M = 0: a vertex fails iff exactly one of (c,w), (d,w) is in V (a vertex seen from both sides cancels) and w is in the lune
+      const unsigned same = __match_any_sync(kFull, w >= 0 ? (uint32_t)w : (0x80000000u | (uint32_t)lane));
+      const bool odd = w >= 0 && (__popc(same) & 1);
+      int best = -1;
+      if (odd && __ldg(&R[(size_t)c * n + w]) < (int)M && __ldg(&R[(size_t)d * n + w]) < (int)M) best = w;
+      return __reduce_max_sync(kFull, best);
+    }
+    // x_M = 1: every lune vertex must have exactly one of its two edges in V: D = those vertices (parity by XOR), fail = lune & ~D
+    ++scans;
+    for (int k = lane; k < W; k += 32) wcd[k] = 0u;
+    __syncwarp();
+    if (w >= 0) atomicXor(&wcd[w >> 5], 1u << (w & 31));
+    __syncwarp();
+    const int* Rc = R + (size_t)c * n;
+    const int* Rd = R + (size_t)d * n;
+    int best = -1;
+    for (int k0 = 0; k0 < W; k0 += 32) {
+      const int kend = min(32, W - k0);
+      uint32_t lmine = 0;
+      for (int kk0 = 0; kk0 < kend; kk0 += 16) {
+        int ra[16], rb[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int ww = (k0 + kk0 + u) * 32 + lane;
+          const bool ok = (kk0 + u) < kend && ww < n;
+          ra[u] = ok ? __ldg(&Rc[ww]) : kRankDiag;
+          rb[u] = ok ? __ldg(&Rd[ww]) : kRankDiag;
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const unsigned word = __ballot_sync(kFull, ra[u] < (int)M && rb[u] < (int)M);
+          if (lane == kk0 + u) lmine = word;
+        }
+      }
+      const int k = k0 + lane;
+      const uint32_t f = k < W ? (lmine & ~wcd[k]) : 0u;
+      if (f) best = k * 32 + 31 - __clz(f);
+    }
+    __syncwarp();
+    return __reduce_max_sync(kFull, best);
+  }
+  // the sweep.  In: V, first row `pos`.  Out: status, V (final, or the state to hand over), pos / key.
+  __device__ __forceinline__ int wc_sweep(WcState& v, uint32_t& pos, unsigned long long& key, bool owned, int p) {
+    uint32_t nheavy = 0, nrows = 0, nscan = 0;
+    int status = WC_NONE;
+    while (status == WC_NONE) {
+      if (pos >= (uint32_t)T) { status = WC_ESSENTIAL; break; }
+      if (nrows > kWcMaxRows || nheavy > kWcMaxHeavy) { status = WC_BIG; break; }
+      const uint32_t base = pos & ~31u;
+      const uint32_t row = base + lane;
+      const bool inwin = row >= pos && row < (uint32_t)T;
+      uint2 ea = make_uint2(0u, 0xffffffffu), par = make_uint2(0u, 0u);
+      if (inwin) { ea = __ldg(&EA[row]); par = __ldg(&PAR[row]); }
+      nrows += 32;
+      const bool app = (int)ea.y >= 0;
+      const uint32_t c = ea.x >> 16, d = ea.x & 0xffffu;
+      uint32_t from = 0;   // rows of this group below `from` are done
+      for (;;) {
+        // heavy rows of the group at or above `from` under the current V
+        bool h = false;
+        for (int e = 0; e < v.nv; ++e) {
+          const uint32_t q = __shfl_sync(kFull, v.ven, e);
+          const uint32_t a = q >> 16, b = q & 0xffffu;
+          h |= (c == a) | (c == b) | (d == a) | (d == b);
+        }
+        const unsigned hb = __ballot_sync(kFull, h && app && lane >= from);
+        if (!hb) break;
+        const int sl = __ffs(hb) - 1;
+        from = (uint32_t)sl + 1;
+        ++nheavy;
+        const uint32_t M = base + (uint32_t)sl;
+        const uint32_t en = __shfl_sync(kFull, ea.x, sl);
+        const uint32_t pa = __shfl_sync(kFull, par.x, sl) & 0x7fffffffu, pb = __shfl_sync(kFull, par.y, sl) & 0x7fffffffu;
+        const uint32_t cc = en >> 16, dd = en & 0xffffu;
+        // substitution (the parents are below M: everything below M is final)
+        const bool want = wc_in(v, pa) != wc_in(v, pb);
+        bool cur = wc_in(v, M);
+        if (want != cur) {
+          if (!wc_toggle(v, M, en)) { pos = M; status = WC_BIG; break; }
+          cur = want;
+        }
+        // verification of the row; an owned pivot adds the owner's V and the row is verified again
+        for (;;) {
+          const int w = wc_verify(v, M, cc, dd, cur, nscan);
+          if (w < 0) break;
+          const unsigned long long k = (unsigned long long)M * (unsigned long long)n + (unsigned long long)(n - 1 - w);
+          int owner = -1;
+          if (owned) owner = hash_find(k);
+          if (owner < 0) { key = k; pos = M; status = WC_DEATH; break; }
+          const long long vs = __ldcg(&P.vstart[(size_t)p * P.cap1 + owner]);
+          const int vn = __ldcg(&P.vlen[(size_t)p * P.cap1 + owner]);
+          const uint32_t* ov = P.vpool + (size_t)p * P.vpool_cap + vs;
+          const WcState saved = v;
+          bool fits = vn <= 2 * kWcMaxV;
+          for (int q = 0; q < vn && fits; ++q) {
+            const uint32_t re = __ldcg(&ov[q]);
+            fits = wc_toggle(v, re, __ldg(&EN[re]));
+          }
+          if (!fits) { v = saved; pos = M; status = WC_BIG; break; }   // the cluster engine meets the same pivot again and adds it itself
+          cur = wc_in(v, M);
+        }
+        if (status != WC_NONE) break;
+      }
+      if (status == WC_NONE) pos = base + 32u;
+    }
+    if (lane == 0) {
+      atomicAdd(&S.wc_rows, (unsigned long long)nrows); atomicAdd(&S.wc_heavy, (unsigned long long)nheavy); atomicAdd(&S.wc_scans, (unsigned long long)nscan);
+    }
+    return status;
+  }
+  __device__ __forceinline__ void wc_store(int ci, int status, const WcState& v, uint32_t pos, unsigned long long key) {
+    uint32_t* r = recs + (size_t)ci * kWcRec;
+    if (lane == 0) {
+      __stcg(&r[0], (uint32_t)status); __stcg(&r[1], pos); __stcg(&r[2], (uint32_t)key); __stcg(&r[3], (uint32_t)(key >> 32)); __stcg(&r[4], (uint32_t)v.nv);
+    }
+    if (lane < v.nv) __stcg(&r[8 + lane], v.vr);
+  }
+  __device__ __forceinline__ int wc_load(int ci, WcState& v, uint32_t& pos, unsigned long long& key) const {
+    const uint32_t* r = recs + (size_t)ci * kWcRec;
+    const int status = (int)__ldcg(&r[0]);
+    pos = __ldcg(&r[1]);
+    key = (unsigned long long)__ldcg(&r[2]) | ((unsigned long long)__ldcg(&r[3]) << 32);
+    v.nv = (int)__ldcg(&r[4]);
+    v.vr = lane < v.nv ? __ldcg(&r[8 + lane]) : 0xffffffffu;
+    v.ven = lane < v.nv ? __ldg(&EN[v.vr]) : 0u;
+    return status;
+  }
+  // one H1 row (birth, death) of column ci; zero-persistence pairs are dropped (as ripser does).  One thread.
+  __device__ __forceinline__ void emit_pair(int p, int rbirth, bool essential, uint64_t pivot) {
     const float* SD = P.sdist + (size_t)p * P.E;
-    int* bl = P.blist + (size_t)p * P.cap1;
-    const int nb = P.bcount[p];
-    unsigned long long* st = P.stats + (size_t)p * ST_N;
-    if (nb > P.cap1) {
-      if (gtid == 0) { P.counts[p * 4 + 3] = TDA_ERR_CAPACITY; P.counts[p * 4 + 1] = 0; }
-      return;
-    }
-    p_valid = false;   // Pm belongs to the previous cloud's rank matrix
-    sort_blist(bl, nb);
-    for (int i = gtid; i < P.hcap; i += nthreads) __stcg(&hkeys[i], kEmpty);
-    for (int i = tid; i < W; i += kS2Threads) { touched[i] = 0; tnew[i] = 0; }
-    if (gtid == 0) {
-      S.vcount = 0; S.vsel = 0; S.abort_flag = 0; S.nundone = 0;
-      for (int q = 0; q < 16; ++q) S.st[q] = 0;
-    }
-    __threadfence();
-    csync();
-    int nrows = 0;
-    int64_t vpool_used = 0;
-    unsigned long long maxv = 0, badd_edges = 0;
-    long long cyc[6] = {0, 0, 0, 0, 0, 0};
-    long long t0;
-    cyc_sync = 0; n_sync = 0;
     float* out = P.h1_pairs + (size_t)p * P.cap1 * 2;
     int64_t* outs = P.h1_simplex ? P.h1_simplex + (size_t)p * P.cap1 * 2 : nullptr;
-    const uint32_t w0 = (uint32_t)P.s2_w0, wsparse = (uint32_t)P.s2_wsparse, wmax = (uint32_t)P.s2_wmax;
-
-    for (int ci = nb - 1; ci >= 0; --ci) {
-      const int rbirth = __ldcg(&bl[ci]);
-      {  // V = {birth edge}
-        const uint32_t en = __ldg(&EN[rbirth]);
-        if (gtid == 0) { toggle_edge((uint32_t)rbirth, en >> 16, en & 0xffffu); __threadfence(); }
-        csync();
+    const float birth = SD[rbirth];
+    float death = INFINITY;
+    int Md = -1, wd = -1;
+    if (!essential) { Md = (int)(pivot / (uint64_t)n); wd = n - 1 - (int)(pivot % (uint64_t)n); death = SD[Md]; }
+    if (essential || death > birth) {
+      const int nrows = S.nrows;
+      out[2 * nrows] = birth; out[2 * nrows + 1] = death;
+      if (outs) {
+        const uint32_t e = EN[rbirth];
+        outs[2 * nrows] = edge_index((int)(e >> 16), (int)(e & 0xffffu));
+        if (essential) outs[2 * nrows + 1] = -1;
+        else {
+          const uint32_t em = EN[Md];
+          int x = (int)(em >> 16), y = (int)(em & 0xffffu), z = wd, t;
+          if (x < y) { t = x; x = y; y = t; }
+          if (y < z) { t = y; y = z; z = t; }
+          if (x < y) { t = x; x = y; y = t; }
+          outs[2 * nrows + 1] = (int64_t)x * (x - 1) * (x - 2) / 6 + (int64_t)y * (y - 1) / 2 + z;
+        }
       }
+      S.nrows = nrows + 1;
+    }
+  }
+  // a finished warp column becomes a reduced column: V into the pool, pivot into the hash map, its pair written.  One warp.
+  __device__ __forceinline__ bool wc_commit(int p, int ci, int rbirth, int status, const WcState& v, unsigned long long key) {
+    if (status == WC_DEATH) {
+      const long long used = S.vpool_used;
+      if (used + v.nv > P.vpool_cap) { if (lane == 0) fail(TDA_ERR_CAPACITY); return false; }
+      uint32_t* dst = P.vpool + (size_t)p * P.vpool_cap + used;
+      if (lane < v.nv) __stcg(&dst[lane], v.vr);
+      if (lane == 0) {
+        __stcg(&P.vstart[(size_t)p * P.cap1 + ci], (int64_t)used);
+        __stcg(&P.vlen[(size_t)p * P.cap1 + ci], v.nv);
+        S.vpool_used = used + v.nv;
+        if ((unsigned long long)v.nv > S.maxv) S.maxv = (unsigned long long)v.nv;
+      }
+      __syncwarp();
+      __threadfence();
+      if (lane == 0) hash_insert(key, ci);
+    }
+    if (lane == 0) emit_pair(p, rbirth, status == WC_ESSENTIAL, key);
+    __syncwarp();
+    return true;
+  }
+
+  // =================================================================================================================
+  // Cluster engine: column ci with windows (all threads of the cluster).  The column starts from the state the warp engine left:
+  // `nv0` edges in the column's record, first row pos0 (nv0 = 1, the birth edge, pos0 = birth + 1 for a fresh column).
+  __device__ __forceinline__ void cluster_column(int p, int ci, int rbirth, uint32_t pos0, long long* cyc, unsigned long long& badd_edges) {
+    const uint32_t w0 = (uint32_t)P.s2_w0, wsparse = (uint32_t)P.s2_wsparse, wmax = (uint32_t)P.s2_wmax;
+    const int nb = P.bcount[p];
+    long long t0;
+    {  // V = the recorded state
+      const uint32_t* r = recs + (size_t)ci * kWcRec;
+      const int nv0 = (int)__ldcg(&r[4]);
+      if (gtid < nv0) {
+        const uint32_t e = __ldcg(&r[8 + gtid]);
+        const uint32_t en = __ldg(&EN[e]);
+        toggle_edge(e, en >> 16, en & 0xffffu);
+        __threadfence();
+      }
+      csync();
+    }
+    {
       bool essential = false, dense = false, keep_hi = false;
       uint64_t pivot = 0;
-      uint32_t pos = (uint32_t)rbirth + 1, win = w0, hi = 0;
+      uint32_t pos = pos0, win = w0, hi = 0;
       unsigned long long guard = 0;
       const unsigned long long guard_max = 1024ull + 4ull * ((unsigned long long)T / max(1u, w0) + 1ull) + 64ull * (unsigned long long)nb;
       for (;;) {
@@ -470,7 +681,7 @@ struct Sweeper2 {
           }
         }
         csync();
-        cyc[0] += clock64() - t0;
+        cyc[2] += clock64() - t0;
         t0 = clock64();
         // ---- later rounds (CTA 0 alone): rows that wait for rows of the window; shared memory only (+ the spill part of the list)
         if (crank == 0 && S.npend[0] != 0) {
@@ -511,7 +722,7 @@ struct Sweeper2 {
         }
         csync();
         if (S.abort_flag) break;
-        cyc[1] += clock64() - t0;
+        cyc[2] += clock64() - t0;
         t0 = clock64();
         // ---- apply: the rows whose x changed flip in X / the V list; the global x words are rewritten (one owner per word)
         {
@@ -612,7 +823,11 @@ struct Sweeper2 {
               big[b] = false;
               if (Mr[b] == 0xffffffffu) { cw[b] = make_uint2(0u, 0u); continue; }
               if (!__any_sync(kFull, (cw[b].x | cw[b].y) != 0)) continue;
-              if (lane == 0) S.nfail = 1;
+              // a later row than the best failure found so far cannot be the event (one lane reads: the test must be warp-uniform)
+              uint32_t fk_now = 0;
+              if (lane == 0) { S.nfail = 1; fk_now = *(volatile uint32_t*)&S.fail_key; }
+              fk_now = __shfl_sync(kFull, fk_now, 0);
+              if (fk_now != 0xffffffffu && (Mr[b] - base_row) > fk_now / (uint32_t)n) { cw[b] = make_uint2(0u, 0u); continue; }
               const int npop = __reduce_add_sync(kFull, (unsigned)(__popc(cw[b].x) + __popc(cw[b].y)));
               if (npop > kS2ProbeMax) { big[b] = true; cw[b] = make_uint2(0u, 0u); }
             }
@@ -720,49 +935,139 @@ struct Sweeper2 {
         else win = w0;
         cyc[4] += clock64() - t0;
       }
-      if (S.abort_flag) break;
+      if (S.abort_flag) return;
       t0 = clock64();
       // ---- finalise the column
       v_compact();
       const uint32_t nv = S.vcount;
-      if (nv > maxv) maxv = nv;
       if (!essential) {
-        if (vpool_used + nv > P.vpool_cap) { csync(); if (gtid == 0) fail(TDA_ERR_CAPACITY); csync(); break; }
-        uint32_t* dst = P.vpool + (size_t)p * P.vpool_cap + vpool_used;
+        const long long used = S.vpool_used;
+        if (used + nv > P.vpool_cap) { csync(); if (gtid == 0) fail(TDA_ERR_CAPACITY); csync(); return; }
+        uint32_t* dst = P.vpool + (size_t)p * P.vpool_cap + used;
         const uint32_t* list = vlist(S.vsel);
         for (uint32_t i = (uint32_t)gtid; i < nv; i += (uint32_t)nthreads) __stcg(&dst[i], __ldcg(&list[i]));
+        __threadfence();
+        csync();
         if (gtid == 0) {
-          __stcg(&P.vstart[(size_t)p * P.cap1 + ci], (int64_t)vpool_used);
+          __stcg(&P.vstart[(size_t)p * P.cap1 + ci], (int64_t)used);
           __stcg(&P.vlen[(size_t)p * P.cap1 + ci], (int)nv);
           hash_insert(pivot, ci);
+          S.vpool_used = used + nv;
         }
-        vpool_used += nv;
       }
-      const float birth = SD[rbirth];
-      float death = INFINITY;
-      int Md = -1, wd = -1;
-      if (!essential) { Md = (int)(pivot / (uint64_t)n); wd = n - 1 - (int)(pivot % (uint64_t)n); death = SD[Md]; }
-      if (essential || death > birth) {
-        if (gtid == 0) {
-          out[2 * nrows] = birth; out[2 * nrows + 1] = death;
-          if (outs) {
-            const uint32_t e = EN[rbirth];
-            outs[2 * nrows] = edge_index((int)(e >> 16), (int)(e & 0xffffu));
-            if (essential) outs[2 * nrows + 1] = -1;
-            else {
-              const uint32_t em = EN[Md];
-              int x = (int)(em >> 16), y = (int)(em & 0xffffu), z = wd, t;
-              if (x < y) { t = x; x = y; y = t; }
-              if (y < z) { t = y; y = z; z = t; }
-              if (x < y) { t = x; x = y; y = t; }
-              outs[2 * nrows + 1] = (int64_t)x * (x - 1) * (x - 2) / 6 + (int64_t)y * (y - 1) / 2 + z;
-            }
-          }
-        }
-        ++nrows;
+      if (gtid == 0) {
+        if ((unsigned long long)nv > S.maxv) S.maxv = nv;
+        emit_pair(p, rbirth, essential, pivot);
       }
       v_clear();
       cyc[5] += clock64() - t0;
+    }
+  }
+
+  __device__ __forceinline__ void run_problem(int p) {
+    R = P.rank + (size_t)p * n * n;
+    EN = P.ends + (size_t)p * P.E;
+    EA = P.ea + (size_t)p * P.E;
+    PAR = P.par + (size_t)p * P.E;
+    T = P.T[p];
+    hkeys = P.hkeys + (size_t)p * P.hcap;
+    hvals = P.hvals + (size_t)p * P.hcap;
+    int* bl = P.blist + (size_t)p * P.cap1;
+    const int nb = P.bcount[p];
+    unsigned long long* st = P.stats + (size_t)p * ST_N;
+    if (nb > P.cap1) {
+      if (gtid == 0) { P.counts[p * 4 + 3] = TDA_ERR_CAPACITY; P.counts[p * 4 + 1] = 0; }
+      return;
+    }
+    p_valid = false;   // Pm belongs to the previous cloud's rank matrix
+    sort_blist(bl, nb);
+    for (int i = gtid; i < P.hcap; i += nthreads) __stcg(&hkeys[i], kEmpty);
+    for (int i = tid; i < W; i += kS2Threads) { touched[i] = 0; tnew[i] = 0; }
+    if (gtid == 0) {
+      S.vcount = 0; S.vsel = 0; S.abort_flag = 0; S.nundone = 0;
+      S.nrows = 0; S.vpool_used = 0; S.maxv = 0; S.badd = 0; S.next_col = 0; S.big_ci = -1;
+      S.wc_cols = S.wc_resumed = S.wc_big = S.wc_rows = S.wc_heavy = S.wc_scans = 0;
+      for (int q = 0; q < 16; ++q) S.st[q] = 0;
+    }
+    __threadfence();
+    csync();
+    unsigned long long badd_edges = 0;
+    long long cyc[6] = {0, 0, 0, 0, 0, 0};
+    long long t0 = clock64();
+    cyc_sync = 0; n_sync = 0;
+    const bool use_warp_engine = P.s2_warp_engine != 0;
+
+    // ---- stage A: every column speculatively by a warp, without owner look-ups (first failure = tentative death)
+    if (use_warp_engine) {
+      for (;;) {
+        int k = 0;
+        if (lane == 0) k = atomicAdd(&S.next_col, 1);
+        k = __shfl_sync(kFull, k, 0);
+        if (k >= nb) break;
+        const int ci = nb - 1 - k;   // (ripser's order first: the early columns are committed first)
+        const uint32_t rbirth = (uint32_t)__ldcg(&bl[ci]);
+        WcState v;
+        v.nv = 1; v.vr = lane == 0 ? rbirth : 0xffffffffu; v.ven = lane == 0 ? __ldg(&EN[rbirth]) : 0u;
+        uint32_t pos = rbirth + 1;
+        unsigned long long key = 0;
+        const int status = wc_sweep(v, pos, key, false, p);
+        wc_store(ci, status, v, pos, key);
+      }
+      __threadfence();
+    } else {
+      for (int ci = gtid; ci < nb; ci += nthreads) {   // every column goes to the cluster engine, from its birth edge
+        uint32_t* r = recs + (size_t)ci * kWcRec;
+        const uint32_t rbirth = (uint32_t)__ldcg(&bl[ci]);
+        __stcg(&r[0], (uint32_t)WC_BIG); __stcg(&r[1], rbirth + 1u); __stcg(&r[4], 1u); __stcg(&r[8], rbirth);
+      }
+      __threadfence();
+    }
+    csync();
+    cyc[0] += clock64() - t0;   // (stage A is booked under the first counter)
+    if (gtid == 0) S.next_col = nb - 1;
+    csync();
+
+    // ---- commit loop, in ripser's order.  Warp 0 of CTA 0 commits the columns whose tentative pivot is still free and resumes
+    // the others with owner look-ups (every earlier column is final by then: exactly the sequential algorithm); a column that
+    // outgrows the warp is reduced by the whole cluster.
+    for (;;) {
+      t0 = clock64();
+      if (gwarp == 0) {
+        int ci = S.next_col;
+        int big = -1;
+        for (; ci >= 0 && !S.abort_flag; --ci) {
+          const int rbirth = __ldcg(&bl[ci]);
+          WcState v;
+          uint32_t pos;
+          unsigned long long key;
+          int status = wc_load(ci, v, pos, key);
+          bool resumed = false;
+          while (status == WC_DEATH && hash_find(key) >= 0) {   // the tentative pivot belongs to an earlier column: go on from there
+            status = wc_sweep(v, pos, key, true, p);
+            resumed = true;
+          }
+          if (lane == 0) { S.wc_cols += 1; if (resumed) S.wc_resumed += 1; }
+          if (status == WC_BIG) {
+            if (resumed) wc_store(ci, status, v, pos, key);
+            if (lane == 0) S.wc_big += 1;
+            big = ci;
+            break;
+          }
+          if (!wc_commit(p, ci, rbirth, status, v, key)) break;
+        }
+        __threadfence();
+        if (lane == 0) { S.big_ci = big; S.next_col = big - 1; }
+      }
+      csync();
+      cyc[1] += clock64() - t0;
+      const int big = S.big_ci;
+      if (big < 0 || S.abort_flag) break;
+      {
+        const uint32_t* r = recs + (size_t)big * kWcRec;
+        cluster_column(p, big, __ldcg(&bl[big]), __ldcg(&r[1]), cyc, badd_edges);
+      }
+      csync();
+      if (S.abort_flag) break;
     }
     csync();
     if (S.abort_flag) {  // leave the scratch clean for the next problem
@@ -774,23 +1079,23 @@ struct Sweeper2 {
       if (gtid == 0) S.vcount = 0;
     }
     if (gtid == 0) {
-      P.counts[p * 4 + 1] = nrows;
+      P.counts[p * 4 + 1] = S.nrows;
       P.counts[p * 4 + 3] = S.abort_flag;
       st[ST_REDUCED] = (unsigned long long)nb;
       st[ST_ADDITIONS] = S.st[S2_FLIPS] - S.st[S2_UNDONE] + S.st[S2_EVENTS];
-      st[ST_PUSHES] = S.st[S2_SUBST];        // rows substituted
-      st[ST_POPS] = S.st[S2_EVENTS] + S.st[S2_DEATHS];   // non-apparent pivots
+      st[ST_PUSHES] = S.st[S2_SUBST] + S.wc_rows;        // rows substituted (windows) + rows swept by warps
+      st[ST_POPS] = S.st[S2_EVENTS] + S.st[S2_DEATHS];   // non-apparent pivots of the cluster engine
       st[ST_EXTENSIONS] = S.st[S2_WINDOWS];
-      st[ST_MAXV] = maxv;
+      st[ST_MAXV] = S.maxv;
       for (int q = 0; q < 6; ++q) st[ST_CYC_EXTRACT + q] = (unsigned long long)cyc[q];
       st[ST_BADD_EDGES] = badd_edges;
-      st[ST_EXT_EDGES] = S.st[S2_HEAVY];
+      st[ST_EXT_EDGES] = S.st[S2_HEAVY] + S.wc_heavy;
       st[ST_S2_ROUNDS] = S.st[S2_ROUNDS];
       st[ST_S2_LATE] = S.st[S2_LATE];
       st[ST_S2_PM] = S.st[S2_PM];
       st[ST_S2_DENSE] = S.st[S2_DENSE];
-      st[ST_S2_SPURIOUS] = S.st[S2_SPURIOUS];
-      st[ST_S2_UNDONE] = S.st[S2_UNDONE];
+      st[ST_S2_SPURIOUS] = S.wc_resumed;     // columns the commit loop had to resume (their tentative pivot was owned)
+      st[ST_S2_UNDONE] = S.wc_big;           // columns handed to the cluster engine
       st[ST_SPARE0] = (unsigned long long)cyc_sync;
       st[ST_SPARE1] = n_sync;
     }

@@ -32,9 +32,9 @@ def pdist_lowdim(pts):
 
 # names of the device counters per reducer (include/tda_b200.h: tda_rips_stats)
 _STAT_NAMES = {
-    "sweep2": ["columns", "apparent", "reduced", "additions", "rows_substituted", "pivots", "windows", "max_v", "cyc_round1", "cyc_late_rounds",
-               "cyc_apply", "cyc_verify", "cyc_events", "cyc_pm_finalise", "edges_via_columns", "heavy_rows", "late_rounds", "late_rows",
-               "pm_rows_moved", "dense_columns", "spurious_stops", "flips_undone", "barrier_cycles", "barriers"],
+    "sweep2": ["columns", "apparent", "reduced", "additions", "rows_substituted", "pivots", "windows", "max_v", "cyc_warp_stage", "cyc_commit_loop",
+               "cyc_substitute", "cyc_verify", "cyc_events", "cyc_pm_finalise", "edges_via_columns", "heavy_rows", "late_rounds", "late_rows",
+               "pm_rows_moved", "dense_columns", "columns_resumed", "columns_to_cluster", "barrier_cycles", "barriers"],
     "sweep": ["columns", "apparent", "reduced", "additions", "rows_streamed", "pivots", "restarts", "max_v", "cyc_filter", "row_groups",
               "cyc_resolve", "cyc_column_add", "cyc_flip_patch", "cyc_dense_final", "edges_via_columns", "heavy_rows"],
     "bitset": ["columns", "apparent", "reduced", "additions", "toggles", "pivots", "slides", "max_v", "cyc_scan", "cyc_owner", "cyc_gen",

@@ -45,13 +45,23 @@ def test_reducer_matches_oracle(tda_option, reducer, gen, n, seed):
 ])
 @pytest.mark.parametrize("gen,n,seed", [(torus3d, 420, 7), (blobs3d, 700, 8), (circle2d, 300, 9)])
 def test_sweep2_window_schedules(tda_option, opts, gen, n, seed):
-    got = _check(gen(n, np.random.default_rng(seed)), "sweep2", tda_option, **opts)
+    """the cluster engine alone (rips_warp_engine=0: every column goes through the windows)"""
+    got = _check(gen(n, np.random.default_rng(seed)), "sweep2", tda_option, rips_warp_engine=0, **opts)
     st = got["stats"]
-    assert st["windows"] > 0 and st["rows_substituted"] > 0
+    assert st["windows"] > 0 and st["rows_substituted"] > 0 and st["columns_to_cluster"] == st["reduced"]
+
+
+@pytest.mark.parametrize("gen,n,seed", [(torus3d, 420, 7), (blobs3d, 700, 8), (circle2d, 300, 9), (torus3d, 1500, 10)])
+def test_sweep2_warp_engine(tda_option, gen, n, seed):
+    """the default: every column first by a single warp (speculative, no owner look-ups), committed in ripser's order by one warp that
+    resumes the columns whose tentative pivot is owned, and only the columns that outgrow a warp go through the windows"""
+    got = _check(gen(n, np.random.default_rng(seed)), "sweep2", tda_option, rips_warp_engine=1, rips_w0=256)
+    st = got["stats"]
+    assert st["columns_to_cluster"] < st["reduced"]
 
 
 def test_sweep2_dense_mode_is_exercised(tda_option):
-    got = _check(torus3d(900, np.random.default_rng(21)), "sweep2", tda_option, rips_w0=256, rips_wsparse=1024, rips_wmax=8192,
+    got = _check(torus3d(900, np.random.default_rng(21)), "sweep2", tda_option, rips_warp_engine=0, rips_w0=256, rips_wsparse=1024, rips_wmax=8192,
                  rips_dense_min=8, rips_dense_div=32)
     assert got["stats"]["dense_columns"] > 0 and got["stats"]["pm_rows_moved"] > 0
 
@@ -80,7 +90,8 @@ def test_bench_size_c3_embedding_matches_oracle(tda_option, reducer):
     Y = umap_.umap_fit_batch(X, n_neighbors=15, n_components=3, metric="cosine", random_state=42)[0].cpu().numpy()
     got = _check(Y, reducer, tda_option)
     if reducer == "sweep2":
-        assert got["stats"]["dense_columns"] > 0   # the long columns of a 2000-point cloud run in dense mode
+        assert got["stats"]["dense_columns"] > 0   # the long columns of a 2000-point cloud run in dense mode (cluster engine)
+        assert 0 < got["stats"]["columns_to_cluster"] < got["stats"]["reduced"] // 2   # most columns never leave their warp
 
 
 def test_sweep2_batch_of_bench_size_clouds_equals_sweep(tda_option):
@@ -104,5 +115,6 @@ def test_sweep2_batch_of_bench_size_clouds_equals_sweep(tda_option):
 def test_sweep2_cluster_sizes(tda_option, cluster, gen, n, seed):
     """sweep2 deals every pass over a window to the warps of a thread-block cluster (default 4 CTAs per cloud); any cluster size
     must give the oracle's pairs."""
-    got = _check(gen(n, np.random.default_rng(seed)), "sweep2", tda_option, rips_cluster=cluster, rips_w0=256, rips_dense_min=16)
-    assert got["stats"]["windows"] > 0
+    for we in (0, 1):
+        got = _check(gen(n, np.random.default_rng(seed)), "sweep2", tda_option, rips_cluster=cluster, rips_w0=256, rips_dense_min=16, rips_warp_engine=we)
+    assert got["stats"]["reduced"] > 0
