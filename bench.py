@@ -3,11 +3,15 @@
 ("32 layers x 2k tokens x 4096-d, UMAP k=15 then Rips H0/H1"), synthetic activations (tda_multimodal_b200/workloads.py).
 
   python bench.py --gpus N --steps K --warmup W            this repo's CUDA path (one rank per GPU under torchrun)
-  python bench.py --impl reference --gpus N --steps K ...  the CPU restatement of umap-learn + ripser (oracle/), all host cores
+  python bench.py --impl reference --gpus N --steps K ...  the CPU implementation of the path, all host cores: the real
+                                                           umap-learn + ripser when they are importable, else the oracle port
+  --scaling weak (default): 32 layers PER GPU;  --scaling strong: the 32 layers of config C3 split over the ranks
+  --workload c3 (default) | c3c4: C3 followed by 256 bootstrap resamples (1000 points, Rips H0/H1) of every layer's cloud
+                                  (the north-star target run; a "layer" then includes its resamples)
 
-A step = one pass of the hot path over one batch: every rank runs the 32-layer sweep (pairwise distances -> exact kNN
-+ sigma/rho -> fuzzy graph -> spectral init -> SGD to 3-D -> Rips H0/H1) on its own 32 layers (weak scaling: layer
-sets differ by rank) and the ranks gather the diagrams (NCCL) -- the only cross-GPU traffic of the path.
+A step = one pass of the hot path over one batch: every rank runs the layer sweep (pairwise distances -> exact kNN
++ sigma/rho -> fuzzy graph -> spectral init -> SGD to 3-D -> Rips H0/H1) on its own layers and the ranks gather the
+diagrams (NCCL) -- the only cross-GPU traffic of the path.
 `value` times the sweep with the activations already resident in HBM; `e2e` times the same sweep from pinned HOST
 buffers (H2D of the activations and D2H of embeddings + diagrams inside the timed region).
 """
@@ -26,9 +30,9 @@ if ROOT not in sys.path:
 
 METRIC = "umap_rips_h0h1_layers_per_sec"
 UNIT = "layers/s"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the round's `ncu --set full` capture of this command
-# (profiles/r01b_ncu_full_summary.csv; 16 clouds of 2000 points per launch): static evidence, not measured by this run
-NCU_TRAFFIC_BYTES = {"rips_reduce": 1.09e9, "pdist_gemm": 3.0e9, "knn_smooth": 0.26e9}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the stage's dominant kernel, from `ncu --set full` captures of this
+# command's kernels at the default shape (committed artefact; written by scripts/ncu_traffic.py from profiles/*.csv)
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02_ncu_dram_bytes.json")
 
 
 def parse():
@@ -37,51 +41,96 @@ def parse():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c3c4"])
     ap.add_argument("--layers", type=int, default=32)
     ap.add_argument("--points", type=int, default=2000)
     ap.add_argument("--dim", type=int, default=4096)
     ap.add_argument("--neighbors", type=int, default=15)
+    ap.add_argument("--resamples", type=int, default=256)
+    ap.add_argument("--resample-points", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-peaks", action="store_true", help="skip the on-box TF32 matmul peak measurement")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
     return ap.parse_args()
 
 
+def layers_of_rank(a, rank, world):
+    """weak: every rank has its own a.layers layers (seeds offset by rank); strong: the a.layers layers of C3 dealt l -> l mod world."""
+    if a.scaling == "weak":
+        return list(range(a.layers)), 3000 + 1000 * rank
+    return list(range(rank, a.layers, world)), 3000
+
+
 def workload_config(a, world):
-    return {"workload": f"C3: {a.layers} layers x {a.points} points x {a.dim}-d synthetic activations per GPU, UMAP(n_neighbors={a.neighbors}, "
-                        f"n_components=3, min_dist=0.1, metric=cosine, 500 epochs) -> ripser(maxdim=1)",
-            "layers_per_gpu": a.layers, "points": a.points, "dim": a.dim, "n_neighbors": a.neighbors,
-            "parallelism": f"layer-sharded x{world}, NCCL gather of diagrams", "l2": "inputs (1.05 GB/step/GPU) larger than L2"}
+    per = a.layers if a.scaling == "weak" else f"{a.layers}/{world}"
+    cfg = {"workload": f"C3: {a.layers} layers x {a.points} points x {a.dim}-d synthetic activations {'per GPU' if a.scaling == 'weak' else 'in total'}, "
+                       f"UMAP(n_neighbors={a.neighbors}, n_components=3, min_dist=0.1, metric=cosine, 500 epochs) -> ripser(maxdim=1)",
+           "layers_per_gpu": per, "points": a.points, "dim": a.dim, "n_neighbors": a.neighbors,
+           "parallelism": f"layer-sharded x{world}, NCCL gather of diagrams", "l2": "inputs (1.05 GB per 32 layers) larger than L2"}
+    if a.workload == "c3c4":
+        cfg["workload"] += f" + C4: {a.resamples} bootstrap resamples of {a.resample_points} points per layer, Rips H0/H1 each"
+        cfg["resamples_per_layer"] = a.resamples
+    return cfg
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# CPU side (oracle port of umap-learn + ripser): used by cpu_baseline and by --impl reference
+# CPU side: used by cpu_baseline and by --impl reference
+def _real_libs():
+    """the real libraries first.  Returns (umap module, ripser function) or None."""
+    try:
+        import umap as _umap
+        from ripser import ripser as _ripser
+        if "tda_multimodal_b200" in (getattr(_umap, "__file__", "") or "") or "shims" in (getattr(_umap, "__file__", "") or ""):
+            return None   # this repo's own shims are not the reference
+        return _umap, _ripser
+    except Exception:
+        return None
+
+
 def _cpu_layer(args):
     layer, n, d, k, n_layers = args
     os.environ.setdefault("OMP_NUM_THREADS", "1")
-    from oracle import umap_oracle as uo, rips as orips
     from tda_multimodal_b200 import workloads
     X = workloads.c3_layer(layer, n=n, d=d, n_layers=n_layers)
+    real = _real_libs()
     t0 = time.perf_counter()
-    Y = uo.UMAPOracle(n_neighbors=k, n_components=3, min_dist=0.1, metric="cosine", random_state=42).fit_transform(X)
-    t1 = time.perf_counter()
-    orips.ripser(Y, maxdim=1)
+    if real:
+        Y = real[0].UMAP(n_neighbors=k, n_components=3, min_dist=0.1, metric="cosine", random_state=42).fit_transform(X)
+        t1 = time.perf_counter()
+        real[1](Y, maxdim=1)
+    else:
+        from oracle import umap_oracle as uo, rips as orips
+        Y = uo.UMAPOracle(n_neighbors=k, n_components=3, min_dist=0.1, metric="cosine", random_state=42).fit_transform(X)
+        t1 = time.perf_counter()
+        orips.ripser(Y, maxdim=1)
     t2 = time.perf_counter()
     return layer, t1 - t0, t2 - t1
 
 
 def _cpu_warm():
     """numba JIT + library load, untimed (tiny cloud)."""
-    from oracle import umap_oracle as uo, rips as orips
     from tda_multimodal_b200 import workloads
     X = workloads.c3_layer(0, n=120, d=64)
+    real = _real_libs()
+    if real:
+        real[1](real[0].UMAP(n_neighbors=10, n_components=3, metric="cosine", random_state=42).fit_transform(X), maxdim=1)
+        return
+    from oracle import umap_oracle as uo, rips as orips
     Y = uo.UMAPOracle(n_neighbors=10, n_components=3, metric="cosine", random_state=42).fit_transform(X)
     orips.ripser(Y, maxdim=1)
+
+
+def _cpu_kind():
+    return ("reference", "umap-learn + ripser (real libraries)") if _real_libs() else \
+        ("port", "oracle/umap_oracle.py (numba) + oracle/rips_oracle.cpp: umap-learn and ripser are not installed in this image")
 
 
 def cpu_baseline_serial(a, budget_s):
     """Single core, as the reference runs it (serial `for i in range(32)`, random_state set => serial numba SGD,
     ripser single-threaded): whole layers of the same workload until the time budget is used."""
     _cpu_warm()
+    kind, what = _cpu_kind()
     done, t_total, per = 0, 0.0, []
     for layer in range(a.layers):
         _, tu, tr = _cpu_layer((layer, a.points, a.dim, a.neighbors, a.layers))
@@ -90,19 +139,19 @@ def cpu_baseline_serial(a, budget_s):
         per.append((round(tu, 2), round(tr, 2)))
         if t_total >= budget_s:
             break
-    return {"value": done / t_total, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"layers 0..{done - 1} of the {a.layers}-layer C3 workload, serial on one core (oracle/umap_oracle.py numba + oracle/rips_oracle.cpp); "
-                      f"per-layer (umap_s, rips_s) = {per}"}
+    return {"value": done / t_total, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": f"layers 0..{done - 1} of the {a.layers}-layer C3 workload, serial on one core ({what}); per-layer (umap_s, rips_s) = {per}"}
 
 
 def run_reference(a):
-    """--impl reference: the oracle port on all host cores (one process per layer, layers are independent)."""
+    """--impl reference: the CPU implementation on all host cores (one process per layer, layers are independent)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, a.layers))
+    kind, what = _cpu_kind()
     ctx = mp.get_context("spawn")
     with ctx.Pool(procs, initializer=_pool_init) as pool:
         for _ in range(max(1, a.warmup)):
@@ -120,12 +169,12 @@ def run_reference(a):
     total = sum(times)
     done = len(times)
     value = procs * done / total
-    sample = (f"per step: layers 0..{procs - 1} of the C3 workload concurrently, one process per core; warm-up steps run tiny clouds "
+    sample = (f"per step: layers 0..{procs - 1} of the C3 workload concurrently, one process per core ({what}); warm-up steps run tiny clouds "
               f"(numba JIT only); {done} of {a.steps} requested steps timed (time box {budget_s:.0f} s)")
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": done, "warmup": a.warmup,
-            "ms_per_step": 1e3 * total / done, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": 1e3 * total / done, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "reference", "config": workload_config(a, a.gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -192,11 +241,40 @@ class ClockSampler:
         return out
 
 
-def algorithmic_work(stage, a, n_layers_done, extra):
-    """Algorithmic bytes / flops of one stage over `n_layers_done` layers (DESIGN.md 'Measurement')."""
+def measure_tf32_peak(torch, dev):
+    """Dense TF32 tensor-core peak of THIS box: torch.matmul fp32 with TF32 allowed, 8192^3; burst = best of
+    10 single calls, sustained = back to back for ~2 s.  The distance GEMM issues kind::tf32 MMAs: this is its roofline."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        A = torch.randn((n, n), device=dev, dtype=torch.float32)
+        B = torch.randn((n, n), device=dev, dtype=torch.float32)
+        C = torch.empty((n, n), device=dev, dtype=torch.float32)
+        for _ in range(3):
+            torch.matmul(A, B, out=C)
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(A, B, out=C); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(20, int(2000.0 / best))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(A, B, out=C)
+        e1.record(); torch.cuda.synchronize()
+        flop = 2.0 * n ** 3
+        return {"burst": flop / (best / 1e3) / 1e12, "sustained": flop * reps / (e0.elapsed_time(e1) / 1e3) / 1e12,
+                "how": "torch.matmul fp32 (allow_tf32) 8192^3 on this box: best of 10 (burst), back to back for ~2 s (sustained)"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def algorithmic_work(stage, a, L, extra):
+    """(bound, algorithmic bytes or flops) of one stage over L layers (DESIGN.md 'Measurement')."""
     n, d, k = a.points, a.dim, a.neighbors
     E = n * (n - 1) // 2
-    L = n_layers_done
     if stage == "pdist_gemm":
         return "tensor", 2.0 * L * n * n * d
     table = {
@@ -204,16 +282,32 @@ def algorithmic_work(stage, a, n_layers_done, extra):
         "knn_smooth": L * (4.0 * n * n + 8.0 * n * k + 8.0 * n),       # read D, write idx+dist, sigma+rho
         "fuzzy_graph": L * (12.0 * n * k + 8.0 * n + 16.0 * 2 * n * k),
         "spectral_init": L * extra.get("spectral_bytes_per_layer", 0.0),
-        "umap_sgd": extra.get("sgd_bytes", 0.0),
+        # SGD: per fired edge two endpoints + ~5 negative samples read (16 B each) and one position written: 124 B
+        "umap_sgd": 124.0 * extra.get("sgd_fired_per_layer", 0.0) * L,
         "rips_pdist": L * (12.0 * n + 4.0 * n * n),
         "rips_edge_sort": L * (4.0 * n * n + 16.0 * E + 16.0 * E),     # read dm, radix sort key+payload, rank scatter
         "rips_h0": L * (4.0 * n * n) * extra.get("boruvka_rounds", 11),
         "rips_apparent": L * 8.0 * (E - n + 1) * (n - 2),
-        # row-sweep reducer: 8 B (endpoints, apex) per streamed row; per heavy row two V rows + two lune sources
-        # (adjacency-bitmatrix rows in dense columns: 4 * n/8 B in total)
-        "rips_reduce": 8.0 * extra.get("reduce_rows", 0.0) + 4.0 * (n / 8.0) * extra.get("reduce_heavy_rows", 0.0),
+        # residual reduction: 16 B (endpoints, apex, parents) per row swept / substituted; per heavy row two V rows + two
+        # adjacency rows (4 * n/8 B)
+        "rips_reduce": L * (16.0 * extra.get("reduce_rows_per_layer", 0.0) + 4.0 * (n / 8.0) * extra.get("reduce_heavy_rows_per_layer", 0.0)),
     }
     return "hbm", table[stage]
+
+
+def union_ms(spans):
+    """total length of the union of [start, end) intervals"""
+    tot, cur_a, cur_b = 0.0, None, None
+    for a_, b_ in sorted(spans):
+        if cur_b is None or a_ > cur_b:
+            if cur_b is not None:
+                tot += cur_b - cur_a
+            cur_a, cur_b = a_, b_
+        else:
+            cur_b = max(cur_b, b_)
+    if cur_b is not None:
+        tot += cur_b - cur_a
+    return tot
 
 
 def run_b200(a):
@@ -231,45 +325,59 @@ def run_b200(a):
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
 
-    # this rank's 32 layers (weak scaling: rank r gets layer seeds offset by r * layers), in pinned host memory
-    Xh = torch.empty((a.layers, a.points, a.dim), dtype=torch.float32).pin_memory()
-    workloads.c3_layers(n_layers=a.layers, n=a.points, d=a.dim, seed=3000 + 1000 * rank, out=Xh.numpy())
+    my_layers, seed = layers_of_rank(a, rank, world)
+    nl = len(my_layers)
+    Xh = torch.empty((max(nl, 1), a.points, a.dim), dtype=torch.float32).pin_memory()
+    if nl:
+        workloads.c3_layers(n_layers=a.layers, n=a.points, d=a.dim, seed=seed, layers=my_layers, out=Xh.numpy())
     Xd = Xh.to(dev)
-    n_units = a.layers * world
-    my_units = list(range(rank * a.layers, (rank + 1) * a.layers))
+    layers_per_step = a.layers * world if a.scaling == "weak" else a.layers
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def units_of(out):
+        """per-layer diagram sets of one sweep (+ the bootstrap resamples of every layer for c3c4)"""
+        units = [r["dgms"] for r in out["results"]]
+        if a.workload == "c3c4" and nl:
+            Y = out["embedding"]
+            Yd = Y if isinstance(Y, torch.Tensor) else torch.from_numpy(Y).to(dev)
+            boot = pipeline.bootstrap_rips(Yd, n_resamples=a.resamples, size=a.resample_points, layer_ids=my_layers)
+            units += [r["dgms"] for per_layer in boot for r in per_layer]
+        return units
+
     def step_resident():
-        out = pipeline.layer_sweep(Xd, n_neighbors=a.neighbors, return_embedding=True)
-        return gather(out)
+        out = pipeline.layer_sweep(Xd[:nl], n_neighbors=a.neighbors, return_embedding=True) if nl else {"results": [], "embedding": None}
+        return gather(units_of(out))
 
     def step_e2e():
-        out = pipeline.layer_sweep_host(Xh, device=dev, n_neighbors=a.neighbors)
-        return gather(out), out
+        out = pipeline.layer_sweep_host(Xh[:nl], device=dev, n_neighbors=a.neighbors) if nl else {"results": [], "embedding": np.zeros((0, a.points, 3), np.float32)}
+        return gather(units_of(out)), out
 
-    def gather(out):
+    def gather(units):
         if world == 1:
-            return [r["dgms"] for r in out["results"]]
-        # contiguous unit ranges per rank: gather with the same two all_gathers, then reorder
-        counts, payload = pipeline.pack_diagrams(out["results"])
-        ct = torch.from_numpy(counts).to(dev)
-        allc = [torch.empty_like(ct) for _ in range(world)]
-        dist.all_gather(allc, ct)
-        rows = max(int(c.sum()) for c in allc)
-        pad = np.zeros((max(rows, 1), 2), np.float32)
-        pad[:payload.shape[0]] = payload
-        pt = torch.from_numpy(pad).to(dev)
-        allp = [torch.empty_like(pt) for _ in range(world)]
-        dist.all_gather(allp, pt)
+            return units
+        counts, payload = pipeline.pack_diagrams([{"dgms": u} for u in units])
+        sizes = torch.tensor([counts.shape[0], payload.shape[0]], device=dev)
+        all_sizes = [torch.empty_like(sizes) for _ in range(world)]
+        dist.all_gather(all_sizes, sizes)
+        mc, mp = max(int(s[0]) for s in all_sizes), max(int(s[1]) for s in all_sizes)
+        cpad = torch.zeros((max(mc, 1), 2), dtype=torch.int32, device=dev)
+        cpad[:counts.shape[0]] = torch.from_numpy(counts).to(dev)
+        ppad = torch.zeros((max(mp, 1), 2), dtype=torch.float32, device=dev)
+        ppad[:payload.shape[0]] = torch.from_numpy(payload).to(dev)
+        gc = [torch.empty_like(cpad) for _ in range(world)]
+        gp = [torch.empty_like(ppad) for _ in range(world)]
+        dist.all_gather(gc, cpad)
+        dist.all_gather(gp, ppad)
         if rank != 0:
             return None
         full = []
         for r in range(world):
-            full += pipeline.unpack_diagrams(allc[r].cpu().numpy(), allp[r].cpu().numpy())
+            nc, npay = int(all_sizes[r][0]), int(all_sizes[r][1])
+            full += pipeline.unpack_diagrams(gc[r][:nc].cpu().numpy(), gp[r][:npay].cpu().numpy())
         return full
 
     def timed(fn, steps):
@@ -296,69 +404,100 @@ def run_b200(a):
     ms_res, dgms = timed(step_resident, a.steps)
     launches = int(L.tda_launch_count())
     stages = _lib.stage_times()
+    timeline = _lib.stage_timeline()
     L.tda_stage_timing_enable(0)
     ms_e2e, (dg2, out2) = timed(step_e2e, a.steps)
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
-        layers_per_step = a.layers * world
         value = layers_per_step * a.steps / (ms_res / 1e3)
         e2e_value = layers_per_step * a.steps / (ms_e2e / 1e3)
-        d2h = int(out2["embedding"].nbytes + sum(sum(d.shape[0] * 8 for d in r["dgms"]) for r in out2["results"]) + 16 * a.layers)
-        # ---- roofline of the dominant stage (timed with CUDA events inside the timed region, rank 0)
-        import json as _json
+        d2h = int(out2["embedding"].nbytes + sum(sum(d.shape[0] * 8 for d in r["dgms"]) for r in out2["results"]) + 16 * nl)
         peaks = {}
         try:
-            peaks = _json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        bf16_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
         peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-        # device-side counters of the last sweep for the reduction's algorithmic bytes
+        tf32 = None
+        if not a.no_peaks:
+            try:
+                tf32 = measure_tf32_peak(torch, dev)
+            except Exception as ex:
+                tf32 = {"error": repr(ex)}
+        if tf32 and "sustained" in tf32:
+            tf32_peak, tf32_src = tf32["sustained"], "measured on this box by this run (cuBLAS TF32 8192^3, sustained)"
+        else:
+            tf32_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))) / 2.0
+            tf32_src = "derived: measured bf16 dense / 2"
+        # ---- device-side counters of one more sweep: the reduction's rows, the SGD's fired edges
         extra = {}
         try:
-            dm = pipeline.pdist_lowdim(torch.from_numpy(out2["embedding"]).to(dev))
+            from tda_multimodal_b200 import umap_
+            nsub = min(nl, 8)
+            dm = pipeline.pdist_lowdim(torch.from_numpy(out2["embedding"][:nsub]).to(dev))
             st = pipeline.rips_batch(dm, maxdim=1, want_stats=True)
             rows_key = "rows_substituted" if "rows_substituted" in st[0]["stats"] else "rows_streamed"
-            extra["reduce_rows"] = float(sum(r["stats"][rows_key] for r in st)) * a.steps
-            extra["reduce_heavy_rows"] = float(sum(r["stats"]["heavy_rows"] for r in st)) * a.steps
-            extra["rips_stats_sum"] = {k: int(sum(r["stats"][k] for r in st)) for k in st[0]["stats"] if not k.startswith(("cyc_", "spare", "max_v"))}
+            extra["reduce_rows_per_layer"] = float(sum(r["stats"][rows_key] for r in st)) / nsub
+            extra["reduce_heavy_rows_per_layer"] = float(sum(r["stats"]["heavy_rows"] for r in st)) / nsub
+            extra["rips_stats_per_layer"] = {k: round(sum(r["stats"][k] for r in st) / nsub, 1) for k in st[0]["stats"]
+                                             if not k.startswith(("cyc_", "spare", "max_v", "barrier"))}
             extra["rips_reducer"] = _lib.rips_reducer()
-        except Exception as ex:  # stats are optional evidence
+            _, state = umap_.umap_fit_batch(Xd[:min(nl, 4)], n_neighbors=a.neighbors, n_components=3, metric="cosine", random_state=42, return_state=True)
+            eps = state["eps"]
+            n_ep = int(state["n_epochs"])
+            fired = torch.where(eps > 0, torch.floor(n_ep / eps.clamp(min=1.0)), torch.zeros_like(eps)).sum().item()
+            extra["sgd_fired_per_layer"] = float(fired) / min(nl, 4)     # directed entries fired over all epochs (counted from the schedule)
+        except Exception as ex:  # optional evidence
             extra["stats_error"] = repr(ex)
-        n_done = a.layers * a.steps
-        fired = 0.0
-        extra["sgd_bytes"] = 124.0 * 500 * 2 * a.points * a.neighbors * 0.35 * n_done  # ~35% of slots fire per epoch on average
+        traffic = {}
+        try:
+            traffic = json.load(open(TRAFFIC_FILE))
+        except Exception:
+            pass
+        default_shape = (a.points, a.dim, a.neighbors) == (2000, 4096, 15)
+        # ---- roofline table: every stage; spans of the two chunk streams overlap, so `wall_ms` (union of the stage's spans) is
+        # what the stage occupies on the clock and `sum_ms` what its launches add up to
+        n_done = nl * a.steps
+        spans_by_stage = {}
+        for name, t0_, t1_ in timeline:
+            spans_by_stage.setdefault(name, []).append((t0_, t1_))
+        table = {}
+        for sname, (ms_sum, calls) in stages.items():
+            if calls == 0:
+                continue
+            kind, work = algorithmic_work(sname, a, n_done, extra)
+            peak = tf32_peak if kind == "tensor" else hbm_peak
+            unit = "TFLOP/s" if kind == "tensor" else "GB/s"
+            scale = 1e12 if kind == "tensor" else 1e9
+            achieved = work / (ms_sum / 1e3) / scale if ms_sum > 0 else 0.0
+            ent = {"bound": "tensor" if kind == "tensor" else "hbm", "sum_ms_per_step": round(ms_sum / a.steps, 3),
+                   "wall_ms_per_step": round(union_ms(spans_by_stage.get(sname, [])) / a.steps, 3), "launches_per_step": calls / a.steps,
+                   "avg_launch_ms": round(ms_sum / calls, 4), "work_per_step": work / a.steps, "achieved": achieved, "peak": peak, "unit": unit,
+                   "frac": achieved / peak if peak else None}
+            tr = traffic.get(sname) if default_shape else None
+            if tr:
+                ent["traffic"] = tr.get("dram_bytes_per_launch")
+                ent["traffic_source"] = tr.get("source")
+            table[sname] = ent
+        dom = max(table, key=lambda s_: table[s_]["sum_ms_per_step"])
+        D = table[dom]
         tot_ms = sum(v[0] for v in stages.values())
-        dom = max(stages, key=lambda s: stages[s][0])
-        kind, work = algorithmic_work(dom, a, n_done, extra)
-        dom_ms = stages[dom][0]
-        calls = max(1, stages[dom][1])
-        if kind == "tensor":
-            achieved = work / (dom_ms / 1e3) / 1e12
-            peak, unit = bf16_peak / 2.0, "TFLOP/s"     # kind::tf32 issues at half the bf16 rate; useful flops = 1/3 of issued (3xTF32)
-        else:
-            achieved = work / (dom_ms / 1e3) / 1e9
-            peak, unit = hbm_peak, "GB/s"
-        default_shape = (a.layers, a.points, a.dim) == (32, 2000, 4096)
-        roofline = {"kernel": dom, "bound": kind, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak if peak else None,
-                    "traffic": NCU_TRAFFIC_BYTES.get(dom) if default_shape else None, "peak_source": peak_src, "avg_launch_ms": dom_ms / calls, "share_of_device_stage_time": dom_ms / tot_ms if tot_ms else None,
-                    "stages_ms_per_step": {s: round(v[0] / a.steps, 3) for s, v in stages.items()}}
-        # the two kernel-level figures BASELINE.json's metric names next to layers/s, from the same stage timers
+        roofline = {"kernel": dom, "bound": D["bound"], "achieved": D["achieved"], "peak": D["peak"], "unit": D["unit"], "frac": D["frac"],
+                    "traffic": D.get("traffic"), "traffic_source": D.get("traffic_source"),
+                    "peak_source": tf32_src if D["bound"] == "tensor" else peak_src, "avg_launch_ms": D["avg_launch_ms"],
+                    "share_of_device_stage_time": D["sum_ms_per_step"] * a.steps / tot_ms if tot_ms else None,
+                    "stages_ms_per_step": {s_: round(v[0] / a.steps, 3) for s_, v in stages.items()},
+                    "stages": table,
+                    "peaks": {"hbm_gbs": hbm_peak, "hbm_source": peak_src, "tf32_tflops": tf32_peak, "tf32_source": tf32_src, "tf32_measurement": tf32},
+                    "note": "stage times are CUDA-event spans on the launching streams; the two chunk streams overlap, so sum_ms adds up to more "
+                            "than the step and wall_ms is the union of a stage's spans"}
+        # the two kernel-level figures BASELINE.json's metric names next to layers/s, each timed alone (cold L2)
         secondary = {}
-        if stages.get("pdist_gemm", (0, 0))[0] > 0:
-            secondary["pdist_useful_tflops"] = algorithmic_work("pdist_gemm", a, n_done, extra)[1] / (stages["pdist_gemm"][0] / 1e3) / 1e12
-            secondary["pdist_issued_tflops_3xtf32"] = 3.0 * secondary["pdist_useful_tflops"]
-            secondary["pdist_frac_of_tf32_peak_issued"] = secondary["pdist_issued_tflops_3xtf32"] / (bf16_peak / 2.0)
-        if stages.get("knn_smooth", (0, 0))[0] > 0:
-            secondary["knn_hbm_gbs"] = algorithmic_work("knn_smooth", a, n_done, extra)[1] / (stages["knn_smooth"][0] / 1e3) / 1e9
-            secondary["knn_frac_of_hbm_peak"] = secondary["knn_hbm_gbs"] / hbm_peak
-        # the same two kernels timed alone (cold L2, CUDA events on the launching stream): inside the sweep they share the
-        # GPU with the other chunk's kernels, so the stage timer understates them
         try:
             from tda_multimodal_b200 import umap_
-            half = max(1, a.layers // 2)                      # one chunk of the sweep
+            half = max(1, nl // 2)                      # one chunk of the sweep
             Xc = Xd[:half]
             flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
@@ -377,7 +516,7 @@ def run_b200(a):
             secondary["alone"] = {
                 "layers": half,
                 "pdist_ms": ms_pd, "pdist_useful_tflops": 2.0 * half * n_ * n_ * d_ / (ms_pd / 1e3) / 1e12,
-                "pdist_issued_frac_of_tf32_peak": 3.0 * 2.0 * half * n_ * n_ * d_ / (ms_pd / 1e3) / 1e12 / (bf16_peak / 2.0),
+                "pdist_issued_frac_of_tf32_peak": 3.0 * 2.0 * half * n_ * n_ * d_ / (ms_pd / 1e3) / 1e12 / tf32_peak,
                 "knn_ms": ms_kn, "knn_hbm_gbs": half * (4.0 * n_ * n_ + 8.0 * n_ * k_ + 8.0 * n_) / (ms_kn / 1e3) / 1e9,
                 "knn_frac_of_hbm_peak": half * (4.0 * n_ * n_ + 8.0 * n_ * k_ + 8.0 * n_) / (ms_kn / 1e3) / 1e9 / hbm_peak,
                 "note": "each call timed alone incl. operand prep (pdist) / memset + sigma floor (kNN), 512 MB L2 flush before every rep"}
@@ -385,14 +524,17 @@ def run_b200(a):
         except Exception as ex:  # optional evidence
             secondary["alone_error"] = repr(ex)
         roofline["secondary"] = secondary
-        if "rips_stats_sum" in extra:
-            roofline["rips_stats_per_step"] = extra["rips_stats_sum"]
+        for k_ in ("rips_stats_per_layer", "rips_reducer", "sgd_fired_per_layer", "stats_error"):
+            if k_ in extra:
+                roofline[k_] = extra[k_]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": ms_res / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "ms_per_step": ms_res / a.steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": workload_config(a, world),
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(Xh.numel() * 4), "d2h_bytes_per_step": d2h,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nl * a.points * a.dim * 4), "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / a.steps},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
+        if dgms is not None:
+            line["diagram_sets_gathered_per_step"] = len(dgms)
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_serial(a, a.cpu_budget_s)
         print(json.dumps(line), flush=True)

@@ -66,6 +66,9 @@ long long tda_get_option(const char* name);
 void tda_stage_timing_enable(int on);
 void tda_stage_timing_reset(void);
 int tda_stage_timing_read(double* ms_out, int64_t* calls_out, int n);
+/* every timed stage span since the last reset, in enqueue order: stage id, start and end in ms after the reset (CUDA events on the
+ * launching streams, so spans of different streams overlap); returns the number of spans (at most `cap` are written). */
+int tda_stage_timeline_read(int* stage_out, double* start_ms_out, double* end_ms_out, int cap);
 
 /* ---- pairwise distances on high-dimensional activations (tcgen05 / TMEM / TMA GEMM, 3xTF32) ------
  * Replaces sklearn.metrics.pairwise_distances inside umap-learn's small-data path (metric='cosine';

@@ -18,6 +18,7 @@ PROTOTYPES = {
     "tda_stage_timing_enable": (None, [c_int]),
     "tda_stage_timing_reset": (None, []),
     "tda_stage_timing_read": (c_int, [c_void_p, c_void_p, c_int]),
+    "tda_stage_timeline_read": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "tda_pdist_lowdim": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tda_pdist_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "tda_pdist": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -86,6 +87,16 @@ def stage_times():
     calls = np.zeros(len(STAGES), dtype=np.int64)
     lib().tda_stage_timing_read(ms.ctypes.data, calls.ctypes.data, len(STAGES))
     return {s: (float(ms[i]), int(calls[i])) for i, s in enumerate(STAGES)}
+
+
+def stage_timeline(cap=65536):
+    """[(stage name, start ms, end ms)] of every timed stage span since the last reset (spans of different streams overlap)."""
+    import numpy as np
+    st = np.zeros(cap, dtype=np.int32)
+    t0 = np.zeros(cap, dtype=np.float64)
+    t1 = np.zeros(cap, dtype=np.float64)
+    k = min(cap, int(lib().tda_stage_timeline_read(st.ctypes.data, t0.ctypes.data, t1.ctypes.data, cap)))
+    return [(STAGES[int(st[i])], float(t0[i]), float(t1[i])) for i in range(k)]
 
 
 class TdaError(RuntimeError):

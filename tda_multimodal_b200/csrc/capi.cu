@@ -16,8 +16,11 @@ int64_t& launch_counter() {
 
 // ---- stage timer: per thread, a list of (stage, start event, stop event); events are pooled and reused
 struct StageRec { int stage; cudaEvent_t e0, e1; };
+struct StageSpan { int stage; double t0, t1; };
 struct StageState {
   bool on = false;
+  cudaEvent_t ref = nullptr;          // recorded at reset: the origin of the timeline
+  std::vector<StageSpan> spans;       // (stage, start, end) in ms since `ref`, in the order the stages were enqueued
   std::vector<StageRec> recs;
   std::vector<cudaEvent_t> pool;
   double ms[STAGE_COUNT] = {0};
@@ -55,6 +58,8 @@ static void stage_collect(StageState& S) {
     if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
       S.ms[r.stage] += (double)ms;
       S.calls[r.stage] += 1;
+      float a = 0.f;
+      if (S.ref && cudaEventElapsedTime(&a, S.ref, r.e0) == cudaSuccess && S.spans.size() < 65536) S.spans.push_back({r.stage, (double)a, (double)a + (double)ms});
     }
     S.pool.push_back(r.e0);
     S.pool.push_back(r.e1);
@@ -111,6 +116,21 @@ extern "C" void tda_stage_timing_reset(void) {
   tda::StageState& S = tda::stage_state();
   tda::stage_collect(S);
   for (int i = 0; i < tda::STAGE_COUNT; ++i) { S.ms[i] = 0; S.calls[i] = 0; }
+  S.spans.clear();
+  if (!S.ref) cudaEventCreate(&S.ref);
+  cudaEventRecord(S.ref, 0);   // legacy default stream: ordered after everything enqueued so far
+  (void)cudaGetLastError();
+}
+extern "C" int tda_stage_timeline_read(int* stage_out, double* start_ms_out, double* end_ms_out, int cap) {
+  tda::StageState& S = tda::stage_state();
+  tda::stage_collect(S);
+  const int k = (int)S.spans.size() < cap ? (int)S.spans.size() : cap;
+  for (int i = 0; i < k; ++i) {
+    if (stage_out) stage_out[i] = S.spans[i].stage;
+    if (start_ms_out) start_ms_out[i] = S.spans[i].t0;
+    if (end_ms_out) end_ms_out[i] = S.spans[i].t1;
+  }
+  return (int)S.spans.size();
 }
 extern "C" int tda_stage_timing_read(double* ms_out, int64_t* calls_out, int n) {
   tda::StageState& S = tda::stage_state();

@@ -389,7 +389,9 @@ struct ReduceParams {
   // sweep2 reducer (rips_sweep2.cuh)
   const uint2* par;                         // [batch, E] parents of the apparent edges (rank | apparent << 31)
   uint2* s2_pend; uint2* s2_heavy;          // per-cluster spill lists: [grid, 2, wmax + 64], [grid, wmax + 64]
-  uint32_t* s2_rec;                         // per-cluster column records of the warp engine: [grid, cap1, kWcRec]
+  uint32_t* s2_rec;                         // per-cluster column records: [grid, s2_nrec, kWcRec]
+  int* s2_lists;                            // per-cluster work lists: [grid, 3 * s2_nrec + cap1] (two round lists, cluster-engine list, final record per column)
+  int s2_nrec;                              // records per cloud (every reduction of a column writes a new one)
   int s2_warp_engine;                       // 1: short columns are reduced by single warps first (stage A + commit loop)
   int s2_w0, s2_wsparse, s2_wmax, s2_dense_min, s2_dense_div;
 };
@@ -2098,7 +2100,7 @@ struct Layout {
   bool sweep;                       // one of the row-sweep reducers (X / Pm bit matrices) rather than the key bitset
   int reducer;                      // 0 sweep2, 1 sweep (resolver), 2 sweep (verify), 3 bitset
   uint2* par;                       // parents of the apparent edges (sweep2)
-  uint2* s2_pend; uint2* s2_heavy; uint32_t* s2_rec; int s2_wmax;
+  uint2* s2_pend; uint2* s2_heavy; uint32_t* s2_rec; int* s2_lists; int s2_nrec; int s2_wmax;
   int* work_counter; unsigned long long* stats;
   int grid; size_t total;
 };
@@ -2166,7 +2168,9 @@ static Layout make_layout(void* ws, int n, int batch, int maxdim, int cap1, size
       L.s2_wmax = s2_wmax_option();
       L.s2_pend = c.take<uint2>((size_t)L.grid * 2 * (size_t)(L.s2_wmax + 64));
       L.s2_heavy = c.take<uint2>((size_t)L.grid * (size_t)(L.s2_wmax + 64));
-      L.s2_rec = c.take<uint32_t>((size_t)L.grid * (size_t)cap1 * kWcRec);
+      L.s2_nrec = 4 * cap1 + 64;
+      L.s2_rec = c.take<uint32_t>((size_t)L.grid * (size_t)L.s2_nrec * kWcRec);
+      L.s2_lists = c.take<int>((size_t)L.grid * (size_t)(3 * L.s2_nrec + cap1));
     }
     if (L.sweep) {
       L.xmat = c.take<uint32_t>((size_t)L.grid * (size_t)n * L.xw);
@@ -2326,7 +2330,7 @@ static int rips_enqueue(const float* dm, int n, int batch, int maxdim, float thr
     P.work_counter = L.work_counter; P.stats = L.stats;
     P.apex4 = nullptr; P.far = nullptr; P.far_cap = 0; P.nbk = 0;
     P.verify_mode = L.reducer == 2 ? 1 : 0;
-    P.par = L.par; P.s2_pend = L.s2_pend; P.s2_heavy = L.s2_heavy; P.s2_rec = L.s2_rec;
+    P.par = L.par; P.s2_pend = L.s2_pend; P.s2_heavy = L.s2_heavy; P.s2_rec = L.s2_rec; P.s2_lists = L.s2_lists; P.s2_nrec = L.s2_nrec;
     P.s2_warp_engine = option("rips_warp_engine") != 0 ? 1 : 0;
     P.s2_wmax = L.s2_wmax;
     P.s2_w0 = (int)option("rips_w0");

@@ -41,7 +41,8 @@ constexpr int kS2ProbeMax = 256;       // candidate bits of a row up to which th
 enum { TDA_ERR_INTERNAL_S2 = -6 };
 // warp engine (short, sparse columns: one warp per column, V in the lanes)
 constexpr int kWcMaxV = 32;            // edges of V a warp holds (one per lane); more -> the column goes to the cluster engine
-constexpr int kWcRec = 40;             // words of a column record: status, pos, key lo, key hi, nv, -, -, -, 32 edge ranks
+constexpr int kWcRec = 40;             // words of a column record: status, pos, key lo, key hi, nv (0xffffffff: V in the pool), column,
+                                       // pool length, pool start, then up to 32 edge ranks.  Records are written once and never changed.
 constexpr uint32_t kWcMaxRows = 1u << 18;   // rows a warp sweeps before it hands the column over
 constexpr uint32_t kWcMaxHeavy = 2048;      // heavy rows a warp handles before it hands the column over
 enum { WC_NONE = 0, WC_DEATH = 1, WC_ESSENTIAL = 2, WC_BIG = 3 };
@@ -54,8 +55,12 @@ struct Sweep2Smem {
   uint32_t fail_key;           // smallest failing key of the window: (row - base_row) * n + (n - 1 - vertex), 32 bits (< 65536 * n)
   // column bookkeeping shared by the warp engine (stage A / commit loop) and the cluster engine
   int nrows;                   // H1 rows written so far
-  int next_col;                // stage A: next column to hand to a warp;  commit loop: next column to commit
-  int big_ci;                  // commit loop -> cluster engine: the column to reduce with windows (-1: all columns are done)
+  int next_col;                // next entry of the round's work list to hand to a warp
+  uint32_t nrec;               // records allocated
+  uint32_t nact[2];            // entries of the two work lists (this round / next round)
+  uint32_t nbig, nbig_done;    // columns waiting for the cluster engine / taken by it
+  int ev_rec;                  // cluster engine: record of the column that owns the pivot of the event (-1: nobody -> death)
+  int ev_slot;                 //                 its slot in the pivot table
   long long vpool_used;
   unsigned long long maxv, badd;
   unsigned long long wc_cols, wc_resumed, wc_big, wc_rows, wc_heavy, wc_scans;   // warp engine counters
@@ -90,7 +95,11 @@ struct Sweeper2 {
   uint32_t *X, *Pm, *vbits, *vl0;
   uint2 *pend_g, *heavy_g;
   uint32_t* wcd;               // this warp's vertex bitmap (warp engine), W words of this CTA's shared memory
-  uint32_t* recs;              // tentative column records of this cluster's cloud: [cap1][kWcRec] words (global)
+  uint32_t* recs;              // column records of this cluster's cloud: [s2_nrec][kWcRec] words (global)
+  int* act;                    // work lists of the rounds: [2][s2_nrec] records to reduce further (global)
+  int* biglist;                // [s2_nrec] records of columns for the cluster engine
+  int* cur_rec;                // [cap1] final (latest) record of every column
+  int act_next;                // which work list the displaced columns go to
   uint32_t p_pos; bool p_valid;
   uint64_t* hkeys; int* hvals;
   long long cyc_sync; unsigned long long n_sync;   // (diagnostics) cycles this thread spent in cluster barriers, and their number
@@ -122,7 +131,11 @@ struct Sweeper2 {
     vl0 = P.vlist + (size_t)slot * 2 * P.vcap;
     pend_g = P.s2_pend + (size_t)slot * 2 * (size_t)(P.s2_wmax + 64);
     heavy_g = P.s2_heavy + (size_t)slot * (size_t)(P.s2_wmax + 64);
-    recs = P.s2_rec + (size_t)slot * (size_t)P.cap1 * kWcRec;
+    recs = P.s2_rec + (size_t)slot * (size_t)P.s2_nrec * kWcRec;
+    act = P.s2_lists + (size_t)slot * (size_t)(3 * P.s2_nrec + P.cap1);
+    biglist = act + 2 * (size_t)P.s2_nrec;
+    cur_rec = biglist + P.s2_nrec;
+    act_next = 1;
   }
   static __host__ __device__ size_t dyn_bytes(int W, int wmax) {
     const int nw = wmax / 32 + 4;
@@ -227,21 +240,36 @@ struct Sweeper2 {
     if (gtid == 0) S.vcount = 0;
     csync();
   }
-  __device__ __forceinline__ int hash_find(uint64_t key) const {
+  // ---- pivot table (open addressing): key = death triangle, value = RECORD of the column that currently owns it (-1: nobody).
+  // Lock-free reduction (Morozov & Nigmetov): columns are reduced in any order; a column b that arrives at a pivot owned by a
+  // column with a larger birth (earlier in ripser's order) adds that column's V and goes on; otherwise it takes the pivot, and
+  // the column it displaces is reduced further in the next round.  Every addition is "earlier column into later column", and at
+  // the fixpoint all pivots are distinct, so the pairing is THE persistence pairing (same pairs as the sequential order).
+  __device__ __forceinline__ int tab_slot(uint64_t key) {   // find or insert (one thread)
     uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32) & (uint32_t)(P.hcap - 1);
-    for (;;) {
+    for (int guard = 0; guard < P.hcap; ++guard) {
       const uint64_t k = __ldcg(&hkeys[h]);
-      if (k == key) return __ldcg(&hvals[h]);
-      if (k == kEmpty) return -1;
+      if (k == key) return (int)h;
+      if (k == kEmpty) {
+        const unsigned long long old = atomicCAS((unsigned long long*)&hkeys[h], (unsigned long long)kEmpty, (unsigned long long)key);
+        if (old == kEmpty || old == key) return (int)h;
+      }
       h = (h + 1) & (uint32_t)(P.hcap - 1);
     }
+    fail(TDA_ERR_CAPACITY);
+    return 0;
   }
-  __device__ __forceinline__ void hash_insert(uint64_t key, int val) {  // one thread
-    uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32) & (uint32_t)(P.hcap - 1);
-    while (__ldcg(&hkeys[h]) != kEmpty) h = (h + 1) & (uint32_t)(P.hcap - 1);
-    __stcg(&hvals[h], val);
-    __stcg(&hkeys[h], key);
-    __threadfence();
+  __device__ __forceinline__ uint32_t* rec_ptr(int rid) const { return recs + (size_t)rid * kWcRec; }
+  __device__ __forceinline__ int rec_col(int rid) const { return rid < 0 ? -1 : (int)__ldcg(&rec_ptr(rid)[5]); }
+  __device__ __forceinline__ int rec_alloc() {   // one thread
+    const uint32_t r = atomicAdd(&S.nrec, 1u);
+    if (r >= (uint32_t)P.s2_nrec) { fail(TDA_ERR_CAPACITY); return (int)P.s2_nrec - 1; }
+    return (int)r;
+  }
+  __device__ __forceinline__ void act_push(int which, int rid) {   // one thread: record `rid` is reduced further in the next round
+    const uint32_t k = atomicAdd(&S.nact[which], 1u);
+    if (k < (uint32_t)P.s2_nrec) __stcg(&act[(size_t)which * P.s2_nrec + k], rid);
+    else fail(TDA_ERR_CAPACITY);
   }
   // CTA 0 sorts the birth list (global memory, bitonic)
   __device__ __forceinline__ void sort_blist(int* bl, int nb) {
@@ -443,9 +471,10 @@ struct Sweeper2 {
     return __reduce_max_sync(kFull, best);
   }
   // the sweep.  In: V, first row `pos`.  Out: status, V (final, or the state to hand over), pos / key.
-  __device__ __forceinline__ int wc_sweep(WcState& v, uint32_t& pos, unsigned long long& key, bool owned, int p) {
+  __device__ __forceinline__ int wc_sweep(WcState& v, uint32_t& pos, unsigned long long& key, int b, int p) {
     uint32_t nheavy = 0, nrows = 0, nscan = 0;
     int status = WC_NONE;
+    int myrec = -1;   // the record this sweep publishes (allocated when it first needs one)
     while (status == WC_NONE) {
       if (pos >= (uint32_t)T) { status = WC_ESSENTIAL; break; }
       if (nrows > kWcMaxRows || nheavy > kWcMaxHeavy) { status = WC_BIG; break; }
@@ -487,113 +516,181 @@ struct Sweeper2 {
           const int w = wc_verify(v, M, cc, dd, cur, nscan);
           if (w < 0) break;
           const unsigned long long k = (unsigned long long)M * (unsigned long long)n + (unsigned long long)(n - 1 - w);
-          int owner = -1;
-          if (owned) owner = hash_find(k);
-          if (owner < 0) { key = k; pos = M; status = WC_DEATH; break; }
-          const long long vs = __ldcg(&P.vstart[(size_t)p * P.cap1 + owner]);
-          const int vn = __ldcg(&P.vlen[(size_t)p * P.cap1 + owner]);
-          const uint32_t* ov = P.vpool + (size_t)p * P.vpool_cap + vs;
-          const WcState saved = v;
-          bool fits = vn <= 2 * kWcMaxV;
-          for (int q = 0; q < vn && fits; ++q) {
-            const uint32_t re = __ldcg(&ov[q]);
-            fits = wc_toggle(v, re, __ldg(&EN[re]));
+          // who owns this pivot?  an earlier column (larger index): add its V and verify the row again; else: take it
+          int slot = 0, rid = -1;
+          if (lane == 0) { slot = tab_slot(k); rid = *(volatile int*)&hvals[slot]; }
+          slot = __shfl_sync(kFull, slot, 0);
+          rid = __shfl_sync(kFull, rid, 0);
+          bool added = false;
+          for (;;) {
+            const int c = rec_col(rid);
+            if (c > b) {
+              const uint32_t* r = rec_ptr(rid);
+              const uint32_t nvc = __ldcg(&r[4]);
+              const WcState saved = v;
+              bool fits = true;
+              if (nvc == 0xffffffffu) {   // the owner's V is in the pool
+                const uint32_t vn = __ldcg(&r[6]);
+                const uint32_t* ov = P.vpool + (size_t)p * P.vpool_cap + __ldcg(&r[7]);
+                fits = vn <= 2u * kWcMaxV;
+                for (uint32_t q = 0; q < vn && fits; ++q) {
+                  const uint32_t re = __ldcg(&ov[q]);
+                  fits = wc_toggle(v, re, __ldg(&EN[re]));
+                }
+              } else {
+                const uint32_t mine = lane < (int)nvc ? __ldcg(&r[8 + lane]) : 0u;
+                for (uint32_t q = 0; q < nvc && fits; ++q) {
+                  const uint32_t re = __shfl_sync(kFull, mine, (int)q);
+                  fits = wc_toggle(v, re, __ldg(&EN[re]));
+                }
+              }
+              if (!fits) { v = saved; pos = M; status = WC_BIG; }   // the cluster engine meets the same pivot again and adds it itself
+              added = true;
+              break;
+            }
+            // take the pivot: the record first (complete before anybody can see it), then the claim
+            if (myrec < 0) { if (lane == 0) myrec = rec_alloc(); myrec = __shfl_sync(kFull, myrec, 0); }
+            rec_write(myrec, WC_DEATH, v, M, k, b);
+            __threadfence();
+            int old = 0;
+            if (lane == 0) old = atomicCAS(&hvals[slot], rid, myrec);
+            old = __shfl_sync(kFull, old, 0);
+            if (old == rid) {
+              if (lane == 0) { if (rid >= 0) act_push(act_next, rid); __stcg(&cur_rec[b], myrec); }
+              key = k; pos = M; status = WC_DEATH;
+              break;
+            }
+            rid = old;   // somebody else was faster: look again
           }
-          if (!fits) { v = saved; pos = M; status = WC_BIG; break; }   // the cluster engine meets the same pivot again and adds it itself
-          cur = wc_in(v, M);
+          if (status != WC_NONE) break;
+          if (added) cur = wc_in(v, M);
         }
         if (status != WC_NONE) break;
       }
       if (status == WC_NONE) pos = base + 32u;
+    }
+    if (status != WC_DEATH) {   // essential: final;  big: the state goes to the cluster engine
+      if (myrec < 0) { if (lane == 0) myrec = rec_alloc(); myrec = __shfl_sync(kFull, myrec, 0); }
+      rec_write(myrec, status, v, pos, 0ull, b);
+      __threadfence();
+      if (lane == 0) {
+        __stcg(&cur_rec[b], myrec);
+        if (status == WC_BIG) {
+          const uint32_t kb = atomicAdd(&S.nbig, 1u);
+          if (kb < (uint32_t)P.s2_nrec) __stcg(&biglist[kb], myrec); else fail(TDA_ERR_CAPACITY);
+        }
+      }
     }
     if (lane == 0) {
       atomicAdd(&S.wc_rows, (unsigned long long)nrows); atomicAdd(&S.wc_heavy, (unsigned long long)nheavy); atomicAdd(&S.wc_scans, (unsigned long long)nscan);
     }
     return status;
   }
-  __device__ __forceinline__ void wc_store(int ci, int status, const WcState& v, uint32_t pos, unsigned long long key) {
-    uint32_t* r = recs + (size_t)ci * kWcRec;
+  __device__ __forceinline__ void rec_write(int rid, int status, const WcState& v, uint32_t pos, unsigned long long key, int col) {
+    uint32_t* r = rec_ptr(rid);
     if (lane == 0) {
       __stcg(&r[0], (uint32_t)status); __stcg(&r[1], pos); __stcg(&r[2], (uint32_t)key); __stcg(&r[3], (uint32_t)(key >> 32)); __stcg(&r[4], (uint32_t)v.nv);
+      __stcg(&r[5], (uint32_t)col);
     }
     if (lane < v.nv) __stcg(&r[8 + lane], v.vr);
   }
-  __device__ __forceinline__ int wc_load(int ci, WcState& v, uint32_t& pos, unsigned long long& key) const {
-    const uint32_t* r = recs + (size_t)ci * kWcRec;
-    const int status = (int)__ldcg(&r[0]);
+  // state of a displaced column.  Returns false if its V does not fit a warp (it is in the pool and longer than 32 edges).
+  __device__ __forceinline__ bool rec_load(int rid, WcState& v, uint32_t& pos, int& col, int p) const {
+    const uint32_t* r = rec_ptr(rid);
     pos = __ldcg(&r[1]);
-    key = (unsigned long long)__ldcg(&r[2]) | ((unsigned long long)__ldcg(&r[3]) << 32);
-    v.nv = (int)__ldcg(&r[4]);
-    v.vr = lane < v.nv ? __ldcg(&r[8 + lane]) : 0xffffffffu;
+    col = (int)__ldcg(&r[5]);
+    const uint32_t nvr = __ldcg(&r[4]);
+    if (nvr == 0xffffffffu) {   // V in the pool (the column was reduced by the cluster engine)
+      const uint32_t vn = __ldcg(&r[6]);
+      if (vn > (uint32_t)kWcMaxV) return false;
+      const uint32_t* ov = P.vpool + (size_t)p * P.vpool_cap + __ldcg(&r[7]);
+      v.nv = (int)vn;
+      v.vr = lane < v.nv ? __ldcg(&ov[lane]) : 0xffffffffu;
+    } else {
+      v.nv = (int)nvr;
+      v.vr = lane < v.nv ? __ldcg(&r[8 + lane]) : 0xffffffffu;
+    }
     v.ven = lane < v.nv ? __ldg(&EN[v.vr]) : 0u;
-    return status;
+    return true;
   }
-  // one H1 row (birth, death) of column ci; zero-persistence pairs are dropped (as ripser does).  One thread.
-  __device__ __forceinline__ void emit_pair(int p, int rbirth, bool essential, uint64_t pivot) {
+  // the H1 rows in ripser's order (column index descending), zero-persistence pairs dropped (as ripser does).  CTA 0.
+  __device__ __forceinline__ void emit_all(int p, const int* bl, int nb) {
     const float* SD = P.sdist + (size_t)p * P.E;
     float* out = P.h1_pairs + (size_t)p * P.cap1 * 2;
     int64_t* outs = P.h1_simplex ? P.h1_simplex + (size_t)p * P.cap1 * 2 : nullptr;
-    const float birth = SD[rbirth];
-    float death = INFINITY;
-    int Md = -1, wd = -1;
-    if (!essential) { Md = (int)(pivot / (uint64_t)n); wd = n - 1 - (int)(pivot % (uint64_t)n); death = SD[Md]; }
-    if (essential || death > birth) {
-      const int nrows = S.nrows;
-      out[2 * nrows] = birth; out[2 * nrows + 1] = death;
-      if (outs) {
-        const uint32_t e = EN[rbirth];
-        outs[2 * nrows] = edge_index((int)(e >> 16), (int)(e & 0xffffu));
-        if (essential) outs[2 * nrows + 1] = -1;
-        else {
-          const uint32_t em = EN[Md];
-          int x = (int)(em >> 16), y = (int)(em & 0xffffu), z = wd, t;
-          if (x < y) { t = x; x = y; y = t; }
-          if (y < z) { t = y; y = z; z = t; }
-          if (x < y) { t = x; x = y; y = t; }
-          outs[2 * nrows + 1] = (int64_t)x * (x - 1) * (x - 2) / 6 + (int64_t)y * (y - 1) / 2 + z;
+    __shared__ int s_wsum[kS2Warps];
+    __shared__ int s_base;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int k0 = 0; k0 < nb; k0 += kS2Threads) {
+      const int k = k0 + tid;
+      bool keep = false, essential = false;
+      float birth = 0.f, death = INFINITY;
+      int rbirth = 0, Md = -1, wd = -1;
+      if (k < nb) {
+        const int ci = nb - 1 - k;
+        rbirth = __ldcg(&bl[ci]);
+        const uint32_t* r = rec_ptr(__ldcg(&cur_rec[ci]));
+        essential = __ldcg(&r[0]) == (uint32_t)WC_ESSENTIAL;
+        birth = SD[rbirth];
+        if (!essential) {
+          const uint64_t pivot = (uint64_t)__ldcg(&r[2]) | ((uint64_t)__ldcg(&r[3]) << 32);
+          Md = (int)(pivot / (uint64_t)n); wd = n - 1 - (int)(pivot % (uint64_t)n); death = SD[Md];
+        }
+        keep = essential || death > birth;
+      }
+      const unsigned bal = __ballot_sync(kFull, keep);
+      if (lane == 0) s_wsum[warp] = __popc(bal);
+      __syncthreads();
+      int off = s_base;
+      for (int w2 = 0; w2 < warp; ++w2) off += s_wsum[w2];
+      if (keep) {
+        const int row = off + __popc(bal & ((1u << lane) - 1));
+        out[2 * row] = birth; out[2 * row + 1] = death;
+        if (outs) {
+          const uint32_t e = EN[rbirth];
+          outs[2 * row] = edge_index((int)(e >> 16), (int)(e & 0xffffu));
+          if (essential) outs[2 * row + 1] = -1;
+          else {
+            const uint32_t em = EN[Md];
+            int x = (int)(em >> 16), y = (int)(em & 0xffffu), z = wd, t;
+            if (x < y) { t = x; x = y; y = t; }
+            if (y < z) { t = y; y = z; z = t; }
+            if (x < y) { t = x; x = y; y = t; }
+            outs[2 * row + 1] = (int64_t)x * (x - 1) * (x - 2) / 6 + (int64_t)y * (y - 1) / 2 + z;
+          }
         }
       }
-      S.nrows = nrows + 1;
+      __syncthreads();
+      if (tid == 0) { int tot = 0; for (int w2 = 0; w2 < kS2Warps; ++w2) tot += s_wsum[w2]; s_base += tot; }
+      __syncthreads();
     }
-  }
-  // a finished warp column becomes a reduced column: V into the pool, pivot into the hash map, its pair written.  One warp.
-  __device__ __forceinline__ bool wc_commit(int p, int ci, int rbirth, int status, const WcState& v, unsigned long long key) {
-    if (status == WC_DEATH) {
-      const long long used = S.vpool_used;
-      if (used + v.nv > P.vpool_cap) { if (lane == 0) fail(TDA_ERR_CAPACITY); return false; }
-      uint32_t* dst = P.vpool + (size_t)p * P.vpool_cap + used;
-      if (lane < v.nv) __stcg(&dst[lane], v.vr);
-      if (lane == 0) {
-        __stcg(&P.vstart[(size_t)p * P.cap1 + ci], (int64_t)used);
-        __stcg(&P.vlen[(size_t)p * P.cap1 + ci], v.nv);
-        S.vpool_used = used + v.nv;
-        if ((unsigned long long)v.nv > S.maxv) S.maxv = (unsigned long long)v.nv;
-      }
-      __syncwarp();
-      __threadfence();
-      if (lane == 0) hash_insert(key, ci);
-    }
-    if (lane == 0) emit_pair(p, rbirth, status == WC_ESSENTIAL, key);
-    __syncwarp();
-    return true;
+    if (tid == 0) S.nrows = s_base;
   }
 
   // =================================================================================================================
   // Cluster engine: column ci with windows (all threads of the cluster).  The column starts from the state the warp engine left:
   // `nv0` edges in the column's record, first row pos0 (nv0 = 1, the birth edge, pos0 = birth + 1 for a fresh column).
-  __device__ __forceinline__ void cluster_column(int p, int ci, int rbirth, uint32_t pos0, long long* cyc, unsigned long long& badd_edges) {
+  __device__ __forceinline__ void cluster_column(int p, int rid0, long long* cyc, unsigned long long& badd_edges) {
     const uint32_t w0 = (uint32_t)P.s2_w0, wsparse = (uint32_t)P.s2_wsparse, wmax = (uint32_t)P.s2_wmax;
     const int nb = P.bcount[p];
     long long t0;
-    {  // V = the recorded state
-      const uint32_t* r = recs + (size_t)ci * kWcRec;
-      const int nv0 = (int)__ldcg(&r[4]);
-      if (gtid < nv0) {
-        const uint32_t e = __ldcg(&r[8 + gtid]);
+    const uint32_t* r0 = rec_ptr(rid0);
+    const int ci = (int)__ldcg(&r0[5]);
+    const uint32_t pos0 = __ldcg(&r0[1]);
+    {  // V = the recorded state (in the record, or in the pool for a column the cluster engine reduced before)
+      const uint32_t nvr = __ldcg(&r0[4]);
+      const bool pooled = nvr == 0xffffffffu;
+      const int nv0 = pooled ? (int)__ldcg(&r0[6]) : (int)nvr;
+      const uint32_t* ov = pooled ? P.vpool + (size_t)p * P.vpool_cap + __ldcg(&r0[7]) : r0 + 8;
+      bool any = false;
+      for (int q = gtid; q < nv0; q += nthreads) {
+        const uint32_t e = __ldcg(&ov[q]);
         const uint32_t en = __ldg(&EN[e]);
         toggle_edge(e, en >> 16, en & 0xffffu);
-        __threadfence();
+        any = true;
       }
+      if (any) __threadfence();
       csync();
     }
     {
@@ -911,12 +1008,21 @@ struct Sweeper2 {
         }
         csync();
         const uint64_t fkey = (uint64_t)evM * (uint64_t)n + (uint64_t)(n - 1 - evw);
-        const int owner = hash_find(fkey);
-        if (owner < 0) { pivot = fkey; if (gtid == 0) S.st[S2_DEATHS] += 1; cyc[4] += clock64() - t0; break; }   // death
+        if (gtid == 0) {   // who owns the pivot (no other column is being reduced while the cluster engine runs)
+          const int slot = tab_slot(fkey);
+          const int rid = *(volatile int*)&hvals[slot];
+          S.ev_slot = slot;
+          S.ev_rec = rec_col(rid) > ci ? rid : -1;
+        }
+        csync();
+        const int orec = S.ev_rec;
+        if (orec < 0) { pivot = fkey; if (gtid == 0) S.st[S2_DEATHS] += 1; cyc[4] += clock64() - t0; break; }   // death (the claim follows)
         {
-          const int64_t vs = __ldcg(&P.vstart[(size_t)p * P.cap1 + owner]);
-          const int vn = __ldcg(&P.vlen[(size_t)p * P.cap1 + owner]);
-          const uint32_t* ov = P.vpool + (size_t)p * P.vpool_cap + vs;
+          const uint32_t* orp = rec_ptr(orec);
+          const uint32_t nvc = __ldcg(&orp[4]);
+          const bool pooled = nvc == 0xffffffffu;
+          const int vn = pooled ? (int)__ldcg(&orp[6]) : (int)nvc;
+          const uint32_t* ov = pooled ? P.vpool + (size_t)p * P.vpool_cap + __ldcg(&orp[7]) : orp + 8;
           if (S.vcount + (uint32_t)vn + 64u > (uint32_t)P.vcap) v_compact();
           bool any = false;
           for (int q = gtid; q < vn; q += nthreads) {
@@ -937,27 +1043,35 @@ struct Sweeper2 {
       }
       if (S.abort_flag) return;
       t0 = clock64();
-      // ---- finalise the column
+      // ---- finalise the column: V into the pool, a record of it, the pivot claimed (whoever held it is reduced further later)
       v_compact();
       const uint32_t nv = S.vcount;
+      const long long used = S.vpool_used;
       if (!essential) {
-        const long long used = S.vpool_used;
         if (used + nv > P.vpool_cap) { csync(); if (gtid == 0) fail(TDA_ERR_CAPACITY); csync(); return; }
         uint32_t* dst = P.vpool + (size_t)p * P.vpool_cap + used;
         const uint32_t* list = vlist(S.vsel);
         for (uint32_t i = (uint32_t)gtid; i < nv; i += (uint32_t)nthreads) __stcg(&dst[i], __ldcg(&list[i]));
         __threadfence();
-        csync();
-        if (gtid == 0) {
-          __stcg(&P.vstart[(size_t)p * P.cap1 + ci], (int64_t)used);
-          __stcg(&P.vlen[(size_t)p * P.cap1 + ci], (int)nv);
-          hash_insert(pivot, ci);
-          S.vpool_used = used + nv;
-        }
       }
+      csync();
       if (gtid == 0) {
+        const int rid = rec_alloc();
+        uint32_t* r = rec_ptr(rid);
+        __stcg(&r[0], (uint32_t)(essential ? WC_ESSENTIAL : WC_DEATH)); __stcg(&r[1], (uint32_t)(pivot / (uint64_t)n));
+        __stcg(&r[2], (uint32_t)pivot); __stcg(&r[3], (uint32_t)(pivot >> 32)); __stcg(&r[4], 0xffffffffu); __stcg(&r[5], (uint32_t)ci);
+        __stcg(&r[6], nv); __stcg(&r[7], (uint32_t)used);
+        __threadfence();
+        if (!essential) {
+          S.vpool_used = used + nv;
+          const int slot = tab_slot(pivot);
+          for (;;) {
+            const int cur = *(volatile int*)&hvals[slot];
+            if (atomicCAS(&hvals[slot], cur, rid) == cur) { if (cur >= 0) act_push(act_next, cur); break; }
+          }
+        }
+        __stcg(&cur_rec[ci], rid);
         if ((unsigned long long)nv > S.maxv) S.maxv = nv;
-        emit_pair(p, rbirth, essential, pivot);
       }
       v_clear();
       cyc[5] += clock64() - t0;
@@ -981,11 +1095,12 @@ struct Sweeper2 {
     }
     p_valid = false;   // Pm belongs to the previous cloud's rank matrix
     sort_blist(bl, nb);
-    for (int i = gtid; i < P.hcap; i += nthreads) __stcg(&hkeys[i], kEmpty);
+    for (int i = gtid; i < P.hcap; i += nthreads) { __stcg(&hkeys[i], kEmpty); __stcg(&hvals[i], -1); }
     for (int i = tid; i < W; i += kS2Threads) { touched[i] = 0; tnew[i] = 0; }
     if (gtid == 0) {
       S.vcount = 0; S.vsel = 0; S.abort_flag = 0; S.nundone = 0;
-      S.nrows = 0; S.vpool_used = 0; S.maxv = 0; S.badd = 0; S.next_col = 0; S.big_ci = -1;
+      S.nrows = 0; S.vpool_used = 0; S.maxv = 0; S.badd = 0; S.next_col = 0;
+      S.nrec = 0; S.nact[0] = S.nact[1] = 0; S.nbig = 0; S.nbig_done = 0; S.ev_rec = -1; S.ev_slot = 0;
       S.wc_cols = S.wc_resumed = S.wc_big = S.wc_rows = S.wc_heavy = S.wc_scans = 0;
       for (int q = 0; q < 16; ++q) S.st[q] = 0;
     }
@@ -997,78 +1112,81 @@ struct Sweeper2 {
     cyc_sync = 0; n_sync = 0;
     const bool use_warp_engine = P.s2_warp_engine != 0;
 
-    // ---- stage A: every column speculatively by a warp, without owner look-ups (first failure = tentative death)
-    if (use_warp_engine) {
-      for (;;) {
-        int k = 0;
-        if (lane == 0) k = atomicAdd(&S.next_col, 1);
-        k = __shfl_sync(kFull, k, 0);
-        if (k >= nb) break;
-        const int ci = nb - 1 - k;   // (ripser's order first: the early columns are committed first)
+    // ---- rounds.  Round 0 reduces every column from its birth edge; later rounds reduce the displaced columns further from
+    // their records; every column is one warp's work (dynamic list).  Columns that outgrow a warp wait for the cluster engine,
+    // which takes them one by one between the rounds; its claims may displace columns again.  Fixpoint: both lists empty.
+    if (!use_warp_engine) {   // every column goes to the cluster engine, from its birth edge (column order = ripser's)
+      for (int k = gtid; k < nb; k += nthreads) {
+        const int ci = nb - 1 - k;
+        uint32_t* r = rec_ptr(k);
         const uint32_t rbirth = (uint32_t)__ldcg(&bl[ci]);
-        WcState v;
-        v.nv = 1; v.vr = lane == 0 ? rbirth : 0xffffffffu; v.ven = lane == 0 ? __ldg(&EN[rbirth]) : 0u;
-        uint32_t pos = rbirth + 1;
-        unsigned long long key = 0;
-        const int status = wc_sweep(v, pos, key, false, p);
-        wc_store(ci, status, v, pos, key);
+        __stcg(&r[0], (uint32_t)WC_BIG); __stcg(&r[1], rbirth + 1u); __stcg(&r[4], 1u); __stcg(&r[5], (uint32_t)ci); __stcg(&r[8], rbirth);
+        __stcg(&biglist[k], k);
       }
+      if (gtid == 0) { S.nrec = (uint32_t)nb; S.nbig = (uint32_t)nb; }
       __threadfence();
-    } else {
-      for (int ci = gtid; ci < nb; ci += nthreads) {   // every column goes to the cluster engine, from its birth edge
-        uint32_t* r = recs + (size_t)ci * kWcRec;
-        const uint32_t rbirth = (uint32_t)__ldcg(&bl[ci]);
-        __stcg(&r[0], (uint32_t)WC_BIG); __stcg(&r[1], rbirth + 1u); __stcg(&r[4], 1u); __stcg(&r[8], rbirth);
-      }
-      __threadfence();
+      csync();
     }
-    csync();
-    cyc[0] += clock64() - t0;   // (stage A is booked under the first counter)
-    if (gtid == 0) S.next_col = nb - 1;
-    csync();
-
-    // ---- commit loop, in ripser's order.  Warp 0 of CTA 0 commits the columns whose tentative pivot is still free and resumes
-    // the others with owner look-ups (every earlier column is final by then: exactly the sequential algorithm); a column that
-    // outgrows the warp is reduced by the whole cluster.
-    for (;;) {
+    int cur_list = 0;       // work list of this round (round 0 of the warp engine: the nb fresh columns, no list)
+    bool fresh = use_warp_engine;
+    for (int round = 0;; ++round) {
+      if (round > 4 * nb + 64) { csync(); if (gtid == 0) fail(TDA_ERR_INTERNAL_S2); csync(); break; }
+      act_next = cur_list ^ 1;
+      const uint32_t nwork = fresh ? (uint32_t)nb : S.nact[cur_list];
+      // (a) warp rounds
       t0 = clock64();
-      if (gwarp == 0) {
-        int ci = S.next_col;
-        int big = -1;
-        for (; ci >= 0 && !S.abort_flag; --ci) {
-          const int rbirth = __ldcg(&bl[ci]);
+      if (nwork) {
+        for (;;) {
+          int k = 0;
+          if (lane == 0) k = atomicAdd(&S.next_col, 1);
+          k = __shfl_sync(kFull, k, 0);
+          if (k >= (int)nwork) break;
           WcState v;
           uint32_t pos;
-          unsigned long long key;
-          int status = wc_load(ci, v, pos, key);
-          bool resumed = false;
-          while (status == WC_DEATH && hash_find(key) >= 0) {   // the tentative pivot belongs to an earlier column: go on from there
-            status = wc_sweep(v, pos, key, true, p);
-            resumed = true;
+          int b;
+          if (fresh) {
+            b = nb - 1 - k;   // ripser's order first: fewer displacements
+            const uint32_t rbirth = (uint32_t)__ldcg(&bl[b]);
+            v.nv = 1; v.vr = lane == 0 ? rbirth : 0xffffffffu; v.ven = lane == 0 ? __ldg(&EN[rbirth]) : 0u;
+            pos = rbirth + 1;
+          } else {
+            const int rid = __ldcg(&act[(size_t)cur_list * P.s2_nrec + k]);
+            if (lane == 0) atomicAdd(&S.wc_resumed, 1ull);
+            if (!rec_load(rid, v, pos, b, p)) {   // too long for a warp: the cluster engine goes on with it
+              if (lane == 0) {
+                const uint32_t kb = atomicAdd(&S.nbig, 1u);
+                if (kb < (uint32_t)P.s2_nrec) __stcg(&biglist[kb], rid); else fail(TDA_ERR_CAPACITY);
+              }
+              continue;
+            }
           }
-          if (lane == 0) { S.wc_cols += 1; if (resumed) S.wc_resumed += 1; }
-          if (status == WC_BIG) {
-            if (resumed) wc_store(ci, status, v, pos, key);
-            if (lane == 0) S.wc_big += 1;
-            big = ci;
-            break;
-          }
-          if (!wc_commit(p, ci, rbirth, status, v, key)) break;
+          unsigned long long key = 0;
+          wc_sweep(v, pos, key, b, p);
+          if (lane == 0) atomicAdd(&S.wc_cols, 1ull);
         }
         __threadfence();
-        if (lane == 0) { S.big_ci = big; S.next_col = big - 1; }
       }
       csync();
-      cyc[1] += clock64() - t0;
-      const int big = S.big_ci;
-      if (big < 0 || S.abort_flag) break;
-      {
-        const uint32_t* r = recs + (size_t)big * kWcRec;
-        cluster_column(p, big, __ldcg(&bl[big]), __ldcg(&r[1]), cyc, badd_edges);
-      }
+      if (gtid == 0) { S.next_col = 0; S.nact[cur_list] = 0; }
       csync();
+      cyc[fresh ? 0 : 1] += clock64() - t0;
+      fresh = false;
       if (S.abort_flag) break;
+      // (b) nothing displaced: the cluster engine takes the next waiting column (largest index first would be ideal; the list
+      //     is in arrival order, which follows the column order of round 0 closely)
+      if (S.nact[cur_list ^ 1] == 0) {
+        if (S.nbig_done >= S.nbig) break;   // fixpoint
+        const int rid = __ldcg(&biglist[S.nbig_done]);
+        csync();
+        if (gtid == 0) { S.nbig_done += 1; S.wc_big += 1; }
+        cluster_column(p, rid, cyc, badd_edges);
+        csync();
+        if (S.abort_flag) break;
+      }
+      cur_list ^= 1;
     }
+    csync();
+    if (!S.abort_flag && crank == 0) emit_all(p, bl, nb);
     csync();
     if (S.abort_flag) {  // leave the scratch clean for the next problem
       for (size_t i = (size_t)gtid; i < (size_t)n * W; i += (size_t)nthreads) X[i] = 0;
@@ -1094,7 +1212,7 @@ struct Sweeper2 {
       st[ST_S2_LATE] = S.st[S2_LATE];
       st[ST_S2_PM] = S.st[S2_PM];
       st[ST_S2_DENSE] = S.st[S2_DENSE];
-      st[ST_S2_SPURIOUS] = S.wc_resumed;     // columns the commit loop had to resume (their tentative pivot was owned)
+      st[ST_S2_SPURIOUS] = S.wc_resumed;     // columns reduced further after they were displaced from their pivot
       st[ST_S2_UNDONE] = S.wc_big;           // columns handed to the cluster engine
       st[ST_SPARE0] = (unsigned long long)cyc_sync;
       st[ST_SPARE1] = n_sync;

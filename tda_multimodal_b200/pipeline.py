@@ -62,7 +62,8 @@ def layer_sweep(X, n_neighbors=15, n_components=3, min_dist=0.1, metric="cosine"
     cur = torch.cuda.current_stream(dev)
     bounds = [(Lc * c) // chunks for c in range(chunks + 1)]
     streams = _sweep_streams(dev, chunks)
-    Ys, jobs = [], []
+    Ys, jobs, checks, Xcs = [], [], [], []
+    kw = dict(n_neighbors=n_neighbors, n_components=n_components, metric=metric, min_dist=min_dist, random_state=random_state, n_epochs=n_epochs)
     for c in range(chunks):
         st = streams[c]
         st.wait_stream(cur)
@@ -72,13 +73,22 @@ def layer_sweep(X, n_neighbors=15, n_components=3, min_dist=0.1, metric="cosine"
                 Xc = Xc.to(device=dev, dtype=torch.float32, non_blocking=True)
             else:
                 Xc.record_stream(st)
-            Y = umap_fit_batch(Xc, n_neighbors=n_neighbors, n_components=n_components, metric=metric, min_dist=min_dist,
-                               random_state=random_state, n_epochs=n_epochs)
+            # nothing below synchronises with the device: every chunk's whole chain is enqueued before the first result is awaited
+            # (the spectral initialisation assumes connected graphs; `ncomp` is checked after the sweep)
+            Y, ncomp = umap_fit_batch(Xc, defer_component_check=True, **kw)
             jobs.append(rips_batch_launch(pdist_lowdim(Y), maxdim=maxdim))
             Ys.append(Y)
+            checks.append(ncomp)
+            Xcs.append(Xc)
     res = []
-    for job in jobs:
-        res += job.finish()
+    for c, job in enumerate(jobs):
+        r = job.finish()
+        if checks[c] is not None and int(checks[c].max().item()) > 1:   # some graph of this chunk is not connected: the exact path
+            with torch.cuda.stream(streams[c]):
+                Ys[c] = umap_fit_batch(Xcs[c], **kw)
+                r = rips_batch(pdist_lowdim(Ys[c]), maxdim=maxdim)
+        res += r
+    del Xcs
     for st in streams[:chunks]:
         cur.wait_stream(st)
     Yall = None

@@ -123,8 +123,11 @@ def _component_meta_layout(Xp, comp, ncomp, dim, metric, torch):
     return emb.to(torch.float32)
 
 
-def spectral_init(X, head, tail, weight, eps, n, dim, seed, metric):
-    """spectral_layout / multi_component_layout.  Returns Y [B,n,dim] (not yet noisy-scaled)."""
+def spectral_init(X, head, tail, weight, eps, n, dim, seed, metric, speculate_connected=False):
+    """spectral_layout / multi_component_layout.  Returns Y [B,n,dim] (not yet noisy-scaled).
+    speculate_connected=True: no host synchronisation -- the eigenvectors are computed as if every graph were connected (the
+    usual case for n_neighbors = 15 on thousands of points) and (Y, ncomp) is returned; the caller checks `ncomp` (device
+    tensor [B]) when it synchronises anyway and repeats the fit without speculation if some graph was not connected."""
     torch = _lib.require_cuda()
     L = _lib.lib()
     B, slots = head.shape
@@ -138,6 +141,13 @@ def spectral_init(X, head, tail, weight, eps, n, dim, seed, metric):
     with torch.cuda.device(dev):
         _lib.check(L.tda_graph_components(_lib.ptr(head), _lib.ptr(tail), _lib.ptr(weight), _lib.ptr(eps), slots, n, B, _lib.ptr(comp),
                                           _lib.ptr(ncomp), _lib.ptr(csize), _lib.ptr(deg), _lib.ptr(ws0), 12 * B * n, _lib.stream_ptr()))
+        if speculate_connected:
+            ws_bytes = int(L.tda_spectral_workspace_bytes(n, B, 1, slots))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            _lib.check(L.tda_spectral_embed(_lib.ptr(head), _lib.ptr(tail), _lib.ptr(weight), _lib.ptr(eps), slots, n, dim, B, _lib.ptr(comp),
+                                            _lib.ptr(ncomp), _lib.ptr(csize), _lib.ptr(deg), 1, 1, int(seed), _lib.ptr(Y), None,
+                                            _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
+            return Y, ncomp
         ncomp_h = ncomp.cpu().numpy()
         maxcomp = int(ncomp_h.max())
         min_size = 1 if maxcomp == 1 else max(2 * dim, dim + 2)
@@ -178,10 +188,12 @@ def spectral_init(X, head, tail, weight, eps, n, dim, seed, metric):
 
 def umap_fit_batch(X, n_neighbors=15, n_components=2, metric="euclidean", n_epochs=None, learning_rate=1.0, init="spectral",
                    min_dist=0.1, spread=1.0, set_op_mix_ratio=1.0, local_connectivity=1.0, repulsion_strength=1.0,
-                   negative_sample_rate=5, random_state=None, a=None, b=None, return_state=False, knn=None):
+                   negative_sample_rate=5, random_state=None, a=None, b=None, return_state=False, knn=None, defer_component_check=False):
     """fit_transform of B clouds at once.  X [B,n,d] float32 CUDA tensor -> embedding [B,n,n_components] (CUDA).
     `knn` = (idx [B,n,k] int32, dist, sigma, rho) skips the distance / kNN stages (e.g. the row-sharded exact kNN of
-    pipeline.knn_row_sharded for clouds whose distance matrix should not be materialised on one GPU)."""
+    pipeline.knn_row_sharded for clouds whose distance matrix should not be materialised on one GPU).
+    defer_component_check=True (spectral init only): the call never synchronises with the device; it returns (Y, ncomp) and the
+    caller must repeat the fit with the default setting if ncomp.max() > 1 (see spectral_init)."""
     torch = _lib.require_cuda()
     L = _lib.lib()
     assert X.is_cuda and X.dim() == 3
@@ -207,7 +219,11 @@ def umap_fit_batch(X, n_neighbors=15, n_components=2, metric="euclidean", n_epoc
     head, tail, weight, eps = fuzzy_graph(idx, dist, sigma, rho, n_ep if n_ep > 10 else (500 if n <= 10000 else 200), set_op_mix_ratio)
     with torch.cuda.device(dev):
         if isinstance(init, str) and init == "spectral":
-            Y = spectral_init(X, head, tail, weight, eps, n, n_components, seed, metric)
+            ncomp_dev = None
+            if defer_component_check:
+                Y, ncomp_dev = spectral_init(X, head, tail, weight, eps, n, n_components, seed, metric, speculate_connected=True)
+            else:
+                Y = spectral_init(X, head, tail, weight, eps, n, n_components, seed, metric)
             _lib.check(L.tda_umap_rescale(_lib.ptr(Y), n, n_components, B, 1e-4, seed + 1, _lib.stream_ptr()))
         elif isinstance(init, str) and init == "random":
             Y = torch.empty((B, n, n_components), dtype=torch.float32, device=dev)
@@ -225,6 +241,8 @@ def umap_fit_batch(X, n_neighbors=15, n_components=2, metric="euclidean", n_epoc
     if return_state:
         return Y, {"knn_indices": idx, "knn_dists": dist, "sigmas": sigma, "rhos": rho, "head": head, "tail": tail, "weight": weight,
                    "eps": eps, "a": a, "b": b, "n_neighbors": k, "n_epochs": n_ep, "init": init_embedding, "seed": seed}
+    if defer_component_check:
+        return Y, (ncomp_dev if (isinstance(init, str) and init == "spectral") else None)
     return Y
 
 
