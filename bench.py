@@ -380,15 +380,18 @@ def run_b200(a):
             full += pipeline.unpack_diagrams(gc[r][:nc].cpu().numpy(), gp[r][:npay].cpu().numpy())
         return full
 
-    def timed(fn, steps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    each = {}
+
+    def timed(fn, steps, tag):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
         barrier()
-        e0.record()
-        for _ in range(steps):
+        evs[0].record()
+        for k in range(steps):
             res = fn()
-        e1.record()
+            evs[k + 1].record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        ms = torch.tensor([evs[0].elapsed_time(evs[-1])], dtype=torch.float64, device=dev)
+        each[tag] = [round(evs[k].elapsed_time(evs[k + 1]), 2) for k in range(steps)]
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), res
@@ -401,12 +404,12 @@ def run_b200(a):
     L.tda_launch_count_reset()
     L.tda_stage_timing_reset()
     L.tda_stage_timing_enable(1)
-    ms_res, dgms = timed(step_resident, a.steps)
+    ms_res, dgms = timed(step_resident, a.steps, "resident")
     launches = int(L.tda_launch_count())
     stages = _lib.stage_times()
     timeline = _lib.stage_timeline()
     L.tda_stage_timing_enable(0)
-    ms_e2e, (dg2, out2) = timed(step_e2e, a.steps)
+    ms_e2e, (dg2, out2) = timed(step_e2e, a.steps, "e2e")
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
@@ -532,7 +535,7 @@ def run_b200(a):
                 "data": "synthetic", "config": workload_config(a, world),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nl * a.points * a.dim * 4), "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / a.steps},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
+                "gpu_launches": launches, "clocks": clocks, "ms_each_step_rank0": each, "roofline": roofline}
         if dgms is not None:
             line["diagram_sets_gathered_per_step"] = len(dgms)
         if world == 1 and not a.no_cpu_baseline:

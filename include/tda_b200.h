@@ -42,7 +42,8 @@ void tda_launch_count_reset(void);
  *   rips_warp_engine (1): sweep2 reduces every column by a single warp first (speculatively, committed in ripser's order); 0: windows only
  *   sgd_mode (0): 0 deterministic SGD (thread-block cluster per cloud for fit, warp per point for transform; bit-reproducible
  *                 for a given seed), 3 per-epoch kernels with float atomics (used anyway for n > 8192 or n_components != 3)
- *   sgd_cluster (4): CTAs per cloud of the deterministic fit kernel;  sweep_exclusive (0), knn_loads (8), debug_sync (0),
+ *   sgd_cluster (4): CTAs per cloud of the deterministic fit kernel;  spectral_cluster (8): CTAs per cloud of the Lanczos kernel
+ *   for connected graphs (0: always the one-CTA-per-component kernel);  sweep_exclusive (0), knn_loads (8), debug_sync (0),
  *   h2_stats (0) */
 int tda_set_option(const char* name, long long value);
 long long tda_get_option(const char* name);
@@ -131,6 +132,15 @@ int tda_umap_transform_init(const int32_t* knn_idx, const float* knn_dist, const
  *   rows of Y [batch,n,dim]; evals [batch,maxcomp,4] (eigenvalues of D^-1/2 W D^-1/2) or NULL.
  */
 size_t tda_spectral_workspace_bytes(int n, int batch, int maxcomp, int slots);
+/* tda_spectral_init: components + eigenvectors + multi_component_layout in one call WITHOUT a host round trip: connected clouds go
+ *   to a thread-block-cluster Lanczos kernel, clouds with 2..min(maxcomp, 2*dim) components to the per-component kernel and the
+ *   +-e_k meta layout of umap-learn's multi_component_layout; ncomp_out [batch] = number of components, status_out [batch] = 0 done,
+ *   1 = more components than that (the caller lays those clouds out through tda_graph_components / tda_spectral_embed and its own
+ *   component_layout).  Y [batch,n,dim] is overwritten. */
+size_t tda_spectral_init_workspace_bytes(int n, int batch, int maxcomp, int slots);
+int tda_spectral_init(const int32_t* head, const int32_t* tail, const float* weight, const float* eps, int slots, int n, int dim,
+                      int batch, int maxcomp, uint64_t seed, float* Y, int32_t* ncomp_out, int32_t* status_out, void* ws, size_t ws_bytes,
+                      void* stream);
 int tda_graph_components(const int32_t* head, const int32_t* tail, const float* weight, const float* eps, int slots, int n, int batch,
                          int32_t* comp, int32_t* ncomp, int32_t* comp_size, float* degree, void* ws, size_t ws_bytes, void* stream);
 int tda_spectral_embed(const int32_t* head, const int32_t* tail, const float* weight, const float* eps, int slots, int n, int dim,
@@ -191,6 +201,13 @@ int tda_rips_launch(const float* dm, int n, int batch, int maxdim, float thresh,
 size_t tda_rips_h2_workspace_bytes(int n, int batch, int cap2, size_t pool_bytes, size_t far_bytes);
 int tda_rips_h2(const void* ws1, int n, int batch, int cap1, size_t pool_bytes1, float* h2_pairs, int cap2, int32_t* counts2,
                 void* ws2, size_t ws2_bytes, size_t pool_bytes2, size_t far_bytes, void* stream);
+/* tda_greedy_perm: furthest-point landmark selection with ripser.py's `n_perm` semantics (ripser(X, n_perm=...): start at point 0,
+ * lowest index on ties), one launch of one thread-block cluster.  X = points [n,d] float32 (is_matrix = 0, euclidean, d <= 16) or a
+ * distance matrix [n,n] (is_matrix = 1); idx_out [n_perm] int32; lambda_out [n_perm] float32 (lambda_out[n_perm-1] = r_cover);
+ * ws: tda_greedy_perm_workspace_bytes(n) (only used when a CTA's share of the minimum distances does not fit in shared memory). */
+size_t tda_greedy_perm_workspace_bytes(int n);
+int tda_greedy_perm(const float* X, int n, int d, int n_perm, int is_matrix, int32_t* idx_out, float* lambda_out, void* ws, size_t ws_bytes,
+                    void* stream);
 /* device statistics of the last tda_rips call on this workspace: [batch, TDA_RIPS_STATS] int64.  For the default reducer (sweep2):
  *  0 columns (non-MST edges <= thresh), 1 apparent pairs, 2 reduced columns, 3 column additions (flips kept + reduced columns
  *  added), 4 rows substituted, 5 non-apparent pivots (events + deaths), 6 windows, 7 largest |V|, 8..13 SM cycles of CTA

@@ -34,11 +34,16 @@ PROTOTYPES = {
     "tda_umap_transform_init": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tda_spectral_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "tda_spectral_init_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "tda_spectral_init": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.c_uint64, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_size_t, c_void_p]),
     "tda_graph_components": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_size_t, c_void_p]),
     "tda_spectral_embed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_int, c_int, ctypes.c_uint64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tda_silhouette": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tda_greedy_perm_workspace_bytes": (c_size_t, [c_int]),
+    "tda_greedy_perm": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tda_rips_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_size_t]),
     "tda_rips": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                          c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]),
@@ -60,7 +65,7 @@ _ENV_OPTIONS = {
     "TDA_RIPS_W0": ("rips_w0", int), "TDA_RIPS_WSPARSE": ("rips_wsparse", int), "TDA_RIPS_WMAX": ("rips_wmax", int),
     "TDA_RIPS_DENSE_MIN": ("rips_dense_min", int), "TDA_RIPS_DENSE_DIV": ("rips_dense_div", int),
     "TDA_RIPS_CLUSTER": ("rips_cluster", int), "TDA_RIPS_WARP_ENGINE": ("rips_warp_engine", int), "TDA_SWEEP_EXCLUSIVE": ("sweep_exclusive", int),
-    "TDA_SGD_MODE": ("sgd_mode", int), "TDA_SGD_CLUSTER": ("sgd_cluster", int),
+    "TDA_SGD_MODE": ("sgd_mode", int), "TDA_SGD_CLUSTER": ("sgd_cluster", int), "TDA_SPECTRAL_CLUSTER": ("spectral_cluster", int),
     "TDA_KNN_LOADS": ("knn_loads", int), "TDA_DEBUG_SYNC": ("debug_sync", lambda v: 1), "TDA_H2_STATS": ("h2_stats", lambda v: 1),
 }
 

@@ -17,6 +17,7 @@
 #include "launch_count.cuh"
 #include "../../include/tda_b200.h"
 #include <cmath>
+#include <cstring>
 
 namespace tda {
 namespace spectral {
@@ -101,6 +102,105 @@ __device__ __forceinline__ uint32_t hash32(uint64_t x) {
   return (uint32_t)x;
 }
 
+// eigenpairs of the meff x meff tridiagonal T (alpha diagonal, beta off-diagonal), the `dim` largest: Sturm-sequence multisection
+// per eigenvalue (one warp each), inverse iteration (one thread each), Gram-Schmidt between the Ritz coefficient vectors.
+// All threads of the CTA call; returns nev.  (Deterministic: CTAs that call it with equal inputs get equal outputs.)
+__device__ __forceinline__ int tridiag_eigs(int meff, int dim, const double* s_alpha, const double* s_beta, double* s_lam,
+                                            double (*s_vec)[kMaxKrylov], int tid, int lane, int warp) {
+  const int nev = min(dim, meff);
+  if (warp < nev) {
+    // Gershgorin bounds
+    double lo = 1e300, hi = -1e300;
+    for (int i = 0; i < meff; ++i) {
+      const double r = (i > 0 ? fabs(s_beta[i - 1]) : 0.0) + (i < meff - 1 ? fabs(s_beta[i]) : 0.0);
+      lo = fmin(lo, s_alpha[i] - r); hi = fmax(hi, s_alpha[i] + r);
+    }
+    const int want = meff - 1 - warp;  // index (ascending) of the eigenvalue this warp looks for
+    for (int round = 0; round < 14; ++round) {
+      const double x = lo + (hi - lo) * (double)(lane + 1) / 33.0;
+      int cnt = 0;  // number of eigenvalues < x (Sturm sequence)
+      double d = 1.0;
+      for (int i = 0; i < meff; ++i) {
+        const double b2 = i > 0 ? s_beta[i - 1] * s_beta[i - 1] : 0.0;
+        d = s_alpha[i] - x - (i > 0 ? b2 / d : 0.0);
+        if (fabs(d) < 1e-300) d = -1e-300;
+        if (d < 0.0) ++cnt;
+      }
+      // eigenvalue `want` lies in (x_l, x_{l+1}] where l = last lane with cnt <= want
+      const unsigned below = __ballot_sync(0xffffffffu, cnt <= want);
+      const int nb = __popc(below);  // lanes 0..nb-1 have cnt <= want (monotone)
+      const double step = (hi - lo) / 33.0;
+      const double nlo = lo + step * nb, nhi = lo + step * (nb + 1);
+      lo = nlo; hi = nhi;
+    }
+    if (lane == 0) s_lam[warp] = 0.5 * (lo + hi);
+  }
+  __syncthreads();
+  if (tid < nev) {
+    // inverse iteration on (T - lam I) with a tiny shift; tridiagonal LU with partial pivoting, 3 sweeps
+    const double lam = s_lam[tid] + 1e-9 * (1.0 + fabs(s_lam[tid])) * (tid + 1);
+    double* y = s_vec[tid];
+    for (int i = 0; i < meff; ++i) y[i] = 1.0 + 0.01 * ((i * 37 + tid * 11) % 17);
+    double dl[kMaxKrylov], dd[kMaxKrylov], du[kMaxKrylov], du2[kMaxKrylov];
+    unsigned char piv[kMaxKrylov];
+    for (int sweep = 0; sweep < 3; ++sweep) {
+      for (int i = 0; i < meff; ++i) {
+        dd[i] = s_alpha[i] - lam;
+        du[i] = i < meff - 1 ? s_beta[i] : 0.0;
+        dl[i] = i < meff - 1 ? s_beta[i] : 0.0;
+        du2[i] = 0.0;
+      }
+      for (int i = 0; i < meff - 1; ++i) {
+        if (fabs(dd[i]) >= fabs(dl[i])) {
+          piv[i] = 0;
+          if (dd[i] == 0.0) dd[i] = 1e-300;
+          const double f = dl[i] / dd[i];
+          dl[i] = f;
+          dd[i + 1] -= f * du[i];
+        } else {
+          piv[i] = 1;
+          const double f = dd[i] / dl[i];
+          dd[i] = dl[i];
+          dl[i] = f;
+          const double t = du[i];
+          du[i] = dd[i + 1];
+          dd[i + 1] = t - f * du[i];
+          du2[i] = du[i + 1];
+          du[i + 1] = -f * du2[i];
+        }
+      }
+      if (dd[meff - 1] == 0.0) dd[meff - 1] = 1e-300;
+      for (int i = 0; i < meff - 1; ++i) {
+        if (piv[i]) { const double t = y[i]; y[i] = y[i + 1]; y[i + 1] = t - dl[i] * y[i]; }
+        else y[i + 1] -= dl[i] * y[i];
+      }
+      y[meff - 1] /= dd[meff - 1];
+      if (meff > 1) y[meff - 2] = (y[meff - 2] - du[meff - 2] * y[meff - 1]) / dd[meff - 2];
+      for (int i = meff - 3; i >= 0; --i) y[i] = (y[i] - du[i] * y[i + 1] - du2[i] * y[i + 2]) / dd[i];
+      double nn = 0.0;
+      for (int i = 0; i < meff; ++i) nn += y[i] * y[i];
+      nn = 1.0 / sqrt(nn);
+      for (int i = 0; i < meff; ++i) y[i] *= nn;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {  // Gram-Schmidt between the few Ritz coefficient vectors (clustered eigenvalues)
+    for (int a = 0; a < nev; ++a) {
+      for (int b = 0; b < a; ++b) {
+        double dot = 0.0;
+        for (int i = 0; i < meff; ++i) dot += s_vec[a][i] * s_vec[b][i];
+        for (int i = 0; i < meff; ++i) s_vec[a][i] -= dot * s_vec[b][i];
+      }
+      double nn = 0.0;
+      for (int i = 0; i < meff; ++i) nn += s_vec[a][i] * s_vec[a][i];
+      nn = nn > 0.0 ? 1.0 / sqrt(nn) : 0.0;
+      for (int i = 0; i < meff; ++i) s_vec[a][i] *= nn;
+    }
+  }
+  __syncthreads();
+  return nev;
+}
+
 struct LanczosParams {
   const int* head; const int* tail; const float* weight; const float* eps; int slots; int n; int dim;
   const int* comp; const float* deg; const int* ncomp; const int* csize;
@@ -111,9 +211,17 @@ struct LanczosParams {
   int* ent_count;  // [batch]         segment allocation cursor
   unsigned long long* wfix;   // [batch, maxcomp, n]  sparse matrix-vector product accumulated in 2^-40 fixed point (order independent)
   int maxcomp; int min_size; uint64_t seed;
+  int skip_connected;   // 1: clouds with one component are left to the cluster kernel
 };
 
-__global__ void __launch_bounds__(kLanczosThreads) lanczos_kernel(LanczosParams P) {
+__device__ __forceinline__ void lanczos_body(const LanczosParams& P);
+__global__ void __launch_bounds__(kLanczosThreads) lanczos_kernel(LanczosParams P) { lanczos_body(P); }
+// the same with the minimum component size applied only to clouds with several components (a connected cloud is always laid out)
+__global__ void __launch_bounds__(kLanczosThreads) lanczos_kernel_ms(LanczosParams P, int min_size_multi) {
+  if (P.ncomp[blockIdx.y] > 1) P.min_size = min_size_multi;
+  lanczos_body(P);
+}
+__device__ __forceinline__ void lanczos_body(const LanczosParams& P) {
   __shared__ double s_alpha[kMaxKrylov], s_beta[kMaxKrylov];
   __shared__ float s_coef[kMaxKrylov + 2];
   __shared__ float s_red[kLanczosThreads / 32];
@@ -121,7 +229,7 @@ __global__ void __launch_bounds__(kLanczosThreads) lanczos_kernel(LanczosParams 
   __shared__ double s_vec[kMaxDim][kMaxKrylov];
   __shared__ int s_m, s_base, s_cursor;
   const int p = blockIdx.y, c = blockIdx.x;
-  if (c >= P.ncomp[p]) return;
+  if (c >= P.ncomp[p] || (P.skip_connected && P.ncomp[p] == 1)) return;
   const int n = P.n, dim = P.dim;
   const int nc = P.csize[(size_t)p * n + c];
   if (nc < P.min_size) return;  // tiny components are placed at random by the host
@@ -252,96 +360,9 @@ __global__ void __launch_bounds__(kLanczosThreads) lanczos_kernel(LanczosParams 
     __syncthreads();
   }
   __syncthreads();
-  // ---- eigenpairs of the meff x meff tridiagonal T (alpha diagonal, beta off-diagonal), `dim` largest
-  const int nev = min(dim, meff);
-  if (warp < nev) {
-    // Gershgorin bounds
-    double lo = 1e300, hi = -1e300;
-    for (int i = 0; i < meff; ++i) {
-      const double r = (i > 0 ? fabs(s_beta[i - 1]) : 0.0) + (i < meff - 1 ? fabs(s_beta[i]) : 0.0);
-      lo = fmin(lo, s_alpha[i] - r); hi = fmax(hi, s_alpha[i] + r);
-    }
-    const int want = meff - 1 - warp;  // index (ascending) of the eigenvalue this warp looks for
-    for (int round = 0; round < 14; ++round) {
-      const double x = lo + (hi - lo) * (double)(lane + 1) / 33.0;
-      int cnt = 0;  // number of eigenvalues < x (Sturm sequence)
-      double d = 1.0;
-      for (int i = 0; i < meff; ++i) {
-        const double b2 = i > 0 ? s_beta[i - 1] * s_beta[i - 1] : 0.0;
-        d = s_alpha[i] - x - (i > 0 ? b2 / d : 0.0);
-        if (fabs(d) < 1e-300) d = -1e-300;
-        if (d < 0.0) ++cnt;
-      }
-      // eigenvalue `want` lies in (x_l, x_{l+1}] where l = last lane with cnt <= want
-      const unsigned below = __ballot_sync(0xffffffffu, cnt <= want);
-      const int nb = __popc(below);  // lanes 0..nb-1 have cnt <= want (monotone)
-      const double step = (hi - lo) / 33.0;
-      const double nlo = lo + step * nb, nhi = lo + step * (nb + 1);
-      lo = nlo; hi = nhi;
-    }
-    if (lane == 0) s_lam[warp] = 0.5 * (lo + hi);
-  }
-  __syncthreads();
-  if (tid < nev) {
-    // inverse iteration on (T - lam I) with a tiny shift; tridiagonal LU with partial pivoting, 3 sweeps
-    const double lam = s_lam[tid] + 1e-9 * (1.0 + fabs(s_lam[tid])) * (tid + 1);
-    double* y = s_vec[tid];
-    for (int i = 0; i < meff; ++i) y[i] = 1.0 + 0.01 * ((i * 37 + tid * 11) % 17);
-    double dl[kMaxKrylov], dd[kMaxKrylov], du[kMaxKrylov], du2[kMaxKrylov];
-    unsigned char piv[kMaxKrylov];
-    for (int sweep = 0; sweep < 3; ++sweep) {
-      for (int i = 0; i < meff; ++i) {
-        dd[i] = s_alpha[i] - lam;
-        du[i] = i < meff - 1 ? s_beta[i] : 0.0;
-        dl[i] = i < meff - 1 ? s_beta[i] : 0.0;
-        du2[i] = 0.0;
-      }
-      for (int i = 0; i < meff - 1; ++i) {
-        if (fabs(dd[i]) >= fabs(dl[i])) {
-          piv[i] = 0;
-          if (dd[i] == 0.0) dd[i] = 1e-300;
-          const double f = dl[i] / dd[i];
-          dl[i] = f;
-          dd[i + 1] -= f * du[i];
-        } else {
-          piv[i] = 1;
-          const double f = dd[i] / dl[i];
-          dd[i] = dl[i];
-          dl[i] = f;
-          const double t = du[i];
-          du[i] = dd[i + 1];
-          dd[i + 1] = t - f * du[i];
-          du2[i] = du[i + 1];
-          du[i + 1] = -f * du2[i];
-        }
-      }
-      if (dd[meff - 1] == 0.0) dd[meff - 1] = 1e-300;
-      for (int i = 0; i < meff - 1; ++i) {
-        if (piv[i]) { const double t = y[i]; y[i] = y[i + 1]; y[i + 1] = t - dl[i] * y[i]; }
-        else y[i + 1] -= dl[i] * y[i];
-      }
-      y[meff - 1] /= dd[meff - 1];
-      if (meff > 1) y[meff - 2] = (y[meff - 2] - du[meff - 2] * y[meff - 1]) / dd[meff - 2];
-      for (int i = meff - 3; i >= 0; --i) y[i] = (y[i] - du[i] * y[i + 1] - du2[i] * y[i + 2]) / dd[i];
-      double nn = 0.0;
-      for (int i = 0; i < meff; ++i) nn += y[i] * y[i];
-      nn = 1.0 / sqrt(nn);
-      for (int i = 0; i < meff; ++i) y[i] *= nn;
-    }
-  }
-  __syncthreads();
-  if (tid == 0) {  // Gram-Schmidt between the few Ritz coefficient vectors (clustered eigenvalues)
-    for (int a = 0; a < nev; ++a) {
-      for (int b = 0; b < a; ++b) {
-        double dot = 0.0;
-        for (int i = 0; i < meff; ++i) dot += s_vec[a][i] * s_vec[b][i];
-        for (int i = 0; i < meff; ++i) s_vec[a][i] -= dot * s_vec[b][i];
-      }
-      double nn = 0.0;
-      for (int i = 0; i < meff; ++i) nn += s_vec[a][i] * s_vec[a][i];
-      nn = nn > 0.0 ? 1.0 / sqrt(nn) : 0.0;
-      for (int i = 0; i < meff; ++i) s_vec[a][i] *= nn;
-    }
+  // ---- eigenpairs of the tridiagonal matrix
+  const int nev = tridiag_eigs(meff, dim, s_alpha, s_beta, s_lam, s_vec, tid, lane, warp);
+  if (tid == 0) {
     for (int a = 0; a < kMaxDim; ++a) P.evals[((size_t)p * P.maxcomp + c) * kMaxDim + a] = a < nev ? (float)s_lam[a] : 0.f;
     s_m = meff;
   }
@@ -361,13 +382,331 @@ __global__ void __launch_bounds__(kLanczosThreads) lanczos_kernel(LanczosParams 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Lanczos for CONNECTED graphs on a thread-block cluster (the usual case: one component = the whole cloud).  The vertex rows are
+// split over the C CTAs of a cluster; each CTA keeps its rows of ALL Krylov vectors and its rows of the matrix (CSR, sorted by
+// column: the products are summed in a fixed order, so the result is reproducible) in shared memory, plus the whole current
+// Lanczos vector.  Scalar products are reduced through distributed shared memory: every CTA writes its partial sums into every
+// CTA's table and, after one cluster barrier, adds them up in rank order (same bits everywhere).  Four cluster barriers per
+// Lanczos step instead of ~100 L2 round trips per thread.
+constexpr int kLcThreads = 512;
+constexpr int kLcMaxCluster = 8;
+__device__ __forceinline__ uint32_t lc_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t lc_size() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void lc_sync() { asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+template <typename T>
+__device__ __forceinline__ T* lc_map(T* p, uint32_t rank) {
+  uint64_t out;
+  asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"((uint64_t)p), "r"(rank));
+  return reinterpret_cast<T*>(out);
+}
+struct LanczosClusterParams {
+  const int* head; const int* tail; const float* weight; const float* eps; int slots; int n; int dim;
+  const float* deg; float* out; float* evals; uint64_t seed;
+  int rows_per; int ent_cap;   // rows of a CTA (ceil(n / C)), entries of its CSR slice that fit in shared memory
+  const int* ncomp;            // optional [batch] with comp [batch,n], csize [batch,n]: component blockIdx.y of every cloud is laid out
+  const int* comp; const int* csize; int min_size_multi;   // (components smaller than min_size_multi of a multi-component cloud are skipped)
+  int2* gent;                  // [batch, C, slots] global room for a CSR slice that does not fit in shared memory (rare: hubs)
+};
+// dynamic shared memory: Qloc[(kMaxKrylov + 2) * rows_per] | qfull[n] | w[rows_per] | part[3][C][kMaxKrylov + 2] | coef[kMaxKrylov + 2]
+//                        | roff[rows_per + 1] | rcnt[rows_per] | ent[ent_cap] (int2: column, value bits)
+__global__ void __launch_bounds__(kLcThreads, 1) lanczos_cluster_kernel(LanczosClusterParams P) {
+  extern __shared__ __align__(16) unsigned char lc_raw[];
+  __shared__ double s_alpha[kMaxKrylov], s_beta[kMaxKrylov];
+  __shared__ double s_lam[kMaxDim];
+  __shared__ double s_vec[kMaxDim][kMaxKrylov];
+  __shared__ float s_red[kLcThreads / 32];
+  __shared__ int s_cnt;
+  const uint32_t C = lc_size(), cr = lc_rank();
+  const int p = blockIdx.x / (int)C;
+  const int c = blockIdx.y;   // component of the cloud (0 when the caller knows the graphs are connected)
+  const int nfull = P.n, dim = P.dim, RP = P.rows_per;
+  int n = nfull;              // vertices of the component = size of the problem
+  if (P.ncomp) {
+    const int ncp = P.ncomp[p];
+    if (c >= ncp) return;     // (the whole cluster leaves together)
+    n = P.csize[(size_t)p * nfull + c];
+    if (ncp > 1 && n < P.min_size_multi) return;
+  } else if (c > 0) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kLcThreads / 32;
+  const int rp = (n + (int)C - 1) / (int)C;   // rows per CTA of THIS component (<= RP, the allocation)
+  const int r0 = min(n, (int)cr * rp), r1 = min(n, r0 + rp), nr = r1 - r0;
+  constexpr int NV = kMaxKrylov + 2;
+  float* Qloc = reinterpret_cast<float*>(lc_raw);
+  float* qfull = Qloc + (size_t)NV * RP;
+  float* w = qfull + nfull;
+  float* part = w + RP;                       // [3][kLcMaxCluster][NV]
+  float* coef = part + 3 * kLcMaxCluster * NV;
+  int* roff = reinterpret_cast<int*>(coef + NV);
+  int* rcnt = roff + RP + 1;
+  int* lidx = rcnt + RP;                      // [nfull] vertex -> index inside the component (-1 outside)
+  int* glob = lidx + nfull;                   // [RP] this CTA's rows -> vertex
+  int2* ent = reinterpret_cast<int2*>((reinterpret_cast<uintptr_t>(glob + RP) + 7) & ~(uintptr_t)7);
+  const int* head = P.head + (size_t)p * P.slots;
+  const int* tail = P.tail + (size_t)p * P.slots;
+  const float* weight = P.weight + (size_t)p * P.slots;
+  const float* eps = P.eps + (size_t)p * P.slots;
+  const float* deg = P.deg + (size_t)p * nfull;
+  const int m = min(kMaxKrylov, n - 1);
+  // vertex -> index inside the component (order preserving), and the vertices of this CTA's rows
+  if (P.ncomp) {
+    const int* comp = P.comp + (size_t)p * nfull;
+    __shared__ int s_carry;
+    __shared__ int s_wsum[kLcThreads / 32];
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nfull; b0 += kLcThreads) {
+      const int i = b0 + tid;
+      const bool in = i < nfull && comp[i] == c;
+      const unsigned bal = __ballot_sync(0xffffffffu, in);
+      if (lane == 0) s_wsum[warp] = __popc(bal);
+      __syncthreads();
+      int off = s_carry;
+      for (int q = 0; q < warp; ++q) off += s_wsum[q];
+      if (i < nfull) lidx[i] = in ? off + __popc(bal & ((1u << lane) - 1)) : -1;
+      __syncthreads();
+      if (tid == 0) { int t = 0; for (int q = 0; q < nwarps; ++q) t += s_wsum[q]; s_carry += t; }
+      __syncthreads();
+    }
+  } else {
+    for (int i = tid; i < nfull; i += kLcThreads) lidx[i] = i;
+    __syncthreads();
+  }
+  for (int i = tid; i < nfull; i += kLcThreads) { const int l = lidx[i]; if (l >= r0 && l < r1) glob[l - r0] = i; }
+  __syncthreads();
+
+  auto block_sum = [&](float v) -> float {
+    v = warp_sum_f32(v);
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int q = 0; q < nwarps; ++q) t += s_red[q];
+    __syncthreads();
+    return t;
+  };
+  // cluster-wide sums of `cnt` values held in coef[0..cnt) as this CTA's partial sums: into coef[0..cnt), same bits in every CTA
+  int red_phase = 0;
+  auto cluster_reduce = [&](int cnt) {
+    float* mine = part + (size_t)red_phase * kLcMaxCluster * NV;
+    __syncthreads();
+    for (uint32_t r = 0; r < C; ++r) {
+      float* dst = lc_map(mine, r) + (size_t)cr * NV;
+      for (int v = tid; v < cnt; v += kLcThreads) dst[v] = coef[v];
+    }
+    lc_sync();
+    for (int v = tid; v < cnt; v += kLcThreads) {
+      float t = 0.f;
+      for (uint32_t r = 0; r < C; ++r) t += mine[(size_t)r * NV + v];
+      coef[v] = t;
+    }
+    __syncthreads();
+    red_phase = (red_phase + 1) % 3;
+  };
+  // every CTA's rows of a vector (local array `src`, nr entries) into every CTA's qfull
+  auto broadcast_rows = [&](const float* src) {
+    for (uint32_t r = 0; r < C; ++r) {
+      float* dst = lc_map(qfull, r) + r0;
+      for (int i = tid; i < nr; i += kLcThreads) dst[i] = src[i];
+    }
+    lc_sync();
+  };
+
+  // ---- this CTA's rows of A = D^-1/2 W D^-1/2 as CSR, columns ascending
+  for (int i = tid; i <= RP; i += kLcThreads) { roff[i] = 0; if (i < RP) rcnt[i] = 0; }
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  for (int e = tid; e < P.slots; e += kLcThreads) {
+    if (eps[e] > 0.f) { const int h = lidx[head[e]]; if (h >= r0 && h < r1) atomicAdd(&rcnt[h - r0], 1); }
+  }
+  __syncthreads();
+  if (tid == 0) { int acc = 0; for (int i = 0; i < nr; ++i) { roff[i] = acc; acc += rcnt[i]; } roff[nr] = acc; s_cnt = acc; }
+  __syncthreads();
+  const int nent = s_cnt;
+  if (nent > P.ent_cap) ent = P.gent + (((size_t)p * gridDim.y + c) * C + cr) * (size_t)P.slots;   // the slice lives in global memory instead
+  for (int i = tid; i < nr; i += kLcThreads) rcnt[i] = roff[i];
+  __syncthreads();
+  {
+    for (int e = tid; e < P.slots; e += kLcThreads) {
+      if (eps[e] > 0.f) {
+        const int hg = head[e], h = lidx[hg];
+        if (h >= r0 && h < r1) {
+          const int tg = tail[e];
+          const int pos = atomicAdd(&rcnt[h - r0], 1);
+          ent[pos] = make_int2(lidx[tg], __float_as_int(weight[e] * rsqrtf(deg[hg] * deg[tg])));
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < nr; i += kLcThreads) {   // the fill order depends on scheduling: sort every row by column
+      const int a0 = roff[i], a1 = roff[i + 1];
+      for (int q = a0 + 1; q < a1; ++q) {
+        const int2 x = ent[q];
+        int k = q - 1;
+        while (k >= a0 && ent[k].x > x.x) { ent[k + 1] = ent[k]; --k; }
+        ent[k + 1] = x;
+      }
+    }
+  }
+  __syncthreads();
+  lc_sync();   // every CTA of the cluster is up (its buffers may be written from now on)
+
+  // ---- u1 = D^1/2 1 normalised (vector 0), q_0 = random, orthogonal to u1, normalised (vector 1)
+  float* u1 = Qloc;
+  float* q0 = Qloc + RP;
+  {
+    float acc = 0.f;
+    for (int i = tid; i < nr; i += kLcThreads) { const float v = sqrtf(deg[glob[i]]); u1[i] = v; acc += v * v; }
+    const float s = block_sum(acc);
+    if (tid == 0) coef[0] = s;
+    cluster_reduce(1);
+    const float nrm = sqrtf(coef[0]);
+    __syncthreads();
+    acc = 0.f;
+    for (int i = tid; i < nr; i += kLcThreads) {
+      const float u = u1[i] / nrm;
+      u1[i] = u;
+      const float r = (float)(hash32(P.seed + ((uint64_t)p << 40) + (uint64_t)glob[i]) >> 8) * (1.f / 8388608.f) - 1.f;
+      q0[i] = r;
+      acc += r * u;
+    }
+    const float s2 = block_sum(acc);
+    if (tid == 0) coef[0] = s2;
+    cluster_reduce(1);
+    const float d0 = coef[0];
+    __syncthreads();
+    acc = 0.f;
+    for (int i = tid; i < nr; i += kLcThreads) { const float r = q0[i] - d0 * u1[i]; q0[i] = r; acc += r * r; }
+    const float s3 = block_sum(acc);
+    if (tid == 0) coef[0] = s3;
+    cluster_reduce(1);
+    const float nrm2 = sqrtf(coef[0]);
+    __syncthreads();
+    for (int i = tid; i < nr; i += kLcThreads) q0[i] /= nrm2;
+    __syncthreads();
+  }
+  int meff = m;
+  for (int j = 0; j < m; ++j) {
+    const float* qj = Qloc + (size_t)(j + 1) * RP;
+    float* wn = Qloc + (size_t)(j + 2) * RP;   // becomes q_{j+1}
+    broadcast_rows(qj);
+    // w = A q_j on this CTA's rows (one thread per row, entries in column order)
+    for (int i = tid; i < nr; i += kLcThreads) {
+      float acc = 0.f;
+      for (int q = roff[i]; q < roff[i + 1]; ++q) { const int2 E = ent[q]; acc += __int_as_float(E.y) * qfull[E.x]; }
+      w[i] = acc;
+    }
+    __syncthreads();
+    // classical Gram-Schmidt, twice, against u1 and q_0..q_j; the coefficient on q_j is alpha_j
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int v = warp; v <= j + 1; v += nwarps) {
+        const float* qv = Qloc + (size_t)v * RP;
+        float s0 = 0.f;
+        for (int i = lane; i < nr; i += 32) s0 += w[i] * qv[i];
+        s0 = warp_sum_f32(s0);
+        if (lane == 0) coef[v] = s0;
+      }
+      cluster_reduce(j + 2);
+      if (tid == 0) { if (pass == 0) s_alpha[j] = (double)coef[j + 1]; else s_alpha[j] += (double)coef[j + 1]; }
+      for (int i = tid; i < nr; i += kLcThreads) {
+        float v0 = w[i];
+        for (int t = 0; t <= j + 1; ++t) v0 -= coef[t] * Qloc[(size_t)t * RP + i];
+        w[i] = v0;
+      }
+      __syncthreads();
+    }
+    float a2 = 0.f;
+    for (int i = tid; i < nr; i += kLcThreads) a2 += w[i] * w[i];
+    const float sb = block_sum(a2);
+    if (tid == 0) coef[0] = sb;
+    cluster_reduce(1);
+    const float beta = sqrtf(coef[0]);
+    __syncthreads();
+    if (tid == 0) s_beta[j] = (double)beta;
+    if (beta < 1e-6f || j == m - 1) { meff = j + 1; break; }   // (same decision in every CTA: same bits)
+    for (int i = tid; i < nr; i += kLcThreads) wn[i] = w[i] / beta;
+    __syncthreads();
+  }
+  __syncthreads();
+  const int nev = tridiag_eigs(meff, dim, s_alpha, s_beta, s_lam, s_vec, tid, lane, warp);
+  if (cr == 0 && tid == 0 && P.evals)
+    for (int a = 0; a < kMaxDim; ++a) P.evals[((size_t)p * gridDim.y + c) * kMaxDim + a] = a < nev ? (float)s_lam[a] : 0.f;
+  float* out = P.out + (size_t)p * nfull * dim;
+  for (int i = tid; i < nr; i += kLcThreads) {
+    for (int a = 0; a < dim; ++a) {
+      float v = 0.f;
+      if (a < nev)
+        for (int t = 0; t < meff; ++t) v += (float)s_vec[a][t] * Qloc[(size_t)(t + 1) * RP + i];
+      else
+        v = ((float)(hash32(P.seed * 31 + (uint64_t)glob[i] * 7 + a) >> 8) * (1.f / 8388608.f) - 1.f) * 1e-3f;
+      out[(size_t)glob[i] * dim + a] = v;
+    }
+  }
+  lc_sync();   // nobody leaves while its shared memory may still be written
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi_component_layout (umap-learn spectral.py) for clouds with 2 .. 2*dim components, on the device: the components are placed
+// around the meta positions +-e_k, each scaled to half the distance to the nearest other meta position; components too small for
+// a spectral layout get uniform random points of that range.  One CTA per cloud.  status[p]: 0 done, 1 = more than 2*dim (or
+// `maxcomp`) components: the meta positions need component_layout (host path).
+__global__ void __launch_bounds__(256) multi_component_kernel(const int* __restrict__ comp_g, const int* __restrict__ ncomp_g, const int* __restrict__ csize_g,
+                                                              int n, int dim, int maxcomp, int min_size, uint64_t seed, float* __restrict__ Y_g,
+                                                              int* __restrict__ status) {
+  __shared__ float s_meta[2 * kMaxDim][kMaxDim];
+  __shared__ float s_range[2 * kMaxDim];
+  __shared__ unsigned int s_amax[2 * kMaxDim];
+  const int p = blockIdx.x, tid = threadIdx.x;
+  const int nc = ncomp_g[p];
+  if (tid == 0) status[p] = (nc > 2 * dim || nc > maxcomp) ? 1 : 0;
+  if (nc == 1 || nc > 2 * dim || nc > maxcomp) return;
+  const int* comp = comp_g + (size_t)p * n;
+  const int* csize = csize_g + (size_t)p * n;
+  float* Y = Y_g + (size_t)p * n * dim;
+  if (tid < nc) {
+    const int k = (nc + 1) / 2;
+    for (int a = 0; a < dim; ++a) s_meta[tid][a] = 0.f;
+    if (tid < k) s_meta[tid][tid] = 1.f; else s_meta[tid][tid - k] = -1.f;
+    s_amax[tid] = 0u;
+  }
+  __syncthreads();
+  if (tid < nc) {
+    float best = INFINITY;
+    for (int o = 0; o < nc; ++o) {
+      float d2 = 0.f;
+      for (int a = 0; a < dim; ++a) { const float t = s_meta[tid][a] - s_meta[o][a]; d2 += t * t; }
+      const float d = sqrtf(d2);
+      if (d > 0.f && d < best) best = d;
+    }
+    s_range[tid] = isfinite(best) ? best * 0.5f : 1.f;
+  }
+  for (int i = tid; i < n; i += blockDim.x) {
+    float m = 0.f;
+    for (int a = 0; a < dim; ++a) m = fmaxf(m, fabsf(Y[(size_t)i * dim + a]));
+    atomicMax(&s_amax[comp[i]], __float_as_uint(m));
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += blockDim.x) {
+    const int c = comp[i];
+    const float r = s_range[c];
+    if (csize[c] < min_size) {
+      for (int a = 0; a < dim; ++a) {
+        const float u = (float)(hash32(seed * 0x9E3779B97F4A7C15ull + ((uint64_t)p << 44) + ((uint64_t)i << 8) + (uint64_t)a + 7919ull) >> 8) * (1.f / 8388608.f) - 1.f;
+        Y[(size_t)i * dim + a] = u * r + s_meta[c][a];
+      }
+    } else {
+      const float sc = r / fmaxf(__uint_as_float(s_amax[c]), 1e-30f);
+      for (int a = 0; a < dim; ++a) Y[(size_t)i * dim + a] = Y[(size_t)i * dim + a] * sc + s_meta[c][a];
+    }
+  }
+}
+
 struct Layout {
   int *label, *comp, *ncomp, *csize;
   float *deg, *Q, *evals;
-  int4* entries; int* ent_count; unsigned long long* wfix;
+  int4* entries; int* ent_count; unsigned long long* wfix; int2* lc_ent;
   size_t total;
 };
-static Layout make_layout(void* ws, int n, int batch, int maxcomp, int slots) {
+static Layout make_layout(void* ws, int n, int batch, int maxcomp, int slots, bool cluster_room = false) {
   Layout L;
   Carver c(ws, ~size_t(0));
   L.label = c.take<int>((size_t)batch * n);
@@ -380,6 +719,7 @@ static Layout make_layout(void* ws, int n, int batch, int maxcomp, int slots) {
   L.entries = c.take<int4>((size_t)batch * (slots > 0 ? slots : 0));
   L.ent_count = c.take<int>(batch);
   L.wfix = c.take<unsigned long long>((size_t)batch * (maxcomp > 0 ? maxcomp : 0) * n);
+  L.lc_ent = c.take<int2>((maxcomp == 1 || cluster_room) ? (size_t)batch * (maxcomp > 0 ? maxcomp : 1) * kLcMaxCluster * (slots > 0 ? slots : 0) : 0);
   L.total = c.off;
   return L;
 }
@@ -389,6 +729,47 @@ static Layout make_layout(void* ws, int n, int batch, int maxcomp, int slots) {
 
 using namespace tda;
 using namespace tda::spectral;
+
+// launches lanczos_cluster_kernel for the clouds whose graph is connected (all of them if ncomp == nullptr).
+// Returns TDA_OK (launched), 1 (not applicable: option off / rows do not fit in shared memory), or an error code.
+static int launch_cluster_lanczos(const int32_t* head, const int32_t* tail, const float* weight, const float* eps, int slots, int n, int dim, int batch,
+                                  const float* degree, const int* ncomp, const int* comp, const int* csize, int maxcomp, int min_size_multi,
+                                  uint64_t seed, float* Y, float* evals, int2* gent, cudaStream_t stream) {
+  if (option("spectral_cluster") == 0 || n < 64) return 1;
+  int C = (int)option("spectral_cluster");
+  if (C != 2 && C != 4 && C != 8) C = 8;
+  const int RP = (n + C - 1) / C;
+  constexpr int NV = kMaxKrylov + 2;
+  const size_t fixed = sizeof(float) * ((size_t)NV * RP + (size_t)n + (size_t)RP + 3 * (size_t)kLcMaxCluster * NV + NV) +
+                       sizeof(int) * ((size_t)(RP + 1) + RP + (size_t)n + RP + 4);
+  const size_t smem_max = (size_t)220 * 1024;
+  const size_t want_ent = (size_t)slots / C + (size_t)slots / (2 * C) + 64;   // 1.5x the mean slice
+  if (fixed + 8 * 1024 >= smem_max) return 1;
+  size_t cap_ent = (smem_max - fixed) / sizeof(int2);
+  if (cap_ent > want_ent) cap_ent = want_ent;
+  const size_t dyn = fixed + cap_ent * sizeof(int2);
+  LanczosClusterParams Q;
+  Q.head = head; Q.tail = tail; Q.weight = weight; Q.eps = eps; Q.slots = slots; Q.n = n; Q.dim = dim;
+  Q.deg = degree; Q.out = Y; Q.evals = evals; Q.seed = seed; Q.rows_per = RP; Q.ent_cap = (int)cap_ent;
+  Q.gent = gent; Q.ncomp = ncomp; Q.comp = comp; Q.csize = csize; Q.min_size_multi = min_size_multi;
+  TDA_CUDA_CHECK(cudaFuncSetAttribute(lanczos_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(batch * C), (unsigned)(ncomp ? maxcomp : 1), 1);
+  cfg.blockDim = dim3(kLcThreads, 1, 1);
+  cfg.dynamicSmemBytes = dyn;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  StageScope st(STAGE_SPECTRAL, stream);
+  TDA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, lanczos_cluster_kernel, Q));
+  count_launch();
+  TDA_LAUNCH_CHECK();
+  return TDA_OK;
+}
 
 extern "C" size_t tda_spectral_workspace_bytes(int n, int batch, int maxcomp, int slots) {
   if (n <= 0 || batch <= 0 || maxcomp < 0 || slots < 0) return 0;
@@ -419,15 +800,71 @@ extern "C" int tda_spectral_embed(const int32_t* head, const int32_t* tail, cons
   if (dim < 1 || dim > kMaxDim) return set_error(TDA_ERR_UNSUPPORTED, "tda_spectral_embed: dim=%d (supported 1..%d)", dim, kMaxDim);
   Layout L = make_layout(ws, n, batch, maxcomp, slots);
   if (L.total > ws_bytes) return set_error(TDA_ERR_WORKSPACE, "tda_spectral_embed: workspace %zu < required %zu", ws_bytes, L.total);
+  // connected graphs (maxcomp == 1, one component holding every vertex): the cluster kernel, if the rows fit in shared memory.
+  // (The caller passes maxcomp = 1 either because it knows, or speculatively -- then it checks ncomp afterwards.)
+  if (maxcomp == 1) {
+    const int rc = launch_cluster_lanczos(head, tail, weight, eps, slots, n, dim, batch, degree, nullptr, nullptr, nullptr, 1, 0, seed, Y,
+                                          evals ? evals : L.evals, L.lc_ent, stream);
+    if (rc != 1) return rc;   // launched (TDA_OK) or failed; 1 = not applicable: the per-component kernel below
+  }
   TDA_CUDA_CHECK(cudaMemsetAsync(L.ent_count, 0, sizeof(int) * batch, stream));
   LanczosParams P;
   P.head = head; P.tail = tail; P.weight = weight; P.eps = eps; P.slots = slots; P.n = n; P.dim = dim;
   P.comp = comp; P.deg = degree; P.ncomp = ncomp; P.csize = comp_size;
-  P.Q = L.Q; P.entries = L.entries; P.ent_count = L.ent_count; P.wfix = L.wfix; P.out = Y; P.evals = evals ? evals : L.evals; P.maxcomp = maxcomp; P.min_size = min_size; P.seed = seed;
+  P.Q = L.Q; P.entries = L.entries; P.ent_count = L.ent_count; P.wfix = L.wfix; P.out = Y; P.evals = evals ? evals : L.evals; P.maxcomp = maxcomp; P.min_size = min_size; P.seed = seed; P.skip_connected = 0;
   dim3 grid(maxcomp, batch);
   StageScope st(STAGE_SPECTRAL, stream);
   lanczos_kernel<<<grid, kLanczosThreads, 0, stream>>>(P);
   count_launch();
   TDA_LAUNCH_CHECK();
+  return TDA_OK;
+}
+
+// ---- the whole spectral initialisation without a host round trip
+extern "C" size_t tda_spectral_init_workspace_bytes(int n, int batch, int maxcomp, int slots) {
+  if (n <= 0 || batch <= 0 || maxcomp <= 0 || slots < 0) return 0;
+  return make_layout(nullptr, n, batch, maxcomp, slots, true).total + 12 * (size_t)batch * n + 4096;
+}
+extern "C" int tda_spectral_init(const int32_t* head, const int32_t* tail, const float* weight, const float* eps, int slots, int n, int dim,
+                                 int batch, int maxcomp, uint64_t seed, float* Y, int32_t* ncomp_out, int32_t* status_out, void* ws,
+                                 size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!head || !tail || !weight || !eps || !Y || !ncomp_out || !status_out || !ws || n <= 0 || batch <= 0 || maxcomp <= 0)
+    return set_error(TDA_ERR_INVALID, "tda_spectral_init: bad arguments");
+  if (dim < 1 || dim > kMaxDim) return set_error(TDA_ERR_UNSUPPORTED, "tda_spectral_init: dim=%d (supported 1..%d)", dim, kMaxDim);
+  if (maxcomp > 2 * kMaxDim) maxcomp = 2 * kMaxDim;
+  Layout L = make_layout(ws, n, batch, maxcomp, slots, true);
+  const size_t need = L.total + 12 * (size_t)batch * n + 256;
+  if (need > ws_bytes) return set_error(TDA_ERR_WORKSPACE, "tda_spectral_init: workspace %zu < required %zu", ws_bytes, need);
+  unsigned long long* degfix = (unsigned long long*)((char*)ws + ((L.total + 255) & ~(size_t)255));
+  {
+    StageScope st(STAGE_SPECTRAL, stream);
+    components_kernel<<<batch, 1024, 0, stream>>>(head, tail, weight, eps, slots, n, L.label, degfix, L.comp, L.deg, ncomp_out, L.csize);
+    count_launch();
+    TDA_LAUNCH_CHECK();
+  }
+  TDA_CUDA_CHECK(cudaMemsetAsync(Y, 0, sizeof(float) * (size_t)batch * n * dim, stream));
+  // every component (up to maxcomp per cloud) by a thread-block cluster; if the rows do not fit in shared memory: one CTA each
+  const int min_size = 2 * dim > dim + 2 ? 2 * dim : dim + 2;
+  const int rc = launch_cluster_lanczos(head, tail, weight, eps, slots, n, dim, batch, L.deg, ncomp_out, L.comp, L.csize, maxcomp, min_size, seed, Y,
+                                        L.evals, L.lc_ent, stream);
+  if (rc < 0) return rc;
+  {
+    StageScope st(STAGE_SPECTRAL, stream);
+    if (rc != TDA_OK) {
+      TDA_CUDA_CHECK(cudaMemsetAsync(L.ent_count, 0, sizeof(int) * batch, stream));
+      LanczosParams P;
+      P.head = head; P.tail = tail; P.weight = weight; P.eps = eps; P.slots = slots; P.n = n; P.dim = dim;
+      P.comp = L.comp; P.deg = L.deg; P.ncomp = ncomp_out; P.csize = L.csize;
+      P.Q = L.Q; P.entries = L.entries; P.ent_count = L.ent_count; P.wfix = L.wfix; P.out = Y; P.evals = L.evals; P.maxcomp = maxcomp;
+      P.min_size = 1; P.seed = seed; P.skip_connected = 0;
+      dim3 grid(maxcomp, batch);
+      lanczos_kernel_ms<<<grid, kLanczosThreads, 0, stream>>>(P, min_size);
+      count_launch();
+    }
+    multi_component_kernel<<<batch, 256, 0, stream>>>(L.comp, ncomp_out, L.csize, n, dim, maxcomp, min_size, seed, Y, status_out);
+    count_launch();
+    TDA_LAUNCH_CHECK();
+  }
   return TDA_OK;
 }

@@ -240,37 +240,30 @@ def _as_cuda_f32(X):
     return torch.from_numpy(np.ascontiguousarray(X, dtype=np.float32)).cuda()
 
 
-def greedy_permutation_device(dm, n_perm):
-    """Furthest-point sampling with ripser.py's `n_perm` semantics (start at index 0), on the device."""
+def _greedy_perm(X, n_perm, is_matrix):
     torch = _lib.require_cuda()
-    n = dm.shape[0]
-    idx = torch.zeros(n_perm, dtype=torch.long, device=dm.device)
-    lambdas = torch.zeros(n_perm, dtype=torch.float32, device=dm.device)
-    ds = dm[0].clone()
-    for i in range(1, n_perm):
-        j = torch.argmax(ds)
-        idx[i] = j
-        lambdas[i - 1] = ds[j]
-        ds = torch.minimum(ds, dm[j])
-    lambdas[-1] = ds.max()
-    return idx, lambdas
+    L = _lib.lib()
+    X = X.contiguous()
+    n, d = X.shape
+    idx = torch.empty(n_perm, dtype=torch.int32, device=X.device)
+    lambdas = torch.empty(n_perm, dtype=torch.float32, device=X.device)
+    ws_bytes = int(L.tda_greedy_perm_workspace_bytes(n))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=X.device)
+    with torch.cuda.device(X.device):
+        _lib.check(L.tda_greedy_perm(_lib.ptr(X), n, d, int(n_perm), int(is_matrix), _lib.ptr(idx), _lib.ptr(lambdas), _lib.ptr(ws), ws_bytes,
+                                     _lib.stream_ptr()))
+    return idx.long(), lambdas
+
+
+def greedy_permutation_device(dm, n_perm):
+    """Furthest-point sampling with ripser.py's `n_perm` semantics (start at index 0, lowest index on ties) from a distance
+    matrix [n,n] on the device: one launch of tda_greedy_perm.  Returns (idx_perm [n_perm] int64, lambdas [n_perm])."""
+    return _greedy_perm(dm, n_perm, True)
 
 
 def greedy_permutation_points(pts, n_perm):
-    """The same furthest-point sampling straight from the points (euclidean): no n x n matrix (clouds of 1e5 points)."""
-    torch = _lib.require_cuda()
-    n = pts.shape[0]
-    idx = torch.zeros(n_perm, dtype=torch.long, device=pts.device)
-    lambdas = torch.zeros(n_perm, dtype=torch.float32, device=pts.device)
-    P = pts.to(torch.float64)
-    ds = (P - P[0]).square().sum(1).sqrt().to(torch.float32)
-    for i in range(1, n_perm):
-        j = torch.argmax(ds)
-        idx[i] = j
-        lambdas[i - 1] = ds[j]
-        ds = torch.minimum(ds, (P - P[j]).square().sum(1).sqrt().to(torch.float32))
-    lambdas[-1] = ds.max()
-    return idx, lambdas
+    """The same furthest-point sampling straight from the points (euclidean, d <= 16): no n x n matrix (clouds of 1e5 points)."""
+    return _greedy_perm(pts, n_perm, False)
 
 
 def ripser(X, maxdim=1, thresh=np.inf, coeff=2, distance_matrix=False, do_cocycles=False, metric="euclidean", n_perm=None):
@@ -303,7 +296,7 @@ def ripser(X, maxdim=1, thresh=np.inf, coeff=2, distance_matrix=False, do_cocycl
         if n_perm < 0:
             raise ValueError("Should be a strictly positive number of points in the greedy permutation")
     Xd = _as_cuda_f32(X)
-    if (n_perm is not None and n_perm < n and not distance_matrix and metric == "euclidean" and shape[1] <= 64 and n > 4096):
+    if (n_perm is not None and n_perm < n and not distance_matrix and metric == "euclidean" and shape[1] <= 16 and n > 4096):
         # large cloud + landmarks: sample from the points, build only the landmark matrix (and landmark-to-all distances)
         idx_t, lambdas = greedy_permutation_points(Xd, n_perm)
         dm = pdist_lowdim(Xd[idx_t][None])[0]

@@ -125,13 +125,25 @@ def _component_meta_layout(Xp, comp, ncomp, dim, metric, torch):
 
 def spectral_init(X, head, tail, weight, eps, n, dim, seed, metric, speculate_connected=False):
     """spectral_layout / multi_component_layout.  Returns Y [B,n,dim] (not yet noisy-scaled).
-    speculate_connected=True: no host synchronisation -- the eigenvectors are computed as if every graph were connected (the
-    usual case for n_neighbors = 15 on thousands of points) and (Y, ncomp) is returned; the caller checks `ncomp` (device
-    tensor [B]) when it synchronises anyway and repeats the fit without speculation if some graph was not connected."""
+    speculate_connected=True: no host synchronisation -- tda_spectral_init lays out connected clouds and clouds with up to 2*dim
+    components on the device and returns (Y, status); status [B] (device) is 1 for a cloud with more components (its meta layout
+    needs component_layout on the data): the caller checks it when it synchronises anyway and repeats the fit of such a batch
+    through the path below."""
     torch = _lib.require_cuda()
     L = _lib.lib()
     B, slots = head.shape
     dev = head.device
+    if speculate_connected:   # everything on the device; `status` (1 = that cloud needs the host path below) is checked by the caller later
+        ncomp = torch.empty((B,), dtype=torch.int32, device=dev)
+        status = torch.empty((B,), dtype=torch.int32, device=dev)
+        Y = torch.empty((B, n, dim), dtype=torch.float32, device=dev)
+        maxcomp = 2 * dim
+        with torch.cuda.device(dev):
+            ws_bytes = int(L.tda_spectral_init_workspace_bytes(n, B, maxcomp, slots))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            _lib.check(L.tda_spectral_init(_lib.ptr(head), _lib.ptr(tail), _lib.ptr(weight), _lib.ptr(eps), slots, n, dim, B, maxcomp, int(seed),
+                                           _lib.ptr(Y), _lib.ptr(ncomp), _lib.ptr(status), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
+        return Y, status
     comp = torch.empty((B, n), dtype=torch.int32, device=dev)
     ncomp = torch.empty((B,), dtype=torch.int32, device=dev)
     csize = torch.empty((B, n), dtype=torch.int32, device=dev)
@@ -141,13 +153,6 @@ def spectral_init(X, head, tail, weight, eps, n, dim, seed, metric, speculate_co
     with torch.cuda.device(dev):
         _lib.check(L.tda_graph_components(_lib.ptr(head), _lib.ptr(tail), _lib.ptr(weight), _lib.ptr(eps), slots, n, B, _lib.ptr(comp),
                                           _lib.ptr(ncomp), _lib.ptr(csize), _lib.ptr(deg), _lib.ptr(ws0), 12 * B * n, _lib.stream_ptr()))
-        if speculate_connected:
-            ws_bytes = int(L.tda_spectral_workspace_bytes(n, B, 1, slots))
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            _lib.check(L.tda_spectral_embed(_lib.ptr(head), _lib.ptr(tail), _lib.ptr(weight), _lib.ptr(eps), slots, n, dim, B, _lib.ptr(comp),
-                                            _lib.ptr(ncomp), _lib.ptr(csize), _lib.ptr(deg), 1, 1, int(seed), _lib.ptr(Y), None,
-                                            _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
-            return Y, ncomp
         ncomp_h = ncomp.cpu().numpy()
         maxcomp = int(ncomp_h.max())
         min_size = 1 if maxcomp == 1 else max(2 * dim, dim + 2)
@@ -192,8 +197,8 @@ def umap_fit_batch(X, n_neighbors=15, n_components=2, metric="euclidean", n_epoc
     """fit_transform of B clouds at once.  X [B,n,d] float32 CUDA tensor -> embedding [B,n,n_components] (CUDA).
     `knn` = (idx [B,n,k] int32, dist, sigma, rho) skips the distance / kNN stages (e.g. the row-sharded exact kNN of
     pipeline.knn_row_sharded for clouds whose distance matrix should not be materialised on one GPU).
-    defer_component_check=True (spectral init only): the call never synchronises with the device; it returns (Y, ncomp) and the
-    caller must repeat the fit with the default setting if ncomp.max() > 1 (see spectral_init)."""
+    defer_component_check=True (spectral init only): the call never synchronises with the device; it returns (Y, status) and the
+    caller must repeat the fit with the default setting if status.max() > 0 (see spectral_init)."""
     torch = _lib.require_cuda()
     L = _lib.lib()
     assert X.is_cuda and X.dim() == 3

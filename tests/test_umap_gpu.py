@@ -203,6 +203,84 @@ def test_fit_transform_trustworthiness_vs_oracle(torch_cuda, kind, n, k):
     assert um.graph_.shape == (n, n) and um._sigmas.shape == (n,) and um.embedding_ is Yg
 
 
+@pytest.mark.parametrize("cluster", [8, 4, 0])
+def test_cluster_lanczos_on_connected_graph(torch_cuda, tda_option, cluster):
+    """Connected graph (maxcomp = 1): the thread-block-cluster Lanczos kernel (spectral_cluster = 8 / 4) and the one-CTA kernel (0)
+    against ARPACK: eigenvalues, orthonormality, residuals; the cluster kernel is bit-reproducible."""
+    torch = torch_cuda
+    import scipy.sparse
+    import scipy.sparse.linalg
+    from tda_multimodal_b200 import umap_, _lib
+    tda_option("spectral_cluster", cluster)
+    rng = np.random.default_rng(29)
+    n, k, dim = 1500, 15, 3
+    Xd = torch.from_numpy(np.stack([activations(n, 64, rng), activations(n, 64, rng)])).cuda()
+    D = umap_.distance_matrix(Xd, metric="cosine")
+    idx, dist, sigma, rho = umap_.knn_smooth(D, k)
+    head, tail, weight, eps = umap_.fuzzy_graph(idx, dist, sigma, rho, 500)
+    L = _lib.lib()
+    B = 2
+    comp = torch.empty((B, n), dtype=torch.int32, device="cuda")
+    ncomp = torch.empty((B,), dtype=torch.int32, device="cuda")
+    csize = torch.empty((B, n), dtype=torch.int32, device="cuda")
+    deg = torch.empty((B, n), dtype=torch.float32, device="cuda")
+    ws0 = torch.empty(12 * B * n, dtype=torch.uint8, device="cuda")
+    _lib.check(L.tda_graph_components(_lib.ptr(head), _lib.ptr(tail), _lib.ptr(weight), _lib.ptr(eps), head.shape[1], n, B, _lib.ptr(comp),
+                                      _lib.ptr(ncomp), _lib.ptr(csize), _lib.ptr(deg), _lib.ptr(ws0), 12 * B * n, _lib.stream_ptr()))
+    assert ncomp.cpu().tolist() == [1, 1]
+    ws_bytes = int(L.tda_spectral_workspace_bytes(n, B, 1, head.shape[1]))
+    outs = []
+    for rep in range(2):
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+        Y = torch.zeros((B, n, dim), dtype=torch.float32, device="cuda")
+        ev = torch.zeros((B, 1, 4), dtype=torch.float32, device="cuda")
+        _lib.check(L.tda_spectral_embed(_lib.ptr(head), _lib.ptr(tail), _lib.ptr(weight), _lib.ptr(eps), head.shape[1], n, dim, B, _lib.ptr(comp),
+                                        _lib.ptr(ncomp), _lib.ptr(csize), _lib.ptr(deg), 1, 1, 1, _lib.ptr(Y), _lib.ptr(ev),
+                                        _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
+        outs.append((Y.cpu().numpy(), ev.cpu().numpy()))
+    assert np.array_equal(outs[0][0], outs[1][0])   # fixed summation order / fixed-point accumulation: reproducible
+    for b in range(B):
+        h, t, w, e = (a[b].cpu().numpy() for a in (head, tail, weight, eps))
+        keep = e > 0
+        G = scipy.sparse.coo_matrix((w[keep].astype(np.float64), (h[keep], t[keep])), shape=(n, n)).tocsr()
+        d = np.asarray(G.sum(1)).ravel()
+        A = scipy.sparse.diags(1 / np.sqrt(d)) @ G @ scipy.sparse.diags(1 / np.sqrt(d))
+        vals = np.sort(scipy.sparse.linalg.eigsh(A, k=dim + 1, which="LA")[0])[::-1][1:]
+        V, evh = outs[0][0][b].astype(np.float64), outs[0][1][b, 0]
+        np.testing.assert_allclose(evh[:dim], vals, atol=2e-3)
+        assert np.abs(V.T @ V - np.eye(dim)).max() < 1e-2
+        for a in range(dim):
+            assert np.linalg.norm(A @ V[:, a] - evh[a] * V[:, a]) < 3e-2
+
+
+def test_spectral_init_on_device_handles_components(torch_cuda):
+    """tda_spectral_init (no host round trip; the path pipeline.layer_sweep takes): a batch mixing a connected cloud, a cloud with
+    three far-apart pieces and one with a piece too small for a spectral layout.  Component counts equal scipy's, every cloud is
+    laid out on the device (status 0), the pieces of a cloud sit around different meta positions (multi_component_layout), and the
+    embedding that follows is as trustworthy as the one of the host path."""
+    torch = torch_cuda
+    from tda_multimodal_b200 import umap_
+    rng = np.random.default_rng(31)
+    n, d = 900, 64
+    a = activations(n, d, rng)
+    b = np.concatenate([activations(300, d, rng), activations(300, d, rng) + 40.0, activations(300, d, rng) - 40.0]).astype(np.float32)
+    c = np.concatenate([activations(n - 4, d, rng), activations(4, d, rng) * 0.01 + 90.0]).astype(np.float32)
+    X = np.stack([a, b, c])
+    Xd = torch.from_numpy(X).cuda()
+    Y, status = umap_.umap_fit_batch(Xd, n_neighbors=10, n_components=3, metric="euclidean", random_state=42, defer_component_check=True)
+    assert status.cpu().tolist() == [0, 0, 0]
+    Y = Y.cpu().numpy()
+    Yh = umap_.umap_fit_batch(Xd, n_neighbors=10, n_components=3, metric="euclidean", random_state=42).cpu().numpy()
+    assert np.isfinite(Y).all()
+    for i in range(3):
+        assert _trust(X[i], Y[i], "euclidean") >= _trust(X[i], Yh[i], "euclidean") - 0.03
+    # the three pieces of cloud b end up apart: centroid distances well above the pieces' radii
+    cents = np.stack([Y[1][j * 300:(j + 1) * 300].mean(0) for j in range(3)])
+    rad = max(np.linalg.norm(Y[1][j * 300:(j + 1) * 300] - cents[j], axis=1).mean() for j in range(3))
+    dmin = min(np.linalg.norm(cents[i] - cents[j]) for i in range(3) for j in range(i))
+    assert dmin > 1.5 * rad, (dmin, rad)
+
+
 def test_sgd_deterministic_kernel_matches_atomic_kernel(torch_cuda, tda_option):
     """The default SGD (sgd_mode 0: a thread-block cluster per cloud, every vertex sums its own displacement in list order, no
     atomics, all epochs in one launch) against the per-epoch kernels with float atomics (sgd_mode 3) on a batch of 8 clouds:
