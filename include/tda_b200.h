@@ -42,7 +42,7 @@ void tda_launch_count_reset(void);
  *   rips_warp_engine (1): sweep2 reduces every column by a single warp first (speculatively, committed in ripser's order); 0: windows only
  *   sgd_mode (0): 0 deterministic SGD (thread-block cluster per cloud for fit, warp per point for transform; bit-reproducible
  *                 for a given seed), 3 per-epoch kernels with float atomics (used anyway for n > 8192 or n_components != 3)
- *   sgd_cluster (4): CTAs per cloud of the deterministic fit kernel;  spectral_cluster (8): CTAs per cloud of the Lanczos kernel
+ *   sgd_cluster (4): CTAs per cloud of the deterministic fit kernel, sgd_tile (16): vertices per warp task;  spectral_cluster (8): CTAs per cloud of the Lanczos kernel
  *   for connected graphs (0: always the one-CTA-per-component kernel);  sweep_exclusive (0), knn_loads (8), debug_sync (0),
  *   h2_stats (0) */
 int tda_set_option(const char* name, long long value);
@@ -132,15 +132,18 @@ int tda_umap_transform_init(const int32_t* knn_idx, const float* knn_dist, const
  *   rows of Y [batch,n,dim]; evals [batch,maxcomp,4] (eigenvalues of D^-1/2 W D^-1/2) or NULL.
  */
 size_t tda_spectral_workspace_bytes(int n, int batch, int maxcomp, int slots);
-/* tda_spectral_init: components + eigenvectors + multi_component_layout in one call WITHOUT a host round trip: connected clouds go
- *   to a thread-block-cluster Lanczos kernel, clouds with 2..min(maxcomp, 2*dim) components to the per-component kernel and the
- *   +-e_k meta layout of umap-learn's multi_component_layout; ncomp_out [batch] = number of components, status_out [batch] = 0 done,
- *   1 = more components than that (the caller lays those clouds out through tda_graph_components / tda_spectral_embed and its own
- *   component_layout).  Y [batch,n,dim] is overwritten. */
-size_t tda_spectral_init_workspace_bytes(int n, int batch, int maxcomp, int slots);
+/* tda_spectral_init: components + eigenvectors + multi_component_layout in one call WITHOUT a host round trip.  Every component
+ *   (up to min(maxcomp, 32) per cloud) is laid out by a thread-block-cluster Lanczos kernel; clouds with 2..2*dim components get
+ *   umap-learn's +-e_k meta positions; clouds with more components get umap-learn's component_layout on the device when the data
+ *   is given (X [batch,n,d] float32, metric TDA_METRIC_SQEUCLIDEAN / EUCLIDEAN / COSINE): centroids of the components in data
+ *   space, affinity exp(-dist^2), spectral embedding of the normalised Laplacian (Jacobi, fp64).  X may be NULL (d, metric
+ *   ignored): such clouds then get status 1.  ncomp_out [batch] = number of components; status_out [batch] = 0 done, 1 = more
+ *   components than handled here (the caller lays those clouds out through tda_graph_components / tda_spectral_embed and its
+ *   own component_layout).  Y [batch,n,dim] is overwritten. */
+size_t tda_spectral_init_workspace_bytes(int n, int batch, int maxcomp, int slots, int d);
 int tda_spectral_init(const int32_t* head, const int32_t* tail, const float* weight, const float* eps, int slots, int n, int dim,
-                      int batch, int maxcomp, uint64_t seed, float* Y, int32_t* ncomp_out, int32_t* status_out, void* ws, size_t ws_bytes,
-                      void* stream);
+                      int batch, int maxcomp, uint64_t seed, const float* X, int d, int metric, float* Y, int32_t* ncomp_out,
+                      int32_t* status_out, void* ws, size_t ws_bytes, void* stream);
 int tda_graph_components(const int32_t* head, const int32_t* tail, const float* weight, const float* eps, int slots, int n, int batch,
                          int32_t* comp, int32_t* ncomp, int32_t* comp_size, float* degree, void* ws, size_t ws_bytes, void* stream);
 int tda_spectral_embed(const int32_t* head, const int32_t* tail, const float* weight, const float* eps, int slots, int n, int dim,

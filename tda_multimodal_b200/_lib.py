@@ -34,9 +34,9 @@ PROTOTYPES = {
     "tda_umap_transform_init": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tda_spectral_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
-    "tda_spectral_init_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
-    "tda_spectral_init": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.c_uint64, c_void_p, c_void_p,
-                                  c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tda_spectral_init_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "tda_spectral_init": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.c_uint64, c_void_p, c_int, c_int,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tda_graph_components": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_size_t, c_void_p]),
     "tda_spectral_embed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,

@@ -406,11 +406,12 @@ struct LanczosClusterParams {
   int rows_per; int ent_cap;   // rows of a CTA (ceil(n / C)), entries of its CSR slice that fit in shared memory
   const int* ncomp;            // optional [batch] with comp [batch,n], csize [batch,n]: component blockIdx.y of every cloud is laid out
   const int* comp; const int* csize; int min_size_multi;   // (components smaller than min_size_multi of a multi-component cloud are skipped)
-  int2* gent;                  // [batch, C, slots] global room for a CSR slice that does not fit in shared memory (rare: hubs)
+  int2* gent;                  // [batch, Gy, C, slots] global room for a CSR slice that does not fit in shared memory (rare: hubs)
+  int maxcomp;                 // clouds with more components are skipped; stride of evals
 };
 // dynamic shared memory: Qloc[(kMaxKrylov + 2) * rows_per] | qfull[n] | w[rows_per] | part[3][C][kMaxKrylov + 2] | coef[kMaxKrylov + 2]
 //                        | roff[rows_per + 1] | rcnt[rows_per] | ent[ent_cap] (int2: column, value bits)
-__global__ void __launch_bounds__(kLcThreads, 1) lanczos_cluster_kernel(LanczosClusterParams P) {
+__device__ __forceinline__ void lc_component(const LanczosClusterParams& P, const int p, const int c, const int n) {
   extern __shared__ __align__(16) unsigned char lc_raw[];
   __shared__ double s_alpha[kMaxKrylov], s_beta[kMaxKrylov];
   __shared__ double s_lam[kMaxDim];
@@ -418,16 +419,7 @@ __global__ void __launch_bounds__(kLcThreads, 1) lanczos_cluster_kernel(LanczosC
   __shared__ float s_red[kLcThreads / 32];
   __shared__ int s_cnt;
   const uint32_t C = lc_size(), cr = lc_rank();
-  const int p = blockIdx.x / (int)C;
-  const int c = blockIdx.y;   // component of the cloud (0 when the caller knows the graphs are connected)
-  const int nfull = P.n, dim = P.dim, RP = P.rows_per;
-  int n = nfull;              // vertices of the component = size of the problem
-  if (P.ncomp) {
-    const int ncp = P.ncomp[p];
-    if (c >= ncp) return;     // (the whole cluster leaves together)
-    n = P.csize[(size_t)p * nfull + c];
-    if (ncp > 1 && n < P.min_size_multi) return;
-  } else if (c > 0) return;
+  const int nfull = P.n, dim = P.dim, RP = P.rows_per;   // n = vertices of the component = size of the problem
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kLcThreads / 32;
   const int rp = (n + (int)C - 1) / (int)C;   // rows per CTA of THIS component (<= RP, the allocation)
   const int r0 = min(n, (int)cr * rp), r1 = min(n, r0 + rp), nr = r1 - r0;
@@ -522,7 +514,7 @@ __global__ void __launch_bounds__(kLcThreads, 1) lanczos_cluster_kernel(LanczosC
   if (tid == 0) { int acc = 0; for (int i = 0; i < nr; ++i) { roff[i] = acc; acc += rcnt[i]; } roff[nr] = acc; s_cnt = acc; }
   __syncthreads();
   const int nent = s_cnt;
-  if (nent > P.ent_cap) ent = P.gent + (((size_t)p * gridDim.y + c) * C + cr) * (size_t)P.slots;   // the slice lives in global memory instead
+  if (nent > P.ent_cap) ent = P.gent + (((size_t)p * gridDim.y + blockIdx.y) * C + cr) * (size_t)P.slots;   // the slice lives in global memory instead
   for (int i = tid; i < nr; i += kLcThreads) rcnt[i] = roff[i];
   __syncthreads();
   {
@@ -629,7 +621,7 @@ __global__ void __launch_bounds__(kLcThreads, 1) lanczos_cluster_kernel(LanczosC
   __syncthreads();
   const int nev = tridiag_eigs(meff, dim, s_alpha, s_beta, s_lam, s_vec, tid, lane, warp);
   if (cr == 0 && tid == 0 && P.evals)
-    for (int a = 0; a < kMaxDim; ++a) P.evals[((size_t)p * gridDim.y + c) * kMaxDim + a] = a < nev ? (float)s_lam[a] : 0.f;
+    for (int a = 0; a < kMaxDim; ++a) P.evals[((size_t)p * P.maxcomp + c) * kMaxDim + a] = a < nev ? (float)s_lam[a] : 0.f;
   float* out = P.out + (size_t)p * nfull * dim;
   for (int i = tid; i < nr; i += kLcThreads) {
     for (int a = 0; a < dim; ++a) {
@@ -641,31 +633,199 @@ __global__ void __launch_bounds__(kLcThreads, 1) lanczos_cluster_kernel(LanczosC
       out[(size_t)glob[i] * dim + a] = v;
     }
   }
-  lc_sync();   // nobody leaves while its shared memory may still be written
+  lc_sync();   // nobody leaves (or starts the next component) while its shared memory may still be written
+}
+// grid: (batch * C, Gy) CTAs in clusters of C.  Cluster (p, y) lays out the components y, y + Gy, ... of cloud p one after the other
+// (every CTA of a cluster takes the same decisions: they depend on p and c only).
+__global__ void __launch_bounds__(kLcThreads, 1) lanczos_cluster_kernel(LanczosClusterParams P) {
+  const int p = blockIdx.x / (int)lc_size();
+  if (!P.ncomp) {             // the caller knows the graphs are connected
+    if (blockIdx.y == 0) lc_component(P, p, 0, P.n);
+    return;
+  }
+  const int ncp = P.ncomp[p];
+  if (ncp > P.maxcomp) return;   // left to the caller (status 1)
+  for (int c = blockIdx.y; c < ncp; c += gridDim.y) {
+    const int nc = P.csize[(size_t)p * P.n + c];
+    if (ncp > 1 && nc < P.min_size_multi) continue;   // too small for a spectral layout: random points (multi_component_kernel)
+    lc_component(P, p, c, nc);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
-// multi_component_layout (umap-learn spectral.py) for clouds with 2 .. 2*dim components, on the device: the components are placed
-// around the meta positions +-e_k, each scaled to half the distance to the nearest other meta position; components too small for
-// a spectral layout get uniform random points of that range.  One CTA per cloud.  status[p]: 0 done, 1 = more than 2*dim (or
-// `maxcomp`) components: the meta positions need component_layout (host path).
+// component_layout (umap-learn spectral.py) for clouds with MORE than 2*dim components, on the device: the meta positions are the
+// spectral embedding (sklearn SpectralEmbedding, affinity = exp(-d^2), normalised Laplacian, first eigenvector dropped, vectors
+// divided by sqrt(degree), deterministic sign flip) of the component centroids in DATA space, divided by their largest entry.
+constexpr int kMetaMaxComp = 32;     // clouds with more components go back to the caller (status 1)
+constexpr int kCentThreads = 128;
+// centroids: one thread per data column, the points in order (a fixed summation order: reproducible).  grid (ceil(d/128), batch)
+__global__ void __launch_bounds__(kCentThreads) centroid_kernel(const float* __restrict__ X_g, int n, int d, const int* __restrict__ comp_g,
+                                                                const int* __restrict__ ncomp_g, const int* __restrict__ csize_g, int dim, int maxcomp,
+                                                                float* __restrict__ cent_g) {
+  __shared__ float s_acc[kMetaMaxComp][kCentThreads];
+  const int p = blockIdx.y, tid = threadIdx.x;
+  const int nc = ncomp_g[p];
+  if (nc <= 2 * dim || nc > maxcomp) return;
+  const int col = blockIdx.x * kCentThreads + tid;
+  const int* comp = comp_g + (size_t)p * n;
+  const float* X = X_g + (size_t)p * n * d;
+  for (int c = 0; c < nc; ++c) s_acc[c][tid] = 0.f;
+  if (col < d) {
+    int i = 0;
+    for (; i + 4 <= n; i += 4) {   // four rows in flight
+      const float x0 = __ldg(&X[(size_t)i * d + col]), x1 = __ldg(&X[(size_t)(i + 1) * d + col]);
+      const float x2 = __ldg(&X[(size_t)(i + 2) * d + col]), x3 = __ldg(&X[(size_t)(i + 3) * d + col]);
+      s_acc[comp[i]][tid] += x0; s_acc[comp[i + 1]][tid] += x1; s_acc[comp[i + 2]][tid] += x2; s_acc[comp[i + 3]][tid] += x3;
+    }
+    for (; i < n; ++i) s_acc[comp[i]][tid] += __ldg(&X[(size_t)i * d + col]);
+    for (int c = 0; c < nc; ++c)
+      cent_g[((size_t)p * kMetaMaxComp + c) * d + col] = s_acc[c][tid] / (float)max(1, csize_g[(size_t)p * n + c]);
+  }
+}
+// meta positions: one CTA (256 threads) per cloud.  metric: 0 sqeuclidean, 1 euclidean, 2 cosine (pdist.cu's numbering).
+__global__ void __launch_bounds__(256) meta_layout_kernel(const float* __restrict__ cent_g, int d, const int* __restrict__ ncomp_g, int dim, int maxcomp,
+                                                          int metric, float* __restrict__ meta_g) {
+  __shared__ double s_A[kMetaMaxComp][kMetaMaxComp + 1];   // distance -> affinity -> Laplacian -> (diagonalised)
+  __shared__ double s_V[kMetaMaxComp][kMetaMaxComp + 1];   // eigenvectors (columns)
+  __shared__ double s_isd[kMetaMaxComp];
+  __shared__ int s_order[kMetaMaxComp];
+  const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int nc = ncomp_g[p];
+  if (nc <= 2 * dim || nc > maxcomp) return;
+  const float* cent = cent_g + (size_t)p * kMetaMaxComp * d;
+  // Gram matrix of the centroids in fp64: one warp per pair
+  for (int pr = warp; pr < nc * (nc + 1) / 2; pr += nwarps) {
+    int a = 0, rem = pr;
+    while (rem > a) { rem -= a + 1; ++a; }   // pr = a(a+1)/2 + b, b <= a
+    const int b = rem;
+    double acc = 0.0;
+    for (int j = lane; j < d; j += 32) acc += (double)cent[(size_t)a * d + j] * (double)cent[(size_t)b * d + j];
+    acc = warp_sum_f64(acc);
+    if (lane == 0) { s_V[a][b] = acc; s_V[b][a] = acc; }
+  }
+  __syncthreads();
+  for (int e = tid; e < nc * nc; e += blockDim.x) {
+    const int a = e / nc, b = e % nc;
+    const double gaa = s_V[a][a], gbb = s_V[b][b], gab = s_V[a][b];
+    double dist;
+    if (metric == 2) {   // sklearn cosine_distances: 1 - normalised dot, clipped to [0, 2], exact zero diagonal
+      const double den = sqrt(gaa) * sqrt(gbb);
+      dist = den > 0.0 ? 1.0 - gab / den : 1.0;
+      dist = fmin(fmax(dist, 0.0), 2.0);
+    } else {
+      const double d2 = fmax(gaa + gbb - 2.0 * gab, 0.0);
+      dist = metric == 0 ? d2 : sqrt(d2);
+    }
+    s_A[a][b] = a == b ? 0.0 : exp(-dist * dist);
+  }
+  __syncthreads();
+  if (tid < nc) {
+    double deg = 0.0;
+    for (int b = 0; b < nc; ++b) deg += s_A[tid][b];
+    s_isd[tid] = 1.0 / sqrt(fmax(deg, 1e-300));
+  }
+  __syncthreads();
+  for (int e = tid; e < nc * nc; e += blockDim.x) {
+    const int a = e / nc, b = e % nc;
+    s_A[a][b] = (a == b ? 1.0 : 0.0) - s_isd[a] * s_A[a][b] * s_isd[b];
+    s_V[a][b] = a == b ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  if (warp == 0) {   // cyclic Jacobi, lane k owns row / column entry k of the two rotated lines
+    for (int sweep = 0; sweep < 60; ++sweep) {
+      double off = 0.0;
+      for (int a = lane; a < nc; a += 32)
+        for (int b = 0; b < nc; ++b) if (b != a) off += s_A[a][b] * s_A[a][b];
+      off = warp_sum_f64(off);
+      off = __shfl_sync(0xffffffffu, off, 0);
+      if (off < 1e-28) break;
+      for (int a = 0; a < nc - 1; ++a)
+        for (int b = a + 1; b < nc; ++b) {
+          const double apq = s_A[a][b];
+          if (fabs(apq) < 1e-300) continue;   // (uniform: every lane reads the same entry)
+          const double theta = (s_A[b][b] - s_A[a][a]) / (2.0 * apq);
+          const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+          const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+          __syncwarp();
+          if (lane < nc) {   // columns a, b
+            const int k = lane;
+            const double xa = s_A[k][a], xb = s_A[k][b];
+            s_A[k][a] = cs * xa - sn * xb; s_A[k][b] = sn * xa + cs * xb;
+            const double va = s_V[k][a], vb = s_V[k][b];
+            s_V[k][a] = cs * va - sn * vb; s_V[k][b] = sn * va + cs * vb;
+          }
+          __syncwarp();
+          if (lane < nc) {   // rows a, b
+            const int k = lane;
+            const double xa = s_A[a][k], xb = s_A[b][k];
+            s_A[a][k] = cs * xa - sn * xb; s_A[b][k] = sn * xa + cs * xb;
+          }
+          __syncwarp();
+        }
+    }
+    if (lane == 0) {   // eigenvalues ascending (ties: lower index first)
+      for (int a = 0; a < nc; ++a) s_order[a] = a;
+      for (int a = 1; a < nc; ++a) {
+        const int x = s_order[a];
+        int k = a - 1;
+        while (k >= 0 && s_A[s_order[k]][s_order[k]] > s_A[x][x]) { s_order[k + 1] = s_order[k]; --k; }
+        s_order[k + 1] = x;
+      }
+    }
+  }
+  __syncthreads();
+  // embedding column q = eigenvector q+1 / sqrt(degree), sign: the entry of largest magnitude positive; all divided by the largest entry
+  __shared__ double s_sign[kMaxDim], s_max;
+  if (tid < dim) {
+    double best = 0.0;
+    if (tid + 1 < nc) {
+      const int col = s_order[tid + 1];
+      for (int a = 0; a < nc; ++a) { const double v = s_V[a][col] * s_isd[a]; if (fabs(v) > fabs(best)) best = v; }
+    }
+    s_sign[tid] = best < 0.0 ? -1.0 : 1.0;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double mx = 0.0;
+    for (int q = 0; q < dim && q + 1 < nc; ++q)
+      for (int a = 0; a < nc; ++a) mx = fmax(mx, s_sign[q] * s_V[a][s_order[q + 1]] * s_isd[a]);
+    s_max = mx > 0.0 ? mx : 1.0;
+  }
+  __syncthreads();
+  for (int e = tid; e < nc * dim; e += blockDim.x) {
+    const int a = e / dim, q = e % dim;
+    const double v = q + 1 < nc ? s_sign[q] * s_V[a][s_order[q + 1]] * s_isd[a] / s_max : 0.0;
+    meta_g[((size_t)p * kMetaMaxComp + a) * kMaxDim + q] = (float)v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi_component_layout (umap-learn spectral.py) on the device: the components are placed around their meta positions (+-e_k for
+// up to 2*dim components, else the component_layout above, read from meta_g), each scaled to half the distance to the nearest
+// other meta position; components too small for a spectral layout get uniform random points of that range.  One CTA per cloud.
+// status[p]: 0 done, 1 = more than `maxcomp` components (or more than 2*dim and no meta layout: meta_g == nullptr): the caller's job.
 __global__ void __launch_bounds__(256) multi_component_kernel(const int* __restrict__ comp_g, const int* __restrict__ ncomp_g, const int* __restrict__ csize_g,
-                                                              int n, int dim, int maxcomp, int min_size, uint64_t seed, float* __restrict__ Y_g,
-                                                              int* __restrict__ status) {
-  __shared__ float s_meta[2 * kMaxDim][kMaxDim];
-  __shared__ float s_range[2 * kMaxDim];
-  __shared__ unsigned int s_amax[2 * kMaxDim];
+                                                              int n, int dim, int maxcomp, int min_size, uint64_t seed, const float* __restrict__ meta_g,
+                                                              float* __restrict__ Y_g, int* __restrict__ status) {
+  __shared__ float s_meta[kMetaMaxComp][kMaxDim];
+  __shared__ float s_range[kMetaMaxComp];
+  __shared__ unsigned int s_amax[kMetaMaxComp];
   const int p = blockIdx.x, tid = threadIdx.x;
   const int nc = ncomp_g[p];
-  if (tid == 0) status[p] = (nc > 2 * dim || nc > maxcomp) ? 1 : 0;
-  if (nc == 1 || nc > 2 * dim || nc > maxcomp) return;
+  const bool todo = nc <= 2 * dim ? nc <= maxcomp : (meta_g != nullptr && nc <= maxcomp && nc <= kMetaMaxComp);
+  if (tid == 0) status[p] = todo ? 0 : 1;
+  if (nc == 1 || !todo) return;
   const int* comp = comp_g + (size_t)p * n;
   const int* csize = csize_g + (size_t)p * n;
   float* Y = Y_g + (size_t)p * n * dim;
   if (tid < nc) {
-    const int k = (nc + 1) / 2;
-    for (int a = 0; a < dim; ++a) s_meta[tid][a] = 0.f;
-    if (tid < k) s_meta[tid][tid] = 1.f; else s_meta[tid][tid - k] = -1.f;
+    if (nc <= 2 * dim) {
+      const int k = (nc + 1) / 2;
+      for (int a = 0; a < dim; ++a) s_meta[tid][a] = 0.f;
+      if (tid < k) s_meta[tid][tid] = 1.f; else s_meta[tid][tid - k] = -1.f;
+    } else {
+      for (int a = 0; a < dim; ++a) s_meta[tid][a] = meta_g[((size_t)p * kMetaMaxComp + tid) * kMaxDim + a];
+    }
     s_amax[tid] = 0u;
   }
   __syncthreads();
@@ -702,24 +862,31 @@ __global__ void __launch_bounds__(256) multi_component_kernel(const int* __restr
 
 struct Layout {
   int *label, *comp, *ncomp, *csize;
-  float *deg, *Q, *evals;
+  float *deg, *Q, *evals, *cent, *meta;
   int4* entries; int* ent_count; unsigned long long* wfix; int2* lc_ent;
   size_t total;
 };
-static Layout make_layout(void* ws, int n, int batch, int maxcomp, int slots, bool cluster_room = false) {
+constexpr int kLcGridY = 8;   // clusters per cloud of the per-component launch (components c, c + 8, ... one after the other)
+// n_lanczos: components per cloud the one-CTA Lanczos kernel needs room for (0: the cluster kernel does every component);
+// n_cluster: cluster slots per cloud with spill room for a CSR slice;  d > 0: room for the component_layout of clouds with more
+// than 2*dim components (centroids in data space)
+static Layout make_layout(void* ws, int n, int batch, int maxcomp, int slots, int n_lanczos, int n_cluster, int d) {
   Layout L;
   Carver c(ws, ~size_t(0));
+  const size_t sl = slots > 0 ? (size_t)slots : 0;
   L.label = c.take<int>((size_t)batch * n);
   L.comp = c.take<int>((size_t)batch * n);
   L.csize = c.take<int>((size_t)batch * n);
   L.ncomp = c.take<int>(batch);
   L.deg = c.take<float>((size_t)batch * n);
   L.evals = c.take<float>((size_t)batch * (maxcomp > 0 ? maxcomp : 1) * kMaxDim);
-  L.Q = c.take<float>((size_t)batch * (maxcomp > 0 ? maxcomp : 0) * (kMaxKrylov + 2) * n);
-  L.entries = c.take<int4>((size_t)batch * (slots > 0 ? slots : 0));
+  L.Q = c.take<float>((size_t)batch * n_lanczos * (kMaxKrylov + 2) * n);
+  L.entries = c.take<int4>(n_lanczos > 0 ? (size_t)batch * sl : 0);
   L.ent_count = c.take<int>(batch);
-  L.wfix = c.take<unsigned long long>((size_t)batch * (maxcomp > 0 ? maxcomp : 0) * n);
-  L.lc_ent = c.take<int2>((maxcomp == 1 || cluster_room) ? (size_t)batch * (maxcomp > 0 ? maxcomp : 1) * kLcMaxCluster * (slots > 0 ? slots : 0) : 0);
+  L.wfix = c.take<unsigned long long>((size_t)batch * n_lanczos * n);
+  L.lc_ent = c.take<int2>((size_t)batch * n_cluster * kLcMaxCluster * sl);
+  L.cent = c.take<float>(d > 0 ? (size_t)batch * kMetaMaxComp * d : 0);
+  L.meta = c.take<float>(d > 0 ? (size_t)batch * kMetaMaxComp * kMaxDim : 0);
   L.total = c.off;
   return L;
 }
@@ -730,12 +897,10 @@ static Layout make_layout(void* ws, int n, int batch, int maxcomp, int slots, bo
 using namespace tda;
 using namespace tda::spectral;
 
-// launches lanczos_cluster_kernel for the clouds whose graph is connected (all of them if ncomp == nullptr).
-// Returns TDA_OK (launched), 1 (not applicable: option off / rows do not fit in shared memory), or an error code.
-static int launch_cluster_lanczos(const int32_t* head, const int32_t* tail, const float* weight, const float* eps, int slots, int n, int dim, int batch,
-                                  const float* degree, const int* ncomp, const int* comp, const int* csize, int maxcomp, int min_size_multi,
-                                  uint64_t seed, float* Y, float* evals, int2* gent, cudaStream_t stream) {
-  if (option("spectral_cluster") == 0 || n < 64) return 1;
+// shape of a lanczos_cluster_kernel launch for clouds of n vertices; false if the option is off or the rows do not fit in shared memory
+struct ClusterShape { int C, RP, cap_ent; size_t dyn; };
+static bool cluster_shape(int n, int slots, ClusterShape& S) {
+  if (option("spectral_cluster") == 0 || n < 64) return false;
   int C = (int)option("spectral_cluster");
   if (C != 2 && C != 4 && C != 8) C = 8;
   const int RP = (n + C - 1) / C;
@@ -744,20 +909,31 @@ static int launch_cluster_lanczos(const int32_t* head, const int32_t* tail, cons
                        sizeof(int) * ((size_t)(RP + 1) + RP + (size_t)n + RP + 4);
   const size_t smem_max = (size_t)220 * 1024;
   const size_t want_ent = (size_t)slots / C + (size_t)slots / (2 * C) + 64;   // 1.5x the mean slice
-  if (fixed + 8 * 1024 >= smem_max) return 1;
+  if (fixed + 8 * 1024 >= smem_max) return false;
   size_t cap_ent = (smem_max - fixed) / sizeof(int2);
   if (cap_ent > want_ent) cap_ent = want_ent;
-  const size_t dyn = fixed + cap_ent * sizeof(int2);
+  S.C = C; S.RP = RP; S.cap_ent = (int)cap_ent; S.dyn = fixed + cap_ent * sizeof(int2);
+  return true;
+}
+// launches lanczos_cluster_kernel for the clouds whose graph is connected (ncomp == nullptr: all of them, one component each), or
+// for every component of every cloud with up to `maxcomp` components (grid.y = min(maxcomp, kLcGridY) clusters per cloud).
+// Returns TDA_OK (launched), 1 (not applicable: option off / rows do not fit in shared memory), or an error code.
+static int launch_cluster_lanczos(const int32_t* head, const int32_t* tail, const float* weight, const float* eps, int slots, int n, int dim, int batch,
+                                  const float* degree, const int* ncomp, const int* comp, const int* csize, int maxcomp, int min_size_multi,
+                                  uint64_t seed, float* Y, float* evals, int2* gent, cudaStream_t stream) {
+  ClusterShape S;
+  if (!cluster_shape(n, slots, S)) return 1;
+  const int C = S.C;
   LanczosClusterParams Q;
   Q.head = head; Q.tail = tail; Q.weight = weight; Q.eps = eps; Q.slots = slots; Q.n = n; Q.dim = dim;
-  Q.deg = degree; Q.out = Y; Q.evals = evals; Q.seed = seed; Q.rows_per = RP; Q.ent_cap = (int)cap_ent;
-  Q.gent = gent; Q.ncomp = ncomp; Q.comp = comp; Q.csize = csize; Q.min_size_multi = min_size_multi;
-  TDA_CUDA_CHECK(cudaFuncSetAttribute(lanczos_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  Q.deg = degree; Q.out = Y; Q.evals = evals; Q.seed = seed; Q.rows_per = S.RP; Q.ent_cap = S.cap_ent;
+  Q.gent = gent; Q.ncomp = ncomp; Q.comp = comp; Q.csize = csize; Q.min_size_multi = min_size_multi; Q.maxcomp = ncomp ? maxcomp : 1;
+  TDA_CUDA_CHECK(cudaFuncSetAttribute(lanczos_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.dyn));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)(batch * C), (unsigned)(ncomp ? maxcomp : 1), 1);
+  cfg.gridDim = dim3((unsigned)(batch * C), (unsigned)(ncomp ? (maxcomp < kLcGridY ? maxcomp : kLcGridY) : 1), 1);
   cfg.blockDim = dim3(kLcThreads, 1, 1);
-  cfg.dynamicSmemBytes = dyn;
+  cfg.dynamicSmemBytes = S.dyn;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -773,7 +949,7 @@ static int launch_cluster_lanczos(const int32_t* head, const int32_t* tail, cons
 
 extern "C" size_t tda_spectral_workspace_bytes(int n, int batch, int maxcomp, int slots) {
   if (n <= 0 || batch <= 0 || maxcomp < 0 || slots < 0) return 0;
-  return make_layout(nullptr, n, batch, maxcomp, slots).total + 1024;
+  return make_layout(nullptr, n, batch, maxcomp, slots, maxcomp, maxcomp == 1 ? 1 : 0, 0).total + 1024;
 }
 
 extern "C" int tda_graph_components(const int32_t* head, const int32_t* tail, const float* weight, const float* eps, int slots, int n, int batch,
@@ -798,7 +974,7 @@ extern "C" int tda_spectral_embed(const int32_t* head, const int32_t* tail, cons
   if (!head || !tail || !weight || !eps || !comp || !ncomp || !comp_size || !degree || !Y || !ws || n <= 0 || batch <= 0 || maxcomp <= 0)
     return set_error(TDA_ERR_INVALID, "tda_spectral_embed: bad arguments");
   if (dim < 1 || dim > kMaxDim) return set_error(TDA_ERR_UNSUPPORTED, "tda_spectral_embed: dim=%d (supported 1..%d)", dim, kMaxDim);
-  Layout L = make_layout(ws, n, batch, maxcomp, slots);
+  Layout L = make_layout(ws, n, batch, maxcomp, slots, maxcomp, maxcomp == 1 ? 1 : 0, 0);
   if (L.total > ws_bytes) return set_error(TDA_ERR_WORKSPACE, "tda_spectral_embed: workspace %zu < required %zu", ws_bytes, L.total);
   // connected graphs (maxcomp == 1, one component holding every vertex): the cluster kernel, if the rows fit in shared memory.
   // (The caller passes maxcomp = 1 either because it knows, or speculatively -- then it checks ncomp afterwards.)
@@ -821,19 +997,28 @@ extern "C" int tda_spectral_embed(const int32_t* head, const int32_t* tail, cons
 }
 
 // ---- the whole spectral initialisation without a host round trip
-extern "C" size_t tda_spectral_init_workspace_bytes(int n, int batch, int maxcomp, int slots) {
-  if (n <= 0 || batch <= 0 || maxcomp <= 0 || slots < 0) return 0;
-  return make_layout(nullptr, n, batch, maxcomp, slots, true).total + 12 * (size_t)batch * n + 4096;
+static Layout init_layout(void* ws, int n, int batch, int maxcomp, int slots, int d) {
+  ClusterShape S;
+  const bool cl = cluster_shape(n, slots, S);
+  return make_layout(ws, n, batch, maxcomp, slots, cl ? 0 : maxcomp, cl ? (maxcomp < kLcGridY ? maxcomp : kLcGridY) : 0, d);
+}
+extern "C" size_t tda_spectral_init_workspace_bytes(int n, int batch, int maxcomp, int slots, int d) {
+  if (n <= 0 || batch <= 0 || maxcomp <= 0 || slots < 0 || d < 0) return 0;
+  if (maxcomp > kMetaMaxComp) maxcomp = kMetaMaxComp;
+  return init_layout(nullptr, n, batch, maxcomp, slots, d).total + 12 * (size_t)batch * n + 4096;
 }
 extern "C" int tda_spectral_init(const int32_t* head, const int32_t* tail, const float* weight, const float* eps, int slots, int n, int dim,
-                                 int batch, int maxcomp, uint64_t seed, float* Y, int32_t* ncomp_out, int32_t* status_out, void* ws,
-                                 size_t ws_bytes, void* stream_) {
+                                 int batch, int maxcomp, uint64_t seed, const float* X, int d, int metric, float* Y, int32_t* ncomp_out,
+                                 int32_t* status_out, void* ws, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!head || !tail || !weight || !eps || !Y || !ncomp_out || !status_out || !ws || n <= 0 || batch <= 0 || maxcomp <= 0)
     return set_error(TDA_ERR_INVALID, "tda_spectral_init: bad arguments");
   if (dim < 1 || dim > kMaxDim) return set_error(TDA_ERR_UNSUPPORTED, "tda_spectral_init: dim=%d (supported 1..%d)", dim, kMaxDim);
-  if (maxcomp > 2 * kMaxDim) maxcomp = 2 * kMaxDim;
-  Layout L = make_layout(ws, n, batch, maxcomp, slots, true);
+  if (X && (d <= 0 || metric < 0 || metric > 2)) return set_error(TDA_ERR_INVALID, "tda_spectral_init: X given with d=%d metric=%d", d, metric);
+  if (!X) d = 0;
+  if (maxcomp > kMetaMaxComp) maxcomp = kMetaMaxComp;
+  if (!X && maxcomp > 2 * dim) maxcomp = 2 * dim;   // no data: no component_layout
+  Layout L = init_layout(ws, n, batch, maxcomp, slots, d);
   const size_t need = L.total + 12 * (size_t)batch * n + 256;
   if (need > ws_bytes) return set_error(TDA_ERR_WORKSPACE, "tda_spectral_init: workspace %zu < required %zu", ws_bytes, need);
   unsigned long long* degfix = (unsigned long long*)((char*)ws + ((L.total + 255) & ~(size_t)255));
@@ -862,7 +1047,14 @@ extern "C" int tda_spectral_init(const int32_t* head, const int32_t* tail, const
       lanczos_kernel_ms<<<grid, kLanczosThreads, 0, stream>>>(P, min_size);
       count_launch();
     }
-    multi_component_kernel<<<batch, 256, 0, stream>>>(L.comp, ncomp_out, L.csize, n, dim, maxcomp, min_size, seed, Y, status_out);
+    if (X && maxcomp > 2 * dim) {   // component_layout for the clouds with more than 2*dim components (the kernels leave at once otherwise)
+      centroid_kernel<<<dim3((unsigned)((d + kCentThreads - 1) / kCentThreads), (unsigned)batch), kCentThreads, 0, stream>>>(
+          X, n, d, L.comp, ncomp_out, L.csize, dim, maxcomp, L.cent);
+      count_launch();
+      meta_layout_kernel<<<batch, 256, 0, stream>>>(L.cent, d, ncomp_out, dim, maxcomp, metric, L.meta);
+      count_launch();
+    }
+    multi_component_kernel<<<batch, 256, 0, stream>>>(L.comp, ncomp_out, L.csize, n, dim, maxcomp, min_size, seed, X ? L.meta : nullptr, Y, status_out);
     count_launch();
     TDA_LAUNCH_CHECK();
   }

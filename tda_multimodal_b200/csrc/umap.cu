@@ -814,7 +814,7 @@ constexpr int kClThreads = 1024;
 constexpr int kClWarps = kClThreads / 32;
 constexpr int kClQueue = 256;     // fired entries a warp queues before it works through them (a tile of 32 vertices usually fires ~150)
 constexpr int kClMaxCluster = 8;
-constexpr int kClTile = 16;       // vertices per warp task (more, smaller tasks: the kernel is bound by the latency of one warp's chain)
+constexpr int kClTile = 16;       // most vertices per warp task (option sgd_tile: more, smaller tasks shorten a warp's chain per epoch)
 
 struct SgdForce {
   float a, b, gamma, nsr;
@@ -877,7 +877,7 @@ __device__ __forceinline__ void dsmem_store_f4(uint32_t addr, const float4& v) {
 // per warp: queue[kClQueue] + acc[32] float4
 __global__ void __launch_bounds__(kClThreads, 1) sgd_cluster_kernel(float* __restrict__ Y, const int* __restrict__ adj_off, const uint2* __restrict__ adj_ent,
                                                                     int slots, int n, int n_epochs, SgdForce F, float alpha0, uint64_t seed,
-                                                                    int max_own_ent) {
+                                                                    int max_own_ent, int tile) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   const uint32_t C = cluster_nctarank(), cr = cluster_ctarank();
   const int p = blockIdx.x / (int)C;
@@ -914,10 +914,10 @@ __global__ void __launch_bounds__(kClThreads, 1) sgd_cluster_kernel(float* __res
     const uint32_t dst_off = (uint32_t)(((ep + 1) & 1) * n) * 16u;
     const uint32_t key_ep = hash32((uint32_t)seed ^ (uint32_t)(seed >> 32) ^ hash32((uint32_t)p * 0x27d4eb2fu + (uint32_t)ep));
     // tiles of kClTile consecutive owned vertices, dealt round robin to the warps
-    for (int tv = warp * kClTile; tv < nown; tv += kClWarps * kClTile) {
-      const int cnt = min(kClTile, nown - tv);
+    for (int tv = warp * tile; tv < nown; tv += kClWarps * tile) {
+      const int cnt = min(tile, nown - tv);
       const int ebase = soff[tv] - e0;
-      if (lane < kClTile) acc[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lane < tile) acc[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
       __syncwarp();
       int qn = 0;
       // phase 2 (called whenever the queue may overflow, and at the end): full warps over the queued (= fired) entries; the
@@ -1239,8 +1239,10 @@ extern "C" int tda_umap_sgd(float* Y, const float* Y_other, const int32_t* head,
       attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
+      int tile = (int)option("sgd_tile");
+      if (tile < 1 || tile > kClTile) tile = kClTile;
       TDA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sgd_cluster_kernel, Y, (const int*)adj_off, (const uint2*)adj_ent, slots, n, n_epochs, F, alpha0, seed,
-                                        (int)cap_ent));
+                                        (int)cap_ent, tile));
       count_launch(2);
       TDA_LAUNCH_CHECK();
       return TDA_OK;

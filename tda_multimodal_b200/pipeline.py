@@ -74,7 +74,7 @@ def layer_sweep(X, n_neighbors=15, n_components=3, min_dist=0.1, metric="cosine"
             else:
                 Xc.record_stream(st)
             # nothing below synchronises with the device: every chunk's whole chain is enqueued before the first result is awaited
-            # (tda_spectral_init handles up to 2*dim components per cloud on the device; its status is checked after the sweep)
+            # (tda_spectral_init handles up to 32 components per cloud on the device; its status is checked after the sweep)
             Y, ncomp = umap_fit_batch(Xc, defer_component_check=True, **kw)
             jobs.append(rips_batch_launch(pdist_lowdim(Y), maxdim=maxdim))
             Ys.append(Y)
@@ -83,7 +83,7 @@ def layer_sweep(X, n_neighbors=15, n_components=3, min_dist=0.1, metric="cosine"
     res = []
     for c, job in enumerate(jobs):
         r = job.finish()
-        if checks[c] is not None and int(checks[c].max().item()) > 0:   # clouds with more than 2*dim components: the host path, for them only
+        if checks[c] is not None and int(checks[c].max().item()) > 0:   # clouds with more than 32 components: the host path, for them only
             bad = torch.nonzero(checks[c] > 0).flatten()
             with torch.cuda.stream(streams[c]):
                 Yb = umap_fit_batch(Xcs[c][bad].contiguous(), **kw)

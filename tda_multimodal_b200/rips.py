@@ -110,11 +110,19 @@ class RipsJob:
         return out
 
 
+def _free_bytes_estimate(torch, dev):
+    """Memory this process can still take: the device's total minus what torch's allocator holds.  Host-side bookkeeping only --
+    cudaMemGetInfo is an ioctl into the kernel driver, and on a shared 8-GPU host it stalled the launching thread for 20-90 ms at
+    random (measured: profiles/r02_step_variance.txt), right in the middle of a step's kernel enqueue."""
+    return max(1 << 30, int(torch.cuda.get_device_properties(dev).total_memory * 0.95) - int(torch.cuda.memory_reserved(dev))
+               + int(torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)))
+
+
 def _default_sizes(torch, dm, cap1, pool_bytes):
     B, n, _ = dm.shape
     dev = dm.device
     cap1 = _next_pow2(cap1 or max(64, 4 * n))
-    free_bytes = torch.cuda.mem_get_info(dev)[0]
+    free_bytes = _free_bytes_estimate(torch, dev)
     if pool_bytes is None:
         E = n * (n - 1) // 2
         if _lib.rips_reducer() == "bitset":

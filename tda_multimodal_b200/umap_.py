@@ -10,7 +10,7 @@ import warnings
 import numpy as np
 
 from . import _lib
-from .pdist import pdist
+from .pdist import METRICS, pdist
 
 try:  # sklearn is present in the image; keep get_params/set_params/clone working like umap-learn's estimator
     from sklearn.base import BaseEstimator
@@ -19,6 +19,7 @@ except Exception:  # pragma: no cover
 
 DISCONNECTION_DISTANCES = {"correlation": 2.0, "cosine": 2.0, "hellinger": 1.0, "jaccard": 1.0, "dice": 1.0}
 _AB_CACHE = {}
+DEVICE_MAX_COMPONENTS = 32   # components per cloud tda_spectral_init lays out on the device (kMetaMaxComp in csrc/spectral.cu)
 
 
 def find_ab_params(spread, min_dist):
@@ -117,18 +118,20 @@ def _component_meta_layout(Xp, comp, ncomp, dim, metric, torch):
     lap = torch.eye(ncomp, dtype=torch.float64, device=Xp.device) - isd[:, None] * aff * isd[None, :]
     vals, vecs = torch.linalg.eigh(lap)
     emb = vecs[:, 1:dim + 1] * isd[:, None]
+    big = emb.abs().argmax(dim=0)                       # sklearn _deterministic_vector_sign_flip: largest entry of every vector positive
+    emb = emb * torch.sign(emb[big, torch.arange(emb.shape[1], device=emb.device)])[None, :]
     if emb.shape[1] < dim:
         emb = torch.cat([emb, torch.zeros((ncomp, dim - emb.shape[1]), dtype=emb.dtype, device=emb.device)], 1)
-    emb = emb / emb.abs().max().clamp_min(1e-300)
+    emb = emb / emb.max().clamp_min(1e-300)             # umap-learn: component_embedding /= component_embedding.max()
     return emb.to(torch.float32)
 
 
 def spectral_init(X, head, tail, weight, eps, n, dim, seed, metric, speculate_connected=False):
     """spectral_layout / multi_component_layout.  Returns Y [B,n,dim] (not yet noisy-scaled).
-    speculate_connected=True: no host synchronisation -- tda_spectral_init lays out connected clouds and clouds with up to 2*dim
-    components on the device and returns (Y, status); status [B] (device) is 1 for a cloud with more components (its meta layout
-    needs component_layout on the data): the caller checks it when it synchronises anyway and repeats the fit of such a batch
-    through the path below."""
+    speculate_connected=True: no host synchronisation -- tda_spectral_init lays out every cloud with up to DEVICE_MAX_COMPONENTS
+    components on the device (component_layout of the centroids included) and returns (Y, status); status [B] (device) is 1 for a
+    cloud with more components: the caller checks it when it synchronises anyway and repeats the fit of such a cloud through the
+    path below."""
     torch = _lib.require_cuda()
     L = _lib.lib()
     B, slots = head.shape
@@ -137,11 +140,14 @@ def spectral_init(X, head, tail, weight, eps, n, dim, seed, metric, speculate_co
         ncomp = torch.empty((B,), dtype=torch.int32, device=dev)
         status = torch.empty((B,), dtype=torch.int32, device=dev)
         Y = torch.empty((B, n, dim), dtype=torch.float32, device=dev)
-        maxcomp = 2 * dim
+        maxcomp = DEVICE_MAX_COMPONENTS
+        have_x = X is not None and metric in METRICS and METRICS[metric] <= 2
+        d = int(X.shape[-1]) if have_x else 0
         with torch.cuda.device(dev):
-            ws_bytes = int(L.tda_spectral_init_workspace_bytes(n, B, maxcomp, slots))
+            ws_bytes = int(L.tda_spectral_init_workspace_bytes(n, B, maxcomp, slots, d))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             _lib.check(L.tda_spectral_init(_lib.ptr(head), _lib.ptr(tail), _lib.ptr(weight), _lib.ptr(eps), slots, n, dim, B, maxcomp, int(seed),
+                                           _lib.ptr(X) if have_x else None, d, METRICS[metric] if have_x else 0,
                                            _lib.ptr(Y), _lib.ptr(ncomp), _lib.ptr(status), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
         return Y, status
     comp = torch.empty((B, n), dtype=torch.int32, device=dev)

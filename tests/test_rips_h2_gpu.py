@@ -48,11 +48,9 @@ def test_h2_many_windows_far_buckets_match_oracle(monkeypatch, far_bytes):
         assert same_diagram(d[2], want[2]), (far_bytes, b, len(d[2]), len(want[2]))
 
 
-@pytest.mark.parametrize("n", [600, pytest.param(1000, marks=pytest.mark.skipif(__import__("os").environ.get("TDA_TEST_UNVALIDATED") != "1",
-                                                                                reason="fixture made after the GPU minutes were spent; the recorded GPU run "
-                                                                                       "has the oracle's row counts and top persistences (DESIGN.md 2.7)"))])
+@pytest.mark.parametrize("n", [600, 1000])
 def test_c2_torus_matches_oracle_golden(n):
-    """Config C2 of BASELINE.json (noisy flat torus in 4096-d, raw distance matrix, maxdim=2) at n=600 against the CPU oracle's
+    """Config C2 of BASELINE.json (noisy flat torus in 4096-d, raw distance matrix, maxdim=2) at n=600 and n=1000 against the CPU oracle's
     diagrams (tests/golden/c2_torus_n{600,1000}_dgms.npz, made by tests/golden/make_c2_golden.py).  The GPU distances come from the
     3xTF32 tensor-core GEMM, the oracle's from float64, so the diagrams are compared by bottleneck distance: north_star's bound
     is 1e-4 x diameter.  The tetrahedron key space spans 15 windows here: the far buckets run with their default sizes."""

@@ -97,3 +97,43 @@ def test_multi_component_init_positions():
     ch, cd, co = cents(init_host), cents(init_dev), cents(init_or)
     print("component centroids host / device / oracle:\n", np.round(ch, 2), "\n", np.round(cd, 2), "\n", np.round(co, 2))
     assert np.abs(ch - co).max() < 1.0 and np.abs(cd - co).max() < 1.0   # [0,10] box: meta positions 5 apart
+
+
+def _nine_pieces():
+    from tda_multimodal_b200 import workloads
+    rng = np.random.default_rng(5)
+    offs = rng.normal(0, 1.0, (9, 24)) * 0.25       # centroid distances ~1.7: affinities exp(-d^2) of a few percent
+    pieces = [workloads._embed(workloads.torus_latent(120, rng, 0.05), 24, rng, noise=0.01) * 0.05 + off for off in offs]
+    return pieces, np.concatenate(pieces).astype(np.float32), np.repeat(np.arange(9), 120)
+
+
+def test_many_component_init_positions():
+    """nine separate pieces (> 2*dim components: umap-learn's component_layout = spectral embedding of the component centroids):
+    the device path (tda_spectral_init with the data: centroid_kernel + meta_layout_kernel, no host round trip), the host path and
+    the oracle's spectral_layout put the pieces at the same meta positions after the common [0,10] rescale of the initialisation.
+    The pieces sit at generic positions, so the centroid Laplacian has distinct eigenvalues and the layout is unique up to the
+    sign convention (sklearn's deterministic flip, which all three follow)."""
+    import torch
+    from oracle import umap_oracle as uo
+    from tda_multimodal_b200 import umap_
+    pieces, X, lab = _nine_pieces()
+    Xd = torch.from_numpy(X).cuda()[None]
+    _, st_host = umap_.umap_fit_batch(Xd, n_neighbors=10, n_components=3, metric="euclidean", random_state=42, n_epochs=11, return_state=True)
+    init_host = st_host["init"][0].cpu().numpy()
+    Yd, status = umap_.umap_fit_batch(Xd, n_neighbors=10, n_components=3, metric="euclidean", random_state=42, n_epochs=0, defer_component_check=True)
+    assert int(status.max()) == 0, "the device path must lay out 9 components itself"
+    init_dev = Yd[0].cpu().numpy()
+    orc = uo.UMAPOracle(n_neighbors=10, n_components=3, metric="euclidean", random_state=42, n_epochs=11).fit(X)
+    e = orc._init_embedding
+    init_or = 10.0 * (e - e.min(0)) / (e.max(0) - e.min(0))
+
+    def cents(Y):
+        return np.stack([Y[lab == c].mean(0) for c in range(9)])
+    ch, cd, co = cents(init_host), cents(init_dev), cents(init_or)
+    print("component centroids host / device / oracle:\n", np.round(ch, 2), "\n", np.round(cd, 2), "\n", np.round(co, 2))
+    assert np.abs(cd - ch).max() < 0.25, "device and host component_layout differ"
+    assert np.abs(cd - co).max() < 1.0    # the oracle runs sklearn's SpectralEmbedding (ARPACK): same vectors up to solver tolerance
+    # cosine metric, batch of two (a connected cloud and one with nine pieces): statuses and finiteness
+    Xb = torch.from_numpy(np.stack([np.random.default_rng(2).normal(0, 1, X.shape).astype(np.float32), X + 0.5])).cuda()
+    Yb, st = umap_.umap_fit_batch(Xb, n_neighbors=10, n_components=3, metric="cosine", random_state=42, defer_component_check=True)
+    assert st.cpu().tolist() == [0, 0] and bool(torch.isfinite(Yb).all())
