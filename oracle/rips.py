@@ -74,6 +74,29 @@ def greedy_permutation(dm, n_perm):
     return idx, lambdas
 
 
+def greedy_permutation_points(X, n_perm):
+    """The same furthest-point sampling (ripser.py getGreedyPerm semantics: start at index 0, np.argmax = lowest index on ties)
+    straight from the points, one distance row at a time -- for clouds whose n x n matrix is too large (config C5: 1e5 points).
+    Distances: float64 accumulation of the squared differences, float64 sqrt, rounded to float32 (what greedy_perm_kernel
+    computes for point input)."""
+    X = np.asarray(X, dtype=np.float64)
+    n = X.shape[0]
+    idx = np.zeros(n_perm, dtype=np.int64)
+    lambdas = np.zeros(n_perm)
+
+    def row(j):
+        diff = X - X[j]
+        return np.sqrt(np.einsum("ij,ij->i", diff, diff)).astype(np.float32)
+    ds = row(0)
+    for i in range(1, n_perm):
+        j = int(np.argmax(ds))
+        idx[i] = j
+        lambdas[i - 1] = ds[j]
+        ds = np.minimum(ds, row(j))
+    lambdas[-1] = ds.max()
+    return idx, lambdas
+
+
 def rips_dm(dm, maxdim=1, thresh=np.inf, with_simplices=False, with_stats=False):
     """Persistence of the Rips filtration of a full float32 distance matrix."""
     dm = np.ascontiguousarray(dm, dtype=np.float32)

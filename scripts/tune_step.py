@@ -23,6 +23,8 @@ def main():
             k, v = item.split("=")
             if k == "chunks":
                 chunks = int(v)
+            elif k == "split":
+                chunks = [int(x) for x in v.split("-")]
             else:
                 kv[k] = int(v)
         for k, v in kv.items():

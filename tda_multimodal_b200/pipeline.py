@@ -42,7 +42,9 @@ def layer_sweep(X, n_neighbors=15, n_components=3, min_dist=0.1, metric="cosine"
     """UMAP + Rips for a stack of layers resident on the device.  X [L,n,d] float32 CUDA tensor.
     Returns {'embedding': [L,n,n_components] CUDA tensor, 'results': [L dicts with 'dgms', 'num_edges', 'thresh']}.
 
-    The layers are cut into `chunks` groups (default: 2 when L >= 8; env TDA_SWEEP_CHUNKS overrides) that run on their own CUDA streams:
+    The layers are cut into `chunks` groups (an int, or a list of group sizes; default: 3 when L >= 24, 2 when L >= 8;
+    env TDA_SWEEP_CHUNKS overrides)
+    that run on their own CUDA streams:
     the Rips reduction of a group (one SM per cloud, latency bound) overlaps the UMAP stages of the next groups, and the
     reductions of all groups overlap each other (tda_rips_launch does not synchronise)."""
     torch = _lib.require_cuda()
@@ -50,17 +52,18 @@ def layer_sweep(X, n_neighbors=15, n_components=3, min_dist=0.1, metric="cosine"
     on_host = not X.is_cuda     # a (pinned) host tensor: every chunk copies its own layers on its own stream, so the copy of
     dev = torch.device("cuda", torch.cuda.current_device()) if on_host else X.device   # one chunk overlaps the compute of another
     if chunks is None:
-        chunks = int(os.environ.get("TDA_SWEEP_CHUNKS", "0")) or (2 if Lc >= 8 else 1)
-    chunks = max(1, min(int(chunks), Lc))
-    if chunks == 1:
-        if on_host:
-            X = X.to(device=dev, dtype=torch.float32, non_blocking=True)
-        Y = umap_fit_batch(X, n_neighbors=n_neighbors, n_components=n_components, metric=metric, min_dist=min_dist,
-                           random_state=random_state, n_epochs=n_epochs)
-        res = rips_batch(pdist_lowdim(Y), maxdim=maxdim)
-        return {"embedding": Y if return_embedding else None, "results": res}
+        chunks = int(os.environ.get("TDA_SWEEP_CHUNKS", "0")) or (3 if Lc >= 24 else 2 if Lc >= 8 else 1)
+    if isinstance(chunks, (list, tuple)):      # explicit group sizes (they must add up to L)
+        sizes = [int(c) for c in chunks if int(c) > 0]
+        assert sum(sizes) == Lc, "chunk sizes must add up to the number of layers"
+        chunks = len(sizes)
+    else:
+        chunks = max(1, min(int(chunks), Lc))
+        sizes = [(Lc * (c + 1)) // chunks - (Lc * c) // chunks for c in range(chunks)]
     cur = torch.cuda.current_stream(dev)
-    bounds = [(Lc * c) // chunks for c in range(chunks + 1)]
+    bounds = [0]
+    for sz in sizes:
+        bounds.append(bounds[-1] + sz)
     streams = _sweep_streams(dev, chunks)
     Ys, jobs, checks, Xcs = [], [], [], []
     kw = dict(n_neighbors=n_neighbors, n_components=n_components, metric=metric, min_dist=min_dist, random_state=random_state, n_epochs=n_epochs)
@@ -188,14 +191,29 @@ def bootstrap_rips(Y, n_resamples=256, size=1000, seed=4000, layer_ids=None, rep
     from . import workloads
     Lc, n, dim = Y.shape
     layer_ids = list(range(Lc)) if layer_ids is None else list(layer_ids)
-    out = []
+    dev = Y.device
+    cur = torch.cuda.current_stream(dev)
+    streams = _sweep_streams(dev, 2)
+    out = [[] for _ in layer_ids]
+    pending = []       # (layer slot, job): at most two batches in flight, on alternating streams -- the host unpacks the
+    k = 0              # diagrams of one batch while the device works on the next
     for li, layer in enumerate(layer_ids):
-        idx = torch.from_numpy(workloads.c4_resample_indices(layer, n, n_resamples, size, seed=seed, replace=replace)).to(Y.device)
-        res = []
+        idx_h = workloads.c4_resample_indices(layer, n, n_resamples, size, seed=seed, replace=replace)
         for r0 in range(0, n_resamples, max_batch):
-            pts = Y[li][idx[r0:r0 + max_batch]].contiguous()      # [b, size, dim]
-            res += rips_batch(pdist_lowdim(pts), maxdim=maxdim)
-        out.append(res)
+            st = streams[k % 2]
+            k += 1
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                idx = torch.from_numpy(idx_h[r0:r0 + max_batch]).to(dev, non_blocking=True)
+                pts = Y[li][idx].contiguous()                      # [b, size, dim]
+                pending.append((li, rips_batch_launch(pdist_lowdim(pts), maxdim=maxdim)))
+            if len(pending) == 2:
+                lj, job = pending.pop(0)
+                out[lj] += job.finish()
+    for lj, job in pending:
+        out[lj] += job.finish()
+    for st in streams[:2]:
+        cur.wait_stream(st)
     return out
 
 

@@ -132,11 +132,20 @@ def c3_layers(n_layers=32, n=2000, d=4096, seed=3000, layers=None, out=None):
 def c4_resample_indices(layer, n_points=2000, n_resamples=256, size=1000, seed=4000, replace=False):
     """C4: bootstrap resamples of one layer's 3-D cloud: [n_resamples, size] int64 indices (without replacement by
     default: duplicate points create zero-length edges; both are supported)."""
-    out = np.empty((n_resamples, size), dtype=np.int64)
-    for r in range(n_resamples):
-        rng = np.random.default_rng(seed + 256 * layer + r)
-        out[r] = rng.choice(n_points, size=size, replace=replace)
-    return out
+    key = (int(layer), int(n_points), int(n_resamples), int(size), int(seed), bool(replace))
+    if key not in _C4_INDEX_CACHE:
+        out = np.empty((n_resamples, size), dtype=np.int64)
+        for r in range(n_resamples):
+            rng = np.random.default_rng(seed + 256 * layer + r)
+            out[r] = rng.choice(n_points, size=size, replace=replace)
+        out.setflags(write=False)
+        if len(_C4_INDEX_CACHE) > 4096:
+            _C4_INDEX_CACHE.clear()
+        _C4_INDEX_CACHE[key] = out
+    return _C4_INDEX_CACHE[key]
+
+
+_C4_INDEX_CACHE = {}   # the index sets are part of the workload definition (seeded), not of the measured path
 
 
 def c5_cloud(n=100000, d=4096, seed=5000, latent_dim=20, n_mix=16):

@@ -47,3 +47,25 @@ def test_umap_from_sharded_knn_and_landmark_rips():
     d = np.linalg.norm(Yh[:, None, :] - Yh[r["idx_perm"][:50]][None, :, :], axis=2)
     for i in range(1, 50):
         assert np.argmax(d[:, :i].min(axis=1)) == r["idx_perm"][i]
+
+
+def test_landmark_selection_at_c5_scale_matches_oracle():
+    """Config C5's landmark step at n = 20 000 / 100 000 points (3-D, the UMAP output's shape): idx_perm of the one-launch cluster
+    kernel equals the oracle's furthest-point sampling index for index, r_cover and every lambda bit for bit (ripser.py
+    getGreedyPerm semantics: start at 0, lowest index on ties)."""
+    import torch
+    from oracle import rips as orips
+    from tda_multimodal_b200 import rips
+    rng = np.random.default_rng(77)
+    for n, n_perm in ((20000, 2000), (100000, 1000)):
+        Y = (rng.normal(0, 1, (n, 3)) * np.array([3.0, 2.0, 1.0]) + rng.integers(0, 4, (n, 1)) * 2.5).astype(np.float32)
+        idx_t, lam_t = rips.greedy_permutation_points(torch.from_numpy(Y).cuda(), n_perm)
+        want_idx, want_lam = orips.greedy_permutation_points(Y, n_perm)
+        assert np.array_equal(idx_t.cpu().numpy(), want_idx)
+        assert np.array_equal(lam_t.cpu().numpy(), want_lam.astype(np.float32))
+    # through the ripser() shim: r_cover and the landmark diagrams (600 landmarks of 20 000 points) against the oracle on the same landmarks
+    r = rips.ripser(Y[:20000], maxdim=1, n_perm=600)
+    wi, wl = orips.greedy_permutation_points(Y[:20000], 600)
+    assert np.array_equal(r["idx_perm"], wi) and r["r_cover"] == float(np.float32(wl[-1]))
+    want = orips.ripser(Y[:20000][wi], maxdim=1)["dgms"]
+    assert np.array_equal(r["dgms"][0], want[0]) and np.array_equal(r["dgms"][1], want[1])

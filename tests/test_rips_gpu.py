@@ -195,3 +195,23 @@ def test_full_size_invariants(torch_cuda):
     assert np.array_equal(c["dgms"][0][:-1] / 4.0, d0[:-1]) and same_diagram(c["dgms"][1] / 4.0, d1)
     pers = np.sort(d1[:, 1] - d1[:, 0])[::-1]
     assert pers[0] > 2 * pers[2]  # torus R=3, r=1: two dominant classes at most
+
+
+def test_c4_full_size_resamples_spot_checked_against_oracle(torch_cuda):
+    """The north-star's bootstrap leg at ITS size (config C4: resamples of 1000 of a 2000-point 3-D cloud, 256 per layer, batched 256
+    problems per call): eight (layer, resample) units picked at random out of 2 x 256 are recomputed by the oracle on the same index
+    sets and must agree row for row (H0 and H1, ripser's order)."""
+    torch = torch_cuda
+    from oracle import rips as orips
+    from tda_multimodal_b200 import pipeline, workloads
+    rng = np.random.default_rng(44)
+    Y = np.stack([torus3d(2000, rng), blobs3d(2000, rng)])
+    res = pipeline.bootstrap_rips(torch.from_numpy(Y).cuda(), n_resamples=256, size=1000, seed=4000, layer_ids=[3, 17])
+    assert len(res) == 2 and len(res[0]) == 256
+    pick = np.random.default_rng(45)
+    for _ in range(8):
+        l, r = int(pick.integers(0, 2)), int(pick.integers(0, 256))
+        idx = workloads.c4_resample_indices([3, 17][l], 2000, 256, 1000, seed=4000)[r]
+        want = orips.ripser(Y[l][idx], maxdim=1)["dgms"]
+        got = res[l][r]["dgms"]
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), (l, r)
