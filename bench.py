@@ -202,6 +202,34 @@ class ClockSampler:
         self.index, self.proc, self.path = index, None, f"/tmp/tda_clocks_{os.getpid()}.csv"
 
     def start(self):
+        """NVML from a thread of this process (the same counters nvidia-smi prints, without a second process polling the driver
+        every 200 ms); falls back to `nvidia-smi -lms 200` when pynvml is missing."""
+        self.samples, self.thread, self.stop_flag = [], None, False
+        try:
+            import threading
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": pynvml.nvmlClocksEventReasonHwSlowdown if hasattr(pynvml, "nvmlClocksEventReasonHwSlowdown") else pynvml.nvmlClocksThrottleReasonHwSlowdown,
+                    "hw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", getattr(pynvml, "nvmlClocksThrottleReasonHwThermalSlowdown", 0)),
+                    "sw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", getattr(pynvml, "nvmlClocksThrottleReasonSwThermalSlowdown", 0)),
+                    "sw_power_cap": getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", getattr(pynvml, "nvmlClocksThrottleReasonSwPowerCap", 0))}
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        self.samples.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), mx, int(get_reasons(h))))
+                    except Exception:
+                        pass
+                    time.sleep(0.1)
+            self.bits = bits
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200",
@@ -211,6 +239,14 @@ class ClockSampler:
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if getattr(self, "thread", None) is not None:
+            self.stop_flag = True
+            self.thread.join(2)
+            if self.samples:
+                reasons = sorted(nm for nm, bit in self.bits.items() if bit and any(s_[2] & bit for s_ in self.samples))
+                out.update(sm_mhz=float(np.median([s_[0] for s_ in self.samples])), sm_max_mhz=float(max(s_[1] for s_ in self.samples)),
+                           reasons=reasons, samples=len(self.samples), source="NVML (pynvml), 100 ms period, during the timed regions")
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -233,7 +269,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm), source="nvidia-smi -lms 200")
         try:
             os.remove(self.path)
         except OSError:

@@ -14,8 +14,19 @@ BUILTIN = ["chunks=2", "chunks=3", "chunks=4", "chunks=2,sgd_tile=8", "chunks=2,
 
 def main():
     cfgs = sys.argv[1:] or BUILTIN
-    X = torch.from_numpy(workloads.c3_layers(n_layers=32)).cuda()
+    Xh = torch.from_numpy(workloads.c3_layers(n_layers=32)).pin_memory()
+    X = Xh.cuda()
     L = _lib.lib()
+    e2e = os.environ.get("TUNE_E2E") == "1"     # time the sweep from pinned host memory (H2D inside, results to the host)
+    if e2e:
+        Xdev = X
+        class _HostSweep:
+            @staticmethod
+            def layer_sweep(_, chunks=None):
+                return pipeline.layer_sweep_host(Xh, chunks=chunks)
+        sweep = _HostSweep.layer_sweep
+    else:
+        sweep = pipeline.layer_sweep
     for cfg in cfgs:
         kv = dict(DEFAULTS)
         chunks = 2
@@ -30,7 +41,7 @@ def main():
         for k, v in kv.items():
             _lib.set_option(k, v)
         for _ in range(2):
-            pipeline.layer_sweep(X, chunks=chunks)
+            sweep(X, chunks=chunks)
         torch.cuda.synchronize()
         ts, host, mallocs = [], [], []
         import time, gc
@@ -42,7 +53,7 @@ def main():
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0 = time.perf_counter()
             e0.record()
-            pipeline.layer_sweep(X, chunks=chunks)
+            sweep(X, chunks=chunks)
             e1.record()
             t1 = time.perf_counter()
             torch.cuda.synchronize()
@@ -57,7 +68,7 @@ def main():
             for _ in range(8):
                 L.tda_stage_timing_reset()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(); pipeline.layer_sweep(X, chunks=chunks); e1.record(); torch.cuda.synchronize()
+                e0.record(); sweep(X, chunks=chunks); e1.record(); torch.cuda.synchronize()
                 runs.append((e0.elapsed_time(e1), _lib.stage_timeline()))
             runs.sort(key=lambda r: r[0])
             for tag, (ms, spans) in (("fastest", runs[0]), ("slowest", runs[-1])):
@@ -65,7 +76,7 @@ def main():
                 print(f"   {tag}: {ms:.1f} ms: " + "  ".join(f"{nm.replace('rips_', 'r_')}[{a - t00:.1f},{b - t00:.1f}]" for nm, a, b in sorted(spans, key=lambda s_: s_[1]) if b - a > 0.4), flush=True)
             L.tda_stage_timing_enable(0)
         L.tda_stage_timing_reset(); L.tda_stage_timing_enable(1)
-        pipeline.layer_sweep(X, chunks=chunks)
+        sweep(X, chunks=chunks)
         torch.cuda.synchronize()
         st = _lib.stage_times()
         L.tda_stage_timing_enable(0)

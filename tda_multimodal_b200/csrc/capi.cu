@@ -113,7 +113,18 @@ extern "C" const char* tda_last_error(void) { return tda::tls_error_buffer(); }
 extern "C" int64_t tda_launch_count(void) { return tda::launch_counter(); }
 extern "C" void tda_launch_count_reset(void) { tda::launch_counter() = 0; }
 
-extern "C" void tda_stage_timing_enable(int on) { tda::stage_state().on = on != 0; }
+extern "C" void tda_stage_timing_enable(int on) {
+  tda::StageState& S = tda::stage_state();
+  S.on = on != 0;
+  // events are created here, not between the launches of a timed step: cudaEventCreate goes through the kernel driver, and on a
+  // shared host such calls were seen to stall the launching thread for tens of milliseconds (profiles/r02_step_variance.txt)
+  if (S.on)
+    while (S.pool.size() < 4096) {
+      cudaEvent_t e = nullptr;
+      if (cudaEventCreate(&e) != cudaSuccess) break;
+      S.pool.push_back(e);
+    }
+}
 extern "C" void tda_stage_timing_reset(void) {
   tda::StageState& S = tda::stage_state();
   tda::stage_collect(S);

@@ -118,11 +118,24 @@ struct GemmParams {
   int tiles_m, tiles_n;
   int metric;              // TDA_METRIC_*
   int symmetric;           // A and B are the same set (zero the diagonal)
+  int tri;                 // symmetric and square tiling: only the tiles on and above the diagonal are computed; the epilogue also
+                           // stores the transposed tile (the distance of (j,i) IS the value computed for (i,j): D is exactly symmetric)
+  int tiles_per_problem;
   float disconnect;        // distances >= disconnect become +inf (umap-learn's disconnection_distance); +inf = off
   const float* norm_a;     // [batch*n] squared norms (euclidean metrics)
   const float* norm_b;     // [batch*m]
   float* out;              // [batch, n, m]
 };
+
+// tile t of the launch -> problem b, tile row ti, tile column tj
+__device__ __forceinline__ void tile_coords(const GemmParams& P, int t, int& b, int& ti, int& tj) {
+  b = t / P.tiles_per_problem;
+  int r = t % P.tiles_per_problem;
+  if (!P.tri) { ti = r / P.tiles_n; tj = r % P.tiles_n; return; }
+  ti = 0;
+  while (r >= P.tiles_n - ti) { r -= P.tiles_n - ti; ++ti; }   // row ti of the upper triangle holds tiles_n - ti tiles
+  tj = ti + r;
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 pdist_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -137,8 +150,7 @@ pdist_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
   uint32_t* tmem_base_slot = (uint32_t*)(bars + 2 * kStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_per_problem = P.tiles_m * P.tiles_n;
-  const int num_tiles = tiles_per_problem * P.batch;
+  const int num_tiles = P.tiles_per_problem * P.batch;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -164,9 +176,10 @@ pdist_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int b = t / tiles_per_problem, r = t % tiles_per_problem;
-        const int row_a = b * P.n + (r / P.tiles_n) * BM;
-        const int row_b = b * P.m + (r % P.tiles_n) * BN;
+        int b, ti, tj;
+        tile_coords(P, t, b, ti, tj);
+        const int row_a = b * P.n + ti * BM;
+        const int row_b = b * P.m + tj * BN;
         // every k-block brings its four operand tiles once; the three products of the split are formed from them
         // (the earlier version re-loaded a tile pair per product: 1.5x the L2 -> shared-memory traffic, which is what
         // bounds this kernel)
@@ -222,9 +235,11 @@ pdist_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     const int q = warp & 3;
     uint32_t acc_iter = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int b = t / tiles_per_problem, r = t % tiles_per_problem;
-      const int i = (r / P.tiles_n) * BM + q * 32 + lane;   // row inside the problem
-      const int j0 = (r % P.tiles_n) * BN;
+      int b, ti, tj;
+      tile_coords(P, t, b, ti, tj);
+      const int i = ti * BM + q * 32 + lane;   // row inside the problem
+      const int j0 = tj * BN;
+      const bool mirror = P.tri && tj > ti;    // off-diagonal tile of a symmetric problem: its transpose is stored as well
       float acc[BN];
 #pragma unroll
       for (int u = 0; u < BN; ++u) acc[u] = 0.f;
@@ -278,6 +293,11 @@ pdist_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
 #pragma unroll
             for (int w = 0; w < 4; ++w)
               if (j + w < P.m) orow[j + w] = o[w];
+          }
+          if (mirror) {   // D[j][i]: the 32 lanes of a warp hold 32 consecutive i -> one 128-byte store per column
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+              if (j + w < P.n) P.out[((size_t)b * P.n + (j + w)) * P.m + i] = o[w];
           }
         }
       }
@@ -449,12 +469,14 @@ extern "C" int tda_pdist(const float* X, const float* Y, int n, int m, int d, in
   P.n = n; P.m = m; P.batch = batch; P.kblocks = L.dp / BK; P.kchunk = 4;
   P.tiles_m = (n + BM - 1) / BM; P.tiles_n = (m + BN - 1) / BN;
   P.metric = metric; P.symmetric = symmetric ? 1 : 0; P.disconnect = disconnect;
+  P.tri = (symmetric && P.tiles_m == P.tiles_n) ? 1 : 0;
+  P.tiles_per_problem = P.tri ? P.tiles_n * (P.tiles_n + 1) / 2 : P.tiles_m * P.tiles_n;
   P.norm_a = L.norm_a; P.norm_b = L.norm_b; P.out = D;
   int sms = 0, dev = 0;
   TDA_CUDA_CHECK(cudaGetDevice(&dev));
   TDA_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   TDA_CUDA_CHECK(cudaFuncSetAttribute(pdist_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-  const long long tiles = (long long)P.tiles_m * P.tiles_n * batch;
+  const long long tiles = (long long)P.tiles_per_problem * batch;
   const int grid = (int)(tiles < sms ? tiles : sms);
   {
     StageScope st(STAGE_PDIST_GEMM, stream);

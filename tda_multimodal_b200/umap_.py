@@ -101,14 +101,13 @@ def _component_meta_layout(Xp, comp, ncomp, dim, metric, torch):
     """meta-embedding of component centroids when there are more than 2*dim components (umap-learn component_layout:
     spectral embedding of exp(-d^2) between centroids); tiny (ncomp x ncomp), done with device-side torch ops."""
     d = Xp.shape[1]
-    cent = torch.zeros((ncomp, d), dtype=torch.float32, device=Xp.device).index_add_(0, comp.long(), Xp)
-    cnt = torch.bincount(comp.long(), minlength=ncomp).clamp_min(1).to(torch.float32)
-    cent = cent / cnt[:, None]
+    onehot = (comp.long()[None, :] == torch.arange(ncomp, device=Xp.device)[:, None]).to(torch.float64)   # (no index_add_: its float
+    cent = (onehot @ Xp.double()) / onehot.sum(1).clamp_min(1.0)[:, None]                                # atomics are not reproducible)
     if metric == "cosine":
-        cn = torch.nn.functional.normalize(cent.double(), dim=1)
+        cn = torch.nn.functional.normalize(cent, dim=1)
         dm = (1.0 - cn @ cn.T).clamp(0, 2)
     else:
-        dm = torch.cdist(cent.double(), cent.double())
+        dm = torch.cdist(cent, cent)
         if metric == "sqeuclidean":
             dm = dm * dm
     aff = torch.exp(-(dm ** 2))
@@ -199,12 +198,14 @@ def spectral_init(X, head, tail, weight, eps, n, dim, seed, metric, speculate_co
 
 def umap_fit_batch(X, n_neighbors=15, n_components=2, metric="euclidean", n_epochs=None, learning_rate=1.0, init="spectral",
                    min_dist=0.1, spread=1.0, set_op_mix_ratio=1.0, local_connectivity=1.0, repulsion_strength=1.0,
-                   negative_sample_rate=5, random_state=None, a=None, b=None, return_state=False, knn=None, defer_component_check=False):
+                   negative_sample_rate=5, random_state=None, a=None, b=None, return_state=False, knn=None, defer_component_check=False,
+                   host_spectral_init=False):
     """fit_transform of B clouds at once.  X [B,n,d] float32 CUDA tensor -> embedding [B,n,n_components] (CUDA).
     `knn` = (idx [B,n,k] int32, dist, sigma, rho) skips the distance / kNN stages (e.g. the row-sharded exact kNN of
     pipeline.knn_row_sharded for clouds whose distance matrix should not be materialised on one GPU).
     defer_component_check=True (spectral init only): the call never synchronises with the device; it returns (Y, status) and the
-    caller must repeat the fit with the default setting if status.max() > 0 (see spectral_init)."""
+    caller must repeat the fit with the default setting if status.max() > 0 (see spectral_init).
+    host_spectral_init=True: components, meta layout and placement through the host-side path (one synchronisation)."""
     torch = _lib.require_cuda()
     L = _lib.lib()
     assert X.is_cuda and X.dim() == 3
@@ -230,11 +231,18 @@ def umap_fit_batch(X, n_neighbors=15, n_components=2, metric="euclidean", n_epoc
     head, tail, weight, eps = fuzzy_graph(idx, dist, sigma, rho, n_ep if n_ep > 10 else (500 if n <= 10000 else 200), set_op_mix_ratio)
     with torch.cuda.device(dev):
         if isinstance(init, str) and init == "spectral":
-            ncomp_dev = None
-            if defer_component_check:
-                Y, ncomp_dev = spectral_init(X, head, tail, weight, eps, n, n_components, seed, metric, speculate_connected=True)
+            # one path for every caller: tda_spectral_init lays out clouds with up to DEVICE_MAX_COMPONENTS components on the device
+            # (bit-reproducible: fixed summation orders).  Clouds with more components (status 1) go through the host path --
+            # here, unless the caller asked to defer that check to its own synchronisation point.
+            if host_spectral_init:      # (tests: the host-side multi_component_layout against the device kernels)
+                Y, ncomp_dev = spectral_init(X, head, tail, weight, eps, n, n_components, seed, metric), None
             else:
-                Y = spectral_init(X, head, tail, weight, eps, n, n_components, seed, metric)
+                Y, ncomp_dev = spectral_init(X, head, tail, weight, eps, n, n_components, seed, metric, speculate_connected=True)
+            if not defer_component_check and not host_spectral_init:
+                bad = torch.nonzero(ncomp_dev > 0).flatten()
+                if bad.numel():
+                    Y[bad] = spectral_init(X[bad].contiguous(), head[bad].contiguous(), tail[bad].contiguous(), weight[bad].contiguous(),
+                                           eps[bad].contiguous(), n, n_components, seed, metric)
             _lib.check(L.tda_umap_rescale(_lib.ptr(Y), n, n_components, B, 1e-4, seed + 1, _lib.stream_ptr()))
         elif isinstance(init, str) and init == "random":
             Y = torch.empty((B, n, n_components), dtype=torch.float32, device=dev)

@@ -270,7 +270,9 @@ def test_spectral_init_on_device_handles_components(torch_cuda):
     Y, status = umap_.umap_fit_batch(Xd, n_neighbors=10, n_components=3, metric="euclidean", random_state=42, defer_component_check=True)
     assert status.cpu().tolist() == [0, 0, 0]
     Y = Y.cpu().numpy()
-    Yh = umap_.umap_fit_batch(Xd, n_neighbors=10, n_components=3, metric="euclidean", random_state=42).cpu().numpy()
+    Yh = umap_.umap_fit_batch(Xd, n_neighbors=10, n_components=3, metric="euclidean", random_state=42, host_spectral_init=True).cpu().numpy()
+    Y2 = umap_.umap_fit_batch(Xd, n_neighbors=10, n_components=3, metric="euclidean", random_state=42).cpu().numpy()
+    assert np.array_equal(Y, Y2), "fit with and without the deferred component check must be the same embedding, bit for bit"
     assert np.isfinite(Y).all()
     for i in range(3):
         assert _trust(X[i], Y[i], "euclidean") >= _trust(X[i], Yh[i], "euclidean") - 0.03

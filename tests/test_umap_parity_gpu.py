@@ -82,7 +82,7 @@ def test_multi_component_init_positions():
     X = np.concatenate(pieces).astype(np.float32)
     Xd = torch.from_numpy(X).cuda()[None]
     lab = np.repeat(np.arange(3), 200)
-    _, st_host = umap_.umap_fit_batch(Xd, n_neighbors=10, n_components=3, metric="euclidean", random_state=42, n_epochs=11, return_state=True)
+    _, st_host = umap_.umap_fit_batch(Xd, n_neighbors=10, n_components=3, metric="euclidean", random_state=42, n_epochs=11, return_state=True, host_spectral_init=True)
     init_host = st_host["init"][0].cpu().numpy()
     # device path: the initialisation is the embedding after zero epochs
     Yd, status = umap_.umap_fit_batch(Xd, n_neighbors=10, n_components=3, metric="euclidean", random_state=42, n_epochs=0, defer_component_check=True)
@@ -118,7 +118,7 @@ def test_many_component_init_positions():
     from tda_multimodal_b200 import umap_
     pieces, X, lab = _nine_pieces()
     Xd = torch.from_numpy(X).cuda()[None]
-    _, st_host = umap_.umap_fit_batch(Xd, n_neighbors=10, n_components=3, metric="euclidean", random_state=42, n_epochs=11, return_state=True)
+    _, st_host = umap_.umap_fit_batch(Xd, n_neighbors=10, n_components=3, metric="euclidean", random_state=42, n_epochs=11, return_state=True, host_spectral_init=True)
     init_host = st_host["init"][0].cpu().numpy()
     Yd, status = umap_.umap_fit_batch(Xd, n_neighbors=10, n_components=3, metric="euclidean", random_state=42, n_epochs=0, defer_component_check=True)
     assert int(status.max()) == 0, "the device path must lay out 9 components itself"
