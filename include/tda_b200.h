@@ -38,11 +38,11 @@ void tda_launch_count_reset(void);
  *   rips_reducer (0): residual H1 reducer -- 0 "sweep2" substitute by rank + verify by window, 1 row sweep with a sequential
  *                     resolver warp, 2 row sweep substitute-then-verify per 512-row chunk, 3 key bitset (any n)
  *   rips_w0 (1024), rips_wsparse (8192), rips_wmax (32768), rips_dense_min (64), rips_dense_div (8): sweep2 window schedule
- *   rips_cluster (4): CTAs of the thread-block cluster that reduces one cloud (sweep2)
+ *   rips_cluster (0 = auto: 8 for up to 4 clouds per launch, else 4): CTAs of the thread-block cluster that reduces one cloud (sweep2)
  *   rips_warp_engine (1): sweep2 reduces every column by a single warp first (speculatively, committed in ripser's order); 0: windows only
  *   sgd_mode (0): 0 deterministic SGD (thread-block cluster per cloud for fit, warp per point for transform; bit-reproducible
  *                 for a given seed), 3 per-epoch kernels with float atomics (used anyway for n > 8192 or n_components != 3)
- *   sgd_cluster (4): CTAs per cloud of the deterministic fit kernel, sgd_tile (16): vertices per warp task;  spectral_cluster (8): CTAs per cloud of the Lanczos kernel
+ *   sgd_cluster (0 = auto, like rips_cluster): CTAs per cloud of the deterministic fit kernel, sgd_tile (16): vertices per warp task;  spectral_cluster (8): CTAs per cloud of the Lanczos kernel
  *   for connected graphs (0: always the one-CTA-per-component kernel);  sweep_exclusive (0), knn_loads (8), debug_sync (0),
  *   h2_stats (0) */
 int tda_set_option(const char* name, long long value);

@@ -78,11 +78,11 @@ static OptionDef g_options[] = {
     {"rips_dense_min", 64},    // sweep2: a window with >= max(dense_min, rows / dense_div) heavy rows switches the column to dense mode
     {"rips_dense_div", 8},
     {"rips_warp_engine", 1},   // sweep2: short columns are reduced by single warps first, speculatively, and committed in order
-    {"rips_cluster", 4},       // sweep2: CTAs per cloud (thread-block cluster: 1, 2, 4 or 8; halved while batch * cluster > 2 * SMs)
+    {"rips_cluster", 0},       // sweep2: CTAs per cloud (thread-block cluster: 1, 2, 4 or 8; 0 = auto: 8 for up to 4 clouds per launch, else 4; halved while batch * cluster > 2 * SMs)
     {"sweep_exclusive", 0},    // reducers 1/2: ask for the whole shared memory of the SM
     {"sgd_mode", 0},           // 0 deterministic kernels (cluster per cloud for fit, warp per point for transform), 3 per-epoch kernels with float atomics
     {"spectral_cluster", 8},   // CTAs per cloud of the Lanczos kernel for connected graphs (2, 4, 8; 0: the one-CTA kernel)
-    {"sgd_cluster", 4},        // CTAs per cloud of the deterministic fit kernel (1, 2, 4 or 8)
+    {"sgd_cluster", 0},        // CTAs per cloud of the deterministic fit kernel (1, 2, 4 or 8; 0 = auto: 8 for up to 4 clouds per launch, else 4)
     {"sgd_tile", 16},          // vertices per warp task of that kernel (1..16)
     {"knn_loads", 8},          // 16-byte loads per lane in flight in the k <= 16 kNN kernel (8 or 16)
     {"debug_sync", 0},         // synchronise after every kernel of tda_rips_h2 (fault location)

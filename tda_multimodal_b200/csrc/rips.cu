@@ -2359,7 +2359,7 @@ static int rips_enqueue(const float* dm, int n, int batch, int maxdim, float thr
         // one thread-block cluster per cloud at a time: cluster size from the option, shrunk for big batches (more clouds than
         // clusters fit on the machine: rather one cloud per SM) 
         int C = (int)option("rips_cluster");
-        if (C != 1 && C != 2 && C != 4 && C != 8) C = 4;
+        if (C != 1 && C != 2 && C != 4 && C != 8) C = batch <= 4 ? 8 : 4;   // auto: few clouds -> more SMs per cloud
         while (C > 1 && (long long)batch * C > 2ll * sms) C >>= 1;
         int nclusters = sms / C;
         if (nclusters > batch) nclusters = batch;

@@ -818,14 +818,16 @@ constexpr int kClTile = 16;       // most vertices per warp task (option sgd_til
 
 struct SgdForce {
   float a, b, gamma, nsr;
-  // attractive step of entry (v -> t) on the epoch's positions; returns the step taken by v
+  float m2ab, g2b, bm1;   // -2ab, 2*gamma*b, b-1 (set by the host next to a, b, gamma)
+  // attractive step of entry (v -> t) on the epoch's positions; returns the step taken by v.  (Approximate division and
+  // exp2/log2 intrinsics: the update is a stochastic gradient step; parity is statistical -- trustworthiness, downstream diagrams.)
   __device__ __forceinline__ float3 attract(const float4& yv, const float4& yt, float alpha) const {
     const float dx = yv.x - yt.x, dy = yv.y - yt.y, dz = yv.z - yt.z;
     const float d2 = dx * dx + dy * dy + dz * dz;
     float g = 0.f;
     if (d2 > 0.f) {
-      const float pw = __powf(d2, b - 1.f);
-      g = (-2.f * a * b * pw) / (a * pw * d2 + 1.f);
+      const float pw = __powf(d2, bm1);
+      g = __fdividef(m2ab * pw, fmaf(a * pw, d2, 1.f));
     }
     return make_float3(clip4(g * dx) * alpha, clip4(g * dy) * alpha, clip4(g * dz) * alpha);
   }
@@ -833,8 +835,8 @@ struct SgdForce {
     const float dx = cur.x - yn.x, dy = cur.y - yn.y, dz = cur.z - yn.z;
     const float dn = dx * dx + dy * dy + dz * dz;
     if (dn > 0.f) {   // (a negative at zero distance gives no update, whichever vertex it is)
-      const float gn = (2.f * gamma * b) / ((0.001f + dn) * (a * __powf(dn, b) + 1.f));
-      if (gn > 0.f) { cur.x += clip4(gn * dx) * alpha; cur.y += clip4(gn * dy) * alpha; cur.z += clip4(gn * dz) * alpha; }
+      const float gn = __fdividef(g2b, (0.001f + dn) * fmaf(a, __powf(dn, b), 1.f));   // > 0 for gamma > 0: always applied
+      cur.x = fmaf(clip4(gn * dx), alpha, cur.x); cur.y = fmaf(clip4(gn * dy), alpha, cur.y); cur.z = fmaf(clip4(gn * dz), alpha, cur.z);
     }
   }
   // does an entry of period eps fire in `epoch` (it fires when floor(epoch / eps) steps up; approximate division: the schedule is
@@ -940,9 +942,9 @@ __global__ void __launch_bounds__(kClThreads, 1) sgd_cluster_kernel(float* __res
             const float4 yv = src[v], yt = src[en.y & 0xffffu];
             const float3 g1 = F.attract(yv, yt, alpha);
             float3 cur = make_float3(yv.x + g1.x, yv.y + g1.y, yv.z + g1.z);
-            const uint32_t key = hash32(key_ep + (uint32_t)(e0 + i) * 0x9E3779B1u);
+            uint32_t r = hash32(key_ep + (uint32_t)(e0 + i) * 0x9E3779B1u);   // stream of this (entry, epoch): one LCG step per sample
             for (int sidx = 0; sidx < tot; ++sidx) {
-              const uint32_t r = hash32(key + (uint32_t)sidx * 0x85ebca6bu);
+              r = r * 0x2c9277b5u + 0xac564b05u;
               F.repel(cur, src[__umulhi(r, (uint32_t)n)], alpha);
             }
             dl = make_float3((cur.x - yv.x) + g1.x, (cur.y - yv.y) + g1.y, (cur.z - yv.z) + g1.z);
@@ -1023,9 +1025,9 @@ __global__ void __launch_bounds__(256) sgd_transform_kernel(float* __restrict__ 
         const float4 yt = make_float4(__ldg(&T3[3 * j]), __ldg(&T3[3 * j + 1]), __ldg(&T3[3 * j + 2]), 0.f);
         const float3 g1 = F.attract(cur, yt, alpha);
         float3 c = make_float3(cur.x + g1.x, cur.y + g1.y, cur.z + g1.z);
-        const uint32_t key = hash32(key_ep + (uint32_t)(sbase + t) * 0x9E3779B1u);
+        uint32_t r = hash32(key_ep + (uint32_t)(sbase + t) * 0x9E3779B1u);
         for (int sidx = 0; sidx < tot; ++sidx) {
-          const uint32_t r = hash32(key + (uint32_t)sidx * 0x85ebca6bu);
+          r = r * 0x2c9277b5u + 0xac564b05u;
           const int kn = (int)__umulhi(r, (uint32_t)n_train);
           F.repel(c, make_float4(__ldg(&T3[3 * kn]), __ldg(&T3[3 * kn + 1]), __ldg(&T3[3 * kn + 2]), 0.f), alpha);
         }
@@ -1196,6 +1198,7 @@ extern "C" int tda_umap_sgd(float* Y, const float* Y_other, const int32_t* head,
   const int sgd_mode = (int)option("sgd_mode");
   SgdForce F;
   F.a = a; F.b = b; F.gamma = gamma; F.nsr = negative_sample_rate;
+  F.m2ab = -2.f * a * b; F.g2b = 2.f * gamma * b; F.bm1 = b - 1.f;
   if (n_epochs == 0) return TDA_OK;
   // ---- deterministic paths (sgd_mode 0): cluster kernel for fit, warp-per-point kernel for transform
   if (sgd_mode == 0 && dim == 3 && !move_other && slots % n_head == 0 && batch <= 65535) {
@@ -1209,7 +1212,7 @@ extern "C" int tda_umap_sgd(float* Y, const float* Y_other, const int32_t* head,
       (((uintptr_t)ws) & 255) == 0) {
     const int n = n_head;
     int C = (int)option("sgd_cluster");
-    if (C != 1 && C != 2 && C != 4 && C != 8) C = 4;
+    if (C != 1 && C != 2 && C != 4 && C != 8) C = batch <= 4 ? 8 : 4;   // auto: few clouds -> more SMs per cloud (the kernel is latency bound)
     const int nown_max = (n + C - 1) / C + 1;
     const size_t base = sizeof(float4) * 2 * (size_t)n + sizeof(float4) * kClWarps * kClTile + sizeof(uint32_t) * kClWarps * kClQueue +
                         sizeof(int) * (size_t)((nown_max + 2) & ~1);
