@@ -317,7 +317,9 @@ def algorithmic_work(stage, a, L, extra):
         "pdist_prep": L * (4.0 * n * d + 8.0 * n * d),                 # read X, write hi + lo
         "knn_smooth": L * (4.0 * n * n + 8.0 * n * k + 8.0 * n),       # read D, write idx+dist, sigma+rho
         "fuzzy_graph": L * (12.0 * n * k + 8.0 * n + 16.0 * 2 * n * k),
-        "spectral_init": L * extra.get("spectral_bytes_per_layer", 0.0),
+        # Lanczos, m = 96 steps with two Gram-Schmidt passes over j + 2 vectors each (dot + update: 4 vector reads of n floats per
+        # vector and pass) + the sparse matrix (8 B per entry, nnz <= 2nk) once per step -- all of it shared-memory traffic
+        "spectral_init": L * (16.0 * n * (96 * 97 / 2 + 2 * 96) + 8.0 * 2 * n * k * 96),
         # SGD: per fired edge two endpoints + ~5 negative samples read (16 B each) and one position written: 124 B
         "umap_sgd": 124.0 * extra.get("sgd_fired_per_layer", 0.0) * L,
         "rips_pdist": L * (12.0 * n + 4.0 * n * n),
@@ -517,6 +519,13 @@ def run_b200(a):
                    "wall_ms_per_step": round(union_ms(spans_by_stage.get(sname, [])) / a.steps, 3), "launches_per_step": calls / a.steps,
                    "avg_launch_ms": round(ms_sum / calls, 4), "work_per_step": work / a.steps, "achieved": achieved, "peak": peak, "unit": unit,
                    "frac": achieved / peak if peak else None}
+            if sname == "rips_apparent":
+                ent["note"] = ("algorithmic bytes = SURVEY 8d's 8(E-n+1)(n-2) (every cofacet of every column); the kernel stops at the first "
+                               "cofacet of equal diameter (top-down scan, ~3 of 63 row chunks per edge), so frac > 1 is expected here")
+            if sname == "pdist_gemm":
+                ent["note"] = "useful FLOPs 2*L*n*n*d of the delivered [n,n] matrices; the kernel computes the tiles on and above the diagonal (53 %) and stores each twice"
+            if sname in ("umap_sgd", "spectral_init", "rips_reduce"):
+                ent["note"] = "state is shared-memory / L2 resident: the algorithmic bytes do not reach HBM (see traffic); the kernel is bound by barrier latency and instruction issue (profiles/r02b_*)"
             tr = traffic.get(sname) if default_shape else None
             if tr:
                 ent["traffic"] = tr.get("dram_bytes_per_launch")
@@ -554,10 +563,15 @@ def run_b200(a):
             ms_pd, Dm = alone(lambda: umap_.distance_matrix(Xc, metric="cosine"))
             ms_kn, _ = alone(lambda: umap_.knn_smooth(Dm, a.neighbors))
             n_, d_, k_ = a.points, a.dim, a.neighbors
+            tn = (n_ + 127) // 128
+            tile_frac = (tn * (tn + 1) / 2) / (tn * tn)
             secondary["alone"] = {
                 "layers": half,
                 "pdist_ms": ms_pd, "pdist_useful_tflops": 2.0 * half * n_ * n_ * d_ / (ms_pd / 1e3) / 1e12,
-                "pdist_issued_frac_of_tf32_peak": 3.0 * 2.0 * half * n_ * n_ * d_ / (ms_pd / 1e3) / 1e12 / tf32_peak,
+                # issued MMA work: 3 products (3xTF32) on the tiles actually computed (symmetric: the T(T+1)/2 tiles on and above the diagonal)
+                "pdist_tiles_computed_frac": tile_frac,
+                "pdist_issued_tflops": 3.0 * tile_frac * 2.0 * half * tn * tn * 128 * 128 * d_ / (ms_pd / 1e3) / 1e12,
+                "pdist_issued_frac_of_tf32_peak": 3.0 * tile_frac * 2.0 * half * tn * tn * 128 * 128 * d_ / (ms_pd / 1e3) / 1e12 / tf32_peak,
                 "knn_ms": ms_kn, "knn_hbm_gbs": half * (4.0 * n_ * n_ + 8.0 * n_ * k_ + 8.0 * n_) / (ms_kn / 1e3) / 1e9,
                 "knn_frac_of_hbm_peak": half * (4.0 * n_ * n_ + 8.0 * n_ * k_ + 8.0 * n_) / (ms_kn / 1e3) / 1e9 / hbm_peak,
                 "note": "each call timed alone incl. operand prep (pdist) / memset + sigma floor (kNN), 512 MB L2 flush before every rep"}
