@@ -83,7 +83,7 @@ static OptionDef g_options[] = {
     {"sgd_mode", 0},           // 0 deterministic kernels (cluster per cloud for fit, warp per point for transform), 3 per-epoch kernels with float atomics
     {"spectral_cluster", 8},   // CTAs per cloud of the Lanczos kernel for connected graphs (2, 4, 8; 0: the one-CTA kernel)
     {"sgd_cluster", 0},        // CTAs per cloud of the deterministic fit kernel (1, 2, 4 or 8; 0 = auto: 8 for up to 4 clouds per launch, else 4)
-    {"sgd_tile", 16},          // vertices per warp task of that kernel (1..16)
+    {"sgd_tile", 16},          // vertices per warp task of that kernel (1..16; tasks are handed out dynamically)
     {"knn_loads", 8},          // 16-byte loads per lane in flight in the k <= 16 kNN kernel (8 or 16)
     {"debug_sync", 0},         // synchronise after every kernel of tda_rips_h2 (fault location)
     {"h2_stats", 0},           // print the H2 reducer's device counters to stderr

@@ -268,7 +268,7 @@ __device__ __forceinline__ void lanczos_body(const LanczosParams& P) {
   for (int i = tid; i < n; i += kLanczosThreads) {
     const float u = u1[i] / nrm;
     u1[i] = u;
-    const float r = comp[i] == c ? ((float)(hash32(P.seed + ((uint64_t)p << 40) + (uint64_t)i) >> 8) * (1.f / 8388608.f) - 1.f) : 0.f;
+    const float r = comp[i] == c ? ((float)(hash32(P.seed + (uint64_t)i) >> 8) * (1.f / 8388608.f) - 1.f) : 0.f;
     q0[i] = r;
     acc += r * u;
   }
@@ -557,7 +557,7 @@ __device__ __forceinline__ void lc_component(const LanczosClusterParams& P, cons
     for (int i = tid; i < nr; i += kLcThreads) {
       const float u = u1[i] / nrm;
       u1[i] = u;
-      const float r = (float)(hash32(P.seed + ((uint64_t)p << 40) + (uint64_t)glob[i]) >> 8) * (1.f / 8388608.f) - 1.f;
+      const float r = (float)(hash32(P.seed + (uint64_t)glob[i]) >> 8) * (1.f / 8388608.f) - 1.f;
       q0[i] = r;
       acc += r * u;
     }
@@ -850,7 +850,7 @@ __global__ void __launch_bounds__(256) multi_component_kernel(const int* __restr
     const float r = s_range[c];
     if (csize[c] < min_size) {
       for (int a = 0; a < dim; ++a) {
-        const float u = (float)(hash32(seed * 0x9E3779B97F4A7C15ull + ((uint64_t)p << 44) + ((uint64_t)i << 8) + (uint64_t)a + 7919ull) >> 8) * (1.f / 8388608.f) - 1.f;
+        const float u = (float)(hash32(seed * 0x9E3779B97F4A7C15ull + ((uint64_t)i << 8) + (uint64_t)a + 7919ull) >> 8) * (1.f / 8388608.f) - 1.f;
         Y[(size_t)i * dim + a] = u * r + s_meta[c][a];
       }
     } else {

@@ -599,7 +599,7 @@ __global__ void __launch_bounds__(256) sgd_epoch_kernel(float* __restrict__ Yh, 
     tot -= (int)floorf((float)prev / epsn) - 1;
   }
   for (int s = 0; s < tot; ++s) {
-    const uint32_t r = mix32(seed ^ ((uint64_t)p << 52) ^ ((uint64_t)e << 20) ^ ((uint64_t)epoch << 4) ^ (uint64_t)s ^ ((uint64_t)s << 40));
+    const uint32_t r = mix32(seed ^ ((uint64_t)e << 20) ^ ((uint64_t)epoch << 4) ^ (uint64_t)s ^ ((uint64_t)s << 40));
     const int kn = (int)(r % (uint32_t)n_tail);
     const float* yn = Yt + ((size_t)p * n_tail + kn) * DIM;
     float dn = 0.f;
@@ -683,7 +683,7 @@ __global__ void __launch_bounds__(kSgdWarps * 32) sgd_epoch_kernel_v4(float4* __
 #pragma unroll
     for (int u = 0; u < kSgdNegBatch; ++u) {
       if (u < tot) {
-        const uint32_t r = mix32(seed ^ ((uint64_t)p << 52) ^ ((uint64_t)e << 20) ^ ((uint64_t)epoch << 4) ^ (uint64_t)u ^ ((uint64_t)u << 40));
+        const uint32_t r = mix32(seed ^ ((uint64_t)e << 20) ^ ((uint64_t)epoch << 4) ^ (uint64_t)u ^ ((uint64_t)u << 40));
         n4[u] = __ldcg(Yt + (size_t)p * n_tail + (int)(r % (uint32_t)n_tail));
       }
     }
@@ -727,7 +727,7 @@ __global__ void __launch_bounds__(kSgdWarps * 32) sgd_epoch_kernel_v4(float4* __
     for (int u = 0; u < kSgdNegBatch; ++u)
       if (u < tot) repel(n4[u]);
     for (int sidx = kSgdNegBatch; sidx < tot; ++sidx) {   // (only with a larger negative_sample_rate)
-      const uint32_t r = mix32(seed ^ ((uint64_t)p << 52) ^ ((uint64_t)e << 20) ^ ((uint64_t)epoch << 4) ^ (uint64_t)sidx ^ ((uint64_t)sidx << 40));
+      const uint32_t r = mix32(seed ^ ((uint64_t)e << 20) ^ ((uint64_t)epoch << 4) ^ (uint64_t)sidx ^ ((uint64_t)sidx << 40));
       repel(__ldcg(Yt + (size_t)p * n_tail + (int)(r % (uint32_t)n_tail)));
     }
     atomicAdd(yh, make_float4(delta[0], delta[1], delta[2], 0.f));
@@ -881,12 +881,17 @@ __global__ void __launch_bounds__(kClThreads, 1) sgd_cluster_kernel(float* __res
                                                                     int slots, int n, int n_epochs, SgdForce F, float alpha0, uint64_t seed,
                                                                     int max_own_ent, int tile) {
   extern __shared__ __align__(16) unsigned char s_raw[];
+  __shared__ int s_next_tile[2];
   const uint32_t C = cluster_nctarank(), cr = cluster_ctarank();
   const int p = blockIdx.x / (int)C;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int v0 = (int)(((long long)n * cr) / C), v1 = (int)(((long long)n * (cr + 1)) / C);
+  if (tid == 0) { s_next_tile[0] = 0; s_next_tile[1] = 0; }
+  // the vertices are dealt to the CTAs in whole tiles [tile*j, tile*j + tile): a tile's fired entries then fall into the same
+  // 32-lane batches for every cluster size, so the embedding does not depend on how many CTAs share a cloud
+  const int ntile = (n + tile - 1) / tile;
+  const int v0 = min(n, tile * (int)(((long long)ntile * cr) / C)), v1 = min(n, tile * (int)(((long long)ntile * (cr + 1)) / C));
   const int nown = v1 - v0;
-  const int nown_max = (n + (int)C - 1) / (int)C + 1;
+  const int nown_max = ((ntile + (int)C - 1) / (int)C) * tile + 1;
   float4* Yb = reinterpret_cast<float4*>(s_raw);
   float4* acc_all = Yb + 2 * (size_t)n;
   uint32_t* queue_all = reinterpret_cast<uint32_t*>(acc_all + kClWarps * kClTile);
@@ -914,9 +919,17 @@ __global__ void __launch_bounds__(kClThreads, 1) sgd_cluster_kernel(float* __res
     const float alpha = ep == 0 ? alpha0 : alpha0 * (1.f - (float)(ep - 1) / (float)n_epochs);
     const float4* src = Yb + (size_t)(ep & 1) * n;
     const uint32_t dst_off = (uint32_t)(((ep + 1) & 1) * n) * 16u;
-    const uint32_t key_ep = hash32((uint32_t)seed ^ (uint32_t)(seed >> 32) ^ hash32((uint32_t)p * 0x27d4eb2fu + (uint32_t)ep));
-    // tiles of kClTile consecutive owned vertices, dealt round robin to the warps
-    for (int tv = warp * tile; tv < nown; tv += kClWarps * tile) {
+    const uint32_t key_ep = hash32((uint32_t)seed ^ (uint32_t)(seed >> 32) ^ hash32(0x27d4eb2fu + (uint32_t)ep));
+    // tiles of `tile` consecutive owned vertices, handed to the warps one by one (a counter per epoch parity in shared memory): a
+    // tile needs 1..4 rounds of 32 fired entries, and the epoch barrier waits for the slowest warp.  Which warp takes a tile does
+    // not matter for the result: a tile reads the epoch's old buffer and writes only its own vertices.
+    if (tid == 0) s_next_tile[(ep + 1) & 1] = 0;   // (last used in epoch ep - 1, which every warp has left)
+    for (;;) {
+      int tix = 0;
+      if (lane == 0) tix = atomicAdd(&s_next_tile[ep & 1], 1);
+      tix = __shfl_sync(0xffffffffu, tix, 0);
+      const int tv = tix * tile;
+      if (tv >= nown) break;
       const int cnt = min(tile, nown - tv);
       const int ebase = soff[tv] - e0;
       if (lane < tile) acc[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1015,7 +1028,7 @@ __global__ void __launch_bounds__(256) sgd_transform_kernel(float* __restrict__ 
   for (int ep = 0; ep < n_epochs; ++ep) {
     const float alpha = ep == 0 ? alpha0 : alpha0 * (1.f - (float)(ep - 1) / (float)n_epochs);
     float3 dl = make_float3(0.f, 0.f, 0.f);
-    const uint32_t key_ep = hash32((uint32_t)seed ^ (uint32_t)(seed >> 32) ^ hash32((uint32_t)p * 0x27d4eb2fu + (uint32_t)ep));
+    const uint32_t key_ep = hash32((uint32_t)seed ^ (uint32_t)(seed >> 32) ^ hash32(0x27d4eb2fu + (uint32_t)ep));
     for (int t = lane; t < k; t += 32) {
       const float eps = eps_arr[sbase + t];
       int q;
@@ -1047,9 +1060,9 @@ __global__ void __launch_bounds__(256) sgd_transform_kernel(float* __restrict__ 
 // initialisation helpers
 __device__ __forceinline__ float u01(uint64_t key) { return ((float)(mix32(key) >> 8) + 0.5f) * (1.f / 16777216.f); }
 
-__global__ void init_random_kernel(float* __restrict__ Y, int total, float lo, float hi, uint64_t seed) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < total) Y[i] = lo + (hi - lo) * u01(seed * 0x9E3779B97F4A7C15ull + (uint64_t)i);
+__global__ void init_random_kernel(float* __restrict__ Y, int total, int per_cloud, float lo, float hi, uint64_t seed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (the draw depends on the index inside the cloud, not on the cloud's place in the batch)
+  if (i < total) Y[i] = lo + (hi - lo) * u01(seed * 0x9E3779B97F4A7C15ull + (uint64_t)(i % per_cloud));
 }
 
 // Y <- 10 * minmax( Y * (10 / max|Y|) + N(0, noise) ) per cloud and axis  (umap-learn's noisy_scale_coords
@@ -1074,7 +1087,7 @@ __global__ void __launch_bounds__(1024) rescale_kernel(float* __restrict__ Yg, i
   am = block_max(am);
   const float expansion = am > 0.f ? 10.f / am : 1.f;
   for (int i = tid; i < n * dim; i += nt) {
-    const uint64_t key = seed * 0xD6E8FEB86659FD93ull + ((uint64_t)p << 40) + (uint64_t)i * 2;
+    const uint64_t key = seed * 0xD6E8FEB86659FD93ull + (uint64_t)i * 2;   // (no cloud index: every cloud of a batch draws what it would draw alone)
     const float u1 = u01(key), u2 = u01(key + 1);
     const float g = sqrtf(-2.f * logf(u1)) * cosf(6.28318530718f * u2);
     Y[i] = Y[i] * expansion + noise * g;
@@ -1213,7 +1226,9 @@ extern "C" int tda_umap_sgd(float* Y, const float* Y_other, const int32_t* head,
     const int n = n_head;
     int C = (int)option("sgd_cluster");
     if (C != 1 && C != 2 && C != 4 && C != 8) C = batch <= 4 ? 8 : 4;   // auto: few clouds -> more SMs per cloud (the kernel is latency bound)
-    const int nown_max = (n + C - 1) / C + 1;
+    int tile = (int)option("sgd_tile");
+    if (tile < 1 || tile > kClTile) tile = kClTile;
+    const int nown_max = (((n + tile - 1) / tile + C - 1) / C) * tile + 1;
     const size_t base = sizeof(float4) * 2 * (size_t)n + sizeof(float4) * kClWarps * kClTile + sizeof(uint32_t) * kClWarps * kClQueue +
                         sizeof(int) * (size_t)((nown_max + 2) & ~1);
     const size_t smem_max = (size_t)224 * 1024;
@@ -1242,8 +1257,6 @@ extern "C" int tda_umap_sgd(float* Y, const float* Y_other, const int32_t* head,
       attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      int tile = (int)option("sgd_tile");
-      if (tile < 1 || tile > kClTile) tile = kClTile;
       TDA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sgd_cluster_kernel, Y, (const int*)adj_off, (const uint2*)adj_ent, slots, n, n_epochs, F, alpha0, seed,
                                         (int)cap_ent, tile));
       count_launch(2);
@@ -1289,7 +1302,7 @@ extern "C" int tda_umap_sgd(float* Y, const float* Y_other, const int32_t* head,
 extern "C" int tda_umap_init_random(float* Y, int n, int dim, int batch, float lo, float hi, uint64_t seed, void* stream_) {
   if (!Y || n <= 0 || dim <= 0 || batch <= 0) return set_error(TDA_ERR_INVALID, "tda_umap_init_random: bad arguments");
   const int total = n * dim * batch;
-  init_random_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(Y, total, lo, hi, seed);
+  init_random_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(Y, total, n * dim, lo, hi, seed);
   count_launch();
   TDA_LAUNCH_CHECK();
   return TDA_OK;

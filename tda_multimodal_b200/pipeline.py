@@ -42,8 +42,8 @@ def layer_sweep(X, n_neighbors=15, n_components=3, min_dist=0.1, metric="cosine"
     """UMAP + Rips for a stack of layers resident on the device.  X [L,n,d] float32 CUDA tensor.
     Returns {'embedding': [L,n,n_components] CUDA tensor, 'results': [L dicts with 'dgms', 'num_edges', 'thresh']}.
 
-    The layers are cut into `chunks` groups (an int, or a list of group sizes; default: 3 when L >= 24 -- 4 for host input --, 2 when
-    L >= 8; env TDA_SWEEP_CHUNKS overrides)
+    The layers are cut into `chunks` groups (an int, or a list of group sizes; default: _default_groups -- four groups for
+    L >= 24, two for L >= 8; env TDA_SWEEP_CHUNKS overrides)
     that run on their own CUDA streams:
     the Rips reduction of a group (one SM per cloud, latency bound) overlaps the UMAP stages of the next groups, and the
     reductions of all groups overlap each other (tda_rips_launch does not synchronise)."""
@@ -52,7 +52,7 @@ def layer_sweep(X, n_neighbors=15, n_components=3, min_dist=0.1, metric="cosine"
     on_host = not X.is_cuda     # a (pinned) host tensor: every chunk copies its own layers on its own stream, so the copy of
     dev = torch.device("cuda", torch.cuda.current_device()) if on_host else X.device   # one chunk overlaps the compute of another
     if chunks is None:
-        chunks = int(os.environ.get("TDA_SWEEP_CHUNKS", "0")) or ((4 if on_host else 3) if Lc >= 24 else 2 if Lc >= 8 else 1)
+        chunks = int(os.environ.get("TDA_SWEEP_CHUNKS", "0")) or _default_groups(Lc, on_host)
     if isinstance(chunks, (list, tuple)):      # explicit group sizes (they must add up to L)
         sizes = [int(c) for c in chunks if int(c) > 0]
         assert sum(sizes) == Lc, "chunk sizes must add up to the number of layers"
@@ -92,8 +92,17 @@ def layer_sweep(X, n_neighbors=15, n_components=3, min_dist=0.1, metric="cosine"
                 Xc.record_stream(st)
             # nothing below synchronises with the device: every chunk's whole chain is enqueued before the first result is awaited
             # (tda_spectral_init handles up to 32 components per cloud on the device; its status is checked after the sweep)
-            Y, ncomp = umap_fit_batch(Xc, defer_component_check=True, **kw)
-            jobs.append(rips_batch_launch(pdist_lowdim(Y), maxdim=maxdim))
+            # the LAST group's chain ends the sweep with nothing left to overlap it: its kernels may take more SMs per cloud
+            tail = TAIL_OPTIONS if (c == chunks - 1 and chunks > 1) else {}
+            saved = {k_: _lib.get_option(k_) for k_ in tail}
+            for k_, v_ in tail.items():
+                _lib.set_option(k_, v_)
+            try:
+                Y, ncomp = umap_fit_batch(Xc, defer_component_check=True, **kw)
+                jobs.append(rips_batch_launch(pdist_lowdim(Y), maxdim=maxdim))
+            finally:
+                for k_, v_ in saved.items():
+                    _lib.set_option(k_, v_)
             Ys.append(Y)
             checks.append(ncomp)
             Xcs.append(Xc)
@@ -233,6 +242,21 @@ def bootstrap_rips(Y, n_resamples=256, size=1000, seed=4000, layer_ids=None, rep
 
 _STREAMS = {}
 _COPY_STREAMS = {}
+# library options (tda_set_option) applied to the launches of the LAST group of a sweep only: its Rips reduction ends the sweep with
+# nothing left to overlap, so it takes 8 CTAs per cloud instead of 4 (measured on C3: 50.8 -> 48.9 ms per step)
+TAIL_OPTIONS = {"rips_cluster": 8}
+
+
+def _default_groups(L, on_host):
+    """Number of groups of a sweep over L layers: four equal groups from 24 layers on (the H2D copy of a group hides behind the
+    compute of the previous ones; with resident input three or four groups are within 1 % of each other, and four equal groups
+    gave the most repeatable step: profiles/r02_tune_groups.txt -- uneven splits such as 10/9/8/5 were up to 3 % faster on one
+    set of clouds and 5 % slower, with a 10 % step-to-step spread, on another), two from 8 layers on."""
+    if L < 8:
+        return 1
+    if L < 24:
+        return 2
+    return 4
 
 
 def _copy_stream(device):

@@ -310,9 +310,9 @@ def test_sgd_deterministic_kernel_matches_atomic_kernel(torch_cuda, tda_option):
 
 @pytest.mark.parametrize("cluster", [1, 2, 8])
 def test_sgd_cluster_sizes(torch_cuda, tda_option, cluster):
-    """The deterministic kernel partitions the vertices over the CTAs of a cluster.  For a given cluster size the result is
-    bit-identical from run to run; between cluster sizes the per-vertex sums are taken in a different tree order (the fired
-    entries fall into different 32-lane batches), so the embeddings agree in quality, not in bits."""
+    """The deterministic kernel deals the vertices to the CTAs of a cluster in whole tiles, so a tile's fired entries fall into the
+    same 32-lane batches whatever the cluster size: the embedding is BIT-IDENTICAL for 1, 2, 4 and 8 CTAs per cloud (the library
+    picks 8 for small batches and 4 otherwise: the same cloud must not depend on what else is in the batch)."""
     torch = torch_cuda
     from tda_multimodal_b200 import umap_
     rng = np.random.default_rng(17)
@@ -322,11 +322,13 @@ def test_sgd_cluster_sizes(torch_cuda, tda_option, cluster):
     want = umap_.umap_fit_batch(Xd, n_neighbors=10, n_components=3, metric="cosine", random_state=7).cpu().numpy()
     tda_option("sgd_cluster", cluster)
     got = umap_.umap_fit_batch(Xd, n_neighbors=10, n_components=3, metric="cosine", random_state=7).cpu().numpy()
-    again = umap_.umap_fit_batch(Xd, n_neighbors=10, n_components=3, metric="cosine", random_state=7).cpu().numpy()
-    assert np.array_equal(got, again)
-    tw = [_trust(X[i], want[i], "cosine") for i in range(3)]
+    assert np.array_equal(got, want)
+    # ... and a cloud embedded alone equals the same cloud embedded inside a batch
+    tda_option("sgd_cluster", 0)
+    alone = umap_.umap_fit_batch(Xd[1:2], n_neighbors=10, n_components=3, metric="cosine", random_state=7).cpu().numpy()
+    assert np.array_equal(alone[0], want[1])
     tg = [_trust(X[i], got[i], "cosine") for i in range(3)]
-    assert min(tg) > 0.8 and np.mean(tg) >= np.mean(tw) - 0.02, (tg, tw)
+    assert min(tg) > 0.8
 
 
 def test_transform_deterministic_and_equals_atomic_kernel(torch_cuda, tda_option):
