@@ -329,6 +329,46 @@ __global__ void apparent_kernel(const int* __restrict__ rank, const uint32_t* __
   }
 }
 
+// The same by matrix ROW (default for n <= 12288): one CTA per vertex a keeps row a of the rank matrix in shared memory and
+// handles every edge (a, b), b < a, one warp per edge.  The a-side of the lune test is then a shared-memory read, the b-side rows
+// are fetched only for the lanes (and only in the chunks) that pass the a-side test -- short edges, whose lune test fails in
+// almost every chunk, no longer stream their two rank rows from L2.  MST edges always have an empty lune (the longest edge of a
+// triangle is not in the MST), so the MST flag is read only for the edges without an apex.
+__global__ void __launch_bounds__(256) apparent_rows_kernel(const int* __restrict__ rank, const uint8_t* __restrict__ mst,
+                                                            const int* __restrict__ Tarr, int n, int64_t E, uint2* __restrict__ ea,
+                                                            int* __restrict__ blist, int* __restrict__ bcount, int cap1) {
+  extern __shared__ int s_rowa[];
+  const int p = blockIdx.y, a = blockIdx.x;
+  const int T = Tarr[p];
+  const int* R = rank + (size_t)p * n * n;
+  for (int v = threadIdx.x; v < n; v += blockDim.x) s_rowa[v] = R[(size_t)a * n + v];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  uint2* EAo = ea + (size_t)p * E;
+  for (int b = warp; b < a; b += nwarps) {
+    const int r = s_rowa[b];
+    if (r >= T) continue;                    // beyond the threshold: not in the filtration
+    const int* rb = R + (size_t)b * n;
+    int found = -1;
+    for (int base = ((n - 1) | 31); base >= 31; base -= 32) {   // chunks from the top, lanes descending
+      const int v = base - lane;
+      const bool ha = v < n && s_rowa[v] < r;
+      if (!__any_sync(0xffffffffu, ha)) continue;
+      const bool hit = ha && __ldg(&rb[v]) < r;
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (m) { found = base - (__ffs(m) - 1); break; }
+    }
+    if (lane == 0) {
+      if (found < 0 && mst[(size_t)p * E + r]) found = -2;
+      EAo[r] = make_uint2(((uint32_t)a << 16) | (uint32_t)b, (uint32_t)found);
+      if (found == -1) {
+        const int pos = atomicAdd(&bcount[p], 1);
+        if (pos < cap1) blist[(size_t)p * cap1 + pos] = r;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // residual reduction
 //
@@ -2315,7 +2355,13 @@ static int rips_enqueue(const float* dm, int n, int batch, int maxdim, float thr
     dim3 g((unsigned)((E * 32 + 255) / 256), batch);
     {
       StageScope st(STAGE_RIPS_APPARENT, stream);
-      apparent_kernel<<<g, 256, 0, stream>>>(L.rank, L.ends, L.mst, L.T, n, E, L.apex, L.ea, L.blist, L.bcount, cap1p, L.stats);
+      if (n <= 12288 && option("rips_apparent_rows") != 0) {
+        const size_t dyn = sizeof(int) * (size_t)n;
+        if (dyn > 48 * 1024) TDA_CUDA_CHECK(cudaFuncSetAttribute(apparent_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        apparent_rows_kernel<<<dim3((unsigned)n, (unsigned)batch), 256, dyn, stream>>>(L.rank, L.mst, L.T, n, E, L.ea, L.blist, L.bcount, cap1p);
+      } else {
+        apparent_kernel<<<g, 256, 0, stream>>>(L.rank, L.ends, L.mst, L.T, n, E, L.apex, L.ea, L.blist, L.bcount, cap1p, L.stats);
+      }
     }
     count_launch();
     TDA_LAUNCH_CHECK();

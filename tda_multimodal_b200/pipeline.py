@@ -248,15 +248,16 @@ TAIL_OPTIONS = {"rips_cluster": 8}
 
 
 def _default_groups(L, on_host):
-    """Number of groups of a sweep over L layers: four equal groups from 24 layers on (the H2D copy of a group hides behind the
-    compute of the previous ones; with resident input three or four groups are within 1 % of each other, and four equal groups
-    gave the most repeatable step: profiles/r02_tune_groups.txt -- uneven splits such as 10/9/8/5 were up to 3 % faster on one
-    set of clouds and 5 % slower, with a 10 % step-to-step spread, on another), two from 8 layers on."""
+    """Number of (equal) groups of a sweep over L layers: from 24 layers on, three groups for resident input and four for host
+    input (the H2D copy of a group hides behind the compute of the previous ones); two from 8 layers on.  Measured on C3
+    (profiles/r02_tune_groups.txt): resident 3 groups 45.7 ms, 4 groups 47.1 ms; host input 4 groups 55.1 ms, 3 groups 57+ ms.
+    Uneven splits (10/9/8/5 ...) were up to 3 % faster on one set of clouds and 5 % slower, with a 10 % step-to-step spread, on
+    another: not used."""
     if L < 8:
         return 1
     if L < 24:
         return 2
-    return 4
+    return 4 if on_host else 3
 
 
 def _copy_stream(device):
