@@ -103,6 +103,16 @@ int tda_knn_smooth(const float* D, int n, int m, int batch, int k, float local_c
  *   float32 (0 = empty slot), eps [batch,2nk] float32 = max_w/w, or -1 for empty slots and for entries pruned by
  *   w < max_w/n_epochs; max_weight [batch] float32.
  */
+/* tda_knn_fused: exact kNN + sigma/rho of the rows [row_begin, row_end) of ONE cloud X [n,d] against all of its points WITHOUT the
+ *   n x n distance matrix (the per-rank body of the row-sharded kNN of a 100k-point cloud, config C5 of
+ *   BASELINE.json): tda_pdist on blocks of `row_block` rows (tensor-core GEMM), each block consumed by the top-k kernel and
+ *   overwritten by the next.  Outputs are indexed from row_begin: knn_idx / knn_dist [row_end-row_begin, k], sigma / rho
+ *   [row_end-row_begin]; column indices are global.  The sigma floor of rows without a positive neighbour distance uses the mean
+ *   distance of the row block.  ws: tda_knn_fused_workspace_bytes(n, d, row_block), 256-byte aligned. */
+size_t tda_knn_fused_workspace_bytes(int n, int d, int row_block);
+int tda_knn_fused(const float* X, int n, int d, int row_begin, int row_end, int k, int metric, float disconnect,
+                  float local_connectivity, int32_t* knn_idx, float* knn_dist, float* sigma, float* rho, int row_block, void* ws,
+                  size_t ws_bytes, void* stream);
 int tda_fuzzy_graph(const int32_t* knn_idx, const float* knn_dist, const float* sigma, const float* rho, int n, int k, int batch,
                     float mix_ratio, int n_epochs, int32_t* head, int32_t* tail, float* weight, float* eps, float* max_weight,
                     void* stream);

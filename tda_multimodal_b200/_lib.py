@@ -33,6 +33,9 @@ PROTOTYPES = {
     "tda_umap_rescale": (c_int, [c_void_p, c_int, c_int, c_int, c_float, ctypes.c_uint64, c_void_p]),
     "tda_umap_transform_init": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tda_knn_fused_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "tda_knn_fused": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                              c_void_p, c_size_t, c_void_p]),
     "tda_spectral_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "tda_spectral_init_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "tda_spectral_init": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.c_uint64, c_void_p, c_int, c_int,

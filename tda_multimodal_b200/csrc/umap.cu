@@ -1168,6 +1168,51 @@ extern "C" int tda_knn_smooth(const float* D, int n, int m, int batch, int k, fl
   return TDA_OK;
 }
 
+// ---- exact kNN + sigma/rho of the rows [row_begin, row_end) of ONE cloud against all of its points, without the n x n matrix:
+// the tensor-core distance GEMM runs on blocks of `row_block` rows and every block goes straight into the top-k kernel (the block
+// lives in the workspace and is overwritten by the next one).  This is the per-rank body of the row-sharded kNN of config C5
+// (SURVEY.md section 8b `tda_knn_fused`, section 8e).
+namespace tda { namespace umap {
+__global__ void zero_self_kernel(float* __restrict__ D, int rows, int m, int col0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows && col0 + i < m) D[(size_t)i * m + col0 + i] = 0.f;   // the point itself: exactly zero (sklearn zeroes the diagonal)
+}
+} }
+extern "C" size_t tda_knn_fused_workspace_bytes(int n, int d, int row_block) {
+  if (n <= 0 || d <= 0 || row_block <= 0) return 0;
+  const int rb = row_block < n ? row_block : n;
+  return ((tda_pdist_workspace_bytes(rb, n, d, 1, 0) + 255) & ~(size_t)255) + ((sizeof(float) * (size_t)rb * (size_t)n + 255) & ~(size_t)255) + 1024;
+}
+extern "C" int tda_knn_fused(const float* X, int n, int d, int row_begin, int row_end, int k, int metric, float disconnect,
+                             float local_connectivity, int32_t* knn_idx, float* knn_dist, float* sigma, float* rho, int row_block, void* ws,
+                             size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!X || !knn_idx || !knn_dist || !sigma || !rho || !ws || n <= 0 || d <= 0 || row_begin < 0 || row_end > n || row_begin >= row_end || row_block <= 0)
+    return set_error(TDA_ERR_INVALID, "tda_knn_fused: bad arguments");
+  if (k < 1 || k > n) return set_error(TDA_ERR_INVALID, "tda_knn_fused: k=%d out of range (1..%d)", k, n);
+  const int rb = row_block < n ? row_block : n;
+  const size_t need = tda_knn_fused_workspace_bytes(n, d, rb);
+  if (ws_bytes < need) return set_error(TDA_ERR_WORKSPACE, "tda_knn_fused: workspace %zu < required %zu", ws_bytes, need);
+  if ((((uintptr_t)ws) & 255) != 0) return set_error(TDA_ERR_INVALID, "tda_knn_fused: workspace must be 256-byte aligned");
+  const size_t pd_bytes = (tda_pdist_workspace_bytes(rb, n, d, 1, 0) + 255) & ~(size_t)255;
+  float* Dblk = (float*)((char*)ws + pd_bytes);
+  double* ksum = (double*)((char*)Dblk + ((sizeof(float) * (size_t)rb * (size_t)n + 255) & ~(size_t)255));
+  for (int b0 = row_begin; b0 < row_end; b0 += rb) {
+    const int rows = (row_end - b0) < rb ? (row_end - b0) : rb;
+    // Y = X + something would be "the same set" for tda_pdist; a row block against all points is the general (two-operand) case
+    int rc = tda_pdist(X + (size_t)b0 * d, X, rows, n, d, 1, metric, disconnect, Dblk, ws, pd_bytes, stream_);
+    if (rc != TDA_OK) return rc;
+    tda::umap::zero_self_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(Dblk, rows, n, b0);
+    count_launch();
+    const size_t off = (size_t)(b0 - row_begin);
+    rc = tda_knn_smooth(Dblk, rows, n, 1, k, local_connectivity, 1.0f, 64, knn_idx + off * k, knn_dist + off * k, sigma + off, rho + off, ksum, 64,
+                        stream_);
+    if (rc != TDA_OK) return rc;
+  }
+  TDA_LAUNCH_CHECK();
+  return TDA_OK;
+}
+
 extern "C" int tda_fuzzy_graph(const int32_t* knn_idx, const float* knn_dist, const float* sigma, const float* rho, int n, int k, int batch,
                                float mix_ratio, int n_epochs, int32_t* head, int32_t* tail, float* weight, float* eps, float* max_weight,
                                void* stream_) {

@@ -170,8 +170,8 @@ def knn_row_sharded(X, k, metric="cosine", rank=None, world=None, group=None, ro
     whole matrix; such rows only occur for duplicated points.)"""
     torch = _lib.require_cuda()
     import torch.distributed as dist
-    from .pdist import pdist
-    from .umap_ import DISCONNECTION_DISTANCES, knn_smooth
+    from .pdist import METRICS
+    from .umap_ import DISCONNECTION_DISTANCES
     n = X.shape[0]
     if rank is None:
         rank = dist.get_rank(group) if (dist.is_available() and dist.is_initialized()) else 0
@@ -179,16 +179,21 @@ def knn_row_sharded(X, k, metric="cosine", rank=None, world=None, group=None, ro
         world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
     r0, r1 = (n * rank) // world, (n * (rank + 1)) // world
     disc = float(DISCONNECTION_DISTANCES.get(metric, float("inf")))
-    Xc = X.contiguous()
-    parts = []
-    for b0 in range(r0, r1, row_block):
-        b1 = min(b0 + row_block, r1)
-        D = pdist(Xc[b0:b1][None], Xc[None], metric=metric, disconnect=disc)[0]      # [rows, n]
-        ar = torch.arange(b1 - b0, device=X.device)
-        D[ar, b0 + ar] = 0.0                                                          # the point itself, exactly (sklearn zeroes the diagonal)
-        parts.append(knn_smooth(D[None], k, local_connectivity=local_connectivity))
-        del D
-    local = [torch.cat([p[q][0] for p in parts], dim=0) for q in range(4)]            # idx, dist, sigma, rho of rows [r0, r1)
+    Xc = X.to(torch.float32).contiguous()
+    d = Xc.shape[1]
+    L = _lib.lib()
+    rows = r1 - r0
+    idx = torch.empty((rows, k), dtype=torch.int32, device=X.device)
+    dst = torch.empty((rows, k), dtype=torch.float32, device=X.device)
+    sig = torch.empty((rows,), dtype=torch.float32, device=X.device)
+    rho = torch.empty((rows,), dtype=torch.float32, device=X.device)
+    if rows > 0:
+        with torch.cuda.device(X.device):   # one C call: GEMM row block -> top-k, block after block (tda_knn_fused)
+            ws_bytes = int(L.tda_knn_fused_workspace_bytes(n, d, int(row_block)))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=X.device)
+            _lib.check(L.tda_knn_fused(_lib.ptr(Xc), n, d, r0, r1, int(k), METRICS[metric], disc, float(local_connectivity), _lib.ptr(idx),
+                                       _lib.ptr(dst), _lib.ptr(sig), _lib.ptr(rho), int(row_block), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
+    local = [idx, dst, sig, rho]                                                       # rows [r0, r1)
     if world == 1 or not (dist.is_available() and dist.is_initialized()):
         return tuple(t[None] for t in local)      # no process group: the caller gets this rank's rows only
     # ragged row counts: pad every block to the largest, gather, trim
