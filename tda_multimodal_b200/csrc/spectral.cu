@@ -103,10 +103,15 @@ __device__ __forceinline__ uint32_t hash32(uint64_t x) {
 }
 
 // eigenpairs of the meff x meff tridiagonal T (alpha diagonal, beta off-diagonal), the `dim` largest: Sturm-sequence multisection
-// per eigenvalue (one warp each), inverse iteration (one thread each), Gram-Schmidt between the Ritz coefficient vectors.
+// per eigenvalue (one warp each, 33 sections per round), inverse iteration (one thread each: the tridiagonal LU with partial
+// pivoting is factored ONCE in shared memory, then three solves), Gram-Schmidt between the Ritz coefficient vectors.
 // All threads of the CTA call; returns nev.  (Deterministic: CTAs that call it with equal inputs get equal outputs.)
+// Measured before this version (scripts/lanczos_phase_cycles.py): 1.0 M of the 2.85 M cycles of a component -- the LU was
+// re-factored in every sweep on arrays in local memory.
 __device__ __forceinline__ int tridiag_eigs(int meff, int dim, const double* s_alpha, const double* s_beta, double* s_lam,
                                             double (*s_vec)[kMaxKrylov], int tid, int lane, int warp) {
+  __shared__ double s_lu[kMaxDim][4][kMaxKrylov];      // dl (multipliers), dd (diagonal), du, du2 of the factored T - lam I
+  __shared__ unsigned char s_piv[kMaxDim][kMaxKrylov];
   const int nev = min(dim, meff);
   if (warp < nev) {
     // Gershgorin bounds
@@ -116,7 +121,7 @@ __device__ __forceinline__ int tridiag_eigs(int meff, int dim, const double* s_a
       lo = fmin(lo, s_alpha[i] - r); hi = fmax(hi, s_alpha[i] + r);
     }
     const int want = meff - 1 - warp;  // index (ascending) of the eigenvalue this warp looks for
-    for (int round = 0; round < 14; ++round) {
+    for (int round = 0; round < 11; ++round) {   // the bracket shrinks 33x per round: 33^11 > 2^53 of the Gershgorin width
       const double x = lo + (hi - lo) * (double)(lane + 1) / 33.0;
       int cnt = 0;  // number of eigenvalues < x (Sturm sequence)
       double d = 1.0;
@@ -137,39 +142,42 @@ __device__ __forceinline__ int tridiag_eigs(int meff, int dim, const double* s_a
   }
   __syncthreads();
   if (tid < nev) {
-    // inverse iteration on (T - lam I) with a tiny shift; tridiagonal LU with partial pivoting, 3 sweeps
+    // inverse iteration on (T - lam I) with a tiny shift; tridiagonal LU with partial pivoting, factored once, 3 solves
     const double lam = s_lam[tid] + 1e-9 * (1.0 + fabs(s_lam[tid])) * (tid + 1);
     double* y = s_vec[tid];
-    for (int i = 0; i < meff; ++i) y[i] = 1.0 + 0.01 * ((i * 37 + tid * 11) % 17);
-    double dl[kMaxKrylov], dd[kMaxKrylov], du[kMaxKrylov], du2[kMaxKrylov];
-    unsigned char piv[kMaxKrylov];
+    double* dl = s_lu[tid][0];
+    double* dd = s_lu[tid][1];
+    double* du = s_lu[tid][2];
+    double* du2 = s_lu[tid][3];
+    unsigned char* piv = s_piv[tid];
+    for (int i = 0; i < meff; ++i) {
+      y[i] = 1.0 + 0.01 * ((i * 37 + tid * 11) % 17);
+      dd[i] = s_alpha[i] - lam;
+      du[i] = i < meff - 1 ? s_beta[i] : 0.0;
+      dl[i] = i < meff - 1 ? s_beta[i] : 0.0;
+      du2[i] = 0.0;
+    }
+    for (int i = 0; i < meff - 1; ++i) {
+      if (fabs(dd[i]) >= fabs(dl[i])) {
+        piv[i] = 0;
+        if (dd[i] == 0.0) dd[i] = 1e-300;
+        const double f = dl[i] / dd[i];
+        dl[i] = f;
+        dd[i + 1] -= f * du[i];
+      } else {
+        piv[i] = 1;
+        const double f = dd[i] / dl[i];
+        dd[i] = dl[i];
+        dl[i] = f;
+        const double t = du[i];
+        du[i] = dd[i + 1];
+        dd[i + 1] = t - f * du[i];
+        du2[i] = du[i + 1];
+        du[i + 1] = -f * du2[i];
+      }
+    }
+    if (dd[meff - 1] == 0.0) dd[meff - 1] = 1e-300;
     for (int sweep = 0; sweep < 3; ++sweep) {
-      for (int i = 0; i < meff; ++i) {
-        dd[i] = s_alpha[i] - lam;
-        du[i] = i < meff - 1 ? s_beta[i] : 0.0;
-        dl[i] = i < meff - 1 ? s_beta[i] : 0.0;
-        du2[i] = 0.0;
-      }
-      for (int i = 0; i < meff - 1; ++i) {
-        if (fabs(dd[i]) >= fabs(dl[i])) {
-          piv[i] = 0;
-          if (dd[i] == 0.0) dd[i] = 1e-300;
-          const double f = dl[i] / dd[i];
-          dl[i] = f;
-          dd[i + 1] -= f * du[i];
-        } else {
-          piv[i] = 1;
-          const double f = dd[i] / dl[i];
-          dd[i] = dl[i];
-          dl[i] = f;
-          const double t = du[i];
-          du[i] = dd[i + 1];
-          dd[i + 1] = t - f * du[i];
-          du2[i] = du[i + 1];
-          du[i + 1] = -f * du2[i];
-        }
-      }
-      if (dd[meff - 1] == 0.0) dd[meff - 1] = 1e-300;
       for (int i = 0; i < meff - 1; ++i) {
         if (piv[i]) { const double t = y[i]; y[i] = y[i + 1]; y[i + 1] = t - dl[i] * y[i]; }
         else y[i + 1] -= dl[i] * y[i];
@@ -408,6 +416,7 @@ struct LanczosClusterParams {
   const int* comp; const int* csize; int min_size_multi;   // (components smaller than min_size_multi of a multi-component cloud are skipped)
   int2* gent;                  // [batch, Gy, C, slots] global room for a CSR slice that does not fit in shared memory (rare: hubs)
   int maxcomp;                 // clouds with more components are skipped; stride of evals
+  int debug;                   // option spectral_debug: cloud 0 prints the cycles of the phases of its first component
 };
 // dynamic shared memory: Qloc[(kMaxKrylov + 2) * rows_per] | qfull[n] | w[rows_per] | part[3][C][kMaxKrylov + 2] | coef[kMaxKrylov + 2]
 //                        | roff[rows_per + 1] | rcnt[rows_per] | ent[ent_cap] (int2: column, value bits)
@@ -577,10 +586,15 @@ __device__ __forceinline__ void lc_component(const LanczosClusterParams& P, cons
     __syncthreads();
   }
   int meff = m;
+  long long cyc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tq = clock64();
+  const long long t_setup = tq;
+#define TDA_LC_T(k) do { if (P.debug) { const long long tn_ = clock64(); cyc[k] += tn_ - tq; tq = tn_; } } while (0)
   for (int j = 0; j < m; ++j) {
     const float* qj = Qloc + (size_t)(j + 1) * RP;
     float* wn = Qloc + (size_t)(j + 2) * RP;   // becomes q_{j+1}
     broadcast_rows(qj);
+    TDA_LC_T(0);
     // w = A q_j on this CTA's rows (one thread per row, entries in column order)
     for (int i = tid; i < nr; i += kLcThreads) {
       float acc = 0.f;
@@ -588,16 +602,34 @@ __device__ __forceinline__ void lc_component(const LanczosClusterParams& P, cons
       w[i] = acc;
     }
     __syncthreads();
+    TDA_LC_T(1);
     // classical Gram-Schmidt, twice, against u1 and q_0..q_j; the coefficient on q_j is alpha_j
     for (int pass = 0; pass < 2; ++pass) {
-      for (int v = warp; v <= j + 1; v += nwarps) {
-        const float* qv = Qloc + (size_t)v * RP;
-        float s0 = 0.f;
-        for (int i = lane; i < nr; i += 32) s0 += w[i] * qv[i];
-        s0 = warp_sum_f32(s0);
-        if (lane == 0) coef[v] = s0;
+      // four vectors per warp and trip: they share the loads of w and their four butterflies interleave (each sum is taken in
+      // the same order as a one-vector-at-a-time loop: same bits)
+      for (int vb = warp * 4; vb <= j + 1; vb += nwarps * 4) {
+        const int nv = min(4, j + 2 - vb);
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int i = lane; i < nr; i += 32) {
+          const float wi = w[i];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (u < nv) s4[u] += wi * Qloc[(size_t)(vb + u) * RP + i];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) s4[u] += __shfl_xor_sync(0xffffffffu, s4[u], o);
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (u < nv) coef[vb + u] = s4[u];
+        }
       }
+      TDA_LC_T(2);
       cluster_reduce(j + 2);
+      TDA_LC_T(3);
       if (tid == 0) { if (pass == 0) s_alpha[j] = (double)coef[j + 1]; else s_alpha[j] += (double)coef[j + 1]; }
       for (int i = tid; i < nr; i += kLcThreads) {
         float v0 = w[i];
@@ -605,6 +637,7 @@ __device__ __forceinline__ void lc_component(const LanczosClusterParams& P, cons
         w[i] = v0;
       }
       __syncthreads();
+      TDA_LC_T(4);
     }
     float a2 = 0.f;
     for (int i = tid; i < nr; i += kLcThreads) a2 += w[i] * w[i];
@@ -617,9 +650,11 @@ __device__ __forceinline__ void lc_component(const LanczosClusterParams& P, cons
     if (beta < 1e-6f || j == m - 1) { meff = j + 1; break; }   // (same decision in every CTA: same bits)
     for (int i = tid; i < nr; i += kLcThreads) wn[i] = w[i] / beta;
     __syncthreads();
+    TDA_LC_T(5);
   }
   __syncthreads();
   const int nev = tridiag_eigs(meff, dim, s_alpha, s_beta, s_lam, s_vec, tid, lane, warp);
+  TDA_LC_T(6);
   if (cr == 0 && tid == 0 && P.evals)
     for (int a = 0; a < kMaxDim; ++a) P.evals[((size_t)p * P.maxcomp + c) * kMaxDim + a] = a < nev ? (float)s_lam[a] : 0.f;
   float* out = P.out + (size_t)p * nfull * dim;
@@ -633,6 +668,11 @@ __device__ __forceinline__ void lc_component(const LanczosClusterParams& P, cons
       out[(size_t)glob[i] * dim + a] = v;
     }
   }
+  TDA_LC_T(7);
+  if (P.debug && p == 0 && blockIdx.y == 0 && tid == 0)
+    printf("lanczos cloud 0 comp %d cta %u: n=%d nr=%d meff=%d nent=%d | cycles: broadcast %lld spmv %lld dots %lld reduce %lld update %lld norm %lld tridiag %lld ritz %lld | since loop start %lld\n",
+           c, cr, n, nr, meff, nent, cyc[0], cyc[1], cyc[2], cyc[3], cyc[4], cyc[5], cyc[6], cyc[7], clock64() - t_setup);
+#undef TDA_LC_T
   lc_sync();   // nobody leaves (or starts the next component) while its shared memory may still be written
 }
 // grid: (batch * C, Gy) CTAs in clusters of C.  Cluster (p, y) lays out the components y, y + Gy, ... of cloud p one after the other
@@ -907,7 +947,7 @@ static bool cluster_shape(int n, int slots, ClusterShape& S) {
   constexpr int NV = kMaxKrylov + 2;
   const size_t fixed = sizeof(float) * ((size_t)NV * RP + (size_t)n + (size_t)RP + 3 * (size_t)kLcMaxCluster * NV + NV) +
                        sizeof(int) * ((size_t)(RP + 1) + RP + (size_t)n + RP + 4);
-  const size_t smem_max = (size_t)220 * 1024;
+  const size_t smem_max = (size_t)206 * 1024;   // (the kernel has ~18 KB of static shared memory: Lanczos scalars + the tridiagonal LU)
   const size_t want_ent = (size_t)slots / C + (size_t)slots / (2 * C) + 64;   // 1.5x the mean slice
   if (fixed + 8 * 1024 >= smem_max) return false;
   size_t cap_ent = (smem_max - fixed) / sizeof(int2);
@@ -928,6 +968,7 @@ static int launch_cluster_lanczos(const int32_t* head, const int32_t* tail, cons
   Q.head = head; Q.tail = tail; Q.weight = weight; Q.eps = eps; Q.slots = slots; Q.n = n; Q.dim = dim;
   Q.deg = degree; Q.out = Y; Q.evals = evals; Q.seed = seed; Q.rows_per = S.RP; Q.ent_cap = S.cap_ent;
   Q.gent = gent; Q.ncomp = ncomp; Q.comp = comp; Q.csize = csize; Q.min_size_multi = min_size_multi; Q.maxcomp = ncomp ? maxcomp : 1;
+  Q.debug = (int)option("spectral_debug");
   TDA_CUDA_CHECK(cudaFuncSetAttribute(lanczos_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.dyn));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
