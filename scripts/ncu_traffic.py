@@ -6,8 +6,8 @@ pipe, SM / DRAM throughput).  bench.py only READS that JSON (roofline.traffic); 
 import csv, json, os, sys
 
 STAGE_OF = {"pdist_gemm_kernel": "pdist_gemm", "prep_kernel": "pdist_prep", "knn_smooth_block_kernel": "knn_smooth", "sgd_cluster_kernel": "umap_sgd",
-            "lanczos_cluster_kernel": "spectral_init", "apparent_kernel": "rips_apparent", "rips_sweep2_kernel": "rips_reduce",
-            "boruvka_scan_kernel": "rips_h0"}
+            "lanczos_cluster_kernel": "spectral_init", "apparent_rows_kernel": "rips_apparent", "apparent_kernel": "rips_apparent", "rips_sweep2_kernel": "rips_reduce",
+            "boruvka_scan_kernel": "rips_h0", "rank_scatter_kernel": "rips_edge_sort"}
 KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",

@@ -141,3 +141,32 @@ def test_persim_plot_diagrams_with_stub_matplotlib(monkeypatch):
     persim.plot_diagrams([h0, np.zeros((0, 2))], show=False)  # empty H1 (happens on the reference's own clouds)
     assert persim.bottleneck(h1, h1) == 0.0
     sys.modules.pop("persim", None)
+
+
+def test_sweep_grouping_and_cached_index_sets():
+    """host logic of the sweep: default group counts (three groups for resident input from 24 layers on, four for host input,
+    two from 8 layers on), the option override for the last group, and the C4 index sets (seeded, cached, read-only)."""
+    from tda_multimodal_b200 import pipeline, workloads
+    assert [pipeline._default_groups(L, False) for L in (1, 7, 8, 23, 24, 32, 64)] == [1, 1, 2, 2, 3, 3, 3]
+    assert [pipeline._default_groups(L, True) for L in (4, 8, 24, 32)] == [1, 2, 4, 4]
+    assert pipeline.TAIL_OPTIONS == {"rips_cluster": 8}
+    a = workloads.c4_resample_indices(3, 2000, 8, 1000)
+    b = workloads.c4_resample_indices(3, 2000, 8, 1000)
+    assert a is b and not a.flags.writeable and a.shape == (8, 1000)
+    assert not np.array_equal(a, workloads.c4_resample_indices(4, 2000, 8, 1000))
+
+
+def test_bench_algorithmic_work_covers_every_stage():
+    """bench.py's roofline table: every stage the library times has an algorithmic-work figure."""
+    import importlib.util
+    import types
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from tda_multimodal_b200 import _lib
+    a = types.SimpleNamespace(points=2000, dim=4096, neighbors=15)
+    extra = {"sgd_fired_per_layer": 6.3e6, "reduce_rows_per_layer": 2.2e6, "reduce_heavy_rows_per_layer": 1.6e5}
+    for stage in _lib.STAGES:
+        kind, work = bench.algorithmic_work(stage, a, 32, extra)
+        assert kind in ("hbm", "tensor") and work > 0, stage
+    assert bench.union_ms([(0, 2), (1, 3), (5, 6)]) == 4.0
