@@ -200,11 +200,12 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.proc, self.path = index, None, f"/tmp/tda_clocks_{os.getpid()}.csv"
+        self.active = False
 
     def start(self):
         """NVML from a thread of this process (the same counters nvidia-smi prints, without a second process polling the driver
         every 200 ms); falls back to `nvidia-smi -lms 200` when pynvml is missing."""
-        self.samples, self.thread, self.stop_flag = [], None, False
+        self.samples, self.thread, self.stop_flag, self.active = [], None, False, False
         try:
             import threading
             import pynvml
@@ -220,7 +221,9 @@ class ClockSampler:
             def loop():
                 while not self.stop_flag:
                     try:
-                        self.samples.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), mx, int(get_reasons(h))))
+                        smp = (float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), mx, int(get_reasons(h)))
+                        if self.active:          # the thread is started before the warm-up (NVML's first queries are slow and
+                            self.samples.append(smp)   # take driver locks); only samples of the timed regions are kept
                     except Exception:
                         pass
                     time.sleep(0.1)
@@ -434,11 +437,12 @@ def run_b200(a):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), res
 
-    for _ in range(a.warmup):
-        step_resident()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(a.warmup):
+        step_resident()
+    sampler.active = True
     L.tda_launch_count_reset()
     L.tda_stage_timing_reset()
     L.tda_stage_timing_enable(1)
@@ -447,8 +451,10 @@ def run_b200(a):
     stages = _lib.stage_times()
     timeline = _lib.stage_timeline()
     L.tda_stage_timing_enable(0)
+    sampler.active = False
     for _ in range(a.warmup):        # the host-input path has its own streams (and allocator pools): warm it up as well, untimed
         step_e2e()
+    sampler.active = True
     ms_e2e, (dg2, out2) = timed(step_e2e, a.steps, "e2e")
     clocks = sampler.stop() if rank == 0 else None
 

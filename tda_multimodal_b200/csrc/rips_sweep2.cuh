@@ -475,14 +475,26 @@ struct Sweeper2 {
     uint32_t nheavy = 0, nrows = 0, nscan = 0;
     int status = WC_NONE;
     int myrec = -1;   // the record this sweep publishes (allocated when it first needs one)
+    // the table entries of the NEXT 32-row group are requested while this group is examined: almost every group has no heavy
+    // row and the sweep just moves on, so the L2 latency of the tables (the whole cost of such a group) overlaps the heavy test
+    uint32_t pf_base = 0xffffffffu;
+    uint2 pf_ea = make_uint2(0u, 0xffffffffu), pf_par = make_uint2(0u, 0u);
+    const uint32_t max_rows = (uint32_t)P.s2_wc_max_rows;
     while (status == WC_NONE) {
       if (pos >= (uint32_t)T) { status = WC_ESSENTIAL; break; }
-      if (nrows > kWcMaxRows || nheavy > kWcMaxHeavy) { status = WC_BIG; break; }
+      if (nrows > max_rows || nheavy > kWcMaxHeavy) { status = WC_BIG; break; }
       const uint32_t base = pos & ~31u;
       const uint32_t row = base + lane;
       const bool inwin = row >= pos && row < (uint32_t)T;
       uint2 ea = make_uint2(0u, 0xffffffffu), par = make_uint2(0u, 0u);
-      if (inwin) { ea = __ldg(&EA[row]); par = __ldg(&PAR[row]); }
+      if (base == pf_base && pos == base) { ea = pf_ea; par = pf_par; }   // (a whole group: what was prefetched is exactly this)
+      else if (inwin) { ea = __ldg(&EA[row]); par = __ldg(&PAR[row]); }
+      {
+        const uint32_t nrow = base + 32u + lane;
+        pf_base = base + 32u;
+        pf_ea = make_uint2(0u, 0xffffffffu); pf_par = make_uint2(0u, 0u);
+        if (nrow < (uint32_t)T) { pf_ea = __ldg(&EA[nrow]); pf_par = __ldg(&PAR[nrow]); }
+      }
       nrows += 32;
       const bool app = (int)ea.y >= 0;
       const uint32_t c = ea.x >> 16, d = ea.x & 0xffffu;
