@@ -87,6 +87,7 @@ static OptionDef g_options[] = {
     {"sgd_cluster", 0},        // CTAs per cloud of the deterministic fit kernel (1, 2, 4 or 8; 0 = auto: 8 for up to 4 clouds per launch, else 4)
     {"sgd_tile", 16},          // vertices per warp task of that kernel (1..16; tasks are handed out dynamically)
     {"knn_loads", 8},          // 16-byte loads per lane in flight in the k <= 16 kNN kernel (8 or 16)
+    {"rips_debug", 0},         // sweep2 prints one line of counters and phase cycles per cloud (diagnostics)
     {"spectral_debug", 0},     // print the phase cycles of the cluster Lanczos kernel for cloud 0 (diagnostics)
     {"debug_sync", 0},         // synchronise after every kernel of tda_rips_h2 (fault location)
     {"h2_stats", 0},           // print the H2 reducer's device counters to stderr

@@ -434,6 +434,7 @@ struct ReduceParams {
   int s2_nrec;                              // records per cloud (every reduction of a column writes a new one)
   int s2_warp_engine;                       // 1: short columns are reduced by single warps first (stage A + commit loop)
   int s2_wc_max_rows;                       // rows a warp sweeps before it hands its column to the cluster engine
+  int s2_debug;                             // option rips_debug: one line of counters per cloud (device printf)
   int s2_w0, s2_wsparse, s2_wmax, s2_dense_min, s2_dense_div;
 };
 
@@ -2379,6 +2380,7 @@ static int rips_enqueue(const float* dm, int n, int batch, int maxdim, float thr
     P.verify_mode = L.reducer == 2 ? 1 : 0;
     P.par = L.par; P.s2_pend = L.s2_pend; P.s2_heavy = L.s2_heavy; P.s2_rec = L.s2_rec; P.s2_lists = L.s2_lists; P.s2_nrec = L.s2_nrec;
     P.s2_warp_engine = option("rips_warp_engine") != 0 ? 1 : 0;
+    P.s2_debug = (int)option("rips_debug");
     P.s2_wc_max_rows = (int)option("rips_wc_max_rows");
     if (P.s2_wc_max_rows < 1024) P.s2_wc_max_rows = 1024;
     P.s2_wmax = L.s2_wmax;

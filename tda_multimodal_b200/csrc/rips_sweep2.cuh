@@ -980,7 +980,10 @@ struct Sweeper2 {
             for (int b = 0; b < kS2Batch; ++b) {
               if (Mr[b] == 0xffffffffu) continue;
               int bb = __reduce_max_sync(kFull, best[b]);
-              if (big[b]) bb = exact_row(Mr[b], cd[b] >> 16, cd[b] & 0xffffu, xm[b]);   // (dense candidate set: the whole lune at once, coalesced)
+              if (big[b]) {   // (dense candidate set: the whole lune at once, coalesced)
+                bb = exact_row(Mr[b], cd[b] >> 16, cd[b] & 0xffffu, xm[b]);
+                if (lane == 0) atomicAdd(&S.st[S2_EXACT], 1ull);
+              }
               if (bb >= 0 && lane == 0) atomicMin(&S.fail_key, (Mr[b] - base_row) * (uint32_t)n + (uint32_t)(n - 1 - bb));
             }
           }
@@ -1208,6 +1211,10 @@ struct Sweeper2 {
       csync();
       if (gtid == 0) S.vcount = 0;
     }
+    if (gtid == 0 && P.s2_debug)
+      printf("sweep2 cloud %d: columns %d to_cluster %llu windows %llu heavy %llu exact_rows %llu events %llu deaths %llu late_rows %llu | Mcyc warp %.2f commit %.2f subst %.2f verify %.2f events %.2f pm/final %.2f | barriers %llu (%.2f Mcyc)\n",
+             p, nb, S.wc_big, S.st[S2_WINDOWS], S.st[S2_HEAVY], S.st[S2_EXACT], S.st[S2_EVENTS], S.st[S2_DEATHS], S.st[S2_LATE], cyc[0] / 1e6, cyc[1] / 1e6,
+             cyc[2] / 1e6, cyc[3] / 1e6, cyc[4] / 1e6, cyc[5] / 1e6, n_sync, cyc_sync / 1e6);
     if (gtid == 0) {
       P.counts[p * 4 + 1] = S.nrows;
       P.counts[p * 4 + 3] = S.abort_flag;
