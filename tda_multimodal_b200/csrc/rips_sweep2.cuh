@@ -766,10 +766,17 @@ struct Sweeper2 {
               base[u] = (xa ^ xb) & 1u;
             }
           }
+          // the window bitmaps and the two lists live in CTA 0: the list cursors are remote atomics for the other CTAs (~700 cycles
+          // each), so the entries of the kS2Unroll groups of a trip are appended with ONE atomic per list
+          uint2 pent[kS2Unroll];
+          unsigned bpend[kS2Unroll], bheavy[kS2Unroll];
+          uint32_t np_trip = 0, nh_trip = 0;
 #pragma unroll
           for (int u = 0; u < kS2Unroll; ++u) {
             const uint32_t g = gb + u;
-            if (g >= g1) break;
+            bpend[u] = 0u; bheavy[u] = 0u;
+            pent[u] = make_uint2(0u, 0u);
+            if (g >= g1) continue;   // (warp-uniform)
             const uint32_t row = (g << 5) + lane;
             const bool app = (int)ea[u].y >= 0;   // (rows outside the window carry apex = -1)
             const uint32_t pa = par[u].x & 0x7fffffffu, pb = par[u].y & 0x7fffffffu;
@@ -783,10 +790,29 @@ struct Sweeper2 {
             const unsigned bdone = __ballot_sync(kFull, computed);
             if (lane == 0) { xo[g - g0] = xold[u]; xs[g - g0] = (xold[u] & ~bapp) | bone; done[g - g0] = bdone; }
             const bool pend = app && (depA || depB);
-            const uint2 pent = make_uint2((row - base_row) | (base[u] << 31) | ((depA ? 1u : 0u) << 30) | ((depB ? 1u : 0u) << 29),
-                                          (depA ? (pa - base_row) : 0u) | ((depB ? (pb - base_row) : 0u) << 16));
-            warp_append(pend, pent, &S.npend[0], [&](uint32_t i) { return pend_ref(0, i); });
-            warp_append(heavy, make_uint2(row, ea[u].x), &S.nheavy, [&](uint32_t i) { return heavy_ref(i); });
+            pent[u] = make_uint2((row - base_row) | (base[u] << 31) | ((depA ? 1u : 0u) << 30) | ((depB ? 1u : 0u) << 29),
+                                 (depA ? (pa - base_row) : 0u) | ((depB ? (pb - base_row) : 0u) << 16));
+            bpend[u] = __ballot_sync(kFull, pend);
+            bheavy[u] = __ballot_sync(kFull, heavy);
+            np_trip += (uint32_t)__popc(bpend[u]);
+            nh_trip += (uint32_t)__popc(bheavy[u]);
+          }
+          if (np_trip | nh_trip) {
+            uint32_t pbase = 0, hbase = 0;
+            if (lane == 0) {
+              if (np_trip) pbase = atomicAdd(&S.npend[0], np_trip);
+              if (nh_trip) hbase = atomicAdd(&S.nheavy, nh_trip);
+            }
+            pbase = __shfl_sync(kFull, pbase, 0);
+            hbase = __shfl_sync(kFull, hbase, 0);
+            const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+            for (int u = 0; u < kS2Unroll; ++u) {
+              if ((bpend[u] >> lane) & 1u) *pend_ref(0, pbase + (uint32_t)__popc(bpend[u] & lt)) = pent[u];
+              if ((bheavy[u] >> lane) & 1u) *heavy_ref(hbase + (uint32_t)__popc(bheavy[u] & lt)) = make_uint2(((gb + u) << 5) + lane, ea[u].x);
+              pbase += (uint32_t)__popc(bpend[u]);
+              hbase += (uint32_t)__popc(bheavy[u]);
+            }
           }
         }
         csync();
@@ -926,16 +952,23 @@ struct Sweeper2 {
             // which rows of the batch have candidates, and few enough to probe them one by one: all their probes go out together
             int best[kS2Batch];
             bool big[kS2Batch];
+            // a later row than the best failure found so far cannot be the event.  The control block lives in CTA 0 (a remote read
+            // for the other CTAs: ~700 cycles), so it is read once per batch, by one lane (the test must be warp-uniform), and only
+            // if some row of the batch has candidate bits at all
+            bool anyc = false;
+#pragma unroll
+            for (int b = 0; b < kS2Batch; ++b) anyc |= Mr[b] != 0xffffffffu && (cw[b].x | cw[b].y) != 0;
+            uint32_t fk_now = 0xffffffffu;
+            if (__any_sync(kFull, anyc)) {
+              if (lane == 0) { S.nfail = 1; fk_now = *(volatile uint32_t*)&S.fail_key; }
+              fk_now = __shfl_sync(kFull, fk_now, 0);
+            }
 #pragma unroll
             for (int b = 0; b < kS2Batch; ++b) {
               best[b] = -1;
               big[b] = false;
               if (Mr[b] == 0xffffffffu) { cw[b] = make_uint2(0u, 0u); continue; }
               if (!__any_sync(kFull, (cw[b].x | cw[b].y) != 0)) continue;
-              // a later row than the best failure found so far cannot be the event (one lane reads: the test must be warp-uniform)
-              uint32_t fk_now = 0;
-              if (lane == 0) { S.nfail = 1; fk_now = *(volatile uint32_t*)&S.fail_key; }
-              fk_now = __shfl_sync(kFull, fk_now, 0);
               if (fk_now != 0xffffffffu && (Mr[b] - base_row) > fk_now / (uint32_t)n) { cw[b] = make_uint2(0u, 0u); continue; }
               const int npop = __reduce_add_sync(kFull, (unsigned)(__popc(cw[b].x) + __popc(cw[b].y)));
               if (npop > kS2ProbeMax) { big[b] = true; cw[b] = make_uint2(0u, 0u); }
