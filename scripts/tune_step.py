@@ -52,7 +52,12 @@ def main():
         if os.environ.get("TUNE_GC") == "off":
             gc.collect(); gc.disable()
         gcs0 = [g["collections"] for g in gc.get_stats()]
-        for _ in range(int(os.environ.get("TUNE_STEPS", "6"))):
+        timing_on = os.environ.get("TUNE_STAGE_TIMING") == "1"    # stage timer enabled inside the timed steps, as bench.py does
+        if timing_on:
+            L.tda_stage_timing_reset(); L.tda_stage_timing_enable(1)
+        for it_ in range(int(os.environ.get("TUNE_STEPS", "6"))):
+            if timing_on and it_ % 8 == 0:
+                L.tda_stage_timing_reset()
             m0 = torch.cuda.memory_stats().get("num_device_alloc", 0)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0 = time.perf_counter()
@@ -64,6 +69,8 @@ def main():
             ts.append(e0.elapsed_time(e1))
             host.append(1e3 * (t1 - t0))
             mallocs.append(torch.cuda.memory_stats().get("num_device_alloc", 0) - m0)
+        if timing_on:
+            L.tda_stage_timing_enable(0)
         if os.environ.get("TUNE_VERBOSE"):
             print("   gpu ms", [round(t, 1) for t in ts], "cudaMallocs", sum(mallocs), "gc collections per generation", [g["collections"] - a for g, a in zip(gc.get_stats(), gcs0)], flush=True)
         if os.environ.get("TUNE_TIMELINE"):   # timelines of the fastest and the slowest of 8 more steps

@@ -7,6 +7,7 @@ The layers are independent (no carried state but the append-only stats list, :13
 rank go through each kernel together (batch dimension = layer), and ranks split the layers (layer l -> rank
 l mod G) with a single gather of the diagrams at the end.
 """
+import gc
 import os
 
 import numpy as np
@@ -79,6 +80,41 @@ def layer_sweep(X, n_neighbors=15, n_components=3, min_dist=0.1, metric="cosine"
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
                 staged.append((Xc, ev))
+    # no garbage collection while the groups' kernels are being enqueued: a generation-1/2 pass of CPython's collector takes
+    # 25-60 ms in a process with torch loaded -- as long as half a step -- and the device idles behind it.  Once everything is
+    # queued a collection costs nothing (the host only waits for the device then).
+    gc_was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        _enqueue_groups(torch, X, on_host, chunks, bounds, streams, staged, cur, kw, maxdim, Ys, jobs, checks, Xcs)
+    finally:
+        if gc_was_enabled:
+            gc.enable()
+    res = []
+    for c, job in enumerate(jobs):
+        r = job.finish()
+        if checks[c] is not None and int(checks[c].max().item()) > 0:   # clouds with more than 32 components: the host path, for them only
+            bad = torch.nonzero(checks[c] > 0).flatten()
+            with torch.cuda.stream(streams[c]):
+                Yb = umap_fit_batch(Xcs[c][bad].contiguous(), **kw)
+                Ys[c][bad] = Yb
+                rb = rips_batch(pdist_lowdim(Yb), maxdim=maxdim)
+            for j, q in enumerate(bad.tolist()):
+                r[q] = rb[j]
+        res += r
+    del Xcs, staged
+    for st in streams[:chunks]:
+        cur.wait_stream(st)
+    Yall = None
+    if return_embedding:
+        Yall = torch.cat(Ys, dim=0)
+        for Y, st in zip(Ys, streams):
+            Y.record_stream(cur)
+    return {"embedding": Yall, "results": res}
+
+
+def _enqueue_groups(torch, X, on_host, chunks, bounds, streams, staged, cur, kw, maxdim, Ys, jobs, checks, Xcs):
+    """Enqueues the whole chain of every group on its stream; nothing here synchronises with the device."""
     for c in range(chunks):
         st = streams[c]
         st.wait_stream(cur)
@@ -106,27 +142,6 @@ def layer_sweep(X, n_neighbors=15, n_components=3, min_dist=0.1, metric="cosine"
             Ys.append(Y)
             checks.append(ncomp)
             Xcs.append(Xc)
-    res = []
-    for c, job in enumerate(jobs):
-        r = job.finish()
-        if checks[c] is not None and int(checks[c].max().item()) > 0:   # clouds with more than 32 components: the host path, for them only
-            bad = torch.nonzero(checks[c] > 0).flatten()
-            with torch.cuda.stream(streams[c]):
-                Yb = umap_fit_batch(Xcs[c][bad].contiguous(), **kw)
-                Ys[c][bad] = Yb
-                rb = rips_batch(pdist_lowdim(Yb), maxdim=maxdim)
-            for j, q in enumerate(bad.tolist()):
-                r[q] = rb[j]
-        res += r
-    del Xcs, staged
-    for st in streams[:chunks]:
-        cur.wait_stream(st)
-    Yall = None
-    if return_embedding:
-        Yall = torch.cat(Ys, dim=0)
-        for Y, st in zip(Ys, streams):
-            Y.record_stream(cur)
-    return {"embedding": Yall, "results": res}
 
 
 def silhouette_score(Y, labels, dm=None):
