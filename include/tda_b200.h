@@ -141,7 +141,9 @@ int tda_umap_transform_init(const int32_t* knn_idx, const float* knn_dist, const
  *   ws: 12*batch*n bytes, 8-byte aligned (degrees are accumulated in 64-bit fixed point: order independent, reproducible).
  *  tda_spectral_embed: for every component with >= min_size vertices, the `dim` non-trivial bottom eigenvectors of the
  *   symmetric normalised Laplacian (Lanczos, full reorthogonalisation), written as unit vectors into the component's
- *   rows of Y [batch,n,dim]; evals [batch,maxcomp,4] (eigenvalues of D^-1/2 W D^-1/2) or NULL.
+ *   rows of Y [batch,n,dim]; evals [batch,maxcomp,4] or NULL: the `dim` eigenvalues of D^-1/2 W D^-1/2 and, for dim < 4, in the
+ *   last slot the largest Ritz residual estimate |beta_m s_m| of the returned pairs after the fixed 96 Lanczos steps (ARPACK, which
+ *   umap-learn uses, iterates until that falls below its tolerance; a caller can warn or fall back to a random init on a large value).
  */
 size_t tda_spectral_workspace_bytes(int n, int batch, int maxcomp, int slots);
 /* tda_spectral_init: components + eigenvectors + multi_component_layout in one call WITHOUT a host round trip.  Every component

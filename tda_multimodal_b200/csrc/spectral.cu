@@ -372,6 +372,11 @@ __device__ __forceinline__ void lanczos_body(const LanczosParams& P) {
   const int nev = tridiag_eigs(meff, dim, s_alpha, s_beta, s_lam, s_vec, tid, lane, warp);
   if (tid == 0) {
     for (int a = 0; a < kMaxDim; ++a) P.evals[((size_t)p * P.maxcomp + c) * kMaxDim + a] = a < nev ? (float)s_lam[a] : 0.f;
+    if (dim < kMaxDim) {   // last slot: the largest Ritz residual estimate |beta_m * s_m| of the returned pairs (what ARPACK iterates on)
+      double rmax = 0.0;
+      for (int a = 0; a < nev; ++a) rmax = fmax(rmax, fabs(s_beta[meff - 1] * s_vec[a][meff - 1]));
+      P.evals[((size_t)p * P.maxcomp + c) * kMaxDim + kMaxDim - 1] = (float)rmax;
+    }
     s_m = meff;
   }
   __syncthreads();
@@ -655,8 +660,14 @@ __device__ __forceinline__ void lc_component(const LanczosClusterParams& P, cons
   __syncthreads();
   const int nev = tridiag_eigs(meff, dim, s_alpha, s_beta, s_lam, s_vec, tid, lane, warp);
   TDA_LC_T(6);
-  if (cr == 0 && tid == 0 && P.evals)
+  if (cr == 0 && tid == 0 && P.evals) {
     for (int a = 0; a < kMaxDim; ++a) P.evals[((size_t)p * P.maxcomp + c) * kMaxDim + a] = a < nev ? (float)s_lam[a] : 0.f;
+    if (dim < kMaxDim) {   // last slot: the largest Ritz residual estimate |beta_m * s_m| of the returned pairs
+      double rmax = 0.0;
+      for (int a = 0; a < nev; ++a) rmax = fmax(rmax, fabs(s_beta[meff - 1] * s_vec[a][meff - 1]));
+      P.evals[((size_t)p * P.maxcomp + c) * kMaxDim + kMaxDim - 1] = (float)rmax;
+    }
+  }
   float* out = P.out + (size_t)p * nfull * dim;
   for (int i = tid; i < nr; i += kLcThreads) {
     for (int a = 0; a < dim; ++a) {
