@@ -816,6 +816,15 @@ constexpr int kClQueue = 256;     // fired entries a warp queues before it works
 constexpr int kClMaxCluster = 8;
 constexpr int kClTile = 16;       // most vertices per warp task (option sgd_tile: more, smaller tasks shorten a warp's chain per epoch)
 
+// MUFU wrappers with flush-to-zero: without .ftz every lg2 / ex2 / rcp carries three extra instructions that rescale denormal
+// operands (9 of ~45 per negative sample).  For normal operands the results are the same bits; a squared distance or a schedule
+// period is never denormal.
+__device__ __forceinline__ float lg2_ftz(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float ex2_ftz(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_ftz(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float pow_ftz(float x, float y) { return ex2_ftz(y * lg2_ftz(x)); }   // == __powf for normal x
+__device__ __forceinline__ float div_ftz(float x, float y) { return x * rcp_ftz(y); }            // == __fdividef for normal y
+
 struct SgdForce {
   float a, b, gamma, nsr;
   float m2ab, g2b, bm1;   // -2ab, 2*gamma*b, b-1 (set by the host next to a, b, gamma)
@@ -825,33 +834,34 @@ struct SgdForce {
     const float dx = yv.x - yt.x, dy = yv.y - yt.y, dz = yv.z - yt.z;
     const float d2 = dx * dx + dy * dy + dz * dz;
     float g = 0.f;
-    if (d2 > 0.f) {
-      const float pw = __powf(d2, bm1);
-      g = __fdividef(m2ab * pw, fmaf(a * pw, d2, 1.f));
+    if (d2 >= 1.17549435e-38f) {   // (a denormal d2 would be flushed by lg2: treated like coincident points)
+      const float pw = pow_ftz(d2, bm1);
+      g = div_ftz(m2ab * pw, fmaf(a * pw, d2, 1.f));
     }
     return make_float3(clip4(g * dx) * alpha, clip4(g * dy) * alpha, clip4(g * dz) * alpha);
   }
   __device__ __forceinline__ void repel(float3& cur, const float4& yn, float alpha) const {
     const float dx = cur.x - yn.x, dy = cur.y - yn.y, dz = cur.z - yn.z;
     const float dn = dx * dx + dy * dy + dz * dz;
-    if (dn > 0.f) {   // (a negative at zero distance gives no update, whichever vertex it is)
-      const float gn = __fdividef(g2b, (0.001f + dn) * fmaf(a, __powf(dn, b), 1.f));   // > 0 for gamma > 0: always applied
-      cur.x = fmaf(clip4(gn * dx), alpha, cur.x); cur.y = fmaf(clip4(gn * dy), alpha, cur.y); cur.z = fmaf(clip4(gn * dz), alpha, cur.z);
-    }
+    // a negative at zero distance gives no update, whichever vertex it is: dx = dy = dz = 0 there, and gn stays finite
+    // (g2b / 0.001), so the three steps are exact zeros without a branch
+    const float gn = div_ftz(g2b, (0.001f + dn) * fmaf(a, pow_ftz(dn, b), 1.f));   // > 0 for gamma > 0: always applied
+    cur.x = fmaf(clip4(gn * dx), alpha, cur.x); cur.y = fmaf(clip4(gn * dy), alpha, cur.y); cur.z = fmaf(clip4(gn * dz), alpha, cur.z);
   }
   // does an entry of period eps fire in `epoch` (it fires when floor(epoch / eps) steps up; approximate division: the schedule is
   // this kernel's own definition, evaluated the same way everywhere) ...
   __device__ __forceinline__ bool fires(float eps, int epoch, int& q) const {
-    q = (int)floorf(__fdividef((float)epoch, eps));
-    return q >= 1 && q > (int)floorf(__fdividef((float)(epoch - 1), eps));
+    const float r = rcp_ftz(eps);
+    q = (int)floorf((float)epoch * r);
+    return q >= 1 && q > (int)floorf((float)(epoch - 1) * r);
   }
   // ... and how many negative samples it owes since its previous firing
   __device__ __forceinline__ int negatives(float eps, int epoch, int q) const {
-    const float epsn = __fdividef(eps, nsr);
-    int tot = (int)floorf(__fdividef((float)epoch, epsn)) - 1;
+    const float rn = rcp_ftz(div_ftz(eps, nsr));
+    int tot = (int)floorf((float)epoch * rn) - 1;
     if (q > 1) {
       const int prev = (int)ceilf((float)(q - 1) * eps);
-      tot -= (int)floorf(__fdividef((float)prev, epsn)) - 1;
+      tot -= (int)floorf((float)prev * rn) - 1;
     }
     return tot;
   }
