@@ -521,8 +521,19 @@ __device__ __forceinline__ void lc_component(const LanczosClusterParams& P, cons
   for (int i = tid; i <= RP; i += kLcThreads) { roff[i] = 0; if (i < RP) rcnt[i] = 0; }
   if (tid == 0) s_cnt = 0;
   __syncthreads();
-  for (int e = tid; e < P.slots; e += kLcThreads) {
-    if (eps[e] > 0.f) { const int h = lidx[head[e]]; if (h >= r0 && h < r1) atomicAdd(&rcnt[h - r0], 1); }
+  // (both passes over the slot table are chains of dependent loads: four slots per thread in flight)
+  for (int e0 = tid; e0 < P.slots; e0 += 4 * kLcThreads) {
+    float ep4[4];
+    int hg4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * kLcThreads;
+      ep4[u] = e < P.slots ? eps[e] : 0.f;
+      hg4[u] = e < P.slots ? head[e] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (ep4[u] > 0.f) { const int h = lidx[hg4[u]]; if (h >= r0 && h < r1) atomicAdd(&rcnt[h - r0], 1); }
   }
   __syncthreads();
   if (tid == 0) { int acc = 0; for (int i = 0; i < nr; ++i) { roff[i] = acc; acc += rcnt[i]; } roff[nr] = acc; s_cnt = acc; }
@@ -532,13 +543,25 @@ __device__ __forceinline__ void lc_component(const LanczosClusterParams& P, cons
   for (int i = tid; i < nr; i += kLcThreads) rcnt[i] = roff[i];
   __syncthreads();
   {
-    for (int e = tid; e < P.slots; e += kLcThreads) {
-      if (eps[e] > 0.f) {
-        const int hg = head[e], h = lidx[hg];
-        if (h >= r0 && h < r1) {
-          const int tg = tail[e];
-          const int pos = atomicAdd(&rcnt[h - r0], 1);
-          ent[pos] = make_int2(lidx[tg], __float_as_int(weight[e] * rsqrtf(deg[hg] * deg[tg])));
+    for (int e0 = tid; e0 < P.slots; e0 += 4 * kLcThreads) {
+      float ep4[4];
+      int hg4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * kLcThreads;
+        ep4[u] = e < P.slots ? eps[e] : 0.f;
+        hg4[u] = e < P.slots ? head[e] : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (ep4[u] > 0.f) {
+          const int e = e0 + u * kLcThreads;
+          const int hg = hg4[u], h = lidx[hg];
+          if (h >= r0 && h < r1) {
+            const int tg = tail[e];
+            const int pos = atomicAdd(&rcnt[h - r0], 1);
+            ent[pos] = make_int2(lidx[tg], __float_as_int(weight[e] * rsqrtf(deg[hg] * deg[tg])));
+          }
         }
       }
     }

@@ -749,6 +749,8 @@ __global__ void __launch_bounds__(kSgdWarps * 32) sgd_epoch_kernel_v4(float4* __
 // the adjacency in shared memory, moves its own vertices and stores the new positions into every CTA's next buffer through
 // distributed shared memory; one cluster barrier per epoch.
 constexpr int kAdjThreads = 1024;
+constexpr int kAdjSplit = 4;      // CTAs per cloud: each counts the whole table (the offsets are global), then fills and sorts its share of the vertices
+constexpr int kAdjUnroll = 4;     // slots per thread in flight (the passes are chains of dependent loads: bound by their latency)
 __global__ void __launch_bounds__(kAdjThreads) sgd_adj_kernel(const int* __restrict__ head, const int* __restrict__ tail, const float* __restrict__ eps_arr,
                                                               int slots, int n, int* __restrict__ adj_off, uint2* __restrict__ adj_ent,
                                                               int* __restrict__ adj_maxdeg) {
@@ -757,7 +759,8 @@ __global__ void __launch_bounds__(kAdjThreads) sgd_adj_kernel(const int* __restr
   int* off = s_adj + n;
   __shared__ int s_part[kAdjThreads / 32];
   __shared__ int s_maxdeg;
-  const int p = blockIdx.x, tid = threadIdx.x;
+  const int p = blockIdx.x / kAdjSplit, part = blockIdx.x % kAdjSplit, tid = threadIdx.x;
+  const int vlo = (int)(((long long)n * part) / kAdjSplit), vhi = (int)(((long long)n * (part + 1)) / kAdjSplit);   // this CTA's vertices
   const int* H = head + (size_t)p * slots;
   const int* Tl = tail + (size_t)p * slots;
   const float* EP = eps_arr + (size_t)p * slots;
@@ -765,8 +768,19 @@ __global__ void __launch_bounds__(kAdjThreads) sgd_adj_kernel(const int* __restr
   for (int i = tid; i < n; i += kAdjThreads) cnt[i] = 0;
   if (tid == 0) s_maxdeg = 0;
   __syncthreads();
-  for (int e = tid; e < slots; e += kAdjThreads)
-    if (EP[e] > 0.f) atomicAdd(&cnt[H[e]], 1);
+  for (int e0 = tid; e0 < slots; e0 += kAdjUnroll * kAdjThreads) {
+    float ep[kAdjUnroll];
+    int h[kAdjUnroll];
+#pragma unroll
+    for (int u = 0; u < kAdjUnroll; ++u) {
+      const int e = e0 + u * kAdjThreads;
+      ep[u] = e < slots ? EP[e] : 0.f;
+      h[u] = e < slots ? H[e] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < kAdjUnroll; ++u)
+      if (ep[u] > 0.f) atomicAdd(&cnt[h[u]], 1);
+  }
   __syncthreads();
   // exclusive scan of cnt -> off (each thread a contiguous chunk)
   const int per = (n + kAdjThreads - 1) / kAdjThreads;
@@ -787,17 +801,27 @@ __global__ void __launch_bounds__(kAdjThreads) sgd_adj_kernel(const int* __restr
   __syncthreads();
   for (int i = tid; i < n; i += kAdjThreads) cnt[i] = off[i];   // fill cursors
   __syncthreads();
-  for (int e = tid; e < slots; e += kAdjThreads) {
-    const float ep = EP[e];
-    if (ep > 0.f) {
-      const int pos = atomicAdd(&cnt[H[e]], 1);
-      ent[pos] = make_uint2(__float_as_uint(ep), (uint32_t)Tl[e] | ((uint32_t)H[e] << 16));   // n <= 8192: 16 bits each
+  for (int e0 = tid; e0 < slots; e0 += kAdjUnroll * kAdjThreads) {
+    float ep[kAdjUnroll];
+    int h[kAdjUnroll], t[kAdjUnroll];
+#pragma unroll
+    for (int u = 0; u < kAdjUnroll; ++u) {
+      const int e = e0 + u * kAdjThreads;
+      ep[u] = e < slots ? EP[e] : 0.f;
+      h[u] = e < slots ? H[e] : 0;
+      t[u] = e < slots ? Tl[e] : 0;
     }
+#pragma unroll
+    for (int u = 0; u < kAdjUnroll; ++u)
+      if (ep[u] > 0.f && h[u] >= vlo && h[u] < vhi) {
+        const int pos = atomicAdd(&cnt[h[u]], 1);
+        ent[pos] = make_uint2(__float_as_uint(ep[u]), (uint32_t)t[u] | ((uint32_t)h[u] << 16));   // n <= 8192: 16 bits each
+      }
   }
   __threadfence_block();
   __syncthreads();
   // the fill order depends on scheduling: sort every list by neighbour id (a vertex has each neighbour once)
-  for (int v = tid; v < n; v += kAdjThreads) {
+  for (int v = vlo + tid; v < vhi; v += kAdjThreads) {
     const int a0 = off[v], a1 = off[v + 1];
     for (int i = a0 + 1; i < a1; ++i) {
       const uint2 x = ent[i];
@@ -806,8 +830,9 @@ __global__ void __launch_bounds__(kAdjThreads) sgd_adj_kernel(const int* __restr
       ent[k + 1] = x;
     }
   }
-  for (int i = tid; i <= n; i += kAdjThreads) adj_off[(size_t)p * (n + 1) + i] = off[i];
-  if (tid == 0) adj_maxdeg[p] = s_maxdeg;
+  for (int i = vlo + tid; i < vhi; i += kAdjThreads) adj_off[(size_t)p * (n + 1) + i] = off[i];
+  if (part == kAdjSplit - 1 && tid == 0) adj_off[(size_t)p * (n + 1) + n] = off[n];
+  if (tid == 0) adj_maxdeg[p] = s_maxdeg;   // (the same value from every CTA of the cloud)
 }
 
 constexpr int kClThreads = 1024;
@@ -1294,7 +1319,7 @@ extern "C" int tda_umap_sgd(float* Y, const float* Y_other, const int32_t* head,
       int* adj_maxdeg = c.take<int>(batch);
       const size_t adj_smem = sizeof(int) * (size_t)(2 * n + 1);
       TDA_CUDA_CHECK(cudaFuncSetAttribute(sgd_adj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adj_smem));
-      sgd_adj_kernel<<<batch, kAdjThreads, adj_smem, stream>>>(head, tail, eps, slots, n, adj_off, adj_ent, adj_maxdeg);
+      sgd_adj_kernel<<<batch * kAdjSplit, kAdjThreads, adj_smem, stream>>>(head, tail, eps, slots, n, adj_off, adj_ent, adj_maxdeg);
       // the CTA's slice of the adjacency goes to shared memory when it fits into what the embedding buffers leave
       size_t cap_ent = (smem_max - base) / sizeof(uint2);
       const size_t want_ent = (size_t)slots / C + (size_t)slots / (2 * C) + 64;   // 1.5x the mean slice (the kernel checks its actual size)
