@@ -442,6 +442,13 @@ def run_b200(a):
         sampler.start()
     for _ in range(a.warmup):
         step_resident()
+    # CPython's cyclic collector scans the whole heap of a process with torch loaded in 15-60 ms -- a third of a step -- and a pass
+    # that lands in the unpacking of a step's last group delays that step (profiles/r02_step_variance.txt; one 57.9 ms step in the
+    # r02m line).  Everything alive after the warm-up is moved to the permanent generation, as a long-running service would do
+    # after start-up: later passes only look at what the steps themselves allocate.
+    import gc as _gc
+    _gc.collect()
+    _gc.freeze()
     sampler.active = True
     L.tda_launch_count_reset()
     L.tda_stage_timing_reset()

@@ -69,6 +69,10 @@ class RipsJob:
             _lib.check(L.tda_rips_launch(_lib.ptr(dm), n, B, maxdim, self.thresh, _lib.ptr(self.h0), _lib.ptr(self.h0s), _lib.ptr(self.h1),
                                          _lib.ptr(self.h1s), cap1, _lib.ptr(self.counts), _lib.ptr(self.th), _lib.ptr(self.ws),
                                          self.ws_bytes, pool_bytes, _lib.stream_ptr()))
+            # the results follow the kernels on the same stream into pinned host buffers (torch's caching host allocator): when the
+            # stream has drained they are already on the host, and finish() has no copy left to wait for
+            self._host = {k: (t.to("cpu", non_blocking=True) if t is not None else None)
+                          for k, t in (("counts", self.counts), ("h0", self.h0), ("h1", self.h1), ("th", self.th), ("h0s", self.h0s), ("h1s", self.h1s))}
 
     def finish(self):
         torch = _lib.require_cuda()
@@ -76,7 +80,8 @@ class RipsJob:
         dm = self.dm
         B, n, _ = dm.shape
         self.stream.synchronize()
-        counts_h = self.counts.cpu().numpy()
+        host = self._host
+        counts_h = host["counts"].numpy()
         if (counts_h[:, 3] != 0).any():
             # some problem overflowed cap1 / the column pool: run the whole batch again, synchronously, with larger buffers
             del self.ws
@@ -88,12 +93,11 @@ class RipsJob:
             stats = np.zeros((B, _lib.RIPS_STATS), dtype=np.int64)
             with torch.cuda.device(dm.device):
                 _lib.check(L.tda_rips_stats(_lib.ptr(self.ws), n, B, self.maxdim, self.cap1, self.pool_bytes, stats.ctypes.data))
-        with torch.cuda.stream(self.stream):
-            h0_h = self.h0.cpu().numpy()
-            h1_h = self.h1.cpu().numpy() if self.h1 is not None else None
-            th_h = self.th.cpu().numpy()
-            h0s_h = self.h0s.cpu().numpy() if self.h0s is not None else None
-            h1s_h = self.h1s.cpu().numpy() if self.h1s is not None else None
+        h0_h = host["h0"].numpy()
+        h1_h = host["h1"].numpy() if host["h1"] is not None else None
+        th_h = host["th"].numpy()
+        h0s_h = host["h0s"].numpy() if host["h0s"] is not None else None
+        h1s_h = host["h1s"].numpy() if host["h1s"] is not None else None
         out = []
         for p in range(B):
             c0, c1 = int(counts_h[p, 0]), int(counts_h[p, 1])
