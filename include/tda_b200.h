@@ -207,6 +207,23 @@ int tda_rips(const float* dm, int n, int batch, int maxdim, float thresh,
 int tda_rips_launch(const float* dm, int n, int batch, int maxdim, float thresh,
                     float* h0_pairs, int64_t* h0_simplex, float* h1_pairs, int64_t* h1_simplex, int cap1,
                     int32_t* counts, float* thresh_out, void* ws, size_t ws_bytes, size_t pool_bytes, void* stream);
+/* Subsets of one cloud (bootstrap resamples: `ripser(Y[idx], maxdim=1)` for many index sets of the same Y; config 4 of
+ * BASELINE.json, the resample loop around debug_tda_pipeline.py:109-110).  A subset given by strictly ascending parent indices keeps
+ * the order of its edges (equal float lengths, tie-break index monotone under the relabelling), so its filtration ranks are a
+ * flag + prefix count over the parent's sorted edge list: no distance matrix, key generation or radix sort per subset.
+ * tda_rips_sort_edges: ALL edges of `batch` clouds in ripser's order (length ascending, index descending; no threshold).
+ *   dm [batch,n,n] float32; ends_out [batch,E] uint32 = (i << 16 | j), i > j; sdist_out [batch,E] float32; E = n(n-1)/2.
+ * tda_rips_subsets_launch: as tda_rips_launch for the `batch` clouds points[subset_idx[b]] (m points each) of ONE parent:
+ *   parent_ends / parent_sdist [E_parent] from tda_rips_sort_edges, parent_dm [n_parent,n_parent] (only read for the enclosing
+ *   radius: may be NULL when `thresh` is finite), subset_idx [batch,m] int32, strictly ascending per row (not checked).
+ *   Outputs, workspace (tda_rips_workspace_bytes(m, batch, ...)) and overflow protocol as tda_rips_launch; the results are
+ *   bit-identical to tda_rips_launch on tda_pdist_lowdim(points[subset_idx[b]]). */
+size_t tda_rips_sort_edges_workspace_bytes(int n, int batch);
+int tda_rips_sort_edges(const float* dm, int n, int batch, uint32_t* ends_out, float* sdist_out, void* ws, size_t ws_bytes, void* stream);
+int tda_rips_subsets_launch(const uint32_t* parent_ends, const float* parent_sdist, const float* parent_dm, int n_parent,
+                            const int32_t* subset_idx, int m, int batch, int maxdim, float thresh,
+                            float* h0_pairs, int64_t* h0_simplex, float* h1_pairs, int64_t* h1_simplex, int cap1,
+                            int32_t* counts, float* thresh_out, void* ws, size_t ws_bytes, size_t pool_bytes, void* stream);
 /* tda_rips_h2: H2 (optional `maxdim=2` of ripser(X, maxdim)) on top of a FINISHED tda_rips(maxdim=1) call: `ws1` is that
  * call's workspace (with the same n, batch, cap1, pool_bytes1), which still holds the rank matrix and the H1 pivots (clearing).
  * Triangles in an apparent pair with a tetrahedron are skipped in parallel, the residual triangle columns are reduced like the

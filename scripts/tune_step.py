@@ -7,7 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from tda_multimodal_b200 import _lib, pipeline, workloads
 
-DEFAULTS = {"sgd_cluster": 0, "sgd_tile": 16, "rips_cluster": 0, "spectral_cluster": 8, "rips_apparent_rows": 1, "rips_wc_max_rows": 262144}   # (tail_* keys: options of the last group only)
+DEFAULTS = {"sgd_cluster": 0, "sgd_tile": 16, "rips_cluster": 0, "spectral_cluster": 8, "rips_apparent_rows": 1, "rips_wc_max_rows": 262144, "rips_h0_chunked": 1}   # (tail_* keys: options of the last group only)
 BUILTIN = ["chunks=2", "chunks=3", "chunks=4", "chunks=2,sgd_tile=8", "chunks=2,sgd_cluster=8,sgd_tile=8", "chunks=4,sgd_cluster=8,sgd_tile=8",
            "chunks=2,rips_cluster=8", "chunks=4,rips_cluster=8", "chunks=4,sgd_tile=8", "chunks=4,sgd_tile=8,rips_cluster=8", "chunks=1"]
 

@@ -52,6 +52,10 @@ PROTOTYPES = {
                          c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]),
     "tda_rips_launch": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                 c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]),
+    "tda_rips_sort_edges_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "tda_rips_sort_edges": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tda_rips_subsets_launch": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]),
     "tda_rips_h2_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_size_t, c_size_t]),
     "tda_rips_h2": (c_int, [c_void_p, c_int, c_int, c_int, c_size_t, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_size_t, c_size_t, c_void_p]),
     "tda_rips_stats": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_size_t, c_void_p]),

@@ -80,6 +80,7 @@ static OptionDef g_options[] = {
     {"rips_warp_engine", 1},   // sweep2: short columns are reduced by single warps first, speculatively, and committed in order
     {"rips_wc_max_rows", 262144}, // sweep2: rows a warp sweeps before it hands its column to the cluster engine
     {"rips_cluster", 0},       // sweep2: CTAs per cloud (thread-block cluster: 1, 2, 4 or 8; 0 = auto: 8 for up to 4 clouds per launch, else 4; halved while batch * cluster > 2 * SMs)
+    {"rips_h0_chunked", 1},    // H0 in one launch from the sorted edge list (Boruvka / Kruskal by chunks, n <= 16384); 0: Boruvka rounds on the rank matrix
     {"rips_apparent_rows", 1}, // apparent pairs by matrix row (one CTA per vertex, its rank row in shared memory); 0: one warp per edge by rank
     {"sweep_exclusive", 0},    // reducers 1/2: ask for the whole shared memory of the SM
     {"sgd_mode", 0},           // 0 deterministic kernels (cluster per cloud for fit, warp per point for transform), 3 per-epoch kernels with float atomics

@@ -121,6 +121,140 @@ __global__ void rank_diag_kernel(int n, int* __restrict__ rank) {  // n == 1 or 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Subsets of a cloud whose edges are already in filtration order (bootstrap resamples, config C4): a subset given by ASCENDING
+// parent indices keeps the order of its edges -- equal lengths are the same float bits (the distance of two points does not
+// depend on the cloud they sit in) and the tie-break, the edge index C(i,2)+j, is monotone under an order-preserving relabelling
+// -- so the rank of a subset edge is the number of subset edges before it in the parent's order: a flag + prefix count over the
+// parent's sorted edge list replaces pairwise distances, key generation and the radix sort of every resample.
+constexpr int kSubThreads = 256;
+constexpr int kSubPerThread = 32;
+constexpr int kSubChunk = kSubThreads * kSubPerThread;   // parent edges per CTA
+__global__ void sorted_edges_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t E,
+                                    uint32_t* __restrict__ ends, float* __restrict__ sdist) {
+  const int p = blockIdx.y;
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= E) return;
+  int i, j;
+  edge_vertices((int64_t)vals[(size_t)p * E + s], i, j);
+  ends[(size_t)p * E + s] = ((uint32_t)i << 16) | (uint32_t)j;
+  sdist[(size_t)p * E + s] = __uint_as_float((uint32_t)(keys[(size_t)p * E + s] & 0xffffffffu));
+}
+// enclosing radius of a subset from the parent's distance matrix: one warp per (subset, point)
+__global__ void subset_enclosing_kernel(const float* __restrict__ dm, int n_parent, const int32_t* __restrict__ idx, int m,
+                                        uint32_t* __restrict__ thresh_bits) {
+  const int p = blockIdx.y;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= m) return;
+  const int32_t* I = idx + (size_t)p * m;
+  const float* row = dm + (size_t)I[warp] * n_parent;
+  float mx = 0.f;
+  for (int j = lane; j < m; j += 32) mx = fmaxf(mx, __ldg(&row[I[j]]));
+  mx = warp_max_f32(mx);
+  if (lane == 0) atomicMin(&thresh_bits[p], __float_as_uint(mx));
+}
+// parent vertex -> index inside the subset (0xffff: not in it), in shared memory: two look-ups per parent edge, random over the
+// table -- from a global table every warp load touched up to 32 cache lines and the L1 throughput bounded both passes
+__device__ __forceinline__ void subset_build_map(uint16_t* smap, const int32_t* __restrict__ I, int m, int n_parent) {
+  uint32_t* w = reinterpret_cast<uint32_t*>(smap);
+  for (int i = threadIdx.x; i < (n_parent + 1) / 2; i += blockDim.x) w[i] = 0xffffffffu;
+  __syncthreads();
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    const int v = I[i];
+    if (v >= 0 && v < n_parent) smap[v] = (uint16_t)i;
+  }
+  __syncthreads();
+}
+// subset edges per chunk of the parent's list, and the number of subset edges within the threshold
+__global__ void __launch_bounds__(kSubThreads) subset_count_kernel(const uint32_t* __restrict__ pends, const float* __restrict__ psdist, int64_t Ep,
+                                                                   const int32_t* __restrict__ idx, int m, int n_parent,
+                                                                   const uint32_t* __restrict__ thresh_bits, int* __restrict__ chunk_cnt,
+                                                                   int nchunks, int* __restrict__ T) {
+  extern __shared__ uint16_t s_submap[];
+  __shared__ int s_cnt, s_valid;
+  const int p = blockIdx.y, c = blockIdx.x, tid = threadIdx.x;
+  const uint32_t tb = thresh_bits[p];
+  if (tid == 0) { s_cnt = 0; s_valid = 0; }
+  subset_build_map(s_submap, idx + (size_t)p * m, m, n_parent);
+  int cnt = 0, valid = 0;
+  const int64_t base = (int64_t)c * kSubChunk;
+#pragma unroll 8
+  for (int k = 0; k < kSubPerThread; ++k) {
+    const int64_t r = base + (int64_t)k * kSubThreads + tid;
+    if (r < Ep) {
+      const uint32_t e = __ldg(&pends[r]);
+      if (s_submap[e >> 16] != 0xffffu && s_submap[e & 0xffffu] != 0xffffu) {
+        ++cnt;
+        valid += __float_as_uint(__ldg(&psdist[r])) <= tb ? 1 : 0;
+      }
+    }
+  }
+  cnt = warp_sum_i32(cnt); valid = warp_sum_i32(valid);
+  if ((tid & 31) == 0) { if (cnt) atomicAdd(&s_cnt, cnt); if (valid) atomicAdd(&s_valid, valid); }
+  __syncthreads();
+  if (tid == 0) {
+    chunk_cnt[(size_t)p * nchunks + c] = s_cnt;
+    if (s_valid) atomicAdd(&T[p], s_valid);
+  }
+}
+// exclusive scan of the chunk counts of one subset (one CTA per subset, in place)
+__global__ void __launch_bounds__(512) subset_scan_kernel(int* __restrict__ chunk_cnt, int nchunks) {
+  __shared__ int s_part[16];
+  const int p = blockIdx.x, tid = threadIdx.x;
+  int* a = chunk_cnt + (size_t)p * nchunks;
+  const int per = (nchunks + 511) / 512;
+  const int lo = min(tid * per, nchunks), hi = min(lo + per, nchunks);
+  int sum = 0;
+  for (int i = lo; i < hi; ++i) sum += a[i];
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += t; }
+  if ((tid & 31) == 31) s_part[tid >> 5] = incl;
+  __syncthreads();
+  int base = incl - sum;
+  for (int w = 0; w < (tid >> 5); ++w) base += s_part[w];
+  for (int i = lo; i < hi; ++i) { const int t = a[i]; a[i] = base; base += t; }
+}
+// ranks, end points and lengths of the subset edges (the same tables rank_scatter_kernel writes from a sorted key list)
+__global__ void __launch_bounds__(kSubThreads) subset_scatter_kernel(const uint32_t* __restrict__ pends, const float* __restrict__ psdist, int64_t Ep,
+                                                                     const int32_t* __restrict__ idx, int n_parent,
+                                                                     const int* __restrict__ chunk_off, int nchunks, int m, int64_t E,
+                                                                     int* __restrict__ rank, uint32_t* __restrict__ ends, float* __restrict__ sdist) {
+  extern __shared__ uint16_t s_submap[];
+  __shared__ int s_warp[2][kSubThreads / 32];
+  const int p = blockIdx.y, c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  subset_build_map(s_submap, idx + (size_t)p * m, m, n_parent);
+  int* R = rank + (size_t)p * m * m;
+  int run = chunk_off[(size_t)p * nchunks + c];
+  const int64_t base = (int64_t)c * kSubChunk;
+  for (int k = 0; k < kSubPerThread; ++k) {
+    const int64_t r = base + (int64_t)k * kSubThreads + tid;
+    uint32_t i = 0xffffu, j = 0xffffu;
+    if (r < Ep) {
+      const uint32_t e = __ldg(&pends[r]);
+      i = s_submap[e >> 16];
+      j = s_submap[e & 0xffffu];
+    }
+    const bool f = i != 0xffffu && j != 0xffffu;
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) s_warp[k & 1][warp] = __popc(bal);   // (double buffered: one barrier per trip)
+    __syncthreads();
+    int off = run, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kSubThreads / 32; ++w) { const int t = s_warp[k & 1][w]; if (w < warp) off += t; tot += t; }
+    if (f) {
+      const int64_t sr = (int64_t)off + __popc(bal & ((1u << lane) - 1));
+      if (sr < E) {   // (always, for distinct indices inside the parent)
+        R[(size_t)i * m + j] = (int)sr;
+        R[(size_t)j * m + i] = (int)sr;
+        ends[(size_t)p * E + sr] = (i << 16) | j;   // i > j: the relabelling preserves the order
+        sdist[(size_t)p * E + sr] = __ldg(&psdist[r]);
+      }
+    }
+    run += tot;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // H0: Boruvka MST on the rank matrix.  Ranks are distinct, so the minimum spanning forest is unique and
 // equals the set of merging edges of ripser's union-find sweep.  Per round: a grid-wide scan kernel (one
 // warp per matrix row: smallest rank leaving the row's component -> atomicMin per component) and a
@@ -202,6 +336,77 @@ __global__ void __launch_bounds__(1024) boruvka_merge_kernel(const uint32_t* __r
     if (!__syncthreads_or(changed)) break;
   }
   for (int i = tid; i < n; i += nt) { comp[i] = parent[comp[i]]; cbest[i] = kNoEdge; }
+}
+
+// The same forest from the SORTED EDGE LIST, one CTA per cloud, one launch (default for n <= 16384): the list is taken in chunks of
+// kBorChunk ranks; on a chunk, Boruvka rounds (lowest rank of the chunk leaving each component -> hook -> pointer jumping, all in
+// shared memory) repeat until no edge of the chunk joins two components, then the next chunk follows.  Earlier chunks hold no
+// joining edge any more, so the lowest joining edge of a component inside the current chunk is its lowest joining edge overall:
+// every hook is an edge of the (unique) minimum spanning forest.  For a point cloud nearly all of the forest lies in the first
+// chunk; the few long edges between clusters are found by one cheap pass per later chunk (Kruskal by chunks).  Replaces ~25 launches
+// that each re-read the whole rank matrix: H0 of 256 x 1000 points 8-13 ms -> well under 1 ms, and one launch instead of 25 in
+// the sweep, where every small launch queues behind the other groups' kernels.
+constexpr int kBorChunk = 32768;
+__global__ void __launch_bounds__(1024) boruvka_chunked_kernel(const uint32_t* __restrict__ ends, const int* __restrict__ Tarr, int n, int64_t E,
+                                                               uint32_t* __restrict__ comp_g, uint8_t* __restrict__ mst,
+                                                               int* __restrict__ mstlist_g, int mst_stride, int* __restrict__ mstcount) {
+  extern __shared__ uint32_t s_bor[];   // comp[n], cbest[n], parent[n]
+  uint32_t* comp = s_bor;
+  uint32_t* cbest = comp + n;
+  uint32_t* parent = cbest + n;
+  __shared__ int s_count;
+  const int p = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const uint32_t* EN = ends + (size_t)p * E;
+  uint8_t* M = mst + (size_t)p * E;
+  int* list = mstlist_g + (size_t)p * mst_stride;
+  const int T = Tarr[p];
+  for (int i = tid; i < n; i += nt) { comp[i] = (uint32_t)i; cbest[i] = kNoEdge; }
+  if (tid == 0) s_count = 0;
+  __syncthreads();
+  int c0 = 0;
+  while (c0 < T && s_count < n - 1) {     // (s_count only changes between barriers: every thread sees the same value here)
+    const int c1 = min(T, c0 + kBorChunk);
+    int any = 0;
+    for (int e = c0 + tid; e < c1; e += nt) {
+      const uint32_t en = __ldg(&EN[e]);
+      const uint32_t cu = comp[en >> 16], cv = comp[en & 0xffffu];
+      if (cu != cv) { atomicMin(&cbest[cu], (uint32_t)e); atomicMin(&cbest[cv], (uint32_t)e); any = 1; }
+    }
+    if (!__syncthreads_or(any)) { c0 = c1; continue; }   // no joining edge left in this chunk
+    for (int c = tid; c < n; c += nt) {
+      const uint32_t r = cbest[c];
+      uint32_t par = (uint32_t)c;
+      if (r != kNoEdge) {   // only component roots ever receive a candidate
+        const uint32_t e = __ldg(&EN[r]);
+        const uint32_t u = e >> 16, v = e & 0xffffu;
+        par = comp[u] == (uint32_t)c ? comp[v] : comp[u];
+        M[r] = 1;           // both sides may pick the same edge: same value written twice ...
+        if (!(cbest[par] == r && par < (uint32_t)c)) {   // ... but it enters the list once (the smaller id of a mutual pick lists it)
+          const int pos = atomicAdd(&s_count, 1);
+          if (pos < n) list[pos] = (int)r;
+        }
+      }
+      parent[c] = par;
+    }
+    __syncthreads();
+    for (int c = tid; c < n; c += nt) {   // a mutual pick is a 2-cycle: the smaller id becomes the root
+      const uint32_t q = parent[c];
+      if (q != (uint32_t)c && parent[q] == (uint32_t)c && (uint32_t)c < q) parent[c] = (uint32_t)c;
+    }
+    __syncthreads();
+    for (int it = 0; it < 32; ++it) {     // pointer jumping
+      int changed = 0;
+      for (int c = tid; c < n; c += nt) {
+        const uint32_t q = parent[c], g = parent[q];
+        if (g != q) { parent[c] = g; changed = 1; }
+      }
+      if (!__syncthreads_or(changed)) break;
+    }
+    for (int i = tid; i < n; i += nt) { comp[i] = parent[comp[i]]; cbest[i] = kNoEdge; }
+    __syncthreads();
+  }
+  for (int i = tid; i < n; i += nt) comp_g[(size_t)p * n + i] = comp[i];
+  if (tid == 0) mstcount[p] = s_count;
 }
 
 // sort the MST ranks (collected by the merge kernel), emit the H0 rows.  One CTA per cloud; the list is sorted in shared
@@ -2271,11 +2476,14 @@ extern "C" size_t tda_rips_workspace_bytes(int n, int batch, int maxdim, int cap
   return L.total + 4096;
 }
 
+// the clouds of a call as SUBSETS of one parent cloud whose edges are already sorted (tda_rips_sort_edges): see subset_*_kernel
+struct SubsetInput { const uint32_t* ends; const float* sdist; const float* dm; int n_parent; const int32_t* idx; };
+
 static int rips_enqueue(const float* dm, int n, int batch, int maxdim, float thresh, float* h0_pairs, int64_t* h0_simplex,
                         float* h1_pairs, int64_t* h1_simplex, int cap1, int32_t* counts, float* thresh_out, void* ws,
-                        size_t ws_bytes, size_t pool_bytes, void* stream_) {
+                        size_t ws_bytes, size_t pool_bytes, void* stream_, const SubsetInput* sub = nullptr) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (!dm || !h0_pairs || !counts || !ws || n <= 0 || batch <= 0) return set_error(TDA_ERR_INVALID, "tda_rips: bad arguments");
+  if ((!dm && !sub) || !h0_pairs || !counts || !ws || n <= 0 || batch <= 0) return set_error(TDA_ERR_INVALID, "tda_rips: bad arguments");
   if (maxdim < 0) return set_error(TDA_ERR_INVALID, "tda_rips: maxdim < 0");
   if (maxdim > 1) return set_error(TDA_ERR_UNSUPPORTED, "tda_rips: maxdim=%d not implemented (H0/H1 only)", maxdim);
   if (n > 65535) return set_error(TDA_ERR_UNSUPPORTED, "tda_rips: n=%d > 65535", n);
@@ -2298,12 +2506,33 @@ static int rips_enqueue(const float* dm, int n, int batch, int maxdim, float thr
   count_launch();
   if (isinf(thresh)) {
     dim3 g((n * 32 + 255) / 256, batch);
-    enclosing_kernel<<<g, 256, 0, stream>>>(dm, n, L.thresh_bits);
+    if (sub) subset_enclosing_kernel<<<g, 256, 0, stream>>>(sub->dm, sub->n_parent, sub->idx, n, L.thresh_bits);
+    else enclosing_kernel<<<g, 256, 0, stream>>>(dm, n, L.thresh_bits);
     count_launch();
   }
   TDA_LAUNCH_CHECK();
   if (thresh_out) TDA_CUDA_CHECK(cudaMemcpyAsync(thresh_out, L.thresh_bits, sizeof(float) * batch, cudaMemcpyDeviceToDevice, stream));
-  if (E > 0) {
+  if (sub && E > 0) {
+    // flag + prefix count over the parent's sorted edges; the chunk counts live in the (unused) sort buffers
+    const int64_t Ep = (int64_t)sub->n_parent * (sub->n_parent - 1) / 2;
+    const int64_t nchunks64 = (Ep + kSubChunk - 1) / kSubChunk;
+    if (nchunks64 > 65535 * 32ll) return set_error(TDA_ERR_UNSUPPORTED, "tda_rips_subsets: parent of %d points is too large", sub->n_parent);
+    const int nchunks = (int)nchunks64;
+    int* chunk_cnt = reinterpret_cast<int*>(L.keys_a);
+    if (sizeof(int) * (size_t)batch * nchunks > sizeof(uint64_t) * (size_t)BE)
+      return set_error(TDA_ERR_WORKSPACE, "tda_rips_subsets: subsets of %d points are too small for a parent of %d (use tda_rips)", n, sub->n_parent);
+    const size_t map_bytes = sizeof(uint32_t) * (size_t)((sub->n_parent + 1) / 2);
+    if (map_bytes > 48 * 1024) {
+      TDA_CUDA_CHECK(cudaFuncSetAttribute(subset_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)map_bytes));
+      TDA_CUDA_CHECK(cudaFuncSetAttribute(subset_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)map_bytes));
+    }
+    dim3 gc((unsigned)nchunks, batch);
+    subset_count_kernel<<<gc, kSubThreads, map_bytes, stream>>>(sub->ends, sub->sdist, Ep, sub->idx, n, sub->n_parent, L.thresh_bits, chunk_cnt, nchunks, L.T);
+    subset_scan_kernel<<<batch, 512, 0, stream>>>(chunk_cnt, nchunks);
+    subset_scatter_kernel<<<gc, kSubThreads, map_bytes, stream>>>(sub->ends, sub->sdist, Ep, sub->idx, sub->n_parent, chunk_cnt, nchunks, n, E, L.rank, L.ends, L.sdist);
+    count_launch(3);
+    TDA_LAUNCH_CHECK();
+  } else if (E > 0) {
     dim3 g((unsigned)((E + 255) / 256), batch);
     edge_keys_kernel<<<g, 256, 0, stream>>>(dm, n, E, L.thresh_bits, L.keys_a, L.vals_a, L.T);
     count_launch();
@@ -2327,17 +2556,24 @@ static int rips_enqueue(const float* dm, int n, int batch, int maxdim, float thr
   TDA_CUDA_CHECK(cudaMemsetAsync(L.mst, 0, (size_t)(BE > 0 ? BE : 1), stream));
   {
     StageScope st(STAGE_RIPS_H0, stream);
-    dim3 gi((n + 255) / 256, batch);
-    boruvka_init_kernel<<<gi, 256, 0, stream>>>(n, L.comp, L.cbest, L.done, L.mstcount);
-    count_launch();
-    int rounds = 1;
-    while ((1 << rounds) < n) ++rounds;
-    ++rounds;  // one extra round detects "no merge" and is a no-op otherwise
-    dim3 gs((n + 7) / 8, batch);
-    for (int r = 0; r < rounds && E > 0; ++r) {
-      boruvka_scan_kernel<<<gs, 256, 0, stream>>>(L.rank, L.T, n, L.comp, L.cbest, L.done);
-      boruvka_merge_kernel<<<batch, 1024, 0, stream>>>(L.ends, n, E, L.comp, L.parent, L.cbest, L.mst, L.done, L.mstlist, next_pow2(n), L.mstcount);
-      count_launch(2);
+    if (n <= 16384 && option("rips_h0_chunked") != 0) {   // one launch: Boruvka / Kruskal by chunks of the sorted edge list
+      const size_t dyn = sizeof(uint32_t) * 3 * (size_t)n;
+      if (dyn > 48 * 1024) TDA_CUDA_CHECK(cudaFuncSetAttribute(boruvka_chunked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+      boruvka_chunked_kernel<<<batch, 1024, dyn, stream>>>(L.ends, L.T, n, E, L.comp, L.mst, L.mstlist, next_pow2(n), L.mstcount);
+      count_launch();
+    } else {
+      dim3 gi((n + 255) / 256, batch);
+      boruvka_init_kernel<<<gi, 256, 0, stream>>>(n, L.comp, L.cbest, L.done, L.mstcount);
+      count_launch();
+      int rounds = 1;
+      while ((1 << rounds) < n) ++rounds;
+      ++rounds;  // one extra round detects "no merge" and is a no-op otherwise
+      dim3 gs((n + 7) / 8, batch);
+      for (int r = 0; r < rounds && E > 0; ++r) {
+        boruvka_scan_kernel<<<gs, 256, 0, stream>>>(L.rank, L.T, n, L.comp, L.cbest, L.done);
+        boruvka_merge_kernel<<<batch, 1024, 0, stream>>>(L.ends, n, E, L.comp, L.parent, L.cbest, L.mst, L.done, L.mstlist, next_pow2(n), L.mstcount);
+        count_launch(2);
+      }
     }
     {
       int np2 = 1;
@@ -2404,14 +2640,16 @@ static int rips_enqueue(const float* dm, int n, int batch, int maxdim, float thr
     {
       StageScope st(STAGE_RIPS_REDUCE, stream);
       if (L.reducer == 0) {
-        const size_t dyn = Sweeper2::dyn_bytes(L.xw, L.s2_wmax);
-        if (dyn > (size_t)200 * 1024) return set_error(TDA_ERR_UNSUPPORTED, "tda_rips: sweep2 needs %zu bytes of shared memory (n=%d, rips_wmax=%d)", dyn, n, L.s2_wmax);
-        TDA_CUDA_CHECK(cudaFuncSetAttribute(rips_sweep2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         // one thread-block cluster per cloud at a time: cluster size from the option, shrunk for big batches (more clouds than
         // clusters fit on the machine: rather one cloud per SM) 
         int C = (int)option("rips_cluster");
         if (C != 1 && C != 2 && C != 4 && C != 8) C = batch <= 4 ? 8 : 4;   // auto: few clouds -> more SMs per cloud
         while (C > 1 && (long long)batch * C > 2ll * sms) C >>= 1;
+        const size_t dyn = Sweeper2::dyn_bytes(L.xw, L.s2_wmax);
+        if (dyn > (size_t)200 * 1024) return set_error(TDA_ERR_UNSUPPORTED, "tda_rips: sweep2 needs %zu bytes of shared memory (n=%d, rips_wmax=%d)", dyn, n, L.s2_wmax);
+        TDA_CUDA_CHECK(cudaFuncSetAttribute(rips_sweep2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        // (tried: CTAs of 256 threads, two per SM, for batches with more clouds than SMs -- 256 bootstrap resamples: 23.4 ms against
+        // 19.4 ms for one 512-thread CTA per SM, profiles/r02n_c4_one_batch.log; not kept)
         int nclusters = sms / C;
         if (nclusters > batch) nclusters = batch;
         if (nclusters > L.grid) nclusters = L.grid;
@@ -2496,6 +2734,67 @@ extern "C" int tda_rips(const float* dm, int n, int batch, int maxdim, float thr
         return set_error(TDA_ERR_CAPACITY, "tda_rips: problem %d overflowed (cap1=%d or column pool %zu bytes); retry with larger sizes", p, cap1, pool_bytes);
   }
   return TDA_OK;
+}
+
+// ---- the edges of `batch` clouds in filtration order (ALL of them: no threshold), for tda_rips_subsets_launch
+namespace {
+struct SortLayout { uint64_t *keys_a, *keys_b; uint32_t *vals_a, *vals_b; void* cub_tmp; size_t cub_bytes; uint32_t* thresh_bits; int* T; size_t total; };
+SortLayout make_sort_layout(void* ws, int n, int batch) {
+  SortLayout L;
+  const int64_t BE = (int64_t)batch * ((int64_t)n * (n - 1) / 2);
+  Carver c(ws, ~size_t(0));
+  L.keys_a = c.take<uint64_t>(BE); L.keys_b = c.take<uint64_t>(BE);
+  L.vals_a = c.take<uint32_t>(BE); L.vals_b = c.take<uint32_t>(BE);
+  L.cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, L.cub_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint32_t*)nullptr,
+                                  (uint32_t*)nullptr, BE > 0 ? BE : 1, 0, 64, (cudaStream_t)0);
+  L.cub_tmp = c.take<char>(L.cub_bytes + 256);
+  L.thresh_bits = c.take<uint32_t>(batch);
+  L.T = c.take<int>(batch);
+  L.total = c.off;
+  return L;
+}
+}  // namespace
+
+extern "C" size_t tda_rips_sort_edges_workspace_bytes(int n, int batch) {
+  if (n <= 0 || batch <= 0) return 0;
+  return make_sort_layout(nullptr, n, batch).total + 4096;
+}
+
+extern "C" int tda_rips_sort_edges(const float* dm, int n, int batch, uint32_t* ends_out, float* sdist_out, void* ws, size_t ws_bytes,
+                                   void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!dm || !ends_out || !sdist_out || !ws || n <= 1 || batch <= 0) return set_error(TDA_ERR_INVALID, "tda_rips_sort_edges: bad arguments");
+  if (n > 65535 || batch > 65535) return set_error(TDA_ERR_UNSUPPORTED, "tda_rips_sort_edges: n=%d batch=%d (at most 65535 each)", n, batch);
+  SortLayout L = make_sort_layout(ws, n, batch);
+  if (L.total > ws_bytes) return set_error(TDA_ERR_WORKSPACE, "tda_rips_sort_edges: workspace %zu < required %zu", ws_bytes, L.total);
+  const int64_t E = (int64_t)n * (n - 1) / 2, BE = (int64_t)batch * E;
+  StageScope st(STAGE_RIPS_SORT, stream);
+  TDA_CUDA_CHECK(cudaMemsetAsync(L.T, 0, sizeof(int) * batch, stream));
+  enclosing_init_kernel<<<(batch + 255) / 256, 256, 0, stream>>>(L.thresh_bits, batch, INFINITY);   // every finite length is in
+  dim3 g((unsigned)((E + 255) / 256), batch);
+  edge_keys_kernel<<<g, 256, 0, stream>>>(dm, n, E, L.thresh_bits, L.keys_a, L.vals_a, L.T);
+  int pbits = 0;
+  while ((1 << pbits) < batch) ++pbits;
+  size_t tmp = L.cub_bytes;
+  TDA_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(L.cub_tmp, tmp, (const uint64_t*)L.keys_a, L.keys_b, (const uint32_t*)L.vals_a, L.vals_b, BE, 0,
+                                                 32 + pbits, stream));
+  sorted_edges_kernel<<<g, 256, 0, stream>>>(L.keys_b, L.vals_b, E, ends_out, sdist_out);
+  count_launch(3 + 4 + (pbits + 7) / 8 + 2);
+  TDA_LAUNCH_CHECK();
+  return TDA_OK;
+}
+
+extern "C" int tda_rips_subsets_launch(const uint32_t* parent_ends, const float* parent_sdist, const float* parent_dm, int n_parent,
+                                       const int32_t* subset_idx, int m, int batch, int maxdim, float thresh, float* h0_pairs,
+                                       int64_t* h0_simplex, float* h1_pairs, int64_t* h1_simplex, int cap1, int32_t* counts, float* thresh_out,
+                                       void* ws, size_t ws_bytes, size_t pool_bytes, void* stream_) {
+  if (!parent_ends || !parent_sdist || !subset_idx || n_parent < 2 || n_parent > 65535 || m < 1 || m > n_parent)
+    return set_error(TDA_ERR_INVALID, "tda_rips_subsets_launch: bad arguments");
+  if (isinf(thresh) && !parent_dm) return set_error(TDA_ERR_INVALID, "tda_rips_subsets_launch: the enclosing radius needs the parent's distance matrix");
+  SubsetInput sub{parent_ends, parent_sdist, parent_dm, n_parent, subset_idx};
+  return rips_enqueue(nullptr, m, batch, maxdim, thresh, h0_pairs, h0_simplex, h1_pairs, h1_simplex, cap1, counts, thresh_out, ws, ws_bytes,
+                      pool_bytes, stream_, &sub);
 }
 
 extern "C" int tda_rips_stats(const void* ws, int n, int batch, int maxdim, int cap1, size_t pool_bytes, int64_t* stats_host) {

@@ -224,14 +224,19 @@ def knn_row_sharded(X, k, metric="cosine", rank=None, world=None, group=None, ro
     return tuple(out)
 
 
-def bootstrap_rips(Y, n_resamples=256, size=1000, seed=4000, layer_ids=None, replace=False, maxdim=1, max_batch=256):
+def bootstrap_rips(Y, n_resamples=256, size=1000, seed=4000, layer_ids=None, replace=False, maxdim=1, max_batch=256, subsets=None):
     """Config C4 of BASELINE.json: for every 3-D cloud Y[l] ([L,n,dim] CUDA tensor, e.g. the UMAP output of layer l),
     `n_resamples` bootstrap resamples of `size` points -> Rips H0/H1 of each, batched `max_batch` problems per call (the
     batch dimension of every Rips kernel is the resample).  The reference has no bootstrap code: the semantics are
     L * n_resamples independent ``ripser(Y_l[idx], maxdim=1)`` calls; index sets come from
-    workloads.c4_resample_indices (seeded per (layer, resample)).  Returns results[l][r] = dict with 'dgms', ..."""
+    workloads.c4_resample_indices (seeded per (layer, resample)).  Returns results[l][r] = dict with 'dgms', ...
+
+    subsets (default: whenever the index sets are strictly ascending, i.e. sampled without replacement): the edges of the layer's
+    cloud are sorted ONCE and every resample takes its filtration ranks from that order (rips_subsets_launch) instead of
+    computing and sorting its own distance matrix; the results are the same bits as the per-resample path (subsets=False)."""
     torch = _lib.require_cuda()
     from . import workloads
+    from .rips import rips_sort_edges, rips_subsets_launch
     Lc, n, dim = Y.shape
     layer_ids = list(range(Lc)) if layer_ids is None else list(layer_ids)
     dev = Y.device
@@ -242,14 +247,25 @@ def bootstrap_rips(Y, n_resamples=256, size=1000, seed=4000, layer_ids=None, rep
     k = 0              # diagrams of one batch while the device works on the next
     for li, layer in enumerate(layer_ids):
         idx_h = workloads.c4_resample_indices(layer, n, n_resamples, size, seed=seed, replace=replace)
+        ascending = size >= 2 and bool((np.diff(idx_h, axis=1) > 0).all())
+        use_sub = ascending and maxdim <= 1 and size * (size - 1) >= n if subsets is None else bool(subsets)
+        if use_sub and not ascending:
+            raise ValueError("bootstrap_rips(subsets=True) needs strictly ascending index sets (sampling without replacement)")
+        if use_sub:   # the layer's cloud: distance matrix and ALL its edges in filtration order, once for its resamples
+            parent_dm = pdist_lowdim(Y[li:li + 1].contiguous())
+            parent_ends, parent_sdist = rips_sort_edges(parent_dm)
         for r0 in range(0, n_resamples, max_batch):
             st = streams[k % 2]
             k += 1
             st.wait_stream(cur)
             with torch.cuda.stream(st):
-                idx = torch.from_numpy(idx_h[r0:r0 + max_batch]).to(dev, non_blocking=True)
-                pts = Y[li][idx].contiguous()                      # [b, size, dim]
-                pending.append((li, rips_batch_launch(pdist_lowdim(pts), maxdim=maxdim)))
+                if use_sub:
+                    idx = torch.from_numpy(idx_h[r0:r0 + max_batch].astype(np.int32)).to(dev, non_blocking=True)
+                    pending.append((li, rips_subsets_launch(parent_ends, parent_sdist, parent_dm, idx, maxdim=maxdim)))
+                else:
+                    idx = torch.from_numpy(idx_h[r0:r0 + max_batch]).to(dev, non_blocking=True)
+                    pts = Y[li][idx].contiguous()                      # [b, size, dim]
+                    pending.append((li, rips_batch_launch(pdist_lowdim(pts), maxdim=maxdim)))
             if len(pending) == 2:
                 lj, job = pending.pop(0)
                 out[lj] += job.finish()

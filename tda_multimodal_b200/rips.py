@@ -48,14 +48,20 @@ class RipsJob:
     stream, checks the per-problem status and returns the list of result dicts; on a capacity overflow it re-runs the
     batch synchronously with larger buffers."""
 
-    def __init__(self, dm, maxdim, thresh, cap1, pool_bytes, want_simplices, want_stats):
+    def __init__(self, dm, maxdim, thresh, cap1, pool_bytes, want_simplices, want_stats, subset=None):
         torch = _lib.require_cuda()
         L = _lib.lib()
         self.dm, self.maxdim, self.thresh = dm, maxdim, float(thresh)
         self.cap1, self.pool_bytes = cap1, pool_bytes
         self.want_simplices, self.want_stats = want_simplices, want_stats
-        B, n, _ = dm.shape
-        dev = dm.device
+        self.subset = subset           # (parent_ends, parent_sdist, parent_dm, n_parent, idx [B,m] int32): clouds = subsets of one parent
+        if subset is None:
+            B, n, _ = dm.shape
+            dev = dm.device
+        else:
+            B, n = subset[4].shape
+            dev = subset[4].device
+        self.B, self.n, self.dev = B, n, dev
         self.stream = torch.cuda.current_stream(dev)
         self.ws_bytes = int(L.tda_rips_workspace_bytes(n, B, maxdim, cap1, pool_bytes))
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
@@ -66,9 +72,16 @@ class RipsJob:
         self.counts = torch.zeros((B, 4), dtype=torch.int32, device=dev)
         self.th = torch.empty((B,), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            _lib.check(L.tda_rips_launch(_lib.ptr(dm), n, B, maxdim, self.thresh, _lib.ptr(self.h0), _lib.ptr(self.h0s), _lib.ptr(self.h1),
-                                         _lib.ptr(self.h1s), cap1, _lib.ptr(self.counts), _lib.ptr(self.th), _lib.ptr(self.ws),
-                                         self.ws_bytes, pool_bytes, _lib.stream_ptr()))
+            if subset is None:
+                _lib.check(L.tda_rips_launch(_lib.ptr(dm), n, B, maxdim, self.thresh, _lib.ptr(self.h0), _lib.ptr(self.h0s), _lib.ptr(self.h1),
+                                             _lib.ptr(self.h1s), cap1, _lib.ptr(self.counts), _lib.ptr(self.th), _lib.ptr(self.ws),
+                                             self.ws_bytes, pool_bytes, _lib.stream_ptr()))
+            else:
+                pe, ps, pdm, n_parent, idx = subset
+                _lib.check(L.tda_rips_subsets_launch(_lib.ptr(pe), _lib.ptr(ps), _lib.ptr(pdm), int(n_parent), _lib.ptr(idx), n, B, maxdim,
+                                                     self.thresh, _lib.ptr(self.h0), _lib.ptr(self.h0s), _lib.ptr(self.h1), _lib.ptr(self.h1s),
+                                                     cap1, _lib.ptr(self.counts), _lib.ptr(self.th), _lib.ptr(self.ws), self.ws_bytes,
+                                                     pool_bytes, _lib.stream_ptr()))
             # the results follow the kernels on the same stream into pinned host buffers (torch's caching host allocator): when the
             # stream has drained they are already on the host, and finish() has no copy left to wait for
             self._host = {k: (t.to("cpu", non_blocking=True) if t is not None else None)
@@ -78,7 +91,7 @@ class RipsJob:
         torch = _lib.require_cuda()
         L = _lib.lib()
         dm = self.dm
-        B, n, _ = dm.shape
+        B, n = self.B, self.n
         self.stream.synchronize()
         host = self._host
         counts_h = host["counts"].numpy()
@@ -86,12 +99,17 @@ class RipsJob:
             # some problem overflowed cap1 / the column pool: run the whole batch again, synchronously, with larger buffers
             del self.ws
             with torch.cuda.stream(self.stream):
+                if self.subset is not None:
+                    if self.cap1 > (1 << 24):
+                        raise RuntimeError("tda_multimodal_b200: Rips job keeps overflowing (cap1=%d)" % self.cap1)
+                    return RipsJob(None, self.maxdim, self.thresh, 2 * self.cap1, 2 * self.pool_bytes, self.want_simplices, self.want_stats,
+                                   subset=self.subset).finish()
                 return rips_batch(dm, maxdim=self.maxdim, thresh=self.thresh, cap1=2 * self.cap1, pool_bytes=2 * self.pool_bytes,
                                   want_simplices=self.want_simplices, want_stats=self.want_stats)
         stats = None
         if self.want_stats and self.maxdim >= 1:
             stats = np.zeros((B, _lib.RIPS_STATS), dtype=np.int64)
-            with torch.cuda.device(dm.device):
+            with torch.cuda.device(self.dev):
                 _lib.check(L.tda_rips_stats(_lib.ptr(self.ws), n, B, self.maxdim, self.cap1, self.pool_bytes, stats.ctypes.data))
         h0_h = host["h0"].numpy()
         h1_h = host["h1"].numpy() if host["h1"] is not None else None
@@ -122,9 +140,9 @@ def _free_bytes_estimate(torch, dev):
                + int(torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)))
 
 
-def _default_sizes(torch, dm, cap1, pool_bytes):
-    B, n, _ = dm.shape
-    dev = dm.device
+def _default_sizes(torch, dm, cap1, pool_bytes, shape=None, device=None):
+    B, n = (dm.shape[0], dm.shape[1]) if shape is None else shape
+    dev = dm.device if device is None else device
     cap1 = _next_pow2(cap1 or max(64, 4 * n))
     free_bytes = _free_bytes_estimate(torch, dev)
     if pool_bytes is None:
@@ -152,6 +170,46 @@ def rips_batch_launch(dm, maxdim=1, thresh=float("inf"), cap1=None, pool_bytes=N
     dm = dm.contiguous()
     cap1, pool_bytes, _ = _default_sizes(torch, dm, cap1, pool_bytes)
     return RipsJob(dm, maxdim, thresh, cap1, pool_bytes, want_simplices, want_stats)
+
+
+def rips_sort_edges(dm):
+    """The edges of `B` clouds in filtration order -- ALL of them, no threshold (tda_rips_sort_edges): dm [B,n,n] float32 CUDA ->
+    (ends [B,E] int32 holding (i << 16 | j), i > j; sdist [B,E] float32), ripser's order (length ascending, edge index descending).
+    Input of rips_subsets_launch."""
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    assert dm.is_cuda and dm.dtype == torch.float32 and dm.dim() == 3 and dm.shape[1] == dm.shape[2]
+    dm = dm.contiguous()
+    B, n, _ = dm.shape
+    E = n * (n - 1) // 2
+    ends = torch.empty((B, E), dtype=torch.int32, device=dm.device)
+    sdist = torch.empty((B, E), dtype=torch.float32, device=dm.device)
+    with torch.cuda.device(dm.device):
+        ws_bytes = int(L.tda_rips_sort_edges_workspace_bytes(n, B))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dm.device)
+        _lib.check(L.tda_rips_sort_edges(_lib.ptr(dm), n, B, _lib.ptr(ends), _lib.ptr(sdist), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()))
+        ws.record_stream(torch.cuda.current_stream(dm.device))
+    return ends, sdist
+
+
+def rips_subsets_launch(parent_ends, parent_sdist, parent_dm, idx, maxdim=1, thresh=float("inf"), cap1=None, pool_bytes=None,
+                        want_simplices=False, want_stats=False):
+    """Persistence of `B` SUBSETS of one parent cloud, enqueued on the current stream (tda_rips_subsets_launch): parent_ends /
+    parent_sdist [E_parent] = rips_sort_edges(parent_dm[None]) of that cloud, parent_dm [n_parent, n_parent] its distance matrix
+    (used for the enclosing radius of each subset), idx [B,m] int32 CUDA: parent indices of every subset, STRICTLY ASCENDING in each
+    row.  The result equals rips_batch_launch(pdist_lowdim(points[idx])) -- same diagrams, same simplex indices -- without the
+    pairwise distances, the key generation and the radix sort of every subset: a subset keeps the parent's edge order, so its
+    ranks are a flag + prefix count over the parent's sorted edge list."""
+    torch = _lib.require_cuda()
+    if maxdim > 1:
+        raise NotImplementedError("tda_multimodal_b200: asynchronous Rips jobs cover maxdim <= 1")
+    assert idx.is_cuda and idx.dtype == torch.int32 and idx.dim() == 2
+    n_parent = int(parent_dm.shape[-1])
+    pe, ps, pdm = parent_ends.reshape(-1).contiguous(), parent_sdist.reshape(-1).contiguous(), parent_dm.reshape(n_parent, n_parent).contiguous()
+    assert pe.numel() == n_parent * (n_parent - 1) // 2 == ps.numel()
+    idx = idx.contiguous()
+    cap1, pool_bytes, _ = _default_sizes(torch, None, cap1, pool_bytes, shape=tuple(idx.shape), device=idx.device)
+    return RipsJob(None, maxdim, thresh, cap1, pool_bytes, want_simplices, want_stats, subset=(pe, ps, pdm, n_parent, idx))
 
 
 def rips_batch(dm, maxdim=1, thresh=float("inf"), cap1=None, pool_bytes=None, want_simplices=False, want_stats=False):

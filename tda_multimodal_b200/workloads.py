@@ -131,13 +131,16 @@ def c3_layers(n_layers=32, n=2000, d=4096, seed=3000, layers=None, out=None):
 
 def c4_resample_indices(layer, n_points=2000, n_resamples=256, size=1000, seed=4000, replace=False):
     """C4: bootstrap resamples of one layer's 3-D cloud: [n_resamples, size] int64 indices (without replacement by
-    default: duplicate points create zero-length edges; both are supported)."""
+    default: duplicate points create zero-length edges; both are supported).  Without replacement every index set is
+    ASCENDING: a resample is a set of points, and in the parent's order its edges keep the parent's filtration order, which
+    pipeline.bootstrap_rips uses (rips_subsets_launch)."""
     key = (int(layer), int(n_points), int(n_resamples), int(size), int(seed), bool(replace))
     if key not in _C4_INDEX_CACHE:
         out = np.empty((n_resamples, size), dtype=np.int64)
         for r in range(n_resamples):
             rng = np.random.default_rng(seed + 256 * layer + r)
-            out[r] = rng.choice(n_points, size=size, replace=replace)
+            pick = rng.choice(n_points, size=size, replace=replace)
+            out[r] = pick if replace else np.sort(pick)
         out.setflags(write=False)
         if len(_C4_INDEX_CACHE) > 4096:
             _C4_INDEX_CACHE.clear()

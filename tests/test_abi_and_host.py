@@ -99,6 +99,8 @@ def test_workload_generators_are_seeded():
     assert not np.array_equal(a, workloads.c3_layer(4, n=50, d=64))
     idx = workloads.c4_resample_indices(0, 200, 4, 100)
     assert idx.shape == (4, 100) and all(len(set(r)) == 100 for r in idx)
+    assert (np.diff(idx, axis=1) > 0).all()          # without replacement: ascending sets (the subset front end relies on it)
+    assert not (np.diff(workloads.c4_resample_indices(0, 200, 4, 100, replace=True), axis=1) > 0).all()
     c1 = workloads.c1_activations(n_layers=2, d=32)
     assert len(c1) == 48 and sum(v["metadata"]["type"] == "bound" for v in c1.values()) == 36
 
