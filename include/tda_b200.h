@@ -40,6 +40,7 @@ void tda_launch_count_reset(void);
  *   rips_w0 (1024), rips_wsparse (8192), rips_wmax (32768), rips_dense_min (64), rips_dense_div (8): sweep2 window schedule
  *   rips_cluster (0 = auto: 8 for up to 4 clouds per launch, else 4): CTAs of the thread-block cluster that reduces one cloud (sweep2)
  *   rips_apparent_rows (1): apparent pairs by matrix row (rank row of a vertex in shared memory); 0: one warp per edge in rank order
+ *   rips_h0_chunked (1): H0 in one launch from the sorted edge list (Boruvka / Kruskal by chunks, n <= 16384); 0: Boruvka rounds on the rank matrix
  *   rips_wc_max_rows (262144): sweep2, rows a single warp sweeps before it hands its column to the cluster engine
  *   rips_warp_engine (1): sweep2 reduces every column by a single warp first (speculatively, committed in ripser's order); 0: windows only
  *   sgd_mode (0): 0 deterministic SGD (thread-block cluster per cloud for fit, warp per point for transform; bit-reproducible
