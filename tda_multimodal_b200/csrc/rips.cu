@@ -343,7 +343,8 @@ __global__ void __launch_bounds__(1024) boruvka_merge_kernel(const uint32_t* __r
 // shared memory) repeat until no edge of the chunk joins two components, then the next chunk follows.  Earlier chunks hold no
 // joining edge any more, so the lowest joining edge of a component inside the current chunk is its lowest joining edge overall:
 // every hook is an edge of the (unique) minimum spanning forest.  For a point cloud nearly all of the forest lies in the first
-// chunk; the few long edges between clusters are found by one cheap pass per later chunk (Kruskal by chunks).  Replaces ~25 launches
+// chunk; the few long edges between clusters are found by one cheap pass per later chunk (Kruskal by chunks; the chunks double
+// in length while they are clean).  Replaces ~25 launches
 // that each re-read the whole rank matrix: H0 of 256 x 1000 points 8-13 ms -> well under 1 ms, and one launch instead of 25 in
 // the sweep, where every small launch queues behind the other groups' kernels.
 constexpr int kBorChunk = 32768;
@@ -363,16 +364,28 @@ __global__ void __launch_bounds__(1024) boruvka_chunked_kernel(const uint32_t* _
   for (int i = tid; i < n; i += nt) { comp[i] = (uint32_t)i; cbest[i] = kNoEdge; }
   if (tid == 0) s_count = 0;
   __syncthreads();
-  int c0 = 0;
+  int c0 = 0, len = kBorChunk;
   while (c0 < T && s_count < n - 1) {     // (s_count only changes between barriers: every thread sees the same value here)
-    const int c1 = min(T, c0 + kBorChunk);
+    const int c1 = (int)min((long long)T, (long long)c0 + len);
     int any = 0;
-    for (int e = c0 + tid; e < c1; e += nt) {
-      const uint32_t en = __ldg(&EN[e]);
-      const uint32_t cu = comp[en >> 16], cv = comp[en & 0xffffu];
-      if (cu != cv) { atomicMin(&cbest[cu], (uint32_t)e); atomicMin(&cbest[cv], (uint32_t)e); any = 1; }
+    for (int e0 = c0 + tid; e0 < c1; e0 += nt * 8) {   // eight edges per thread in flight: the pass is bound by the latency of its loads
+      uint32_t en[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { const int e = e0 + u * nt; en[u] = e < c1 ? __ldg(&EN[e]) : 0u; }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int e = e0 + u * nt;
+        if (e < c1) {
+          const uint32_t cu = comp[en[u] >> 16], cv = comp[en[u] & 0xffffu];
+          if (cu != cv) { atomicMin(&cbest[cu], (uint32_t)e); atomicMin(&cbest[cv], (uint32_t)e); any = 1; }
+        }
+      }
     }
-    if (!__syncthreads_or(any)) { c0 = c1; continue; }   // no joining edge left in this chunk
+    if (!__syncthreads_or(any)) {   // no joining edge left in this chunk: on to the next one, twice as long (few components are
+      c0 = c1;                      // left once a chunk is clean, and what joins them may lie far up the list)
+      if (len < (1 << 20)) len <<= 1;
+      continue;
+    }
     for (int c = tid; c < n; c += nt) {
       const uint32_t r = cbest[c];
       uint32_t par = (uint32_t)c;
