@@ -327,7 +327,9 @@ def algorithmic_work(stage, a, L, extra):
         "umap_sgd": 124.0 * extra.get("sgd_fired_per_layer", 0.0) * L,
         "rips_pdist": L * (12.0 * n + 4.0 * n * n),
         "rips_edge_sort": L * (4.0 * n * n + 16.0 * E + 16.0 * E),     # read dm, radix sort key+payload, rank scatter
-        "rips_h0": L * (4.0 * n * n) * extra.get("boruvka_rounds", 11),
+        # H0 from the sorted edge list (boruvka_chunked_kernel): at most one pass over the 4-byte end points of the E edges, plus a
+        # few repeated passes over the chunks that hold forest edges (not counted)
+        "rips_h0": L * 4.0 * E,
         "rips_apparent": L * 8.0 * (E - n + 1) * (n - 2),
         # residual reduction: 16 B (endpoints, apex, parents) per row swept / substituted; per heavy row two V rows + two
         # adjacency rows (4 * n/8 B)

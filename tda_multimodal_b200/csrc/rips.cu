@@ -177,14 +177,17 @@ __global__ void __launch_bounds__(kSubThreads) subset_count_kernel(const uint32_
   subset_build_map(s_submap, idx + (size_t)p * m, m, n_parent);
   int cnt = 0, valid = 0;
   const int64_t base = (int64_t)c * kSubChunk;
-#pragma unroll 8
-  for (int k = 0; k < kSubPerThread; ++k) {
-    const int64_t r = base + (int64_t)k * kSubThreads + tid;
-    if (r < Ep) {
-      const uint32_t e = __ldg(&pends[r]);
-      if (s_submap[e >> 16] != 0xffffu && s_submap[e & 0xffffu] != 0xffffu) {
-        ++cnt;
-        valid += __float_as_uint(__ldg(&psdist[r])) <= tb ? 1 : 0;
+#pragma unroll 2
+  for (int k = 0; k < kSubPerThread / 4; ++k) {
+    const int64_t r0 = base + ((int64_t)k * kSubThreads + tid) * 4;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (r0 + u < Ep) {
+        const uint32_t e = __ldg(&pends[r0 + u]);
+        if (s_submap[e >> 16] != 0xffffu && s_submap[e & 0xffffu] != 0xffffu) {
+          ++cnt;
+          valid += __float_as_uint(__ldg(&psdist[r0 + u])) <= tb ? 1 : 0;
+        }
       }
     }
   }
@@ -226,28 +229,41 @@ __global__ void __launch_bounds__(kSubThreads) subset_scatter_kernel(const uint3
   int* R = rank + (size_t)p * m * m;
   int run = chunk_off[(size_t)p * nchunks + c];
   const int64_t base = (int64_t)c * kSubChunk;
-  for (int k = 0; k < kSubPerThread; ++k) {
-    const int64_t r = base + (int64_t)k * kSubThreads + tid;
-    uint32_t i = 0xffffu, j = 0xffffu;
-    if (r < Ep) {
-      const uint32_t e = __ldg(&pends[r]);
-      i = s_submap[e >> 16];
-      j = s_submap[e & 0xffffu];
+  // four CONSECUTIVE parent edges per thread and trip (positions ascend with the thread, then inside the thread): one warp scan and
+  // one barrier per 1024 edges instead of per 256 -- at one edge per thread the prefix bookkeeping was 125 instructions per
+  // 32 edges and the kernel was bound by instruction issue, not by its 3.6 GB of traffic (profiles/r02n_c4_raw.csv)
+  for (int k = 0; k < kSubPerThread / 4; ++k) {
+    const int64_t r0 = base + ((int64_t)k * kSubThreads + tid) * 4;
+    uint32_t vi[4], vj[4];
+    int cnt = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      vi[u] = 0xffffu; vj[u] = 0xffffu;
+      if (r0 + u < Ep) {
+        const uint32_t e = __ldg(&pends[r0 + u]);
+        vi[u] = s_submap[e >> 16];
+        vj[u] = s_submap[e & 0xffffu];
+      }
+      cnt += (vi[u] != 0xffffu && vj[u] != 0xffffu) ? 1 : 0;
     }
-    const bool f = i != 0xffffu && j != 0xffffu;
-    const unsigned bal = __ballot_sync(0xffffffffu, f);
-    if (lane == 0) s_warp[k & 1][warp] = __popc(bal);   // (double buffered: one barrier per trip)
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) s_warp[k & 1][warp] = incl;   // (double buffered: one barrier per trip)
     __syncthreads();
-    int off = run, tot = 0;
+    int off = run + incl - cnt, tot = 0;
 #pragma unroll
     for (int w = 0; w < kSubThreads / 32; ++w) { const int t = s_warp[k & 1][w]; if (w < warp) off += t; tot += t; }
-    if (f) {
-      const int64_t sr = (int64_t)off + __popc(bal & ((1u << lane) - 1));
-      if (sr < E) {   // (always, for distinct indices inside the parent)
-        R[(size_t)i * m + j] = (int)sr;
-        R[(size_t)j * m + i] = (int)sr;
-        ends[(size_t)p * E + sr] = (i << 16) | j;   // i > j: the relabelling preserves the order
-        sdist[(size_t)p * E + sr] = __ldg(&psdist[r]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (vi[u] != 0xffffu && vj[u] != 0xffffu) {
+        const int64_t sr = off++;
+        if (sr < E) {   // (always, for distinct indices inside the parent)
+          R[(size_t)vi[u] * m + vj[u]] = (int)sr;
+          R[(size_t)vj[u] * m + vi[u]] = (int)sr;
+          ends[(size_t)p * E + sr] = (vi[u] << 16) | vj[u];   // i > j: the relabelling preserves the order
+          sdist[(size_t)p * E + sr] = __ldg(&psdist[r0 + u]);
+        }
       }
     }
     run += tot;
