@@ -263,7 +263,7 @@ def bootstrap_rips(Y, n_resamples=256, size=1000, seed=4000, layer_ids=None, rep
                     idx = torch.from_numpy(idx_h[r0:r0 + max_batch].astype(np.int32)).to(dev, non_blocking=True)
                     pending.append((li, rips_subsets_launch(parent_ends, parent_sdist, parent_dm, idx, maxdim=maxdim)))
                 else:
-                    idx = torch.from_numpy(idx_h[r0:r0 + max_batch]).to(dev, non_blocking=True)
+                    idx = torch.from_numpy(np.array(idx_h[r0:r0 + max_batch])).to(dev, non_blocking=True)   # (a copy: the cached sets are read-only)
                     pts = Y[li][idx].contiguous()                      # [b, size, dim]
                     pending.append((li, rips_batch_launch(pdist_lowdim(pts), maxdim=maxdim)))
             if len(pending) == 2:
