@@ -204,8 +204,15 @@ def rips_subsets_launch(parent_ends, parent_sdist, parent_dm, idx, maxdim=1, thr
     if maxdim > 1:
         raise NotImplementedError("tda_multimodal_b200: asynchronous Rips jobs cover maxdim <= 1")
     assert idx.is_cuda and idx.dtype == torch.int32 and idx.dim() == 2
-    n_parent = int(parent_dm.shape[-1])
-    pe, ps, pdm = parent_ends.reshape(-1).contiguous(), parent_sdist.reshape(-1).contiguous(), parent_dm.reshape(n_parent, n_parent).contiguous()
+    pe, ps = parent_ends.reshape(-1).contiguous(), parent_sdist.reshape(-1).contiguous()
+    if parent_dm is None:      # only read for the enclosing radius: a finite threshold does without it
+        if not np.isfinite(thresh):
+            raise ValueError("rips_subsets_launch: parent_dm is needed unless thresh is finite (enclosing radius of every subset)")
+        n_parent = (1 + int(round((1 + 8 * pe.numel()) ** 0.5))) // 2
+        pdm = None
+    else:
+        n_parent = int(parent_dm.shape[-1])
+        pdm = parent_dm.reshape(n_parent, n_parent).contiguous()
     assert pe.numel() == n_parent * (n_parent - 1) // 2 == ps.numel()
     idx = idx.contiguous()
     cap1, pool_bytes, _ = _default_sizes(torch, None, cap1, pool_bytes, shape=tuple(idx.shape), device=idx.device)

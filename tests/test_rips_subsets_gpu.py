@@ -82,6 +82,17 @@ def test_subsets_with_user_threshold_and_tiny_sets(torch_cuda):
     _assert_same(*_both_paths(torch_cuda, pts, _subsets(rng, 200, 200, 1)))            # the whole cloud
     sub, reg = _both_paths(torch_cuda, pts[:40], _subsets(rng, 40, 12, 2))              # few points: E_sub * 8 bytes still hold the vertex map
     _assert_same(sub, reg)
+    # a finite threshold needs no parent distance matrix (it is only read for the enclosing radius)
+    from tda_multimodal_b200 import rips
+    torch = torch_cuda
+    P = torch.from_numpy(pts.astype(np.float32)).cuda()
+    idx = _subsets(rng, 200, 90, 2)
+    ends, sdist = rips.rips_sort_edges(rips.pdist_lowdim(P[None]))
+    got = rips.rips_subsets_launch(ends, sdist, None, torch.from_numpy(idx).cuda(), thresh=0.9, want_simplices=True).finish()
+    want = rips.rips_batch(rips.pdist_lowdim(P[torch.from_numpy(idx).cuda().long()].contiguous()), thresh=0.9, want_simplices=True)
+    _assert_same(got, want)
+    with pytest.raises(ValueError):
+        rips.rips_subsets_launch(ends, sdist, None, torch.from_numpy(idx).cuda())
 
 
 def test_bootstrap_both_paths_and_replacement(torch_cuda):
