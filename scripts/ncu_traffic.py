@@ -2,12 +2,12 @@
 profiles/r02_ncu_dram_bytes.json: per stage of bench.py's roofline table, dram__bytes_read.sum + dram__bytes_write.sum per launch of
 the stage's dominant kernel (mean over the captured launches), with the other counters the judge reads (duration, grid, tensor
 pipe, SM / DRAM throughput).  bench.py only READS that JSON (roofline.traffic); it never runs ncu.
-  python scripts/ncu_traffic.py profiles/r02_full_raw.csv"""
+  python scripts/ncu_traffic.py profiles/r02_full_raw.csv [--merge]"""
 import csv, json, os, sys
 
 STAGE_OF = {"pdist_gemm_kernel": "pdist_gemm", "prep_kernel": "pdist_prep", "knn_smooth_block_kernel": "knn_smooth", "sgd_cluster_kernel": "umap_sgd",
             "lanczos_cluster_kernel": "spectral_init", "apparent_rows_kernel": "rips_apparent", "apparent_kernel": "rips_apparent", "rips_sweep2_kernel": "rips_reduce",
-            "boruvka_scan_kernel": "rips_h0", "rank_scatter_kernel": "rips_edge_sort"}
+            "boruvka_scan_kernel": "rips_h0", "boruvka_chunked_kernel": "rips_h0", "rank_scatter_kernel": "rips_edge_sort"}
 KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
@@ -49,8 +49,12 @@ def main(path):
                       "sm_throughput_pct": sum(x.get("sm__throughput.avg.pct_of_peak_sustained_elapsed", 0.0) for x in recs) / n,
                       "dram_throughput_pct": sum(x.get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", 0.0) for x in recs) / n,
                       "tensor_pipe_pct": sum(x.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", 0.0) for x in recs) / n,
-                      "source": os.path.relpath(path, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))) + " (ncu --set full, one 16-layer chunk per launch)"}
+                      "source": os.path.relpath(path, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))) + " (ncu --set full, per launch of one group of layers)"}
     dst = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r02_ncu_dram_bytes.json")
+    if "--merge" in sys.argv and os.path.exists(dst):   # a capture of the kernels that changed: the other stages keep their entries
+        old = json.load(open(dst))
+        old.update(out)
+        out = old
     json.dump(out, open(dst, "w"), indent=1)
     sm = os.path.splitext(path)[0].replace("_raw", "") + "_summary.json"
     json.dump(summary, open(sm, "w"), indent=1)
