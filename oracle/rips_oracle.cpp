@@ -75,6 +75,8 @@ struct Rips {
   int maxdim;
   val_t thresh;
   std::vector<val_t> dist;  // full n*n
+  std::vector<val_t> distT;  // its transpose: the cofacet enumerator reads d(v, s) for consecutive v along a ROW of distT (one
+                            // cache line per 16 cofacets instead of one miss per cofacet); same values, same semantics
   Binom C;
   std::vector<std::vector<double>> dgm;       // per dim: flat (birth, death)
   std::vector<std::vector<idx_t>> pair_simplex;  // per dim: flat (birth idx, death idx or -1)
@@ -116,9 +118,11 @@ struct Rips {
     idx_t below, above;
     int v, k, dim;
     int vs[8];
+    const val_t* row[8];  // row[a][v] == d(v, vs[a])
     val_t sdiam;
     Cofacets(const Rips& r_, Simplex s, int dim_) : r(r_), below(s.idx), above(0), v(r_.n - 1), k(dim_ + 1), dim(dim_), sdiam(s.diam) {
       r.vertices(s.idx, dim, vs);
+      for (int a = 0; a <= dim; ++a) row[a] = r.distT.data() + (size_t)vs[a] * r.n;
     }
     bool has_next(bool all = true) {
       if (!all) return v >= k && r.C(v, k) > below;  // only vertices above every simplex vertex
@@ -131,7 +135,7 @@ struct Rips {
     }
     Simplex next() {
       val_t cd = sdiam;
-      for (int a = 0; a <= dim; ++a) cd = std::max(cd, r.d(v, vs[a]));
+      for (int a = 0; a <= dim; ++a) cd = std::max(cd, row[a][v]);
       idx_t ci = above + r.C(v, k + 1) + below;
       --v;
       return Simplex{cd, ci};
@@ -331,6 +335,9 @@ void* rips_oracle_run(const float* dist, int n, int maxdim, float thresh) {
   Rips* r = new Rips();
   r->n = n; r->maxdim = maxdim; r->thresh = thresh;
   r->dist.assign(dist, dist + (size_t)n * n);
+  r->distT.resize((size_t)n * n);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) r->distT[(size_t)j * n + i] = dist[(size_t)i * n + j];
   r->run();
   return r;
 }
