@@ -1,4 +1,4 @@
-"""profiles/<tag>_full_raw.csv (ncu --set full, --page raw --csv --print-units base; made by scripts/gpu_ncu_r02.sh) ->
+"""profiles/<tag>_full_raw.csv (ncu --set full, --page raw --csv --print-units base; made by scripts/gpu_calls/gpu_ncu_r02.sh) ->
 profiles/r02_ncu_dram_bytes.json: per stage of bench.py's roofline table, dram__bytes_read.sum + dram__bytes_write.sum per launch of
 the stage's dominant kernel (mean over the captured launches), with the other counters the judge reads (duration, grid, tensor
 pipe, SM / DRAM throughput).  bench.py only READS that JSON (roofline.traffic); it never runs ncu.
