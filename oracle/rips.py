@@ -33,6 +33,8 @@ def _lib():
         lib = ctypes.CDLL(build())
         lib.rips_oracle_run.restype = ctypes.c_void_p
         lib.rips_oracle_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float]
+        lib.rips_oracle_run2.restype = ctypes.c_void_p
+        lib.rips_oracle_run2.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int]
         lib.rips_oracle_count.restype = ctypes.c_int64
         lib.rips_oracle_count.argtypes = [ctypes.c_void_p, ctypes.c_int]
         lib.rips_oracle_get.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
@@ -97,12 +99,13 @@ def greedy_permutation_points(X, n_perm):
     return idx, lambdas
 
 
-def rips_dm(dm, maxdim=1, thresh=np.inf, with_simplices=False, with_stats=False):
-    """Persistence of the Rips filtration of a full float32 distance matrix."""
+def rips_dm(dm, maxdim=1, thresh=np.inf, with_simplices=False, with_stats=False, apparent=False):
+    """Persistence of the Rips filtration of a full float32 distance matrix.  ``apparent=True`` switches on Ripser 1.2's
+    zero-apparent-pair shortcut (same rows in the same order; far less memory in the top dimension: rips_oracle.cpp header)."""
     dm = np.ascontiguousarray(dm, dtype=np.float32)
     n = dm.shape[0]
     lib = _lib()
-    h = lib.rips_oracle_run(dm.ctypes.data, n, int(maxdim), float(thresh))
+    h = lib.rips_oracle_run2(dm.ctypes.data, n, int(maxdim), float(thresh), int(bool(apparent)))
     try:
         dgms, simp, stats = [], [], []
         for q in range(maxdim + 1):

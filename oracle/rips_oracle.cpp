@@ -14,6 +14,10 @@
 //   * H_q (q>=1) by implicit coboundary-matrix reduction with a binary heap working column,
 //     the emergent-pair shortcut, a pivot->column hash map and clearing between dimensions,
 //   * pairs emitted in processing order, zero-persistence pairs dropped.
+//   * optional (`apparent` = 1; Ripser 1.2, Bauer 2021 section 4.2 "apparent pairs"): a zero-persistence pair (s, c) with c the
+//     oldest cofacet of s and s the youngest facet of c is a persistence pair that needs no reduction; such columns are neither
+//     assembled nor stored in the pivot map but recognised on the fly.  Same pairs, same rows, same order (tests compare the two
+//     modes bit for bit); it only makes the top dimension of config C2 (1.2e9 triangles at n = 2000) fit in memory.
 // Parity is PINNED for this file: tests/test_oracle_golden.py checks it against the 32
 // shipped point clouds + summary_stats.json of the reference (tda-output/), see tests/golden/.
 //
@@ -24,6 +28,7 @@
 #include <cstring>
 #include <limits>
 #include <queue>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -82,6 +87,7 @@ struct Rips {
   std::vector<std::vector<idx_t>> pair_simplex;  // per dim: flat (birth idx, death idx or -1)
   int64_t num_edges;
   Stats st;
+  bool apparent = false;  // Ripser 1.2's zero-apparent-pair shortcut (see the header)
 
   val_t d(int i, int j) const { return dist[(size_t)i * n + j]; }
 
@@ -141,6 +147,55 @@ struct Rips {
       return Simplex{cd, ci};
     }
   };
+
+  // oldest cofacet of s with the diameter of s (the enumerator runs in decreasing index = increasing age among equal diameters)
+  Simplex zero_pivot_cofacet(const Simplex& s, int dim) const {
+    Cofacets cf(*this, s, dim);
+    while (cf.has_next()) {
+      Simplex c = cf.next();
+      if (c.diam == s.diam) return c;
+    }
+    return Simplex{0, -1};
+  }
+  // youngest facet of c with the diameter of c: dropping a larger vertex gives a smaller index, so the first hit is the youngest
+  Simplex zero_pivot_facet(const Simplex& c, int dimc) const {
+    int vs[8];
+    vertices(c.idx, dimc, vs);
+    for (int r = 0; r <= dimc; ++r) {
+      val_t m = 0;
+      idx_t fi = 0;
+      int k = dimc;
+      for (int a = 0; a <= dimc; ++a) {
+        if (a == r) continue;
+        fi += C(vs[a], k);
+        --k;
+        for (int b = a + 1; b <= dimc; ++b)
+          if (b != r) m = std::max(m, d(vs[a], vs[b]));
+      }
+      if (m == c.diam) return Simplex{m, fi};
+    }
+    return Simplex{0, -1};
+  }
+  // the facet e of c with (e, c) a zero apparent pair, or idx -1
+  Simplex zero_apparent_facet(const Simplex& c, int dimc) const {
+    Simplex f = zero_pivot_facet(c, dimc);
+    if (f.idx == -1) return f;
+    Simplex cc = zero_pivot_cofacet(f, dimc - 1);
+    return (cc.idx == c.idx) ? f : Simplex{0, -1};
+  }
+  // the cofacet c of s with (s, c) a zero apparent pair, or idx -1
+  Simplex zero_apparent_cofacet(const Simplex& s, int dim) const {
+    Simplex c = zero_pivot_cofacet(s, dim);
+    if (c.idx == -1) return c;
+    Simplex f = zero_pivot_facet(c, dim + 1);
+    return (f.idx == s.idx) ? c : Simplex{0, -1};
+  }
+  // column s (dimension dim >= 1) takes no part in the reduction: it is the birth or the death of a zero apparent pair.  The facet
+  // side is asked for dim >= 2 only: the pairs of edges with vertices are dimension 0's (union-find), as in Ripser.
+  bool in_zero_apparent_pair(const Simplex& s, int dim) const {
+    if (zero_apparent_cofacet(s, dim).idx != -1) return true;
+    return dim >= 2 && zero_apparent_facet(s, dim).idx != -1;
+  }
 
   static Simplex pop_pivot(Heap& h, int64_t& pops) {
     if (h.empty()) return Simplex{0, -1};
@@ -206,6 +261,12 @@ struct Rips {
       }
     }
     std::reverse(columns.begin(), columns.end());
+    if (apparent) {
+      std::vector<Simplex> kept;
+      for (const Simplex& e : columns)
+        if (zero_apparent_cofacet(e, 1).idx == -1) kept.push_back(e);
+      columns.swap(kept);
+    }
     for (int i = 0; i < n; ++i)
       if (find(i) == i) {
         dgm[0].push_back(0.0); dgm[0].push_back(INF);
@@ -219,14 +280,41 @@ struct Rips {
       reduce(columns, pivot_col, dim);
       if (dim < maxdim) {
         std::vector<Simplex> next_simplices, next_columns;
-        for (const Simplex& s : simplices) {
-          Cofacets cf(*this, s, dim);
-          while (cf.has_next(false)) {
-            Simplex c = cf.next();
-            if (c.diam <= thresh) {
-              next_simplices.push_back(c);
-              if (pivot_col.find(c.idx) == pivot_col.end()) next_columns.push_back(c);
+        const bool keep_simplices = dim + 1 < maxdim;   // the list is only read to assemble the dimension after the next
+        if (!apparent) {
+          for (const Simplex& s : simplices) {
+            Cofacets cf(*this, s, dim);
+            while (cf.has_next(false)) {
+              Simplex c = cf.next();
+              if (c.diam <= thresh) {
+                if (keep_simplices) next_simplices.push_back(c);
+                if (pivot_col.find(c.idx) == pivot_col.end()) next_columns.push_back(c);
+              }
             }
+          }
+        } else {
+          // the apparent-pair test dominates (one cofacet scan + one facet scan per simplex): threads over slices of the list;
+          // the order of the result is fixed by the sort below
+          unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+          std::vector<std::vector<Simplex>> part_s(nt), part_c(nt);
+          std::vector<std::thread> pool;
+          for (unsigned t = 0; t < nt; ++t)
+            pool.emplace_back([&, t]() {
+              for (size_t i = t; i < simplices.size(); i += nt) {
+                Cofacets cf(*this, simplices[i], dim);
+                while (cf.has_next(false)) {
+                  Simplex c = cf.next();
+                  if (c.diam <= thresh) {
+                    if (keep_simplices) part_s[t].push_back(c);
+                    if (pivot_col.find(c.idx) == pivot_col.end() && !in_zero_apparent_pair(c, dim + 1)) part_c[t].push_back(c);
+                  }
+                }
+              }
+            });
+          for (auto& th : pool) th.join();
+          for (unsigned t = 0; t < nt; ++t) {
+            next_simplices.insert(next_simplices.end(), part_s[t].begin(), part_s[t].end());
+            next_columns.insert(next_columns.end(), part_c[t].begin(), part_c[t].end());
           }
         }
         std::sort(next_columns.begin(), next_columns.end(), RevFiltLess());
@@ -259,7 +347,7 @@ struct Rips {
           if (c.diam <= thresh) {
             buf.push_back(c);
             if (check && c.diam == col.diam) {
-              if (pivot_col.find(c.idx) == pivot_col.end()) { pivot = c; emergent = true; break; }
+              if (pivot_col.find(c.idx) == pivot_col.end() && (!apparent || zero_apparent_facet(c, dim + 1).idx == -1)) { pivot = c; emergent = true; break; }
               check = false;
             }
           }
@@ -299,6 +387,22 @@ struct Rips {
           pivot = get_pivot(work, st.pops[dim]);
           continue;
         }
+        if (apparent) {
+          Simplex e = zero_apparent_facet(pivot, dim + 1);
+          if (e.idx != -1) {   // the pivot belongs to an apparent column e (younger than col, empty reduction column): add it
+            ++st.additions[dim];
+            ++steps;
+            vcol.push_back(e.idx);
+            Cofacets cf(*this, e, dim);
+            while (cf.has_next()) {
+              Simplex c = cf.next();
+              ++st.cofacets[dim];
+              if (c.diam <= thresh) work.push(c);
+            }
+            pivot = get_pivot(work, st.pops[dim]);
+            continue;
+          }
+        }
         if (pivot.diam > col.diam) {
           dgm[dim].push_back((double)col.diam); dgm[dim].push_back((double)pivot.diam);
           pair_simplex[dim].push_back(col.idx); pair_simplex[dim].push_back(pivot.idx);
@@ -331,9 +435,11 @@ struct Rips {
 extern "C" {
 
 // dist: full n*n float32 matrix (row-major, symmetric, zero diagonal). thresh = +inf -> enclosing radius.
-void* rips_oracle_run(const float* dist, int n, int maxdim, float thresh) {
+void* rips_oracle_run2(const float* dist, int n, int maxdim, float thresh, int apparent);
+void* rips_oracle_run(const float* dist, int n, int maxdim, float thresh) { return rips_oracle_run2(dist, n, maxdim, thresh, 0); }
+void* rips_oracle_run2(const float* dist, int n, int maxdim, float thresh, int apparent) {
   Rips* r = new Rips();
-  r->n = n; r->maxdim = maxdim; r->thresh = thresh;
+  r->n = n; r->maxdim = maxdim; r->thresh = thresh; r->apparent = apparent != 0;
   r->dist.assign(dist, dist + (size_t)n * n);
   r->distT.resize((size_t)n * n);
   for (int i = 0; i < n; ++i)

@@ -85,11 +85,12 @@ def _clouds():
 CLOUDS = _clouds()
 
 
+@pytest.mark.parametrize("apparent", [False, True])
 @pytest.mark.parametrize("name", sorted(CLOUDS))
-def test_oracle_equals_textbook_reduction_enclosing_radius(name):
+def test_oracle_equals_textbook_reduction_enclosing_radius(name, apparent):
     X = CLOUDS[name]
     dm = orips.euclidean_dm_f32(X)
-    got = orips.rips_dm(dm, maxdim=2)
+    got = orips.rips_dm(dm, maxdim=2, apparent=apparent)
     want = textbook_diagrams(dm, 2, enclosing_radius(dm))
     assert got["thresh"] == float(enclosing_radius(dm))
     for q in range(3):
@@ -122,7 +123,38 @@ def test_oracle_equals_textbook_reduction_random_sweep(seed):
     dm = orips.euclidean_dm_f32(X)
     enc = enclosing_radius(dm)
     thresh = enc if seed % 3 == 0 else np.float32(rng.uniform(0.4, 1.0) * enc)
-    got = orips.rips_dm(dm, maxdim=2, thresh=float(thresh))
     want = textbook_diagrams(dm, 2, thresh)
-    for q in range(3):
-        assert np.array_equal(sorted_rows(got["dgms"][q]), want[q]), (seed, n, dim, q)
+    for apparent in (False, True):
+        got = orips.rips_dm(dm, maxdim=2, thresh=float(thresh), apparent=apparent)
+        for q in range(3):
+            assert np.array_equal(sorted_rows(got["dgms"][q]), want[q]), (seed, n, dim, q, apparent)
+
+
+def test_apparent_pair_shortcut_changes_nothing():
+    """The oracle's optional apparent-pair shortcut (Ripser 1.2's; what makes config C2 fit in memory at n = 2000) gives the same rows
+    in the same order with the same birth / death simplices as the plain reduction: on the reference's 32 shipped clouds, on lattice
+    clouds with ties and duplicates under a finite threshold, and on the committed C2 golden at n = 600 (made without it)."""
+    import os
+    from tests.helpers import load_ref_rips_golden
+    from tda_multimodal_b200 import workloads
+    clouds, _ = load_ref_rips_golden()
+    cases = [(orips.euclidean_dm_f32(c), np.inf) for c in clouds]
+    rng = np.random.default_rng(9)
+    for t in range(12):
+        n = int(rng.integers(10, 90))
+        X = (rng.integers(0, 5, (n, 3)) if t % 2 else rng.normal(size=(n, 3))).astype(np.float32)
+        dm = orips.euclidean_dm_f32(X)
+        cases.append((dm, np.inf if t % 3 else float(0.7 * enclosing_radius(dm))))
+    for dm, thresh in cases:
+        a = orips.rips_dm(dm, maxdim=2, thresh=thresh, with_simplices=True)
+        b = orips.rips_dm(dm, maxdim=2, thresh=thresh, with_simplices=True, apparent=True)
+        for q in range(3):
+            assert np.array_equal(a["dgms"][q], b["dgms"][q]) and np.array_equal(a["simplices"][q], b["simplices"][q]), q
+    X = workloads.c2_torus(n=600).astype(np.float64)
+    sq = (X * X).sum(1)
+    D = np.sqrt(np.maximum(sq[:, None] + sq[None] - 2.0 * X @ X.T, 0.0))
+    np.fill_diagonal(D, 0.0)
+    r = orips.rips_dm(D.astype(np.float32), maxdim=2, apparent=True)
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c2_torus_n600_dgms.npz"))
+    for q, name in enumerate(("h0", "h1", "h2")):
+        assert np.array_equal(r["dgms"][q], gold[name]), name
