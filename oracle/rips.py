@@ -45,6 +45,7 @@ def _lib():
         lib.rips_oracle_stats.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         lib.rips_oracle_dep_stats.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         lib.rips_oracle_free.argtypes = [ctypes.c_void_p]
+        lib.rips_oracle_set_compact.argtypes = [ctypes.c_int64]
         _LIB = lib
     return _LIB
 
@@ -97,6 +98,11 @@ def greedy_permutation_points(X, n_perm):
         ds = np.minimum(ds, row(j))
     lambdas[-1] = ds.max()
     return idx, lambdas
+
+
+def set_compact(min_entries=1 << 25):
+    """Entries a working column of the oracle may hold before its cancelling pairs are removed (tests lower it)."""
+    _lib().rips_oracle_set_compact(int(min_entries))
 
 
 def rips_dm(dm, maxdim=1, thresh=np.inf, with_simplices=False, with_stats=False, apparent=False):

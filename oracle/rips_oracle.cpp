@@ -54,7 +54,39 @@ struct HeapCmp {
     return (a.diam > b.diam) || (a.diam == b.diam && a.idx < b.idx);
   }
 };
-typedef std::priority_queue<Simplex, std::vector<Simplex>, HeapCmp> Heap;
+// Binary heap of the working coboundary (std::push_heap / pop_heap on a vector = what std::priority_queue does), with one
+// addition: entries cancel in pairs (Z/2), and pop_pivot only cancels them when they reach the top, so a long reduction piles up
+// billions of dead pairs (config C2 at n = 2000: tens of GB).  compact() removes the pairs in place once the heap has grown past
+// a bound; the multiset of surviving entries, hence every pivot, is unchanged.
+size_t g_compact_min = (size_t)1 << 25;   // 32 M entries = 512 MB (tests lower it through rips_oracle_set_compact)
+struct Heap {
+  std::vector<Simplex> v;
+  size_t next_compact = g_compact_min;
+  bool empty() const { return v.empty(); }
+  const Simplex& top() const { return v.front(); }
+  void push(const Simplex& s) {
+    v.push_back(s);
+    std::push_heap(v.begin(), v.end(), HeapCmp());
+    if (v.size() >= next_compact) compact();
+  }
+  void pop() {
+    std::pop_heap(v.begin(), v.end(), HeapCmp());
+    v.pop_back();
+  }
+  void compact() {
+    std::sort(v.begin(), v.end(), [](const Simplex& a, const Simplex& b) { return a.idx < b.idx; });
+    size_t w = 0;
+    for (size_t a = 0; a < v.size();) {
+      size_t b = a;
+      while (b < v.size() && v[b].idx == v[a].idx) ++b;
+      if ((b - a) & 1) v[w++] = v[a];
+      a = b;
+    }
+    v.resize(w);
+    std::make_heap(v.begin(), v.end(), HeapCmp());
+    next_compact = std::max(g_compact_min, 2 * w);
+  }
+};
 
 struct Binom {
   std::vector<std::vector<idx_t>> t;  // t[k][n]
@@ -324,6 +356,18 @@ struct Rips {
     }
   }
 
+  static void cancel_pairs(std::vector<idx_t>& v) {   // sorted, entries that occur an even number of times removed
+    std::sort(v.begin(), v.end());
+    size_t w = 0;
+    for (size_t a = 0; a < v.size();) {
+      size_t b = a;
+      while (b < v.size() && v[b] == v[a]) ++b;
+      if ((b - a) & 1) v[w++] = v[a];
+      a = b;
+    }
+    v.resize(w);
+  }
+
   void reduce(const std::vector<Simplex>& columns, std::unordered_map<idx_t, int64_t>& pivot_col, int dim) {
     const double INF = std::numeric_limits<double>::infinity();
     std::vector<std::vector<idx_t>> V(columns.size());  // reduction columns (excluding the column itself)
@@ -335,6 +379,7 @@ struct Rips {
       int64_t steps = 1, dep_chain = 0, dep_depth = 0;
       Heap work;           // working coboundary
       std::vector<idx_t> vcol;  // working reduction column entries (with multiplicity)
+      size_t vcol_compact = g_compact_min;
       Simplex pivot{0, -1};
       bool emergent = false;
       {  // init coboundary + emergent-pair check
@@ -374,6 +419,10 @@ struct Rips {
           // add column a: its own coboundary plus the coboundaries of its reduction column
           auto add_simplex = [&](idx_t sidx) {
             vcol.push_back(sidx);
+            if (vcol.size() >= vcol_compact) {   // same idea for the working reduction column: cancel pairs early
+              cancel_pairs(vcol);
+              vcol_compact = std::max(g_compact_min, 2 * vcol.size());
+            }
             Simplex s{diameter(sidx, dim), sidx};
             Cofacets cf(*this, s, dim);
             while (cf.has_next()) {
@@ -409,13 +458,8 @@ struct Rips {
         }
         pivot_col.emplace(pivot.idx, (int64_t)j);
         // store the reduction column mod 2
-        std::sort(vcol.begin(), vcol.end());
-        for (size_t a = 0; a < vcol.size();) {
-          size_t b = a;
-          while (b < vcol.size() && vcol[b] == vcol[a]) ++b;
-          if ((b - a) & 1) V[j].push_back(vcol[a]);
-          a = b;
-        }
+        cancel_pairs(vcol);
+        V[j].assign(vcol.begin(), vcol.end());
         st.max_v[dim] = std::max<int64_t>(st.max_v[dim], (int64_t)V[j].size());
         if (!emergent) {
           chain[j] = steps + dep_chain;
@@ -467,5 +511,7 @@ void rips_oracle_dep_stats(void* h, int dim, int64_t* out) {
   out[0] = r->st.dep_total[dim]; out[1] = r->st.dep_critical[dim]; out[2] = r->st.dep_depth[dim];
 }
 void rips_oracle_free(void* h) { delete (Rips*)h; }
+// entries a working column may hold before its cancelling pairs are removed (default 2^25); tests use a few dozen
+void rips_oracle_set_compact(int64_t min_entries) { g_compact_min = (size_t)std::max<int64_t>(4, min_entries); }
 
 }  // extern "C"

@@ -158,3 +158,23 @@ def test_apparent_pair_shortcut_changes_nothing():
     gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c2_torus_n600_dgms.npz"))
     for q, name in enumerate(("h0", "h1", "h2")):
         assert np.array_equal(r["dgms"][q], gold[name]), name
+
+
+def test_working_column_compaction_changes_nothing():
+    """The oracle removes cancelling pairs from its working columns once they hold 2^25 entries (config C2 at n = 2000 would need tens
+    of GB otherwise).  With the bound lowered to 16 entries the compaction runs all the time: same rows, order and simplices."""
+    from tests.helpers import torus3d
+    rng = np.random.default_rng(21)
+    cases = [orips.euclidean_dm_f32(torus3d(120, rng)), orips.euclidean_dm_f32(rng.integers(0, 5, (70, 3)).astype(np.float32)),
+             orips.euclidean_dm_f32(rng.normal(size=(90, 3)).astype(np.float32))]
+    for dm in cases:
+        for apparent in (False, True):
+            a = orips.rips_dm(dm, maxdim=2, with_simplices=True, with_stats=True, apparent=apparent)
+            try:
+                orips.set_compact(16)
+                b = orips.rips_dm(dm, maxdim=2, with_simplices=True, with_stats=True, apparent=apparent)
+            finally:
+                orips.set_compact()
+            assert a["stats"][1]["additions"] > 0
+            for q in range(3):
+                assert np.array_equal(a["dgms"][q], b["dgms"][q]) and np.array_equal(a["simplices"][q], b["simplices"][q]), q
