@@ -46,6 +46,7 @@ def _lib():
         lib.rips_oracle_dep_stats.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         lib.rips_oracle_free.argtypes = [ctypes.c_void_p]
         lib.rips_oracle_set_compact.argtypes = [ctypes.c_int64]
+        lib.rips_oracle_set_window.argtypes = [ctypes.c_int64, ctypes.c_int64]
         _LIB = lib
     return _LIB
 
@@ -103,6 +104,11 @@ def greedy_permutation_points(X, n_perm):
 def set_compact(min_entries=1 << 25):
     """Entries a working column of the oracle may hold before its cancelling pairs are removed (tests lower it)."""
     _lib().rips_oracle_set_compact(int(min_entries))
+
+
+def set_window(min_ranks=64, div=256):
+    """First diameter window of the lean mode's working coboundary: max(min_ranks, edges / div) edge ranks (tests use 1 rank)."""
+    _lib().rips_oracle_set_window(int(min_ranks), int(div))
 
 
 def rips_dm(dm, maxdim=1, thresh=np.inf, with_simplices=False, with_stats=False, apparent=False):

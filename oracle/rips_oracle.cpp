@@ -18,6 +18,11 @@
 //     oldest cofacet of s and s the youngest facet of c is a persistence pair that needs no reduction; such columns are neither
 //     assembled nor stored in the pivot map but recognised on the fly.  Same pairs, same rows, same order (tests compare the two
 //     modes bit for bit); it only makes the top dimension of config C2 (1.2e9 triangles at n = 2000) fit in memory.
+//     In this mode the working coboundary is also WINDOWED by diameter: only cofacets up to a bound B (a number of edge ranks
+//     above the column's own diameter) are kept in the heap; every cofacet that is left out is longer than everything kept, so
+//     the heap's pivot is the column's pivot; when the kept part cancels completely, B moves up (doubling) and the cofacets
+//     between the old and the new bound are enumerated again from the column and its reduction column.  Exact, and the long
+//     reductions of C2 (one column: > 1e9 live heap entries otherwise) stay in a few GB.
 // Parity is PINNED for this file: tests/test_oracle_golden.py checks it against the 32
 // shipped point clouds + summary_stats.json of the reference (tda-output/), see tests/golden/.
 //
@@ -58,6 +63,7 @@ struct HeapCmp {
 // addition: entries cancel in pairs (Z/2), and pop_pivot only cancels them when they reach the top, so a long reduction piles up
 // billions of dead pairs (config C2 at n = 2000: tens of GB).  compact() removes the pairs in place once the heap has grown past
 // a bound; the multiset of surviving entries, hence every pivot, is unchanged.
+size_t g_window_min = 64, g_window_div = 256;   // first window of the lean mode: max(min, edges / div) edge ranks (tests: 1 rank)
 size_t g_compact_min = (size_t)1 << 25;   // 32 M entries = 512 MB (tests lower it through rips_oracle_set_compact)
 struct Heap {
   std::vector<Simplex> v;
@@ -119,7 +125,8 @@ struct Rips {
   std::vector<std::vector<idx_t>> pair_simplex;  // per dim: flat (birth idx, death idx or -1)
   int64_t num_edges;
   Stats st;
-  bool apparent = false;  // Ripser 1.2's zero-apparent-pair shortcut (see the header)
+  bool apparent = false;  // Ripser 1.2's zero-apparent-pair shortcut + windowed working coboundary (see the header)
+  std::vector<val_t> edge_diams;  // ascending lengths of the edges <= thresh (the window bounds of the lean mode)
 
   val_t d(int i, int j) const { return dist[(size_t)i * n + j]; }
 
@@ -268,6 +275,10 @@ struct Rips {
         if (d(i, j) <= thresh) edges.push_back(Simplex{d(i, j), C(i, 2) + j});
     num_edges = (int64_t)edges.size();
     std::sort(edges.begin(), edges.end(), RevFiltLess());  // reverse filtration order
+    if (apparent) {
+      edge_diams.resize(edges.size());
+      for (size_t i = 0; i < edges.size(); ++i) edge_diams[i] = edges[edges.size() - 1 - i].diam;
+    }
     std::vector<int> parent(n), rnk(n, 0);
     for (int i = 0; i < n; ++i) parent[i] = i;
     auto find = [&](int x) {
@@ -380,6 +391,15 @@ struct Rips {
       Heap work;           // working coboundary
       std::vector<idx_t> vcol;  // working reduction column entries (with multiplicity)
       size_t vcol_compact = g_compact_min;
+      // lean mode: the heap holds the cofacets with diameter <= bound only (bound = +inf: everything up to thresh)
+      const val_t VINF = std::numeric_limits<val_t>::infinity();
+      val_t bound = VINF;
+      size_t bound_rank = 0, bound_step = 0;
+      if (apparent && !edge_diams.empty()) {
+        bound_step = std::max<size_t>(g_window_min, edge_diams.size() / g_window_div);
+        bound_rank = (size_t)(std::upper_bound(edge_diams.begin(), edge_diams.end(), col.diam) - edge_diams.begin()) + bound_step;
+        bound = bound_rank < edge_diams.size() ? edge_diams[bound_rank] : VINF;
+      }
       Simplex pivot{0, -1};
       bool emergent = false;
       {  // init coboundary + emergent-pair check
@@ -398,12 +418,34 @@ struct Rips {
           }
         }
         if (!emergent) {
-          for (const Simplex& c : buf) work.push(c);
+          for (const Simplex& c : buf)
+            if (c.diam <= bound) work.push(c);
           pivot = get_pivot(work, st.pops[dim]);
         }
       }
       if (emergent) ++st.emergent[dim]; else ++st.reduced[dim];
       for (;;) {
+        if (pivot.idx == -1 && bound < VINF) {
+          // everything up to the bound cancelled: move the bound up and enumerate the cofacets in (old bound, new bound] of the
+          // column and of its reduction column again
+          const val_t lo = bound;
+          bound_step *= 2;
+          bound_rank += bound_step;
+          bound = bound_rank < edge_diams.size() ? edge_diams[bound_rank] : VINF;
+          cancel_pairs(vcol);
+          auto refill = [&](const Simplex& s) {
+            Cofacets cf(*this, s, dim);
+            while (cf.has_next()) {
+              Simplex c = cf.next();
+              ++st.cofacets[dim];
+              if (c.diam <= thresh && c.diam > lo && c.diam <= bound) work.push(c);
+            }
+          };
+          refill(col);
+          for (idx_t sidx : vcol) refill(Simplex{diameter(sidx, dim), sidx});
+          pivot = get_pivot(work, st.pops[dim]);
+          continue;
+        }
         if (pivot.idx == -1) {
           dgm[dim].push_back((double)col.diam); dgm[dim].push_back(INF);
           pair_simplex[dim].push_back(col.idx); pair_simplex[dim].push_back(-1);
@@ -428,7 +470,7 @@ struct Rips {
             while (cf.has_next()) {
               Simplex c = cf.next();
               ++st.cofacets[dim];
-              if (c.diam <= thresh) work.push(c);
+              if (c.diam <= thresh && c.diam <= bound) work.push(c);
             }
           };
           add_simplex(columns[a].idx);
@@ -446,7 +488,7 @@ struct Rips {
             while (cf.has_next()) {
               Simplex c = cf.next();
               ++st.cofacets[dim];
-              if (c.diam <= thresh) work.push(c);
+              if (c.diam <= thresh && c.diam <= bound) work.push(c);
             }
             pivot = get_pivot(work, st.pops[dim]);
             continue;
@@ -512,6 +554,10 @@ void rips_oracle_dep_stats(void* h, int dim, int64_t* out) {
 }
 void rips_oracle_free(void* h) { delete (Rips*)h; }
 // entries a working column may hold before its cancelling pairs are removed (default 2^25); tests use a few dozen
+void rips_oracle_set_window(int64_t min_ranks, int64_t div) {
+  g_window_min = (size_t)std::max<int64_t>(1, min_ranks);
+  g_window_div = (size_t)std::max<int64_t>(1, div);
+}
 void rips_oracle_set_compact(int64_t min_entries) { g_compact_min = (size_t)std::max<int64_t>(4, min_entries); }
 
 }  // extern "C"

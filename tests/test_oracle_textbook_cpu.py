@@ -162,7 +162,9 @@ def test_apparent_pair_shortcut_changes_nothing():
 
 def test_working_column_compaction_changes_nothing():
     """The oracle removes cancelling pairs from its working columns once they hold 2^25 entries (config C2 at n = 2000 would need tens
-    of GB otherwise).  With the bound lowered to 16 entries the compaction runs all the time: same rows, order and simplices."""
+    of GB otherwise), and in the lean mode keeps only the cofacets inside a diameter window in the heap, re-enumerating when the window
+    moves.  With the bound lowered to 16 entries and the window to one edge rank both mechanisms run all the time: same rows, order
+    and simplices."""
     from tests.helpers import torus3d
     rng = np.random.default_rng(21)
     cases = [orips.euclidean_dm_f32(torus3d(120, rng)), orips.euclidean_dm_f32(rng.integers(0, 5, (70, 3)).astype(np.float32)),
@@ -172,9 +174,11 @@ def test_working_column_compaction_changes_nothing():
             a = orips.rips_dm(dm, maxdim=2, with_simplices=True, with_stats=True, apparent=apparent)
             try:
                 orips.set_compact(16)
+                orips.set_window(1, 1 << 40)      # lean mode: the diameter window of the working coboundary starts at ONE edge rank
                 b = orips.rips_dm(dm, maxdim=2, with_simplices=True, with_stats=True, apparent=apparent)
             finally:
                 orips.set_compact()
+                orips.set_window()
             assert a["stats"][1]["additions"] > 0
             for q in range(3):
                 assert np.array_equal(a["dgms"][q], b["dgms"][q]) and np.array_equal(a["simplices"][q], b["simplices"][q]), q
