@@ -103,7 +103,7 @@ def _cpu_layer(args):
         from oracle import umap_oracle as uo, rips as orips
         Y = uo.UMAPOracle(n_neighbors=k, n_components=3, min_dist=0.1, metric="cosine", random_state=42).fit_transform(X)
         t1 = time.perf_counter()
-        orips.ripser(Y, maxdim=1)
+        orips.ripser(Y, maxdim=1, apparent=True)   # the oracle's fastest mode (2-3x the plain restatement of ripser's loop; same diagrams)
     t2 = time.perf_counter()
     return layer, t1 - t0, t2 - t1
 
@@ -118,12 +118,13 @@ def _cpu_warm():
         return
     from oracle import umap_oracle as uo, rips as orips
     Y = uo.UMAPOracle(n_neighbors=10, n_components=3, metric="cosine", random_state=42).fit_transform(X)
-    orips.ripser(Y, maxdim=1)
+    orips.ripser(Y, maxdim=1, apparent=True)
 
 
 def _cpu_kind():
     return ("reference", "umap-learn + ripser (real libraries)") if _real_libs() else \
-        ("port", "oracle/umap_oracle.py (numba) + oracle/rips_oracle.cpp: umap-learn and ripser are not installed in this image")
+        ("port", "oracle/umap_oracle.py (numba) + oracle/rips_oracle.cpp in its fastest mode (apparent-pair shortcut of Ripser 1.2 + diameter-windowed "
+                 "working column: 2-3x faster than the plain restatement of ripser.py's loop, same diagrams); umap-learn and ripser are not installed in this image")
 
 
 def cpu_baseline_serial(a, budget_s):

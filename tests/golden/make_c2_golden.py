@@ -23,4 +23,4 @@ t = time.time()
 r = orips.rips_dm(D.astype(np.float32), maxdim=2, apparent=True, with_stats=True)
 print(f"oracle n={n}: {time.time() - t:.1f} s; rows", [len(d) for d in r["dgms"]], "num_edges", r["num_edges"], "stats", r["stats"][1:])
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"c2_torus_n{n}_dgms.npz"), h0=r["dgms"][0], h1=r["dgms"][1], h2=r["dgms"][2],
-                    diameter=np.float64(D.max()))
+                    diameter=np.float64(D.max()), num_edges=np.int64(r["num_edges"]))
