@@ -66,3 +66,23 @@ def test_oracle_maxdim2_sphere():
     d = orips.ripser(v.astype(np.float32), maxdim=2)["dgms"]
     pers2 = np.sort(d[2][:, 1] - d[2][:, 0])[::-1]
     assert len(pers2) >= 1 and pers2[0] > 0.3 and (len(pers2) == 1 or pers2[0] > 2 * pers2[1])
+
+
+def test_c2_full_size_golden_agrees_with_the_logged_gpu_run():
+    """Config C2 at its full size (2000-point torus in 4096-d, maxdim=2): the oracle's diagrams (tests/golden/c2_torus_n2000_dgms.npz,
+    650 s in the oracle's lean mode) against the GPU run recorded in profiles/r02_c2_n2000.log earlier in the round -- same number
+    of edges, H1 and H2 rows, same top persistences to the three decimals the log holds.  (The GPU suite compares the diagrams
+    themselves by bottleneck distance: tests/test_rips_h2_gpu.py.)"""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gold = np.load(os.path.join(root, "tests", "golden", "c2_torus_n2000_dgms.npz"))
+    line = [l for l in open(os.path.join(root, "profiles", "r02_c2_n2000.log")) if l.startswith("C2 n=2000")][0]
+    m = re.search(r"num_edges (\d+); H1 rows (\d+) top \[([^\]]*)\]; H2 rows (\d+) top \[([^\]]*)\]", line)
+    assert m, line
+    assert int(m.group(1)) == int(gold["num_edges"]) and int(m.group(2)) == len(gold["h1"]) and int(m.group(4)) == len(gold["h2"])
+    for name, txt in (("h1", m.group(3)), ("h2", m.group(5))):
+        logged = np.array([float(t) for t in txt.split()])
+        pers = np.sort(gold[name][:, 1] - gold[name][:, 0])[::-1][:len(logged)]
+        assert np.allclose(pers, logged, atol=6e-4), (name, pers, logged)
+    assert gold["h0"].shape == (2000, 2) and np.isinf(gold["h0"][-1, 1])
