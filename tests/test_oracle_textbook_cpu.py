@@ -182,3 +182,18 @@ def test_working_column_compaction_changes_nothing():
             assert a["stats"][1]["additions"] > 0
             for q in range(3):
                 assert np.array_equal(a["dgms"][q], b["dgms"][q]) and np.array_equal(a["simplices"][q], b["simplices"][q]), q
+
+
+def test_lean_mode_reproduces_the_c2_golden_at_n1000():
+    """tests/golden/c2_torus_n1000_dgms.npz was made by the plain reduction (5 min, 19 GB); the lean mode (apparent pairs + windowed
+    working column, 20 s, 0.5 GB) must give the same three arrays bit for bit -- the n = 2000 golden exists only in that mode."""
+    import os
+    from tda_multimodal_b200 import workloads
+    X = workloads.c2_torus(n=1000).astype(np.float64)
+    sq = (X * X).sum(1)
+    D = np.sqrt(np.maximum(sq[:, None] + sq[None] - 2.0 * X @ X.T, 0.0))
+    np.fill_diagonal(D, 0.0)
+    r = orips.rips_dm(D.astype(np.float32), maxdim=2, apparent=True)
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c2_torus_n1000_dgms.npz"))
+    for q, name in enumerate(("h0", "h1", "h2")):
+        assert np.array_equal(r["dgms"][q], gold[name]), name
