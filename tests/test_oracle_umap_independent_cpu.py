@@ -139,3 +139,15 @@ def test_sgd_steps_are_gradient_steps_of_the_cross_entropy():
     assert np.abs(out[0] - y).max() < 2e-4 * np.abs(y).max(), (out[0], y)
     # and the attraction really pulls towards the tail, the repulsion pushes away from it
     assert np.dot(attract(y0[0].astype(np.float64)), pp - y0[0]) > 0 > np.dot(repel(y0[0].astype(np.float64)), pp - y0[0])
+
+
+def test_exact_knn_equals_sklearn_brute_force(fitted):
+    """The oracle's kNN (row-wise stable argsort of sklearn pairwise_distances) against sklearn's own brute-force neighbour search."""
+    from sklearn.neighbors import NearestNeighbors
+    X, um = fitted
+    k = um._n_neighbors
+    dist, idx = NearestNeighbors(n_neighbors=k, metric="cosine", algorithm="brute").fit(X).kneighbors(X)
+    # the self-distance is ~1e-16 rather than exactly 0 in sklearn's search, so position 0 can hold a near-duplicate: compare as sets
+    same_rows = sum(set(idx[i]) == set(um._knn_indices[i]) for i in range(len(X)))
+    assert same_rows == len(X)
+    assert np.abs(np.sort(dist, axis=1)[:, 1:] - um._knn_dists[:, 1:]).max() < 1e-6
