@@ -26,7 +26,9 @@
 // Parity is PINNED for this file: tests/test_oracle_golden.py checks it against the 32
 // shipped point clouds + summary_stats.json of the reference (tda-output/), see tests/golden/.
 //
-// Single-threaded on purpose (Ripser is single-threaded) -- it doubles as the CPU baseline.
+// Single-threaded on purpose (Ripser is single-threaded) -- it doubles as the CPU baseline (bench.py times the lean mode, the
+// faster of the two).  One exception, outside the baseline's path: with maxdim >= 2 the lean mode assembles the columns of the next
+// dimension on all host threads (the apparent-pair test of 1.2e9 triangles for config C2); the reduction itself stays serial.
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
